@@ -1,0 +1,15 @@
+"""omg_tools_b200: B200-native batched solver for OMG-tools' per-MPC-step
+spline-trajectory NLP, behind the reference's Problem.solve()/OptiFather API."""
+from .basics.spline import BSplineBasis, BSpline
+from .basics.shape import (Circle, Polyhedron, Rectangle, Square, Beam,
+                           RegularPolyhedron, Sphere, Cuboid, Cube)
+from .basics.optilayer import OptiChild, OptiFather, create_nlp
+from .vehicles.vehicle import Vehicle
+from .vehicles.holonomic import Holonomic
+from .vehicles.fleet import Fleet
+from .environment.environment import Environment
+from .environment.obstacle import Obstacle
+from .problems.problem import Problem
+from .problems.point2point import Point2point, FixedTPoint2point
+
+__version__ = '0.1.0'

@@ -1,0 +1,367 @@
+"""Lower a polynomial NLP (rows of ``Poly``) to the flat constant tables that
+the CUDA kernels (csrc/omg_b200.cu) and the CPU oracle (oracle/) consume.
+
+This replaces what the reference obtains from CasADi: ``nlpsol(..., {x,p,f,g},
+{expand: True})`` builds SX evaluators for g, J_g, grad f and the Hessian of the
+Lagrangian by algorithmic differentiation (reference optilayer.py:49-60).  Here
+the problem is a polynomial in x with parameter-only coefficients, so all
+derivatives are generated symbolically once, as term lists
+
+    out[s] += coef * V[cidx] * prod_k x_ext[xi[k]]      (* lam_ext[lrow] for W)
+
+grouped by output slot s (CSR).  ``V`` is the per-instance *parameter tape*:
+V[0] = 1, V[1..n_par] = p, and further entries are parameter-only expressions
+(products/sums, 1/p, indicators, sin/cos) evaluated level by level once per
+solve.  ``x_ext`` is x with a trailing 1 so that padded factors are no-ops.
+
+Row/variable order is the reference's flat order:
+children in insertion order, entries in definition order, matrices column-major
+(reference optilayer.py:225-272).
+"""
+from collections import OrderedDict
+
+import numpy as np
+
+from .poly import Poly, resolve, sym_info
+
+FUNC_CODE = {'id': 0, 'inv': 1, 'ge': 2, 'gt': 3, 'sin': 4, 'cos': 5,
+             'sqrt': 6}
+MAX_FAC = 4          # V-factors per tape term (longer products are chained)
+PRUNE = 1e-14
+
+
+class TermList(object):
+    """CSR list of polynomial terms per output slot."""
+
+    def __init__(self, n_out, width, with_lrow=False):
+        self.n_out = n_out
+        self.width = max(1, width)
+        self.slots = [[] for _ in range(n_out)]
+        self.with_lrow = with_lrow
+
+    def add(self, slot, coef, cidx, xmon, lrow=0):
+        self.slots[slot].append((coef, cidx, tuple(xmon), lrow))
+
+    def finalize(self, n):
+        nt = sum(len(s) for s in self.slots)
+        self.ptr = np.zeros(self.n_out + 1, dtype=np.int32)
+        self.coef = np.zeros(nt, dtype=np.float64)
+        self.cidx = np.zeros(nt, dtype=np.int32)
+        self.xi = np.full((nt, self.width), n, dtype=np.int32)
+        self.lrow = np.zeros(nt, dtype=np.int32)
+        k = 0
+        for s, terms in enumerate(self.slots):
+            # merge identical (cidx, xmon, lrow) terms
+            merged = OrderedDict()
+            for coef, cidx, xmon, lrow in terms:
+                key = (cidx, xmon, lrow)
+                merged[key] = merged.get(key, 0.0) + coef
+            for (cidx, xmon, lrow), coef in merged.items():
+                if coef == 0.0:
+                    continue
+                self.coef[k] = coef
+                self.cidx[k] = cidx
+                self.xi[k, :len(xmon)] = xmon
+                self.lrow[k] = lrow
+                k += 1
+            self.ptr[s + 1] = k
+        self.coef = self.coef[:k].copy()
+        self.cidx = self.cidx[:k].copy()
+        self.xi = np.ascontiguousarray(self.xi[:k])
+        self.lrow = self.lrow[:k].copy()
+        del self.slots
+        return self
+
+    @property
+    def n_terms(self):
+        return len(self.coef)
+
+
+class _Tape(object):
+    """Builder of the parameter tape V."""
+
+    def __init__(self, par_index):
+        self.par_index = par_index            # resolved sid -> k
+        self.n_par = len(par_index)
+        self.entries = []                     # (func, [(coef, [vidx...])], level)
+        self.level = {0: 0}
+        for k in range(self.n_par):
+            self.level[1 + k] = 0
+        self.sym_entry = {}                   # atom sid -> V idx
+        self.poly_entry = {}                  # poly key -> V idx
+
+    def _new_entry(self, func, terms):
+        lvl = 1 + max([self.level[f] for _, fac in terms for f in fac] + [0])
+        idx = 1 + self.n_par + len(self.entries)
+        self.entries.append((func, terms, lvl))
+        self.level[idx] = lvl
+        return idx
+
+    def v_of_symbol(self, sid):
+        sid = resolve(sid)
+        if sid in self.par_index:
+            return 1 + self.par_index[sid]
+        info = sym_info(sid)
+        if info.kind != 'atom':
+            raise ValueError('symbol %r is neither parameter nor atom: a '
+                             'constraint coefficient depends on it' % info)
+        if sid not in self.sym_entry:
+            terms = self._terms_of(self._ppoly(info.arg))
+            self.sym_entry[sid] = self._new_entry(info.func, terms)
+        return self.sym_entry[sid]
+
+    def _ppoly(self, poly):
+        """Poly over parameter symbols -> {pmon(resolved sids): coef}."""
+        out = {}
+        for mono, c in poly.t.items():
+            pm = tuple(sorted(resolve(s) for s in mono))
+            out[pm] = out.get(pm, 0.0) + c
+        return out
+
+    def _product(self, vidx):
+        vidx = sorted(vidx)
+        while len(vidx) > MAX_FAC:
+            head, vidx = vidx[:MAX_FAC], vidx[MAX_FAC:]
+            key = ('prod', tuple(head))
+            if key not in self.poly_entry:
+                self.poly_entry[key] = self._new_entry('id', [(1.0, head)])
+            vidx = sorted([self.poly_entry[key]] + vidx)
+        return vidx
+
+    def _terms_of(self, ppoly):
+        terms = []
+        for pm in sorted(ppoly):
+            c = ppoly[pm]
+            if c == 0.0:
+                continue
+            fac = self._product([self.v_of_symbol(s) for s in pm])
+            terms.append((c, fac))
+        return terms
+
+    def v_of_ppoly(self, ppoly):
+        """(scale, V index) such that ppoly == scale * V[index]."""
+        ppoly = {pm: c for pm, c in ppoly.items() if abs(c) > PRUNE}
+        if not ppoly:
+            return 0.0, 0
+        if len(ppoly) == 1:
+            (pm, c), = ppoly.items()
+            if len(pm) == 0:
+                return c, 0
+            if len(pm) == 1:
+                return c, self.v_of_symbol(pm[0])
+        lead_pm = sorted(ppoly)[0]
+        scale = ppoly[lead_pm]
+        key = tuple((pm, ppoly[pm] / scale) for pm in sorted(ppoly))
+        if key not in self.poly_entry:
+            terms = self._terms_of({pm: c for pm, c in key})
+            self.poly_entry[key] = self._new_entry('id', terms)
+        return scale, self.poly_entry[key]
+
+    def finalize(self):
+        """Sort entries by level; return arrays and the index remap."""
+        base = 1 + self.n_par
+        order = sorted(range(len(self.entries)),
+                       key=lambda e: (self.entries[e][2], e))
+        remap = np.arange(base + len(self.entries), dtype=np.int64)
+        for new, old in enumerate(order):
+            remap[base + old] = base + new
+        func = np.zeros(len(order), dtype=np.int32)
+        ptr = np.zeros(len(order) + 1, dtype=np.int32)
+        coef, fac = [], []
+        levels = []
+        for new, old in enumerate(order):
+            f, terms, lvl = self.entries[old]
+            func[new] = FUNC_CODE[f]
+            levels.append(lvl)
+            for c, fs in terms:
+                coef.append(c)
+                row = [int(remap[v]) for v in fs] + [0] * (MAX_FAC - len(fs))
+                fac.append(row)
+            ptr[new + 1] = len(coef)
+        n_levels = max(levels) if levels else 0
+        level_ptr = np.zeros(n_levels + 1, dtype=np.int32)
+        for lvl in levels:
+            level_ptr[lvl] += 1
+        level_ptr = np.concatenate([[0], np.cumsum(level_ptr[1:])]).astype(np.int32)
+        return dict(n_v=base + len(order), tape_func=func, tape_ptr=ptr,
+                    tape_coef=np.array(coef, dtype=np.float64),
+                    tape_fac=np.array(fac, dtype=np.int32).reshape(-1, MAX_FAC),
+                    level_ptr=level_ptr), remap
+
+
+class NLPTables(object):
+    """Flat description of  min f(x,p)  s.t.  lbg <= g(x,p) <= ubg."""
+
+    def summary(self):
+        return ('n=%d m=%d n_par=%d n_v=%d | terms g=%d J=%d(nnz %d) '
+                'W=%d(nnz %d) f=%d | deg=%d' % (
+                    self.n, self.m, self.n_par, self.n_v, self.G.n_terms,
+                    self.J.n_terms, self.nnz_j, self.W.n_terms, self.nnz_w,
+                    self.F.n_terms, self.degree))
+
+
+def _split(poly, x_index, tape):
+    """Poly -> {xmon: {pmon: coef}} with xmon sorted x indices."""
+    out = {}
+    for mono, c in poly.t.items():
+        xm, pm = [], []
+        for s in mono:
+            r = resolve(s)
+            j = x_index.get(r)
+            if j is None:
+                pm.append(r)
+            else:
+                xm.append(j)
+        xm, pm = tuple(sorted(xm)), tuple(sorted(pm))
+        d = out.setdefault(xm, {})
+        d[pm] = d.get(pm, 0.0) + c
+    return out
+
+
+def _first_derivs(xmon):
+    """d(prod x)/dx_j for every distinct j: [(j, mult, reduced monomial)]."""
+    res = []
+    for j in sorted(set(xmon)):
+        mult = xmon.count(j)
+        red = list(xmon)
+        red.remove(j)
+        res.append((j, float(mult), tuple(red)))
+    return res
+
+
+def lower(var_ids, par_ids, rows, objective, lbg, ubg):
+    """Build NLPTables.
+
+    var_ids / par_ids : flat lists of (resolved) symbol ids defining x and p
+    rows              : list of Poly (or float) constraint rows, flat order
+    objective         : Poly
+    """
+    x_index = {resolve(s): j for j, s in enumerate(var_ids)}
+    p_index = {resolve(s): k for k, s in enumerate(par_ids)}
+    if len(x_index) != len(var_ids) or len(p_index) != len(par_ids):
+        raise ValueError('duplicate symbols in variable/parameter lists')
+    n, m = len(var_ids), len(rows)
+    tape = _Tape(p_index)
+
+    def as_poly(e):
+        if isinstance(e, Poly):
+            return e
+        if isinstance(e, np.ndarray) and e.size == 1:
+            return as_poly(e.reshape(-1)[0])
+        c = float(e)
+        return Poly({(): c} if c != 0.0 else {})
+
+    split_rows = [_split(as_poly(r), x_index, tape) for r in rows]
+    split_obj = _split(as_poly(objective), x_index, tape)
+    degree = max([len(xm) for sr in split_rows + [split_obj] for xm in sr] + [1])
+
+    def coef_of(ppoly):
+        return tape.v_of_ppoly(ppoly)
+
+    # resolve all coefficients first (tape indices are remapped afterwards)
+    lowered_rows = []
+    for sr in split_rows:
+        lowered_rows.append([(xm,) + coef_of(pp) for xm, pp in sorted(sr.items())])
+    lowered_obj = [(xm,) + coef_of(pp) for xm, pp in sorted(split_obj.items())]
+    tape_arrays, remap = tape.finalize()
+
+    G = TermList(m, degree)
+    F = TermList(1, degree)
+    DF = TermList(n, degree - 1)
+    jslots = OrderedDict()     # (row, col) -> list of (coef, cidx, xmon)
+    wslots = OrderedDict()     # (j, k), j>=k -> list of (coef, cidx, xmon, lrow)
+
+    def add_hess(xm, c, cidx, lrow):
+        for j, mj, red in _first_derivs(xm):
+            for k, mk, red2 in _first_derivs(red):
+                if k > j:
+                    continue
+                # d2/dxj dxk of prod: mj*mk*(reduced); for j==k: mj*(mj-1)
+                wslots.setdefault((j, k), []).append(
+                    (c * mj * mk, cidx, red2, lrow))
+
+    for i, terms in enumerate(lowered_rows):
+        for xm, scale, cidx in terms:
+            if scale == 0.0:
+                continue
+            cidx = int(remap[cidx])
+            G.add(i, scale, cidx, xm)
+            for j, mj, red in _first_derivs(xm):
+                jslots.setdefault((i, j), []).append((scale * mj, cidx, red))
+            if len(xm) >= 2:
+                add_hess(xm, scale, cidx, i)
+    for xm, scale, cidx in lowered_obj:
+        if scale == 0.0:
+            continue
+        cidx = int(remap[cidx])
+        F.add(0, scale, cidx, xm)
+        for j, mj, red in _first_derivs(xm):
+            DF.add(j, scale * mj, cidx, red)
+        if len(xm) >= 2:
+            add_hess(xm, scale, cidx, m)
+
+    jkeys = sorted(jslots)
+    J = TermList(len(jkeys), degree - 1)
+    for s, key in enumerate(jkeys):
+        for c, cidx, red in jslots[key]:
+            J.add(s, c, cidx, red)
+    wkeys = sorted(wslots)
+    W = TermList(len(wkeys), degree - 2, with_lrow=True)
+    for s, key in enumerate(wkeys):
+        for c, cidx, red, lrow in wslots[key]:
+            W.add(s, c, cidx, red, lrow)
+
+    tb = NLPTables()
+    tb.n, tb.m, tb.n_par, tb.degree = n, m, len(par_ids), degree
+    for k, v in tape_arrays.items():
+        setattr(tb, k, v)
+    tb.G, tb.F, tb.DF = G.finalize(n), F.finalize(n), DF.finalize(n)
+    tb.J, tb.W = J.finalize(n), W.finalize(n)
+    tb.jrow = np.array([k[0] for k in jkeys], dtype=np.int32)
+    tb.jcol = np.array([k[1] for k in jkeys], dtype=np.int32)
+    tb.jrow_ptr = np.searchsorted(tb.jrow, np.arange(m + 1)).astype(np.int32)
+    tb.wrow = np.array([k[0] for k in wkeys], dtype=np.int32)
+    tb.wcol = np.array([k[1] for k in wkeys], dtype=np.int32)
+    tb.nnz_j, tb.nnz_w = len(jkeys), len(wkeys)
+    tb.lbg = np.asarray(lbg, dtype=np.float64).copy()
+    tb.ubg = np.asarray(ubg, dtype=np.float64).copy()
+    _build_kkt_pattern(tb)
+    return tb
+
+
+def _build_kkt_pattern(tb):
+    """Gather lists for the condensed KKT matrix  H = W + J^T Sigma J.
+
+    For every structurally non-zero lower-triangular position (j >= k) the
+    contributing pairs of Jacobian slots (s1, s2) of a common row: a
+    deterministic gather instead of scattered atomics.
+    """
+    pos = {}
+    for s in range(tb.nnz_w):
+        pos.setdefault((int(tb.wrow[s]), int(tb.wcol[s])), [])
+    for i in range(tb.m):
+        lo, hi = int(tb.jrow_ptr[i]), int(tb.jrow_ptr[i + 1])
+        for s1 in range(lo, hi):
+            for s2 in range(lo, s1 + 1):
+                j, k = int(tb.jcol[s1]), int(tb.jcol[s2])   # j >= k (sorted)
+                pos.setdefault((j, k), []).append((s1, s2, i))
+    keys = sorted(pos)
+    tb.hrow = np.array([k[0] for k in keys], dtype=np.int32)
+    tb.hcol = np.array([k[1] for k in keys], dtype=np.int32)
+    tb.nnz_h = len(keys)
+    ptr = np.zeros(len(keys) + 1, dtype=np.int32)
+    s1l, s2l, rowl = [], [], []
+    for q, key in enumerate(keys):
+        for s1, s2, i in pos[key]:
+            s1l.append(s1)
+            s2l.append(s2)
+            rowl.append(i)
+        ptr[q + 1] = len(s1l)
+    tb.hp_ptr = ptr
+    tb.hp_s1 = np.array(s1l, dtype=np.int32)
+    tb.hp_s2 = np.array(s2l, dtype=np.int32)
+    tb.hp_row = np.array(rowl, dtype=np.int32)
+    # position of every W slot inside the H pattern
+    index = {k: q for q, k in enumerate(keys)}
+    tb.w2h = np.array([index[(int(r), int(c))]
+                       for r, c in zip(tb.wrow, tb.wcol)], dtype=np.int32)

@@ -348,6 +348,27 @@ def _indicator(func, arg):
     return _atom(func, arg)
 
 
+def substitute(expr, mapping):
+    """Replace symbols (ids in ``mapping``) of a Poly by Poly expressions."""
+    if not isinstance(expr, Poly):
+        return expr
+    if not any(s in mapping for s in expr.symbols()):
+        return expr
+    res = Poly()
+    for mono, c in expr.t.items():
+        term = Poly({(): c})
+        rest = []
+        for s in mono:
+            if s in mapping:
+                term = term * mapping[s]
+            else:
+                rest.append(s)
+        if rest:
+            term = term * Poly({tuple(rest): 1.0})
+        res = res + term
+    return res
+
+
 def _unary(func, x):
     if isinstance(x, numbers.Real):
         return apply_atom(func, float(x))

@@ -1,0 +1,156 @@
+"""Vehicle/obstacle shapes: only what the NLP needs -- checkpoints + radii,
+canvas limits and room hyperplanes (reference omgtools/basics/shape.py:62-67,
+146-171, 330-336, 350-362).  Drawing is out of scope."""
+import numpy as np
+
+
+class Shape(object):
+    def __init__(self, dimensions):
+        self.n_dim = dimensions
+
+
+class Shape2D(Shape):
+    def __init__(self):
+        Shape.__init__(self, 2)
+
+    @staticmethod
+    def rotate(orientation, coordinate):
+        if isinstance(orientation, np.ndarray):
+            orientation = orientation.reshape(-1)[0]
+        cth, sth = np.cos(orientation), np.sin(orientation)
+        return np.array([[cth, -sth], [sth, cth]]).dot(coordinate)
+
+
+class Circle(Shape2D):
+    def __init__(self, radius):
+        Shape2D.__init__(self)
+        self.radius = radius
+        self.n_chck = 1
+
+    def get_checkpoints(self):
+        return [[0., 0.]], [self.radius]
+
+    def get_canvas_limits(self):
+        return [np.array([-self.radius, self.radius]),
+                np.array([-self.radius, self.radius])]
+
+
+class Polyhedron(Shape2D):
+    def __init__(self, vertices, orientation=0., radius=1e-3):
+        Shape2D.__init__(self)
+        self.n_vert = vertices.shape[1]
+        self.orientation = orientation
+        self.vertices = self.rotate(orientation, vertices)
+        # radius > 0 is required for polyhedron-polyhedron avoidance
+        self.radius = radius
+
+    def get_checkpoints(self):
+        chck = [[self.vertices[0, l], self.vertices[1, l]]
+                for l in range(self.n_vert)]
+        return chck, [self.radius for _ in range(self.n_vert)]
+
+    def get_canvas_limits(self):
+        hi, lo = np.amax(self.vertices, axis=1), np.amin(self.vertices, axis=1)
+        return [np.array([lo[0], hi[0]]), np.array([lo[1], hi[1]])]
+
+    def get_hyperplanes(self, **kwargs):
+        pos = kwargs.get('position', [0, 0])
+        v = np.hstack((self.vertices, np.vstack(self.vertices[:, 0])))
+        hyperplanes = {}
+        for k in range(v.shape[1] - 1):
+            d = [v[0][k + 1] - v[0][k], v[1][k + 1] - v[1][k]]
+            normal = np.array([-d[1], d[0]]) / np.sqrt(d[0]**2 + d[1]**2)
+            b = normal[0] * (v[0][k + 1] + pos[0]) + normal[1] * (v[1][k + 1] + pos[1])
+            hyperplanes[k] = {'a': normal, 'b': b}
+        return hyperplanes
+
+
+class Beam(Polyhedron):
+    def __init__(self, width, height, orientation=0.):
+        self.width, self.height = width, height
+        Polyhedron.__init__(self, np.c_[[0.5 * width, 0.], [-0.5 * width, 0.]],
+                            orientation=orientation, radius=0.5 * height)
+
+
+def _tangent_polygon(normals_angle, offsets):
+    """Vertices of the polygon with faces a_l . x = b_l, a_l = (sin, cos)(l*dth)."""
+    n = len(offsets)
+    A = np.array([[np.sin(th), np.cos(th)] for th in normals_angle])
+    vertices = np.zeros((2, n))
+    for l in range(n):
+        a = np.vstack((A[l], A[(l + 1) % n]))
+        b = np.array([offsets[l], offsets[(l + 1) % n]])
+        vertices[:, l] = np.linalg.solve(a, b)
+    return vertices
+
+
+class RegularPolyhedron(Polyhedron):
+    def __init__(self, radius, n_vert, orientation=0.):
+        dth = 2 * np.pi / n_vert
+        off = [radius * np.cos(np.pi / n_vert)] * n_vert
+        vertices = _tangent_polygon([l * dth for l in range(n_vert)], off)
+        Polyhedron.__init__(self, vertices, orientation)
+        self.radius_outer = radius
+
+
+class Rectangle(Polyhedron):
+    def __init__(self, width, height, orientation=0.):
+        self.width, self.height = width, height
+        off = [0.5 * height, 0.5 * width, 0.5 * height, 0.5 * width]
+        vertices = _tangent_polygon([l * 0.5 * np.pi for l in range(4)], off)
+        Polyhedron.__init__(self, vertices, orientation)
+
+
+class Square(Rectangle):
+    def __init__(self, side, orientation=0.):
+        Rectangle.__init__(self, side, side, orientation)
+
+
+class Shape3D(Shape):
+    def __init__(self):
+        Shape.__init__(self, 3)
+
+
+class Sphere(Shape3D):
+    def __init__(self, radius):
+        Shape3D.__init__(self)
+        self.radius = radius
+        self.n_chck = 1
+
+    def get_checkpoints(self):
+        return [[0., 0., 0.]], [self.radius]
+
+    def get_canvas_limits(self):
+        return [np.array([-self.radius, self.radius]) for _ in range(3)]
+
+
+class Polyhedron3D(Shape3D):
+    def __init__(self, vertices, radius=1e-3):
+        Shape3D.__init__(self)
+        self.vertices = vertices
+        self.n_vert = vertices.shape[1]
+        self.radius = radius
+
+    def get_checkpoints(self):
+        chck = [[self.vertices[0, l], self.vertices[1, l], self.vertices[2, l]]
+                for l in range(self.n_vert)]
+        return chck, [self.radius for _ in range(self.n_vert)]
+
+    def get_canvas_limits(self):
+        hi, lo = np.amax(self.vertices, axis=1), np.amin(self.vertices, axis=1)
+        return [np.array([lo[k], hi[k]]) for k in range(3)]
+
+
+class Cuboid(Polyhedron3D):
+    def __init__(self, width, depth, height, radius=1e-3):
+        self.width, self.depth, self.height = width, depth, height
+        w, d, h = 0.5 * width, 0.5 * depth, 0.5 * height
+        vertices = np.array([[sx * w, sy * d, sz * h]
+                             for sz in (-1, 1) for sy in (-1, 1)
+                             for sx in (-1, 1)]).T
+        Polyhedron3D.__init__(self, vertices, radius)
+
+
+class Cube(Cuboid):
+    def __init__(self, side, radius=1e-3):
+        Cuboid.__init__(self, side, side, side, radius)

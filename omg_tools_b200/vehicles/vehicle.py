@@ -1,0 +1,259 @@
+"""Vehicle base class: spline definition and collision/room constraint rows.
+
+Model-building interface and row order follow the reference's
+``omgtools/vehicles/vehicle.py`` (define_knots 80-87, define_splines 105-120,
+define_collision_constraints_2d 122-190, _3d 192-232, get_fleet_center 234-241).
+Host-side bookkeeping after a solve (store / predict / simulate) is reduced to
+the ideal, noise-free case: the vehicle follows its computed spline exactly
+(reference options 'ideal_prediction'/'ideal_update', vehicle.py:70-78,
+302-337, 339-410); plotting, delays and disturbances are out of scope.
+"""
+import numpy as np
+
+from ..basics.optilayer import OptiChild, inf
+from ..basics.spline import BSplineBasis
+from ..basics.spline_extra import definite_integral, sample_splines
+from ..basics.shape import Rectangle, Square, Circle
+
+
+class Vehicle(OptiChild):
+
+    def __init__(self, n_spl, degree, shapes, options=None):
+        options = options or {}
+        OptiChild.__init__(self, 'vehicle')
+        self.shapes = shapes if isinstance(shapes, list) else [shapes]
+        self.n_dim = self.shapes[0].n_dim
+        for shape in self.shapes:
+            if shape.n_dim != self.n_dim:
+                raise ValueError('All vehicle shapes should have same spatial' +
+                                 'dimension.')
+        self.prediction = {}
+        self.init_spline_values = None
+        self.degree = degree
+        self.to_simulate = True
+        self.set_default_options()
+        self.set_options(options)
+        self.define_knots(knot_intervals=10)
+        self.n_spl = n_spl
+
+    # ------------------------------------------------------------------
+    # options
+    # ------------------------------------------------------------------
+
+    def set_default_options(self):
+        self.options = {'safety_distance': 0., 'safety_weight': 10.,
+                        'room_constraints': True, 'stop_tol': 1.e-3,
+                        'ideal_prediction': True, 'ideal_update': True,
+                        '1storder_delay': False, 'time_constant': 0.1,
+                        'input_disturbance': None}
+
+    def set_options(self, options):
+        self.options.update(options)
+
+    def define_knots(self, **kwargs):
+        if 'knot_intervals' in kwargs:
+            self.knot_intervals = kwargs['knot_intervals']
+            self.knots = np.r_[np.zeros(self.degree), np.linspace(
+                0., 1., self.knot_intervals + 1), np.ones(self.degree)]
+        if 'knots' in kwargs:
+            self.knots = kwargs['knots']
+        self.basis = BSplineBasis(self.knots, self.degree)
+
+    def set_init_spline_values(self, values, n_seg=1):
+        self.init_spline_values = [0] * n_seg
+        for k in range(n_seg):
+            if values[k].shape != (len(self.basis), self.n_spl):
+                raise ValueError('Initial guess has wrong dimensions for spline ' +
+                                 str(k) + ', required: ' +
+                                 str((len(self.basis), self.n_spl)) +
+                                 ' while you gave: ' + str(values[k].shape))
+            self.init_spline_values[k] = values[k]
+
+    # ------------------------------------------------------------------
+    # optimization modelling
+    # ------------------------------------------------------------------
+
+    def define_splines(self, n_seg=1):
+        self.n_seg = n_seg
+        self.splines = []
+        if self.init_spline_values is not None:
+            init = self.init_spline_values
+            self.init_spline_values = None
+        else:
+            init = [None] * n_seg
+        for k in range(self.n_seg):
+            spline = self.define_spline_variable(
+                'splines_seg' + str(k), self.n_spl, value=init[k])
+            self.splines.append(spline)
+        return self.splines
+
+    def define_collision_constraints_2d(self, hyperplanes, room, positions,
+                                        horizon_time, tg_ha=0, offset=0):
+        t = self.define_symbol('t')
+        safety_distance = self.options['safety_distance']
+        safety_weight = self.options['safety_weight']
+        positions = [positions] if not isinstance(positions[0], list) \
+            else positions
+        for s, shape in enumerate(self.shapes):
+            position = positions[s]
+            checkpoints, rad = shape.get_checkpoints()
+            # obstacle avoidance: a.(R chk + pos) - b + rad + sd - eps <= 0
+            if shape in hyperplanes:
+                for k, hyperplane in enumerate(hyperplanes[shape]):
+                    a, b = hyperplane['a'], hyperplane['b']
+                    sl = 1 if 'slack' not in hyperplane else hyperplane['slack']
+                    if safety_distance > 0.:
+                        eps = self.define_spline_variable(
+                            'eps_' + str(s) + str(k))[0]
+                        obj = safety_weight * definite_integral(
+                            eps, t / horizon_time, 1.)
+                        self.define_objective(obj)
+                        self.define_constraint(eps - safety_distance, -inf, 0.)
+                        self.define_constraint(-eps, -inf, 0.)
+                    else:
+                        eps = 0.
+                    for l, chck in enumerate(checkpoints):
+                        con = 0
+                        con += (a[0] * chck[0] + a[1] * chck[1]) * (1. - tg_ha**2)
+                        con += (-a[0] * chck[1] + a[1] * chck[0]) * (2 * tg_ha)
+                        pos = [0, 0]
+                        pos[0] = position[0] * (1 + tg_ha**2) + offset * (1 - tg_ha**2)
+                        pos[1] = position[1] * (1 + tg_ha**2) + offset * (2 * tg_ha)
+                        con += (a[0] * pos[0] + a[1] * pos[1])
+                        con += (-b + sl * rad[l] + safety_distance - eps) * (1 + tg_ha**2)
+                        self.define_constraint(con, -inf, 0)
+            # room constraints
+            if self.options['room_constraints']:
+                lims = room['shape'].get_canvas_limits()
+                room_limits = [lims[k] + room['position'][k]
+                               for k in range(self.n_dim)]
+                axis_aligned = (
+                    isinstance(room['shape'], (Rectangle, Square)) and
+                    room['shape'].orientation == 0.0 and
+                    (isinstance(shape, Circle) or
+                     (isinstance(shape, (Rectangle, Square)) and
+                      shape.orientation == 0)) and
+                    isinstance(tg_ha, (int, float)) and tg_ha == 0.)
+                if axis_aligned:
+                    for chck in checkpoints:
+                        for k in range(self.n_dim):
+                            self.define_constraint(
+                                -(chck[k] + position[k]) + room_limits[k][0] + rad[0], -inf, 0.)
+                            self.define_constraint(
+                                (chck[k] + position[k]) - room_limits[k][1] + rad[0], -inf, 0.)
+                else:
+                    hyp_room = room['shape'].get_hyperplanes(
+                        position=room['position'])
+                    for l, chck in enumerate(checkpoints):
+                        for hpp in hyp_room.values():
+                            con = 0
+                            con += (hpp['a'][0] * chck[0] + hpp['a'][1] * chck[1]) * (1. - tg_ha**2)
+                            con += (-hpp['a'][0] * chck[1] + hpp['a'][1] * chck[0]) * (2 * tg_ha)
+                            pos = [0, 0]
+                            pos[0] = position[0] * (1 + tg_ha**2) + offset * (1 - tg_ha**2)
+                            pos[1] = position[1] * (1 + tg_ha**2) + offset * (2 * tg_ha)
+                            con += (hpp['a'][0] * pos[0] + hpp['a'][1] * pos[1])
+                            con += (-hpp['b'] + rad[l]) * (1 + tg_ha**2)
+                            self.define_constraint(con, -inf, 0)
+
+    def define_collision_constraints_3d(self, hyperplanes, room, positions,
+                                        horizon_time):
+        t = self.define_symbol('t')
+        safety_distance = self.options['safety_distance']
+        safety_weight = self.options['safety_weight']
+        positions = [positions] if not isinstance(positions[0], list) \
+            else positions
+        for s, shape in enumerate(self.shapes):
+            position = positions[s]
+            checkpoints, rad = shape.get_checkpoints()
+            if shape in hyperplanes:
+                for k, hyperplane in enumerate(hyperplanes[shape]):
+                    a, b = hyperplane['a'], hyperplane['b']
+                    if safety_distance > 0.:
+                        eps = self.define_spline_variable(
+                            'eps_' + str(s) + str(k))[0]
+                        obj = safety_weight * definite_integral(
+                            eps, t / horizon_time, 1.)
+                        self.define_objective(obj)
+                        self.define_constraint(eps - safety_distance, -inf, 0.)
+                        self.define_constraint(-eps, -inf, 0.)
+                    else:
+                        eps = 0.
+                    for l, chck in enumerate(checkpoints):
+                        self.define_constraint(
+                            sum([a[q] * (chck[q] + position[q]) for q in range(3)])
+                            - b + rad[l] + safety_distance - eps, -inf, 0)
+            if self.options['room_constraints']:
+                lims = room['shape'].get_canvas_limits()
+                room_limits = [lims[k] + room['position'][k]
+                               for k in range(self.n_dim)]
+                for chck in checkpoints:
+                    for k in range(3):
+                        self.define_constraint(
+                            -(chck[k] + position[k]) + room_limits[k][0], -inf, 0.)
+                        self.define_constraint(
+                            (chck[k] + position[k]) - room_limits[k][1], -inf, 0.)
+
+    def get_fleet_center(self, splines, rel_pos, substitute=True):
+        rel_pos = list(rel_pos) if not isinstance(rel_pos, list) else rel_pos
+        center = [s + rp for s, rp in zip(splines, rel_pos)]
+        if substitute:
+            return self.define_substitute('fleet_center', center)
+        return center
+
+    def set_parameters(self, current_time):
+        return {self: {}}
+
+    def init(self):
+        pass
+
+    # ------------------------------------------------------------------
+    # ideal host-side bookkeeping between MPC steps
+    # ------------------------------------------------------------------
+
+    def store(self, current_time, sample_time, spline_segments, segment_times,
+              time_axis=None, **kwargs):
+        """Sample the computed splines into trajectories
+        (reference vehicle.py:250-300, single segment)."""
+        splines = spline_segments[0]
+        horizon_time = segment_times if not isinstance(segment_times, list) \
+            else segment_times[0]
+        if time_axis is None:
+            n_samp = int(round(horizon_time / sample_time, 6)) + 1
+            time_axis = np.linspace(0., (n_samp - 1) * sample_time, n_samp)
+        self.trajectories = self.splines2signals(
+            [s.scale(horizon_time) for s in splines], time_axis)
+        self.trajectories['time'] = time_axis - time_axis[0] + current_time
+        self.trajectories['splines'] = np.c_[
+            sample_splines([s.scale(horizon_time) for s in splines], time_axis)]
+        if not hasattr(self, 'signals'):
+            self.signals = {}
+            for key in self.trajectories:
+                val = np.atleast_2d(self.trajectories[key])
+                self.signals[key] = val[:, :1] if key != 'time' \
+                    else np.array([[current_time]])
+
+    def predict(self, current_time, predict_time, sample_time, state0=None,
+                input0=None, dinput0=None, delay=0, enforce_states=False,
+                enforce_inputs=False):
+        """Ideal prediction: state/input of the stored trajectory after
+        predict_time (reference vehicle.py:302-337 with ideal_prediction)."""
+        if not hasattr(self, 'trajectories') or enforce_states and state0 is None \
+                and not hasattr(self, 'trajectories'):
+            return
+        if state0 is not None and input0 is not None:
+            self.prediction['state'] = np.asarray(state0, dtype=float)
+            self.prediction['input'] = np.asarray(input0, dtype=float)
+            return
+        n_samp = int(np.round(predict_time / sample_time, 6))
+        self.prediction['state'] = self.trajectories['state'][:, n_samp]
+        self.prediction['input'] = self.trajectories['input'][:, n_samp]
+        if 'dinput' in self.trajectories:
+            self.prediction['dinput'] = self.trajectories['dinput'][:, n_samp]
+
+    def simulate(self, simulation_time, sample_time):
+        """Ideal update: follow the stored trajectory."""
+        n_samp = int(np.round(simulation_time / sample_time, 6))
+        for key in self.trajectories:
+            val = np.atleast_2d(self.trajectories[key])
+            self.signals[key] = np.c_[self.signals[key], val[:, 1:n_samp + 1]]

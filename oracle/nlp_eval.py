@@ -1,0 +1,88 @@
+"""ORACLE (test infrastructure, not product code): numpy evaluation of the
+lowered NLP tables -- parameter tape V(p), g, J, f, grad f and the Lagrangian
+Hessian slots.  It restates what CasADi's expanded SX functions compute for the
+reference (optilayer.py:49-60: nlpsol builds f, g, J_g, H_L evaluators) on this
+framework's table format.  Only tests/, bench.py's cpu_baseline leg and
+__graft_entry__.smoke() may import it.  parity unpinned: no CasADi/IPOPT
+binary exists in this image, see DESIGN.md.
+"""
+import numpy as np
+
+
+def eval_tape(tb, p):
+    V = np.zeros(tb.n_v)
+    V[0] = 1.0
+    V[1:1 + tb.n_par] = p
+    base = 1 + tb.n_par
+    for e in range(len(tb.tape_func)):
+        lo, hi = tb.tape_ptr[e], tb.tape_ptr[e + 1]
+        acc = 0.0
+        for t in range(lo, hi):
+            f = tb.tape_fac[t]
+            acc += tb.tape_coef[t] * V[f[0]] * V[f[1]] * V[f[2]] * V[f[3]]
+        fn = tb.tape_func[e]
+        if fn == 1:
+            acc = 1.0 / acc
+        elif fn == 2:
+            acc = 1.0 if acc >= 0.0 else 0.0
+        elif fn == 3:
+            acc = 1.0 if acc > 0.0 else 0.0
+        elif fn == 4:
+            acc = np.sin(acc)
+        elif fn == 5:
+            acc = np.cos(acc)
+        elif fn == 6:
+            acc = np.sqrt(acc)
+        V[base + e] = acc
+    return V
+
+
+def _eval_terms(tl, V, xe, lam_ext=None):
+    vals = tl.coef * V[tl.cidx]
+    for k in range(tl.xi.shape[1]):
+        vals = vals * xe[tl.xi[:, k]]
+    if lam_ext is not None:
+        vals = vals * lam_ext[tl.lrow]
+    out = np.zeros(tl.n_out)
+    seg = np.repeat(np.arange(tl.n_out), np.diff(tl.ptr))
+    np.add.at(out, seg, vals)
+    return out
+
+
+class TableEval(object):
+    def __init__(self, tb):
+        self.tb = tb
+
+    def tape(self, p):
+        return eval_tape(self.tb, np.asarray(p, dtype=float))
+
+    def _xe(self, x):
+        return np.r_[np.asarray(x, dtype=float), 1.0]
+
+    def g(self, x, V):
+        return _eval_terms(self.tb.G, V, self._xe(x))
+
+    def f(self, x, V):
+        return _eval_terms(self.tb.F, V, self._xe(x))[0]
+
+    def gradf(self, x, V):
+        return _eval_terms(self.tb.DF, V, self._xe(x))
+
+    def jac_vals(self, x, V):
+        return _eval_terms(self.tb.J, V, self._xe(x))
+
+    def jac_dense(self, x, V):
+        J = np.zeros((self.tb.m, self.tb.n))
+        J[self.tb.jrow, self.tb.jcol] = self.jac_vals(x, V)
+        return J
+
+    def hess_vals(self, x, V, lam, obj_factor=1.0):
+        lam_ext = np.r_[np.asarray(lam, dtype=float), obj_factor]
+        return _eval_terms(self.tb.W, V, self._xe(x), lam_ext)
+
+    def hess_dense(self, x, V, lam, obj_factor=1.0):
+        W = np.zeros((self.tb.n, self.tb.n))
+        vals = self.hess_vals(x, V, lam, obj_factor)
+        W[self.tb.wrow, self.tb.wcol] = vals
+        W[self.tb.wcol, self.tb.wrow] = vals
+        return W
