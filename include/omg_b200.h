@@ -1,0 +1,155 @@
+/* omg_b200.h -- C ABI of libomgb200.so: batched spline-NLP interior-point solve
+ * on NVIDIA B200 (sm_100a).
+ *
+ * This library replaces, for OMG-tools' per-MPC-step solve, the CasADi+IPOPT
+ * call of the reference:
+ *
+ *   omg_problem_create   <->  nlpsol('solver','ipopt',{x,p,f,g},opts)
+ *                              omgtools/basics/optilayer.py:49-60 (create_nlp);
+ *                              C++ twin: Point2Point.cpp:80-91 (nlpsol(..."nlp.so"))
+ *   omg_solve_batch      <->  result = self.problem(x0=var,p=par,lbg=lb,ubg=ub)
+ *                              omgtools/problems/problem.py:113 (and admm.py:390);
+ *                              C++ twin: Point2Point::solve, Point2Point.cpp:207-231
+ *   status/iters arrays  <->  self.problem.stats()['return_status']
+ *                              omgtools/problems/problem.py:119-128
+ *   omg_shift_batch      <->  father.transform_primal_splines(T.dot(coeffs))
+ *                              omgtools/problems/point2point.py:187-198,
+ *                              optilayer.py:470-490; C++: transformSplines,
+ *                              export.py:406-444
+ *   omg_problem_destroy  <->  (garbage collection of the casadi Function)
+ *
+ * Conventions: plain C, no C++/torch types.  Unless a function name ends in
+ * _host, all data pointers are DEVICE pointers owned by the caller; the library
+ * owns only the uploaded tables and its workspaces.  Calls on one handle are
+ * stream-ordered and not re-entrant.  Every function returns 0 on success or a
+ * negative error code; omg_last_error() gives the message (thread-local).
+ * Nothing throws across this boundary.
+ */
+#ifndef OMG_B200_H
+#define OMG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OMG_ABI_VERSION 1
+
+/* CSR list of polynomial terms per output slot:
+ *   out[s] = sum_{t in [ptr[s],ptr[s+1])} coef[t] * V[cidx[t]]
+ *            * prod_{k<width} x_ext[xi[t*width+k]]   ( * lam_ext[lrow[t]] if lrow )
+ * x_ext = [x, 1], lam_ext = [lambda (m rows), obj_factor]. */
+typedef struct omg_termlist {
+  int32_t n_out, n_terms, width;
+  const int32_t* ptr;   /* [n_out+1] */
+  const double*  coef;  /* [n_terms] */
+  const int32_t* cidx;  /* [n_terms] index into the parameter tape V */
+  const int32_t* xi;    /* [n_terms*width] indices into x_ext (n = constant 1) */
+  const int32_t* lrow;  /* [n_terms] or NULL */
+} omg_termlist;
+
+/* Lowered NLP  min f(x,p)  s.t.  lbg <= g(x,p) <= ubg  (HOST pointers; copied
+ * by omg_problem_create).  Built by omg_tools_b200/basics/lowering.py. */
+typedef struct omg_tables {
+  int32_t abi_version;
+  int32_t n, m, n_par, n_v, degree;
+  /* parameter tape: V[0]=1, V[1..n_par]=p, entry e -> V[1+n_par+e] =
+   * func( sum_t coef[t]*V[f0]*V[f1]*V[f2]*V[f3] ), evaluated level by level */
+  int32_t n_tape, n_tape_terms, n_levels;
+  const int32_t* tape_func;   /* [n_tape] 0 id,1 inv,2 ge0,3 gt0,4 sin,5 cos,6 sqrt */
+  const int32_t* tape_ptr;    /* [n_tape+1] */
+  const double*  tape_coef;   /* [n_tape_terms] */
+  const int32_t* tape_fac;    /* [n_tape_terms*4] */
+  const int32_t* level_ptr;   /* [n_levels+1] entry ranges per level */
+  omg_termlist G, F, DF, J, W;
+  /* Jacobian pattern, slots sorted by (row, col) */
+  int32_t nnz_j;
+  const int32_t* jrow; const int32_t* jcol; const int32_t* jrow_ptr; /* [m+1] */
+  /* Lagrangian-Hessian pattern (lower triangle) and its position in H */
+  int32_t nnz_w;
+  const int32_t* wrow; const int32_t* wcol; const int32_t* w2h;
+  /* condensed KKT pattern H = W + J^T Sigma J: gather lists of slot pairs */
+  int32_t nnz_h, n_hp;
+  const int32_t* hrow; const int32_t* hcol; const int32_t* hp_ptr; /* [nnz_h+1] */
+  const int32_t* hp_s1; const int32_t* hp_s2; const int32_t* hp_row; /* [n_hp] */
+  /* default bounds (used to size the equality border) */
+  const double* lbg; const double* ubg;
+} omg_tables;
+
+/* Interior-point options; defaults = the reference's IPOPT settings
+ * (problem.py:57-60) + IPOPT defaults.  Fill with omg_default_options first. */
+typedef struct omg_options {
+  double tol, constr_viol_tol, dual_inf_tol, compl_inf_tol;
+  double mu_init, bound_push, bound_frac, mult_bound_push, bound_relax_factor;
+  double scaling_max_gradient;
+  int32_t max_iter;
+  int32_t trace;          /* 1: record per-iteration diagnostics (debug) */
+} omg_options;
+
+/* per-instance status codes (mapped to IPOPT strings in solver/b200.py) */
+enum {
+  OMG_SOLVE_SUCCEEDED = 0,
+  OMG_MAX_ITER_EXCEEDED = 1,
+  OMG_RESTORATION_FAILED = 2,
+  OMG_ERROR_IN_STEP_COMPUTATION = 3,
+  OMG_INVALID_NUMBER_DETECTED = 4,
+  OMG_INFEASIBLE_PROBLEM_DETECTED = 5
+};
+
+typedef struct omg_problem omg_problem;   /* opaque handle */
+
+void omg_default_options(omg_options* opt);
+
+/* Upload tables to `device`, size workspaces.  Returns NULL on error. */
+omg_problem* omg_problem_create(const omg_tables* tables,
+                                const omg_options* opt, int device);
+void omg_problem_destroy(omg_problem* h);
+int  omg_set_options(omg_problem* h, const omg_options* opt);
+
+/* Solve B independent instances of the structure (DEVICE pointers, row-major
+ * [B][.] ; lbg/ubg are [m] if bounds_shared else [B][m]; lam_g0 may be NULL).
+ * stream: a cudaStream_t (NULL = default stream).  Asynchronous. */
+int omg_solve_batch(omg_problem* h, int32_t B,
+                    const double* x0, const double* p,
+                    const double* lbg, const double* ubg, int32_t bounds_shared,
+                    const double* lam_g0,
+                    double* x, double* lam_g, double* f,
+                    int32_t* status, int32_t* iters, void* stream);
+
+/* Same call with HOST buffers: H2D of inputs, solve, D2H of results,
+ * synchronous.  This is the call the reference-facing plugin times end to end. */
+int omg_solve_batch_host(omg_problem* h, int32_t B,
+                         const double* x0, const double* p,
+                         const double* lbg, const double* ubg,
+                         int32_t bounds_shared, const double* lam_g0,
+                         double* x, double* lam_g, double* f,
+                         int32_t* status, int32_t* iters);
+
+/* Receding-horizon warm start: x[b, off:off+len*ncol] <- T (len x len) applied
+ * to each of the ncol columns, for n_blocks spline variables (DEVICE x,
+ * in place).  offs/lens/ncols: HOST int arrays [n_blocks]; T: HOST array of the
+ * n_blocks row-major matrices, concatenated. */
+int omg_shift_batch(omg_problem* h, int32_t B, double* x,
+                    int32_t n_blocks, const int32_t* offs, const int32_t* lens,
+                    const int32_t* ncols, const double* T, void* stream);
+
+/* Debug trace of the last omg_solve_batch with opt.trace=1: per iteration of
+ * instance 0, 8 doubles {iter, f, constr_inf, dual_inf, mu, E0, alpha, delta_w}.
+ * Copies up to max_rows rows to HOST `out`; returns the number of rows. */
+int omg_get_trace(omg_problem* h, double* out, int32_t max_rows);
+
+/* Introspection */
+int omg_get_info(omg_problem* h, int32_t* n, int32_t* m, int32_t* n_par,
+                 int32_t* smem_bytes, int32_t* ctas_per_sm, int32_t* n_sm);
+/* Device time (ms) and kernel-launch count of the last omg_solve_batch,
+ * measured with CUDA events on the caller's stream. */
+int omg_last_timing(omg_problem* h, float* kernel_ms, int32_t* launches);
+
+const char* omg_last_error(void);
+int omg_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OMG_B200_H */

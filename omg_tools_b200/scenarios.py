@@ -1,0 +1,122 @@
+"""BASELINE.json scenario builders, shared by tests and
+bench.py.  Each returns an initialised problem whose ``father.tables`` is the
+lowered structure; instance data (x0, p) come from ``instance_data``."""
+import numpy as np
+
+from . import (Holonomic, Environment, Obstacle, Point2point, Square, Circle,
+               Beam, Rectangle)
+
+
+def _p2p(vehicle, environment, options, build_solver):
+    opts = {'verbose': 0}
+    opts.update(options or {})
+    problem = Point2point(vehicle, environment, options=opts, freeT=False)
+    if build_solver:
+        problem.init()
+    else:
+        # model + tables only (no CUDA library needed): used by the CPU tests
+        problem.father.reset()
+        problem.construct()
+        f = problem.father
+        f.translate_symbols()
+        f.construct_variables()
+        f.construct_parameters()
+        rows, lb, ub = f.construct_constraints()
+        from .basics.lowering import lower
+        f.tables = lower(f._var_ids, f._par_ids, rows, f.construct_objective(),
+                         lb, ub)
+        f.init_variables()
+        f.init_parameters()
+        f.init_transformations(problem.init_primal_transform,
+                               problem.init_dual_transform)
+    problem.reinitialize()
+    return problem
+
+
+def config1(options=None, build_solver=True):
+    """examples/p2p_holonomic.py as written at the surveyed commit: one moving
+    Circle(0.5) obstacle, safety_distance 0.1 (n=98, m=325, n_par=17)."""
+    vehicle = Holonomic()
+    vehicle.set_options({'safety_distance': 0.1})
+    vehicle.set_initial_conditions([-1.5, -1.5])
+    vehicle.set_terminal_conditions([2., 2.])
+    environment = Environment(room={'shape': Square(5.)})
+    trajectories = {'velocity': {'time': [0., 40.],
+                                 'values': [[-0.35, 0.35], [0., 0.15]]}}
+    environment.add_obstacle(Obstacle(
+        {'position': [1.5, -1]}, shape=Circle(0.5), options={'bounce': False},
+        simulation={'trajectories': trajectories}))
+    return _p2p(vehicle, environment, options, build_solver)
+
+
+CONFIG2_OBSTACLES = [(-0.5, -0.3), (0.6, 0.4), (1.4, -0.6)]
+
+
+def config2(options=None, build_solver=True):
+    """batch Holonomic Point2point, 3 static Circle(0.4) obstacles, sd=0.1
+    (n=190, m=563, n_par=35); layout fixed by SURVEY.md section 8d."""
+    vehicle = Holonomic()
+    vehicle.set_options({'safety_distance': 0.1})
+    vehicle.set_initial_conditions([-1.5, -1.5])
+    vehicle.set_terminal_conditions([2., 2.])
+    environment = Environment(room={'shape': Square(5.)})
+    for pos in CONFIG2_OBSTACLES:
+        environment.add_obstacle(Obstacle({'position': list(pos)},
+                                          shape=Circle(0.4)))
+    return _p2p(vehicle, environment, options, build_solver)
+
+
+def config5(options=None, build_solver=True):
+    """examples/revolving_door.py: 2 static + 2 rotating Beam obstacles
+    (n=184, m=862)."""
+    vehicle = Holonomic()
+    vehicle.set_initial_conditions([0., -2.0])
+    vehicle.set_terminal_conditions([0., 2.0])
+    environment = Environment(room={'shape': Square(5.)})
+    beam1 = Beam(width=2.2, height=0.2)
+    environment.add_obstacle(Obstacle({'position': [-2., 0.]}, shape=beam1))
+    environment.add_obstacle(Obstacle({'position': [2., 0.]}, shape=beam1))
+    beam2 = Beam(width=1.4, height=0.2)
+    horizon_time = 10.
+    omega = 1.5 * (2 * np.pi / horizon_time)
+    environment.add_obstacle(Obstacle(
+        {'position': [0., 0.], 'velocity': [0., 0.], 'angular_velocity': omega},
+        shape=beam2, simulation={}, options={'horizon_time': horizon_time}))
+    environment.add_obstacle(Obstacle(
+        {'position': [0., 0.], 'velocity': [0., 0.], 'orientation': 0.5 * np.pi,
+         'angular_velocity': omega},
+        shape=beam2, simulation={}, options={'horizon_time': horizon_time}))
+    opts = {'horizon_time': horizon_time}
+    opts.update(options or {})
+    return _p2p(vehicle, environment, opts, build_solver)
+
+
+def instance_data(problem, batch, jitter=0.0, seed=0, current_time=0.):
+    """(X0[B,n], P[B,n_par]) for a cold solve: linear initial guess
+    (holonomic.py:118-127) and parameters at current_time.  jitter>0 perturbs
+    state0/poseT by U(-jitter,jitter) and obstacle positions by U(-j/2, j/2)
+    (SURVEY.md section 8d)."""
+    f = problem.father
+    rng = np.random.default_rng(seed)
+    vehicle = problem.vehicles[0]
+    state0 = np.array(vehicle.prediction['state'], dtype=float)
+    poseT = np.array(vehicle.poseT, dtype=float)
+    obst0 = [o.signals['position'][:, -1].copy()
+             for o in problem.environment.obstacles]
+    X0 = np.zeros((batch, f.tables.n))
+    P = np.zeros((batch, f.tables.n_par))
+    for b in range(batch):
+        if jitter > 0. and b > 0:
+            vehicle.prediction['state'] = state0 + rng.uniform(-jitter, jitter, 2)
+            vehicle.poseT = poseT + rng.uniform(-jitter, jitter, 2)
+            for o, p0 in zip(problem.environment.obstacles, obst0):
+                o.signals['position'][:, -1] = p0 + rng.uniform(
+                    -0.5 * jitter, 0.5 * jitter, len(p0))
+        problem.reinitialize()
+        X0[b] = f.get_variables().cat
+        P[b] = f.set_parameters(current_time).cat
+    vehicle.prediction['state'], vehicle.poseT = state0, poseT
+    for o, p0 in zip(problem.environment.obstacles, obst0):
+        o.signals['position'][:, -1] = p0
+    problem.reinitialize()
+    return X0, P

@@ -1,0 +1,316 @@
+"""ctypes binding of libomgb200.so and the solver object that stands where the
+reference holds ``nlpsol('solver','ipopt',...)``.
+
+``B200Solver`` keeps the reference's call contract (problem.py:113-128):
+
+    result = problem(x0=var, p=par, lbg=lb, ubg=ub)   # -> {'x','lam_g','f'}
+    problem.stats()['return_status']                  # IPOPT status strings
+
+and adds the batched entry points ``solve_batch`` (host numpy arrays; H2D/D2H
+inside the C call) and ``solve_batch_device`` (torch CUDA tensors, zero-copy).
+There is no CPU fallback: if the shared library or a CUDA device is missing the
+constructor raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), 'csrc', 'libomgb200.so')
+
+STATUS_STRINGS = {
+    0: 'Solve_Succeeded', 1: 'Maximum_Iterations_Exceeded',
+    2: 'Restoration_Failed', 3: 'Error_In_Step_Computation',
+    4: 'Invalid_Number_Detected', 5: 'Infeasible_Problem_Detected'}
+
+_i32p = C.POINTER(C.c_int32)
+_f64p = C.POINTER(C.c_double)
+
+
+class _TermList(C.Structure):
+    _fields_ = [('n_out', C.c_int32), ('n_terms', C.c_int32), ('width', C.c_int32),
+                ('ptr', _i32p), ('coef', _f64p), ('cidx', _i32p), ('xi', _i32p),
+                ('lrow', _i32p)]
+
+
+class _Tables(C.Structure):
+    _fields_ = [
+        ('abi_version', C.c_int32),
+        ('n', C.c_int32), ('m', C.c_int32), ('n_par', C.c_int32),
+        ('n_v', C.c_int32), ('degree', C.c_int32),
+        ('n_tape', C.c_int32), ('n_tape_terms', C.c_int32), ('n_levels', C.c_int32),
+        ('tape_func', _i32p), ('tape_ptr', _i32p), ('tape_coef', _f64p),
+        ('tape_fac', _i32p), ('level_ptr', _i32p),
+        ('G', _TermList), ('F', _TermList), ('DF', _TermList), ('J', _TermList),
+        ('W', _TermList),
+        ('nnz_j', C.c_int32), ('jrow', _i32p), ('jcol', _i32p), ('jrow_ptr', _i32p),
+        ('nnz_w', C.c_int32), ('wrow', _i32p), ('wcol', _i32p), ('w2h', _i32p),
+        ('nnz_h', C.c_int32), ('n_hp', C.c_int32),
+        ('hrow', _i32p), ('hcol', _i32p), ('hp_ptr', _i32p),
+        ('hp_s1', _i32p), ('hp_s2', _i32p), ('hp_row', _i32p),
+        ('lbg', _f64p), ('ubg', _f64p)]
+
+
+class _Options(C.Structure):
+    _fields_ = [('tol', C.c_double), ('constr_viol_tol', C.c_double),
+                ('dual_inf_tol', C.c_double), ('compl_inf_tol', C.c_double),
+                ('mu_init', C.c_double), ('bound_push', C.c_double),
+                ('bound_frac', C.c_double), ('mult_bound_push', C.c_double),
+                ('bound_relax_factor', C.c_double),
+                ('scaling_max_gradient', C.c_double),
+                ('max_iter', C.c_int32), ('trace', C.c_int32)]
+
+
+EXPORTS = ['omg_abi_version', 'omg_last_error', 'omg_default_options',
+           'omg_problem_create', 'omg_problem_destroy', 'omg_set_options',
+           'omg_solve_batch', 'omg_solve_batch_host', 'omg_shift_batch',
+           'omg_get_trace', 'omg_get_info', 'omg_last_timing']
+
+_lib = None
+
+
+def load_library(path=None):
+    """Load libomgb200.so (built by __graft_entry__.build() / csrc/Makefile)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise RuntimeError(
+            'libomgb200.so not found at %s: build it with '
+            '`python -c "import __graft_entry__ as g; g.build()"` '
+            '(there is no CPU fallback)' % path)
+    lib = C.CDLL(path)
+    lib.omg_abi_version.restype = C.c_int
+    lib.omg_last_error.restype = C.c_char_p
+    lib.omg_default_options.argtypes = [C.POINTER(_Options)]
+    lib.omg_default_options.restype = None
+    lib.omg_problem_create.argtypes = [C.POINTER(_Tables), C.POINTER(_Options), C.c_int]
+    lib.omg_problem_create.restype = C.c_void_p
+    lib.omg_problem_destroy.argtypes = [C.c_void_p]
+    lib.omg_problem_destroy.restype = None
+    lib.omg_set_options.argtypes = [C.c_void_p, C.POINTER(_Options)]
+    vp = C.c_void_p
+    lib.omg_solve_batch.argtypes = [vp, C.c_int32, vp, vp, vp, vp, C.c_int32, vp,
+                                    vp, vp, vp, vp, vp, vp]
+    lib.omg_solve_batch_host.argtypes = [vp, C.c_int32, vp, vp, vp, vp, C.c_int32,
+                                         vp, vp, vp, vp, vp, vp]
+    lib.omg_shift_batch.argtypes = [vp, C.c_int32, vp, C.c_int32, vp, vp, vp, vp, vp]
+    lib.omg_get_trace.argtypes = [vp, vp, C.c_int32]
+    lib.omg_get_info.argtypes = [vp] + [_i32p] * 6
+    lib.omg_last_timing.argtypes = [vp, C.POINTER(C.c_float), _i32p]
+    _lib = lib
+    return lib
+
+
+def _ptr(arr, typ):
+    return arr.ctypes.data_as(typ)
+
+
+class _Keep(object):
+    """Owns contiguous numpy copies referenced by a ctypes struct."""
+
+    def __init__(self):
+        self.arrays = []
+
+    def i32(self, a):
+        a = np.ascontiguousarray(a, dtype=np.int32)
+        self.arrays.append(a)
+        return _ptr(a, _i32p)
+
+    def f64(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        self.arrays.append(a)
+        return _ptr(a, _f64p)
+
+
+def pack_tables(tb):
+    """NLPTables -> (ctypes omg_tables, keep-alive object)."""
+    keep = _Keep()
+
+    def tl(t, with_lrow=False):
+        s = _TermList()
+        s.n_out, s.n_terms, s.width = t.n_out, t.n_terms, t.width
+        s.ptr, s.coef = keep.i32(t.ptr), keep.f64(t.coef)
+        s.cidx, s.xi = keep.i32(t.cidx), keep.i32(t.xi.reshape(-1))
+        s.lrow = keep.i32(t.lrow) if with_lrow else None
+        return s
+
+    T = _Tables()
+    T.abi_version = 1
+    T.n, T.m, T.n_par, T.n_v, T.degree = tb.n, tb.m, tb.n_par, tb.n_v, tb.degree
+    T.n_tape, T.n_tape_terms = len(tb.tape_func), len(tb.tape_coef)
+    T.n_levels = len(tb.level_ptr) - 1
+    T.tape_func, T.tape_ptr = keep.i32(tb.tape_func), keep.i32(tb.tape_ptr)
+    T.tape_coef, T.tape_fac = keep.f64(tb.tape_coef), keep.i32(tb.tape_fac.reshape(-1))
+    T.level_ptr = keep.i32(tb.level_ptr)
+    T.G, T.F, T.DF, T.J = tl(tb.G), tl(tb.F), tl(tb.DF), tl(tb.J)
+    T.W = tl(tb.W, True)
+    T.nnz_j = tb.nnz_j
+    T.jrow, T.jcol, T.jrow_ptr = keep.i32(tb.jrow), keep.i32(tb.jcol), keep.i32(tb.jrow_ptr)
+    T.nnz_w = tb.nnz_w
+    T.wrow, T.wcol, T.w2h = keep.i32(tb.wrow), keep.i32(tb.wcol), keep.i32(tb.w2h)
+    T.nnz_h, T.n_hp = tb.nnz_h, len(tb.hp_s1)
+    T.hrow, T.hcol, T.hp_ptr = keep.i32(tb.hrow), keep.i32(tb.hcol), keep.i32(tb.hp_ptr)
+    T.hp_s1, T.hp_s2, T.hp_row = keep.i32(tb.hp_s1), keep.i32(tb.hp_s2), keep.i32(tb.hp_row)
+    T.lbg, T.ubg = keep.f64(tb.lbg), keep.f64(tb.ubg)
+    return T, keep
+
+
+class B200Solver(object):
+    """Batched interior-point solver on one B200 for one NLP structure."""
+
+    def __init__(self, tables, options=None, device=None):
+        self.lib = load_library()
+        if self.lib.omg_abi_version() != 1:
+            raise RuntimeError('libomgb200.so ABI version mismatch')
+        self.tables = tables
+        self.n, self.m, self.n_par = tables.n, tables.m, tables.n_par
+        self._opt = _Options()
+        self.lib.omg_default_options(C.byref(self._opt))
+        self._apply_options(options or {})
+        if device is None:
+            device = int(os.environ.get('LOCAL_RANK', '0')) \
+                if 'OMG_B200_DEVICE' not in os.environ \
+                else int(os.environ['OMG_B200_DEVICE'])
+        self.device = device
+        T, keep = pack_tables(tables)
+        self._handle = self.lib.omg_problem_create(C.byref(T), C.byref(self._opt),
+                                                   int(device))
+        del keep
+        if not self._handle:
+            raise RuntimeError('omg_problem_create failed: %s' %
+                               self.lib.omg_last_error().decode())
+        self._stats = {'return_status': None, 'iter_count': 0}
+
+    def _apply_options(self, options):
+        fields = dict((f[0], f[1]) for f in _Options._fields_)
+        for key, value in options.items():
+            if key in fields:
+                setattr(self._opt, key, value)
+            # other IPOPT keys (print_level, warm_start_init_point='yes',
+            # fixed_variable_treatment, linear_solver ...) have no effect here:
+            # warm start pushes are always the 'yes' variants
+
+    def set_options(self, options):
+        self._apply_options(options)
+        self._check(self.lib.omg_set_options(self._handle, C.byref(self._opt)))
+
+    def __del__(self):
+        try:
+            if getattr(self, '_handle', None):
+                self.lib.omg_problem_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError('libomgb200: %s' % self.lib.omg_last_error().decode())
+
+    # ------------------------------------------------------------------
+    def info(self):
+        vals = [C.c_int32() for _ in range(6)]
+        self._check(self.lib.omg_get_info(self._handle, *[C.byref(v) for v in vals]))
+        keys = ('n', 'm', 'n_par', 'smem_bytes', 'ctas_per_sm', 'n_sm')
+        return dict(zip(keys, [v.value for v in vals]))
+
+    def last_timing(self):
+        ms, nl = C.c_float(), C.c_int32()
+        self._check(self.lib.omg_last_timing(self._handle, C.byref(ms), C.byref(nl)))
+        return ms.value, nl.value
+
+    def trace(self, max_rows=512):
+        out = np.zeros((max_rows, 8))
+        rows = self.lib.omg_get_trace(self._handle, out.ctypes.data, max_rows)
+        if rows < 0:
+            self._check(rows)
+        return out[:rows]
+
+    # ------------------------------------------------------------------
+    def _bounds(self, lbg, ubg, B):
+        lbg = self.tables.lbg if lbg is None else np.asarray(lbg, dtype=np.float64)
+        ubg = self.tables.ubg if ubg is None else np.asarray(ubg, dtype=np.float64)
+        lbg = np.ascontiguousarray(np.asarray(lbg, dtype=np.float64))
+        ubg = np.ascontiguousarray(np.asarray(ubg, dtype=np.float64))
+        shared = 1 if lbg.ndim == 1 else 0
+        if (shared and lbg.size != self.m) or (not shared and lbg.shape != (B, self.m)):
+            raise ValueError('lbg/ubg must have shape (m,) or (B, m)')
+        if ubg.shape != lbg.shape:
+            raise ValueError('lbg and ubg shapes differ')
+        return lbg, ubg, shared
+
+    def solve_batch(self, X0, P, lbg=None, ubg=None, lam_g0=None):
+        """Host arrays in, host arrays out (H2D + solve + D2H in one C call)."""
+        X0 = np.ascontiguousarray(X0, dtype=np.float64).reshape(-1, self.n)
+        B = X0.shape[0]
+        P = np.ascontiguousarray(P, dtype=np.float64).reshape(B, self.n_par)
+        lbg, ubg, shared = self._bounds(lbg, ubg, B)
+        lam0 = None
+        if lam_g0 is not None:
+            lam0 = np.ascontiguousarray(lam_g0, dtype=np.float64).reshape(B, self.m)
+        X = np.empty((B, self.n))
+        LAM = np.empty((B, self.m))
+        F = np.empty(B)
+        status = np.empty(B, dtype=np.int32)
+        iters = np.empty(B, dtype=np.int32)
+        self._check(self.lib.omg_solve_batch_host(
+            self._handle, B, X0.ctypes.data, P.ctypes.data, lbg.ctypes.data,
+            ubg.ctypes.data, shared, lam0.ctypes.data if lam0 is not None else None,
+            X.ctypes.data, LAM.ctypes.data, F.ctypes.data, status.ctypes.data,
+            iters.ctypes.data))
+        return {'x': X, 'lam_g': LAM, 'f': F, 'status': status, 'iters': iters}
+
+    def solve_batch_device(self, X0, P, LBG, UBG, X, LAM, F, STATUS, ITERS,
+                           lam_g0=None, stream=None):
+        """torch CUDA tensors (float64 / int32, contiguous); asynchronous on
+        ``stream`` (torch.cuda.Stream or None = current)."""
+        import torch
+        B = X0.shape[0]
+        for t in (X0, P, LBG, UBG, X, LAM, F):
+            if t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous():
+                raise ValueError('expected contiguous float64 CUDA tensors')
+        shared = 1 if LBG.dim() == 1 else 0
+        if stream is None:
+            stream = torch.cuda.current_stream(X0.device)
+        self._check(self.lib.omg_solve_batch(
+            self._handle, B, X0.data_ptr(), P.data_ptr(), LBG.data_ptr(),
+            UBG.data_ptr(), shared, lam_g0.data_ptr() if lam_g0 is not None else None,
+            X.data_ptr(), LAM.data_ptr(), F.data_ptr(), STATUS.data_ptr(),
+            ITERS.data_ptr(), C.c_void_p(stream.cuda_stream)))
+
+    def shift_batch_device(self, X, blocks, stream=None):
+        """In-place warm-start shift of spline variables (torch CUDA tensor X
+        [B, n]); blocks = [(offset, len_basis, n_columns, T)]."""
+        import torch
+        offs = np.array([b[0] for b in blocks], dtype=np.int32)
+        lens = np.array([b[1] for b in blocks], dtype=np.int32)
+        ncols = np.array([b[2] for b in blocks], dtype=np.int32)
+        Tm = np.concatenate([np.asarray(b[3], dtype=np.float64).reshape(-1)
+                             for b in blocks])
+        if stream is None:
+            stream = torch.cuda.current_stream(X.device)
+        self._check(self.lib.omg_shift_batch(
+            self._handle, X.shape[0], X.data_ptr(), len(blocks), offs.ctypes.data,
+            lens.ctypes.data, ncols.ctypes.data, Tm.ctypes.data,
+            C.c_void_p(stream.cuda_stream)))
+
+    # ------------------------------------------------------------------
+    # the reference's single-instance call contract
+    # ------------------------------------------------------------------
+    def __call__(self, x0=None, p=None, lbg=None, ubg=None, lam_g0=None, **kwargs):
+        x0 = np.asarray(x0, dtype=np.float64).reshape(1, self.n)
+        p = np.asarray(p, dtype=np.float64).reshape(1, self.n_par)
+        lb = None if lbg is None else np.asarray(lbg, dtype=np.float64).reshape(-1)
+        ub = None if ubg is None else np.asarray(ubg, dtype=np.float64).reshape(-1)
+        lam0 = None if lam_g0 is None else \
+            np.asarray(lam_g0, dtype=np.float64).reshape(1, self.m)
+        res = self.solve_batch(x0, p, lb, ub, lam0)
+        self._stats = {'return_status': STATUS_STRINGS[int(res['status'][0])],
+                       'iter_count': int(res['iters'][0]),
+                       'success': int(res['status'][0]) == 0}
+        return {'x': res['x'][0], 'lam_g': res['lam_g'][0], 'f': float(res['f'][0])}
+
+    def stats(self):
+        return dict(self._stats)

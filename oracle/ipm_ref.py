@@ -45,7 +45,7 @@ DEFAULTS = dict(
     theta_min_fact=1e-4, delta_w0=1e-4, delta_w_min=1e-20, delta_w_max=1e40,
     kappa_w_plus_first=100.0, kappa_w_plus=8.0, kappa_w_minus=1.0 / 3.0,
     delta_c_val=1e-8, delta_c_exp=0.25, piv_tol=1e-12, inf_bound=1e19,
-    soft_resto_factor=0.9999, max_filter=32, max_ls=40)
+    soft_resto_factor=0.9999, soft_resto=0, max_filter=32, max_ls=40)
 
 EPS = np.finfo(float).eps
 
@@ -293,7 +293,7 @@ def solve(tb, x0, p, lbg=None, ubg=None, options=None, lam_g0=None,
                 break
             alpha *= 0.5
 
-        if not accepted:
+        if not accepted and o['soft_resto']:
             # soft restoration: accept a step that reduces the primal-dual error
             pd0 = _pd_error(r_x, r_s, c, dL, zL, dU, zU, hasL, hasU, mu)
             alpha = a_p
@@ -316,9 +316,9 @@ def solve(tb, x0, p, lbg=None, ubg=None, options=None, lam_g0=None,
                     filt = []
                     break
                 alpha *= 0.5
-            if not accepted:
-                status = 2
-                break
+        if not accepted:
+            status = 2
+            break
 
         # ---- accept ---------------------------------------------------------
         x, s, f, g = xt, st, ft, gt
