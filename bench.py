@@ -1,0 +1,293 @@
+"""bench.py -- MPC solves/sec of the batched Point2point hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W          (N>1 under torchrun)
+  python bench.py --impl reference ...                   (CPU oracle arm)
+
+A "step" is one cold solve of the whole batch (BASELINE config 2: batch 1024
+Holonomic Point2point, 10 knot intervals, 3 circular obstacles) from the linear
+initial guess.  `value` times the kernel with inputs resident in HBM (CUDA
+events on the launching stream); `e2e` times the reference-facing C-ABI call
+omg_solve_batch_host with host buffers (H2D + solve + D2H inside).  Per-GPU batch
+is fixed (weak scaling): the batch shards across ranks with no collective.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 1024
+L2_FLUSH_BYTES = 256 << 20
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=BATCH)
+    ap.add_argument('--jitter', type=float, default=0.0)
+    ap.add_argument('--cpu-sample', type=int, default=0)
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.check_output(
+                    ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                     '--format=csv,noheader,nounits'], timeout=5).decode()
+                self.rows.append([c.strip() for c in out.strip().split(',')])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if r and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                 'sw_power_cap']
+        reasons = [n for k, n in enumerate(names)
+                   if any(len(r) > 3 + k and r[3 + k].lower().startswith('active')
+                          for r in self.rows)]
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(self.rows)}
+
+
+def roofline_bytes_per_solve(tb, K):
+    """SURVEY.md 8(d) staged-KKT model: one write + one read of the packed
+    condensed KKT per interior-point iteration + compulsory I/O."""
+    n, m, n_par = tb.n, tb.m, tb.n_par
+    return K * 2 * 8 * n * (n + 1) / 2 + 8 * (2 * n + n_par + 3 * m)
+
+
+def flops_per_solve(tb, K):
+    n = tb.n
+    nnz2 = float(np.sum(np.diff(tb.jrow_ptr).astype(float) ** 2))
+    return K * (n ** 3 / 3.0 + 4 * n * n + 2 * nnz2)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d['hbm_gbs']), 'measured'
+    return 6650.0, 'fallback'
+
+
+def cpu_baseline(problem, X0, P, sample, threads):
+    """Time the CPU oracle (the host restatement of the reference's
+    CasADi+IPOPT path) on `sample` instances using `threads` processes."""
+    from oracle import cpu_runner
+    return cpu_runner.run(problem.father.tables, X0[:sample], P[:sample], threads)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (oracle; CasADi+IPOPT is not
+    installable in this image) on the host cores, same config and metric."""
+    if rank != 0:
+        return
+    from omg_tools_b200 import scenarios as sc
+    problem = sc.config2(build_solver=False)
+    cores = os.cpu_count() or 1
+    sample = args.cpu_sample or max(cores, 16)
+    X0, P = sc.instance_data(problem, 1, jitter=0.0)
+    X0, P = np.repeat(X0, sample, 0), np.repeat(P, sample, 0)
+    times = []
+    info = None
+    for k in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        info = cpu_baseline(problem, X0, P, sample, cores)
+        dt = time.perf_counter() - t0
+        if k >= args.warmup:
+            times.append(dt)
+    tot = sum(times)
+    value = sample * args.steps / tot
+    line = {
+        'impl': 'reference', 'metric': 'mpc_solves_per_sec', 'value': value,
+        'unit': 'solves/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * tot / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'config2: Holonomic Point2point, 10 knot '
+                   'intervals, 3 circular obstacles, cold solve, identical '
+                   'instances', 'sample_per_step': sample},
+        'cpu_baseline': {'value': value, 'unit': 'solves/s', 'cores': cores,
+                         'kind': info['kind'],
+                         'sample': '%d identical config-2 instances per step' % sample},
+        'e2e': {'value': value, 'unit': 'solves/s', 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0},
+        'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (no CPU fallback)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    from omg_tools_b200 import scenarios as sc
+    os.environ['OMG_B200_DEVICE'] = str(local)
+    problem = sc.config2()
+    slv, tb = problem.problem, problem.father.tables
+    B = args.batch                      # per GPU (weak scaling)
+    if args.jitter > 0:
+        X0h, Ph = sc.instance_data(problem, B, jitter=args.jitter, seed=100 + rank)
+    else:
+        X0h, Ph = sc.instance_data(problem, 1, jitter=0.0)
+        X0h, Ph = np.repeat(X0h, B, 0), np.repeat(Ph, B, 0)
+    X0 = torch.tensor(X0h, device=dev)
+    P = torch.tensor(Ph, device=dev)
+    LB, UB = torch.tensor(tb.lbg, device=dev), torch.tensor(tb.ubg, device=dev)
+    X = torch.empty_like(X0)
+    LAM = torch.empty((B, tb.m), dtype=torch.float64, device=dev)
+    F = torch.empty(B, dtype=torch.float64, device=dev)
+    ST = torch.empty(B, dtype=torch.int32, device=dev)
+    IT = torch.empty(B, dtype=torch.int32, device=dev)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step():
+        slv.solve_batch_device(X0, P, LB, UB, X, LAM, F, ST, IT, stream=stream)
+
+    for _ in range(max(args.warmup, 3)):
+        flush.fill_(1)
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    # ---- device-timed region: EXACTLY args.steps steps -------------------------
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(args.steps)]
+    barrier()
+    for k in range(args.steps):
+        flush.fill_(k & 1)              # evict L2 between timed iterations
+        evs[k][0].record(stream)
+        step()
+        evs[k][1].record(stream)
+    barrier()
+    ms = [a.elapsed_time(b) for a, b in evs]
+    tot_ms = float(sum(ms))
+    kern_ms = tot_ms / args.steps       # one kernel launch per step
+    iters = IT.cpu().numpy()
+    status = ST.cpu().numpy()
+    # ---- e2e: host buffers through the C-ABI call --------------------------------
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    X0p, Pp = pin(X0h), pin(Ph)
+    for _ in range(2):
+        slv.solve_batch(X0p, Pp)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = slv.solve_batch(X0p, Pp)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    h2d = X0p.nbytes + Pp.nbytes + 2 * tb.m * 8
+    d2h = res['x'].nbytes + res['lam_g'].nbytes + res['f'].nbytes + \
+        res['status'].nbytes + res['iters'].nbytes
+    # ---- max over ranks ------------------------------------------------------------
+    agg = torch.tensor([tot_ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(agg, op=dist.ReduceOp.MAX)
+    tot_ms, e2e_s = float(agg[0]), float(agg[1])
+    if rank == 0:
+        K = float(iters.mean())
+        value = world * B * args.steps / (tot_ms * 1e-3)
+        e2e_v = world * B * args.steps / e2e_s
+        peak, how = measured_peaks()
+        bps = roofline_bytes_per_solve(tb, K)
+        achieved = B * bps / (kern_ms * 1e-3) / 1e9
+        info = slv.info()
+        line = {
+            'metric': 'mpc_solves_per_sec', 'value': value, 'unit': 'solves/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': tot_ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic',
+            'config': {'workload': 'config2: batch=%d/GPU Holonomic Point2point, '
+                       '10 knot intervals, 3 circular obstacles, cold solve from '
+                       'the linear initial guess, %s instances' %
+                       (B, 'jittered' if args.jitter > 0 else 'identical'),
+                       'n': tb.n, 'm': tb.m, 'n_par': tb.n_par,
+                       'global_batch': world * B, 'tol': 1e-3,
+                       'mean_ip_iterations': K,
+                       'succeeded_frac': float((status == 0).mean()),
+                       'l2': 'flushed between timed iterations (256 MiB fill)',
+                       'parallelism': 'dp%d (batch sharded, no collective)' % world},
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak,
+                         'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                         'peak_source': how,
+                         'model': 'staged-KKT bytes/solve = K*2*8*n(n+1)/2 + '
+                                  '8(2n+n_par+3m) (SURVEY 8d); K=mean iterations',
+                         'bytes_per_solve': bps,
+                         'fp64_gflops_achieved': B * flops_per_solve(tb, K) /
+                         (kern_ms * 1e-3) / 1e9,
+                         'kernel_ms': kern_ms, 'smem_bytes': info['smem_bytes'],
+                         'ctas_per_sm': info['ctas_per_sm']},
+            'e2e': {'value': e2e_v, 'unit': 'solves/s',
+                    'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
+            'gpu_launches': args.steps,
+            'clocks': sampler.summary()}
+        cores = os.cpu_count() or 1
+        if world == 1:
+            sample = args.cpu_sample or max(cores, 16)
+            t0 = time.perf_counter()
+            cinfo = cpu_baseline(problem, X0h, Ph, sample, cores)
+            dt = time.perf_counter() - t0
+            line['cpu_baseline'] = {
+                'value': sample / dt, 'unit': 'solves/s', 'cores': cores,
+                'kind': cinfo['kind'],
+                'sample': '%d instances of the same workload, %.1f s' % (sample, dt),
+                'max_abs_dx_vs_gpu': cinfo.get('max_dx')}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -935,8 +935,9 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
              h->smem_bytes, (size_t)prop.sharedMemPerBlockOptin, T.n, T.n_eq_max);
     set_err(buf); ok = false;
   }
+  // the attribute is per function (shared by all handles): opt in to the device maximum
   if (ok && cudaFuncSetAttribute(omg_ipm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)h->smem_bytes) != cudaSuccess) { set_err("cudaFuncSetAttribute failed"); ok = false; }
+                                 (int)prop.sharedMemPerBlockOptin) != cudaSuccess) { set_err("cudaFuncSetAttribute failed"); ok = false; }
   if (ok) {
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, omg_ipm_kernel, NT, h->smem_bytes);

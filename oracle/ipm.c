@@ -1,0 +1,426 @@
+/* ORACLE (test infrastructure, not product code): plain-C restatement of the
+ * interior-point method in oracle/ipm_ref.py (IPOPT semantics, Waechter &
+ * Biegler 2006, with the reference's options problem.py:57-60), operating on
+ * the lowered tables (include/omg_b200.h: omg_tables).  It is the CPU baseline
+ * bench.py times next to the GPU (cpu_baseline.kind = "port") and the checker
+ * of the GPU parity tests at sizes where the numpy twin is too slow.
+ * parity unpinned: no CasADi/IPOPT binary exists in this image.
+ *
+ * Build: make -C oracle   ->  oracle/_build/libipm_oracle.so
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu legs may load it.
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <float.h>
+#include <pthread.h>
+#include "../include/omg_b200.h"
+
+#define KAPPA_EPS 10.0
+#define KAPPA_MU 0.2
+#define THETA_MU 1.5
+#define TAU_MIN 0.99
+#define S_MAX 100.0
+#define KAPPA_SIGMA 1e10
+#define GAMMA_THETA 1e-5
+#define GAMMA_PHI 1e-8
+#define ETA_PHI 1e-8
+#define S_THETA 1.1
+#define S_PHI 2.3
+#define DELTA_LS 1.0
+#define GAMMA_ALPHA 0.05
+#define THETA_MAX_FACT 1e4
+#define THETA_MIN_FACT 1e-4
+#define DELTA_W0 1e-4
+#define DELTA_W_MIN 1e-20
+#define DELTA_W_MAX 1e40
+#define KAPPA_W_PLUS_FIRST 100.0
+#define KAPPA_W_PLUS 8.0
+#define KAPPA_W_MINUS (1.0 / 3.0)
+#define DELTA_C_VAL 1e-8
+#define DELTA_C_EXP 0.25
+#define PIV_TOL 1e-12
+#define INF_BOUND 1e19
+#define MAX_LS 40
+#define MAXF 32
+
+static double eval_slot(const omg_termlist* L, int s, const double* V, const double* xe) {
+  double acc = 0.0;
+  for (int t = L->ptr[s]; t < L->ptr[s + 1]; ++t) {
+    double v = L->coef[t] * V[L->cidx[t]];
+    for (int k = 0; k < L->width; ++k) v *= xe[L->xi[t * L->width + k]];
+    acc += v;
+  }
+  return acc;
+}
+
+static void eval_tape(const omg_tables* T, const double* p, double* V) {
+  V[0] = 1.0;
+  for (int i = 0; i < T->n_par; ++i) V[1 + i] = p[i];
+  for (int e = 0; e < T->n_tape; ++e) {
+    double acc = 0.0;
+    for (int t = T->tape_ptr[e]; t < T->tape_ptr[e + 1]; ++t) {
+      const int32_t* f = T->tape_fac + 4 * t;
+      acc += T->tape_coef[t] * V[f[0]] * V[f[1]] * V[f[2]] * V[f[3]];
+    }
+    switch (T->tape_func[e]) {
+      case 1: acc = 1.0 / acc; break;
+      case 2: acc = (acc >= 0.0) ? 1.0 : 0.0; break;
+      case 3: acc = (acc > 0.0) ? 1.0 : 0.0; break;
+      case 4: acc = sin(acc); break;
+      case 5: acc = cos(acc); break;
+      case 6: acc = sqrt(acc); break;
+      default: break;
+    }
+    V[1 + T->n_par + e] = acc;
+  }
+}
+
+static int cmp_le(double lhs, double rhs, double base) {
+  return lhs - rhs <= 10.0 * DBL_EPSILON * fabs(base);
+}
+
+/* K = L S L^T (S = diag(I_n, -I)), row-major full storage, lower part used. */
+static int gen_cholesky(double* K, int N, int n, int* eq_fail) {
+  *eq_fail = 0;
+  /* original diagonal for the relative pivot test */
+  double* d0 = (double*)malloc(sizeof(double) * N);
+  for (int j = 0; j < N; ++j) d0[j] = fabs(K[j * N + j]);
+  for (int j = 0; j < N; ++j) {
+    const double sgn = (j < n) ? 1.0 : -1.0;
+    const double piv = sgn * K[j * N + j];
+    const double ref = (j < n) ? d0[j] : piv;   /* eq. part: relative to itself */
+    if (!(piv > PIV_TOL * fmax(ref, 1e-300)) || !isfinite(piv)) {
+      *eq_fail = (j >= n);
+      free(d0);
+      return 0;
+    }
+    const double ljj = sqrt(piv);
+    K[j * N + j] = ljj;
+    for (int i = j + 1; i < N; ++i) K[i * N + j] /= (sgn * ljj);
+    for (int i = j + 1; i < N; ++i) {
+      const double lij = K[i * N + j];
+      if (lij == 0.0) continue;
+      for (int k = j + 1; k <= i; ++k) K[i * N + k] -= sgn * lij * K[k * N + j];
+    }
+  }
+  free(d0);
+  return 1;
+}
+
+static void gen_solve(const double* L, int N, int n, double* w) {
+  for (int j = 0; j < N; ++j) {
+    w[j] /= L[j * N + j];
+    for (int i = j + 1; i < N; ++i) w[i] -= L[i * N + j] * w[j];
+  }
+  for (int j = n; j < N; ++j) w[j] = -w[j];
+  for (int j = N - 1; j >= 0; --j) {
+    w[j] /= L[j * N + j];
+    for (int i = 0; i < j; ++i) w[i] -= L[j * N + i] * w[j];
+  }
+}
+
+typedef struct {
+  double *V, *xe, *xt, *g, *s, *y, *zL, *zU, *dsc, *sL, *sU, *beq, *sig, *wv, *ds, *dy,
+         *dzL, *dzU, *gt, *st, *jval, *gf, *K, *rhs, *rx;
+  int *rt, *eqidx, *eqrow;
+} Work;
+
+static void* xalloc(size_t n) { return calloc(n ? n : 1, 1); }
+
+static void work_alloc(Work* w, const omg_tables* T, int Nmax) {
+  const int n = T->n, m = T->m;
+  w->V = xalloc(sizeof(double) * T->n_v);
+  w->xe = xalloc(sizeof(double) * (n + 1)); w->xt = xalloc(sizeof(double) * (n + 1));
+  double** mv[] = {&w->g, &w->s, &w->y, &w->zL, &w->zU, &w->dsc, &w->sL, &w->sU, &w->beq,
+                   &w->sig, &w->wv, &w->ds, &w->dy, &w->dzL, &w->dzU, &w->gt, &w->st};
+  for (unsigned k = 0; k < sizeof(mv) / sizeof(mv[0]); ++k) *mv[k] = xalloc(sizeof(double) * m);
+  w->jval = xalloc(sizeof(double) * T->nnz_j);
+  w->gf = xalloc(sizeof(double) * n); w->rx = xalloc(sizeof(double) * n);
+  w->K = xalloc(sizeof(double) * Nmax * Nmax); w->rhs = xalloc(sizeof(double) * Nmax);
+  w->rt = xalloc(sizeof(int) * m); w->eqidx = xalloc(sizeof(int) * m);
+  w->eqrow = xalloc(sizeof(int) * (m + 1));
+}
+
+static void work_free(Work* w) {
+  void* all[] = {w->V, w->xe, w->xt, w->g, w->s, w->y, w->zL, w->zU, w->dsc, w->sL, w->sU, w->beq,
+                 w->sig, w->wv, w->ds, w->dy, w->dzL, w->dzU, w->gt, w->st, w->jval, w->gf, w->rx,
+                 w->K, w->rhs, w->rt, w->eqidx, w->eqrow};
+  for (unsigned k = 0; k < sizeof(all) / sizeof(all[0]); ++k) free(all[k]);
+}
+
+static void solve_one(const omg_tables* T, const omg_options* O, Work* w, const double* x0,
+                      const double* par, const double* lbg, const double* ubg, const double* lam0,
+                      double* xout, double* lamout, double* fout, int* status_out, int* iters_out) {
+  const int n = T->n, m = T->m;
+  double* V = w->V; double* xe = w->xe; double* xt = w->xt;
+  double *g = w->g, *s = w->s, *y = w->y, *zL = w->zL, *zU = w->zU, *dsc = w->dsc, *sL = w->sL,
+         *sU = w->sU, *beq = w->beq, *sig = w->sig, *wv = w->wv, *ds = w->ds, *dy = w->dy,
+         *dzL = w->dzL, *dzU = w->dzU, *gt = w->gt, *st = w->st, *jval = w->jval, *gf = w->gf;
+  int *rt = w->rt, *eqidx = w->eqidx, *eqrow = w->eqrow;
+  eval_tape(T, par, V);
+  for (int i = 0; i < n; ++i) xe[i] = x0[i];
+  xe[n] = 1.0; xt[n] = 1.0;
+  /* scaling */
+  const double smg = O->scaling_max_gradient;
+  double fmaxv = 0.0;
+  for (int j = 0; j < n; ++j) fmaxv = fmax(fmaxv, fabs(eval_slot(&T->DF, j, V, xe)));
+  const double fsc = (fmaxv > smg) ? fmax(smg / fmaxv, 1e-8) : 1.0;
+  int n_eq = 0, n_bounds = 0;
+  for (int i = 0; i < m; ++i) {
+    double gm = 0.0;
+    for (int sl = T->jrow_ptr[i]; sl < T->jrow_ptr[i + 1]; ++sl)
+      gm = fmax(gm, fabs(eval_slot(&T->J, sl, V, xe)));
+    const double d = (gm > smg) ? fmax(smg / gm, 1e-8) : 1.0;
+    dsc[i] = d;
+    const double lb = lbg[i], ub = ubg[i];
+    const int eq = (lb == ub);
+    const int hL = (lb > -INF_BOUND) && !eq, hU = (ub < INF_BOUND) && !eq;
+    rt[i] = (hL ? 1 : 0) | (hU ? 2 : 0) | (eq ? 4 : 0);
+    if (eq) { eqrow[n_eq] = i; eqidx[i] = n_eq++; } else eqidx[i] = -1;
+    n_bounds += hL + hU;
+    double l = lb * d, u = ub * d;
+    beq[i] = l;
+    if (hL) l -= O->bound_relax_factor * fmax(1.0, fabs(l));
+    if (hU) u += O->bound_relax_factor * fmax(1.0, fabs(u));
+    sL[i] = l; sU[i] = u;
+    const double gi = d * eval_slot(&T->G, i, V, xe);
+    g[i] = gi;
+    double si = gi;
+    double pl = O->bound_push * fmax(1.0, fabs(l)), pu = O->bound_push * fmax(1.0, fabs(u));
+    if (hL && hU) { pl = fmin(pl, O->bound_frac * (u - l)); pu = fmin(pu, O->bound_frac * (u - l)); }
+    if (hL) si = fmax(si, l + pl);
+    if (hU) si = fmin(si, u - pu);
+    s[i] = si;
+    const double yi = lam0 ? lam0[i] * fsc / d : 0.0;
+    y[i] = yi;
+    zL[i] = hL ? fmax(O->mult_bound_push, -yi) : 0.0;
+    zU[i] = hU ? fmax(O->mult_bound_push, yi) : 0.0;
+  }
+  const int N = n + n_eq;
+  double mu = O->mu_init, tau = fmax(TAU_MIN, 1.0 - mu);
+  double theta_max = -1.0, theta_min = -1.0, delta_w_last = 0.0;
+  double filt[2 * MAXF]; int nfilt = 0;
+  double f = fsc * eval_slot(&T->F, 0, V, xe);
+  int status = OMG_MAX_ITER_EXCEEDED, iter = 0;
+
+  for (iter = 0;; ++iter) {
+    double cinf = 0, maxprod = 0, minprod = 1e300, viol = 0, rsinf = 0, rsinf_un = 0, ysum = 0,
+           zsum = 0, theta = 0, logsum = 0, rxinf = 0;
+    for (int i = 0; i < m; ++i) {
+      const int r = rt[i]; const double d = dsc[i];
+      for (int sl = T->jrow_ptr[i]; sl < T->jrow_ptr[i + 1]; ++sl) jval[sl] = d * eval_slot(&T->J, sl, V, xe);
+      const double gi = g[i], si = s[i], yi = y[i];
+      const double ci = (r & 4) ? gi - beq[i] : gi - si;
+      cinf = fmax(cinf, fabs(ci)); theta += fabs(ci);
+      if (r & 1) { const double dl = si - sL[i], pz = dl * zL[i];
+        maxprod = fmax(maxprod, pz); minprod = fmin(minprod, pz); logsum += log(dl); zsum += zL[i]; }
+      if (r & 2) { const double du = sU[i] - si, pz = du * zU[i];
+        maxprod = fmax(maxprod, pz); minprod = fmin(minprod, pz); logsum += log(du); zsum += zU[i]; }
+      const double gun = gi / d;
+      if (r & 6) viol = fmax(viol, gun - ubg[i]);
+      if (r & 5) viol = fmax(viol, lbg[i] - gun);
+      if (!(r & 4)) { const double rs = fabs(-yi - zL[i] + zU[i]); rsinf = fmax(rsinf, rs); rsinf_un = fmax(rsinf_un, rs * d); }
+      ysum += fabs(yi);
+    }
+    for (int j = 0; j < n; ++j) gf[j] = fsc * eval_slot(&T->DF, j, V, xe);
+    memcpy(w->rx, gf, sizeof(double) * n);
+    for (int sl = 0; sl < T->nnz_j; ++sl) w->rx[T->jcol[sl]] += jval[sl] * y[T->jrow[sl]];
+    for (int j = 0; j < n; ++j) rxinf = fmax(rxinf, fabs(w->rx[j]));
+    const double dinf = fmax(rxinf, rsinf), dinf_un = fmax(rxinf, rsinf_un) / fsc;
+    const double s_d = fmax(S_MAX, (ysum + zsum) / fmax(1.0, (double)(m + n_bounds))) / S_MAX;
+    const double s_c = fmax(S_MAX, zsum / fmax(1.0, (double)n_bounds)) / S_MAX;
+    const double cmpl0 = n_bounds ? fmax(fabs(maxprod), fabs(minprod)) : 0.0;
+    const double E0 = fmax(fmax(dinf / s_d, cinf), cmpl0 / s_c);
+    if (!isfinite(E0)) { status = OMG_INVALID_NUMBER_DETECTED; break; }
+    if (E0 <= O->tol && dinf_un <= O->dual_inf_tol && viol <= O->constr_viol_tol &&
+        cmpl0 / fsc <= O->compl_inf_tol) { status = OMG_SOLVE_SUCCEEDED; break; }
+    if (iter >= O->max_iter) { status = OMG_MAX_ITER_EXCEEDED; break; }
+    const double mu_min = fmin(O->tol, O->compl_inf_tol * fsc) / (KAPPA_EPS + 1.0);
+    for (;;) {
+      const double cm = n_bounds ? fmax(fabs(maxprod - mu), fabs(minprod - mu)) : 0.0;
+      const double Emu = fmax(fmax(dinf / s_d, cinf), cm / s_c);
+      if (Emu <= KAPPA_EPS * mu && mu > mu_min) {
+        mu = fmax(mu_min, fmin(KAPPA_MU * mu, pow(mu, THETA_MU)));
+        tau = fmax(TAU_MIN, 1.0 - mu); nfilt = 0;
+      } else break;
+    }
+    if (theta_max < 0.0) { theta_max = THETA_MAX_FACT * fmax(1.0, theta); theta_min = THETA_MIN_FACT * fmax(1.0, theta); }
+    const double phi = f - mu * logsum;
+    for (int i = 0; i < m; ++i) {
+      const int r = rt[i]; double sg = 0, ph = 0, rd = 0;
+      if (!(r & 4)) { const double si = s[i]; rd = g[i] - si;
+        if (r & 1) { const double dl = si - sL[i]; sg += zL[i] / dl; ph -= mu / dl; }
+        if (r & 2) { const double du = sU[i] - si; sg += zU[i] / du; ph += mu / du; } }
+      sig[i] = sg; wv[i] = (r & 4) ? y[i] : (sg * rd + ph);
+    }
+    /* ---- assemble + factorise -------------------------------------------- */
+    double delta_w = 0.0, delta_c = 0.0; int first_try = 1, ok = 0;
+    double* K = w->K; double* rhs = w->rhs;
+    for (;;) {
+      memset(K, 0, sizeof(double) * N * N);
+      for (int q = 0; q < T->nnz_h; ++q) {
+        double acc = 0.0;
+        for (int e = T->hp_ptr[q]; e < T->hp_ptr[q + 1]; ++e) acc += sig[T->hp_row[e]] * jval[T->hp_s1[e]] * jval[T->hp_s2[e]];
+        if (T->hrow[q] == T->hcol[q]) acc += delta_w;
+        K[T->hrow[q] * N + T->hcol[q]] = acc;
+      }
+      for (int q = 0; q < T->nnz_w; ++q) {
+        double acc = 0.0; const omg_termlist* L = &T->W;
+        for (int t = L->ptr[q]; t < L->ptr[q + 1]; ++t) {
+          double v = L->coef[t] * V[L->cidx[t]];
+          for (int k = 0; k < L->width; ++k) v *= xe[L->xi[t * L->width + k]];
+          const int lr = L->lrow[t];
+          v *= (lr < m) ? (y[lr] * dsc[lr]) : fsc;
+          acc += v;
+        }
+        const int h = T->w2h[q];
+        K[T->hrow[h] * N + T->hcol[h]] += acc;
+      }
+      for (int k = 0; k < n_eq; ++k) {
+        const int i = eqrow[k];
+        for (int sl = T->jrow_ptr[i]; sl < T->jrow_ptr[i + 1]; ++sl) K[(n + k) * N + T->jcol[sl]] = jval[sl];
+        K[(n + k) * N + n + k] = -delta_c;
+        rhs[n + k] = -(g[i] - beq[i]);
+      }
+      for (int j = 0; j < n; ++j) rhs[j] = -gf[j];
+      for (int sl = 0; sl < T->nnz_j; ++sl) rhs[T->jcol[sl]] -= jval[sl] * wv[T->jrow[sl]];
+      int eq_fail = 0;
+      ok = gen_cholesky(K, N, n, &eq_fail);
+      if (ok) break;
+      if (eq_fail) delta_c = DELTA_C_VAL * pow(mu, DELTA_C_EXP);
+      if (first_try) { delta_w = (delta_w_last == 0.0) ? DELTA_W0 : fmax(DELTA_W_MIN, KAPPA_W_MINUS * delta_w_last); first_try = 0; }
+      else delta_w *= (delta_w_last == 0.0) ? KAPPA_W_PLUS_FIRST : KAPPA_W_PLUS;
+      if (delta_w > DELTA_W_MAX) break;
+    }
+    if (!ok) { status = OMG_ERROR_IN_STEP_COMPUTATION; break; }
+    if (delta_w > 0.0) delta_w_last = delta_w;
+    gen_solve(K, N, n, rhs);
+    const double* dx = rhs;
+    double a_p = 1.0, a_d = 1.0, gphi = 0.0;
+    for (int i = 0; i < m; ++i) {
+      const int r = rt[i]; double jd = 0.0;
+      for (int sl = T->jrow_ptr[i]; sl < T->jrow_ptr[i + 1]; ++sl) jd += jval[sl] * dx[T->jcol[sl]];
+      if (r & 4) { ds[i] = 0; dy[i] = dx[n + eqidx[i]]; dzL[i] = 0; dzU[i] = 0; }
+      else {
+        const double si = s[i], dsi = jd + (g[i] - si); double ph = 0, a = 0, b = 0;
+        if (r & 1) { const double dl = si - sL[i]; ph -= mu / dl; a = mu / dl - zL[i] - (zL[i] / dl) * dsi;
+          if (dsi < 0.0) a_p = fmin(a_p, -tau * dl / dsi);
+          if (a < 0.0) a_d = fmin(a_d, -tau * zL[i] / a); }
+        if (r & 2) { const double du = sU[i] - si; ph += mu / du; b = mu / du - zU[i] + (zU[i] / du) * dsi;
+          if (dsi > 0.0) a_p = fmin(a_p, tau * du / dsi);
+          if (b < 0.0) a_d = fmin(a_d, -tau * zU[i] / b); }
+        ds[i] = dsi; dzL[i] = a; dzU[i] = b; dy[i] = sig[i] * dsi + ph - y[i];
+        gphi += ph * dsi;
+      }
+    }
+    for (int j = 0; j < n; ++j) gphi += gf[j] * dx[j];
+    double a_min;
+    if (gphi < 0.0) { a_min = fmin(GAMMA_THETA, GAMMA_PHI * theta / (-gphi));
+      if (theta <= theta_min) a_min = fmin(a_min, DELTA_LS * pow(theta, S_THETA) / pow(-gphi, S_PHI)); }
+    else a_min = GAMMA_THETA;
+    a_min *= GAMMA_ALPHA;
+    double alpha = a_p, ft = 0.0; int accepted = 0, ftype = 0, n_ls = 0;
+    while (alpha >= a_min && n_ls < MAX_LS) {
+      ++n_ls;
+      for (int j = 0; j < n; ++j) xt[j] = xe[j] + alpha * dx[j];
+      double tht = 0.0, lg = 0.0;
+      for (int i = 0; i < m; ++i) {
+        const int r = rt[i]; const double gi = dsc[i] * eval_slot(&T->G, i, V, xt);
+        gt[i] = gi;
+        if (r & 4) tht += fabs(gi - beq[i]);
+        else { const double si = s[i] + alpha * ds[i]; st[i] = si; tht += fabs(gi - si);
+          if (r & 1) lg += log(si - sL[i]);
+          if (r & 2) lg += log(sU[i] - si); }
+      }
+      ft = fsc * eval_slot(&T->F, 0, V, xt);
+      const double pht = ft - mu * lg;
+      int okk = isfinite(pht) && isfinite(tht) && tht <= theta_max;
+      if (okk) for (int q = 0; q < nfilt; ++q) if (!(tht < filt[2 * q] || pht < filt[2 * q + 1])) { okk = 0; break; }
+      ftype = 0;
+      if (okk) {
+        const int switching = (theta <= theta_min && gphi < 0.0 && alpha * pow(-gphi, S_PHI) > DELTA_LS * pow(theta, S_THETA));
+        if (switching) { okk = cmp_le(pht - phi, ETA_PHI * alpha * gphi, phi); ftype = okk; }
+        else okk = cmp_le(tht, (1.0 - GAMMA_THETA) * theta, theta) || cmp_le(pht - phi, -GAMMA_PHI * theta, phi);
+      }
+      if (okk) { accepted = 1; break; }
+      alpha *= 0.5;
+    }
+    if (!accepted) { status = OMG_RESTORATION_FAILED; break; }
+    if (!ftype) {
+      const double th = (1.0 - GAMMA_THETA) * theta, ph = phi - GAMMA_PHI * theta; int nf = 0;
+      for (int q = 0; q < nfilt; ++q) if (!(filt[2 * q] >= th && filt[2 * q + 1] >= ph)) { filt[2 * nf] = filt[2 * q]; filt[2 * nf + 1] = filt[2 * q + 1]; ++nf; }
+      if (nf >= MAXF) { memmove(filt, filt + 2, sizeof(double) * 2 * (nf - 1)); --nf; }
+      filt[2 * nf] = th; filt[2 * nf + 1] = ph; nfilt = nf + 1;
+    }
+    f = ft;
+    for (int j = 0; j < n; ++j) xe[j] = xt[j];
+    for (int i = 0; i < m; ++i) {
+      const int r = rt[i]; g[i] = gt[i]; y[i] += alpha * dy[i];
+      if (!(r & 4)) { const double si = st[i]; s[i] = si;
+        if (r & 1) { const double dl = si - sL[i]; double z = zL[i] + a_d * dzL[i]; z = fmin(fmax(z, mu / (KAPPA_SIGMA * dl)), KAPPA_SIGMA * mu / dl); zL[i] = z; }
+        if (r & 2) { const double du = sU[i] - si; double z = zU[i] + a_d * dzU[i]; z = fmin(fmax(z, mu / (KAPPA_SIGMA * du)), KAPPA_SIGMA * mu / du); zU[i] = z; } }
+    }
+  }
+  for (int i = 0; i < n; ++i) xout[i] = xe[i];
+  for (int i = 0; i < m; ++i) lamout[i] = y[i] * dsc[i] / fsc;
+  *fout = f / fsc; *status_out = status; *iters_out = iter;
+}
+
+typedef struct {
+  const omg_tables* T; const omg_options* O; int B, shared, Nw;
+  const double *x0, *p, *lbg, *ubg, *lam0; double *x, *lam, *f; int *status, *iters;
+  int* next;
+} Job;
+
+static void* worker(void* arg) {
+  Job* J = (Job*)arg;
+  const omg_tables* T = J->T;
+  Work w;
+  work_alloc(&w, T, J->Nw);
+  for (;;) {
+    const int b = __atomic_fetch_add(J->next, 1, __ATOMIC_RELAXED);
+    if (b >= J->B) break;
+    const double* lb = J->lbg + (J->shared ? 0 : (size_t)b * T->m);
+    const double* ub = J->ubg + (J->shared ? 0 : (size_t)b * T->m);
+    int ne = 0;
+    for (int i = 0; i < T->m; ++i) if (lb[i] == ub[i]) ++ne;
+    if (T->n + ne > J->Nw) { J->status[b] = OMG_ERROR_IN_STEP_COMPUTATION; J->iters[b] = 0; continue; }
+    solve_one(T, J->O, &w, J->x0 + (size_t)b * T->n, J->p + (size_t)b * T->n_par, lb, ub,
+              J->lam0 ? J->lam0 + (size_t)b * T->m : 0, J->x + (size_t)b * T->n,
+              J->lam + (size_t)b * T->m, J->f + b, J->status + b, J->iters + b);
+  }
+  work_free(&w);
+  return 0;
+}
+
+/* Solve B instances on `threads` host threads (one instance per thread at a time). */
+int oracle_solve_batch(const omg_tables* T, const omg_options* O, int B, const double* x0,
+                       const double* p, const double* lbg, const double* ubg, int shared,
+                       const double* lam0, double* x, double* lam, double* f, int* status,
+                       int* iters, int threads) {
+  int neq = 0;
+  for (int i = 0; i < T->m; ++i) if (T->lbg[i] == T->ubg[i]) ++neq;
+  int next = 0;
+  Job J = {T, O, B, shared, shared ? T->n + neq + 8 : T->n + T->m, x0, p, lbg, ubg, lam0,
+           x, lam, f, status, iters, &next};
+  if (shared) {   /* size the border from the bounds actually passed */
+    int ne = 0;
+    for (int i = 0; i < T->m; ++i) if (lbg[i] == ubg[i]) ++ne;
+    J.Nw = T->n + ne + 8;
+  }
+  if (threads < 1) threads = 1;
+  if (threads > B) threads = B;
+  if (threads == 1) { worker(&J); return 0; }
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * threads);
+  for (int t = 0; t < threads; ++t) pthread_create(&th[t], 0, worker, &J);
+  for (int t = 0; t < threads; ++t) pthread_join(th[t], 0);
+  free(th);
+  return 0;
+}
+
+void oracle_default_options(omg_options* o) {
+  o->tol = 1e-3; o->constr_viol_tol = 1e-4; o->dual_inf_tol = 1.0; o->compl_inf_tol = 1e-4;
+  o->mu_init = 0.1; o->bound_push = 1e-3; o->bound_frac = 1e-3; o->mult_bound_push = 1e-3;
+  o->bound_relax_factor = 1e-8; o->scaling_max_gradient = 100.0; o->max_iter = 3000; o->trace = 0;
+}

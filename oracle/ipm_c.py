@@ -1,0 +1,61 @@
+"""ORACLE: ctypes wrapper of oracle/_build/libipm_oracle.so (C restatement of
+oracle/ipm_ref.py).  Test infrastructure / CPU baseline only."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(_HERE, '_build', 'libipm_oracle.so')
+_lib = None
+
+
+def available():
+    return os.path.exists(LIB)
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(LIB)
+        vp = C.c_void_p
+        _lib.oracle_solve_batch.argtypes = [vp, vp, C.c_int] + [vp] * 4 + [C.c_int] + \
+            [vp] * 6 + [C.c_int]
+    return _lib
+
+
+def solve_batch(tb, X0, P, threads=0, options=None, lbg=None, ubg=None, lam_g0=None):
+    """Returns (X, status, iters); extra results via return_all=True variant."""
+    out = solve_batch_full(tb, X0, P, threads, options, lbg, ubg, lam_g0)
+    return out['x'], out['status'], out['iters']
+
+
+def solve_batch_full(tb, X0, P, threads=0, options=None, lbg=None, ubg=None,
+                     lam_g0=None):
+    # the struct definitions are data-format declarations shared with the product
+    from omg_tools_b200.solver.b200 import pack_tables, _Options
+    lib = _load()
+    T, keep = pack_tables(tb)
+    opt = _Options()
+    lib.oracle_default_options(C.byref(opt))
+    for k, v in (options or {}).items():
+        setattr(opt, k, v)
+    X0 = np.ascontiguousarray(X0, dtype=np.float64).reshape(-1, tb.n)
+    B = X0.shape[0]
+    P = np.ascontiguousarray(P, dtype=np.float64).reshape(B, tb.n_par)
+    lb = np.ascontiguousarray(tb.lbg if lbg is None else lbg, dtype=np.float64)
+    ub = np.ascontiguousarray(tb.ubg if ubg is None else ubg, dtype=np.float64)
+    shared = 1 if lb.ndim == 1 else 0
+    lam0 = None if lam_g0 is None else np.ascontiguousarray(lam_g0, dtype=np.float64)
+    X = np.empty((B, tb.n))
+    LAM = np.empty((B, tb.m))
+    F = np.empty(B)
+    st = np.empty(B, dtype=np.int32)
+    it = np.empty(B, dtype=np.int32)
+    lib.oracle_solve_batch(C.byref(T), C.byref(opt), B, X0.ctypes.data, P.ctypes.data,
+                           lb.ctypes.data, ub.ctypes.data, shared,
+                           lam0.ctypes.data if lam0 is not None else None,
+                           X.ctypes.data, LAM.ctypes.data, F.ctypes.data,
+                           st.ctypes.data, it.ctypes.data, int(threads))
+    del keep
+    return {'x': X, 'lam_g': LAM, 'f': F, 'status': st, 'iters': it}

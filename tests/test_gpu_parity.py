@@ -1,0 +1,205 @@
+"""GPU parity tests (call through the C-ABI): CUDA solver vs the CPU oracle on
+seeded instances and committed golden vectors; size-independent properties at
+BASELINE batch sizes."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from omg_tools_b200 import scenarios as sc
+from oracle import ipm_ref
+from oracle.nlp_eval import TableEval
+
+G = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'p2p_golden.npz'))
+TIGHT = {'tol': 1e-8, 'compl_inf_tol': 1e-8, 'constr_viol_tol': 1e-8}
+# GPU and oracle run the same algorithm in fp64 with different summation order
+# and a different factorisation blocking; rounding differences are amplified by
+# the interior-point iteration on ill-conditioned instances (non-unique
+# separating hyperplanes).  X_TOL is for well-conditioned instances; the
+# north-star criterion is 1e-4 on the spline coefficients.
+X_TOL = 1e-7
+NORTH_STAR_TOL = 1e-4
+
+
+@pytest.fixture(scope='module')
+def solvers():
+    import __graft_entry__ as ge
+    ge.build()
+    out = {}
+    for name in ('config1', 'config2', 'config5'):
+        out[name] = getattr(sc, name)()
+    return out
+
+
+@pytest.mark.parametrize('name', ['config1', 'config2', 'config5'])
+def test_matches_golden_default_tolerance(solvers, name):
+    pr = solvers[name]
+    res = pr.problem.solve_batch(G[name + '_X0'], G[name + '_P'])
+    assert np.array_equal(res['status'], G[name + '_loose_status'])
+    assert np.array_equal(res['iters'], G[name + '_loose_iters'])
+    err = np.abs(res['x'] - G[name + '_loose_x']).max(axis=1)
+    assert err.max() < NORTH_STAR_TOL
+    assert np.median(err) < X_TOL
+    assert np.abs(res['f'] - G[name + '_loose_f']).max() < 1e-6
+    assert np.abs(res['lam_g'] - G[name + '_loose_lam']).max() < 1e-3
+
+
+def test_matches_golden_tight_tolerance(solvers):
+    pr = solvers['config2']
+    pr.problem.set_options(TIGHT)
+    try:
+        res = pr.problem.solve_batch(G['config2_X0'], G['config2_P'])
+    finally:
+        pr.problem.set_options({'tol': 1e-3, 'compl_inf_tol': 1e-4,
+                                'constr_viol_tol': 1e-4})
+    assert np.array_equal(res['status'], G['config2_tight_status'])
+    assert np.abs(res['x'] - G['config2_tight_x']).max() < 1e-5
+    # IPOPT-parity criterion of the north star: 1e-4 on the spline coefficients
+    assert np.abs(res['x'][:, :26] - G['config2_tight_x'][:, :26]).max() < 1e-4
+
+
+def test_matches_live_oracle_on_fresh_seed(solvers):
+    pr = solvers['config1']
+    tb = pr.father.tables
+    X0, P = sc.instance_data(pr, 3, jitter=0.3, seed=7)
+    res = pr.problem.solve_batch(X0, P)
+    for b in range(3):
+        ref = ipm_ref.solve(tb, X0[b], P[b])
+        assert res['status'][b] == ref.status and res['iters'][b] == ref.iters
+        assert np.abs(res['x'][b] - ref.x).max() < X_TOL
+
+
+def test_full_batch_properties_config2(solvers):
+    """BASELINE config 2 at full size (batch 1024): identical instances give
+    bit-identical results; jittered instances all satisfy the KKT conditions."""
+    pr = solvers['config2']
+    tb = pr.father.tables
+    ev = TableEval(tb)
+    X0, P = sc.instance_data(pr, 1, jitter=0.0)
+    B = 1024
+    res = pr.problem.solve_batch(np.repeat(X0, B, 0), np.repeat(P, B, 0))
+    assert np.all(res['status'] == 0)
+    assert np.all(res['x'] == res['x'][0]) and np.all(res['iters'] == res['iters'][0])
+    assert np.abs(res['x'][0] - G['config2_loose_x'][0]).max() < 1e-6
+    Xj, Pj = sc.instance_data(pr, 256, jitter=0.2, seed=11)
+    rj = pr.problem.solve_batch(Xj, Pj)
+    ok = rj['status'] == 0
+    assert ok.mean() > 0.95
+    eq = tb.lbg == tb.ubg
+    for b in np.nonzero(ok)[0][:24]:
+        V = ev.tape(Pj[b])
+        g = ev.g(rj['x'][b], V)
+        assert np.abs(g[eq]).max() < 2e-4 and g[~eq].max() < 2e-4
+        stat = ev.gradf(rj['x'][b], V) + ev.jac_dense(rj['x'][b], V).T @ rj['lam_g'][b]
+        assert np.abs(stat).max() < 1.0 + 1e-9          # dual_inf_tol (unscaled)
+        assert abs(ev.f(rj['x'][b], V) - rj['f'][b]) < 1e-10
+        assert np.abs(rj['lam_g'][b][~eq] * g[~eq]).max() < 1e-3
+
+
+def test_edge_cases(solvers):
+    pr = solvers['config1']
+    tb = pr.father.tables
+    X0, P = G['config1_X0'], G['config1_P']
+    # per-instance bounds == shared bounds
+    LB, UB = np.repeat(tb.lbg[None], 4, 0), np.repeat(tb.ubg[None], 4, 0)
+    a = pr.problem.solve_batch(X0, P)
+    b = pr.problem.solve_batch(X0, P, LB, UB)
+    assert np.array_equal(a['x'], b['x'])
+    # batch of one / ragged batch sizes around the SM count
+    one = pr.problem.solve_batch(X0[:1], P[:1])
+    assert np.array_equal(one['x'][0], a['x'][0])
+    many = pr.problem.solve_batch(np.repeat(X0, 75, 0), np.repeat(P, 75, 0))  # 300
+    assert np.array_equal(many['x'][::75], a['x'])
+    # max_iter exhaustion is reported, not hidden
+    pr.problem.set_options({'max_iter': 5})
+    try:
+        r = pr.problem.solve_batch(X0[:2], P[:2])
+    finally:
+        pr.problem.set_options({'max_iter': 3000})
+    assert np.all(r['status'] == 1) and np.all(r['iters'] == 5)
+    ref = ipm_ref.solve(tb, X0[0], P[0], options={'max_iter': 5})
+    assert np.abs(r['x'][0] - ref.x).max() < 1e-10
+    # NaN parameters -> Invalid_Number_Detected, other instances unaffected
+    Pn = P.copy()
+    Pn[1, 0] = np.nan
+    r = pr.problem.solve_batch(X0, Pn)
+    assert r['status'][1] == 4 and r['status'][0] == 0
+    assert np.array_equal(r['x'][0], a['x'][0])
+    # warm start from the solution converges in far fewer iterations
+    w = pr.problem.solve_batch(a['x'], P, lam_g0=a['lam_g'])
+    assert np.all(w['status'] == 0) and np.all(w['iters'] < a['iters'])
+
+
+def test_problem_solve_dropin(solvers):
+    """Problem.solve() -- the reference's call (problem.py:103-136)."""
+    pr = sc.config1()
+    tb = pr.father.tables
+    x0 = pr.father.get_variables().cat.copy()
+    p = pr.father.set_parameters(0.).cat.copy()
+    pr.solve(0., 0.1)
+    assert pr.problem.stats()['return_status'] == 'Solve_Succeeded'
+    ref = ipm_ref.solve(tb, x0, p)
+    assert np.abs(pr.father.get_variables().cat - ref.x).max() < X_TOL
+    assert np.abs(pr.father.get_dual_variables().cat - ref.lam_g).max() < 1e-6
+    splines = pr.father.get_variables(pr.vehicles[0], 'splines_seg0')
+    assert abs(splines[0](0.)[0] + 1.5) < 1e-6 and abs(splines[1](1.)[0] - 2.) < 1e-3
+
+
+def test_device_pointer_api_and_shift(solvers):
+    import torch
+    pr = solvers['config1']
+    tb, slv = pr.father.tables, pr.problem
+    dev = torch.device('cuda:0')
+    X0 = torch.tensor(G['config1_X0'], device=dev)
+    P = torch.tensor(G['config1_P'], device=dev)
+    LB, UB = torch.tensor(tb.lbg, device=dev), torch.tensor(tb.ubg, device=dev)
+    B = X0.shape[0]
+    X = torch.empty_like(X0)
+    LAM = torch.empty((B, tb.m), dtype=torch.float64, device=dev)
+    F = torch.empty(B, dtype=torch.float64, device=dev)
+    ST = torch.empty(B, dtype=torch.int32, device=dev)
+    IT = torch.empty(B, dtype=torch.int32, device=dev)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        slv.solve_batch_device(X0, P, LB, UB, X, LAM, F, ST, IT)
+    side.synchronize()
+    assert np.abs(X.cpu().numpy() - G['config1_loose_x']).max() < X_TOL
+    ms, launches = slv.last_timing()
+    assert ms > 0 and launches == 1
+    # warm-start knot shift on device == T.dot(coeffs) of the reference
+    blocks = [(off, shape[0], shape[1], T) for (_, _, off, shape, T)
+              in pr.father.shifted_entries()]
+    Xs = X.clone()
+    slv.shift_batch_device(Xs, blocks)
+    want = X.cpu().numpy().copy()
+    for off, L, nc, T in blocks:
+        for c in range(nc):
+            seg = slice(off + c * L, off + (c + 1) * L)
+            want[:, seg] = X.cpu().numpy()[:, seg] @ np.asarray(T).T
+    assert np.abs(Xs.cpu().numpy() - want).max() < 1e-13
+
+
+def test_receding_horizon_config1(solvers):
+    """10 MPC steps of the p2p_holonomic scenario through Problem.solve(),
+    each checked against the oracle started from the same warm start."""
+    pr = sc.config1()
+    tb = pr.father.tables
+    pr.initialize(0.)
+    t, dt = 0., 0.1
+    for k in range(12):
+        pr.predict(t, dt, 0.01)
+        pr.init_step(t, dt)
+        x0 = pr.father.get_variables().cat.copy()
+        p = pr.father.set_parameters(t).cat.copy()
+        ref = ipm_ref.solve(tb, x0, p)
+        pr.solve(t, dt)
+        assert pr.problem.stats()['return_status'] == ipm_ref.STATUS[ref.status]
+        assert np.abs(pr.father.get_variables().cat - ref.x).max() < 1e-7
+        pr.store(t, dt, 0.01)
+        pr.simulate(t, dt, 0.01)
+        t += dt
+    # vehicle moved towards the goal and stayed on its trajectory
+    assert pr.vehicles[0].signals['state'][0, -1] > -1.5

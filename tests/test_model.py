@@ -1,0 +1,131 @@
+"""Model layer + lowering: sizes and flat layouts of the BASELINE configs
+(SURVEY.md section 8 table and appendix A), table evaluation against direct
+polynomial evaluation and finite differences, warm-start shift."""
+import numpy as np
+import pytest
+
+from omg_tools_b200 import scenarios as sc
+from omg_tools_b200.basics import poly as pl
+from omg_tools_b200.basics.spline_extra import shiftoverknot_T
+from oracle.nlp_eval import TableEval
+
+
+@pytest.fixture(scope='module')
+def cfg1():
+    return sc.config1(build_solver=False)
+
+
+@pytest.mark.parametrize('name,n,m,n_par', [('config1', 98, 325, 17),
+                                            ('config2', 190, 563, 35),
+                                            ('config5', 184, 862, 58)])
+def test_problem_dimensions(name, n, m, n_par):
+    pr = getattr(sc, name)(build_solver=False)
+    tb = pr.father.tables
+    assert (tb.n, tb.m, tb.n_par) == (n, m, n_par)
+    assert tb.degree == 2
+    assert int((tb.lbg == tb.ubg).sum()) == 10     # 4 initial + 6 terminal rows
+
+
+def test_flat_layout_config1(cfg1):
+    f = cfg1.father
+    names = [k[1] for k in f._var_struct.keys()]
+    assert names == ['splines_seg0', 'eps_00', 'g0', 'g1',
+                     'a_%s_seg0_00' % cfg1.vehicles[0].label,
+                     'b_%s_seg0_00' % cfg1.vehicles[0].label]
+    pnames = [k[1] for k in f._par_struct.keys()]
+    assert pnames == ['state0', 'input0', 'poseT', 'x', 'v', 'a', 'checkpoints',
+                      'rad', 'T', 't']
+    rows = [v[1] for v in f._con_struct.entries.values()]
+    assert rows == [12] * 4 + [11] * 4 + [13, 13, 41] + [13] * 4 + [31] + \
+        [1] * 4 + [13] * 4 + [1] * 6 + [21]
+    # cold start = linear interpolation of the vehicle spline, zeros elsewhere
+    x0 = f.get_variables().cat
+    assert np.allclose(x0[:13], np.linspace(-1.5, 2., 13))
+    assert np.allclose(x0[13:26], np.linspace(-1.5, 2., 13))
+    assert np.all(x0[26:] == 0.)
+    p = f.set_parameters(0.37).cat
+    assert np.allclose(p[:6], [-1.5, -1.5, 0, 0, 2, 2])
+    assert np.allclose(p[-2:], [10., 0.37])
+
+
+def test_tables_match_polynomials_and_derivatives(cfg1):
+    f, tb = cfg1.father, cfg1.father.tables
+    ev = TableEval(tb)
+    rng = np.random.default_rng(3)
+    x = f.get_variables().cat + 0.1 * rng.standard_normal(tb.n)
+    p = f.set_parameters(0.37).cat.copy()
+    V = ev.tape(p)
+    vals = {pl.resolve(s): v for s, v in zip(f._var_ids, x)}
+    vals.update({pl.resolve(s): v for s, v in zip(f._par_ids, p)})
+    rows, _, _ = f.construct_constraints()
+    direct = np.array([r.evaluate(dict(vals)) for r in rows])
+    assert np.abs(ev.g(x, V) - direct).max() < 1e-12
+    obj = f.construct_objective()
+    assert abs(ev.f(x, V) - obj.evaluate(dict(vals))) < 1e-13
+    h = 1e-6
+    J = ev.jac_dense(x, V)
+    lam = rng.standard_normal(tb.m)
+    W = ev.hess_dense(x, V, lam)
+    for j in rng.choice(tb.n, 12, replace=False):
+        e = np.zeros(tb.n)
+        e[j] = h
+        assert np.abs((ev.g(x + e, V) - ev.g(x - e, V)) / (2 * h) - J[:, j]).max() < 1e-5
+        dj = (ev.jac_dense(x + e, V).T @ lam - ev.jac_dense(x - e, V).T @ lam) / (2 * h)
+        assert np.abs(dj - W[:, j]).max() < 1e-5
+    g0 = ev.gradf(x, V)
+    assert abs((ev.f(x + 1e-6 * g0, V) - ev.f(x, V)) / 1e-6 - g0 @ g0) < 1e-6
+
+
+def test_collision_rows_are_the_pointwise_constraint(cfg1):
+    """Property independent of the reference: the 41 vehicle-side rows are the
+    B-spline coefficients of a(t).(x(t),y(t)) - b(t) + r + sd - eps(t)."""
+    from omg_tools_b200.basics.spline import BSpline, BSplineBasis
+    f, tb = cfg1.father, cfg1.father.tables
+    ev = TableEval(tb)
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(tb.n)
+    p = f.set_parameters(0.).cat
+    g = ev.g(x, ev.tape(p))
+    off, size, _ = f._con_struct.entries[(None, 'c_10_%s' % cfg1.vehicles[0].label)]
+    assert size == 41
+    veh = cfg1.vehicles[0]
+    b3 = veh.basis
+    b1 = BSplineBasis(np.r_[0., veh.knots[3:-3], 1.], 1)
+    xs, ys, eps = (BSpline(b3, x[k * 13:(k + 1) * 13]) for k in (0, 1, 2))
+    a0, a1, b = (BSpline(b1, x[65 + k * 11:65 + (k + 1) * 11]) for k in (0, 1, 2))
+    con = a0 * xs + a1 * ys + (-b + 0.1 + 0.1 - eps)
+    assert np.abs(con.coeffs - g[off:off + 41]).max() < 1e-11
+    tt = np.linspace(0, 1, 50)
+    point = a0(tt) * xs(tt) + a1(tt) * ys(tt) - b(tt) + 0.2 - eps(tt)
+    assert np.abs(con(tt) - point).max() < 1e-11
+
+
+def test_knot_shift_of_seg0_variables(cfg1):
+    f = cfg1.father
+    blocks = f.shifted_entries()
+    names = [b[1] for b in blocks]
+    assert names[0] == 'splines_seg0' and all('seg0' in n for n in names)
+    assert not any(n.startswith('g') or n.startswith('eps') for n in names)
+    rng = np.random.default_rng(2)
+    before = rng.standard_normal(f.tables.n)
+    f.set_variables(before)
+    cfg1.initialize(0.)
+    cfg1.init_step(1.0, 0.1)          # passes the first knot (knot_time = 1 s)
+    after = f.get_variables().cat
+    T3 = shiftoverknot_T(cfg1.vehicles[0].basis)
+    assert np.allclose(after[:13], T3 @ before[:13])
+    assert np.allclose(after[13:26], T3 @ before[13:26])
+    assert np.array_equal(after[26:65], before[26:65])     # eps, g untouched
+    f.init_variables()
+    cfg1.reinitialize()
+
+
+def test_rotating_obstacle_rows_config5():
+    pr = sc.config5(build_solver=False)
+    f = pr.father
+    rows = {k[1]: v[1] for k, v in f._con_struct.entries.items()}
+    lab = [o.label for o in pr.environment.obstacles]
+    assert rows['c_0_' + lab[0]] == 31 and rows['c_1_' + lab[0]] == 31
+    assert rows['c_0_' + lab[2]] == 71 and rows['c_1_' + lab[2]] == 71
+    # theta enters through cos/sin atoms of the parameter tape
+    assert 4 in f.tables.tape_func and 5 in f.tables.tape_func
