@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define OMG_ABI_VERSION 1
+#define OMG_ABI_VERSION 2
 
 /* CSR list of polynomial terms per output slot:
  *   out[s] = sum_{t in [ptr[s],ptr[s+1])} coef[t] * V[cidx[t]]
@@ -73,8 +73,24 @@ typedef struct omg_tables {
   int32_t nnz_h, n_hp;
   const int32_t* hrow; const int32_t* hcol; const int32_t* hp_ptr; /* [nnz_h+1] */
   const int32_t* hp_s1; const int32_t* hp_s2; const int32_t* hp_row; /* [n_hp] */
-  /* default bounds (used to size the equality border) */
+  /* default bounds: rows with lbg==ubg are the structural equality rows */
   const double* lbg; const double* ubg;
+  /* condensed KKT K = [[H,Jc^T],[Jc,-dc I]] = L S L^T: fill-reducing symmetric
+   * permutation, signs S, lower envelope (row i stored from env_first[i], a
+   * multiple of 16, to i; row kkt_n = right-hand side) and the rows reached by
+   * each 16-column panel (lowering.build_kkt_structure) */
+  int32_t kkt_n, kkt_n_eq, env_size, n_panel_rows, max_panel_rows;
+  const int32_t* kkt_eq_rows;   /* [kkt_n_eq] constraint rows that are equalities */
+  const int32_t* kkt_pos_var;   /* [n] permuted index of variable j */
+  const int32_t* kkt_pos_eq;    /* [kkt_n_eq] permuted index of equality row k */
+  const int32_t* kkt_sign;      /* [kkt_n] +1 / -1 */
+  const int32_t* env_first;     /* [kkt_n+1] */
+  const int32_t* env_ptr;       /* [kkt_n+2] */
+  const int32_t* kkt_hdst;      /* [nnz_h] envelope offset of H position q */
+  const int32_t* kkt_jdst;      /* [nnz_j] envelope offset of J slot (eq rows) or -1 */
+  const int32_t* kkt_diag;      /* [kkt_n] envelope offset of the diagonal */
+  const int32_t* kkt_panel_ptr; /* [n_panels+1] */
+  const int32_t* kkt_panel_rows;/* [n_panel_rows] */
 } omg_tables;
 
 /* Interior-point options; defaults = the reference's IPOPT settings

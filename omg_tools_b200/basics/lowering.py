@@ -229,7 +229,7 @@ def _first_derivs(xmon):
     return res
 
 
-def lower(var_ids, par_ids, rows, objective, lbg, ubg):
+def lower(var_ids, par_ids, rows, objective, lbg, ubg, order_hint=None):
     """Build NLPTables.
 
     var_ids / par_ids : flat lists of (resolved) symbol ids defining x and p
@@ -326,6 +326,7 @@ def lower(var_ids, par_ids, rows, objective, lbg, ubg):
     tb.lbg = np.asarray(lbg, dtype=np.float64).copy()
     tb.ubg = np.asarray(ubg, dtype=np.float64).copy()
     _build_kkt_pattern(tb)
+    build_kkt_structure(tb, order_hint)
     return tb
 
 
@@ -365,3 +366,138 @@ def _build_kkt_pattern(tb):
     index = {k: q for q, k in enumerate(keys)}
     tb.w2h = np.array([index[(int(r), int(c))]
                        for r, c in zip(tb.wrow, tb.wcol)], dtype=np.int32)
+
+
+# ---------------------------------------------------------------------------
+# KKT ordering + envelope (skyline) structure
+# ---------------------------------------------------------------------------
+KKT_NB = 16      # panel width of the blocked factorisation (csrc/omg_b200.cu)
+
+
+def _envelope_first(adj_lower_rows, perm_pos, N):
+    """first[i] (permuted) = smallest permuted column index coupled to row i."""
+    first = np.arange(N)
+    for a, cols in adj_lower_rows.items():
+        pa = perm_pos[a]
+        for b in cols:
+            pb = perm_pos[b]
+            lo, hi = (pb, pa) if pb < pa else (pa, pb)
+            if lo < first[hi]:
+                first[hi] = lo
+    return first
+
+
+def build_kkt_structure(tb, hint=None):
+    """Choose a symmetric permutation of the condensed KKT matrix
+
+        K = [[H, Jc^T], [Jc, -delta_c I]],   H = W + J^T Sigma J  (n x n)
+
+    and lay out its lower envelope.  B-spline locality makes K banded once the
+    unknowns are ordered by "time"; the envelope of the factor L (K = L S L^T,
+    S = diag(+1 variables, -1 equality rows)) equals the envelope of K, so the
+    factorisation needs ~7x fewer flops and ~2.5x less storage than dense
+    packed storage.  Each equality row is placed right after the last variable
+    it couples, so its pivot is a (negative) Schur complement.
+
+    hint: optional array [n] of relative positions in [0,1] (spline
+    coefficient index / length) used as the ordering key; a reverse
+    Cuthill-McKee ordering of the pattern is the alternative, the one with the
+    smaller envelope wins.
+    """
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import reverse_cuthill_mckee
+    n = tb.n
+    eq_rows = np.nonzero(tb.lbg == tb.ubg)[0].astype(np.int32)
+    n_eq = len(eq_rows)
+    N = n + n_eq
+    # adjacency (lower part, natural numbering: variables then equality rows)
+    adj = {}
+    for r, c in zip(tb.hrow, tb.hcol):
+        adj.setdefault(int(r), set()).add(int(c))
+    eq_cols = []
+    for k, i in enumerate(eq_rows):
+        cols = [int(tb.jcol[s]) for s in range(tb.jrow_ptr[i], tb.jrow_ptr[i + 1])]
+        eq_cols.append(cols)
+        adj.setdefault(n + k, set()).update(cols)
+
+    def finish(order_vars_key):
+        """order by key, then insert equality rows after their last variable."""
+        order = list(np.argsort(order_vars_key, kind='stable'))
+        rank = {v: r for r, v in enumerate(order)}
+        ins = {}
+        for k, cols in enumerate(eq_cols):
+            last = max(rank[c] for c in cols)
+            ins.setdefault(last, []).append(n + k)
+        seq = []
+        for r, v in enumerate(order):
+            seq.append(v)
+            seq += ins.get(r, [])
+        pos = np.empty(N, dtype=np.int64)
+        pos[np.array(seq)] = np.arange(N)
+        first = _envelope_first(adj, pos, N)
+        first = (first // KKT_NB) * KKT_NB
+        return pos, first, int(np.sum(np.arange(N) - first + 1))
+
+    cands = []
+    rows = np.concatenate([tb.hrow, tb.hcol]).astype(np.int64)
+    cols = np.concatenate([tb.hcol, tb.hrow]).astype(np.int64)
+    A = coo_matrix((np.ones(len(rows)), (rows, cols)), shape=(n, n)).tocsr()
+    rcm = np.asarray(reverse_cuthill_mckee(A, symmetric_mode=True))
+    key = np.empty(n)
+    key[rcm] = np.arange(n)
+    cands.append(finish(key))
+    cands.append(finish(-key))
+    if hint is not None:
+        cands.append(finish(np.asarray(hint, dtype=float)))
+    cands.append(finish(np.arange(n, dtype=float)))
+    pos, first, size = min(cands, key=lambda c: c[2])
+
+    tb.kkt_n = N
+    tb.kkt_n_eq = n_eq
+    tb.kkt_eq_rows = eq_rows
+    tb.kkt_pos_var = pos[:n].astype(np.int32)
+    tb.kkt_pos_eq = pos[n:].astype(np.int32)
+    sign = np.ones(N, dtype=np.int32)
+    sign[tb.kkt_pos_eq] = -1
+    tb.kkt_sign = sign
+    # rows 0..N-1 of K plus the right-hand-side row N (dense)
+    first_all = np.concatenate([first, [0]]).astype(np.int32)
+    width = np.arange(N + 1) - first_all + 1
+    width[N] = N                         # rhs row has no diagonal entry
+    ptr = np.concatenate([[0], np.cumsum(width)]).astype(np.int32)
+    tb.env_first, tb.env_ptr = first_all, ptr
+    tb.env_size = int(ptr[-1])
+
+    def env(i, j):
+        return int(ptr[i] + (j - first_all[i]))
+
+    # destinations of the assembly gathers
+    hdst = np.empty(tb.nnz_h, dtype=np.int32)
+    for q, (r, c) in enumerate(zip(tb.hrow, tb.hcol)):
+        pr, pc = pos[r], pos[c]
+        hi, lo = (pr, pc) if pr >= pc else (pc, pr)
+        hdst[q] = env(hi, lo)
+    tb.kkt_hdst = hdst
+    jdst = np.full(tb.nnz_j, -1, dtype=np.int32)
+    for k, i in enumerate(eq_rows):
+        pk = pos[n + k]
+        for s in range(tb.jrow_ptr[i], tb.jrow_ptr[i + 1]):
+            pc = pos[tb.jcol[s]]
+            hi, lo = (pk, pc) if pk >= pc else (pc, pk)
+            jdst[s] = env(hi, lo)
+    tb.kkt_jdst = jdst
+    tb.kkt_diag = np.array([env(i, i) for i in range(N)], dtype=np.int32)
+    # panels and the rows each panel reaches
+    n_pan = (N + KKT_NB - 1) // KKT_NB
+    prow_ptr = [0]
+    prows = []
+    for pb in range(n_pan):
+        kb = pb * KKT_NB
+        ke = min(N, kb + KKT_NB)
+        rr = [i for i in range(ke, N + 1) if first_all[i] < ke]
+        prows += rr
+        prow_ptr.append(len(prows))
+    tb.kkt_panel_ptr = np.array(prow_ptr, dtype=np.int32)
+    tb.kkt_panel_rows = np.array(prows, dtype=np.int32)
+    tb.kkt_max_panel_rows = int(np.max(np.diff(prow_ptr))) if n_pan else 0
+    return tb

@@ -193,7 +193,7 @@ class OptiFather(object):
         rows, lb, ub = self.construct_constraints()
         objective = self.construct_objective()
         self.tables = lower(self._var_ids, self._par_ids, rows, objective,
-                            lb, ub)
+                            lb, ub, self.order_hint())
         self.problem_description = {'tables': self.tables, 'opt': options}
         if problem is None:
             problem, buildtime = create_nlp(self.tables, options, name)
@@ -202,6 +202,18 @@ class OptiFather(object):
         self.init_variables()
         self.init_parameters()
         return problem, buildtime
+
+    def order_hint(self):
+        """Relative "time" position of every variable (spline coefficient index /
+        basis length): the key of the banded KKT ordering (lowering.py)."""
+        hint = np.full(self._var_struct.size, 0.5)
+        for (label, name), (off, size, shape) in self._var_struct.entries.items():
+            child = self.children[label]
+            if name in child._splines_prim and shape[0] > 1:
+                L = shape[0]
+                for c in range(shape[1]):
+                    hint[off + c * L:off + (c + 1) * L] = np.arange(L) / (L - 1.0)
+        return hint
 
     def translate_symbols(self):
         """Resolve named placeholders to the child that defines them

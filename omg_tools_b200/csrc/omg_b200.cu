@@ -44,7 +44,10 @@ struct TL {
 
 struct DevTab {
   int n, m, n_par, n_v, n_tape, n_levels, nnz_j, nnz_w, nnz_h, n_hp;
-  int n_eq_max, N;                 // N = n + n_eq_max (order of the KKT block)
+  int n_eq, N;                     // structural equality rows; N = n + n_eq (order of K)
+  int env_size, n_panels, max_panel_rows;
+  const int *eq_rows, *pos_var, *pos_eq, *ksign, *env_first, *env_ptr, *hdst, *jdst, *kdiag,
+            *panel_ptr, *panel_rows;
   const int *tape_func, *tape_ptr, *tape_fac, *level_ptr; const double* tape_coef;
   TL G, F, DF, J, W;
   const int *jrow, *jcol, *jrow_ptr, *jcol_ptr, *jcol_slot;
@@ -52,7 +55,7 @@ struct DevTab {
 };
 
 struct Smem {                      // offsets in doubles
-  int K, Pt, xe, xt, dx, gf, diag0, invd, V, red, filt, total;
+  int K, Pt, PtS, xe, xt, dx, u, gf, diag0, invd, V, red, filt, rbase, total;
   int LDP;
 };
 
@@ -151,58 +154,70 @@ __device__ __forceinline__ bool cmp_le(double lhs, double rhs, double base) {
 }
 
 // ---------------------------------------------------------------------------
-// blocked Cholesky of the packed lower matrix K (rows 0..N, columns 0..N-1; row
-// N carries the right-hand side).  Columns [c0,c1) are processed; pivots must be
-// > PIV_TOL*diag0.  Sets ctl->fail (and eq_fail for columns >= n) on breakdown.
+// Blocked right-looking factorisation K = L S L^T on envelope storage.
+//   row i (permuted order) is stored from column first[i] (multiple of NB) to i
+//   at K[env_ptr[i] + j - first[i]]; row N is the right-hand side (never a
+//   pivot), so after the sweep it holds S L^{-1} r.
+// Per 16-column panel: (1) warp 0 factors the diagonal block in registers with
+// shuffles, (2) one thread per reached row does the panel solve, (3) the
+// trailing update runs over the rows the panel reaches, 32x16 super-tiles per
+// warp, 4x4 register tiles per lane with 128-bit shared loads.
+// Pivot j must satisfy sign[j]*pivot > PIV_TOL*|K_jj| (variables) or > 0
+// (equality rows); otherwise ctl->fail (eq_fail for an equality pivot).
 // ---------------------------------------------------------------------------
-__device__ void chol_range(double* __restrict__ K, double* __restrict__ Pt, int LDP,
-                           const double* __restrict__ diag0, double* __restrict__ invd,
-                           int c0, int c1, int N, int n, Ctl* ctl) {
+__device__ void factor_env(const DevTab& T, double* __restrict__ K, double* __restrict__ Pt,
+                           double* __restrict__ PtS, int LDP, const double* __restrict__ diag0,
+                           double* __restrict__ invd, int* __restrict__ rbase, Ctl* ctl) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int kb = c0; kb < c1; kb += NB) {
-    const int nb = min(NB, c1 - kb);
-    // ---- 1. diagonal block on warp 0 (lane r = row kb+r, registers) --------
+  const int N = T.N;
+  int* rrow = rbase + LDP;
+  for (int pb = 0; pb < T.n_panels; ++pb) {
+    const int kb = pb * NB;
+    const int nb = min(NB, N - kb);
+    // ---- 1. diagonal block (warp 0) ------------------------------------------
     if (warp == 0) {
       double a[NB];
+      const int row = kb + lane;
+      const int base = (lane < nb) ? (T.env_ptr[row] + kb - T.env_first[row]) : 0;
 #pragma unroll
-      for (int c = 0; c < NB; ++c)
-        a[c] = (lane < nb && c <= lane) ? K[tri(kb + lane, kb + c)] : 0.0;
+      for (int c = 0; c < NB; ++c) a[c] = (lane < nb && c <= lane) ? K[base + c] : 0.0;
       bool ok = true;
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
         if (j < nb && ok) {
-          double d = __shfl_sync(FULL, a[j], j);
-          double thr = PIV_TOL * fmax(diag0[kb + j], 1e-300);
+          const double sj = (double)T.ksign[kb + j];
+          const double d = sj * __shfl_sync(FULL, a[j], j);
+          const double thr = (sj > 0.0) ? PIV_TOL * fmax(diag0[kb + j], 1e-300) : 0.0;
           if (!(d > thr) || !isfinite(d)) {
             ok = false;
-            if (lane == 0) { ctl->fail = 1; ctl->eq_fail = (kb + j >= n) ? 1 : 0; }
+            if (lane == 0) { ctl->fail = 1; ctl->eq_fail = (sj < 0.0) ? 1 : 0; }
           } else {
-            double inv = rsqrt(d);
-            double ljj = d * inv;
-            if (lane == j) { a[j] = ljj; invd[kb + j] = inv; }
-            else if (lane > j) a[j] *= inv;
+            const double inv = rsqrt(d);
+            if (lane == j) { a[j] = d * inv; invd[kb + j] = inv; }
+            else if (lane > j) a[j] *= inv * sj;
 #pragma unroll
             for (int k = j + 1; k < NB; ++k) {
-              double lkj = __shfl_sync(FULL, a[j], k);
-              if (lane >= k) a[k] -= a[j] * lkj;
+              const double lkj = __shfl_sync(FULL, a[j], k);
+              if (lane >= k) a[k] -= sj * a[j] * lkj;
             }
           }
         }
       }
       if (ok) {
 #pragma unroll
-        for (int c = 0; c < NB; ++c)
-          if (lane < nb && c <= lane) K[tri(kb + lane, kb + c)] = a[c];
+        for (int c = 0; c < NB; ++c) if (lane < nb && c <= lane) K[base + c] = a[c];
       }
     }
     __syncthreads();
     if (ctl->fail) return;
-    // ---- 2. panel solve: rows r_lo..N ------------------------------------
-    const int r_lo = kb + nb;
-    const int nrows = N + 1 - r_lo;
+    // ---- 2. panel solve over the rows this panel reaches ----------------------
+    const int p0 = T.panel_ptr[pb];
+    const int nrows = T.panel_ptr[pb + 1] - p0;
     for (int rr = tid; rr < nrows; rr += NT) {
-      const int r = r_lo + rr;
-      double* Kr = K + tri(r, kb);
+      const int r = T.panel_rows[p0 + rr];
+      const int rb = T.env_ptr[r] - T.env_first[r];
+      rbase[rr] = rb; rrow[rr] = r;
+      double* Kr = K + rb + kb;
       double a[NB];
 #pragma unroll
       for (int c = 0; c < NB; ++c) a[c] = (c < nb) ? Kr[c] : 0.0;
@@ -210,40 +225,44 @@ __device__ void chol_range(double* __restrict__ K, double* __restrict__ Pt, int 
       for (int c = 0; c < NB; ++c) {
         if (c < nb) {
           double v = a[c];
-          const double* Lc = K + tri(kb + c, kb);
+          const int rc = kb + c;
+          const double* Lc = K + T.env_ptr[rc] + kb - T.env_first[rc];
 #pragma unroll
           for (int j = 0; j < NB; ++j)
-            if (j < c) v -= a[j] * Lc[j];
-          a[c] = v * invd[kb + c];
+            if (j < c) v -= (double)T.ksign[kb + j] * a[j] * Lc[j];
+          a[c] = v * invd[rc] * (double)T.ksign[rc];
         }
       }
 #pragma unroll
       for (int c = 0; c < NB; ++c)
-        if (c < nb) { Kr[c] = a[c]; Pt[c * LDP + rr] = a[c]; }
+        if (c < nb) { Kr[c] = a[c]; Pt[c * LDP + rr] = a[c]; PtS[c * LDP + rr] = (double)T.ksign[kb + c] * a[c]; }
+    }
+    // zero padding so that vector loads past nrows are harmless
+    for (int q = tid; q < NB * 4; q += NT) {
+      const int c = q >> 2, rr = nrows + (q & 3);
+      if (rr < LDP) { Pt[c * LDP + rr] = 0.0; PtS[c * LDP + rr] = 0.0; }
     }
     __syncthreads();
-    // ---- 3. trailing update with 4x4 register tiles ------------------------
-    const int nt4 = (nrows + 3) >> 2;
-    const int ntiles = nt4 * (nt4 + 1) / 2;
-    for (int t = tid; t < ntiles; t += NT) {
-      int ti = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-      while (ti * (ti + 1) / 2 > t) --ti;
-      while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-      const int tk = t - ti * (ti + 1) / 2;
-      const int i0 = ti * 4, k0 = tk * 4;          // relative to r_lo
+    // ---- 3. trailing update ------------------------------------------------------
+    // list positions a (rows) x b (columns), b <= a; super-tiles 32 (a) x 16 (b)
+    const int nsa = (nrows + 31) >> 5, nsb = (nrows + 15) >> 4;
+    const int ty = lane >> 2, tx = lane & 3;
+    for (int st = warp; st < nsa * nsb; st += NWARP) {
+      const int sa = st / nsb, sb = st - sa * nsb;
+      if (sb * 16 > sa * 32 + 31) continue;          // entirely above the diagonal
+      const int a0 = sa * 32 + ty * 4, b0 = sb * 16 + tx * 4;
+      if (a0 >= nrows || b0 >= nrows || b0 > a0 + 3) continue;
       double acc[4][4];
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
       for (int c = 0; c < nb; ++c) {
-        const double* P = Pt + c * LDP;
-        double ri[4], ck[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          ri[a] = (i0 + a < nrows) ? P[i0 + a] : 0.0;
-          ck[a] = (k0 + a < nrows) ? P[k0 + a] : 0.0;
-        }
+        const double2* Pa = reinterpret_cast<const double2*>(Pt + c * LDP + a0);
+        const double2* Pb = reinterpret_cast<const double2*>(PtS + c * LDP + b0);
+        const double2 r01 = Pa[0], r23 = Pa[1], c01 = Pb[0], c23 = Pb[1];
+        const double ri[4] = {r01.x, r01.y, r23.x, r23.y};
+        const double ck[4] = {c01.x, c01.y, c23.x, c23.y};
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -251,12 +270,16 @@ __device__ void chol_range(double* __restrict__ K, double* __restrict__ Pt, int 
       }
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
-        const int r = r_lo + i0 + a;
-        if (r <= N) {
+        const int la = a0 + a;
+        if (la < nrows) {
+          const int ra = rrow[la], rba = rbase[la];
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
-            const int cc = r_lo + k0 + b;
-            if (cc <= r && cc < N) K[tri(r, cc)] -= acc[a][b];
+            const int lb = b0 + b;
+            if (lb <= la && lb < nrows) {
+              const int cb = rrow[lb];
+              if (cb < N) K[rba + cb] -= acc[a][b];
+            }
           }
         }
       }
@@ -265,48 +288,52 @@ __device__ void chol_range(double* __restrict__ K, double* __restrict__ Pt, int 
   }
 }
 
-// Back substitution L^T u = w (w in dx[0..N)), same block boundaries as the
-// factorisation: [0,n) in steps of NB, then [n,N).
-__device__ void back_solve(const double* __restrict__ K, const double* __restrict__ invd,
-                           double* __restrict__ w, int N, int n) {
+// Back substitution L^T u = w on envelope storage (w = row N of L on entry).
+__device__ void back_solve_env(const DevTab& T, const double* __restrict__ K,
+                               const double* __restrict__ invd, double* __restrict__ w) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // enumerate blocks from the last to the first
-  for (int part = 1; part >= 0; --part) {
-    const int c0 = part ? n : 0, c1 = part ? N : n;
-    if (c1 <= c0) continue;
-    const int nblk = (c1 - c0 + NB - 1) / NB;
-    for (int bi = nblk - 1; bi >= 0; --bi) {
-      const int kb = c0 + bi * NB;
-      const int nb = min(NB, c1 - kb);
-      if (warp == 0) {
-        double wv = (lane < nb) ? w[kb + lane] : 0.0;
-        for (int j = nb - 1; j >= 0; --j) {
-          double uj = __shfl_sync(FULL, wv, j) * invd[kb + j];
-          if (lane == j) wv = uj;
-          else if (lane < j) wv -= K[tri(kb + j, kb + lane)] * uj;
-        }
-        if (lane < nb) w[kb + lane] = wv;
+  const int N = T.N;
+  for (int pb = T.n_panels - 1; pb >= 0; --pb) {
+    const int kb = pb * NB;
+    const int nb = min(NB, N - kb);
+    if (warp == 0) {
+      double wv = (lane < nb) ? w[kb + lane] : 0.0;
+      for (int j = nb - 1; j >= 0; --j) {
+        const int rj = kb + j;
+        const double uj = __shfl_sync(FULL, wv, j) * invd[rj];
+        if (lane == j) wv = uj;
+        else if (lane < j) wv -= K[T.env_ptr[rj] + kb - T.env_first[rj] + lane] * uj;
       }
-      __syncthreads();
-      for (int c = tid; c < kb; c += NT) {
-        double acc = w[c];
-        for (int j = 0; j < nb; ++j) acc -= K[tri(kb + j, c)] * w[kb + j];
-        w[c] = acc;
-      }
-      __syncthreads();
+      if (lane < nb) w[kb + lane] = wv;
     }
+    __syncthreads();
+    // columns left of the block: c in [first(block), kb)
+    int cmin = kb;
+    for (int j = 0; j < nb; ++j) cmin = min(cmin, T.env_first[kb + j]);
+    for (int c = cmin + tid; c < kb; c += NT) {
+      double acc = w[c];
+      for (int j = 0; j < nb; ++j) {
+        const int rj = kb + j, fj = T.env_first[rj];
+        if (c >= fj) acc -= K[T.env_ptr[rj] + c - fj] * w[rj];
+      }
+      w[c] = acc;
+    }
+    __syncthreads();
   }
 }
 
 // ---------------------------------------------------------------------------
 // the solver kernel
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT, 2)
 omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S) {
   extern __shared__ double sm[];
   __shared__ Ctl ctl;
   double* K = sm + S.K;
   double* Pt = sm + S.Pt;
+  double* PtS = sm + S.PtS;
+  double* u = sm + S.u;
+  int* rbase = reinterpret_cast<int*>(sm + S.rbase);
   double* xe = sm + S.xe;
   double* xt = sm + S.xt;
   double* dx = sm + S.dx;
@@ -411,30 +438,33 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
     }
     __syncthreads();
     if (tid == 0) {
-      int ne = 0, nbnd = 0;
+      int ne = 0, nbnd = 0, bad = 0;
       for (int i = 0; i < m; ++i) {
         const int r = rt[i];
-        if (r & 4) { if (ne < T.n_eq_max) eqrow[ne] = i; eqidx[i] = ne; ++ne; }
-        else eqidx[i] = -1;
+        if (r & 4) {
+          if (ne < T.n_eq && T.eq_rows[ne] == i) { eqrow[ne] = i; eqidx[i] = ne; } else bad = 1;
+          ++ne;
+        } else eqidx[i] = -1;
         nbnd += (r & 1) + ((r >> 1) & 1);
       }
-      ctl.n_eq = ne; ctl.n_bounds = nbnd;
+      if (ne != T.n_eq) bad = 1;
+      ctl.n_eq = bad ? -1 : ne; ctl.n_bounds = nbnd;
       ctl.mu = O.mu_init; ctl.tau = fmax(TAU_MIN, 1.0 - O.mu_init);
       ctl.theta_max = -1.0; ctl.theta_min = -1.0;
       ctl.delta_w_last = 0.0; ctl.nfilt = 0; ctl.status = -1; ctl.iter = 0;
-      ctl.fsc = fsc;
+      ctl.fsc = fsc; ctl.alpha = 0.0; ctl.delta_w = 0.0;
       ctl.f = fsc * eval_slot(T.F, 0, V, xe);
     }
     __syncthreads();
-    if (ctl.n_eq > T.n_eq_max) {         // structure mismatch: cannot fit the border
-      if (tid == 0) { A.status[inst] = OMG_ERROR_IN_STEP_COMPUTATION; A.iters[inst] = 0; }
+    if (ctl.n_eq < 0) {   // equality pattern differs from the lowered structure
+      if (tid == 0) { A.status[inst] = OMG_ERROR_IN_STEP_COMPUTATION; A.iters[inst] = 0; A.f[inst] = 0.0; }
       for (int i = tid; i < n; i += NT) A.x[(size_t)inst * n + i] = x0[i];
       for (int i = tid; i < m; i += NT) A.lam[(size_t)inst * m + i] = 0.0;
       __syncthreads();
       continue;
     }
     const int n_eq = ctl.n_eq;
-    const int N = n + n_eq;
+    const int N = T.N;
     const int n_bounds = ctl.n_bounds;
 
     // =========================== IP iterations ===============================
@@ -547,17 +577,15 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
 
       // ---- I7/I8: assemble + factorise, with inertia correction -----------------
       for (;;) {
-        const int ksz = (N + 1) * (N + 2) / 2;
-        for (int q = tid; q < ksz; q += NT) K[q] = 0.0;
+        for (int q = tid; q < T.env_size; q += NT) K[q] = 0.0;
         __syncthreads();
-        // H positions: gather J^T Sigma J
+        // H positions: gather J^T Sigma J (+ delta_w on the diagonal)
         for (int q = tid; q < T.nnz_h; q += NT) {
           double acc = 0.0;
           for (int e = T.hp_ptr[q]; e < T.hp_ptr[q + 1]; ++e)
             acc += sig[T.hp_row[e]] * jval[T.hp_s1[e]] * jval[T.hp_s2[e]];
-          const int rr = T.hrow[q], cc = T.hcol[q];
-          if (rr == cc) acc += ctl.delta_w;
-          K[tri(rr, cc)] = acc;
+          if (T.hrow[q] == T.hcol[q]) acc += ctl.delta_w;
+          K[T.hdst[q]] = acc;
         }
         __syncthreads();
         // Lagrangian Hessian W (lambda = y*dsc, objective factor fsc)
@@ -571,26 +599,21 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
             v *= (lr < m) ? (y[lr] * dsc[lr]) : ctl.fsc;
             acc += v;
           }
-          const int h = T.w2h[q];
-          K[tri(T.hrow[h], T.hcol[h])] += acc;
+          K[T.hdst[T.w2h[q]]] += acc;
         }
-        // diagonal entries that are structurally zero still get delta_w
         __syncthreads();
         for (int j = tid; j < n; j += NT) {
-          // positions present in the pattern were handled above; detect absent ones
-          // by checking whether (j,j) is in H: done on host -> all diagonals are
-          // forced into the pattern (see host code), nothing to do here.
-          diag0[j] = fabs(K[tri(j, j)]);
+          const int pj = T.pos_var[j];
+          diag0[pj] = fabs(K[T.kdiag[pj]]);
         }
-        // equality border + rhs row
+        // equality border + right-hand-side row
+        const int rhs0 = T.env_ptr[N];
         for (int k = tid; k < n_eq; k += NT) {
-          const int i = eqrow[k];
-          for (int sl = T.jrow_ptr[i]; sl < T.jrow_ptr[i + 1]; ++sl)
-            K[tri(n + k, T.jcol[sl])] = jval[sl];
-          K[tri(n + k, n + k)] = -ctl.delta_c;
-          diag0[n + k] = ctl.delta_c;
-          const double ci = g[i] - beq[i];
-          K[tri(N, n + k)] = -ci;
+          const int i = eqrow[k], pk = T.pos_eq[k];
+          for (int sl = T.jrow_ptr[i]; sl < T.jrow_ptr[i + 1]; ++sl) K[T.jdst[sl]] = jval[sl];
+          K[T.kdiag[pk]] = -ctl.delta_c;
+          diag0[pk] = ctl.delta_c;
+          K[rhs0 + pk] = -(g[i] - beq[i]);
         }
         for (int j = tid; j < n; j += NT) {
           double acc = gf[j];
@@ -598,26 +621,11 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
             const int sl = T.jcol_slot[q];
             acc += jval[sl] * wv[T.jrow[sl]];
           }
-          K[tri(N, j)] = -acc;
+          K[rhs0 + T.pos_var[j]] = -acc;
         }
         if (tid == 0) { ctl.fail = 0; ctl.eq_fail = 0; }
         __syncthreads();
-        chol_range(K, Pt, S.LDP, diag0, invd, 0, n, N, n, &ctl);
-        if (!ctl.fail && n_eq > 0) {
-          // corner block -> its negative (K = L S L^T with S = diag(I, -I))
-          const int ne2 = n_eq * (n_eq + 1) / 2;
-          for (int q = tid; q < ne2; q += NT) {
-            int i = (int)((sqrt(8.0 * (double)q + 1.0) - 1.0) * 0.5);
-            while (i * (i + 1) / 2 > q) --i;
-            while ((i + 1) * (i + 2) / 2 <= q) ++i;
-            const int k = q - i * (i + 1) / 2;
-            double* e = &K[tri(n + i, n + k)];
-            *e = -*e;
-            if (i == k) diag0[n + i] = fabs(*e);
-          }
-          __syncthreads();
-          chol_range(K, Pt, S.LDP, diag0, invd, n, N, N, n, &ctl);
-        }
+        factor_env(T, K, Pt, PtS, S.LDP, diag0, invd, rbase, &ctl);
         __syncthreads();
         if (!ctl.fail) break;
         // inertia correction (IPOPT algorithm IC on the condensed matrix)
@@ -641,12 +649,12 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
       }
       if (tid == 0 && ctl.delta_w > 0.0) ctl.delta_w_last = ctl.delta_w;
       // ---- I9: solve -----------------------------------------------------------
-      for (int j = tid; j < N; j += NT) {
-        const double w = K[tri(N, j)];
-        dx[j] = (j >= n) ? -w : w;
-      }
+      for (int j = tid; j < N; j += NT) u[j] = K[T.env_ptr[N] + j];
       __syncthreads();
-      back_solve(K, invd, dx, N, n);
+      back_solve_env(T, K, invd, u);
+      for (int j = tid; j < n; j += NT) dx[j] = u[T.pos_var[j]];
+      for (int k = tid; k < n_eq; k += NT) dx[n + k] = u[T.pos_eq[k]];
+      __syncthreads();
       // ---- I10: ds, dy, dz, fraction to the boundary --------------------------
       double sv[4];   // 0 a_p(min) 1 a_d(min) 2 gphi(sum) 3 unused
       const int sop[4] = {OP_MIN, OP_MIN, OP_SUM, OP_SUM};
@@ -880,9 +888,23 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
   T.n = tb->n; T.m = tb->m; T.n_par = tb->n_par; T.n_v = tb->n_v;
   T.n_tape = tb->n_tape; T.n_levels = tb->n_levels;
   T.nnz_j = tb->nnz_j; T.nnz_w = tb->nnz_w; T.nnz_h = tb->nnz_h; T.n_hp = tb->n_hp;
-  int neq = 0;
-  for (int i = 0; i < tb->m; ++i) if (tb->lbg[i] == tb->ubg[i]) ++neq;
-  T.n_eq_max = neq; T.N = tb->n + neq;
+  T.n_eq = tb->kkt_n_eq; T.N = tb->kkt_n;
+  T.env_size = tb->env_size; T.max_panel_rows = tb->max_panel_rows;
+  T.n_panels = (tb->kkt_n + NB - 1) / NB;
+  if (tb->kkt_n != tb->n + tb->kkt_n_eq) { set_err("inconsistent KKT structure"); ok = false; }
+  for (int i = 0; ok && i <= tb->kkt_n; ++i)
+    if (tb->env_first[i] % NB != 0) { set_err("env_first must be a multiple of the panel width"); ok = false; }
+  T.eq_rows = upload(h, tb->kkt_eq_rows, tb->kkt_n_eq, &ok);
+  T.pos_var = upload(h, tb->kkt_pos_var, tb->n, &ok);
+  T.pos_eq = upload(h, tb->kkt_pos_eq, tb->kkt_n_eq, &ok);
+  T.ksign = upload(h, tb->kkt_sign, tb->kkt_n, &ok);
+  T.env_first = upload(h, tb->env_first, (size_t)tb->kkt_n + 1, &ok);
+  T.env_ptr = upload(h, tb->env_ptr, (size_t)tb->kkt_n + 2, &ok);
+  T.hdst = upload(h, tb->kkt_hdst, tb->nnz_h, &ok);
+  T.jdst = upload(h, tb->kkt_jdst, tb->nnz_j, &ok);
+  T.kdiag = upload(h, tb->kkt_diag, tb->kkt_n, &ok);
+  T.panel_ptr = upload(h, tb->kkt_panel_ptr, (size_t)T.n_panels + 1, &ok);
+  T.panel_rows = upload(h, tb->kkt_panel_rows, tb->n_panel_rows, &ok);
   T.tape_func = upload(h, tb->tape_func, tb->n_tape, &ok);
   T.tape_ptr = upload(h, tb->tape_ptr, (size_t)tb->n_tape + 1, &ok);
   T.tape_coef = upload(h, tb->tape_coef, tb->n_tape_terms, &ok);
@@ -918,10 +940,12 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
   const int N = T.N;
   int off = 0;
   auto take = [&](int cnt) { int o = off; off += (cnt + 1) & ~1; return o; };
-  S.K = take((N + 1) * (N + 2) / 2);
-  S.LDP = ((N + 1) + 3) & ~3;
-  S.Pt = take(NB * S.LDP);
-  S.xe = take(T.n + 1); S.xt = take(T.n + 1); S.dx = take(N + 1); S.gf = take(T.n);
+  S.K = take(T.env_size);
+  S.LDP = (T.max_panel_rows + 4 + 3) & ~3;
+  S.Pt = take(NB * S.LDP); S.PtS = take(NB * S.LDP);
+  S.rbase = take(S.LDP);               // 2*LDP ints: row base offsets + row ids
+  S.xe = take(T.n + 1); S.xt = take(T.n + 1); S.dx = take(N + 1); S.u = take(N + 1);
+  S.gf = take(T.n);
   S.diag0 = take(N + 1); S.invd = take(N + 1); S.V = take(T.n_v);
   S.red = take(NWARP * NRED); S.filt = take(2 * MAXF);
   S.total = off;
@@ -932,18 +956,23 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
   if (ok && h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
     char buf[256];
     snprintf(buf, sizeof buf, "KKT block does not fit shared memory: need %zu B, have %zu B (n=%d, n_eq=%d)",
-             h->smem_bytes, (size_t)prop.sharedMemPerBlockOptin, T.n, T.n_eq_max);
+             h->smem_bytes, (size_t)prop.sharedMemPerBlockOptin, T.n, T.n_eq);
     set_err(buf); ok = false;
   }
   // the attribute is per function (shared by all handles): opt in to the device maximum
-  if (ok && cudaFuncSetAttribute(omg_ipm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)prop.sharedMemPerBlockOptin) != cudaSuccess) { set_err("cudaFuncSetAttribute failed"); ok = false; }
+  if (ok) {
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, omg_ipm_kernel) != cudaSuccess) { set_err("cudaFuncGetAttributes failed"); ok = false; }
+    else if (cudaFuncSetAttribute(omg_ipm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(prop.sharedMemPerBlockOptin - fa.sharedSizeBytes)) != cudaSuccess) {
+      set_err(std::string("cudaFuncSetAttribute failed: ") + cudaGetErrorString(cudaGetLastError())); ok = false; }
+  }
   if (ok) {
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, omg_ipm_kernel, NT, h->smem_bytes);
     h->ctas_per_sm = occ > 0 ? occ : 1;
     h->dscr_stride = 17 * T.m + T.nnz_j + 8;
-    h->iscr_stride = 2 * T.m + T.n_eq_max + 8;
+    h->iscr_stride = 2 * T.m + T.n_eq + 8;
     if (cudaMalloc(&h->counter, sizeof(int)) != cudaSuccess) ok = false;
     if (cudaMalloc(&h->trace, sizeof(double) * TRACE_ROWS * TRACE_COLS) != cudaSuccess) ok = false;
     else cudaMemset(h->trace, 0, sizeof(double) * TRACE_ROWS * TRACE_COLS);

@@ -24,7 +24,7 @@ def _p2p(vehicle, environment, options, build_solver):
         rows, lb, ub = f.construct_constraints()
         from .basics.lowering import lower
         f.tables = lower(f._var_ids, f._par_ids, rows, f.construct_objective(),
-                         lb, ub)
+                         lb, ub, f.order_hint())
         f.init_variables()
         f.init_parameters()
         f.init_transformations(problem.init_primal_transform,

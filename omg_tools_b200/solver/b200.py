@@ -24,6 +24,8 @@ STATUS_STRINGS = {
     2: 'Restoration_Failed', 3: 'Error_In_Step_Computation',
     4: 'Invalid_Number_Detected', 5: 'Infeasible_Problem_Detected'}
 
+ABI_VERSION = 2
+
 _i32p = C.POINTER(C.c_int32)
 _f64p = C.POINTER(C.c_double)
 
@@ -49,7 +51,13 @@ class _Tables(C.Structure):
         ('nnz_h', C.c_int32), ('n_hp', C.c_int32),
         ('hrow', _i32p), ('hcol', _i32p), ('hp_ptr', _i32p),
         ('hp_s1', _i32p), ('hp_s2', _i32p), ('hp_row', _i32p),
-        ('lbg', _f64p), ('ubg', _f64p)]
+        ('lbg', _f64p), ('ubg', _f64p),
+        ('kkt_n', C.c_int32), ('kkt_n_eq', C.c_int32), ('env_size', C.c_int32),
+        ('n_panel_rows', C.c_int32), ('max_panel_rows', C.c_int32),
+        ('kkt_eq_rows', _i32p), ('kkt_pos_var', _i32p), ('kkt_pos_eq', _i32p),
+        ('kkt_sign', _i32p), ('env_first', _i32p), ('env_ptr', _i32p),
+        ('kkt_hdst', _i32p), ('kkt_jdst', _i32p), ('kkt_diag', _i32p),
+        ('kkt_panel_ptr', _i32p), ('kkt_panel_rows', _i32p)]
 
 
 class _Options(C.Structure):
@@ -138,7 +146,7 @@ def pack_tables(tb):
         return s
 
     T = _Tables()
-    T.abi_version = 1
+    T.abi_version = ABI_VERSION
     T.n, T.m, T.n_par, T.n_v, T.degree = tb.n, tb.m, tb.n_par, tb.n_v, tb.degree
     T.n_tape, T.n_tape_terms = len(tb.tape_func), len(tb.tape_coef)
     T.n_levels = len(tb.level_ptr) - 1
@@ -155,6 +163,15 @@ def pack_tables(tb):
     T.hrow, T.hcol, T.hp_ptr = keep.i32(tb.hrow), keep.i32(tb.hcol), keep.i32(tb.hp_ptr)
     T.hp_s1, T.hp_s2, T.hp_row = keep.i32(tb.hp_s1), keep.i32(tb.hp_s2), keep.i32(tb.hp_row)
     T.lbg, T.ubg = keep.f64(tb.lbg), keep.f64(tb.ubg)
+    T.kkt_n, T.kkt_n_eq, T.env_size = tb.kkt_n, tb.kkt_n_eq, tb.env_size
+    T.n_panel_rows, T.max_panel_rows = len(tb.kkt_panel_rows), tb.kkt_max_panel_rows
+    T.kkt_eq_rows, T.kkt_pos_var = keep.i32(tb.kkt_eq_rows), keep.i32(tb.kkt_pos_var)
+    T.kkt_pos_eq, T.kkt_sign = keep.i32(tb.kkt_pos_eq), keep.i32(tb.kkt_sign)
+    T.env_first, T.env_ptr = keep.i32(tb.env_first), keep.i32(tb.env_ptr)
+    T.kkt_hdst, T.kkt_jdst = keep.i32(tb.kkt_hdst), keep.i32(tb.kkt_jdst)
+    T.kkt_diag = keep.i32(tb.kkt_diag)
+    T.kkt_panel_ptr = keep.i32(tb.kkt_panel_ptr)
+    T.kkt_panel_rows = keep.i32(tb.kkt_panel_rows)
     return T, keep
 
 
@@ -163,7 +180,7 @@ class B200Solver(object):
 
     def __init__(self, tables, options=None, device=None):
         self.lib = load_library()
-        if self.lib.omg_abi_version() != 1:
+        if self.lib.omg_abi_version() != ABI_VERSION:
             raise RuntimeError('libomgb200.so ABI version mismatch')
         self.tables = tables
         self.n, self.m, self.n_par = tables.n, tables.m, tables.n_par

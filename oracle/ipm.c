@@ -80,40 +80,34 @@ static int cmp_le(double lhs, double rhs, double base) {
   return lhs - rhs <= 10.0 * DBL_EPSILON * fabs(base);
 }
 
-/* K = L S L^T (S = diag(I_n, -I)), row-major full storage, lower part used. */
-static int gen_cholesky(double* K, int N, int n, int* eq_fail) {
+/* K = L S L^T, S = diag(sign) in the permuted order of
+ * lowering.build_kkt_structure; row-major full storage, lower part used. */
+static int signed_cholesky(double* K, int N, const int32_t* sign, double* d0, int* eq_fail) {
   *eq_fail = 0;
-  /* original diagonal for the relative pivot test */
-  double* d0 = (double*)malloc(sizeof(double) * N);
   for (int j = 0; j < N; ++j) d0[j] = fabs(K[j * N + j]);
   for (int j = 0; j < N; ++j) {
-    const double sgn = (j < n) ? 1.0 : -1.0;
+    const double sgn = (double)sign[j];
     const double piv = sgn * K[j * N + j];
-    const double ref = (j < n) ? d0[j] : piv;   /* eq. part: relative to itself */
-    if (!(piv > PIV_TOL * fmax(ref, 1e-300)) || !isfinite(piv)) {
-      *eq_fail = (j >= n);
-      free(d0);
-      return 0;
-    }
+    const double thr = (sgn > 0) ? PIV_TOL * fmax(d0[j], 1e-300) : 0.0;
+    if (!(piv > thr) || !isfinite(piv)) { *eq_fail = (sgn < 0); return 0; }
     const double ljj = sqrt(piv);
     K[j * N + j] = ljj;
     for (int i = j + 1; i < N; ++i) K[i * N + j] /= (sgn * ljj);
     for (int i = j + 1; i < N; ++i) {
-      const double lij = K[i * N + j];
+      const double lij = sgn * K[i * N + j];
       if (lij == 0.0) continue;
-      for (int k = j + 1; k <= i; ++k) K[i * N + k] -= sgn * lij * K[k * N + j];
+      for (int k = j + 1; k <= i; ++k) K[i * N + k] -= lij * K[k * N + j];
     }
   }
-  free(d0);
   return 1;
 }
 
-static void gen_solve(const double* L, int N, int n, double* w) {
+static void signed_solve(const double* L, int N, const int32_t* sign, double* w) {
   for (int j = 0; j < N; ++j) {
     w[j] /= L[j * N + j];
     for (int i = j + 1; i < N; ++i) w[i] -= L[i * N + j] * w[j];
   }
-  for (int j = n; j < N; ++j) w[j] = -w[j];
+  for (int j = 0; j < N; ++j) w[j] *= (double)sign[j];
   for (int j = N - 1; j >= 0; --j) {
     w[j] /= L[j * N + j];
     for (int i = 0; i < j; ++i) w[i] -= L[j * N + i] * w[j];
@@ -122,7 +116,7 @@ static void gen_solve(const double* L, int N, int n, double* w) {
 
 typedef struct {
   double *V, *xe, *xt, *g, *s, *y, *zL, *zU, *dsc, *sL, *sU, *beq, *sig, *wv, *ds, *dy,
-         *dzL, *dzU, *gt, *st, *jval, *gf, *K, *rhs, *rx;
+         *dzL, *dzU, *gt, *st, *jval, *gf, *K, *rhs, *rx, *d0, *sol;
   int *rt, *eqidx, *eqrow;
 } Work;
 
@@ -138,6 +132,7 @@ static void work_alloc(Work* w, const omg_tables* T, int Nmax) {
   w->jval = xalloc(sizeof(double) * T->nnz_j);
   w->gf = xalloc(sizeof(double) * n); w->rx = xalloc(sizeof(double) * n);
   w->K = xalloc(sizeof(double) * Nmax * Nmax); w->rhs = xalloc(sizeof(double) * Nmax);
+  w->d0 = xalloc(sizeof(double) * Nmax); w->sol = xalloc(sizeof(double) * Nmax);
   w->rt = xalloc(sizeof(int) * m); w->eqidx = xalloc(sizeof(int) * m);
   w->eqrow = xalloc(sizeof(int) * (m + 1));
 }
@@ -145,7 +140,7 @@ static void work_alloc(Work* w, const omg_tables* T, int Nmax) {
 static void work_free(Work* w) {
   void* all[] = {w->V, w->xe, w->xt, w->g, w->s, w->y, w->zL, w->zU, w->dsc, w->sL, w->sU, w->beq,
                  w->sig, w->wv, w->ds, w->dy, w->dzL, w->dzU, w->gt, w->st, w->jval, w->gf, w->rx,
-                 w->K, w->rhs, w->rt, w->eqidx, w->eqrow};
+                 w->K, w->rhs, w->d0, w->sol, w->rt, w->eqidx, w->eqrow};
   for (unsigned k = 0; k < sizeof(all) / sizeof(all[0]); ++k) free(all[k]);
 }
 
@@ -196,6 +191,14 @@ static void solve_one(const omg_tables* T, const omg_options* O, Work* w, const 
     y[i] = yi;
     zL[i] = hL ? fmax(O->mult_bound_push, -yi) : 0.0;
     zU[i] = hU ? fmax(O->mult_bound_push, yi) : 0.0;
+  }
+  int mismatch = (n_eq != T->kkt_n_eq);
+  for (int k = 0; k < n_eq && !mismatch; ++k) if (eqrow[k] != T->kkt_eq_rows[k]) mismatch = 1;
+  if (mismatch) {   /* equality pattern differs from the lowered structure */
+    for (int i = 0; i < n; ++i) xout[i] = x0[i];
+    for (int i = 0; i < m; ++i) lamout[i] = 0.0;
+    *fout = 0.0; *status_out = OMG_ERROR_IN_STEP_COMPUTATION; *iters_out = 0;
+    return;
   }
   const int N = n + n_eq;
   double mu = O->mu_init, tau = fmax(TAU_MIN, 1.0 - mu);
@@ -263,7 +266,8 @@ static void solve_one(const omg_tables* T, const omg_options* O, Work* w, const 
         double acc = 0.0;
         for (int e = T->hp_ptr[q]; e < T->hp_ptr[q + 1]; ++e) acc += sig[T->hp_row[e]] * jval[T->hp_s1[e]] * jval[T->hp_s2[e]];
         if (T->hrow[q] == T->hcol[q]) acc += delta_w;
-        K[T->hrow[q] * N + T->hcol[q]] = acc;
+        { const int a = T->kkt_pos_var[T->hrow[q]], b = T->kkt_pos_var[T->hcol[q]];
+          K[(a > b ? a : b) * N + (a > b ? b : a)] = acc; }
       }
       for (int q = 0; q < T->nnz_w; ++q) {
         double acc = 0.0; const omg_termlist* L = &T->W;
@@ -275,18 +279,23 @@ static void solve_one(const omg_tables* T, const omg_options* O, Work* w, const 
           acc += v;
         }
         const int h = T->w2h[q];
-        K[T->hrow[h] * N + T->hcol[h]] += acc;
+        { const int a = T->kkt_pos_var[T->hrow[h]], b = T->kkt_pos_var[T->hcol[h]];
+          K[(a > b ? a : b) * N + (a > b ? b : a)] += acc; }
       }
       for (int k = 0; k < n_eq; ++k) {
         const int i = eqrow[k];
-        for (int sl = T->jrow_ptr[i]; sl < T->jrow_ptr[i + 1]; ++sl) K[(n + k) * N + T->jcol[sl]] = jval[sl];
-        K[(n + k) * N + n + k] = -delta_c;
-        rhs[n + k] = -(g[i] - beq[i]);
+        const int pk = T->kkt_pos_eq[k];
+        for (int sl = T->jrow_ptr[i]; sl < T->jrow_ptr[i + 1]; ++sl) {
+          const int b = T->kkt_pos_var[T->jcol[sl]];
+          K[(pk > b ? pk : b) * N + (pk > b ? b : pk)] = jval[sl];
+        }
+        K[pk * N + pk] = -delta_c;
+        rhs[pk] = -(g[i] - beq[i]);
       }
-      for (int j = 0; j < n; ++j) rhs[j] = -gf[j];
-      for (int sl = 0; sl < T->nnz_j; ++sl) rhs[T->jcol[sl]] -= jval[sl] * wv[T->jrow[sl]];
+      for (int j = 0; j < n; ++j) rhs[T->kkt_pos_var[j]] = -gf[j];
+      for (int sl = 0; sl < T->nnz_j; ++sl) rhs[T->kkt_pos_var[T->jcol[sl]]] -= jval[sl] * wv[T->jrow[sl]];
       int eq_fail = 0;
-      ok = gen_cholesky(K, N, n, &eq_fail);
+      ok = signed_cholesky(K, N, T->kkt_sign, w->d0, &eq_fail);
       if (ok) break;
       if (eq_fail) delta_c = DELTA_C_VAL * pow(mu, DELTA_C_EXP);
       if (first_try) { delta_w = (delta_w_last == 0.0) ? DELTA_W0 : fmax(DELTA_W_MIN, KAPPA_W_MINUS * delta_w_last); first_try = 0; }
@@ -295,8 +304,10 @@ static void solve_one(const omg_tables* T, const omg_options* O, Work* w, const 
     }
     if (!ok) { status = OMG_ERROR_IN_STEP_COMPUTATION; break; }
     if (delta_w > 0.0) delta_w_last = delta_w;
-    gen_solve(K, N, n, rhs);
-    const double* dx = rhs;
+    signed_solve(K, N, T->kkt_sign, rhs);
+    double* dx = w->sol;   /* natural order: variables, then equality multipliers */
+    for (int j = 0; j < n; ++j) dx[j] = rhs[T->kkt_pos_var[j]];
+    for (int k = 0; k < n_eq; ++k) dx[n + k] = rhs[T->kkt_pos_eq[k]];
     double a_p = 1.0, a_d = 1.0, gphi = 0.0;
     for (int i = 0; i < m; ++i) {
       const int r = rt[i]; double jd = 0.0;

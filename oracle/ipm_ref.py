@@ -76,6 +76,14 @@ def solve(tb, x0, p, lbg=None, ubg=None, options=None, lam_g0=None,
     ineq = ~is_eq
     eq_idx = np.nonzero(is_eq)[0]
     n_eq = len(eq_idx)
+    if n_eq != tb.kkt_n_eq or np.any(eq_idx != tb.kkt_eq_rows):
+        res = Result()           # equality pattern differs from the structure
+        res.x, res.lam_g, res.f = x, np.zeros(m), 0.0
+        res.status, res.return_status, res.iters, res.mu, res.log = \
+            3, STATUS[3], 0, o['mu_init'], []
+        return res
+    kperm = np.argsort(np.r_[tb.kkt_pos_var, tb.kkt_pos_eq])
+    ksign = tb.kkt_sign.astype(float)
 
     # ---- gradient-based scaling at x0 ---------------------------------
     jv = np.abs(ev.jac_vals(x, V))
@@ -206,9 +214,13 @@ def solve(tb, x0, p, lbg=None, ubg=None, options=None, lam_g0=None,
             K[n:, :n] = Jc
             K[:n, n:] = Jc.T
             K[n:, n:] = -delta_c * np.eye(n_eq)
-            ok, L, eq_fail = _gen_cholesky(K, n, o['piv_tol'])
+            # symmetric permutation of lowering.build_kkt_structure: equality
+            # rows interleaved, K = L S L^T with S = diag(kkt_sign)
+            ok, L, eq_fail = _signed_cholesky(K[np.ix_(kperm, kperm)], ksign,
+                                              o['piv_tol'])
             if ok:
-                sol = _gen_solve(L, n, np.r_[rhs1, rhs2])
+                sol = np.empty(n + n_eq)
+                sol[kperm] = _signed_solve(L, ksign, np.r_[rhs1, rhs2][kperm])
                 break
             if eq_fail:
                 delta_c = o['delta_c_val'] * mu ** o['delta_c_exp']
@@ -356,19 +368,20 @@ def _filter_add(filt, th, ph, cap):
     filt.append((th, ph))
 
 
-def _gen_cholesky(K, n, piv_tol):
-    """K = L S L^T, S = diag(+1 (first n), -1 (rest)); lower-triangular L.
-    Fails when one of the first n pivots is not positive (wrong inertia of the
-    condensed Hessian) or one of the others is not negative (rank-deficient
-    equality Jacobian).  Returns (ok, L, failure_in_equality_part)."""
+def _signed_cholesky(K, sign, piv_tol):
+    """K = L S L^T with S = diag(sign) (+1 variables, -1 equality rows, in the
+    permuted order); lower-triangular L.  Fails when a pivot does not have the
+    expected sign (wrong inertia -> caller adds delta_w / delta_c).
+    Returns (ok, L, failure_at_an_equality_pivot)."""
     N = K.shape[0]
     A = np.tril(K).copy()
     d0 = np.abs(np.diag(K)).copy()
     for j in range(N):
-        sgn = 1.0 if j < n else -1.0
+        sgn = sign[j]
         piv = sgn * A[j, j]
-        if not (piv > piv_tol * max(d0[j], 1e-300)) or not np.isfinite(piv):
-            return False, None, j >= n
+        thr = piv_tol * max(d0[j], 1e-300) if sgn > 0 else 0.0
+        if not (piv > thr) or not np.isfinite(piv):
+            return False, None, sgn < 0
         ljj = np.sqrt(piv)
         A[j, j] = ljj
         if j + 1 < N:
@@ -378,13 +391,13 @@ def _gen_cholesky(K, n, piv_tol):
     return True, A, False
 
 
-def _gen_solve(L, n, rhs):
+def _signed_solve(L, sign, rhs):
     N = L.shape[0]
     w = np.array(rhs, dtype=float)
     for j in range(N):
         w[j] /= L[j, j]
         w[j + 1:] -= L[j + 1:, j] * w[j]
-    w[n:] = -w[n:]
+    w = w * sign
     for j in range(N - 1, -1, -1):
         w[j] /= L[j, j]
         w[:j] -= L[j, :j] * w[j]
