@@ -37,9 +37,14 @@
 // ---------------------------------------------------------------------------
 // device-side table views
 // ---------------------------------------------------------------------------
+struct PTerm {                     // packed term (width <= 2): one 16-byte load
+  double coef; unsigned short cidx, x0, x1, lrow;
+};
+
 struct TL {
   int n_out, n_terms, width;
   const int* ptr; const double* coef; const int* cidx; const int* xi; const int* lrow;
+  const PTerm* pk;                 // non-null when width <= 2
 };
 
 struct DevTab {
@@ -47,7 +52,8 @@ struct DevTab {
   int n_eq, N;                     // structural equality rows; N = n + n_eq (order of K)
   int env_size, n_panels, max_panel_rows;
   const int *eq_rows, *pos_var, *pos_eq, *ksign, *env_first, *env_ptr, *hdst, *jdst, *kdiag,
-            *panel_ptr, *panel_rows;
+            *panel_ptr, *panel_rows, *panel_cmin;
+  const unsigned* hp_pack;         // pair list packed: s1 | s2 << 16 (nnz_j < 65536)
   const int *tape_func, *tape_ptr, *tape_fac, *level_ptr; const double* tape_coef;
   TL G, F, DF, J, W;
   const int *jrow, *jcol, *jrow_ptr, *jcol_ptr, *jcol_slot;
@@ -56,6 +62,7 @@ struct DevTab {
 
 struct Smem {                      // offsets in doubles
   int K, Pt, PtS, xe, xt, dx, u, gf, diag0, invd, V, red, filt, rbase, total;
+  int sgn, eptr, efirst, pptr, prow, pcmin;   // structure arrays cached in shared memory
   int LDP;
 };
 
@@ -104,12 +111,33 @@ struct Ctl {                       // uniform per-block control scalars
 
 enum { OP_MAX = 0, OP_MIN = 1, OP_SUM = 2 };
 
+// phase timers (debug, opt.trace=1, instance 0): cycles per phase summed over the solve
+#define NPHASE 16
+#define TICK(k) do { if (tracing && threadIdx.x == 0) { const long long t_ = clock64(); \
+  phase_cyc[k] += (double)(t_ - phase_t0); phase_t0 = t_; } } while (0)
+
 __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+
+__device__ __forceinline__ PTerm load_pterm(const PTerm* p) {
+  const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+  PTerm t;
+  t.coef = __hiloint2double((int)r.y, (int)r.x);
+  t.cidx = (unsigned short)(r.z & 0xffffu); t.x0 = (unsigned short)(r.z >> 16);
+  t.x1 = (unsigned short)(r.w & 0xffffu); t.lrow = (unsigned short)(r.w >> 16);
+  return t;
+}
 
 __device__ __forceinline__ double eval_slot(const TL& L, int s, const double* __restrict__ V,
                                             const double* __restrict__ xe) {
   double acc = 0.0;
   const int lo = L.ptr[s], hi = L.ptr[s + 1], w = L.width;
+  if (L.pk) {
+    for (int t = lo; t < hi; ++t) {
+      const PTerm q = load_pterm(L.pk + t);
+      acc += q.coef * V[q.cidx] * xe[q.x0] * xe[q.x1];
+    }
+    return acc;
+  }
   for (int t = lo; t < hi; ++t) {
     double v = L.coef[t] * V[L.cidx[t]];
     for (int k = 0; k < w; ++k) v *= xe[L.xi[t * w + k]];
@@ -165,12 +193,19 @@ __device__ __forceinline__ bool cmp_le(double lhs, double rhs, double base) {
 // Pivot j must satisfy sign[j]*pivot > PIV_TOL*|K_jj| (variables) or > 0
 // (equality rows); otherwise ctl->fail (eq_fail for an equality pivot).
 // ---------------------------------------------------------------------------
-__device__ void factor_env(const DevTab& T, double* __restrict__ K, double* __restrict__ Pt,
+struct KS {   // shared-memory copies of the KKT structure arrays
+  const double* sgn; const int* eptr; const int* efirst; const int* pptr; const int* prow;
+  const int* pcmin;
+};
+
+__device__ void factor_env(const DevTab& T, const KS& ks, double* __restrict__ K, double* __restrict__ Pt,
                            double* __restrict__ PtS, int LDP, const double* __restrict__ diag0,
-                           double* __restrict__ invd, int* __restrict__ rbase, Ctl* ctl) {
+                           double* __restrict__ invd, int* __restrict__ rbase, Ctl* ctl, double* pc) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = T.N;
   int* rrow = rbase + LDP;
+  long long t0 = clock64();
+#define FT(k) do { if (pc && tid == 0) { const long long t_ = clock64(); pc[k] += (double)(t_ - t0); t0 = t_; } } while (0)
   for (int pb = 0; pb < T.n_panels; ++pb) {
     const int kb = pb * NB;
     const int nb = min(NB, N - kb);
@@ -178,21 +213,23 @@ __device__ void factor_env(const DevTab& T, double* __restrict__ K, double* __re
     if (warp == 0) {
       double a[NB];
       const int row = kb + lane;
-      const int base = (lane < nb) ? (T.env_ptr[row] + kb - T.env_first[row]) : 0;
+      const int base = (lane < nb) ? (ks.eptr[row] + kb - ks.efirst[row]) : 0;
 #pragma unroll
       for (int c = 0; c < NB; ++c) a[c] = (lane < nb && c <= lane) ? K[base + c] : 0.0;
+      const double my_s = (lane < nb) ? ks.sgn[row] : 1.0;
+      const double my_thr = (lane < nb && my_s > 0.0) ? PIV_TOL * fmax(diag0[row], 1e-300) : 0.0;
       bool ok = true;
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
         if (j < nb && ok) {
-          const double sj = (double)T.ksign[kb + j];
+          const double sj = __shfl_sync(FULL, my_s, j);
+          const double thr = __shfl_sync(FULL, my_thr, j);
           const double d = sj * __shfl_sync(FULL, a[j], j);
-          const double thr = (sj > 0.0) ? PIV_TOL * fmax(diag0[kb + j], 1e-300) : 0.0;
           if (!(d > thr) || !isfinite(d)) {
             ok = false;
             if (lane == 0) { ctl->fail = 1; ctl->eq_fail = (sj < 0.0) ? 1 : 0; }
           } else {
-            const double inv = rsqrt(d);
+            const double inv = rsqrt(d);   // 62 cycles on B200 (tools/ubench/lat.cu), faster than a float seed + Newton
             if (lane == j) { a[j] = d * inv; invd[kb + j] = inv; }
             else if (lane > j) a[j] *= inv * sj;
 #pragma unroll
@@ -209,13 +246,17 @@ __device__ void factor_env(const DevTab& T, double* __restrict__ K, double* __re
       }
     }
     __syncthreads();
+    FT(7);
     if (ctl->fail) return;
     // ---- 2. panel solve over the rows this panel reaches ----------------------
-    const int p0 = T.panel_ptr[pb];
-    const int nrows = T.panel_ptr[pb + 1] - p0;
+    const int p0 = ks.pptr[pb];
+    const int nrows = ks.pptr[pb + 1] - p0;
     for (int rr = tid; rr < nrows; rr += NT) {
-      const int r = T.panel_rows[p0 + rr];
-      const int rb = T.env_ptr[r] - T.env_first[r];
+      const int r = ks.prow[p0 + rr];
+      const int rb = ks.eptr[r] - ks.efirst[r];
+      double sg[NB];
+#pragma unroll
+      for (int c = 0; c < NB; ++c) sg[c] = (c < nb) ? ks.sgn[kb + c] : 1.0;
       rbase[rr] = rb; rrow[rr] = r;
       double* Kr = K + rb + kb;
       double a[NB];
@@ -226,16 +267,16 @@ __device__ void factor_env(const DevTab& T, double* __restrict__ K, double* __re
         if (c < nb) {
           double v = a[c];
           const int rc = kb + c;
-          const double* Lc = K + T.env_ptr[rc] + kb - T.env_first[rc];
+          const double* Lc = K + ks.eptr[rc] + kb - ks.efirst[rc];
 #pragma unroll
           for (int j = 0; j < NB; ++j)
-            if (j < c) v -= (double)T.ksign[kb + j] * a[j] * Lc[j];
-          a[c] = v * invd[rc] * (double)T.ksign[rc];
+            if (j < c) v -= sg[j] * a[j] * Lc[j];
+          a[c] = v * invd[rc] * sg[c];
         }
       }
 #pragma unroll
       for (int c = 0; c < NB; ++c)
-        if (c < nb) { Kr[c] = a[c]; Pt[c * LDP + rr] = a[c]; PtS[c * LDP + rr] = (double)T.ksign[kb + c] * a[c]; }
+        if (c < nb) { Kr[c] = a[c]; Pt[c * LDP + rr] = a[c]; PtS[c * LDP + rr] = sg[c] * a[c]; }
     }
     // zero padding so that vector loads past nrows are harmless
     for (int q = tid; q < NB * 4; q += NT) {
@@ -243,6 +284,7 @@ __device__ void factor_env(const DevTab& T, double* __restrict__ K, double* __re
       if (rr < LDP) { Pt[c * LDP + rr] = 0.0; PtS[c * LDP + rr] = 0.0; }
     }
     __syncthreads();
+    FT(8);
     // ---- 3. trailing update ------------------------------------------------------
     // list positions a (rows) x b (columns), b <= a; super-tiles 32 (a) x 16 (b)
     const int nsa = (nrows + 31) >> 5, nsb = (nrows + 15) >> 4;
@@ -272,7 +314,7 @@ __device__ void factor_env(const DevTab& T, double* __restrict__ K, double* __re
       for (int a = 0; a < 4; ++a) {
         const int la = a0 + a;
         if (la < nrows) {
-          const int ra = rrow[la], rba = rbase[la];
+          const int rba = rbase[la];
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
             const int lb = b0 + b;
@@ -285,11 +327,13 @@ __device__ void factor_env(const DevTab& T, double* __restrict__ K, double* __re
       }
     }
     __syncthreads();
+    FT(9);
   }
+#undef FT
 }
 
 // Back substitution L^T u = w on envelope storage (w = row N of L on entry).
-__device__ void back_solve_env(const DevTab& T, const double* __restrict__ K,
+__device__ void back_solve_env(const DevTab& T, const KS& ks, const double* __restrict__ K,
                                const double* __restrict__ invd, double* __restrict__ w) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = T.N;
@@ -302,19 +346,18 @@ __device__ void back_solve_env(const DevTab& T, const double* __restrict__ K,
         const int rj = kb + j;
         const double uj = __shfl_sync(FULL, wv, j) * invd[rj];
         if (lane == j) wv = uj;
-        else if (lane < j) wv -= K[T.env_ptr[rj] + kb - T.env_first[rj] + lane] * uj;
+        else if (lane < j) wv -= K[ks.eptr[rj] + kb - ks.efirst[rj] + lane] * uj;
       }
       if (lane < nb) w[kb + lane] = wv;
     }
     __syncthreads();
     // columns left of the block: c in [first(block), kb)
-    int cmin = kb;
-    for (int j = 0; j < nb; ++j) cmin = min(cmin, T.env_first[kb + j]);
+    const int cmin = ks.pcmin[pb];
     for (int c = cmin + tid; c < kb; c += NT) {
       double acc = w[c];
       for (int j = 0; j < nb; ++j) {
-        const int rj = kb + j, fj = T.env_first[rj];
-        if (c >= fj) acc -= K[T.env_ptr[rj] + c - fj] * w[rj];
+        const int rj = kb + j, fj = ks.efirst[rj];
+        if (c >= fj) acc -= K[ks.eptr[rj] + c - fj] * w[rj];
       }
       w[c] = acc;
     }
@@ -329,6 +372,7 @@ __global__ void __launch_bounds__(NT, 2)
 omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S) {
   extern __shared__ double sm[];
   __shared__ Ctl ctl;
+  __shared__ double phase_cyc[NPHASE];
   double* K = sm + S.K;
   double* Pt = sm + S.Pt;
   double* PtS = sm + S.PtS;
@@ -345,6 +389,27 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
   double* filt = sm + S.filt;
   const int tid = threadIdx.x;
   const int n = T.n, m = T.m;
+  {  // KKT structure arrays -> shared memory (once per block)
+    double* sgn = sm + S.sgn;
+    int* eptr = reinterpret_cast<int*>(sm + S.eptr);
+    int* efirst = reinterpret_cast<int*>(sm + S.efirst);
+    int* pptr = reinterpret_cast<int*>(sm + S.pptr);
+    int* prow = reinterpret_cast<int*>(sm + S.prow);
+    int* pcmin = reinterpret_cast<int*>(sm + S.pcmin);
+    for (int i = tid; i < T.N; i += NT) sgn[i] = (double)T.ksign[i];
+    for (int i = tid; i < T.N + 2; i += NT) eptr[i] = T.env_ptr[i];
+    for (int i = tid; i < T.N + 1; i += NT) efirst[i] = T.env_first[i];
+    for (int i = tid; i < T.n_panels + 1; i += NT) pptr[i] = T.panel_ptr[i];
+    for (int i = tid; i < T.panel_ptr[T.n_panels]; i += NT) prow[i] = T.panel_rows[i];
+    for (int i = tid; i < T.n_panels; i += NT) pcmin[i] = T.panel_cmin[i];
+  }
+  KS ks;
+  ks.sgn = sm + S.sgn; ks.eptr = reinterpret_cast<const int*>(sm + S.eptr);
+  ks.efirst = reinterpret_cast<const int*>(sm + S.efirst);
+  ks.pptr = reinterpret_cast<const int*>(sm + S.pptr);
+  ks.prow = reinterpret_cast<const int*>(sm + S.prow);
+  ks.pcmin = reinterpret_cast<const int*>(sm + S.pcmin);
+  __syncthreads();
 
   // per-block global scratch (L2 resident)
   double* D = A.dscr + (size_t)blockIdx.x * A.dscr_stride;
@@ -354,6 +419,7 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
   double* wv = sig + m;     double* ds = wv + m;    double* dy = ds + m;
   double* dzL = dy + m;     double* dzU = dzL + m;  double* gt = dzU + m;
   double* st = gt + m;      double* jval = st + m;  double* beq = jval + T.nnz_j;
+  double* jsv = beq + m;
   int* I = A.iscr + (size_t)blockIdx.x * A.iscr_stride;
   int* rt = I;              int* eqidx = rt + m;    int* eqrow = eqidx + m;
 
@@ -368,6 +434,8 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
     const double* lbg = A.lbg + (A.bounds_shared ? 0 : (size_t)inst * m);
     const double* ubg = A.ubg + (A.bounds_shared ? 0 : (size_t)inst * m);
     const bool tracing = (O.trace != 0) && inst == 0 && A.trace != nullptr;
+    long long phase_t0 = clock64();
+    if (tracing && tid == 0) for (int k = 0; k < NPHASE; ++k) phase_cyc[k] = 0.0;
 
     // ---- S1: parameter tape ---------------------------------------------------
     for (int i = tid; i < 1 + T.n_par; i += NT) V[i] = (i == 0) ? 1.0 : par[i - 1];
@@ -469,6 +537,7 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
 
     // =========================== IP iterations ===============================
     for (int iter = 0;; ++iter) {
+      TICK(0);   // setup / previous accept
       // ---- I1: rows: g (kept from trial), Jacobian values, residual terms -------
       double rv[NRED];
       // 0 cinf(max) 1 maxprod(max) 2 minprod(min) 3 viol(max) 4 rsinf(max)
@@ -500,6 +569,7 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
         rv[6] += fabs(yi);
       }
       __syncthreads();   // jval visible to the column pass
+      TICK(1);   // row pass
       // ---- I2: columns: grad f, dual residual ------------------------------------
       for (int j = tid; j < n; j += NT) {
         const double gj = ctl.fsc * eval_slot(T.DF, j, V, xe);
@@ -521,6 +591,7 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
       double mu = ctl.mu;
       const double cmpl0 = n_bounds ? fmax(fabs(maxprod), fabs(minprod)) : 0.0;
       const double E0 = fmax(fmax(dinf / s_d, cinf), cmpl0 / s_c);
+      TICK(2);   // column pass + reduction
       // ---- I3: termination + barrier update (uniform) ---------------------------
       int status = -1;
       if (!isfinite(E0)) status = OMG_INVALID_NUMBER_DETECTED;
@@ -559,6 +630,7 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
       }
       __syncthreads();
       const double tau = ctl.tau;
+      TICK(3);   // barrier logic
       // ---- I4: Sigma and w = Sigma r_d + phi_s ------------------------------------
       for (int i = tid; i < m; i += NT) {
         const int r = rt[i];
@@ -571,10 +643,12 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
         }
         sig[i] = sg;
         wv[i] = (r & 4) ? y[i] : (sg * rd + ph);
+        for (int sl = T.jrow_ptr[i]; sl < T.jrow_ptr[i + 1]; ++sl) jsv[sl] = sg * jval[sl];
       }
       // ---- I6: Hessian slots into gt-scratch? -> kept in st[] (nnz_w <= m assumed no) ---
       __syncthreads();
 
+      TICK(4);   // sigma pass
       // ---- I7/I8: assemble + factorise, with inertia correction -----------------
       for (;;) {
         for (int q = tid; q < T.env_size; q += NT) K[q] = 0.0;
@@ -582,20 +656,29 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
         // H positions: gather J^T Sigma J (+ delta_w on the diagonal)
         for (int q = tid; q < T.nnz_h; q += NT) {
           double acc = 0.0;
-          for (int e = T.hp_ptr[q]; e < T.hp_ptr[q + 1]; ++e)
-            acc += sig[T.hp_row[e]] * jval[T.hp_s1[e]] * jval[T.hp_s2[e]];
+          for (int e = T.hp_ptr[q]; e < T.hp_ptr[q + 1]; ++e) {
+            const unsigned pk = __ldg(T.hp_pack + e);
+            acc += jsv[pk & 0xffffu] * jval[pk >> 16];
+          }
           if (T.hrow[q] == T.hcol[q]) acc += ctl.delta_w;
           K[T.hdst[q]] = acc;
         }
         __syncthreads();
+        TICK(5);   // zero + H gather
         // Lagrangian Hessian W (lambda = y*dsc, objective factor fsc)
         for (int q = tid; q < T.nnz_w; q += NT) {
           double acc = 0.0;
           const TL& L = T.W;
           for (int t = L.ptr[q]; t < L.ptr[q + 1]; ++t) {
-            double v = L.coef[t] * V[L.cidx[t]];
-            for (int k = 0; k < L.width; ++k) v *= xe[L.xi[t * L.width + k]];
-            const int lr = L.lrow[t];
+            double v; int lr;
+            if (L.pk) {
+              const PTerm pt = load_pterm(L.pk + t);
+              v = pt.coef * V[pt.cidx] * xe[pt.x0] * xe[pt.x1]; lr = pt.lrow;
+            } else {
+              v = L.coef[t] * V[L.cidx[t]];
+              for (int k = 0; k < L.width; ++k) v *= xe[L.xi[t * L.width + k]];
+              lr = L.lrow[t];
+            }
             v *= (lr < m) ? (y[lr] * dsc[lr]) : ctl.fsc;
             acc += v;
           }
@@ -607,7 +690,7 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
           diag0[pj] = fabs(K[T.kdiag[pj]]);
         }
         // equality border + right-hand-side row
-        const int rhs0 = T.env_ptr[N];
+        const int rhs0 = ks.eptr[N];
         for (int k = tid; k < n_eq; k += NT) {
           const int i = eqrow[k], pk = T.pos_eq[k];
           for (int sl = T.jrow_ptr[i]; sl < T.jrow_ptr[i + 1]; ++sl) K[T.jdst[sl]] = jval[sl];
@@ -625,8 +708,10 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
         }
         if (tid == 0) { ctl.fail = 0; ctl.eq_fail = 0; }
         __syncthreads();
-        factor_env(T, K, Pt, PtS, S.LDP, diag0, invd, rbase, &ctl);
+        TICK(6);   // W + border + rhs
+        factor_env(T, ks, K, Pt, PtS, S.LDP, diag0, invd, rbase, &ctl, tracing ? phase_cyc : nullptr);
         __syncthreads();
+        phase_t0 = clock64();
         if (!ctl.fail) break;
         // inertia correction (IPOPT algorithm IC on the condensed matrix)
         if (tid == 0) {
@@ -649,9 +734,10 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
       }
       if (tid == 0 && ctl.delta_w > 0.0) ctl.delta_w_last = ctl.delta_w;
       // ---- I9: solve -----------------------------------------------------------
-      for (int j = tid; j < N; j += NT) u[j] = K[T.env_ptr[N] + j];
+      for (int j = tid; j < N; j += NT) u[j] = K[ks.eptr[N] + j];
       __syncthreads();
-      back_solve_env(T, K, invd, u);
+      back_solve_env(T, ks, K, invd, u);
+      TICK(10);  // back substitution
       for (int j = tid; j < n; j += NT) dx[j] = u[T.pos_var[j]];
       for (int k = tid; k < n_eq; k += NT) dx[n + k] = u[T.pos_eq[k]];
       __syncthreads();
@@ -685,6 +771,7 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
       for (int j = tid; j < n; j += NT) sv[2] += gf[j] * dx[j];
       block_reduce<4>(sv, sop, red);
       const double a_p = sv[0], a_d = sv[1], gphi = sv[2];
+      TICK(11);  // step pass
       // ---- I11: filter line search --------------------------------------------
       const double theta0 = ctl.theta, phi0 = ctl.phi;
       double a_min;
@@ -760,6 +847,7 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
         }
         ctl.f = ft; ctl.alpha = alpha;
       }
+      TICK(12);  // line search
       // ---- I12: accept -------------------------------------------------------------
       for (int j = tid; j < n; j += NT) xe[j] = xt[j];
       for (int i = tid; i < m; i += NT) {
@@ -782,6 +870,11 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
     __syncthreads();
     for (int i = tid; i < n; i += NT) A.x[(size_t)inst * n + i] = xe[i];
     for (int i = tid; i < m; i += NT) A.lam[(size_t)inst * m + i] = y[i] * dsc[i] / ctl.fsc;
+    if (tracing && tid == 0) {
+      TICK(13);
+      double* tr = A.trace + (TRACE_ROWS - 2) * TRACE_COLS;
+      for (int k = 0; k < NPHASE; ++k) tr[k] = phase_cyc[k];
+    }
     if (tid == 0) {
       A.f[inst] = ctl.f / ctl.fsc;
       A.status[inst] = ctl.status;
@@ -850,7 +943,7 @@ static const Tp* upload(omg_problem* h, const Tp* src, size_t count, bool* ok) {
   return (const Tp*)d;
 }
 
-static TL upload_tl(omg_problem* h, const omg_termlist& L, bool* ok) {
+static TL upload_tl(omg_problem* h, const omg_termlist& L, int n_one, bool* ok) {
   TL t;
   t.n_out = L.n_out; t.n_terms = L.n_terms; t.width = L.width;
   t.ptr = upload(h, L.ptr, (size_t)L.n_out + 1, ok);
@@ -858,6 +951,18 @@ static TL upload_tl(omg_problem* h, const omg_termlist& L, bool* ok) {
   t.cidx = upload(h, L.cidx, (size_t)L.n_terms, ok);
   t.xi = upload(h, L.xi, (size_t)L.n_terms * L.width, ok);
   t.lrow = L.lrow ? upload(h, L.lrow, (size_t)L.n_terms, ok) : nullptr;
+  t.pk = nullptr;
+  if (L.width <= 2) {
+    std::vector<PTerm> pk((size_t)L.n_terms + 1);
+    for (int k = 0; k < L.n_terms; ++k) {
+      PTerm& q = pk[k];
+      q.coef = L.coef[k]; q.cidx = (unsigned short)L.cidx[k];
+      q.x0 = (unsigned short)(L.width >= 1 ? L.xi[(size_t)k * L.width] : n_one);
+      q.x1 = (unsigned short)(L.width >= 2 ? L.xi[(size_t)k * L.width + 1] : n_one);
+      q.lrow = (unsigned short)(L.lrow ? L.lrow[k] : 0);
+    }
+    t.pk = upload(h, pk.data(), pk.size(), ok);
+  }
   return t;
 }
 
@@ -905,13 +1010,25 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
   T.kdiag = upload(h, tb->kkt_diag, tb->kkt_n, &ok);
   T.panel_ptr = upload(h, tb->kkt_panel_ptr, (size_t)T.n_panels + 1, &ok);
   T.panel_rows = upload(h, tb->kkt_panel_rows, tb->n_panel_rows, &ok);
+  {
+    std::vector<int> cmin(T.n_panels > 0 ? T.n_panels : 1);
+    for (int pb = 0; pb < T.n_panels; ++pb) {
+      int c = pb * NB;
+      for (int r = pb * NB; r < tb->kkt_n && r < (pb + 1) * NB; ++r) c = tb->env_first[r] < c ? tb->env_first[r] : c;
+      cmin[pb] = c;
+    }
+    T.panel_cmin = upload(h, cmin.data(), cmin.size(), &ok);
+  }
   T.tape_func = upload(h, tb->tape_func, tb->n_tape, &ok);
   T.tape_ptr = upload(h, tb->tape_ptr, (size_t)tb->n_tape + 1, &ok);
   T.tape_coef = upload(h, tb->tape_coef, tb->n_tape_terms, &ok);
   T.tape_fac = upload(h, tb->tape_fac, (size_t)tb->n_tape_terms * 4, &ok);
   T.level_ptr = upload(h, tb->level_ptr, (size_t)tb->n_levels + 1, &ok);
-  T.G = upload_tl(h, tb->G, &ok); T.F = upload_tl(h, tb->F, &ok); T.DF = upload_tl(h, tb->DF, &ok);
-  T.J = upload_tl(h, tb->J, &ok); T.W = upload_tl(h, tb->W, &ok);
+  const bool small_idx = tb->n < 65535 && tb->n_v < 65536 && tb->m < 65535 && tb->nnz_j < 65536;
+  if (!small_idx) { set_err("problem too large for 16-bit packed indices"); ok = false; }
+  T.G = upload_tl(h, tb->G, tb->n, &ok); T.F = upload_tl(h, tb->F, tb->n, &ok);
+  T.DF = upload_tl(h, tb->DF, tb->n, &ok);
+  T.J = upload_tl(h, tb->J, tb->n, &ok); T.W = upload_tl(h, tb->W, tb->n, &ok);
   T.jrow = upload(h, tb->jrow, tb->nnz_j, &ok); T.jcol = upload(h, tb->jcol, tb->nnz_j, &ok);
   T.jrow_ptr = upload(h, tb->jrow_ptr, (size_t)tb->m + 1, &ok);
   {  // CSC view of the Jacobian pattern
@@ -929,6 +1046,12 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
   T.hp_ptr = upload(h, tb->hp_ptr, (size_t)tb->nnz_h + 1, &ok);
   T.hp_s1 = upload(h, tb->hp_s1, tb->n_hp, &ok); T.hp_s2 = upload(h, tb->hp_s2, tb->n_hp, &ok);
   T.hp_row = upload(h, tb->hp_row, tb->n_hp, &ok);
+  {
+    std::vector<unsigned> pack((size_t)tb->n_hp + 1);
+    for (int e = 0; e < tb->n_hp; ++e)
+      pack[e] = (unsigned)tb->hp_s1[e] | ((unsigned)tb->hp_s2[e] << 16);
+    T.hp_pack = upload(h, pack.data(), pack.size(), &ok);
+  }
   {  // every diagonal (j,j) must be part of the H pattern (delta_w lands there)
     std::vector<char> has(tb->n, 0);
     for (int q = 0; q < tb->nnz_h; ++q) if (tb->hrow[q] == tb->hcol[q]) has[tb->hrow[q]] = 1;
@@ -948,6 +1071,9 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
   S.gf = take(T.n);
   S.diag0 = take(N + 1); S.invd = take(N + 1); S.V = take(T.n_v);
   S.red = take(NWARP * NRED); S.filt = take(2 * MAXF);
+  S.sgn = take(N); S.eptr = take((N + 2 + 1) / 2); S.efirst = take((N + 1 + 1) / 2);
+  S.pptr = take((T.n_panels + 1 + 1) / 2); S.prow = take((tb->n_panel_rows + 1) / 2);
+  S.pcmin = take((T.n_panels + 1) / 2);
   S.total = off;
   h->smem_bytes = (size_t)off * sizeof(double);
   cudaDeviceProp prop;
@@ -971,7 +1097,7 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, omg_ipm_kernel, NT, h->smem_bytes);
     h->ctas_per_sm = occ > 0 ? occ : 1;
-    h->dscr_stride = 17 * T.m + T.nnz_j + 8;
+    h->dscr_stride = 18 * T.m + 2 * T.nnz_j + 8;
     h->iscr_stride = 2 * T.m + T.n_eq + 8;
     if (cudaMalloc(&h->counter, sizeof(int)) != cudaSuccess) ok = false;
     if (cudaMalloc(&h->trace, sizeof(double) * TRACE_ROWS * TRACE_COLS) != cudaSuccess) ok = false;

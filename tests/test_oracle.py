@@ -52,18 +52,46 @@ def test_oracle_optimum_matches_independent_slsqp():
     assert np.abs(G['config1_loose_x'][0][:26] - G['config1_slsqp_x'][:26]).max() < 1e-3
 
 
-def test_generalised_cholesky_solves_saddle_system():
+def test_signed_cholesky_solves_permuted_saddle_system():
+    """K = L S L^T with equality rows interleaved after their variables."""
     rng = np.random.default_rng(0)
     n, ne = 12, 3
     A = rng.standard_normal((n, n))
     H = A @ A.T + n * np.eye(n)
-    Jc = rng.standard_normal((ne, n))
+    Jc = np.zeros((ne, n))
+    for k in range(ne):
+        Jc[k, 3 * k:3 * k + 4] = rng.standard_normal(4)
     K = np.block([[H, Jc.T], [Jc, np.zeros((ne, ne))]])
-    ok, L, eqf = ipm_ref._gen_cholesky(K, n, 1e-12)
+    order = list(range(4)) + [n] + list(range(4, 7)) + [n + 1] + \
+        list(range(7, 10)) + [n + 2] + list(range(10, n))
+    sign = np.array([1.0 if v < n else -1.0 for v in order])
+    Kp = K[np.ix_(order, order)]
+    ok, L, eqf = ipm_ref._signed_cholesky(Kp, sign, 1e-12)
     assert ok and not eqf
+    assert np.abs(L @ np.diag(sign) @ L.T - Kp).max() < 1e-10
     rhs = rng.standard_normal(n + ne)
-    u = ipm_ref._gen_solve(L, n, rhs)
+    u = np.empty(n + ne)
+    u[order] = ipm_ref._signed_solve(L, sign, rhs[order])
     assert np.abs(K @ u - rhs).max() < 1e-10
-    Kbad = K.copy()
-    Kbad[:n, :n] -= 100 * np.eye(n)
-    assert not ipm_ref._gen_cholesky(Kbad, n, 1e-12)[0]
+    Kbad = Kp.copy()
+    Kbad[0, 0] -= 1000.0
+    assert not ipm_ref._signed_cholesky(Kbad, sign, 1e-12)[0]
+
+
+def test_kkt_structure_is_consistent(cfg1):
+    tb = cfg1.father.tables
+    N = tb.kkt_n
+    pos = np.r_[tb.kkt_pos_var, tb.kkt_pos_eq]
+    assert sorted(pos) == list(range(N))
+    assert np.all(tb.env_first[:N] % 16 == 0) and np.all(tb.env_first[:N] <= np.arange(N))
+    assert tb.env_size == tb.env_ptr[-1] and tb.env_size < (N + 1) * (N + 2) // 2
+    # every equality row sits after all variables it couples (negative pivot)
+    for k, i in enumerate(tb.kkt_eq_rows):
+        cols = tb.jcol[tb.jrow_ptr[i]:tb.jrow_ptr[i + 1]]
+        assert tb.kkt_pos_eq[k] > tb.kkt_pos_var[cols].max()
+    # every H entry and border entry lies inside the envelope
+    for q in range(tb.nnz_h):
+        a, b = tb.kkt_pos_var[tb.hrow[q]], tb.kkt_pos_var[tb.hcol[q]]
+        hi, lo = max(a, b), min(a, b)
+        assert lo >= tb.env_first[hi]
+        assert tb.kkt_hdst[q] == tb.env_ptr[hi] + lo - tb.env_first[hi]

@@ -29,3 +29,11 @@ print('max|x_gpu - x_twin| =', np.abs(res['x'][0] - ref.x).max(), ' lam:', np.ab
 for b in range(1, min(B, 4)):
     r = ipm_ref.solve(tb, X0[b], P[b])
     print(b, 'twin', r.return_status, r.iters, 'gpu', res['status'][b], res['iters'][b], 'dx', np.abs(res['x'][b] - r.x).max())
+ph = slv.trace(512)[510:512].reshape(-1)
+names = ['setup/accept', 'row pass', 'col pass+reduce', 'barrier logic', 'sigma pass', 'zero+H gather',
+         'W+border+rhs', 'factor:diag', 'factor:panel', 'factor:trailing', 'back solve', 'step pass',
+         'line search', 'tail']
+tot = ph[:14].sum()
+print('phase cycles of instance 0 (total %.0f, %d iterations -> %.0f cycles/iter):' % (tot, res['iters'][0], tot / max(1, res['iters'][0])))
+for nme, c in zip(names, ph):
+    print('  %-16s %12.0f  %5.1f%%' % (nme, c, 100 * c / tot))
