@@ -77,8 +77,8 @@ typedef struct omg_tables {
   const double* lbg; const double* ubg;
   /* condensed KKT K = [[H,Jc^T],[Jc,-dc I]] = L S L^T: fill-reducing symmetric
    * permutation, signs S, lower envelope (row i stored from env_first[i], a
-   * multiple of 16, to i; row kkt_n = right-hand side) and the rows reached by
-   * each 16-column panel (lowering.build_kkt_structure) */
+   * multiple of 8, to i; row kkt_n = right-hand side) and the rows reached by
+   * each 8-column panel (lowering.build_kkt_structure) */
   int32_t kkt_n, kkt_n_eq, env_size, n_panel_rows, max_panel_rows;
   const int32_t* kkt_eq_rows;   /* [kkt_n_eq] constraint rows that are equalities */
   const int32_t* kkt_pos_var;   /* [n] permuted index of variable j */

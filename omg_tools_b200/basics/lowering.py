@@ -371,7 +371,7 @@ def _build_kkt_pattern(tb):
 # ---------------------------------------------------------------------------
 # KKT ordering + envelope (skyline) structure
 # ---------------------------------------------------------------------------
-KKT_NB = 16      # panel width of the blocked factorisation (csrc/omg_b200.cu)
+KKT_NB = 8       # panel width of the blocked factorisation (csrc/omg_b200.cu)
 
 
 def _envelope_first(adj_lower_rows, perm_pos, N):
@@ -466,7 +466,8 @@ def build_kkt_structure(tb, hint=None):
     width[N] = N                         # rhs row has no diagonal entry
     ptr = np.concatenate([[0], np.cumsum(width)]).astype(np.int32)
     tb.env_first, tb.env_ptr = first_all, ptr
-    tb.env_size = int(ptr[-1])
+    tb.env_size = int(ptr[-1])            # natural (unpadded) row widths spread the
+    # rows of a panel over the shared-memory banks
 
     def env(i, j):
         return int(ptr[i] + (j - first_all[i]))

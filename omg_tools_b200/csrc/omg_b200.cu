@@ -1,69 +1,79 @@
 // omg_b200.cu -- batched primal-dual interior-point solve of OMG-tools' spline
-// NLP on B200 (sm_100a).  One thread block per problem instance; the condensed
-// KKT matrix lives packed in shared memory for the whole solve.
+// NLP on B200 (sm_100a).  One 512-thread block per problem instance; the whole
+// per-instance state (KKT envelope, Jacobian values, iterate vectors) lives in
+// shared memory for the duration of the solve, constant tables stream from L2.
 //
 // Replaces the CasADi+IPOPT call of the reference (omgtools/problems/
 // problem.py:113, optilayer.py:49-60).  Algorithm = oracle/ipm_ref.py (IPOPT
 // semantics, Waechter & Biegler 2006); tables = basics/lowering.py.
 //
-// Kernel phases per interior-point iteration (all inside one launch):
-//   rows   : g, J slots, residuals, error terms        (thread per constraint row)
-//   cols   : grad f, dual residual J^T y               (thread per variable)
-//   barrier: convergence test / monotone mu update     (uniform scalar code)
-//   assem  : H = W + J^T Sigma J gathered into packed K, equality border, rhs row
-//   factor : blocked Cholesky (16-column panels, warp-shuffle diagonal block,
-//            4x4 register-tiled trailing update), rhs eliminated as extra row
-//   solve  : blocked back substitution
-//   step   : ds, dy, dz, fraction-to-boundary, filter line search, update
+// Design rules (from tools/ubench/lat.cu on B200: DFMA 8 cyc, LDS 29, SHFL.64 27,
+// rsqrt 62, __syncthreads 28, dependent LDG ~525 cycles):
+//   * no dependent chains through global memory: every pass reads one record
+//     per work item (row / column / H position / W slot) and then streams
+//     contiguous 32-byte term records with independent loads;
+//   * the sequential part of the factorisation (8x8 diagonal blocks, 8x8
+//     triangular solves) runs in the registers of a single thread -- no
+//     shuffles, little code;
+//   * shared-memory placement is adaptive: arrays that do not fit fall back to
+//     an L2-resident per-block scratch (generic pointers, same code path).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
 #include <math.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 
 #include "../../include/omg_b200.h"
 
-#define NT 256            // threads per block
+#define NT ((int)blockDim.x)   // threads per block: 512 (1 block/SM) or 256 (2 blocks/SM)
 #define NWARP (NT / 32)
-#define NB 16             // Cholesky panel width
+#define MAX_NT 512
+#define MAX_NWARP (MAX_NT / 32)
+#define NB 8              // panel width (== lowering.KKT_NB)
 #define MAXF 32           // filter capacity
 #define NRED 12           // values per fused block reduction
 #define FULL 0xffffffffu
 #define TRACE_COLS 8
 #define TRACE_ROWS 512
+#define MAXW 5            // max x-factors per term record
 
 // ---------------------------------------------------------------------------
-// device-side table views
+// table records (device)
 // ---------------------------------------------------------------------------
-struct PTerm {                     // packed term (width <= 2): one 16-byte load
-  double coef; unsigned short cidx, x0, x1, lrow;
+struct __align__(16) PTerm {       // 32 bytes: coef * V[cidx] * prod x_ext[x[k]]
+  double coef;
+  unsigned short cidx, aux;        // aux: lambda row (W terms) or slot offset in row (J terms)
+  unsigned short x[MAXW];
+  unsigned short pad[5];
 };
+struct __align__(16) RowRec { int g0, g1, jt0, jt1, s0, ns, pad0, pad1; };  // per constraint row
+struct __align__(16) HqRec { int dst, p0, p1, diag; };                      // per H position
+struct __align__(16) WRec { int dst, t0, t1, pad; };                        // per Hessian slot
 
-struct TL {
-  int n_out, n_terms, width;
-  const int* ptr; const double* coef; const int* cidx; const int* xi; const int* lrow;
-  const PTerm* pk;                 // non-null when width <= 2
-};
+enum { A_JVAL = 0, A_SIG, A_JSV, A_G, A_S, A_Y, A_ZU, A_DSC, A_SU, A_DS, A_DY, A_DZU, A_GT,
+       A_ST, A_WV, A_ZL, A_SL, A_DZL, A_BEQ, N_ARR };
 
 struct DevTab {
-  int n, m, n_par, n_v, n_tape, n_levels, nnz_j, nnz_w, nnz_h, n_hp;
-  int n_eq, N;                     // structural equality rows; N = n + n_eq (order of K)
-  int env_size, n_panels, max_panel_rows;
-  const int *eq_rows, *pos_var, *pos_eq, *ksign, *env_first, *env_ptr, *hdst, *jdst, *kdiag,
-            *panel_ptr, *panel_rows, *panel_cmin;
-  const unsigned* hp_pack;         // pair list packed: s1 | s2 << 16 (nnz_j < 65536)
+  int n, m, n_par, n_v, n_tape, n_levels, nnz_j, nnz_w, nnz_h, n_eq, N;
+  int env_size, n_panels, max_panel_rows, n_panel_rows, n_f;
   const int *tape_func, *tape_ptr, *tape_fac, *level_ptr; const double* tape_coef;
-  TL G, F, DF, J, W;
-  const int *jrow, *jcol, *jrow_ptr, *jcol_ptr, *jcol_slot;
-  const int *wrow, *wcol, *w2h, *hrow, *hcol, *hp_ptr, *hp_s1, *hp_s2, *hp_row;
+  const PTerm *Gt, *Jt, *Wt, *Ft, *DFt;
+  const RowRec* rowrec; const WRec* wrec; const HqRec* hq; const unsigned* hpack;
+  const int *dfptr;                     // [n+1] grad-f term ranges per column
+  const int *colptr; const unsigned* colrec;   // CSC of J: slot | row << 16
+  const unsigned short* jcol16;         // [nnz_j] column of each slot
+  const int *eq_rows, *pos_var, *pos_eq, *ksign, *env_first, *env_ptr, *jdst, *kdiag,
+            *panel_ptr, *panel_rows, *panel_cmin;
 };
 
 struct Smem {                      // offsets in doubles
-  int K, Pt, PtS, xe, xt, dx, u, gf, diag0, invd, V, red, filt, rbase, total;
-  int sgn, eptr, efirst, pptr, prow, pcmin;   // structure arrays cached in shared memory
-  int LDP;
+  int K, Pt, PtS, Ld, xe, xt, dx, u, gf, diag0, invd, V, red, filt, rbase, rt8;
+  int sgn, eptr, efirst, pptr, prow, pcmin;
+  int arr[N_ARR];                  // >= 0: shared offset; < 0: -(scratch offset + 1)
+  int LDP, total;
 };
 
 struct Batch {
@@ -76,8 +86,8 @@ struct Batch {
 
 struct Ctl {                       // uniform per-block control scalars
   double mu, tau, theta_max, theta_min, delta_w, delta_w_last, delta_c;
-  double alpha, a_p, a_d, theta, phi, gphi, f, ft, fsc;
-  int n_eq, n_bounds, iter, status, fail, eq_fail, first_try, nfilt, accepted, inst;
+  double alpha, theta, phi, f, fsc;
+  int n_eq, n_bounds, iter, status, fail, eq_fail, first_try, nfilt, inst;
 };
 
 // IPOPT constants not exposed as options (oracle/ipm_ref.py DEFAULTS)
@@ -116,33 +126,24 @@ enum { OP_MAX = 0, OP_MIN = 1, OP_SUM = 2 };
 #define TICK(k) do { if (tracing && threadIdx.x == 0) { const long long t_ = clock64(); \
   phase_cyc[k] += (double)(t_ - phase_t0); phase_t0 = t_; } } while (0)
 
-__device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }
-
-__device__ __forceinline__ PTerm load_pterm(const PTerm* p) {
-  const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
-  PTerm t;
-  t.coef = __hiloint2double((int)r.y, (int)r.x);
-  t.cidx = (unsigned short)(r.z & 0xffffu); t.x0 = (unsigned short)(r.z >> 16);
-  t.x1 = (unsigned short)(r.w & 0xffffu); t.lrow = (unsigned short)(r.w >> 16);
-  return t;
+__device__ __forceinline__ double term_value(const PTerm* __restrict__ p, const double* __restrict__ V,
+                                             const double* __restrict__ xe, int* aux) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint4 b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+  double v = __hiloint2double((int)a.y, (int)a.x) * V[a.z & 0xffffu];
+  *aux = (int)(a.z >> 16);
+  v *= xe[a.w & 0xffffu]; v *= xe[a.w >> 16];
+  v *= xe[b.x & 0xffffu]; v *= xe[b.x >> 16];
+  v *= xe[b.y & 0xffffu];
+  return v;
 }
 
-__device__ __forceinline__ double eval_slot(const TL& L, int s, const double* __restrict__ V,
-                                            const double* __restrict__ xe) {
+__device__ __forceinline__ double eval_range(const PTerm* __restrict__ t, int lo, int hi,
+                                             const double* __restrict__ V, const double* __restrict__ xe) {
   double acc = 0.0;
-  const int lo = L.ptr[s], hi = L.ptr[s + 1], w = L.width;
-  if (L.pk) {
-    for (int t = lo; t < hi; ++t) {
-      const PTerm q = load_pterm(L.pk + t);
-      acc += q.coef * V[q.cidx] * xe[q.x0] * xe[q.x1];
-    }
-    return acc;
-  }
-  for (int t = lo; t < hi; ++t) {
-    double v = L.coef[t] * V[L.cidx[t]];
-    for (int k = 0; k < w; ++k) v *= xe[L.xi[t * w + k]];
-    acc += v;
-  }
+  int aux;
+#pragma unroll 4
+  for (int k = lo; k < hi; ++k) acc += term_value(t + k, V, xe, &aux);
   return acc;
 }
 
@@ -165,7 +166,6 @@ __device__ __forceinline__ void block_reduce(double (&v)[NR], const int (&op)[NR
 #pragma unroll
   for (int r = 0; r < NR; ++r) {
     double a = red[r];
-#pragma unroll
     for (int w = 1; w < NWARP; ++w) {
       double o = red[w * NR + r];
       if (op[r] == OP_MAX) a = fmax(a, o);
@@ -181,149 +181,169 @@ __device__ __forceinline__ bool cmp_le(double lhs, double rhs, double base) {
   return lhs - rhs <= 10.0 * DBL_EPS * fabs(base);
 }
 
+extern __shared__ double sm[];
+
+// shared-memory copies of the KKT structure arrays, addressed from the block's
+// dynamic shared array so the compiler emits LDS (not generic loads)
+#define KS_SGN    (sm + S.sgn)
+#define KS_EPTR   (reinterpret_cast<const int*>(sm + S.eptr))
+#define KS_EFIRST (reinterpret_cast<const int*>(sm + S.efirst))
+#define KS_PPTR   (reinterpret_cast<const int*>(sm + S.pptr))
+#define KS_PROW   (reinterpret_cast<const int*>(sm + S.prow))
+#define KS_PCMIN  (reinterpret_cast<const int*>(sm + S.pcmin))
+
 // ---------------------------------------------------------------------------
 // Blocked right-looking factorisation K = L S L^T on envelope storage.
 //   row i (permuted order) is stored from column first[i] (multiple of NB) to i
 //   at K[env_ptr[i] + j - first[i]]; row N is the right-hand side (never a
 //   pivot), so after the sweep it holds S L^{-1} r.
-// Per 16-column panel: (1) warp 0 factors the diagonal block in registers with
-// shuffles, (2) one thread per reached row does the panel solve, (3) the
-// trailing update runs over the rows the panel reaches, 32x16 super-tiles per
-// warp, 4x4 register tiles per lane with 128-bit shared loads.
+// Per 8-column panel: (1) ONE thread factors the 8x8 diagonal block in
+// registers, (2) one thread per reached row does the panel solve, (3) the
+// rank-8 trailing update runs over 2x2 register tiles of the reached rows.
 // Pivot j must satisfy sign[j]*pivot > PIV_TOL*|K_jj| (variables) or > 0
 // (equality rows); otherwise ctl->fail (eq_fail for an equality pivot).
 // ---------------------------------------------------------------------------
-struct KS {   // shared-memory copies of the KKT structure arrays
-  const double* sgn; const int* eptr; const int* efirst; const int* pptr; const int* prow;
-  const int* pcmin;
-};
-
-__device__ void factor_env(const DevTab& T, const KS& ks, double* __restrict__ K, double* __restrict__ Pt,
-                           double* __restrict__ PtS, int LDP, const double* __restrict__ diag0,
-                           double* __restrict__ invd, int* __restrict__ rbase, Ctl* ctl, double* pc) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+__device__ __forceinline__ void factor_env(const DevTab& T, const Smem& S, Ctl* ctl, double* pc) {
+  const int tid = threadIdx.x;
   const int N = T.N;
+  const int LDP = S.LDP;
+  double* K = sm + S.K; double* Pt = sm + S.Pt; double* PtS = sm + S.PtS; double* Ld = sm + S.Ld;
+  const double* diag0 = sm + S.diag0; double* invd = sm + S.invd;
+  int* rbase = reinterpret_cast<int*>(sm + S.rbase);
   int* rrow = rbase + LDP;
+  const double* sgn = KS_SGN; const int* eptr = KS_EPTR; const int* efirst = KS_EFIRST;
+  const int* pptr = KS_PPTR; const int* prow = KS_PROW;
   long long t0 = clock64();
 #define FT(k) do { if (pc && tid == 0) { const long long t_ = clock64(); pc[k] += (double)(t_ - t0); t0 = t_; } } while (0)
   for (int pb = 0; pb < T.n_panels; ++pb) {
     const int kb = pb * NB;
     const int nb = min(NB, N - kb);
-    // ---- 1. diagonal block (warp 0) ------------------------------------------
-    if (warp == 0) {
-      double a[NB];
-      const int row = kb + lane;
-      const int base = (lane < nb) ? (ks.eptr[row] + kb - ks.efirst[row]) : 0;
+    // ---- 1. diagonal block: staged into Ld (64 threads), factored by ONE thread in
+    //         registers (branch-free pivots), scattered back by 64 threads ----------
+    if (tid < NB * NB) {
+      const int r = tid >> 3, c = tid & 7;
+      double v = 0.0;
+      if (r < nb && c <= r) v = K[eptr[kb + r] + kb - efirst[kb + r] + c];
+      Ld[tid] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double a[NB][NB];
 #pragma unroll
-      for (int c = 0; c < NB; ++c) a[c] = (lane < nb && c <= lane) ? K[base + c] : 0.0;
-      const double my_s = (lane < nb) ? ks.sgn[row] : 1.0;
-      const double my_thr = (lane < nb && my_s > 0.0) ? PIV_TOL * fmax(diag0[row], 1e-300) : 0.0;
-      bool ok = true;
+      for (int r = 0; r < NB; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) a[r][c] = Ld[r * NB + c];
+      bool bad = false, bad_eq = false;
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
-        if (j < nb && ok) {
-          const double sj = __shfl_sync(FULL, my_s, j);
-          const double thr = __shfl_sync(FULL, my_thr, j);
-          const double d = sj * __shfl_sync(FULL, a[j], j);
-          if (!(d > thr) || !isfinite(d)) {
-            ok = false;
-            if (lane == 0) { ctl->fail = 1; ctl->eq_fail = (sj < 0.0) ? 1 : 0; }
-          } else {
-            const double inv = rsqrt(d);   // 62 cycles on B200 (tools/ubench/lat.cu), faster than a float seed + Newton
-            if (lane == j) { a[j] = d * inv; invd[kb + j] = inv; }
-            else if (lane > j) a[j] *= inv * sj;
+        // rows >= nb are zero-padded: give them a unit pivot so the arithmetic stays finite
+        const bool live = (j < nb);
+        const double sj = live ? sgn[kb + j] : 1.0;
+        const double d = live ? sj * a[j][j] : 1.0;
+        const double thr = (live && sj > 0.0) ? PIV_TOL * fmax(diag0[kb + j], 1e-300) : 0.0;
+        const bool fail_j = !(d > thr) || !(d < 1e300);
+        if (fail_j && !bad) { bad = true; bad_eq = (sj < 0.0); }
+        const double inv = rsqrt(d);
+        a[j][j] = d * inv;
+        if (live) invd[kb + j] = inv;
+        const double f = inv * sj;
 #pragma unroll
-            for (int k = j + 1; k < NB; ++k) {
-              const double lkj = __shfl_sync(FULL, a[j], k);
-              if (lane >= k) a[k] -= sj * a[j] * lkj;
-            }
-          }
+        for (int r = j + 1; r < NB; ++r) a[r][j] *= f;
+#pragma unroll
+        for (int r = j + 1; r < NB; ++r) {
+          const double lr = sj * a[r][j];
+#pragma unroll
+          for (int c = j + 1; c <= r; ++c) a[r][c] -= lr * a[c][j];
         }
       }
-      if (ok) {
+      if (bad) { ctl->fail = 1; ctl->eq_fail = bad_eq ? 1 : 0; }
 #pragma unroll
-        for (int c = 0; c < NB; ++c) if (lane < nb && c <= lane) K[base + c] = a[c];
-      }
+      for (int r = 0; r < NB; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) Ld[r * NB + c] = a[r][c];
+    }
+    __syncthreads();
+    if (!ctl->fail && tid < NB * NB) {
+      const int r = tid >> 3, c = tid & 7;
+      if (r < nb && c <= r) K[eptr[kb + r] + kb - efirst[kb + r] + c] = Ld[tid];
     }
     __syncthreads();
     FT(7);
     if (ctl->fail) return;
     // ---- 2. panel solve over the rows this panel reaches ----------------------
-    const int p0 = ks.pptr[pb];
-    const int nrows = ks.pptr[pb + 1] - p0;
-    for (int rr = tid; rr < nrows; rr += NT) {
-      const int r = ks.prow[p0 + rr];
-      const int rb = ks.eptr[r] - ks.efirst[r];
-      double sg[NB];
-#pragma unroll
-      for (int c = 0; c < NB; ++c) sg[c] = (c < nb) ? ks.sgn[kb + c] : 1.0;
+    const int p0 = pptr[pb];
+    const int nrows = pptr[pb + 1] - p0;
+    if (tid < nrows) {
+      const int rr = tid;
+      const int r = prow[p0 + rr];
+      const int rb = eptr[r] - efirst[r];
       rbase[rr] = rb; rrow[rr] = r;
       double* Kr = K + rb + kb;
-      double a[NB];
+      double a[NB], sg[NB];
 #pragma unroll
-      for (int c = 0; c < NB; ++c) a[c] = (c < nb) ? Kr[c] : 0.0;
+      for (int c = 0; c < NB; ++c) { a[c] = (c < nb) ? Kr[c] : 0.0; sg[c] = (c < nb) ? sgn[kb + c] : 1.0; }
 #pragma unroll
       for (int c = 0; c < NB; ++c) {
         if (c < nb) {
           double v = a[c];
-          const int rc = kb + c;
-          const double* Lc = K + ks.eptr[rc] + kb - ks.efirst[rc];
 #pragma unroll
-          for (int j = 0; j < NB; ++j)
-            if (j < c) v -= sg[j] * a[j] * Lc[j];
-          a[c] = v * invd[rc] * sg[c];
+          for (int j = 0; j < c; ++j) v -= sg[j] * a[j] * Ld[c * NB + j];
+          a[c] = v * invd[kb + c] * sg[c];
         }
       }
 #pragma unroll
-      for (int c = 0; c < NB; ++c)
-        if (c < nb) { Kr[c] = a[c]; Pt[c * LDP + rr] = a[c]; PtS[c * LDP + rr] = sg[c] * a[c]; }
-    }
-    // zero padding so that vector loads past nrows are harmless
-    for (int q = tid; q < NB * 4; q += NT) {
-      const int c = q >> 2, rr = nrows + (q & 3);
-      if (rr < LDP) { Pt[c * LDP + rr] = 0.0; PtS[c * LDP + rr] = 0.0; }
+      for (int c = 0; c < NB; ++c) if (c < nb) Kr[c] = a[c];
+      // panel buffers as double2 [column pair][row]: conflict-free stores here, and
+      // at most 2-way conflicts for the 2x2-tile loads of the trailing update
+      double2* P2 = reinterpret_cast<double2*>(Pt);
+      double2* PS2 = reinterpret_cast<double2*>(PtS);
+#pragma unroll
+      for (int q = 0; q < NB / 2; ++q) {
+        const double v0 = (2 * q < nb) ? a[2 * q] : 0.0, v1 = (2 * q + 1 < nb) ? a[2 * q + 1] : 0.0;
+        P2[q * LDP + rr] = make_double2(v0, v1);
+        PS2[q * LDP + rr] = make_double2(sg[2 * q] * v0, sg[2 * q + 1] * v1);
+      }
+    } else if (tid < nrows + 2 && tid < LDP) {   // zero padding rows for the 2x2 tiles
+      double2* P2 = reinterpret_cast<double2*>(Pt);
+      double2* PS2 = reinterpret_cast<double2*>(PtS);
+#pragma unroll
+      for (int q = 0; q < NB / 2; ++q) { P2[q * LDP + tid] = make_double2(0.0, 0.0); PS2[q * LDP + tid] = make_double2(0.0, 0.0); }
     }
     __syncthreads();
     FT(8);
-    // ---- 3. trailing update ------------------------------------------------------
-    // list positions a (rows) x b (columns), b <= a; super-tiles 32 (a) x 16 (b)
-    const int nsa = (nrows + 31) >> 5, nsb = (nrows + 15) >> 4;
-    const int ty = lane >> 2, tx = lane & 3;
-    for (int st = warp; st < nsa * nsb; st += NWARP) {
-      const int sa = st / nsb, sb = st - sa * nsb;
-      if (sb * 16 > sa * 32 + 31) continue;          // entirely above the diagonal
-      const int a0 = sa * 32 + ty * 4, b0 = sb * 16 + tx * 4;
-      if (a0 >= nrows || b0 >= nrows || b0 > a0 + 3) continue;
-      double acc[4][4];
+    // ---- 3. trailing update: 2x2 tiles over list positions (a >= b) -----------
+    const int nt2 = (nrows + 1) >> 1;
+    const int W = nt2 + 1, H2 = (nt2 + 1) >> 1;
+    for (int t = tid; t < H2 * W; t += NT) {
+      const int ra = t / W, cb = t - ra * W;
+      int ta, tb;
+      if (cb <= ra) { ta = ra; tb = cb; }
+      else { ta = nt2 - 1 - ra; tb = cb - ra - 1; if (ta == ra) continue; }
+      const int a0 = ta * 2, b0 = tb * 2;
+      const double2* A0 = reinterpret_cast<const double2*>(Pt) + a0;
+      const double2* B0 = reinterpret_cast<const double2*>(PtS) + b0;
+      double acc00 = 0.0, acc01 = 0.0, acc10 = 0.0, acc11 = 0.0;
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-      for (int c = 0; c < nb; ++c) {
-        const double2* Pa = reinterpret_cast<const double2*>(Pt + c * LDP + a0);
-        const double2* Pb = reinterpret_cast<const double2*>(PtS + c * LDP + b0);
-        const double2 r01 = Pa[0], r23 = Pa[1], c01 = Pb[0], c23 = Pb[1];
-        const double ri[4] = {r01.x, r01.y, r23.x, r23.y};
-        const double ck[4] = {c01.x, c01.y, c23.x, c23.y};
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) acc[a][b] += ri[a] * ck[b];
+      for (int q = 0; q < NB / 2; ++q) {
+        const double2 x0 = A0[q * LDP], x1 = A0[q * LDP + 1], y0 = B0[q * LDP], y1 = B0[q * LDP + 1];
+        acc00 += x0.x * y0.x; acc00 += x0.y * y0.y;
+        acc01 += x0.x * y1.x; acc01 += x0.y * y1.y;
+        acc10 += x1.x * y0.x; acc10 += x1.y * y0.y;
+        acc11 += x1.x * y1.x; acc11 += x1.y * y1.y;
       }
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int la = a0 + a;
-        if (la < nrows) {
-          const int rba = rbase[la];
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const int lb = b0 + b;
-            if (lb <= la && lb < nrows) {
-              const int cb = rrow[lb];
-              if (cb < N) K[rba + cb] -= acc[a][b];
-            }
-          }
-        }
+      // scatter into K (only b <= a, column < N)
+      const int la0 = a0, la1 = a0 + 1, lb0 = b0, lb1 = b0 + 1;
+      const int c0 = rrow[lb0];
+      const int c1 = (lb1 < nrows) ? rrow[lb1] : N;
+      if (la0 < nrows) {
+        const int rb = rbase[la0];
+        if (lb0 <= la0 && c0 < N) K[rb + c0] -= acc00;
+        if (lb1 <= la0 && c1 < N) K[rb + c1] -= acc01;
+      }
+      if (la1 < nrows) {
+        const int rb = rbase[la1];
+        if (lb0 <= la1 && c0 < N) K[rb + c0] -= acc10;
+        if (lb1 <= la1 && c1 < N) K[rb + c1] -= acc11;
       }
     }
     __syncthreads();
@@ -333,33 +353,54 @@ __device__ void factor_env(const DevTab& T, const KS& ks, double* __restrict__ K
 }
 
 // Back substitution L^T u = w on envelope storage (w = row N of L on entry).
-__device__ void back_solve_env(const DevTab& T, const KS& ks, const double* __restrict__ K,
-                               const double* __restrict__ invd, double* __restrict__ w) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+__device__ __forceinline__ void back_solve_env(const DevTab& T, const Smem& S) {
+  const int tid = threadIdx.x;
   const int N = T.N;
+  const double* K = sm + S.K; const double* invd = sm + S.invd; double* w = sm + S.u;
+  const int* eptr = KS_EPTR; const int* efirst = KS_EFIRST; const int* pcmin = KS_PCMIN;
   for (int pb = T.n_panels - 1; pb >= 0; --pb) {
     const int kb = pb * NB;
     const int nb = min(NB, N - kb);
-    if (warp == 0) {
-      double wv = (lane < nb) ? w[kb + lane] : 0.0;
-      for (int j = nb - 1; j >= 0; --j) {
-        const int rj = kb + j;
-        const double uj = __shfl_sync(FULL, wv, j) * invd[rj];
-        if (lane == j) wv = uj;
-        else if (lane < j) wv -= K[ks.eptr[rj] + kb - ks.efirst[rj] + lane] * uj;
+    // per-row bases of the block (uniform; 16 independent shared loads)
+    int rbs[NB], rfs[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int rj = min(kb + j, N - 1);
+      rfs[j] = efirst[rj]; rbs[j] = eptr[rj] - rfs[j];
+    }
+    if (tid == 0) {        // 8x8 upper-triangular solve in registers
+      double wv[NB], dinv[NB], L[NB][NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        wv[j] = (j < nb) ? w[kb + j] : 0.0;
+        dinv[j] = (j < nb) ? invd[kb + j] : 1.0;
+#pragma unroll
+        for (int c = 0; c < j; ++c) L[j][c] = (j < nb) ? K[rbs[j] + kb + c] : 0.0;
       }
-      if (lane < nb) w[kb + lane] = wv;
+#pragma unroll
+      for (int j = NB - 1; j >= 0; --j) {
+        const double uj = wv[j] * dinv[j];
+        wv[j] = uj;
+#pragma unroll
+        for (int c = 0; c < j; ++c) wv[c] -= L[j][c] * uj;
+      }
+#pragma unroll
+      for (int j = 0; j < NB; ++j) if (j < nb) w[kb + j] = wv[j];
     }
     __syncthreads();
-    // columns left of the block: c in [first(block), kb)
-    const int cmin = ks.pcmin[pb];
+    const int cmin = pcmin[pb];
     for (int c = cmin + tid; c < kb; c += NT) {
-      double acc = w[c];
-      for (int j = 0; j < nb; ++j) {
-        const int rj = kb + j, fj = ks.efirst[rj];
-        if (c >= fj) acc -= K[ks.eptr[rj] + c - fj] * w[rj];
+      double l[NB], uu[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const bool in = (j < nb) && (c >= rfs[j]);
+        l[j] = in ? K[rbs[j] + c] : 0.0;
+        uu[j] = (j < nb) ? w[kb + j] : 0.0;
       }
-      w[c] = acc;
+      double acc0 = w[c], acc1 = 0.0;
+#pragma unroll
+      for (int j = 0; j < NB; j += 2) { acc0 -= l[j] * uu[j]; acc1 -= l[j + 1] * uu[j + 1]; }
+      w[c] = acc0 + acc1;
     }
     __syncthreads();
   }
@@ -368,25 +409,20 @@ __device__ void back_solve_env(const DevTab& T, const KS& ks, const double* __re
 // ---------------------------------------------------------------------------
 // the solver kernel
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT, 2)
-omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S) {
-  extern __shared__ double sm[];
+__device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, const Batch& A, const Smem& S) {
   __shared__ Ctl ctl;
   __shared__ double phase_cyc[NPHASE];
   double* K = sm + S.K;
-  double* Pt = sm + S.Pt;
-  double* PtS = sm + S.PtS;
   double* u = sm + S.u;
-  int* rbase = reinterpret_cast<int*>(sm + S.rbase);
   double* xe = sm + S.xe;
   double* xt = sm + S.xt;
   double* dx = sm + S.dx;
   double* gf = sm + S.gf;
   double* diag0 = sm + S.diag0;
-  double* invd = sm + S.invd;
   double* V = sm + S.V;
   double* red = sm + S.red;
   double* filt = sm + S.filt;
+  unsigned char* rt = reinterpret_cast<unsigned char*>(sm + S.rt8);
   const int tid = threadIdx.x;
   const int n = T.n, m = T.m;
   {  // KKT structure arrays -> shared memory (once per block)
@@ -400,28 +436,22 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
     for (int i = tid; i < T.N + 2; i += NT) eptr[i] = T.env_ptr[i];
     for (int i = tid; i < T.N + 1; i += NT) efirst[i] = T.env_first[i];
     for (int i = tid; i < T.n_panels + 1; i += NT) pptr[i] = T.panel_ptr[i];
-    for (int i = tid; i < T.panel_ptr[T.n_panels]; i += NT) prow[i] = T.panel_rows[i];
+    for (int i = tid; i < T.n_panel_rows; i += NT) prow[i] = T.panel_rows[i];
     for (int i = tid; i < T.n_panels; i += NT) pcmin[i] = T.panel_cmin[i];
   }
-  KS ks;
-  ks.sgn = sm + S.sgn; ks.eptr = reinterpret_cast<const int*>(sm + S.eptr);
-  ks.efirst = reinterpret_cast<const int*>(sm + S.efirst);
-  ks.pptr = reinterpret_cast<const int*>(sm + S.pptr);
-  ks.prow = reinterpret_cast<const int*>(sm + S.prow);
-  ks.pcmin = reinterpret_cast<const int*>(sm + S.pcmin);
   __syncthreads();
 
-  // per-block global scratch (L2 resident)
+  // per-instance arrays: shared memory if they fit, else L2-resident scratch
   double* D = A.dscr + (size_t)blockIdx.x * A.dscr_stride;
-  double* g = D;            double* s = g + m;      double* y = s + m;
-  double* zL = y + m;       double* zU = zL + m;    double* dsc = zU + m;
-  double* sL = dsc + m;     double* sU = sL + m;    double* sig = sU + m;
-  double* wv = sig + m;     double* ds = wv + m;    double* dy = ds + m;
-  double* dzL = dy + m;     double* dzU = dzL + m;  double* gt = dzU + m;
-  double* st = gt + m;      double* jval = st + m;  double* beq = jval + T.nnz_j;
-  double* jsv = beq + m;
+#define ARR(k) ((S.arr[k] >= 0) ? (sm + S.arr[k]) : (D + (-(S.arr[k]) - 1)))
+  double* jval = ARR(A_JVAL); double* sig = ARR(A_SIG); double* jsv = ARR(A_JSV);
+  double* g = ARR(A_G); double* s = ARR(A_S); double* y = ARR(A_Y); double* zU = ARR(A_ZU);
+  double* dsc = ARR(A_DSC); double* sU = ARR(A_SU); double* ds = ARR(A_DS); double* dy = ARR(A_DY);
+  double* dzU = ARR(A_DZU); double* gt = ARR(A_GT); double* st = ARR(A_ST); double* wv = ARR(A_WV);
+  double* zL = ARR(A_ZL); double* sL = ARR(A_SL); double* dzL = ARR(A_DZL); double* beq = ARR(A_BEQ);
+#undef ARR
   int* I = A.iscr + (size_t)blockIdx.x * A.iscr_stride;
-  int* rt = I;              int* eqidx = rt + m;    int* eqrow = eqidx + m;
+  int* eqidx = I;           int* eqrow = eqidx + m;
 
   for (;;) {
     // ---- fetch next instance ------------------------------------------------
@@ -444,8 +474,8 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
       for (int e = T.level_ptr[l] + tid; e < T.level_ptr[l + 1]; e += NT) {
         double acc = 0.0;
         for (int t = T.tape_ptr[e]; t < T.tape_ptr[e + 1]; ++t) {
-          const int* f = T.tape_fac + 4 * t;
-          acc += T.tape_coef[t] * V[f[0]] * V[f[1]] * V[f[2]] * V[f[3]];
+          const int4 f = __ldg(reinterpret_cast<const int4*>(T.tape_fac) + t);
+          acc += T.tape_coef[t] * V[f.x] * V[f.y] * V[f.z] * V[f.w];
         }
         switch (T.tape_func[e]) {
           case 1: acc = 1.0 / acc; break;
@@ -466,7 +496,8 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
 
     // ---- S3: row classification, scaling, starting point -----------------------
     double fmaxv = 0.0;
-    for (int j = tid; j < n; j += NT) fmaxv = fmax(fmaxv, fabs(eval_slot(T.DF, j, V, xe)));
+    for (int j = tid; j < n; j += NT)
+      fmaxv = fmax(fmaxv, fabs(eval_range(T.DFt, T.dfptr[j], T.dfptr[j + 1], V, xe)));
     {
       double r1[1] = {fmaxv}; const int o1[1] = {OP_MAX};
       block_reduce<1>(r1, o1, red);
@@ -475,28 +506,37 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
     const double smg = O.scaling_max_gradient;
     const double fsc = (fmaxv > smg) ? fmax(smg / fmaxv, 1e-8) : 1.0;
     for (int i = tid; i < m; i += NT) {
+      const RowRec rr = T.rowrec[i];
+      // Jacobian row: max |J| for the gradient-based scaling
       double gm = 0.0;
-      for (int sl = T.jrow_ptr[i]; sl < T.jrow_ptr[i + 1]; ++sl)
-        gm = fmax(gm, fabs(eval_slot(T.J, sl, V, xe)));
+      {
+        double acc = 0.0; int cur = 0, aux;
+        for (int k = rr.jt0; k < rr.jt1; ++k) {
+          const double v = term_value(T.Jt + k, V, xe, &aux);
+          if (aux != cur) { gm = fmax(gm, fabs(acc)); acc = 0.0; cur = aux; }
+          acc += v;
+        }
+        gm = fmax(gm, fabs(acc));
+      }
       const double d = (gm > smg) ? fmax(smg / gm, 1e-8) : 1.0;
       dsc[i] = d;
       const double lb = lbg[i], ub = ubg[i];
       const bool eq = (lb == ub);
       const bool hL = (lb > -INF_BOUND) && !eq, hU = (ub < INF_BOUND) && !eq;
-      rt[i] = (hL ? 1 : 0) | (hU ? 2 : 0) | (eq ? 4 : 0);
-      double l = lb * d, u = ub * d;
+      rt[i] = (unsigned char)((hL ? 1 : 0) | (hU ? 2 : 0) | (eq ? 4 : 0));
+      double l = lb * d, uu = ub * d;
       beq[i] = l;
       if (hL) l -= O.bound_relax_factor * fmax(1.0, fabs(l));
-      if (hU) u += O.bound_relax_factor * fmax(1.0, fabs(u));
-      sL[i] = l; sU[i] = u;
-      const double gi = d * eval_slot(T.G, i, V, xe);
+      if (hU) uu += O.bound_relax_factor * fmax(1.0, fabs(uu));
+      sL[i] = l; sU[i] = uu;
+      const double gi = d * eval_range(T.Gt, rr.g0, rr.g1, V, xe);
       g[i] = gi;
       double si = gi;
       const double k1 = O.bound_push, k2 = O.bound_frac;
-      double pl = k1 * fmax(1.0, fabs(l)), pu = k1 * fmax(1.0, fabs(u));
-      if (hL && hU) { pl = fmin(pl, k2 * (u - l)); pu = fmin(pu, k2 * (u - l)); }
+      double pl = k1 * fmax(1.0, fabs(l)), pu = k1 * fmax(1.0, fabs(uu));
+      if (hL && hU) { pl = fmin(pl, k2 * (uu - l)); pu = fmin(pu, k2 * (uu - l)); }
       if (hL) si = fmax(si, l + pl);
-      if (hU) si = fmin(si, u - pu);
+      if (hU) si = fmin(si, uu - pu);
       s[i] = si;
       double yi = 0.0;
       if (A.lam0) yi = A.lam0[(size_t)inst * m + i] * fsc / d;
@@ -521,7 +561,7 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
       ctl.theta_max = -1.0; ctl.theta_min = -1.0;
       ctl.delta_w_last = 0.0; ctl.nfilt = 0; ctl.status = -1; ctl.iter = 0;
       ctl.fsc = fsc; ctl.alpha = 0.0; ctl.delta_w = 0.0;
-      ctl.f = fsc * eval_slot(T.F, 0, V, xe);
+      ctl.f = fsc * eval_range(T.Ft, 0, T.n_f, V, xe);
     }
     __syncthreads();
     if (ctl.n_eq < 0) {   // equality pattern differs from the lowered structure
@@ -538,33 +578,42 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
     // =========================== IP iterations ===============================
     for (int iter = 0;; ++iter) {
       TICK(0);   // setup / previous accept
-      // ---- I1: rows: g (kept from trial), Jacobian values, residual terms -------
+      // ---- I1: rows: Jacobian values, residual terms (g kept from the trial) ------
       double rv[NRED];
       // 0 cinf(max) 1 maxprod(max) 2 minprod(min) 3 viol(max) 4 rsinf(max)
-      // 5 rsinf_un(max) 6 ysum 7 zsum 8 theta 9 logsum
+      // 5 rsinf_un(max) 6 ysum 7 zsum 8 theta 9 logsum 10 rxinf(max)
       const int rop[NRED] = {OP_MAX, OP_MAX, OP_MIN, OP_MAX, OP_MAX, OP_MAX,
                              OP_SUM, OP_SUM, OP_SUM, OP_SUM, OP_MAX, OP_SUM};
       for (int r = 0; r < NRED; ++r) rv[r] = 0.0;
       rv[2] = 1e300;
       for (int i = tid; i < m; i += NT) {
+        const RowRec rr = T.rowrec[i];
         const int r = rt[i];
         const double d = dsc[i];
-        for (int sl = T.jrow_ptr[i]; sl < T.jrow_ptr[i + 1]; ++sl)
-          jval[sl] = d * eval_slot(T.J, sl, V, xe);
+        {
+          double acc = 0.0; int cur = 0, aux;
+          double* jv = jval + rr.s0;
+#pragma unroll 4
+          for (int k = rr.jt0; k < rr.jt1; ++k) {
+            const double v = term_value(T.Jt + k, V, xe, &aux);
+            if (aux != cur) { jv[cur] = d * acc; acc = 0.0; cur = aux; }
+            acc += v;
+          }
+          if (rr.ns > 0) jv[cur] = d * acc;
+        }
         const double gi = g[i], si = s[i], yi = y[i];
-        double ci;
-        if (r & 4) ci = gi - beq[i];
-        else ci = gi - si;
+        const double ci = (r & 4) ? gi - beq[i] : gi - si;
         rv[0] = fmax(rv[0], fabs(ci));
         rv[8] += fabs(ci);
-        if (r & 1) { const double dl = si - sL[i]; const double pz = dl * zL[i];
-          rv[1] = fmax(rv[1], pz); rv[2] = fmin(rv[2], pz); rv[9] += log(dl); rv[7] += zL[i]; }
-        if (r & 2) { const double du = sU[i] - si; const double pz = du * zU[i];
-          rv[1] = fmax(rv[1], pz); rv[2] = fmin(rv[2], pz); rv[9] += log(du); rv[7] += zU[i]; }
+        double zl = 0.0, zu = 0.0;
+        if (r & 1) { zl = zL[i]; const double dl = si - sL[i]; const double pz = dl * zl;
+          rv[1] = fmax(rv[1], pz); rv[2] = fmin(rv[2], pz); rv[9] += log(dl); rv[7] += zl; }
+        if (r & 2) { zu = zU[i]; const double du = sU[i] - si; const double pz = du * zu;
+          rv[1] = fmax(rv[1], pz); rv[2] = fmin(rv[2], pz); rv[9] += log(du); rv[7] += zu; }
         const double gun = gi / d;
         if (r & 6) rv[3] = fmax(rv[3], gun - ubg[i]);
         if (r & 5) rv[3] = fmax(rv[3], lbg[i] - gun);
-        if (!(r & 4)) { const double rs = fabs(-yi - zL[i] + zU[i]);
+        if (!(r & 4)) { const double rs = fabs(-yi - zl + zu);
           rv[4] = fmax(rv[4], rs); rv[5] = fmax(rv[5], rs * d); }
         rv[6] += fabs(yi);
       }
@@ -572,12 +621,14 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
       TICK(1);   // row pass
       // ---- I2: columns: grad f, dual residual ------------------------------------
       for (int j = tid; j < n; j += NT) {
-        const double gj = ctl.fsc * eval_slot(T.DF, j, V, xe);
+        const double gj = ctl.fsc * eval_range(T.DFt, T.dfptr[j], T.dfptr[j + 1], V, xe);
         gf[j] = gj;
         double rx = gj;
-        for (int q = T.jcol_ptr[j]; q < T.jcol_ptr[j + 1]; ++q) {
-          const int sl = T.jcol_slot[q];
-          rx += jval[sl] * y[T.jrow[sl]];
+        const int q0 = T.colptr[j], q1 = T.colptr[j + 1];
+#pragma unroll 4
+        for (int q = q0; q < q1; ++q) {
+          const unsigned cr = __ldg(T.colrec + q);
+          rx += jval[cr & 0xffffu] * y[cr >> 16];
         }
         rv[10] = fmax(rv[10], fabs(rx));
       }
@@ -594,11 +645,11 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
       TICK(2);   // column pass + reduction
       // ---- I3: termination + barrier update (uniform) ---------------------------
       int status = -1;
-      if (!isfinite(E0)) status = OMG_INVALID_NUMBER_DETECTED;
+      if (!isfinite(E0) || !isfinite(theta)) status = OMG_INVALID_NUMBER_DETECTED;
       else if (E0 <= O.tol && dinf_un <= O.dual_inf_tol && viol <= O.constr_viol_tol &&
                cmpl0 / ctl.fsc <= O.compl_inf_tol) status = OMG_SOLVE_SUCCEEDED;
       else if (iter >= O.max_iter) status = OMG_MAX_ITER_EXCEEDED;
-      if (tracing && tid == 0 && iter < TRACE_ROWS) {
+      if (tracing && tid == 0 && iter < TRACE_ROWS - 2) {
         double* tr = A.trace + iter * TRACE_COLS;
         tr[0] = iter; tr[1] = ctl.f / ctl.fsc; tr[2] = cinf; tr[3] = dinf; tr[4] = mu; tr[5] = E0;
         tr[6] = ctl.alpha; tr[7] = ctl.delta_w;
@@ -631,7 +682,7 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
       __syncthreads();
       const double tau = ctl.tau;
       TICK(3);   // barrier logic
-      // ---- I4: Sigma and w = Sigma r_d + phi_s ------------------------------------
+      // ---- I4: Sigma, w = Sigma r_d + phi_s, sigma-scaled Jacobian ----------------
       for (int i = tid; i < m; i += NT) {
         const int r = rt[i];
         double sg = 0.0, ph = 0.0, rd = 0.0;
@@ -643,46 +694,45 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
         }
         sig[i] = sg;
         wv[i] = (r & 4) ? y[i] : (sg * rd + ph);
-        for (int sl = T.jrow_ptr[i]; sl < T.jrow_ptr[i + 1]; ++sl) jsv[sl] = sg * jval[sl];
+        const RowRec rr = T.rowrec[i];
+        for (int k = 0; k < rr.ns; ++k) jsv[rr.s0 + k] = sg * jval[rr.s0 + k];
       }
-      // ---- I6: Hessian slots into gt-scratch? -> kept in st[] (nnz_w <= m assumed no) ---
       __syncthreads();
-
       TICK(4);   // sigma pass
+
       // ---- I7/I8: assemble + factorise, with inertia correction -----------------
       for (;;) {
-        for (int q = tid; q < T.env_size; q += NT) K[q] = 0.0;
+        {
+          double2* K2 = reinterpret_cast<double2*>(K);
+          const int h2 = (T.env_size + 1) >> 1;
+          for (int q = tid; q < h2; q += NT) K2[q] = make_double2(0.0, 0.0);
+        }
         __syncthreads();
         // H positions: gather J^T Sigma J (+ delta_w on the diagonal)
         for (int q = tid; q < T.nnz_h; q += NT) {
+          const HqRec h = T.hq[q];
           double acc = 0.0;
-          for (int e = T.hp_ptr[q]; e < T.hp_ptr[q + 1]; ++e) {
-            const unsigned pk = __ldg(T.hp_pack + e);
+#pragma unroll 4
+          for (int e = h.p0; e < h.p1; ++e) {
+            const unsigned pk = __ldg(T.hpack + e);
             acc += jsv[pk & 0xffffu] * jval[pk >> 16];
           }
-          if (T.hrow[q] == T.hcol[q]) acc += ctl.delta_w;
-          K[T.hdst[q]] = acc;
+          if (h.diag) acc += ctl.delta_w;
+          K[h.dst] = acc;
         }
         __syncthreads();
         TICK(5);   // zero + H gather
         // Lagrangian Hessian W (lambda = y*dsc, objective factor fsc)
         for (int q = tid; q < T.nnz_w; q += NT) {
+          const WRec w = T.wrec[q];
           double acc = 0.0;
-          const TL& L = T.W;
-          for (int t = L.ptr[q]; t < L.ptr[q + 1]; ++t) {
-            double v; int lr;
-            if (L.pk) {
-              const PTerm pt = load_pterm(L.pk + t);
-              v = pt.coef * V[pt.cidx] * xe[pt.x0] * xe[pt.x1]; lr = pt.lrow;
-            } else {
-              v = L.coef[t] * V[L.cidx[t]];
-              for (int k = 0; k < L.width; ++k) v *= xe[L.xi[t * L.width + k]];
-              lr = L.lrow[t];
-            }
+          for (int t = w.t0; t < w.t1; ++t) {
+            int lr;
+            double v = term_value(T.Wt + t, V, xe, &lr);
             v *= (lr < m) ? (y[lr] * dsc[lr]) : ctl.fsc;
             acc += v;
           }
-          K[T.hdst[T.w2h[q]]] += acc;
+          K[w.dst] += acc;
         }
         __syncthreads();
         for (int j = tid; j < n; j += NT) {
@@ -690,26 +740,29 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
           diag0[pj] = fabs(K[T.kdiag[pj]]);
         }
         // equality border + right-hand-side row
-        const int rhs0 = ks.eptr[N];
+        const int rhs0 = KS_EPTR[N];
         for (int k = tid; k < n_eq; k += NT) {
           const int i = eqrow[k], pk = T.pos_eq[k];
-          for (int sl = T.jrow_ptr[i]; sl < T.jrow_ptr[i + 1]; ++sl) K[T.jdst[sl]] = jval[sl];
+          const RowRec rr = T.rowrec[i];
+          for (int q = 0; q < rr.ns; ++q) K[T.jdst[rr.s0 + q]] = jval[rr.s0 + q];
           K[T.kdiag[pk]] = -ctl.delta_c;
           diag0[pk] = ctl.delta_c;
           K[rhs0 + pk] = -(g[i] - beq[i]);
         }
         for (int j = tid; j < n; j += NT) {
           double acc = gf[j];
-          for (int q = T.jcol_ptr[j]; q < T.jcol_ptr[j + 1]; ++q) {
-            const int sl = T.jcol_slot[q];
-            acc += jval[sl] * wv[T.jrow[sl]];
+          const int q0 = T.colptr[j], q1 = T.colptr[j + 1];
+#pragma unroll 4
+          for (int q = q0; q < q1; ++q) {
+            const unsigned cr = __ldg(T.colrec + q);
+            acc += jval[cr & 0xffffu] * wv[cr >> 16];
           }
           K[rhs0 + T.pos_var[j]] = -acc;
         }
         if (tid == 0) { ctl.fail = 0; ctl.eq_fail = 0; }
         __syncthreads();
         TICK(6);   // W + border + rhs
-        factor_env(T, ks, K, Pt, PtS, S.LDP, diag0, invd, rbase, &ctl, tracing ? phase_cyc : nullptr);
+        factor_env(T, S, &ctl, tracing ? phase_cyc : nullptr);
         __syncthreads();
         phase_t0 = clock64();
         if (!ctl.fail) break;
@@ -734,36 +787,38 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
       }
       if (tid == 0 && ctl.delta_w > 0.0) ctl.delta_w_last = ctl.delta_w;
       // ---- I9: solve -----------------------------------------------------------
-      for (int j = tid; j < N; j += NT) u[j] = K[ks.eptr[N] + j];
+      for (int j = tid; j < N; j += NT) u[j] = K[KS_EPTR[N] + j];
       __syncthreads();
-      back_solve_env(T, ks, K, invd, u);
-      TICK(10);  // back substitution
+      back_solve_env(T, S);
       for (int j = tid; j < n; j += NT) dx[j] = u[T.pos_var[j]];
       for (int k = tid; k < n_eq; k += NT) dx[n + k] = u[T.pos_eq[k]];
       __syncthreads();
+      TICK(10);  // back substitution
       // ---- I10: ds, dy, dz, fraction to the boundary --------------------------
-      double sv[4];   // 0 a_p(min) 1 a_d(min) 2 gphi(sum) 3 unused
+      double sv[4];   // 0 a_p(min) 1 a_d(min) 2 gphi(sum)
       const int sop[4] = {OP_MIN, OP_MIN, OP_SUM, OP_SUM};
       sv[0] = 1.0; sv[1] = 1.0; sv[2] = 0.0; sv[3] = 0.0;
       for (int i = tid; i < m; i += NT) {
         const int r = rt[i];
+        const RowRec rr = T.rowrec[i];
         double jd = 0.0;
-        for (int sl = T.jrow_ptr[i]; sl < T.jrow_ptr[i + 1]; ++sl) jd += jval[sl] * dx[T.jcol[sl]];
+#pragma unroll 4
+        for (int k = 0; k < rr.ns; ++k) jd += jval[rr.s0 + k] * dx[T.jcol16[rr.s0 + k]];
         if (r & 4) {
           ds[i] = 0.0; dy[i] = dx[n + eqidx[i]]; dzL[i] = 0.0; dzU[i] = 0.0;
         } else {
           const double si = s[i];
           const double dsi = jd + (g[i] - si);
-          double ph = 0.0, dl = 1.0, du = 1.0, a = 0.0, b = 0.0;
-          if (r & 1) { dl = si - sL[i]; ph -= mu / dl;
-            a = mu / dl - zL[i] - (zL[i] / dl) * dsi;
+          double ph = 0.0, a = 0.0, b = 0.0;
+          if (r & 1) { const double dl = si - sL[i]; const double z = zL[i]; ph -= mu / dl;
+            a = mu / dl - z - (z / dl) * dsi;
             if (dsi < 0.0) sv[0] = fmin(sv[0], -tau * dl / dsi);
-            if (a < 0.0) sv[1] = fmin(sv[1], -tau * zL[i] / a); }
-          if (r & 2) { du = sU[i] - si; ph += mu / du;
-            b = mu / du - zU[i] + (zU[i] / du) * dsi;
+            if (a < 0.0) sv[1] = fmin(sv[1], -tau * z / a); dzL[i] = a; }
+          if (r & 2) { const double du = sU[i] - si; const double z = zU[i]; ph += mu / du;
+            b = mu / du - z + (z / du) * dsi;
             if (dsi > 0.0) sv[0] = fmin(sv[0], tau * du / dsi);
-            if (b < 0.0) sv[1] = fmin(sv[1], -tau * zU[i] / b); }
-          ds[i] = dsi; dzL[i] = a; dzU[i] = b;
+            if (b < 0.0) sv[1] = fmin(sv[1], -tau * z / b); }
+          ds[i] = dsi; dzU[i] = b;
           dy[i] = sig[i] * dsi + ph - y[i];
           sv[2] += ph * dsi;
         }
@@ -789,12 +844,13 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
         ++n_ls;
         for (int j = tid; j < n; j += NT) xt[j] = xe[j] + alpha * dx[j];
         __syncthreads();
-        double tv[3];  // 0 theta 1 logsum 2 unused
+        double tv[3];  // 0 theta 1 logsum 2 f
         const int top[3] = {OP_SUM, OP_SUM, OP_SUM};
         tv[0] = 0.0; tv[1] = 0.0; tv[2] = 0.0;
         for (int i = tid; i < m; i += NT) {
+          const RowRec rr = T.rowrec[i];
           const int r = rt[i];
-          const double gi = dsc[i] * eval_slot(T.G, i, V, xt);
+          const double gi = dsc[i] * eval_range(T.Gt, rr.g0, rr.g1, V, xt);
           gt[i] = gi;
           if (r & 4) tv[0] += fabs(gi - beq[i]);
           else {
@@ -805,8 +861,10 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
             if (r & 2) tv[1] += log(sU[i] - si);
           }
         }
+        // objective terms spread over the block (summed by the same reduction)
+        for (int t = tid; t < T.n_f; t += NT) { int aux; tv[2] += term_value(T.Ft + t, V, xt, &aux); }
         block_reduce<3>(tv, top, red);
-        ft = ctl.fsc * eval_slot(T.F, 0, V, xt);
+        ft = ctl.fsc * tv[2];
         const double tht = tv[0], pht = ft - mu * tv[1];
         bool ok = isfinite(pht) && isfinite(tht) && tht <= ctl.theta_max;
         if (ok) {
@@ -884,6 +942,12 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
   }
 }
 
+__global__ void __launch_bounds__(512, 1)
+omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S) { ipm_body(T, O, A, S); }
+
+__global__ void __launch_bounds__(256, 2)
+omg_ipm_kernel_2cta(const DevTab T, const omg_options O, const Batch A, const Smem S) { ipm_body(T, O, A, S); }
+
 // warm-start shift: x[b, off + c*len + i] <- sum_k T[i,k] x[b, off + c*len + k]
 __global__ void omg_shift_kernel(double* x, int B, int n, int n_blocks, const int* offs,
                                  const int* lens, const int* ncols, const int* toffs,
@@ -920,7 +984,7 @@ struct omg_problem {
   Smem S;
   omg_options opt;
   std::vector<void*> allocs;
-  int n_sm = 0, ctas_per_sm = 1;
+  int n_sm = 0, ctas_per_sm = 1, nt = 512, target_ctas = 1;
   size_t smem_bytes = 0;
   double* dscr = nullptr; int* iscr = nullptr; int scr_ctas = 0;
   int dscr_stride = 0, iscr_stride = 0;
@@ -943,27 +1007,20 @@ static const Tp* upload(omg_problem* h, const Tp* src, size_t count, bool* ok) {
   return (const Tp*)d;
 }
 
-static TL upload_tl(omg_problem* h, const omg_termlist& L, int n_one, bool* ok) {
-  TL t;
-  t.n_out = L.n_out; t.n_terms = L.n_terms; t.width = L.width;
-  t.ptr = upload(h, L.ptr, (size_t)L.n_out + 1, ok);
-  t.coef = upload(h, L.coef, (size_t)L.n_terms, ok);
-  t.cidx = upload(h, L.cidx, (size_t)L.n_terms, ok);
-  t.xi = upload(h, L.xi, (size_t)L.n_terms * L.width, ok);
-  t.lrow = L.lrow ? upload(h, L.lrow, (size_t)L.n_terms, ok) : nullptr;
-  t.pk = nullptr;
-  if (L.width <= 2) {
-    std::vector<PTerm> pk((size_t)L.n_terms + 1);
-    for (int k = 0; k < L.n_terms; ++k) {
-      PTerm& q = pk[k];
-      q.coef = L.coef[k]; q.cidx = (unsigned short)L.cidx[k];
-      q.x0 = (unsigned short)(L.width >= 1 ? L.xi[(size_t)k * L.width] : n_one);
-      q.x1 = (unsigned short)(L.width >= 2 ? L.xi[(size_t)k * L.width + 1] : n_one);
-      q.lrow = (unsigned short)(L.lrow ? L.lrow[k] : 0);
-    }
-    t.pk = upload(h, pk.data(), pk.size(), ok);
+// pack a term list into 32-byte records; aux = lrow (W) / slot offset within the row (J)
+static const PTerm* upload_terms(omg_problem* h, const omg_termlist& L, int n_one,
+                                 const std::vector<int>* aux, bool* ok) {
+  std::vector<PTerm> pk((size_t)L.n_terms + 1);
+  memset(pk.data(), 0, pk.size() * sizeof(PTerm));
+  for (int k = 0; k < L.n_terms; ++k) {
+    PTerm& q = pk[k];
+    q.coef = L.coef[k]; q.cidx = (unsigned short)L.cidx[k];
+    q.aux = (unsigned short)(aux ? (*aux)[k] : (L.lrow ? L.lrow[k] : 0));
+    for (int w = 0; w < MAXW; ++w)
+      q.x[w] = (unsigned short)(w < L.width ? L.xi[(size_t)k * L.width + w] : n_one);
   }
-  return t;
+  for (int w = 0; w < MAXW; ++w) pk[L.n_terms].x[w] = (unsigned short)n_one;
+  return upload(h, pk.data(), pk.size(), ok);
 }
 
 extern "C" {
@@ -985,27 +1042,114 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
     set_err("no CUDA device available: libomgb200 has no CPU fallback"); return nullptr; }
   if (device < 0 || device >= ndev) { set_err("invalid device index"); return nullptr; }
   if (cudaSetDevice(device) != cudaSuccess) { set_err("cudaSetDevice failed"); return nullptr; }
+  g_err.clear();
   omg_problem* h = new omg_problem();
   h->device = device;
   if (opt) h->opt = *opt; else omg_default_options(&h->opt);
   bool ok = true;
   DevTab& T = h->T;
-  T.n = tb->n; T.m = tb->m; T.n_par = tb->n_par; T.n_v = tb->n_v;
+  memset(&T, 0, sizeof(T));
+  const int n = tb->n, m = tb->m;
+  T.n = n; T.m = m; T.n_par = tb->n_par; T.n_v = tb->n_v;
   T.n_tape = tb->n_tape; T.n_levels = tb->n_levels;
-  T.nnz_j = tb->nnz_j; T.nnz_w = tb->nnz_w; T.nnz_h = tb->nnz_h; T.n_hp = tb->n_hp;
+  T.nnz_j = tb->nnz_j; T.nnz_w = tb->nnz_w; T.nnz_h = tb->nnz_h;
   T.n_eq = tb->kkt_n_eq; T.N = tb->kkt_n;
   T.env_size = tb->env_size; T.max_panel_rows = tb->max_panel_rows;
+  T.n_panel_rows = tb->n_panel_rows;
   T.n_panels = (tb->kkt_n + NB - 1) / NB;
-  if (tb->kkt_n != tb->n + tb->kkt_n_eq) { set_err("inconsistent KKT structure"); ok = false; }
+  if (tb->kkt_n != n + tb->kkt_n_eq) { set_err("inconsistent KKT structure"); ok = false; }
+  if (!(n < 65535 && tb->n_v < 65536 && m < 65535 && tb->nnz_j < 65536)) {
+    set_err("problem too large for 16-bit packed indices"); ok = false; }
+  const omg_termlist* lists[5] = {&tb->G, &tb->F, &tb->DF, &tb->J, &tb->W};
+  for (int k = 0; k < 5 && ok; ++k)
+    if (lists[k]->width > MAXW) { set_err("term degree exceeds the record width (5 factors)"); ok = false; }
   for (int i = 0; ok && i <= tb->kkt_n; ++i)
-    if (tb->env_first[i] % NB != 0) { set_err("env_first must be a multiple of the panel width"); ok = false; }
+    if (tb->env_first[i] % NB != 0) {
+      set_err("envelope rows must start at multiples of the panel width"); ok = false; }
+  if (!ok) { delete h; return nullptr; }
+
+  T.tape_func = upload(h, tb->tape_func, tb->n_tape, &ok);
+  T.tape_ptr = upload(h, tb->tape_ptr, (size_t)tb->n_tape + 1, &ok);
+  T.tape_coef = upload(h, tb->tape_coef, tb->n_tape_terms, &ok);
+  T.tape_fac = upload(h, tb->tape_fac, (size_t)tb->n_tape_terms * 4, &ok);
+  T.level_ptr = upload(h, tb->level_ptr, (size_t)tb->n_levels + 1, &ok);
+  // term records
+  T.Gt = upload_terms(h, tb->G, n, nullptr, &ok);
+  T.Ft = upload_terms(h, tb->F, n, nullptr, &ok); T.n_f = tb->F.n_terms;
+  T.DFt = upload_terms(h, tb->DF, n, nullptr, &ok);
+  T.dfptr = upload(h, tb->DF.ptr, (size_t)n + 1, &ok);
+  T.Wt = upload_terms(h, tb->W, n, nullptr, &ok);
+  {
+    std::vector<int> aux(tb->J.n_terms > 0 ? tb->J.n_terms : 1);
+    for (int s = 0; s < tb->nnz_j; ++s) {
+      const int off = s - tb->jrow_ptr[tb->jrow[s]];
+      for (int t = tb->J.ptr[s]; t < tb->J.ptr[s + 1]; ++t) aux[t] = off;
+    }
+    T.Jt = upload_terms(h, tb->J, n, &aux, &ok);
+  }
+  {  // per-row records
+    std::vector<RowRec> rr(m > 0 ? m : 1);
+    for (int i = 0; i < m; ++i) {
+      RowRec& r = rr[i];
+      r.g0 = tb->G.ptr[i]; r.g1 = tb->G.ptr[i + 1];
+      r.s0 = tb->jrow_ptr[i]; r.ns = tb->jrow_ptr[i + 1] - tb->jrow_ptr[i];
+      r.jt0 = tb->J.ptr[r.s0]; r.jt1 = tb->J.ptr[r.s0 + r.ns];
+      r.pad0 = r.pad1 = 0;
+      // every slot of the row must own at least one term (aux bookkeeping)
+      for (int s = r.s0; s < r.s0 + r.ns; ++s)
+        if (tb->J.ptr[s + 1] == tb->J.ptr[s]) { set_err("empty Jacobian slot"); ok = false; }
+    }
+    T.rowrec = upload(h, rr.data(), rr.size(), &ok);
+  }
+  {  // CSC view of the Jacobian pattern: slot | row << 16
+    std::vector<int> cptr(n + 1, 0);
+    std::vector<unsigned> crec(tb->nnz_j > 0 ? tb->nnz_j : 1);
+    std::vector<unsigned short> jc(tb->nnz_j > 0 ? tb->nnz_j : 1);
+    for (int s = 0; s < tb->nnz_j; ++s) { cptr[tb->jcol[s] + 1]++; jc[s] = (unsigned short)tb->jcol[s]; }
+    for (int j = 0; j < n; ++j) cptr[j + 1] += cptr[j];
+    std::vector<int> fill(cptr.begin(), cptr.end() - 1);
+    for (int s = 0; s < tb->nnz_j; ++s)
+      crec[fill[tb->jcol[s]]++] = (unsigned)s | ((unsigned)tb->jrow[s] << 16);
+    T.colptr = upload(h, cptr.data(), cptr.size(), &ok);
+    T.colrec = upload(h, crec.data(), crec.size(), &ok);
+    T.jcol16 = upload(h, jc.data(), jc.size(), &ok);
+  }
+  {  // H positions sorted by descending pair count (balanced warps) + packed pairs
+    std::vector<int> order(tb->nnz_h);
+    for (int q = 0; q < tb->nnz_h; ++q) order[q] = q;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      return (tb->hp_ptr[a + 1] - tb->hp_ptr[a]) > (tb->hp_ptr[b + 1] - tb->hp_ptr[b]); });
+    std::vector<HqRec> hq(tb->nnz_h > 0 ? tb->nnz_h : 1);
+    std::vector<unsigned> pack((size_t)tb->n_hp + 1);
+    int pos = 0;
+    std::vector<char> has(n, 0);
+    for (int k = 0; k < tb->nnz_h; ++k) {
+      const int q = order[k];
+      HqRec& r = hq[k];
+      r.dst = tb->kkt_hdst[q]; r.p0 = pos; r.diag = (tb->hrow[q] == tb->hcol[q]) ? 1 : 0;
+      if (r.diag) has[tb->hrow[q]] = 1;
+      for (int e = tb->hp_ptr[q]; e < tb->hp_ptr[q + 1]; ++e)
+        pack[pos++] = (unsigned)tb->hp_s1[e] | ((unsigned)tb->hp_s2[e] << 16);
+      r.p1 = pos;
+    }
+    for (int j = 0; j < n; ++j) if (!has[j]) {
+      set_err("H pattern lacks a diagonal entry (variable without constraint)"); ok = false; break; }
+    T.hq = upload(h, hq.data(), hq.size(), &ok);
+    T.hpack = upload(h, pack.data(), pack.size(), &ok);
+  }
+  {  // Hessian slots: destination in the envelope + term range
+    std::vector<WRec> wr(tb->nnz_w > 0 ? tb->nnz_w : 1);
+    for (int q = 0; q < tb->nnz_w; ++q) {
+      wr[q].dst = tb->kkt_hdst[tb->w2h[q]]; wr[q].t0 = tb->W.ptr[q]; wr[q].t1 = tb->W.ptr[q + 1]; wr[q].pad = 0;
+    }
+    T.wrec = upload(h, wr.data(), wr.size(), &ok);
+  }
   T.eq_rows = upload(h, tb->kkt_eq_rows, tb->kkt_n_eq, &ok);
-  T.pos_var = upload(h, tb->kkt_pos_var, tb->n, &ok);
+  T.pos_var = upload(h, tb->kkt_pos_var, n, &ok);
   T.pos_eq = upload(h, tb->kkt_pos_eq, tb->kkt_n_eq, &ok);
   T.ksign = upload(h, tb->kkt_sign, tb->kkt_n, &ok);
   T.env_first = upload(h, tb->env_first, (size_t)tb->kkt_n + 1, &ok);
   T.env_ptr = upload(h, tb->env_ptr, (size_t)tb->kkt_n + 2, &ok);
-  T.hdst = upload(h, tb->kkt_hdst, tb->nnz_h, &ok);
   T.jdst = upload(h, tb->kkt_jdst, tb->nnz_j, &ok);
   T.kdiag = upload(h, tb->kkt_diag, tb->kkt_n, &ok);
   T.panel_ptr = upload(h, tb->kkt_panel_ptr, (size_t)T.n_panels + 1, &ok);
@@ -1019,86 +1163,66 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
     }
     T.panel_cmin = upload(h, cmin.data(), cmin.size(), &ok);
   }
-  T.tape_func = upload(h, tb->tape_func, tb->n_tape, &ok);
-  T.tape_ptr = upload(h, tb->tape_ptr, (size_t)tb->n_tape + 1, &ok);
-  T.tape_coef = upload(h, tb->tape_coef, tb->n_tape_terms, &ok);
-  T.tape_fac = upload(h, tb->tape_fac, (size_t)tb->n_tape_terms * 4, &ok);
-  T.level_ptr = upload(h, tb->level_ptr, (size_t)tb->n_levels + 1, &ok);
-  const bool small_idx = tb->n < 65535 && tb->n_v < 65536 && tb->m < 65535 && tb->nnz_j < 65536;
-  if (!small_idx) { set_err("problem too large for 16-bit packed indices"); ok = false; }
-  T.G = upload_tl(h, tb->G, tb->n, &ok); T.F = upload_tl(h, tb->F, tb->n, &ok);
-  T.DF = upload_tl(h, tb->DF, tb->n, &ok);
-  T.J = upload_tl(h, tb->J, tb->n, &ok); T.W = upload_tl(h, tb->W, tb->n, &ok);
-  T.jrow = upload(h, tb->jrow, tb->nnz_j, &ok); T.jcol = upload(h, tb->jcol, tb->nnz_j, &ok);
-  T.jrow_ptr = upload(h, tb->jrow_ptr, (size_t)tb->m + 1, &ok);
-  {  // CSC view of the Jacobian pattern
-    std::vector<int> cptr(tb->n + 1, 0), cslot(tb->nnz_j > 0 ? tb->nnz_j : 1);
-    for (int s = 0; s < tb->nnz_j; ++s) cptr[tb->jcol[s] + 1]++;
-    for (int j = 0; j < tb->n; ++j) cptr[j + 1] += cptr[j];
-    std::vector<int> fill(cptr.begin(), cptr.end() - 1);
-    for (int s = 0; s < tb->nnz_j; ++s) cslot[fill[tb->jcol[s]]++] = s;
-    T.jcol_ptr = upload(h, cptr.data(), cptr.size(), &ok);
-    T.jcol_slot = upload(h, cslot.data(), (size_t)tb->nnz_j, &ok);
-  }
-  T.wrow = upload(h, tb->wrow, tb->nnz_w, &ok); T.wcol = upload(h, tb->wcol, tb->nnz_w, &ok);
-  T.w2h = upload(h, tb->w2h, tb->nnz_w, &ok);
-  T.hrow = upload(h, tb->hrow, tb->nnz_h, &ok); T.hcol = upload(h, tb->hcol, tb->nnz_h, &ok);
-  T.hp_ptr = upload(h, tb->hp_ptr, (size_t)tb->nnz_h + 1, &ok);
-  T.hp_s1 = upload(h, tb->hp_s1, tb->n_hp, &ok); T.hp_s2 = upload(h, tb->hp_s2, tb->n_hp, &ok);
-  T.hp_row = upload(h, tb->hp_row, tb->n_hp, &ok);
-  {
-    std::vector<unsigned> pack((size_t)tb->n_hp + 1);
-    for (int e = 0; e < tb->n_hp; ++e)
-      pack[e] = (unsigned)tb->hp_s1[e] | ((unsigned)tb->hp_s2[e] << 16);
-    T.hp_pack = upload(h, pack.data(), pack.size(), &ok);
-  }
-  {  // every diagonal (j,j) must be part of the H pattern (delta_w lands there)
-    std::vector<char> has(tb->n, 0);
-    for (int q = 0; q < tb->nnz_h; ++q) if (tb->hrow[q] == tb->hcol[q]) has[tb->hrow[q]] = 1;
-    for (int j = 0; j < tb->n; ++j) if (!has[j]) {
-      set_err("H pattern lacks a diagonal entry (variable without constraint)"); ok = false; break; }
-  }
-  // shared-memory layout
+
+  // ---- shared-memory layout: mandatory part, then per-instance arrays by priority
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) ok = false;
+  h->n_sm = prop.multiProcessorCount;
   Smem& S = h->S;
   const int N = T.N;
   int off = 0;
   auto take = [&](int cnt) { int o = off; off += (cnt + 1) & ~1; return o; };
-  S.K = take(T.env_size);
-  S.LDP = (T.max_panel_rows + 4 + 3) & ~3;
-  S.Pt = take(NB * S.LDP); S.PtS = take(NB * S.LDP);
+  S.K = take(T.env_size + 2);
+  S.LDP = (T.max_panel_rows + 2 + 3) & ~3;
+  S.Pt = take(NB * S.LDP); S.PtS = take(NB * S.LDP); S.Ld = take(NB * NB);
   S.rbase = take(S.LDP);               // 2*LDP ints: row base offsets + row ids
-  S.xe = take(T.n + 1); S.xt = take(T.n + 1); S.dx = take(N + 1); S.u = take(N + 1);
-  S.gf = take(T.n);
+  S.xe = take(n + 1); S.xt = take(n + 1); S.dx = take(N + 1); S.u = take(N + 1);
+  S.gf = take(n);
   S.diag0 = take(N + 1); S.invd = take(N + 1); S.V = take(T.n_v);
-  S.red = take(NWARP * NRED); S.filt = take(2 * MAXF);
+  S.red = take(MAX_NWARP * NRED); S.filt = take(2 * MAXF);
+  S.rt8 = take((m + 7) / 8);
   S.sgn = take(N); S.eptr = take((N + 2 + 1) / 2); S.efirst = take((N + 1 + 1) / 2);
   S.pptr = take((T.n_panels + 1 + 1) / 2); S.prow = take((tb->n_panel_rows + 1) / 2);
   S.pcmin = take((T.n_panels + 1) / 2);
-  S.total = off;
-  h->smem_bytes = (size_t)off * sizeof(double);
-  cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) ok = false;
-  h->n_sm = prop.multiProcessorCount;
-  if (ok && h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) {
+  // blocks per SM: 2 x 256 threads overlap one block's serial pivots with the other's
+  // parallel phases; 1 x 512 keeps every per-instance array in shared memory.
+  cudaFuncAttributes fa;
+  if (ok && cudaFuncGetAttributes(&fa, (const void*)omg_ipm_kernel) != cudaSuccess) { set_err("cudaFuncGetAttributes failed"); ok = false; }
+  const size_t budget1 = ok ? (size_t)prop.sharedMemPerBlockOptin - fa.sharedSizeBytes : 0;
+  const size_t budget2 = ok ? ((size_t)prop.sharedMemPerMultiprocessor - 2 * 1024) / 2 - fa.sharedSizeBytes : 0;
+  {
+    const char* e = getenv("OMG_B200_CTAS");
+    const int want = (e && atoi(e) == 1) ? 1 : 2;
+    h->target_ctas = (want == 2 && (size_t)off * 8 <= budget2) ? 2 : 1;
+    h->nt = (h->target_ctas == 1) ? 512 : 256;
+  }
+  const void* kfn = (h->target_ctas == 1) ? (const void*)omg_ipm_kernel : (const void*)omg_ipm_kernel_2cta;
+  const size_t budget = (h->target_ctas == 1) ? budget1 : budget2;
+  if (ok && (size_t)off * 8 > budget) {
     char buf[256];
-    snprintf(buf, sizeof buf, "KKT block does not fit shared memory: need %zu B, have %zu B (n=%d, n_eq=%d)",
-             h->smem_bytes, (size_t)prop.sharedMemPerBlockOptin, T.n, T.n_eq);
+    snprintf(buf, sizeof buf, "KKT envelope does not fit shared memory: need %zu B, have %zu B (n=%d, n_eq=%d)",
+             (size_t)off * 8, budget, n, T.n_eq);
     set_err(buf); ok = false;
   }
-  // the attribute is per function (shared by all handles): opt in to the device maximum
-  if (ok) {
-    cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, omg_ipm_kernel) != cudaSuccess) { set_err("cudaFuncGetAttributes failed"); ok = false; }
-    else if (cudaFuncSetAttribute(omg_ipm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(prop.sharedMemPerBlockOptin - fa.sharedSizeBytes)) != cudaSuccess) {
-      set_err(std::string("cudaFuncSetAttribute failed: ") + cudaGetErrorString(cudaGetLastError())); ok = false; }
+  int goff = 0;   // global scratch offset (doubles)
+  const int sizes[N_ARR] = {tb->nnz_j, m, tb->nnz_j, m, m, m, m, m, m, m, m, m, m, m, m, m, m, m, m};
+  for (int k = 0; k < N_ARR; ++k) {
+    const int cnt = (sizes[k] + 1) & ~1;
+    const bool optional_low = (k >= A_ZL);     // lower-bound / equality-only arrays: rarely touched
+    if (!optional_low && (size_t)(off + cnt) * 8 <= budget) { S.arr[k] = off; off += cnt; }
+    else { S.arr[k] = -(goff + 1); goff += cnt; }
   }
+  S.total = off;
+  h->smem_bytes = (size_t)off * sizeof(double);
+  if (ok && cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)((size_t)prop.sharedMemPerBlockOptin - fa.sharedSizeBytes)) != cudaSuccess) {
+    set_err(std::string("cudaFuncSetAttribute failed: ") + cudaGetErrorString(cudaGetLastError())); ok = false; }
   if (ok) {
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, omg_ipm_kernel, NT, h->smem_bytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, h->nt, h->smem_bytes);
     h->ctas_per_sm = occ > 0 ? occ : 1;
-    h->dscr_stride = 18 * T.m + 2 * T.nnz_j + 8;
-    h->iscr_stride = 2 * T.m + T.n_eq + 8;
+    h->dscr_stride = goff + 8;
+    h->iscr_stride = 2 * m + 8;
     if (cudaMalloc(&h->counter, sizeof(int)) != cudaSuccess) ok = false;
     if (cudaMalloc(&h->trace, sizeof(double) * TRACE_ROWS * TRACE_COLS) != cudaSuccess) ok = false;
     else cudaMemset(h->trace, 0, sizeof(double) * TRACE_ROWS * TRACE_COLS);
@@ -1165,7 +1289,8 @@ int omg_solve_batch(omg_problem* h, int32_t B, const double* x0, const double* p
   A.counter = h->counter; A.trace = h->trace;
   CK(cudaMemsetAsync(h->counter, 0, sizeof(int), stream));
   CK(cudaEventRecord(h->ev0, stream));
-  omg_ipm_kernel<<<grid, NT, h->smem_bytes, stream>>>(h->T, h->opt, A, h->S);
+  if (h->target_ctas == 1) omg_ipm_kernel<<<grid, 512, h->smem_bytes, stream>>>(h->T, h->opt, A, h->S);
+  else omg_ipm_kernel_2cta<<<grid, 256, h->smem_bytes, stream>>>(h->T, h->opt, A, h->S);
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->ev1, stream));
   h->timed = true; h->launches = 1;

@@ -156,7 +156,7 @@ def test_problem_solve_dropin(solvers):
     assert np.abs(pr.father.get_variables().cat - ref.x).max() < X_TOL
     assert np.abs(pr.father.get_dual_variables().cat - ref.lam_g).max() < 1e-6
     splines = pr.father.get_variables(pr.vehicles[0], 'splines_seg0')
-    assert abs(splines[0](0.)[0] + 1.5) < 1e-6 and abs(splines[1](1.)[0] - 2.) < 1e-3
+    assert abs(splines[0](0.)[0] + 1.5) < 1e-6 and abs(splines[0](1.)[0] - 2.) < 1e-2
 
 
 def test_device_pointer_api_and_shift(solvers):

@@ -83,7 +83,7 @@ def test_kkt_structure_is_consistent(cfg1):
     N = tb.kkt_n
     pos = np.r_[tb.kkt_pos_var, tb.kkt_pos_eq]
     assert sorted(pos) == list(range(N))
-    assert np.all(tb.env_first[:N] % 16 == 0) and np.all(tb.env_first[:N] <= np.arange(N))
+    assert np.all(tb.env_first[:N] % 8 == 0) and np.all(tb.env_first[:N] <= np.arange(N))
     assert tb.env_size == tb.env_ptr[-1] and tb.env_size < (N + 1) * (N + 2) // 2
     # every equality row sits after all variables it couples (negative pivot)
     for k, i in enumerate(tb.kkt_eq_rows):
