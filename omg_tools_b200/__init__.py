@@ -2,10 +2,11 @@
 spline-trajectory NLP, behind the reference's Problem.solve()/OptiFather API."""
 from .basics.spline import BSplineBasis, BSpline
 from .basics.shape import (Circle, Polyhedron, Rectangle, Square, Beam,
-                           RegularPolyhedron, Sphere, Cuboid, Cube)
+                           RegularPolyhedron, Sphere, Cuboid, Cube, Plate)
 from .basics.optilayer import OptiChild, OptiFather, create_nlp
 from .vehicles.vehicle import Vehicle
 from .vehicles.holonomic import Holonomic
+from .vehicles.quadrotor3d import Quadrotor3D
 from .vehicles.fleet import Fleet
 from .environment.environment import Environment
 from .environment.obstacle import Obstacle

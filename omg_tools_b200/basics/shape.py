@@ -110,6 +110,20 @@ class Shape3D(Shape):
     def __init__(self):
         Shape.__init__(self, 3)
 
+    @staticmethod
+    def rotate(orientation, coordinate):
+        """roll-pitch-yaw rotation (reference shape.py:269-279)."""
+        if len(orientation) != 3:
+            raise ValueError('Orientation is a list with 3 elements: roll, pitch, yaw!')
+        roll, pitch, yaw = orientation
+        cpsi, spsi = np.cos(yaw), np.sin(yaw)
+        cth, sth = np.cos(pitch), np.sin(pitch)
+        cphi, sphi = np.cos(roll), np.sin(roll)
+        rot = np.array([[cth*cpsi, sphi*sth*cpsi-cphi*spsi, cphi*sth*cpsi+sphi*spsi],
+                        [cth*spsi, sphi*sth*spsi+cphi*cpsi, cphi*sth*spsi-sphi*cpsi],
+                        [-sth, sphi*cth, cphi*cth]])
+        return rot.dot(coordinate)
+
 
 class Sphere(Shape3D):
     def __init__(self, radius):
@@ -125,11 +139,12 @@ class Sphere(Shape3D):
 
 
 class Polyhedron3D(Shape3D):
-    def __init__(self, vertices, radius=1e-3):
+    def __init__(self, vertices, orientation=(0, 0, 0), radius=1e-3):
         Shape3D.__init__(self)
-        self.vertices = vertices
         self.n_vert = vertices.shape[1]
         self.radius = radius
+        self.orientation = list(orientation)
+        self.vertices = self.rotate(self.orientation, vertices)
 
     def get_checkpoints(self):
         chck = [[self.vertices[0, l], self.vertices[1, l], self.vertices[2, l]]
@@ -142,15 +157,29 @@ class Polyhedron3D(Shape3D):
 
 
 class Cuboid(Polyhedron3D):
-    def __init__(self, width, depth, height, radius=1e-3):
+    """Vertex order of the reference (shape.py:402-428): 4 bottom, 4 top."""
+
+    def __init__(self, width, depth, height, orientation=(0, 0, 0)):
         self.width, self.depth, self.height = width, depth, height
-        w, d, h = 0.5 * width, 0.5 * depth, 0.5 * height
-        vertices = np.array([[sx * w, sy * d, sz * h]
-                             for sz in (-1, 1) for sy in (-1, 1)
-                             for sx in (-1, 1)]).T
-        Polyhedron3D.__init__(self, vertices, radius)
+        base = _tangent_polygon([l * 0.5 * np.pi for l in range(4)],
+                                [0.5 * depth, 0.5 * width, 0.5 * depth, 0.5 * width])
+        vertices = np.zeros((3, 8))
+        vertices[:2, :4] = base
+        vertices[2, :4] = -0.5 * height
+        vertices[:2, 4:] = base
+        vertices[2, 4:] = 0.5 * height
+        Polyhedron3D.__init__(self, vertices, orientation)
 
 
 class Cube(Cuboid):
-    def __init__(self, side, radius=1e-3):
-        Cuboid.__init__(self, side, side, side, radius)
+    def __init__(self, side, orientation=(0, 0, 0)):
+        Cuboid.__init__(self, side, side, side, orientation)
+
+
+class Plate(Polyhedron3D):
+    """Flat polygon with half-thickness as radius (reference shape.py:447-454)."""
+
+    def __init__(self, shape2d, height, orientation=(0, 0, 0)):
+        self.shape2d = shape2d
+        vertices = np.r_[shape2d.vertices, np.zeros((1, shape2d.vertices.shape[1]))]
+        Polyhedron3D.__init__(self, vertices, orientation, 0.5 * height)

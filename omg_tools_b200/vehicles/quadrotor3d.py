@@ -1,0 +1,191 @@
+"""Quadrotor3D: flat outputs f~ (thrust), q_phi = tan(phi/2), q_theta =
+tan(theta/2) as degree-2 splines; accelerations tied to degree-4 slack
+splines that are integrated twice to the position.
+
+Model-building interface and row order of the reference's
+``omgtools/vehicles/quadrotor3d.py`` (bounds 51-62, init 70-74, trajectory
+constraints 76-133, initial/terminal constraints 135-174, initial guess
+189-201, parameters 211-223, collision constraints 225-238, integrate_twice
+240-254).  Rows are polynomials up to degree 5 in the decision variables.
+"""
+import numpy as np
+
+from .vehicle import Vehicle
+from ..basics.optilayer import inf
+from ..basics.poly import Poly
+from ..basics.shape import Sphere
+from ..basics.spline import BSplineBasis
+from ..basics.spline_extra import evalspline, running_integral, sample_splines
+
+
+class Quadrotor3D(Vehicle):
+
+    def __init__(self, radius=0.2, options=None, bounds=None):
+        bounds = bounds or {}
+        Vehicle.__init__(self, n_spl=3, degree=2, shapes=Sphere(radius), options=options)
+        self.u1min = bounds.get('u1min', 2.)
+        self.u1max = bounds.get('u1max', 15.)
+        self.u2min = bounds.get('u2min', -2.)
+        self.u2max = bounds.get('u2max', 2.)
+        self.u3min = bounds.get('u3min', -2.)
+        self.u3max = bounds.get('u3max', 2.)
+        self.phimin = bounds.get('phimin', -np.pi / 6)
+        self.phimax = bounds.get('phimax', np.pi / 6)
+        self.thetamin = bounds.get('thetamin', -np.pi / 6)
+        self.thetamax = bounds.get('thetamax', np.pi / 6)
+        self.g = 9.81
+        self.radius = radius
+
+    def set_default_options(self):
+        Vehicle.set_default_options(self)
+        self.options['stop_tol'] = 5.e-1
+        self.options['substitution'] = True
+        self.options['exact_substitution'] = False
+
+    def init(self):
+        self.t = self.define_symbol('t')
+        self.pos0 = self.define_parameter('pos0', 3)
+        self.dpos0 = self.define_parameter('dpos0', 3)
+
+    def define_trajectory_constraints(self, splines, horizon_time=None):
+        if horizon_time is None:
+            horizon_time = self.define_symbol('T')
+        T = horizon_time
+        f_til, q_phi, q_theta = splines
+        dq_phi, dq_theta = q_phi.derivative(), q_theta.derivative()
+        # thrust, roll rate, pitch rate
+        self.define_constraint(f_til * (1 + q_phi**2) * (1 + q_theta**2) - self.u1max, -inf, 0)
+        self.define_constraint(-f_til * (1 + q_phi**2) * (1 + q_theta**2) + self.u1min, -inf, 0)
+        self.define_constraint(2 * dq_phi - (1 + q_phi**2) * T * self.u2max, -inf, 0.)
+        self.define_constraint(-2 * dq_phi + (1 + q_phi**2) * T * self.u2min, -inf, 0.)
+        self.define_constraint(2 * dq_theta - (1 + q_theta**2) * T * self.u3max, -inf, 0.)
+        self.define_constraint(-2 * dq_theta + (1 + q_theta**2) * T * self.u3min, -inf, 0.)
+        # attitude limits
+        self.define_constraint(q_phi - np.tan(0.5 * self.phimax), -inf, 0)
+        self.define_constraint(-q_phi + np.tan(0.5 * self.phimin), -inf, 0)
+        self.define_constraint(q_theta - np.tan(0.5 * self.thetamax), -inf, 0)
+        self.define_constraint(-q_theta + np.tan(0.5 * self.thetamin), -inf, 0)
+        if self.options['substitution']:
+            ddx = f_til * (1 - q_phi**2) * (2 * q_theta)
+            ddy = -f_til * (1 + q_theta**2) * (2 * q_phi)
+            ddz = f_til * (1 - q_phi**2) * (1 - q_theta**2) - self.g
+            if self.options['exact_substitution']:
+                bx, by, bz = ddx.basis, ddy.basis, ddz.basis
+            else:
+                degree = 4
+                knots = np.r_[np.zeros(degree), np.linspace(0., 1., 10 + 1), np.ones(degree)]
+                bx = by = bz = BSplineBasis(knots, degree)
+            self.ddx = self.define_spline_variable('ddx', 1, 1, basis=bx)[0]
+            self.ddy = self.define_spline_variable('ddy', 1, 1, basis=by)[0]
+            self.ddz = self.define_spline_variable('ddz', 1, 1, basis=bz)[0]
+            self.x, self.dx = self.integrate_twice(self.ddx, self.dpos0[0], self.pos0[0], self.t, T)
+            self.y, self.dy = self.integrate_twice(self.ddy, self.dpos0[1], self.pos0[1], self.t, T)
+            self.z, self.dz = self.integrate_twice(self.ddz, self.dpos0[2], self.pos0[2], self.t, T)
+            if self.options['exact_substitution']:
+                self.define_constraint(self.ddx - ddx, 0, 0)
+                self.define_constraint(self.ddy - ddy, 0, 0)
+                self.define_constraint(self.ddz - ddz, 0, 0)
+            else:
+                x, _ = self.integrate_twice(ddx, self.dpos0[0], self.pos0[0], self.t, T)
+                y, _ = self.integrate_twice(ddy, self.dpos0[1], self.pos0[1], self.t, T)
+                z, _ = self.integrate_twice(ddz, self.dpos0[2], self.pos0[2], self.t, T)
+                eps = 1e-3
+                self.define_constraint(self.x - x, -eps, eps)
+                self.define_constraint(self.y - y, -eps, eps)
+                self.define_constraint(self.z - z, -eps, eps)
+
+    def _positions(self, splines, horizon_time):
+        f_til, q_phi, q_theta = splines
+        if self.options['substitution']:
+            return (self.x, self.y, self.z), (self.dx, self.dy, self.dz)
+        ddx = f_til * (1 - q_phi**2) * (2 * q_theta)
+        ddy = -f_til * (1 + q_theta**2) * (2 * q_phi)
+        ddz = f_til * (1 - q_phi**2) * (1 - q_theta**2) - self.g
+        x, dx = self.integrate_twice(ddx, self.dpos0[0], self.pos0[0], self.t, horizon_time)
+        y, dy = self.integrate_twice(ddy, self.dpos0[1], self.pos0[1], self.t, horizon_time)
+        z, dz = self.integrate_twice(ddz, self.dpos0[2], self.pos0[2], self.t, horizon_time)
+        return (x, y, z), (dx, dy, dz)
+
+    def get_initial_constraints(self, splines, horizon_time=None):
+        f_til0 = self.define_parameter('f_til0', 1)
+        q_phi0 = self.define_parameter('q_phi0', 1)
+        q_theta0 = self.define_parameter('q_theta0', 1)
+        self.define_parameter('dq_phi0', 1)
+        self.define_parameter('dq_theta0', 1)
+        f_til, q_phi, q_theta = splines
+        return [(f_til, f_til0), (q_phi, q_phi0), (q_theta, q_theta0)]
+
+    def get_terminal_constraints(self, splines, horizon_time=None):
+        if horizon_time is None:
+            horizon_time = self.define_symbol('T')
+        posT = self.define_parameter('posT', 3)
+        q_phiT = self.define_parameter('q_phiT', 1)
+        q_thetaT = self.define_parameter('q_thetaT', 1)
+        f_til, q_phi, q_theta = splines
+        (x, y, z), (dx, dy, dz) = self._positions(splines, horizon_time)
+        term_con = [(x, posT[0]), (y, posT[1]), (z, posT[2])]
+        term_con_der = [(q_phi, q_phiT), (q_theta, q_thetaT), (f_til, self.g),
+                        (dx, 0.), (dy, 0.), (dz, 0.)]
+        return [term_con, term_con_der]
+
+    def set_initial_conditions(self, state, input=None):
+        if input is None:
+            input = np.array([self.g, 0., 0.])
+        self.prediction['state'] = np.asarray(state, dtype=float)
+        self.prediction['input'] = np.asarray(input, dtype=float)
+        self.pose0 = np.r_[state[:3], state[6:], 0.]
+
+    def set_terminal_conditions(self, position, roll=0, pitch=0):
+        self.poseT = np.r_[position, roll, pitch, 0.].T
+
+    def get_init_spline_value(self):
+        L = len(self.basis)
+        init_value = np.zeros((L, 3))
+        q_phi0 = np.tan(self.prediction['state'][6] / 2.)
+        q_theta0 = np.tan(self.prediction['state'][7] / 2.)
+        init_value[:, 1] = np.linspace(q_phi0, np.tan(self.poseT[3] / 2.), L)
+        init_value[:, 2] = np.linspace(q_theta0, np.tan(self.poseT[4] / 2.), L)
+        return [init_value]
+
+    def check_terminal_conditions(self):
+        tol = self.options['stop_tol']
+        return not (np.linalg.norm(self.signals['pose'][:3, -1] - self.poseT[:3]) > tol or
+                    np.linalg.norm(self.signals['input'][:, -1]) - self.g > tol)
+
+    def set_parameters(self, current_time):
+        parameters = Vehicle.set_parameters(self, current_time)
+        p = parameters[self]
+        st, inp = self.prediction['state'], self.prediction['input']
+        p['q_phi0'] = np.tan(st[6] / 2.)
+        p['q_theta0'] = np.tan(st[7] / 2.)
+        p['f_til0'] = inp[0] / ((1 + p['q_phi0']**2) * (1 + p['q_theta0']**2))
+        p['dq_phi0'] = 0.5 * inp[1] * (1 + p['q_phi0']**2)
+        p['dq_theta0'] = 0.5 * inp[2] * (1 + p['q_theta0']**2)
+        p['pos0'] = st[:3]
+        p['dpos0'] = st[3:6]
+        p['posT'] = self.poseT[:3]
+        p['q_phiT'] = np.tan(self.poseT[3] / 2.)
+        p['q_thetaT'] = np.tan(self.poseT[4] / 2.)
+        return parameters
+
+    def define_collision_constraints(self, hyperplanes, room, splines, horizon_time=None):
+        if horizon_time is None:
+            horizon_time = self.define_symbol('T')
+        (x, y, z), _ = self._positions(splines, horizon_time)
+        self.define_collision_constraints_3d(hyperplanes, room, [x, y, z], horizon_time)
+
+    def integrate_twice(self, ddx, dx0, x0, t, T=1.):
+        """x(tau) with x(t/T) = x0, x'(t/T) = T dx0 ... as in the reference
+        (quadrotor3d.py:240-254): two running integrals re-anchored at t/T."""
+        symbolic = isinstance(t, Poly)
+        ddx_int = T * running_integral(ddx)
+        at = evalspline(ddx_int, t / T) if symbolic else ddx_int(t / T)[0]
+        dx = ddx_int - at + dx0
+        dx_int = T * running_integral(dx)
+        at = evalspline(dx_int, t / T) if symbolic else dx_int(t / T)[0]
+        x = dx_int - at + x0
+        return x, dx
+
+    def splines2signals(self, splines, time):
+        raise NotImplementedError('trajectory extraction for Quadrotor3D is '
+                                  'host-side bookkeeping outside this round')

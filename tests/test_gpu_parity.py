@@ -215,3 +215,42 @@ def test_receding_horizon_config1(solvers):
         t += dt
     # vehicle moved towards the goal and stayed on its trajectory
     assert pr.vehicles[0].signals['state'][0, -1] > -1.5
+
+
+def test_batched_receding_horizon_config5(solvers):
+    """BASELINE config 5 (revolving door, rotating obstacles): the batched
+    device-resident MPC loop equals the reference-style sequential loop
+    Problem.predict/solve/store/simulate, step by step."""
+    from omg_tools_b200.execution.batch_mpc import BatchMPC
+    seq = sc.config5()
+    seq.initialize(0.)
+    bat = BatchMPC(sc.config5(), batch=3, update_time=0.1)
+    t, dt = 0., 0.1
+    for k in range(15):                      # crosses the first knot at t = 1.0
+        seq.predict(t, dt, 0.01)
+        seq.solve(t, dt)
+        Xb = bat.step()
+        xs = seq.father.get_variables().cat
+        assert seq.problem.stats()['return_status'] == 'Solve_Succeeded'
+        assert np.all(bat.history['status'][-1] == 0)
+        assert np.abs(Xb - xs[None]).max() < NORTH_STAR_TOL, k
+        assert np.abs(Xb[:, :26] - xs[None, :26]).max() < X_TOL, k
+        seq.store(t, dt, 0.01)
+        seq.simulate(t, dt, 0.01)
+        t = np.round(t + dt, 6)
+    assert np.abs(bat.state[0] - seq.vehicles[0].signals['state'][:, -1]).max() < 1e-5
+
+
+def test_receding_horizon_batch256_50_steps(solvers):
+    """Config 5 at BASELINE size: 256 jittered instances, 50 MPC steps on device."""
+    from omg_tools_b200.execution.batch_mpc import BatchMPC
+    bat = BatchMPC(sc.config5(), batch=256, update_time=0.1, jitter=0.1, seed=3)
+    start = bat.state.copy()
+    hist = bat.run(50)
+    status = np.array(hist['status'])
+    assert (status == 0).mean() > 0.97
+    # every vehicle made progress towards its goal
+    d0 = np.linalg.norm(start - bat.poseT, axis=1)
+    d1 = np.linalg.norm(bat.state - bat.poseT, axis=1)
+    assert np.all(d1 < d0)
+    assert np.isfinite(bat.state).all()
