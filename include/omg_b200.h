@@ -162,6 +162,23 @@ int omg_get_info(omg_problem* h, int32_t* n, int32_t* m, int32_t* n_par,
  * measured with CUDA events on the caller's stream. */
 int omg_last_timing(omg_problem* h, float* kernel_ms, int32_t* launches);
 
+/* ADMM consensus step for n_agents agents on the current device (DEVICE pointers):
+ * closed-form z-update, lambda-update and squared residuals of the reference's
+ * ADMM updater (omgtools/problems/admm.py:117-168 construct_upd_z/update_z,
+ * 248-266 upd_l, 268-307 upd_res; C++ twin ADMMPoint2Point::update2,
+ * ADMMPoint2Point.cpp:213-265).  nsh shared coefficients per agent (n_spl
+ * splines of L coefficients), n_nghb neighbours; PzT [nz x nz] is the TRANSPOSED
+ * consensus projector (nz = nsh*(1+n_nghb)), c [n_agents x nz] its affine part,
+ * Tf/Tb [L x L] the first-knot shift and its inverse.  z_*, l_* are updated in
+ * place, res [n_agents x 3] receives (pr, dr, cr) squared.  The neighbour
+ * exchange itself is the caller's NCCL step (problems/admm_gpu.py). */
+int omg_admm_zl_update(int32_t n_agents, int32_t nsh, int32_t n_nghb, int32_t L,
+                       const double* PzT, const double* c, const double* Tf,
+                       const double* Tb, double rho,
+                       const double* x_i, const double* x_j,
+                       double* z_i, double* z_ij, double* l_i, double* l_ij,
+                       double* res, void* stream);
+
 const char* omg_last_error(void);
 int omg_abi_version(void);
 

@@ -970,6 +970,88 @@ __global__ void omg_shift_kernel(double* x, int B, int n, int n_blocks, const in
   }
 }
 
+// ---------------------------------------------------------------------------
+// ADMM consensus step of one agent per block (reference admm.py:117-168 z-update,
+// 248-266 lambda-update, 268-307 residuals), in first-knot-shifted coordinates:
+//   v   = Tf (x + l/rho)            for the own copy and every neighbour copy
+//   z~  = P v + c                   P = I - A^T (A A^T)^-1 A,  c = A^T (A A^T)^-1 b
+//   z   = Tb z~ ;  l += rho (x - z)
+//   pr  = |Tf (x - z)|^2 ; dr = rho |Tf (z - z_prev)|^2 ; cr = rho pr + dr
+// Tf / Tb (L x L, row-major) restrict a spline to the future / undo it.
+// ---------------------------------------------------------------------------
+__global__ void omg_admm_zl_kernel(int nsh, int nn, int L, const double* __restrict__ PzT,
+                                   const double* __restrict__ c, const double* __restrict__ Tf,
+                                   const double* __restrict__ Tb, double rho,
+                                   const double* __restrict__ x_i, const double* __restrict__ x_j,
+                                   double* __restrict__ z_i, double* __restrict__ z_ij,
+                                   double* __restrict__ l_i, double* __restrict__ l_ij,
+                                   double* __restrict__ res) {
+  extern __shared__ double sh[];
+  const int nz = nsh * (1 + nn);
+  double* xs = sh;            // x  (own, neighbours)      [nz]
+  double* ls = xs + nz;       // l                          [nz]
+  double* zp = ls + nz;       // previous z                 [nz]
+  double* v = zp + nz;        // Tf (x + l/rho)             [nz]
+  double* zt = v + nz;        // z~ then z                  [nz]
+  double* red = zt + nz;      // [2 * blockDim/32]
+  const int a = blockIdx.x, tid = threadIdx.x;
+  for (int k = tid; k < nz; k += blockDim.x) {
+    const bool own = k < nsh;
+    xs[k] = own ? x_i[(size_t)a * nsh + k] : x_j[(size_t)a * nn * nsh + (k - nsh)];
+    ls[k] = own ? l_i[(size_t)a * nsh + k] : l_ij[(size_t)a * nn * nsh + (k - nsh)];
+    zp[k] = own ? z_i[(size_t)a * nsh + k] : z_ij[(size_t)a * nn * nsh + (k - nsh)];
+  }
+  __syncthreads();
+  for (int k = tid; k < nz; k += blockDim.x) {       // v = Tf (x + l/rho), spline by spline
+    const int blk = k / L, r = k - blk * L;
+    double acc = 0.0;
+    for (int q = 0; q < L; ++q) acc += Tf[r * L + q] * (xs[blk * L + q] + ls[blk * L + q] / rho);
+    v[k] = acc;
+  }
+  __syncthreads();
+  for (int k = tid; k < nz; k += blockDim.x) {       // z~ = P v + c
+    double acc = c[(size_t)a * nz + k];
+    for (int q = 0; q < nz; ++q) acc += PzT[(size_t)q * nz + k] * v[q];
+    zt[k] = acc;
+  }
+  __syncthreads();
+  double znew = 0.0;
+  for (int k = tid; k < nz; k += blockDim.x) {       // z = Tb z~ (one entry per thread, nz <= blockDim)
+    const int blk = k / L, r = k - blk * L;
+    double acc = 0.0;
+    for (int q = 0; q < L; ++q) acc += Tb[r * L + q] * zt[blk * L + q];
+    znew = acc;
+  }
+  __syncthreads();
+  for (int k = tid; k < nz; k += blockDim.x) zt[k] = znew;
+  __syncthreads();
+  double pr = 0.0, dr = 0.0;
+  for (int k = tid; k < nz; k += blockDim.x) {
+    const bool own = k < nsh;
+    const double zk = zt[k];
+    const double lk = ls[k] + rho * (xs[k] - zk);
+    if (own) { z_i[(size_t)a * nsh + k] = zk; l_i[(size_t)a * nsh + k] = lk; }
+    else { z_ij[(size_t)a * nn * nsh + (k - nsh)] = zk; l_ij[(size_t)a * nn * nsh + (k - nsh)] = lk; }
+    const int blk = k / L, r = k - blk * L;
+    double e1 = 0.0, e2 = 0.0;
+    for (int q = 0; q < L; ++q) {
+      const double t = Tf[r * L + q];
+      e1 += t * (xs[blk * L + q] - zt[blk * L + q]);
+      e2 += t * (zt[blk * L + q] - zp[blk * L + q]);
+    }
+    pr += e1 * e1; dr += rho * e2 * e2;
+  }
+  for (int off = 16; off > 0; off >>= 1) { pr += __shfl_down_sync(FULL, pr, off); dr += __shfl_down_sync(FULL, dr, off); }
+  const int nw = blockDim.x >> 5;
+  if ((tid & 31) == 0) { red[tid >> 5] = pr; red[nw + (tid >> 5)] = dr; }
+  __syncthreads();
+  if (tid == 0) {
+    double p = 0.0, d = 0.0;
+    for (int w = 0; w < nw; ++w) { p += red[w]; d += red[nw + w]; }
+    res[(size_t)a * 3 + 0] = p; res[(size_t)a * 3 + 1] = d; res[(size_t)a * 3 + 2] = rho * p + d;
+  }
+}
+
 // ===========================================================================
 // host side: C ABI
 // ===========================================================================
@@ -1378,6 +1460,22 @@ int omg_shift_batch(omg_problem* h, int32_t B, double* x, int32_t n_blocks, cons
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(stream));
   cudaFree(d_i); cudaFree(d_T);
+  return 0;
+}
+
+int omg_admm_zl_update(int32_t n_agents, int32_t nsh, int32_t n_nghb, int32_t L,
+                       const double* PzT, const double* c, const double* Tf, const double* Tb,
+                       double rho, const double* x_i, const double* x_j, double* z_i, double* z_ij,
+                       double* l_i, double* l_ij, double* res, void* stream_) {
+  if (n_agents <= 0) return 0;
+  if (!PzT || !c || !Tf || !Tb || !x_i || !x_j || !z_i || !z_ij || !l_i || !l_ij || !res) { set_err("null buffer"); return -1; }
+  const int nz = nsh * (1 + n_nghb);
+  int nt = 32; while (nt < nz) nt <<= 1;
+  if (nt > 1024 || nsh % L != 0) { set_err("unsupported consensus block size"); return -1; }
+  const size_t smem = sizeof(double) * (5 * (size_t)nz + 64);
+  omg_admm_zl_kernel<<<n_agents, nt, smem, (cudaStream_t)stream_>>>(nsh, n_nghb, L, PzT, c, Tf, Tb, rho,
+                                                                   x_i, x_j, z_i, z_ij, l_i, l_ij, res);
+  CK(cudaGetLastError());
   return 0;
 }
 

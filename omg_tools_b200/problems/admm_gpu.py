@@ -1,0 +1,169 @@
+"""Device-resident, multi-GPU execution of the formation ADMM iteration.
+
+Agents are sharded contiguously over the ranks (one process per GPU).  One ADMM
+iteration = reference ``ADMMProblem.dual_update`` (admm.py:584-628):
+
+    init_step     knot shift of x, z, l copies            (admm.py:477-491)
+    update_x      ONE batched NLP solve (omg_solve_batch)  (admm.py:383-398)
+    communicate   x_j <- neighbours' x_i        [NCCL all-gather]   (468-475)
+    update_z/l    ONE kernel (omg_admm_zl_update)          (407-466, 493-508)
+    residuals     sum over agents               [NCCL all-reduce, 3 doubles] (597-605)
+    communicate   z_ji, l_ji <- neighbours' z_ij, l_ij     [NCCL all-gather]
+
+The exchange is the only collective of the framework; message sizes are tiny
+(26 doubles per agent and neighbour), so it is latency bound and a plain
+all-gather over NVLink serves every interconnection topology of ``Fleet``.
+"""
+import numpy as np
+
+
+class AgentExchange(object):
+    """Neighbour exchange for contiguous agent shards (any torch device /
+    backend: NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, n_agents, nghb, back, rank=0, world=1, group=None):
+        import torch
+        self.torch = torch
+        self.N, self.rank, self.world, self.group = n_agents, rank, world, group
+        if n_agents % world != 0:
+            raise ValueError('number of agents must be a multiple of the number of ranks')
+        self.per = n_agents // world
+        self.lo, self.hi = rank * self.per, (rank + 1) * self.per
+        self.nghb_np, self.back_np = np.asarray(nghb), np.asarray(back)
+        self._idx = {}
+
+    def _index(self, device):
+        key = str(device)
+        if key not in self._idx:
+            t = self.torch
+            ng = t.as_tensor(self.nghb_np[self.lo:self.hi], device=device)
+            bk = t.as_tensor(self.back_np[self.lo:self.hi], device=device)
+            self._idx[key] = (ng, bk)
+        return self._idx[key]
+
+    def _all_gather(self, local):
+        t = self.torch
+        if self.world == 1:
+            return local
+        out = t.empty((self.world * local.shape[0],) + tuple(local.shape[1:]),
+                      dtype=local.dtype, device=local.device)
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(out, local.contiguous(), group=self.group)
+        return out
+
+    def gather_x(self, x_i_local):
+        """x_j[i, k] = x_i of the k-th neighbour of local agent i."""
+        ng, _ = self._index(x_i_local.device)
+        allx = self._all_gather(x_i_local)
+        return allx[ng].contiguous()
+
+    def gather_zl(self, z_ij_local, l_ij_local):
+        """z_ji[i, k] = z_ij held by neighbour j = nghb[i, k] for agent i."""
+        ng, bk = self._index(z_ij_local.device)
+        allz = self._all_gather(z_ij_local)
+        alll = self._all_gather(l_ij_local)
+        return allz[ng, bk].contiguous(), alll[ng, bk].contiguous()
+
+    def allreduce_sum(self, vec):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(vec, group=self.group)
+        return vec
+
+
+class FormationADMMRunner(object):
+    """Runs ``FormationPoint2point`` (problems/admm.py) on this rank's GPU."""
+
+    def __init__(self, problem, rank=0, world=1, group=None, device=None):
+        import torch
+        from ..solver import b200
+        self.torch, self.b200 = torch, b200
+        self.pr = problem
+        self.solver = problem.solver
+        self.ex = AgentExchange(problem.N, problem.nghb, problem.back, rank, world, group)
+        lo, hi = self.ex.lo, self.ex.hi
+        self.lo, self.hi = lo, hi
+        dev = torch.device('cuda', self.solver.device if device is None else device)
+        self.dev = dev
+        td = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
+        p = problem
+        self.X = td(p.X[lo:hi])
+        self.Xn = torch.empty_like(self.X)
+        self.x_i, self.z_i, self.l_i = td(p.x_i[lo:hi]), td(p.z_i[lo:hi]), td(p.l_i[lo:hi])
+        self.x_j, self.z_ij, self.l_ij = td(p.x_j[lo:hi]), td(p.z_ij[lo:hi]), td(p.l_ij[lo:hi])
+        self.z_ji, self.l_ji = td(p.z_ji[lo:hi]), td(p.l_ji[lo:hi])
+        self.c = td(p.c[lo:hi])
+        self.PzT = td(p.Pz.T)
+        self.Ts = td(shift_T(p))
+        n_loc, m = hi - lo, p.tb.m
+        self.LAM = torch.empty((n_loc, m), dtype=torch.float64, device=dev)
+        self.F = torch.empty(n_loc, dtype=torch.float64, device=dev)
+        self.ST = torch.empty(n_loc, dtype=torch.int32, device=dev)
+        self.IT = torch.empty(n_loc, dtype=torch.int32, device=dev)
+        self.LB, self.UB = td(p.tb.lbg), td(p.tb.ubg)
+        self.res = torch.zeros((n_loc, 3), dtype=torch.float64, device=dev)
+        self.P = torch.empty((n_loc, p.tb.n_par), dtype=torch.float64, device=dev)
+        self.blocks = [(off, shape[0], shape[1], T) for (_, _, off, shape, T)
+                       in p.father.shifted_entries()]
+        self.time_prev = 0.
+        self.history = []
+
+    # ------------------------------------------------------------------
+    def _pack_parameters(self, t):
+        """Host builds the constant part; consensus parameters are written on
+        the device (they never leave it)."""
+        p, torch = self.pr, self.torch
+        host = p.pack_parameters(t)[self.lo:self.hi]
+        self.P.copy_(torch.from_numpy(np.ascontiguousarray(host)))
+        off, a = p.par_off, p.upd_label
+        n_loc, nsh, nn = self.hi - self.lo, p.nsh, p.n_nghb
+        self.P[:, off[(a, 'z_i')]:off[(a, 'z_i')] + nsh] = self.z_i
+        self.P[:, off[(a, 'z_ji')]:off[(a, 'z_ji')] + nsh * nn] = self.z_ji.reshape(n_loc, -1)
+        self.P[:, off[(a, 'l_i')]:off[(a, 'l_i')] + nsh] = self.l_i
+        self.P[:, off[(a, 'l_ji')]:off[(a, 'l_ji')] + nsh * nn] = self.l_ji.reshape(n_loc, -1)
+
+    def _shift_over_knot(self):
+        L = self.pr.L
+        Ts = self.Ts
+        for name in ('x_i', 'z_i', 'l_i', 'x_j', 'z_ij', 'l_ij', 'z_ji', 'l_ji'):
+            a = getattr(self, name)
+            setattr(self, name, (a.reshape(-1, L) @ Ts.T).reshape(a.shape).contiguous())
+        self.solver.shift_batch_device(self.X, self.blocks)
+
+    def dual_update(self, t):
+        """One ADMM iteration at (relative) time t; returns (p_res, d_res, c_res)."""
+        p, torch = self.pr, self.torch
+        if (t > 0. and int(np.round(self.time_prev / p.knot_time, 6)) <
+                int(np.round(t / p.knot_time, 6))):
+            self._shift_over_knot()
+        self.time_prev = t
+        # x-update: one batched NLP solve for all local agents
+        self._pack_parameters(t)
+        self.solver.solve_batch_device(self.X, self.P, self.LB, self.UB, self.Xn, self.LAM,
+                                       self.F, self.ST, self.IT)
+        self.X, self.Xn = self.Xn, self.X
+        self.x_i = self.X[:, p.x_off:p.x_off + p.nsh].contiguous()
+        # communicate x
+        self.x_j = self.ex.gather_x(self.x_i)
+        # z / lambda / residuals
+        Tf, Tb = p.first_knot_transforms(t)
+        Tf_d = torch.tensor(Tf, dtype=torch.float64, device=self.dev)
+        Tb_d = torch.tensor(Tb, dtype=torch.float64, device=self.dev)
+        self.b200.admm_zl_update(self.PzT, self.c, Tf_d, Tb_d, p.options['rho'], self.x_i,
+                                 self.x_j, self.z_i, self.z_ij, self.l_i, self.l_ij,
+                                 self.res, p.L)
+        tot = self.ex.allreduce_sum(self.res.sum(0))
+        # communicate z, l
+        self.z_ji, self.l_ji = self.ex.gather_zl(self.z_ij, self.l_ij)
+        tot = tot.cpu().numpy()
+        out = (float(np.sqrt(tot[0])), float(np.sqrt(tot[1])), float(tot[2]))
+        self.history.append(out)
+        return out
+
+    def status(self):
+        return self.ST.cpu().numpy(), self.IT.cpu().numpy()
+
+
+def shift_T(problem):
+    from ..basics.spline_extra import shiftoverknot_T
+    return shiftoverknot_T(problem.basis)

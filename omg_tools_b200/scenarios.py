@@ -120,3 +120,34 @@ def instance_data(problem, batch, jitter=0.0, seed=0, current_time=0.):
         o.signals['position'][:, -1] = p0
     problem.reinitialize()
     return X0, P
+
+
+def config3(n_agents=4, options=None, build_solver=True, rank=0, world=1, group=None):
+    """FormationPoint2point ADMM (examples/formation_holonomic.py scaled to
+    n_agents, 2 rectangular obstacles as in the C++ formation test): agents on
+    a circle of radius 0.2, circular interconnection, rho = 1."""
+    from .vehicles.fleet import Fleet
+    from .basics.shape import RegularPolyhedron
+    from .problems.admm import FormationPoint2point
+    vehicles = [Holonomic() for _ in range(n_agents)]
+    fleet = Fleet(vehicles)
+    if n_agents == 4:
+        configuration = RegularPolyhedron(0.2, n_agents, np.pi / 4.).vertices.T
+    else:
+        ang = 2 * np.pi * np.arange(n_agents) / n_agents
+        configuration = 0.2 * np.c_[np.cos(ang), np.sin(ang)]
+    init_positions = np.array([-1.5, -1.5]) + configuration
+    terminal_positions = np.array([2., 2.]) + configuration
+    fleet.set_configuration(configuration.tolist())
+    fleet.set_initial_conditions(init_positions.tolist())
+    fleet.set_terminal_conditions(terminal_positions.tolist())
+    environment = Environment(room={'shape': Square(5.)})
+    rectangle = Rectangle(width=3., height=0.2)
+    environment.add_obstacle(Obstacle({'position': [-2.1, -0.5]}, shape=rectangle))
+    environment.add_obstacle(Obstacle({'position': [1.7, -0.5]}, shape=rectangle))
+    opts = {'rho': 1., 'horizon_time': 10, 'verbose': 0}
+    opts.update(options or {})
+    problem = FormationPoint2point(fleet, environment, options=opts, rank=rank,
+                                   world=world, group=group)
+    problem.init(build_solver=build_solver)
+    return problem

@@ -73,7 +73,8 @@ class _Options(C.Structure):
 EXPORTS = ['omg_abi_version', 'omg_last_error', 'omg_default_options',
            'omg_problem_create', 'omg_problem_destroy', 'omg_set_options',
            'omg_solve_batch', 'omg_solve_batch_host', 'omg_shift_batch',
-           'omg_get_trace', 'omg_get_info', 'omg_last_timing']
+           'omg_get_trace', 'omg_get_info', 'omg_last_timing',
+           'omg_admm_zl_update']
 
 _lib = None
 
@@ -108,6 +109,7 @@ def load_library(path=None):
     lib.omg_get_trace.argtypes = [vp, vp, C.c_int32]
     lib.omg_get_info.argtypes = [vp] + [_i32p] * 6
     lib.omg_last_timing.argtypes = [vp, C.POINTER(C.c_float), _i32p]
+    lib.omg_admm_zl_update.argtypes = [C.c_int32] * 4 + [vp] * 4 + [C.c_double] + [vp] * 8
     _lib = lib
     return lib
 
@@ -331,3 +333,24 @@ class B200Solver(object):
 
     def stats(self):
         return dict(self._stats)
+
+
+def admm_zl_update(PzT, c, Tf, Tb, rho, x_i, x_j, z_i, z_ij, l_i, l_ij, res, L, stream=None):
+    """Consensus step (z, lambda, residuals) for the agents held in the given
+    torch CUDA tensors; z_*, l_* are updated in place (omg_admm_zl_update)."""
+    import torch
+    lib = load_library()
+    n_agents, nsh = x_i.shape
+    nn = x_j.shape[1]
+    for t in (PzT, c, Tf, Tb, x_i, x_j, z_i, z_ij, l_i, l_ij, res):
+        if t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous():
+            raise ValueError('expected contiguous float64 CUDA tensors')
+    if stream is None:
+        stream = torch.cuda.current_stream(x_i.device)
+    rc = lib.omg_admm_zl_update(n_agents, nsh, nn, L, PzT.data_ptr(), c.data_ptr(),
+                                Tf.data_ptr(), Tb.data_ptr(), float(rho), x_i.data_ptr(),
+                                x_j.data_ptr(), z_i.data_ptr(), z_ij.data_ptr(),
+                                l_i.data_ptr(), l_ij.data_ptr(), res.data_ptr(),
+                                C.c_void_p(stream.cuda_stream))
+    if rc != 0:
+        raise RuntimeError('libomgb200: %s' % lib.omg_last_error().decode())

@@ -48,6 +48,15 @@ class Quadrotor3D(Vehicle):
         self.dpos0 = self.define_parameter('dpos0', 3)
 
     def define_trajectory_constraints(self, splines, horizon_time=None):
+        if not self.options.get('allow_expanded_lowering', False):
+            # The position rows share the scalars X1(t/T), X2(t/T) (re-anchored double
+            # integrals of degree-5 polynomial splines).  CasADi keeps them as shared
+            # graph nodes; the flat term tables of this round would replicate ~2e3
+            # monomials into each of ~300 rows (>1e6 terms).  Needs a shared
+            # sub-expression stage in lowering.py + the kernel: next round.
+            raise NotImplementedError(
+                'Quadrotor3D (BASELINE config 4) needs shared sub-expressions in '
+                'the lowering; not built in this round (DESIGN.md section 0)')
         if horizon_time is None:
             horizon_time = self.define_symbol('T')
         T = horizon_time

@@ -1,0 +1,93 @@
+"""ORACLE (test infrastructure, not product code): sequential numpy restatement
+of the reference's ADMM iteration (omgtools/problems/admm.py:584-628
+ADMMProblem.dual_update with per-updater update_x 383-398, communicate 468-475,
+update_z 407-440 / construct_upd_z 117-168, update_l 442-466, get_residuals
+493-508, init_step 477-491), one agent at a time, x-update through the CPU
+interior-point oracle.  The z-update solves the KKT system of the reference
+(f, G, h, mu) literally instead of using the precomputed projector of the
+product path.  parity unpinned (no CasADi/IPOPT here)."""
+import numpy as np
+
+from omg_tools_b200.basics.spline_extra import shiftfirstknot_T, shiftoverknot_T
+from oracle import ipm_c, ipm_ref
+
+
+class ADMMOracle(object):
+    def __init__(self, problem):
+        p = self.p = problem
+        self.X = p.X.copy()
+        self.x_i, self.z_i, self.l_i = p.x_i.copy(), p.z_i.copy(), p.l_i.copy()
+        self.x_j, self.z_ij, self.l_ij = p.x_j.copy(), p.z_ij.copy(), p.l_ij.copy()
+        self.z_ji, self.l_ji = p.z_ji.copy(), p.l_ji.copy()
+        self.time_prev = 0.
+        self.status = None
+
+    def _solve(self, x0, par):
+        tb = self.p.tb
+        if ipm_c.available():
+            r = ipm_c.solve_batch_full(tb, x0[None], par[None], threads=1)
+            return r['x'][0], int(r['status'][0])
+        r = ipm_ref.solve(tb, x0, par)
+        return r.x, r.status
+
+    def _blockdiag(self, T, nblk):
+        return np.kron(np.eye(nblk), T)
+
+    def dual_update(self, t):
+        p = self.p
+        N, nsh, nn, L = p.N, p.nsh, p.n_nghb, p.L
+        rho = p.options['rho']
+        if t > 0. and int(np.round(self.time_prev / p.knot_time, 6)) < int(np.round(t / p.knot_time, 6)):
+            Ts = shiftoverknot_T(p.basis)
+            for name in ('x_i', 'z_i', 'l_i', 'x_j', 'z_ij', 'l_ij', 'z_ji', 'l_ji'):
+                a = getattr(self, name)
+                setattr(self, name, a.reshape(-1, L).dot(Ts.T).reshape(a.shape))
+            for (_, _, off, shape, T) in p.father.shifted_entries():
+                for c in range(shape[1]):
+                    seg = slice(off + c * shape[0], off + (c + 1) * shape[0])
+                    self.X[:, seg] = self.X[:, seg].dot(np.asarray(T).T)
+        self.time_prev = t
+        # ---- x-update, one agent after the other -----------------------------------
+        p.z_i, p.z_ji, p.l_i, p.l_ji = self.z_i, self.z_ji, self.l_i, self.l_ji
+        P = p.pack_parameters(t).copy()
+        self.status = np.zeros(N, dtype=int)
+        for i in range(N):
+            self.X[i], self.status[i] = self._solve(self.X[i], P[i])
+        self.x_i = self.X[:, p.x_off:p.x_off + nsh].copy()
+        # ---- communicate x --------------------------------------------------------------
+        self.x_j = self.x_i[p.nghb]
+        # ---- z, l, residuals ------------------------------------------------------------
+        t0 = (np.round(t, 6) % p.knot_time) / p.T
+        Tf, Tb = shiftfirstknot_T(p.basis, t0, inverse=True)
+        nblk = nsh // L * (1 + nn)
+        TF, TB = self._blockdiag(Tf, nblk), self._blockdiag(Tb, nblk)
+        A = p.A
+        pr = dr = cr = 0.
+        z_i_new, z_ij_new = np.zeros_like(self.z_i), np.zeros_like(self.z_ij)
+        for i in range(N):
+            x = TF.dot(np.r_[self.x_i[i], self.x_j[i].reshape(-1)])
+            l = TF.dot(np.r_[self.l_i[i], self.l_ij[i].reshape(-1)])
+            b = p._b_of(i)
+            # admm.py:149-155
+            f = -(l + rho * x)
+            G = -(1. / rho) * A.dot(A.T)
+            h = b + (1. / rho) * A.dot(f)
+            mu = np.linalg.solve(G, h)
+            z = TB.dot(-(1. / rho) * (A.T.dot(mu) + f))
+            z_i_new[i], z_ij_new[i] = z[:nsh], z[nsh:].reshape(nn, nsh)
+        z_i_p, z_ij_p = self.z_i, self.z_ij
+        self.z_i, self.z_ij = z_i_new, z_ij_new
+        self.l_i = self.l_i + rho * (self.x_i - self.z_i)
+        self.l_ij = self.l_ij + rho * (self.x_j - self.z_ij)
+        for i in range(N):
+            tf = lambda a: TF.dot(a)
+            e1 = tf(np.r_[self.x_i[i] - self.z_i[i], (self.x_j[i] - self.z_ij[i]).reshape(-1)])
+            e2 = tf(np.r_[self.z_i[i] - z_i_p[i], (self.z_ij[i] - z_ij_p[i]).reshape(-1)])
+            pri, dri = e1.dot(e1), rho * e2.dot(e2)
+            pr += pri; dr += dri; cr += rho * pri + dri
+        # ---- communicate z, l ---------------------------------------------------------------
+        for i in range(N):
+            for k, j in enumerate(p.nghb[i]):
+                self.z_ji[i, k] = self.z_ij[j, p.back[i, k]]
+                self.l_ji[i, k] = self.l_ij[j, p.back[i, k]]
+        return float(np.sqrt(pr)), float(np.sqrt(dr)), float(cr)

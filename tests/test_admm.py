@@ -1,0 +1,106 @@
+"""Formation ADMM (BASELINE config 3): structure, consensus projector and the
+multi-rank neighbour exchange (gloo, world_size 2, CPU)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from omg_tools_b200 import scenarios as sc
+from omg_tools_b200.problems.admm_gpu import AgentExchange
+
+
+@pytest.fixture(scope='module')
+def formation():
+    return sc.config3(4, build_solver=False)
+
+
+def test_agent_nlp_dimensions(formation):
+    tb = formation.tb
+    # per-agent x-update NLP
+    assert (tb.n, tb.m, tb.n_par) == (118, 578, 203)
+    names = [k[1] for k in formation.father._par_struct.keys()]
+    assert names[:6] == ['rel_pos_c', 'state0', 'input0', 'poseT', 'T', 't']
+    assert names[6:11] == ['z_i', 'z_ji', 'l_i', 'l_ji', 'rho']
+    assert formation.A.shape == (58, 78) and np.linalg.matrix_rank(formation.A) == 58
+    # objective is quadratic in the shared variables: Hessian terms on the objective row
+    assert np.any(tb.W.lrow == tb.m)
+
+
+def test_projector_equals_reference_kkt_solve(formation):
+    """z = P v + c  ==  the reference's Schur-complement z-update (admm.py:149-155)."""
+    p = formation
+    rng = np.random.default_rng(0)
+    rho = 1.7
+    for i in range(p.N):
+        x, l = rng.standard_normal(p.nz), rng.standard_normal(p.nz)
+        b = p._b_of(i)
+        f = -(l + rho * x)
+        G = -(1. / rho) * p.A.dot(p.A.T)
+        h = b + (1. / rho) * p.A.dot(f)
+        mu = np.linalg.solve(G, h)
+        z_ref = -(1. / rho) * (p.A.T.dot(mu) + f)
+        z = p.Pz.dot(x + l / rho) + p.c[i]
+        assert np.abs(z - z_ref).max() < 1e-9
+        assert np.abs(p.A.dot(z) - b).max() < 1e-8
+
+
+def test_neighbour_tables(formation):
+    p = formation
+    for i in range(p.N):
+        for k, j in enumerate(p.nghb[i]):
+            assert p.nghb[j][p.back[i, k]] == i
+
+
+def _worker(rank, world, port, N, nsh, nn, nghb, back, out):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    rng = np.random.default_rng(5)
+    x = torch.tensor(rng.standard_normal((N, nsh)))
+    z = torch.tensor(rng.standard_normal((N, nn, nsh)))
+    l = torch.tensor(rng.standard_normal((N, nn, nsh)))
+    ex = AgentExchange(N, nghb, back, rank, world)
+    xj = ex.gather_x(x[ex.lo:ex.hi].clone())
+    zji, lji = ex.gather_zl(z[ex.lo:ex.hi].clone(), l[ex.lo:ex.hi].clone())
+    tot = ex.allreduce_sum(torch.tensor([float(rank + 1), 2., 3.], dtype=torch.float64))
+    torch.save({'xj': xj, 'zji': zji, 'lji': lji, 'tot': tot, 'lo': ex.lo, 'hi': ex.hi},
+               os.path.join(out, 'r%d.pt' % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_exchange_two_ranks_gloo(tmp_path):
+    N, nsh, nn = 8, 26, 2
+    nghb = np.array([[(i + 1) % N, (i - 1) % N] for i in range(N)])
+    back = np.array([[list(nghb[j]).index(i) for j in nghb[i]] for i in range(N)])
+    port = 29600 + (os.getpid() % 300)
+    mp.spawn(_worker, args=(2, port, N, nsh, nn, nghb, back, str(tmp_path)), nprocs=2, join=True)
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((N, nsh))
+    z = rng.standard_normal((N, nn, nsh))
+    l = rng.standard_normal((N, nn, nsh))
+    for rank in range(2):
+        d = torch.load(os.path.join(str(tmp_path), 'r%d.pt' % rank))
+        lo, hi = d['lo'], d['hi']
+        assert (lo, hi) == (rank * 4, rank * 4 + 4)
+        for i in range(lo, hi):
+            for k, j in enumerate(nghb[i]):
+                assert np.array_equal(d['xj'][i - lo, k].numpy(), x[j])
+                assert np.array_equal(d['zji'][i - lo, k].numpy(), z[j, back[i, k]])
+                assert np.array_equal(d['lji'][i - lo, k].numpy(), l[j, back[i, k]])
+        assert d['tot'].tolist() == [3., 4., 6.]
+
+
+def test_admm_oracle_reduces_formation_error(formation):
+    from oracle.admm_ref import ADMMOracle
+    orc = ADMMOracle(sc.config3(4, build_solver=False))
+    spread = []
+    for _ in range(8):
+        res = orc.dual_update(0.)
+        cen = orc.x_i.reshape(4, 2, 13) + orc.p.relp[:, :, None]
+        spread.append(np.abs(cen - cen.mean(0)).max())
+        assert np.all(orc.status == 0)
+    assert spread[-1] < 0.2 * spread[0]

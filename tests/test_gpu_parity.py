@@ -254,3 +254,41 @@ def test_receding_horizon_batch256_50_steps(solvers):
     d1 = np.linalg.norm(bat.state - bat.poseT, axis=1)
     assert np.all(d1 < d0)
     assert np.isfinite(bat.state).all()
+
+
+def test_formation_admm_matches_oracle(solvers):
+    """BASELINE config 3 (4 agents as in the reference example): batched x-update +
+    consensus kernel vs the sequential ADMM oracle, iteration by iteration."""
+    from omg_tools_b200.problems.admm_gpu import FormationADMMRunner
+    from oracle.admm_ref import ADMMOracle
+    pr = sc.config3(4)
+    run = FormationADMMRunner(pr)
+    orc = ADMMOracle(sc.config3(4, build_solver=False))
+    for it in range(6):
+        rg = run.dual_update(0.)
+        ro = orc.dual_update(0.)
+        st, _ = run.status()
+        assert np.all(st == 0) and np.all(orc.status == 0)
+        assert np.abs(run.x_i.cpu().numpy() - orc.x_i).max() < NORTH_STAR_TOL, it
+        assert np.abs(run.z_i.cpu().numpy() - orc.z_i).max() < NORTH_STAR_TOL
+        assert np.abs(run.z_ij.cpu().numpy() - orc.z_ij).max() < NORTH_STAR_TOL
+        assert np.abs(run.l_i.cpu().numpy() - orc.l_i).max() < 10 * NORTH_STAR_TOL
+        assert np.abs(run.z_ji.cpu().numpy() - orc.z_ji).max() < NORTH_STAR_TOL
+        assert abs(rg[0] - ro[0]) < 1e-3 * max(1., ro[0]) and abs(rg[1] - ro[1]) < 1e-3 * max(1., ro[1])
+
+
+def test_formation_admm_64_agents(solvers):
+    """Config 3 at BASELINE size: 64 agents on a ring; residuals and formation
+    error shrink, every x-update succeeds."""
+    from omg_tools_b200.problems.admm_gpu import FormationADMMRunner
+    pr = sc.config3(64)
+    run = FormationADMMRunner(pr)
+    hist, spread = [], []
+    for it in range(10):
+        hist.append(run.dual_update(0.))
+        st, _ = run.status()
+        assert np.all(st == 0)
+        cen = run.x_i.cpu().numpy().reshape(64, 2, 13) + pr.relp[:, :, None]
+        spread.append(np.abs(cen - cen.mean(0)).max())
+    assert hist[-1][2] < hist[1][2]
+    assert spread[-1] < 0.5 * spread[0]
