@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define OMG_ABI_VERSION 2
+#define OMG_ABI_VERSION 3
 
 /* CSR list of polynomial terms per output slot:
  *   out[s] = sum_{t in [ptr[s],ptr[s+1])} coef[t] * V[cidx[t]]
@@ -101,6 +101,13 @@ typedef struct omg_options {
   double scaling_max_gradient;
   int32_t max_iter;
   int32_t trace;          /* 1: record per-iteration diagnostics (debug) */
+  /* feasibility restart, the stand-in for IPOPT's restoration phase: when the
+   * filter line search fails, keep x, re-centre the slacks (push restart_push),
+   * zero the multipliers, clear the filter and continue from mu = restart_mu;
+   * at most max_restarts times, then Restoration_Failed. */
+  int32_t max_restarts;
+  int32_t reserved;
+  double restart_mu, restart_push;
 } omg_options;
 
 /* per-instance status codes (mapped to IPOPT strings in solver/b200.py) */

@@ -87,7 +87,7 @@ struct Batch {
 struct Ctl {                       // uniform per-block control scalars
   double mu, tau, theta_max, theta_min, delta_w, delta_w_last, delta_c;
   double alpha, theta, phi, f, fsc;
-  int n_eq, n_bounds, iter, status, fail, eq_fail, first_try, nfilt, inst;
+  int n_eq, n_bounds, iter, status, fail, eq_fail, first_try, nfilt, inst, n_restart;
 };
 
 // IPOPT constants not exposed as options (oracle/ipm_ref.py DEFAULTS)
@@ -560,7 +560,7 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
       ctl.mu = O.mu_init; ctl.tau = fmax(TAU_MIN, 1.0 - O.mu_init);
       ctl.theta_max = -1.0; ctl.theta_min = -1.0;
       ctl.delta_w_last = 0.0; ctl.nfilt = 0; ctl.status = -1; ctl.iter = 0;
-      ctl.fsc = fsc; ctl.alpha = 0.0; ctl.delta_w = 0.0;
+      ctl.fsc = fsc; ctl.alpha = 0.0; ctl.delta_w = 0.0; ctl.n_restart = 0;
       ctl.f = fsc * eval_range(T.Ft, 0, T.n_f, V, xe);
     }
     __syncthreads();
@@ -884,6 +884,27 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
         alpha *= 0.5;
       }
       if (!accepted) {
+        if (ctl.n_restart < O.max_restarts) {
+          // feasibility restart (stand-in for IPOPT's restoration phase, oracle/ipm_ref.py):
+          // keep x, re-centre the slacks, zero the multipliers, clear the filter, mu = restart_mu
+          __syncthreads();
+          const double mu_r = O.restart_mu;
+          for (int i = tid; i < m; i += NT) {
+            const int r = rt[i];
+            double si = g[i];
+            if (r & 1) si = fmax(si, sL[i] + O.restart_push * fmax(1.0, fabs(sL[i])));
+            if (r & 2) si = fmin(si, sU[i] - O.restart_push * fmax(1.0, fabs(sU[i])));
+            s[i] = si; y[i] = 0.0;
+            if (r & 1) zL[i] = mu_r / (si - sL[i]);
+            if (r & 2) zU[i] = mu_r / (sU[i] - si);
+          }
+          if (tid == 0) {
+            ctl.n_restart += 1; ctl.mu = mu_r; ctl.tau = fmax(TAU_MIN, 1.0 - mu_r);
+            ctl.nfilt = 0; ctl.theta_max = -1.0; ctl.delta_w_last = 0.0;
+          }
+          __syncthreads();
+          continue;
+        }
         if (tid == 0) { ctl.status = OMG_RESTORATION_FAILED; ctl.iter = iter; }
         __syncthreads();
         break;
@@ -1115,6 +1136,7 @@ void omg_default_options(omg_options* o) {
   o->mu_init = 0.1; o->bound_push = 1e-3; o->bound_frac = 1e-3; o->mult_bound_push = 1e-3;
   o->bound_relax_factor = 1e-8; o->scaling_max_gradient = 100.0;
   o->max_iter = 3000; o->trace = 0;
+  o->max_restarts = 5; o->reserved = 0; o->restart_mu = 1.0; o->restart_push = 0.1;
 }
 
 omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, int device) {

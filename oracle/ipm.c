@@ -205,7 +205,7 @@ static void solve_one(const omg_tables* T, const omg_options* O, Work* w, const 
   double theta_max = -1.0, theta_min = -1.0, delta_w_last = 0.0;
   double filt[2 * MAXF]; int nfilt = 0;
   double f = fsc * eval_slot(&T->F, 0, V, xe);
-  int status = OMG_MAX_ITER_EXCEEDED, iter = 0;
+  int status = OMG_MAX_ITER_EXCEEDED, iter = 0, n_restarts = 0;
 
   for (iter = 0;; ++iter) {
     double cinf = 0, maxprod = 0, minprod = 1e300, viol = 0, rsinf = 0, rsinf_un = 0, ysum = 0,
@@ -357,7 +357,24 @@ static void solve_one(const omg_tables* T, const omg_options* O, Work* w, const 
       if (okk) { accepted = 1; break; }
       alpha *= 0.5;
     }
-    if (!accepted) { status = OMG_RESTORATION_FAILED; break; }
+    if (!accepted) {
+      if (n_restarts < O->max_restarts) {   /* feasibility restart (see ipm_ref.py) */
+        ++n_restarts;
+        mu = O->restart_mu; tau = fmax(TAU_MIN, 1.0 - mu);
+        for (int i = 0; i < m; ++i) {
+          const int r = rt[i];
+          double si = g[i];
+          if (r & 1) si = fmax(si, sL[i] + O->restart_push * fmax(1.0, fabs(sL[i])));
+          if (r & 2) si = fmin(si, sU[i] - O->restart_push * fmax(1.0, fabs(sU[i])));
+          s[i] = si; y[i] = 0.0;
+          zL[i] = (r & 1) ? mu / (si - sL[i]) : 0.0;
+          zU[i] = (r & 2) ? mu / (sU[i] - si) : 0.0;
+        }
+        nfilt = 0; theta_max = -1.0; delta_w_last = 0.0;
+        continue;
+      }
+      status = OMG_RESTORATION_FAILED; break;
+    }
     if (!ftype) {
       const double th = (1.0 - GAMMA_THETA) * theta, ph = phi - GAMMA_PHI * theta; int nf = 0;
       for (int q = 0; q < nfilt; ++q) if (!(filt[2 * q] >= th && filt[2 * q + 1] >= ph)) { filt[2 * nf] = filt[2 * q]; filt[2 * nf + 1] = filt[2 * q + 1]; ++nf; }
@@ -434,4 +451,5 @@ void oracle_default_options(omg_options* o) {
   o->tol = 1e-3; o->constr_viol_tol = 1e-4; o->dual_inf_tol = 1.0; o->compl_inf_tol = 1e-4;
   o->mu_init = 0.1; o->bound_push = 1e-3; o->bound_frac = 1e-3; o->mult_bound_push = 1e-3;
   o->bound_relax_factor = 1e-8; o->scaling_max_gradient = 100.0; o->max_iter = 3000; o->trace = 0;
+  o->max_restarts = 5; o->reserved = 0; o->restart_mu = 1.0; o->restart_push = 0.1;
 }

@@ -20,8 +20,8 @@ warm_start_init_point=yes) and IPOPT's documented defaults:
     1e-8, warm-start pushes 1e-3, multiplier safeguard kappa_Sigma=1e10.
 
 Deviations from IPOPT (documented in DESIGN.md): no second-order correction,
-no restoration phase (a soft-restoration step on the primal-dual error is
-tried instead, then status Restoration_Failed), inertia is checked on the
+no restoration phase (a feasibility restart -- slacks re-centred, multipliers
+and filter reset, mu = 1 -- is tried up to 5 times, then Restoration_Failed), inertia is checked on the
 condensed matrix H = W + J_d^T Sigma J_d (Cholesky) instead of the full
 augmented system.  parity unpinned: no IPOPT binary is available here.
 
@@ -45,7 +45,8 @@ DEFAULTS = dict(
     theta_min_fact=1e-4, delta_w0=1e-4, delta_w_min=1e-20, delta_w_max=1e40,
     kappa_w_plus_first=100.0, kappa_w_plus=8.0, kappa_w_minus=1.0 / 3.0,
     delta_c_val=1e-8, delta_c_exp=0.25, piv_tol=1e-12, inf_bound=1e19,
-    soft_resto_factor=0.9999, soft_resto=0, max_filter=32, max_ls=40)
+    soft_resto_factor=0.9999, soft_resto=0, max_filter=32, max_ls=40,
+    max_restarts=5, restart_mu=1.0, restart_push=1e-1)
 
 EPS = np.finfo(float).eps
 
@@ -128,6 +129,7 @@ def solve(tb, x0, p, lbg=None, ubg=None, options=None, lam_g0=None,
     filt = []
     theta_max = theta_min = None
     delta_w_last = 0.0
+    n_restarts = 0
     status, it = 1, 0
     log = []
 
@@ -329,6 +331,24 @@ def solve(tb, x0, p, lbg=None, ubg=None, options=None, lam_g0=None,
                     break
                 alpha *= 0.5
         if not accepted:
+            if n_restarts < o['max_restarts']:
+                # feasibility restart (stand-in for IPOPT's restoration phase): keep x,
+                # re-centre the slacks, forget the multipliers and the filter, and
+                # continue from a large barrier parameter
+                n_restarts += 1
+                mu = o['restart_mu']
+                tau = max(o['tau_min'], 1.0 - mu)
+                kp = o['restart_push']
+                s = g.copy()
+                s = np.where(hasL, np.maximum(s, sL + kp * np.maximum(1, np.abs(sL))), s)
+                s = np.where(hasU, np.minimum(s, sU - kp * np.maximum(1, np.abs(sU))), s)
+                y = np.zeros(m)
+                zL = np.where(hasL, mu / np.where(hasL, s - sL, 1.0), 0.0)
+                zU = np.where(hasU, mu / np.where(hasU, sU - s, 1.0), 0.0)
+                filt = []
+                theta_max = None
+                delta_w_last = 0.0
+                continue
             status = 2
             break
 
