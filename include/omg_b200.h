@@ -169,6 +169,16 @@ int omg_get_info(omg_problem* h, int32_t* n, int32_t* m, int32_t* n_par,
  * measured with CUDA events on the caller's stream. */
 int omg_last_timing(omg_problem* h, float* kernel_ms, int32_t* launches);
 
+/* Batched spline sampling (post-solve trajectory extraction, reference
+ * Vehicle.store -> sample_splines, omgtools/vehicles/vehicle.py:250-300,
+ * spline_extra.py:406-410; C++ twin Vehicle.cpp:112-190): for each of n_blocks
+ * spline variables (offset, basis length, columns) apply the HOST matrix
+ * S_blk [nsamp x len] (precomputed basis / derivative rows) to every column:
+ * out[b] = concat_blk( [col][sample] ), DEVICE x [B][n] and out [B][sum nsamp*ncols]. */
+int omg_sample_batch(int32_t B, int32_t n, const double* x, int32_t n_blocks,
+                     const int32_t* offs, const int32_t* lens, const int32_t* ncols,
+                     const int32_t* nsamp, const double* S, double* out, void* stream);
+
 /* ADMM consensus step for n_agents agents on the current device (DEVICE pointers):
  * closed-form z-update, lambda-update and squared residuals of the reference's
  * ADMM updater (omgtools/problems/admm.py:117-168 construct_upd_z/update_z,

@@ -991,6 +991,34 @@ __global__ void omg_shift_kernel(double* x, int B, int n, int n_blocks, const in
   }
 }
 
+// trajectory sampling: out[b, blk, c, s] = sum_k S_blk[s,k] * x[b, off_blk + c*len_blk + k]
+// (batched Cox-de Boor evaluation with precomputed basis rows; reference
+//  Vehicle.store -> sample_splines, vehicle.py:250-300, spline_extra.py:406-410;
+//  C++ twin Vehicle::sampleSplines, Vehicle.cpp:112-190)
+__global__ void omg_sample_kernel(const double* __restrict__ x, int B, int n, int n_blocks,
+                                  const int* __restrict__ offs, const int* __restrict__ lens,
+                                  const int* __restrict__ ncols, const int* __restrict__ nsamp,
+                                  const int* __restrict__ soffs, const int* __restrict__ ooffs,
+                                  const double* __restrict__ Sm, double* __restrict__ out, int n_out) {
+  extern __shared__ double xs[];
+  const int b = blockIdx.x;
+  if (b >= B) return;
+  const double* xb = x + (size_t)b * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) xs[i] = xb[i];
+  __syncthreads();
+  double* ob = out + (size_t)b * n_out;
+  for (int blk = 0; blk < n_blocks; ++blk) {
+    const int L = lens[blk], nc = ncols[blk], ns = nsamp[blk], off = offs[blk];
+    const double* Sb = Sm + soffs[blk];
+    for (int e = threadIdx.x; e < ns * nc; e += blockDim.x) {
+      const int c = e / ns, sidx = e - c * ns;
+      double acc = 0.0;
+      for (int k = 0; k < L; ++k) acc += Sb[sidx * L + k] * xs[off + c * L + k];
+      ob[ooffs[blk] + c * ns + sidx] = acc;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // ADMM consensus step of one agent per block (reference admm.py:117-168 z-update,
 // 248-266 lambda-update, 268-307 residuals), in first-knot-shifted coordinates:
@@ -1482,6 +1510,31 @@ int omg_shift_batch(omg_problem* h, int32_t B, double* x, int32_t n_blocks, cons
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(stream));
   cudaFree(d_i); cudaFree(d_T);
+  return 0;
+}
+
+int omg_sample_batch(int32_t B, int32_t n, const double* x, int32_t n_blocks, const int32_t* offs,
+                     const int32_t* lens, const int32_t* ncols, const int32_t* nsamp,
+                     const double* Sm, double* out, void* stream_) {
+  if (!x || !offs || !lens || !ncols || !nsamp || !Sm || !out) { set_err("null argument"); return -1; }
+  if (B <= 0 || n_blocks <= 0) return 0;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  std::vector<int> soffs(n_blocks), ooffs(n_blocks);
+  int stot = 0, otot = 0;
+  for (int b = 0; b < n_blocks; ++b) { soffs[b] = stot; stot += nsamp[b] * lens[b]; ooffs[b] = otot; otot += nsamp[b] * ncols[b]; }
+  int* d_i = nullptr; double* d_S = nullptr;
+  CK(cudaMalloc(&d_i, sizeof(int) * 6 * n_blocks));
+  CK(cudaMalloc(&d_S, sizeof(double) * stot));
+  const int32_t* hosts[6] = {offs, lens, ncols, nsamp, soffs.data(), ooffs.data()};
+  for (int k = 0; k < 6; ++k)
+    CK(cudaMemcpyAsync(d_i + k * n_blocks, hosts[k], sizeof(int) * n_blocks, cudaMemcpyHostToDevice, stream));
+  CK(cudaMemcpyAsync(d_S, Sm, sizeof(double) * stot, cudaMemcpyHostToDevice, stream));
+  omg_sample_kernel<<<B, 128, sizeof(double) * n, stream>>>(x, B, n, n_blocks, d_i, d_i + n_blocks, d_i + 2 * n_blocks,
+                                                           d_i + 3 * n_blocks, d_i + 4 * n_blocks, d_i + 5 * n_blocks,
+                                                           d_S, out, otot);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(stream));
+  cudaFree(d_i); cudaFree(d_S);
   return 0;
 }
 

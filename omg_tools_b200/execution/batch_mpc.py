@@ -21,8 +21,9 @@ import numpy as np
 
 class BatchMPC(object):
 
-    def __init__(self, problem, batch, update_time=0.1, jitter=0.0, seed=0):
+    def __init__(self, problem, batch, update_time=0.1, jitter=0.0, seed=0, device_predict=True):
         import torch
+        self.device_predict = device_predict
         self.torch = torch
         self.problem = problem
         self.solver = problem.problem
@@ -106,6 +107,20 @@ class BatchMPC(object):
             c = Xh[:, k * L:(k + 1) * L]
             self.state[:, k] = c.dot(B0)
             self.inp[:, k] = c.dot(B1) / self.T
+        return Xh
+
+    def _predict_device(self, t_rel, dt):
+        from ..solver.b200 import sample_batch
+        basis = self.vehicle.basis
+        tau = (t_rel + dt) / self.T
+        B0 = basis.eval_basis([tau])
+        Bd, P1 = basis.derivative(1)
+        B1 = Bd.eval_basis([tau]).dot(P1) / self.T
+        out = sample_batch(self.X, [(0, len(basis), 2, np.vstack([B0, B1]))]).cpu().numpy()
+        # layout: [column][sample] with samples (value, derivative)
+        self.state[:, 0], self.inp[:, 0] = out[:, 0], out[:, 1]
+        self.state[:, 1], self.inp[:, 1] = out[:, 2], out[:, 3]
+        return None
 
     def _advance_obstacles(self, dt):
         for d in self.obs:
@@ -127,12 +142,13 @@ class BatchMPC(object):
         self.solver.solve_batch_device(self.X, self.Pd, self.LB, self.UB, self.Xn,
                                        self.LAM, self.F, self.ST, self.IT)
         self.X, self.Xn = self.Xn, self.X
-        Xh = self.X.cpu().numpy()
         self.history['iters'].append(self.IT.cpu().numpy().copy())
         self.history['status'].append(self.ST.cpu().numpy().copy())
-        # ideal update: vehicle and obstacles move over update_time
+        # ideal update: vehicle and obstacles move over update_time; the prediction
+        # (spline value / derivative at t + update_time) is sampled on the device
         t_rel = np.round(t, 6) % self.knot_time
-        self._predict(Xh, t_rel, self.update_time)
+        Xh = self._predict_device(t_rel, self.update_time) if self.device_predict \
+            else self._predict(self.X.cpu().numpy(), t_rel, self.update_time)
         self._advance_obstacles(self.update_time)
         self.history['state'].append(self.state.copy())
         self.time = np.round(t + self.update_time, 6)

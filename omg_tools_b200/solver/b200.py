@@ -76,7 +76,7 @@ EXPORTS = ['omg_abi_version', 'omg_last_error', 'omg_default_options',
            'omg_problem_create', 'omg_problem_destroy', 'omg_set_options',
            'omg_solve_batch', 'omg_solve_batch_host', 'omg_shift_batch',
            'omg_get_trace', 'omg_get_info', 'omg_last_timing',
-           'omg_admm_zl_update']
+           'omg_admm_zl_update', 'omg_sample_batch']
 
 _lib = None
 
@@ -112,6 +112,7 @@ def load_library(path=None):
     lib.omg_get_info.argtypes = [vp] + [_i32p] * 6
     lib.omg_last_timing.argtypes = [vp, C.POINTER(C.c_float), _i32p]
     lib.omg_admm_zl_update.argtypes = [C.c_int32] * 4 + [vp] * 4 + [C.c_double] + [vp] * 8
+    lib.omg_sample_batch.argtypes = [C.c_int32, C.c_int32, vp, C.c_int32] + [vp] * 7
     _lib = lib
     return lib
 
@@ -356,3 +357,25 @@ def admm_zl_update(PzT, c, Tf, Tb, rho, x_i, x_j, z_i, z_ij, l_i, l_ij, res, L, 
                                 C.c_void_p(stream.cuda_stream))
     if rc != 0:
         raise RuntimeError('libomgb200: %s' % lib.omg_last_error().decode())
+
+
+def sample_batch(X, blocks, stream=None):
+    """Apply sampling matrices to spline variables of a batch on the device.
+    X: torch CUDA tensor [B, n]; blocks = [(offset, len_basis, n_columns, S[nsamp, len])].
+    Returns a CUDA tensor [B, sum(nsamp * n_columns)] laid out block / column / sample."""
+    import torch
+    lib = load_library()
+    offs = np.array([b[0] for b in blocks], dtype=np.int32)
+    lens = np.array([b[1] for b in blocks], dtype=np.int32)
+    ncols = np.array([b[2] for b in blocks], dtype=np.int32)
+    nsamp = np.array([np.asarray(b[3]).shape[0] for b in blocks], dtype=np.int32)
+    Sm = np.concatenate([np.ascontiguousarray(b[3], dtype=np.float64).reshape(-1) for b in blocks])
+    out = torch.empty((X.shape[0], int((nsamp * ncols).sum())), dtype=torch.float64, device=X.device)
+    if stream is None:
+        stream = torch.cuda.current_stream(X.device)
+    rc = lib.omg_sample_batch(X.shape[0], X.shape[1], X.data_ptr(), len(blocks), offs.ctypes.data,
+                              lens.ctypes.data, ncols.ctypes.data, nsamp.ctypes.data,
+                              Sm.ctypes.data, out.data_ptr(), C.c_void_p(stream.cuda_stream))
+    if rc != 0:
+        raise RuntimeError('libomgb200: %s' % lib.omg_last_error().decode())
+    return out

@@ -229,7 +229,8 @@ def test_batched_receding_horizon_config5(solvers):
     for k in range(15):                      # crosses the first knot at t = 1.0
         seq.predict(t, dt, 0.01)
         seq.solve(t, dt)
-        Xb = bat.step()
+        bat.step()
+        Xb = bat.X.cpu().numpy()
         xs = seq.father.get_variables().cat
         assert seq.problem.stats()['return_status'] == 'Solve_Succeeded'
         assert np.all(bat.history['status'][-1] == 0)
@@ -294,3 +295,28 @@ def test_formation_admm_64_agents(solvers):
         spread.append(np.abs(cen - np.roll(cen, 1, axis=0)).max())
     assert hist[-1][2] < hist[1][2]
     assert spread[-1] < 0.5 * spread[0]
+
+
+def test_device_trajectory_sampling(solvers):
+    """Post-solve extraction on device == scipy splev of the reference's
+    sample_splines (spline_extra.py:406-410), state and input trajectories."""
+    import torch
+    from omg_tools_b200.solver.b200 import sample_batch
+    from omg_tools_b200.basics.spline import BSpline
+    from omg_tools_b200.basics.spline_extra import sample_splines
+    pr = solvers['config1']
+    veh = pr.vehicles[0]
+    X = torch.tensor(G['config1_loose_x'], device='cuda:0')
+    tau = np.linspace(0., 1., 101)
+    basis = veh.basis
+    S0 = basis.eval_basis(tau)
+    Bd, P1 = basis.derivative(1)
+    S1 = Bd.eval_basis(tau).dot(P1) / 10.
+    out = sample_batch(X, [(0, 13, 2, S0), (0, 13, 2, S1)]).cpu().numpy()
+    for b in range(X.shape[0]):
+        for c in range(2):
+            coeffs = G['config1_loose_x'][b, c * 13:(c + 1) * 13]
+            ref = sample_splines(BSpline(basis, coeffs), tau)
+            dref = sample_splines(BSpline(basis, coeffs).derivative(), tau) / 10.
+            assert np.abs(out[b, c * 101:(c + 1) * 101] - ref).max() < 1e-12
+            assert np.abs(out[b, 202 + c * 101:202 + (c + 1) * 101] - dref).max() < 1e-10
