@@ -15,7 +15,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -39,31 +38,48 @@ def parse():
     return ap.parse_args()
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms during the timed
+    region (one long-running nvidia-smi -lms process, read afterwards)."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
-        threading.Thread.__init__(self, daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.proc = index, [], None
 
-    def run(self):
-        while not self.stop_flag:
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                 '--format=csv,noheader,nounits', '-lms', '50'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return
+        try:
+            self.proc.terminate()
+            out, _ = self.proc.communicate(timeout=5)
+            for line in out.decode().strip().splitlines():
+                self.rows.append([c.strip() for c in line.split(',')])
+        except Exception:
             try:
-                out = subprocess.check_output(
-                    ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                     '--format=csv,noheader,nounits'], timeout=5).decode()
-                self.rows.append([c.strip() for c in out.strip().split(',')])
+                self.proc.kill()
             except Exception:
                 pass
-            time.sleep(0.1)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
-        mx = [float(r[1]) for r in self.rows if r and r[1].replace('.', '').isdigit()]
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+        sm = [num(r[0]) for r in self.rows if r and num(r[0]) is not None]
+        mx = [num(r[1]) for r in self.rows if len(r) > 1 and num(r[1]) is not None]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
                  'sw_power_cap']
         reasons = [n for k, n in enumerate(names)
@@ -224,8 +240,7 @@ def main():
         res = slv.solve_batch(X0p, Pp)
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
+    sampler.stop()
     h2d = X0p.nbytes + Pp.nbytes + 2 * tb.m * 8
     d2h = res['x'].nbytes + res['lam_g'].nbytes + res['f'].nbytes + \
         res['status'].nbytes + res['iters'].nbytes
@@ -281,7 +296,7 @@ def main():
             line['cpu_baseline'] = {
                 'value': sample / dt, 'unit': 'solves/s', 'cores': cores,
                 'kind': cinfo['kind'],
-                'sample': '%d instances of the same workload, %.1f s' % (sample, dt),
+                'sample': '%d instances of the same workload, %.3f s' % (sample, dt),
                 'max_abs_dx_vs_gpu': cinfo.get('max_dx')}
         print(json.dumps(line))
     if world > 1:
