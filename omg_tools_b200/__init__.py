@@ -2,10 +2,13 @@
 spline-trajectory NLP, behind the reference's Problem.solve()/OptiFather API."""
 from .basics.spline import BSplineBasis, BSpline
 from .basics.shape import (Circle, Polyhedron, Rectangle, Square, Beam,
-                           RegularPolyhedron, Sphere, Cuboid, Cube, Plate)
+                           RegularPolyhedron, Sphere, Cuboid, Cube, Plate,
+                           RegularPrisma)
 from .basics.optilayer import OptiChild, OptiFather, create_nlp
 from .vehicles.vehicle import Vehicle
 from .vehicles.holonomic import Holonomic
+from .vehicles.holonomic3d import Holonomic3D
+from .vehicles.holonomic1d import Holonomic1D
 from .vehicles.quadrotor3d import Quadrotor3D
 from .vehicles.fleet import Fleet
 from .environment.environment import Environment

@@ -28,6 +28,7 @@ FUNC_CODE = {'id': 0, 'inv': 1, 'ge': 2, 'gt': 3, 'sin': 4, 'cos': 5,
              'sqrt': 6}
 MAX_FAC = 4          # V-factors per tape term (longer products are chained)
 PRUNE = 1e-14
+SPLIT_MAX = 4       # see lower(): coefficients of intermediates
 
 
 class TermList(object):
@@ -251,21 +252,53 @@ def lower(var_ids, par_ids, rows, objective, lbg, ubg, order_hint=None):
         c = float(e)
         return Poly({(): c} if c != 0.0 else {})
 
-    split_rows = [_split(as_poly(r), x_index, tape) for r in rows]
-    split_obj = _split(as_poly(objective), x_index, tape)
+    rows = [as_poly(r) for r in rows]
+    objective = as_poly(objective)
+    # intermediates ('mid' symbols): x_ext = [x, 1, mids]; their definitions
+    # become pseudo-rows m+1.. of the G/J/W term lists (slot m of lam_ext is the
+    # objective factor) and the rows' derivatives follow by the chain rule
+    mids = sorted({resolve(s) for r in rows for s in r.symbols()
+                   if sym_info(resolve(s)).kind == 'mid'})
+    n_mid = len(mids)
+    for l, sid in enumerate(mids):
+        x_index[sid] = n + 1 + l
+    mid_defs = [sym_info(sid).arg for sid in mids]
+    if any(sym_info(resolve(s)).kind == 'mid'
+           for d in mid_defs + [objective] for s in d.symbols()):
+        raise NotImplementedError('nested intermediates / intermediates in '
+                                  'the objective are not supported')
+
+    split_rows = [_split(r, x_index, tape) for r in rows + mid_defs]
+    split_obj = _split(objective, x_index, tape)
     degree = max([len(xm) for sr in split_rows + [split_obj] for xm in sr] + [1])
+    for sr in split_rows[:m]:
+        for xm in sr:
+            if len(xm) > 1 and any(j > n for j in xm):
+                raise NotImplementedError(
+                    'rows must be affine in intermediates with parameter-only '
+                    'coefficients')
 
     def coef_of(ppoly):
         return tape.v_of_ppoly(ppoly)
 
+    def lowered(sr):
+        out = []
+        for xm, pp in sorted(sr.items()):
+            if len(xm) == 1 and xm[0] > n and 1 < len(pp) <= SPLIT_MAX:
+                # coefficient of an intermediate: a few monomials over shared
+                # parameter symbols, distinct for every (row, mid) pair -- one
+                # term per monomial keeps the tape small (shared-memory sized)
+                out += [(xm,) + coef_of({pm: c}) for pm, c in sorted(pp.items())]
+            else:
+                out.append((xm,) + coef_of(pp))
+        return out
+
     # resolve all coefficients first (tape indices are remapped afterwards)
-    lowered_rows = []
-    for sr in split_rows:
-        lowered_rows.append([(xm,) + coef_of(pp) for xm, pp in sorted(sr.items())])
+    lowered_rows = [lowered(sr) for sr in split_rows]
     lowered_obj = [(xm,) + coef_of(pp) for xm, pp in sorted(split_obj.items())]
     tape_arrays, remap = tape.finalize()
 
-    G = TermList(m, degree)
+    G = TermList(m + n_mid, degree)
     F = TermList(1, degree)
     DF = TermList(n, degree - 1)
     jslots = OrderedDict()     # (row, col) -> list of (coef, cidx, xmon)
@@ -289,7 +322,7 @@ def lower(var_ids, par_ids, rows, objective, lbg, ubg, order_hint=None):
             for j, mj, red in _first_derivs(xm):
                 jslots.setdefault((i, j), []).append((scale * mj, cidx, red))
             if len(xm) >= 2:
-                add_hess(xm, scale, cidx, i)
+                add_hess(xm, scale, cidx, i if i < m else i + 1)
     for xm, scale, cidx in lowered_obj:
         if scale == 0.0:
             continue
@@ -300,10 +333,23 @@ def lower(var_ids, par_ids, rows, objective, lbg, ubg, order_hint=None):
         if len(xm) >= 2:
             add_hess(xm, scale, cidx, m)
 
-    jkeys = sorted(jslots)
-    J = TermList(len(jkeys), degree - 1)
-    for s, key in enumerate(jkeys):
-        for c, cidx, red in jslots[key]:
+    # Jacobian slots: [real (row<m, col<n) incl. chain-rule fill | A = d row /
+    # d mid | C = d mid / d x]
+    akeys = sorted(k for k in jslots if k[0] < m and k[1] > n)
+    ckeys = sorted(k for k in jslots if k[0] >= m)
+    real = {k for k in jslots if k[0] < m and k[1] < n}
+    c_by_mid = {}
+    for (i, j) in ckeys:
+        c_by_mid.setdefault(i - m, []).append(j)
+    for (i, jm) in akeys:
+        for j in c_by_mid.get(jm - n - 1, ()):
+            real.add((i, j))
+    jkeys = sorted(real)
+    allkeys = jkeys + akeys + ckeys
+    slot_of = {k: s for s, k in enumerate(allkeys)}
+    J = TermList(len(allkeys), degree - 1)
+    for s, key in enumerate(allkeys):
+        for c, cidx, red in jslots.get(key, ()):
             J.add(s, c, cidx, red)
     wkeys = sorted(wslots)
     W = TermList(len(wkeys), degree - 2, with_lrow=True)
@@ -313,6 +359,7 @@ def lower(var_ids, par_ids, rows, objective, lbg, ubg, order_hint=None):
 
     tb = NLPTables()
     tb.n, tb.m, tb.n_par, tb.degree = n, m, len(par_ids), degree
+    tb.n_mid = n_mid
     for k, v in tape_arrays.items():
         setattr(tb, k, v)
     tb.G, tb.F, tb.DF = G.finalize(n), F.finalize(n), DF.finalize(n)
@@ -323,6 +370,34 @@ def lower(var_ids, par_ids, rows, objective, lbg, ubg, order_hint=None):
     tb.wrow = np.array([k[0] for k in wkeys], dtype=np.int32)
     tb.wcol = np.array([k[1] for k in wkeys], dtype=np.int32)
     tb.nnz_j, tb.nnz_w = len(jkeys), len(wkeys)
+    tb.nnz_jx = len(allkeys)
+    # chain rule  J[s] += sum_l A[i,l] C[l,j]  and  mu_l = sum_i lam_i A[i,l]
+    a_by_row = {}
+    for (i, jm) in akeys:
+        a_by_row.setdefault(i, []).append((jm - n - 1, slot_of[(i, jm)]))
+    jp_ptr, jp_a, jp_c = [0], [], []
+    for (i, j) in jkeys:
+        for l, sa in a_by_row.get(i, ()):
+            sc = slot_of.get((m + l, j))
+            if sc is not None:
+                jp_a.append(sa)
+                jp_c.append(sc)
+        jp_ptr.append(len(jp_a))
+    tb.jp_ptr = np.array(jp_ptr, dtype=np.int32)
+    tb.jp_a = np.array(jp_a, dtype=np.int32)
+    tb.jp_c = np.array(jp_c, dtype=np.int32)
+    mu_ptr, mu_row, mu_slot = [0], [], []
+    by_mid = {}
+    for (i, jm) in akeys:
+        by_mid.setdefault(jm - n - 1, []).append((i, slot_of[(i, jm)]))
+    for l in range(n_mid):
+        for i, sa in by_mid.get(l, ()):
+            mu_row.append(i)
+            mu_slot.append(sa)
+        mu_ptr.append(len(mu_row))
+    tb.mu_ptr = np.array(mu_ptr, dtype=np.int32)
+    tb.mu_row = np.array(mu_row, dtype=np.int32)
+    tb.mu_slot = np.array(mu_slot, dtype=np.int32)
     tb.lbg = np.asarray(lbg, dtype=np.float64).copy()
     tb.ubg = np.asarray(ubg, dtype=np.float64).copy()
     _build_kkt_pattern(tb)

@@ -558,6 +558,11 @@ class OptiChild(object):
         return dictionary[name]
 
     def define_symbol(self, name, size0=1, size1=1):
+        # a child may ask for the same placeholder several times (Quadrotor3D
+        # takes 't' in init() and again in the collision constraints): all of
+        # them must resolve, so the first definition is reused
+        if name in self._symbols and self._symbols[name].shape == (size0, size1):
+            return self._view(self._symbols[name])
         return self._view(self._define(name, size0, size1, self._symbols, 'sym'))
 
     def define_variable(self, name, size0=1, size1=1, **kwargs):

@@ -17,7 +17,15 @@ sparse polynomial over a global symbol registry.  Symbols are
               (1/p, indicator p>=0 / p>0, sin, cos, sqrt).  They appear in
               ``t/T`` (point2point.py:55), the Cox-de Boor indicators of
               ``evalspline`` (spline_extra.py:28-55) and rotating obstacles
-              (obstacle.py:292-332).
+              (obstacle.py:292-332).  The identity atom ``id`` names a
+              parameter-only polynomial so that it is evaluated once (what a
+              shared node of CasADi's expression graph is).
+* ``mid``  -- a named intermediate: a polynomial of the decision variables
+              that many rows share (the product-spline coefficients of
+              Quadrotor3D's accelerations, quadrotor3d.py:91-93).  Rows must
+              be affine in mids with parameter-only coefficients; lowering.py
+              differentiates through them by the chain rule instead of
+              expanding them into every row.
 
 A ``Poly`` is a dict {monomial: coef}; a monomial is a sorted tuple of symbol
 ids (repetition = power).  ``lowering.py`` turns rows of Poly into the flat
@@ -51,7 +59,7 @@ class SymInfo(object):
 _SYMS = []
 _ATOMS = {}
 
-ATOM_FUNCS = ('inv', 'ge', 'gt', 'sin', 'cos', 'sqrt')
+ATOM_FUNCS = ('id', 'inv', 'ge', 'gt', 'sin', 'cos', 'sqrt')
 
 
 def sym_info(sid):
@@ -72,6 +80,43 @@ def new_symbol(name, kind):
     info = SymInfo(len(_SYMS), name, kind)
     _SYMS.append(info)
     return Poly({(info.id,): 1.0})
+
+
+def new_mid(name, definition):
+    """Intermediate symbol standing for the Poly ``definition``."""
+    info = SymInfo(len(_SYMS), name, 'mid', None, definition)
+    _SYMS.append(info)
+    return Poly({(info.id,): 1.0})
+
+
+def share(poly):
+    """Parameter-only Poly -> one symbol (identity atom) evaluated once."""
+    poly = _as_poly(poly)
+    if poly.is_constant() or (len(poly.t) == 1 and abs(list(poly.t.values())[0] - 1.) == 0.
+                              and len(list(poly.t)[0]) == 1):
+        return poly
+    return _atom('id', poly)
+
+
+def collapse(poly):
+    """Rewrite a Poly that is affine in its var/mid symbols so that every
+    var/mid monomial carries ONE parameter symbol as coefficient (its former
+    parameter polynomial, shared through an identity atom).  Placeholder
+    symbols count as parameters here (fixed-T problems)."""
+    if not isinstance(poly, Poly):
+        return poly
+    groups = {}
+    for mono, c in poly.t.items():
+        xm = tuple(s for s in mono if _SYMS[resolve(s)].kind in ('var', 'mid'))
+        pm = tuple(s for s in mono if _SYMS[resolve(s)].kind not in ('var', 'mid'))
+        groups.setdefault(xm, {})[pm] = c
+    out = Poly()
+    for xm, pp in groups.items():
+        coef = Poly(pp)
+        if len(pp) > 1 and xm:
+            coef = share(coef)
+        out = out + coef * Poly({xm: 1.0})
+    return out
 
 
 def set_alias(placeholder, target):
@@ -318,6 +363,10 @@ def _value_of(sid, values):
     if sid in values:
         return values[sid]
     info = _SYMS[sid]
+    if info.kind == 'mid':
+        v = info.arg.evaluate(values)
+        values[sid] = v
+        return v
     if info.kind != 'atom':
         raise KeyError('no value for %r' % info)
     v = apply_atom(info.func, info.arg.evaluate(values))
@@ -326,6 +375,8 @@ def _value_of(sid, values):
 
 
 def apply_atom(func, a):
+    if func == 'id':
+        return a
     if func == 'inv':
         return 1.0 / a
     if func == 'ge':

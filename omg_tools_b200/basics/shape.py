@@ -171,6 +171,23 @@ class Cuboid(Polyhedron3D):
         Polyhedron3D.__init__(self, vertices, orientation)
 
 
+class RegularPrisma(Polyhedron3D):
+    """Prism over a regular polygon; ``radius`` is the circle through the
+    vertices (reference shape.py:364-390): n bottom vertices, then n top."""
+
+    def __init__(self, radius, height, n_faces, orientation=(0, 0, 0)):
+        self.radius_outer, self.height, self.n_faces = radius, height, n_faces
+        dth = 2 * np.pi / n_faces
+        base = _tangent_polygon([l * dth for l in range(n_faces)],
+                                [radius * np.cos(np.pi / n_faces)] * n_faces)
+        vertices = np.zeros((3, 2 * n_faces))
+        vertices[:2, :n_faces] = base
+        vertices[2, :n_faces] = -0.5 * height
+        vertices[:2, n_faces:] = base
+        vertices[2, n_faces:] = 0.5 * height
+        Polyhedron3D.__init__(self, vertices, orientation)
+
+
 class Cube(Cuboid):
     def __init__(self, side, orientation=(0, 0, 0)):
         Cuboid.__init__(self, side, side, side, orientation)

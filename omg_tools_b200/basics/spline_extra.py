@@ -19,12 +19,14 @@ def _scalar(x):
     return x
 
 
-def evalspline(s, x):
+def evalspline(s, x, share_weights=False):
     """Value of spline ``s`` at abscissa ``x`` (float or parameter Poly).
 
     Cox-de Boor recursion with indicator functions of x, so the result stays
     a polynomial in the coefficients with parameter-only weights
-    (reference spline_extra.py:28-55).
+    (reference spline_extra.py:28-55).  ``share_weights`` names every basis
+    value B_l(x) once (identity atom) instead of expanding it into each
+    coefficient's monomials -- for long splines with symbolic coefficients.
     """
     x = _scalar(x)
     basis = s.basis
@@ -47,6 +49,9 @@ def evalspline(s, x):
                 b = b + (k[i + d + 1] - x) * lvl[i + 1] / den
             nxt.append(b)
         lvl = nxt
+    if share_weights:
+        from .poly import share
+        lvl = [share(b) if isinstance(b, Poly) else b for b in lvl]
     result = 0.
     for l in range(len(basis)):
         result = result + s.coeffs[l] * lvl[l]

@@ -91,6 +91,56 @@ def config5(options=None, build_solver=True):
     return _p2p(vehicle, environment, opts, build_solver)
 
 
+def config_holonomic3d(options=None, build_solver=True, start=(-2., -2., -2.),
+                        goal=(2., 2., -2.)):
+    """examples/p2p_holonomic_3d.py: Plate vehicle in a Cube(5) room, a static
+    Cuboid and a rising RegularPrisma obstacle, hard terminal constraints,
+    horizon 12 s (n=166, m=1536, n_par=109)."""
+    from . import Holonomic3D, Plate, Cube, Cuboid, RegularPrisma
+    vehicle = Holonomic3D(Plate(Rectangle(0.5, 1.), height=0.1))
+    # NB the example's start and goal put the plate exactly on the room limit:
+    # jittered copies need interior points
+    vehicle.set_initial_conditions(list(start))
+    vehicle.set_terminal_conditions(list(goal))
+    environment = Environment(room={'shape': Cube(5.)})
+    environment.add_obstacle(Obstacle(
+        {'position': [0., 0., -1.5]}, shape=Cuboid(width=0.5, depth=4., height=2.)))
+    trajectories = {'velocity': {'time': [4.], 'values': [[0.0, 0.0, 1.]]}}
+    environment.add_obstacle(Obstacle(
+        {'position': [1., 1., -2.25]}, shape=RegularPrisma(0.25, 0.25, 6),
+        simulation={'trajectories': trajectories}))
+    opts = {'hard_term_con': True, 'horizon_time': 12}
+    opts.update(options or {})
+    return _p2p(vehicle, environment, opts, build_solver)
+
+
+def config4(n_obstacles=2, options=None, build_solver=True):
+    """examples/p2p_3dquadrotor.py: Quadrotor3D(0.5), Cuboid(8,6,8) room,
+    safety distance 0.1 / weight 10, horizon 5 s, knot_intervals 10
+    (13 is not usable in the reference).  n_obstacles=2
+    is the example (two upright plates, the second sinking; n=238, m=1319);
+    n_obstacles=5 adds three more static plates (BASELINE config 4, n=406)."""
+    from . import Quadrotor3D, Plate, Cuboid
+    vehicle = Quadrotor3D(0.5)
+    vehicle.set_initial_conditions([-3, -2, -0.5, 0, 0, 0, 0, 0])
+    vehicle.set_terminal_conditions([3, 2, 0.5])
+    vehicle.set_options({'safety_distance': 0.1, 'safety_weight': 10})
+    environment = Environment(room={'shape': Cuboid(8, 6, 8)})
+    plate = lambda: Plate(Rectangle(5., 8.), 0.1, orientation=[0., np.pi / 2, 0.])
+    trajectory = {'velocity': {'time': [1.5], 'values': [[0, 0, -0.6]]}}
+    environment.add_obstacle(Obstacle({'position': [-2, 0, -2]}, shape=plate()))
+    environment.add_obstacle(Obstacle({'position': [2, 0, 3.5]}, shape=plate(),
+                                      simulation={'trajectories': trajectory}))
+    extra = [([0., 0., -3.5], Plate(Rectangle(1., 8.), 0.1, orientation=[0., np.pi / 2, 0.])),
+             ([-3.5, 2.5, 3.], Plate(Rectangle(1., 1.), 0.1)),
+             ([3.5, -2.5, -3.], Plate(Rectangle(1., 1.), 0.1))]
+    for pos, shape in extra[:max(0, n_obstacles - 2)]:
+        environment.add_obstacle(Obstacle({'position': pos}, shape=shape))
+    opts = {'horizon_time': 5.}
+    opts.update(options or {})
+    return _p2p(vehicle, environment, opts, build_solver)
+
+
 def instance_data(problem, batch, jitter=0.0, seed=0, current_time=0.):
     """(X0[B,n], P[B,n_par]) for a cold solve: linear initial guess
     (holonomic.py:118-127) and parameters at current_time.  jitter>0 perturbs
@@ -107,8 +157,8 @@ def instance_data(problem, batch, jitter=0.0, seed=0, current_time=0.):
     P = np.zeros((batch, f.tables.n_par))
     for b in range(batch):
         if jitter > 0. and b > 0:
-            vehicle.prediction['state'] = state0 + rng.uniform(-jitter, jitter, 2)
-            vehicle.poseT = poseT + rng.uniform(-jitter, jitter, 2)
+            vehicle.prediction['state'] = state0 + rng.uniform(-jitter, jitter, len(state0))
+            vehicle.poseT = poseT + rng.uniform(-jitter, jitter, len(poseT))
             for o, p0 in zip(problem.environment.obstacles, obst0):
                 o.signals['position'][:, -1] = p0 + rng.uniform(
                     -0.5 * jitter, 0.5 * jitter, len(p0))

@@ -12,9 +12,9 @@ import numpy as np
 
 from .vehicle import Vehicle
 from ..basics.optilayer import inf
-from ..basics.poly import Poly
+from ..basics.poly import Poly, new_mid, collapse
 from ..basics.shape import Sphere
-from ..basics.spline import BSplineBasis
+from ..basics.spline import BSplineBasis, BSpline
 from ..basics.spline_extra import evalspline, running_integral, sample_splines
 
 
@@ -48,15 +48,11 @@ class Quadrotor3D(Vehicle):
         self.dpos0 = self.define_parameter('dpos0', 3)
 
     def define_trajectory_constraints(self, splines, horizon_time=None):
-        if not self.options.get('allow_expanded_lowering', False):
-            # The position rows share the scalars X1(t/T), X2(t/T) (re-anchored double
-            # integrals of degree-5 polynomial splines).  CasADi keeps them as shared
-            # graph nodes; the flat term tables of this round would replicate ~2e3
-            # monomials into each of ~300 rows (>1e6 terms).  Needs a shared
-            # sub-expression stage in lowering.py + the kernel: next round.
-            raise NotImplementedError(
-                'Quadrotor3D (BASELINE config 4) needs shared sub-expressions in '
-                'the lowering; not built in this round (DESIGN.md section 0)')
+        # The position rows all depend on the 72 (94 for z) product-spline
+        # coefficients of ddx/ddy/ddz through two running integrals re-anchored
+        # at t/T.  CasADi keeps those coefficients as shared graph nodes; here
+        # they are 'mid' symbols (basics/poly.py) and the rows stay affine in
+        # them, lowering.py applies the chain rule.
         if horizon_time is None:
             horizon_time = self.define_symbol('T')
         T = horizon_time
@@ -95,13 +91,25 @@ class Quadrotor3D(Vehicle):
                 self.define_constraint(self.ddy - ddy, 0, 0)
                 self.define_constraint(self.ddz - ddz, 0, 0)
             else:
-                x, _ = self.integrate_twice(ddx, self.dpos0[0], self.pos0[0], self.t, T)
-                y, _ = self.integrate_twice(ddy, self.dpos0[1], self.pos0[1], self.t, T)
-                z, _ = self.integrate_twice(ddz, self.dpos0[2], self.pos0[2], self.t, T)
+                x, _ = self.integrate_twice(self._shared('ddx', ddx), self.dpos0[0],
+                                            self.pos0[0], self.t, T)
+                y, _ = self.integrate_twice(self._shared('ddy', ddy), self.dpos0[1],
+                                            self.pos0[1], self.t, T)
+                z, _ = self.integrate_twice(self._shared('ddz', ddz), self.dpos0[2],
+                                            self.pos0[2], self.t, T)
                 eps = 1e-3
                 self.define_constraint(self.x - x, -eps, eps)
                 self.define_constraint(self.y - y, -eps, eps)
                 self.define_constraint(self.z - z, -eps, eps)
+
+    def _shared(self, name, spline):
+        """Spline whose nonlinear coefficients are named intermediates."""
+        coeffs = np.empty(len(spline.coeffs), dtype=object)
+        for k, c in enumerate(spline.coeffs):
+            if isinstance(c, Poly) and c.degree() >= 2:
+                c = new_mid('%s_%s_%d' % (self.label, name, k), c)
+            coeffs[k] = c
+        return BSpline(spline.basis, coeffs)
 
     def _positions(self, splines, horizon_time):
         f_til, q_phi, q_theta = splines
@@ -188,10 +196,10 @@ class Quadrotor3D(Vehicle):
         (quadrotor3d.py:240-254): two running integrals re-anchored at t/T."""
         symbolic = isinstance(t, Poly)
         ddx_int = T * running_integral(ddx)
-        at = evalspline(ddx_int, t / T) if symbolic else ddx_int(t / T)[0]
+        at = collapse(evalspline(ddx_int, t / T, True)) if symbolic else ddx_int(t / T)[0]
         dx = ddx_int - at + dx0
         dx_int = T * running_integral(dx)
-        at = evalspline(dx_int, t / T) if symbolic else dx_int(t / T)[0]
+        at = collapse(evalspline(dx_int, t / T, True)) if symbolic else dx_int(t / T)[0]
         x = dx_int - at + x0
         return x, dx
 

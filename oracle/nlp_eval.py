@@ -50,17 +50,30 @@ def _eval_terms(tl, V, xe, lam_ext=None):
 
 
 class TableEval(object):
+    """Intermediates ('mid' symbols, lowering.py): x_ext = [x, 1, mids]; the
+    mids are the pseudo-rows m.. of G.  Rows are affine in the mids, so
+    J = J_direct + A C (A = d row/d mid, C = d mid/d x, both slots of the J
+    term list) and the Lagrangian Hessian takes mu = A^T lam as the
+    multipliers of the pseudo-rows."""
+
     def __init__(self, tb):
         self.tb = tb
+        self.n_mid = getattr(tb, 'n_mid', 0)
 
     def tape(self, p):
         return eval_tape(self.tb, np.asarray(p, dtype=float))
 
-    def _xe(self, x):
-        return np.r_[np.asarray(x, dtype=float), 1.0]
+    def _xe(self, x, V=None):
+        xe = np.r_[np.asarray(x, dtype=float), 1.0, np.zeros(self.n_mid)]
+        if self.n_mid and V is not None:
+            tb = self.tb
+            lo = tb.G.ptr[tb.m]
+            sub = _Slice(tb.G, lo, len(tb.G.coef), tb.m, tb.m + self.n_mid)
+            xe[tb.n + 1:] = _eval_terms(sub, V, xe)
+        return xe
 
     def g(self, x, V):
-        return _eval_terms(self.tb.G, V, self._xe(x))
+        return _eval_terms(self.tb.G, V, self._xe(x, V))[:self.tb.m]
 
     def f(self, x, V):
         return _eval_terms(self.tb.F, V, self._xe(x))[0]
@@ -68,8 +81,18 @@ class TableEval(object):
     def gradf(self, x, V):
         return _eval_terms(self.tb.DF, V, self._xe(x))
 
+    def _jac_all(self, x, V):
+        return _eval_terms(self.tb.J, V, self._xe(x, V))
+
     def jac_vals(self, x, V):
-        return _eval_terms(self.tb.J, V, self._xe(x))
+        tb = self.tb
+        jv = self._jac_all(x, V)
+        if not self.n_mid:
+            return jv
+        out = jv[:tb.nnz_j].copy()
+        seg = np.repeat(np.arange(tb.nnz_j), np.diff(tb.jp_ptr))
+        np.add.at(out, seg, jv[tb.jp_a] * jv[tb.jp_c])
+        return out
 
     def jac_dense(self, x, V):
         J = np.zeros((self.tb.m, self.tb.n))
@@ -77,8 +100,16 @@ class TableEval(object):
         return J
 
     def hess_vals(self, x, V, lam, obj_factor=1.0):
-        lam_ext = np.r_[np.asarray(lam, dtype=float), obj_factor]
-        return _eval_terms(self.tb.W, V, self._xe(x), lam_ext)
+        tb = self.tb
+        lam = np.asarray(lam, dtype=float)
+        lam_ext = np.r_[lam, obj_factor]
+        if self.n_mid:
+            jv = self._jac_all(x, V)
+            mu = np.zeros(self.n_mid)
+            seg = np.repeat(np.arange(self.n_mid), np.diff(tb.mu_ptr))
+            np.add.at(mu, seg, lam[tb.mu_row] * jv[tb.mu_slot])
+            lam_ext = np.r_[lam_ext, mu]
+        return _eval_terms(tb.W, V, self._xe(x, V), lam_ext)
 
     def hess_dense(self, x, V, lam, obj_factor=1.0):
         W = np.zeros((self.tb.n, self.tb.n))
@@ -86,3 +117,13 @@ class TableEval(object):
         W[self.tb.wrow, self.tb.wcol] = vals
         W[self.tb.wcol, self.tb.wrow] = vals
         return W
+
+
+class _Slice(object):
+    """Term-list view of the slots [s0, s1) (terms [lo, hi))."""
+
+    def __init__(self, tl, lo, hi, s0, s1):
+        self.coef, self.cidx = tl.coef[lo:hi], tl.cidx[lo:hi]
+        self.xi, self.lrow = tl.xi[lo:hi], tl.lrow[lo:hi]
+        self.ptr = tl.ptr[s0:s1 + 1] - lo
+        self.n_out = s1 - s0

@@ -129,3 +129,56 @@ def test_rotating_obstacle_rows_config5():
     assert rows['c_0_' + lab[2]] == 71 and rows['c_1_' + lab[2]] == 71
     # theta enters through cos/sin atoms of the parameter tape
     assert 4 in f.tables.tape_func and 5 in f.tables.tape_func
+
+
+def test_holonomic3d_example_dimensions_and_rows():
+    """examples/p2p_holonomic_3d.py: 3 position splines, 3 terminal-objective
+    slacks, 2 obstacles x (a[3], b) degree-1 hyperplanes; obstacle checkpoints
+    are parameters (obstacle.py:191-193).  The collision rows must be the
+    pointwise separation a.(chk + p(t)) - b + r <= 0 in coefficient form."""
+    pr = sc.config_holonomic3d(build_solver=False)
+    tb = pr.father.tables
+    assert (tb.n, tb.m, tb.n_par) == (166, 1536, 109)
+    ent = pr.father._var_struct.entries
+    shapes = sorted(v[2] for v in ent.values())
+    assert shapes == sorted([(13, 3)] + [(13, 1)] * 3 + [(11, 3), (11, 1)] * 2)
+    # 6 initial + 3 terminal position + 9 terminal derivative equalities
+    assert int((tb.lbg == tb.ubg).sum()) == 18
+    # tables evaluate consistently with finite differences
+    rng = np.random.default_rng(0)
+    X0, P = sc.instance_data(pr, 1)
+    x = X0[0] + 0.1 * rng.standard_normal(tb.n)
+    ev = TableEval(tb)
+    v = ev.tape(P[0])
+    g0 = ev.g(x, v)
+    J = ev.jac_dense(x, v)
+    h = 1e-6
+    for k in rng.choice(tb.n, 12, replace=False):
+        xp = x.copy()
+        xp[k] += h
+        xm = x.copy()
+        xm[k] -= h
+        fd = (ev.g(xp, v) - ev.g(xm, v)) / (2 * h)
+        assert np.abs(fd - J[:, k]).max() < 1e-6
+    assert np.isfinite(g0).all()
+
+
+def test_holonomic1d_problem_solves_on_oracle():
+    """Smallest member of the family (holonomic1d.py): one spline, no
+    collision rows; the oracle must reach the target with zero end velocity."""
+    from omg_tools_b200 import Holonomic1D, Environment, Square
+    from oracle import ipm_ref
+    veh = Holonomic1D()
+    veh.set_initial_conditions([0.])
+    veh.set_terminal_conditions([2.])
+    pr = sc._p2p(veh, Environment(room={'shape': Square(10.)}), None, False)
+    tb = pr.father.tables
+    assert tb.n == 26          # 13 spline + 13 objective slack coefficients
+    X0, P = sc.instance_data(pr, 1)
+    res = ipm_ref.solve(tb, X0[0], P[0])
+    assert res.status == 0
+    assert abs(res.x[12] - 2.) < 1e-6 and abs(res.x[0]) < 1e-6
+    # velocity bound 0.5 m/s over T=10 s: derivative coefficients within bound
+    basis = veh.basis
+    Bd, P1 = basis.derivative(1)
+    assert (P1.dot(res.x[:13]) / 10. <= 0.5 + 1e-6).all()
