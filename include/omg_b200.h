@@ -34,12 +34,23 @@
 extern "C" {
 #endif
 
-#define OMG_ABI_VERSION 3
+#define OMG_ABI_VERSION 4
 
 /* CSR list of polynomial terms per output slot:
  *   out[s] = sum_{t in [ptr[s],ptr[s+1])} coef[t] * V[cidx[t]]
  *            * prod_{k<width} x_ext[xi[t*width+k]]   ( * lam_ext[lrow[t]] if lrow )
- * x_ext = [x, 1], lam_ext = [lambda (m rows), obj_factor]. */
+ * x_ext = [x, 1, mids], lam_ext = [lambda (m rows), obj_factor, mu (n_mid)].
+ *
+ * Intermediates ("mids", n_mid >= 0): polynomials of x shared by many rows (the
+ * graph nodes CasADi shares in the reference's expression graph; Quadrotor3D's
+ * acceleration product splines, quadrotor3d.py:91-126).  They are the outputs
+ * m .. m+n_mid-1 of G; rows are affine in them.  The J term list then has
+ * nnz_jx >= nnz_j slots: [0,nnz_j) the constraint Jacobian (direct part),
+ * then A = d row/d mid, then C = d mid/d x, and
+ *     J[s] += sum_{e in [jp_ptr[s],jp_ptr[s+1])} Jx[jp_a[e]] * Jx[jp_c[e]]
+ *     mu_l  = sum_{e in [mu_ptr[l],mu_ptr[l+1])} lambda[mu_row[e]] * Jx[mu_slot[e]]
+ * give the chain rule for the Jacobian and the multipliers of the mids' own
+ * Hessians (W terms with lrow = m+1+l). */
 typedef struct omg_termlist {
   int32_t n_out, n_terms, width;
   const int32_t* ptr;   /* [n_out+1] */
@@ -66,6 +77,10 @@ typedef struct omg_tables {
   /* Jacobian pattern, slots sorted by (row, col) */
   int32_t nnz_j;
   const int32_t* jrow; const int32_t* jcol; const int32_t* jrow_ptr; /* [m+1] */
+  /* intermediates (see omg_termlist); n_mid = 0: all of this is unused */
+  int32_t n_mid, nnz_jx, n_jp, n_mu;
+  const int32_t* jp_ptr; const int32_t* jp_a; const int32_t* jp_c;   /* [nnz_j+1],[n_jp] */
+  const int32_t* mu_ptr; const int32_t* mu_row; const int32_t* mu_slot; /* [n_mid+1],[n_mu] */
   /* Lagrangian-Hessian pattern (lower triangle) and its position in H */
   int32_t nnz_w;
   const int32_t* wrow; const int32_t* wcol; const int32_t* w2h;

@@ -67,6 +67,11 @@ struct DevTab {
   const unsigned short* jcol16;         // [nnz_j] column of each slot
   const int *eq_rows, *pos_var, *pos_eq, *ksign, *env_first, *env_ptr, *jdst, *kdiag,
             *panel_ptr, *panel_rows, *panel_cmin;
+  // intermediates (XL kernel only): G term ranges of the mids, term ranges of the extra
+  // J slots (A = d row/d mid, C = d mid/d x), chain-rule pair lists, mu = A^T lambda lists
+  int n_mid, nnz_jx;
+  const int2* midg; const int* jx_tptr;
+  const int *jp_ptr, *jp_a, *jp_c, *mu_ptr, *mu_row, *mu_slot;
 };
 
 struct Smem {                      // offsets in doubles
@@ -74,6 +79,7 @@ struct Smem {                      // offsets in doubles
   int sgn, eptr, efirst, pptr, prow, pcmin;
   int arr[N_ARR];                  // >= 0: shared offset; < 0: -(scratch offset + 1)
   int LDP, total;
+  int Kg, Vg, jxg, mug;            // XL kernel: scratch offsets (K only if S.K < 0)
 };
 
 struct Batch {
@@ -203,11 +209,11 @@ extern __shared__ double sm[];
 // Pivot j must satisfy sign[j]*pivot > PIV_TOL*|K_jj| (variables) or > 0
 // (equality rows); otherwise ctl->fail (eq_fail for an equality pivot).
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void factor_env(const DevTab& T, const Smem& S, Ctl* ctl, double* pc) {
+__device__ __forceinline__ void factor_env(const DevTab& T, const Smem& S, double* K, Ctl* ctl, double* pc) {
   const int tid = threadIdx.x;
   const int N = T.N;
   const int LDP = S.LDP;
-  double* K = sm + S.K; double* Pt = sm + S.Pt; double* PtS = sm + S.PtS; double* Ld = sm + S.Ld;
+  double* Pt = sm + S.Pt; double* PtS = sm + S.PtS; double* Ld = sm + S.Ld;
   const double* diag0 = sm + S.diag0; double* invd = sm + S.invd;
   int* rbase = reinterpret_cast<int*>(sm + S.rbase);
   int* rrow = rbase + LDP;
@@ -353,10 +359,10 @@ __device__ __forceinline__ void factor_env(const DevTab& T, const Smem& S, Ctl* 
 }
 
 // Back substitution L^T u = w on envelope storage (w = row N of L on entry).
-__device__ __forceinline__ void back_solve_env(const DevTab& T, const Smem& S) {
+__device__ __forceinline__ void back_solve_env(const DevTab& T, const Smem& S, const double* K) {
   const int tid = threadIdx.x;
   const int N = T.N;
-  const double* K = sm + S.K; const double* invd = sm + S.invd; double* w = sm + S.u;
+  const double* invd = sm + S.invd; double* w = sm + S.u;
   const int* eptr = KS_EPTR; const int* efirst = KS_EFIRST; const int* pcmin = KS_PCMIN;
   for (int pb = T.n_panels - 1; pb >= 0; --pb) {
     const int kb = pb * NB;
@@ -406,20 +412,45 @@ __device__ __forceinline__ void back_solve_env(const DevTab& T, const Smem& S) {
   }
 }
 
+// Chain rule through the intermediates (XL kernel).  Evaluates the extra Jacobian slots
+// jx[s], s in [nnz_j, nnz_jx): A = d row/d mid (parameter-only) and C = d mid/d x, then
+// initialises every constraint-Jacobian slot with  sum_e A[jp_a[e]] * C[jp_c[e]]  (raw,
+// unscaled); the row pass adds the direct terms.  Ends with a block barrier.
+__device__ __forceinline__ void jac_chain(const DevTab& T, const double* __restrict__ V,
+                                          const double* __restrict__ xe, double* jx, double* jval) {
+  const int tid = threadIdx.x;
+  for (int s = T.nnz_j + tid; s < T.nnz_jx; s += NT)
+    jx[s] = eval_range(T.Jt, T.jx_tptr[s - T.nnz_j], T.jx_tptr[s - T.nnz_j + 1], V, xe);
+  __syncthreads();
+  for (int s = tid; s < T.nnz_j; s += NT) {
+    double acc = 0.0;
+    for (int e = T.jp_ptr[s]; e < T.jp_ptr[s + 1]; ++e) acc += jx[T.jp_a[e]] * jx[T.jp_c[e]];
+    jval[s] = acc;
+  }
+  __syncthreads();
+}
+
 // ---------------------------------------------------------------------------
 // the solver kernel
 // ---------------------------------------------------------------------------
+// XL = true: problems with intermediates (n_mid > 0) and/or a KKT envelope / parameter tape
+// that exceeds shared memory: V (and K if needed) live in the block's L2-resident scratch.
+template <bool XL>
 __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, const Batch& A, const Smem& S) {
   __shared__ Ctl ctl;
   __shared__ double phase_cyc[NPHASE];
-  double* K = sm + S.K;
+  double* const Dx = A.dscr + (size_t)blockIdx.x * A.dscr_stride;
+  double* K = (XL && S.K < 0) ? Dx + S.Kg : sm + S.K;
   double* u = sm + S.u;
   double* xe = sm + S.xe;
   double* xt = sm + S.xt;
   double* dx = sm + S.dx;
   double* gf = sm + S.gf;
   double* diag0 = sm + S.diag0;
-  double* V = sm + S.V;
+  double* V = XL ? Dx + S.Vg : sm + S.V;
+  double* jx = XL ? Dx + S.jxg - T.nnz_j : nullptr;   // indexed by slot id >= nnz_j
+  double* mu_mid = XL ? Dx + S.mug : nullptr;
+  const int n_xe = T.n + 1 + (XL ? T.n_mid : 0);
   double* red = sm + S.red;
   double* filt = sm + S.filt;
   unsigned char* rt = reinterpret_cast<unsigned char*>(sm + S.rt8);
@@ -493,6 +524,11 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
     // ---- S2: x ------------------------------------------------------------------
     for (int i = tid; i <= n; i += NT) { xe[i] = (i < n) ? x0[i] : 1.0; xt[i] = 1.0; }
     __syncthreads();
+    if (XL) {
+      for (int l = tid; l < T.n_mid; l += NT) { const int2 r = T.midg[l]; xe[n + 1 + l] = eval_range(T.Gt, r.x, r.y, V, xe); }
+      __syncthreads();
+      jac_chain(T, V, xe, jx, jval);
+    }
 
     // ---- S3: row classification, scaling, starting point -----------------------
     double fmaxv = 0.0;
@@ -509,7 +545,17 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
       const RowRec rr = T.rowrec[i];
       // Jacobian row: max |J| for the gradient-based scaling
       double gm = 0.0;
-      {
+      if (XL) {       // jval holds the chain-rule part (jac_chain); add the direct terms
+        double* jv = jval + rr.s0;
+        double acc = 0.0; int cur = 0, aux;
+        for (int k = rr.jt0; k < rr.jt1; ++k) {
+          const double v = term_value(T.Jt + k, V, xe, &aux);
+          if (aux != cur) { jv[cur] += acc; acc = 0.0; cur = aux; }
+          acc += v;
+        }
+        if (rr.jt1 > rr.jt0) jv[cur] += acc;
+        for (int k = 0; k < rr.ns; ++k) gm = fmax(gm, fabs(jv[k]));
+      } else {
         double acc = 0.0; int cur = 0, aux;
         for (int k = rr.jt0; k < rr.jt1; ++k) {
           const double v = term_value(T.Jt + k, V, xe, &aux);
@@ -586,11 +632,22 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
                              OP_SUM, OP_SUM, OP_SUM, OP_SUM, OP_MAX, OP_SUM};
       for (int r = 0; r < NRED; ++r) rv[r] = 0.0;
       rv[2] = 1e300;
+      if (XL) jac_chain(T, V, xe, jx, jval);
       for (int i = tid; i < m; i += NT) {
         const RowRec rr = T.rowrec[i];
         const int r = rt[i];
         const double d = dsc[i];
-        {
+        if (XL) {
+          double* jv = jval + rr.s0;
+          for (int k = 0; k < rr.ns; ++k) jv[k] *= d;
+          double acc = 0.0; int cur = 0, aux;
+          for (int k = rr.jt0; k < rr.jt1; ++k) {
+            const double v = term_value(T.Jt + k, V, xe, &aux);
+            if (aux != cur) { jv[cur] += d * acc; acc = 0.0; cur = aux; }
+            acc += v;
+          }
+          if (rr.jt1 > rr.jt0) jv[cur] += d * acc;
+        } else {
           double acc = 0.0; int cur = 0, aux;
           double* jv = jval + rr.s0;
 #pragma unroll 4
@@ -700,6 +757,17 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
       __syncthreads();
       TICK(4);   // sigma pass
 
+      if (XL) {   // multipliers of the mids' Hessians: mu = A^T (y*dsc), A raw (unscaled)
+        for (int l = tid; l < T.n_mid; l += NT) {
+          double acc = 0.0;
+          for (int e = T.mu_ptr[l]; e < T.mu_ptr[l + 1]; ++e) {
+            const int i = T.mu_row[e];
+            acc += y[i] * dsc[i] * jx[T.mu_slot[e]];
+          }
+          mu_mid[l] = acc;
+        }
+        __syncthreads();
+      }
       // ---- I7/I8: assemble + factorise, with inertia correction -----------------
       for (;;) {
         {
@@ -729,7 +797,8 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
           for (int t = w.t0; t < w.t1; ++t) {
             int lr;
             double v = term_value(T.Wt + t, V, xe, &lr);
-            v *= (lr < m) ? (y[lr] * dsc[lr]) : ctl.fsc;
+            if (XL) v *= (lr < m) ? (y[lr] * dsc[lr]) : (lr == m ? ctl.fsc : mu_mid[lr - m - 1]);
+            else v *= (lr < m) ? (y[lr] * dsc[lr]) : ctl.fsc;
             acc += v;
           }
           K[w.dst] += acc;
@@ -762,7 +831,7 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
         if (tid == 0) { ctl.fail = 0; ctl.eq_fail = 0; }
         __syncthreads();
         TICK(6);   // W + border + rhs
-        factor_env(T, S, &ctl, tracing ? phase_cyc : nullptr);
+        factor_env(T, S, K, &ctl, tracing ? phase_cyc : nullptr);
         __syncthreads();
         phase_t0 = clock64();
         if (!ctl.fail) break;
@@ -789,7 +858,7 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
       // ---- I9: solve -----------------------------------------------------------
       for (int j = tid; j < N; j += NT) u[j] = K[KS_EPTR[N] + j];
       __syncthreads();
-      back_solve_env(T, S);
+      back_solve_env(T, S, K);
       for (int j = tid; j < n; j += NT) dx[j] = u[T.pos_var[j]];
       for (int k = tid; k < n_eq; k += NT) dx[n + k] = u[T.pos_eq[k]];
       __syncthreads();
@@ -844,6 +913,10 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
         ++n_ls;
         for (int j = tid; j < n; j += NT) xt[j] = xe[j] + alpha * dx[j];
         __syncthreads();
+        if (XL) {
+          for (int l = tid; l < T.n_mid; l += NT) { const int2 r = T.midg[l]; xt[n + 1 + l] = eval_range(T.Gt, r.x, r.y, V, xt); }
+          __syncthreads();
+        }
         double tv[3];  // 0 theta 1 logsum 2 f
         const int top[3] = {OP_SUM, OP_SUM, OP_SUM};
         tv[0] = 0.0; tv[1] = 0.0; tv[2] = 0.0;
@@ -928,7 +1001,7 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
       }
       TICK(12);  // line search
       // ---- I12: accept -------------------------------------------------------------
-      for (int j = tid; j < n; j += NT) xe[j] = xt[j];
+      for (int j = tid; j < n_xe; j += NT) xe[j] = xt[j];
       for (int i = tid; i < m; i += NT) {
         const int r = rt[i];
         g[i] = gt[i];
@@ -964,10 +1037,13 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
 }
 
 __global__ void __launch_bounds__(512, 1)
-omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S) { ipm_body(T, O, A, S); }
+omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S) { ipm_body<false>(T, O, A, S); }
 
 __global__ void __launch_bounds__(256, 2)
-omg_ipm_kernel_2cta(const DevTab T, const omg_options O, const Batch A, const Smem S) { ipm_body(T, O, A, S); }
+omg_ipm_kernel_2cta(const DevTab T, const omg_options O, const Batch A, const Smem S) { ipm_body<false>(T, O, A, S); }
+
+__global__ void __launch_bounds__(512, 1)
+omg_ipm_kernel_xl(const DevTab T, const omg_options O, const Batch A, const Smem S) { ipm_body<true>(T, O, A, S); }
 
 // warm-start shift: x[b, off + c*len + i] <- sum_k T[i,k] x[b, off + c*len + k]
 __global__ void omg_shift_kernel(double* x, int B, int n, int n_blocks, const int* offs,
@@ -1116,6 +1192,7 @@ struct omg_problem {
   omg_options opt;
   std::vector<void*> allocs;
   int n_sm = 0, ctas_per_sm = 1, nt = 512, target_ctas = 1;
+  bool xl = false;
   size_t smem_bytes = 0;
   double* dscr = nullptr; int* iscr = nullptr; int scr_ctas = 0;
   int dscr_stride = 0, iscr_stride = 0;
@@ -1190,7 +1267,9 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
   T.n_panel_rows = tb->n_panel_rows;
   T.n_panels = (tb->kkt_n + NB - 1) / NB;
   if (tb->kkt_n != n + tb->kkt_n_eq) { set_err("inconsistent KKT structure"); ok = false; }
-  if (!(n < 65535 && tb->n_v < 65536 && m < 65535 && tb->nnz_j < 65536)) {
+  const int n_mid = tb->n_mid;
+  T.n_mid = n_mid; T.nnz_jx = n_mid ? tb->nnz_jx : tb->nnz_j;
+  if (!(n + 1 + n_mid < 65535 && tb->n_v < 65536 && m + 1 + n_mid < 65535 && tb->nnz_j < 65536)) {
     set_err("problem too large for 16-bit packed indices"); ok = false; }
   const omg_termlist* lists[5] = {&tb->G, &tb->F, &tb->DF, &tb->J, &tb->W};
   for (int k = 0; k < 5 && ok; ++k)
@@ -1227,11 +1306,24 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
       r.s0 = tb->jrow_ptr[i]; r.ns = tb->jrow_ptr[i + 1] - tb->jrow_ptr[i];
       r.jt0 = tb->J.ptr[r.s0]; r.jt1 = tb->J.ptr[r.s0 + r.ns];
       r.pad0 = r.pad1 = 0;
-      // every slot of the row must own at least one term (aux bookkeeping)
-      for (int s = r.s0; s < r.s0 + r.ns; ++s)
+      // every slot of the row must own at least one term (aux bookkeeping); with
+      // intermediates the chain-rule pass initialises every slot instead
+      for (int s = r.s0; s < r.s0 + r.ns && !n_mid; ++s)
         if (tb->J.ptr[s + 1] == tb->J.ptr[s]) { set_err("empty Jacobian slot"); ok = false; }
     }
     T.rowrec = upload(h, rr.data(), rr.size(), &ok);
+  }
+  if (n_mid) {  // intermediates: term ranges and chain-rule lists
+    std::vector<int2> mg(n_mid);
+    for (int l = 0; l < n_mid; ++l) mg[l] = make_int2(tb->G.ptr[m + l], tb->G.ptr[m + l + 1]);
+    T.midg = upload(h, mg.data(), mg.size(), &ok);
+    T.jx_tptr = upload(h, tb->J.ptr + tb->nnz_j, (size_t)(tb->nnz_jx - tb->nnz_j) + 1, &ok);
+    T.jp_ptr = upload(h, tb->jp_ptr, (size_t)tb->nnz_j + 1, &ok);
+    T.jp_a = upload(h, tb->jp_a, tb->n_jp, &ok);
+    T.jp_c = upload(h, tb->jp_c, tb->n_jp, &ok);
+    T.mu_ptr = upload(h, tb->mu_ptr, (size_t)n_mid + 1, &ok);
+    T.mu_row = upload(h, tb->mu_row, tb->n_mu, &ok);
+    T.mu_slot = upload(h, tb->mu_slot, tb->n_mu, &ok);
   }
   {  // CSC view of the Jacobian pattern: slot | row << 16
     std::vector<int> cptr(n + 1, 0);
@@ -1304,31 +1396,51 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
   const int N = T.N;
   int off = 0;
   auto take = [&](int cnt) { int o = off; off += (cnt + 1) & ~1; return o; };
-  S.K = take(T.env_size + 2);
-  S.LDP = (T.max_panel_rows + 2 + 3) & ~3;
-  S.Pt = take(NB * S.LDP); S.PtS = take(NB * S.LDP); S.Ld = take(NB * NB);
-  S.rbase = take(S.LDP);               // 2*LDP ints: row base offsets + row ids
-  S.xe = take(n + 1); S.xt = take(n + 1); S.dx = take(N + 1); S.u = take(N + 1);
-  S.gf = take(n);
-  S.diag0 = take(N + 1); S.invd = take(N + 1); S.V = take(T.n_v);
-  S.red = take(MAX_NWARP * NRED); S.filt = take(2 * MAXF);
-  S.rt8 = take((m + 7) / 8);
-  S.sgn = take(N); S.eptr = take((N + 2 + 1) / 2); S.efirst = take((N + 1 + 1) / 2);
-  S.pptr = take((T.n_panels + 1 + 1) / 2); S.prow = take((tb->n_panel_rows + 1) / 2);
-  S.pcmin = take((T.n_panels + 1) / 2);
+  const int xe_len = n + 1 + n_mid;
+  // mandatory shared-memory part; K and the parameter tape V optionally in scratch
+  auto layout = [&](bool k_smem, bool v_smem) {
+    off = 0;
+    S.K = k_smem ? take(T.env_size + 2) : -1;
+    S.LDP = (T.max_panel_rows + 2 + 3) & ~3;
+    S.Pt = take(NB * S.LDP); S.PtS = take(NB * S.LDP); S.Ld = take(NB * NB);
+    S.rbase = take(S.LDP);               // 2*LDP ints: row base offsets + row ids
+    S.xe = take(xe_len); S.xt = take(xe_len); S.dx = take(N + 1); S.u = take(N + 1);
+    S.gf = take(n);
+    S.diag0 = take(N + 1); S.invd = take(N + 1); S.V = v_smem ? take(T.n_v) : -1;
+    S.red = take(MAX_NWARP * NRED); S.filt = take(2 * MAXF);
+    S.rt8 = take((m + 7) / 8);
+    S.sgn = take(N); S.eptr = take((N + 2 + 1) / 2); S.efirst = take((N + 1 + 1) / 2);
+    S.pptr = take((T.n_panels + 1 + 1) / 2); S.prow = take((tb->n_panel_rows + 1) / 2);
+    S.pcmin = take((T.n_panels + 1) / 2);
+    return (size_t)off * 8;
+  };
+  // standard kernels keep K and V in shared memory; the XL kernel (intermediates, or a
+  // structure too large for that) keeps V in scratch, and K too if it leaves no room
+  bool k_in_smem = true;
+  {
+    cudaFuncAttributes f0, fx;
+    size_t b0 = 0, bx = 0;
+    if (cudaFuncGetAttributes(&f0, (const void*)omg_ipm_kernel) == cudaSuccess)
+      b0 = (size_t)prop.sharedMemPerBlockOptin - f0.sharedSizeBytes;
+    if (cudaFuncGetAttributes(&fx, (const void*)omg_ipm_kernel_xl) == cudaSuccess)
+      bx = (size_t)prop.sharedMemPerBlockOptin - fx.sharedSizeBytes;
+    h->xl = (n_mid > 0) || layout(true, true) > b0;
+    if (h->xl && layout(true, false) > bx) { k_in_smem = false; layout(false, false); }
+  }
   // blocks per SM: 2 x 256 threads overlap one block's serial pivots with the other's
   // parallel phases; 1 x 512 keeps every per-instance array in shared memory.
   cudaFuncAttributes fa;
-  if (ok && cudaFuncGetAttributes(&fa, (const void*)omg_ipm_kernel) != cudaSuccess) { set_err("cudaFuncGetAttributes failed"); ok = false; }
+  if (ok && cudaFuncGetAttributes(&fa, h->xl ? (const void*)omg_ipm_kernel_xl : (const void*)omg_ipm_kernel) != cudaSuccess) { set_err("cudaFuncGetAttributes failed"); ok = false; }
   const size_t budget1 = ok ? (size_t)prop.sharedMemPerBlockOptin - fa.sharedSizeBytes : 0;
   const size_t budget2 = ok ? ((size_t)prop.sharedMemPerMultiprocessor - 2 * 1024) / 2 - fa.sharedSizeBytes : 0;
   {
     const char* e = getenv("OMG_B200_CTAS");
     const int want = (e && atoi(e) == 1) ? 1 : 2;
-    h->target_ctas = (want == 2 && (size_t)off * 8 <= budget2) ? 2 : 1;
+    h->target_ctas = (want == 2 && !h->xl && (size_t)off * 8 <= budget2) ? 2 : 1;
     h->nt = (h->target_ctas == 1) ? 512 : 256;
   }
-  const void* kfn = (h->target_ctas == 1) ? (const void*)omg_ipm_kernel : (const void*)omg_ipm_kernel_2cta;
+  const void* kfn = h->xl ? (const void*)omg_ipm_kernel_xl
+                          : (h->target_ctas == 1) ? (const void*)omg_ipm_kernel : (const void*)omg_ipm_kernel_2cta;
   const size_t budget = (h->target_ctas == 1) ? budget1 : budget2;
   if (ok && (size_t)off * 8 > budget) {
     char buf[256];
@@ -1337,6 +1449,14 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
     set_err(buf); ok = false;
   }
   int goff = 0;   // global scratch offset (doubles)
+  S.Kg = S.Vg = S.jxg = S.mug = 0;
+  if (h->xl) {
+    auto gtake = [&](int cnt) { int o = goff; goff += (cnt + 1) & ~1; return o; };
+    S.Vg = gtake(T.n_v);
+    S.jxg = gtake(T.nnz_jx - T.nnz_j + 1);
+    S.mug = gtake(n_mid + 1);
+    if (!k_in_smem) S.Kg = gtake(T.env_size + 2);
+  }
   const int sizes[N_ARR] = {tb->nnz_j, m, tb->nnz_j, m, m, m, m, m, m, m, m, m, m, m, m, m, m, m, m};
   for (int k = 0; k < N_ARR; ++k) {
     const int cnt = (sizes[k] + 1) & ~1;
@@ -1421,7 +1541,8 @@ int omg_solve_batch(omg_problem* h, int32_t B, const double* x0, const double* p
   A.counter = h->counter; A.trace = h->trace;
   CK(cudaMemsetAsync(h->counter, 0, sizeof(int), stream));
   CK(cudaEventRecord(h->ev0, stream));
-  if (h->target_ctas == 1) omg_ipm_kernel<<<grid, 512, h->smem_bytes, stream>>>(h->T, h->opt, A, h->S);
+  if (h->xl) omg_ipm_kernel_xl<<<grid, 512, h->smem_bytes, stream>>>(h->T, h->opt, A, h->S);
+  else if (h->target_ctas == 1) omg_ipm_kernel<<<grid, 512, h->smem_bytes, stream>>>(h->T, h->opt, A, h->S);
   else omg_ipm_kernel_2cta<<<grid, 256, h->smem_bytes, stream>>>(h->T, h->opt, A, h->S);
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->ev1, stream));

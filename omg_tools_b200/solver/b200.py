@@ -24,7 +24,7 @@ STATUS_STRINGS = {
     2: 'Restoration_Failed', 3: 'Error_In_Step_Computation',
     4: 'Invalid_Number_Detected', 5: 'Infeasible_Problem_Detected'}
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _i32p = C.POINTER(C.c_int32)
 _f64p = C.POINTER(C.c_double)
@@ -47,6 +47,9 @@ class _Tables(C.Structure):
         ('G', _TermList), ('F', _TermList), ('DF', _TermList), ('J', _TermList),
         ('W', _TermList),
         ('nnz_j', C.c_int32), ('jrow', _i32p), ('jcol', _i32p), ('jrow_ptr', _i32p),
+        ('n_mid', C.c_int32), ('nnz_jx', C.c_int32), ('n_jp', C.c_int32), ('n_mu', C.c_int32),
+        ('jp_ptr', _i32p), ('jp_a', _i32p), ('jp_c', _i32p),
+        ('mu_ptr', _i32p), ('mu_row', _i32p), ('mu_slot', _i32p),
         ('nnz_w', C.c_int32), ('wrow', _i32p), ('wcol', _i32p), ('w2h', _i32p),
         ('nnz_h', C.c_int32), ('n_hp', C.c_int32),
         ('hrow', _i32p), ('hcol', _i32p), ('hp_ptr', _i32p),
@@ -162,6 +165,13 @@ def pack_tables(tb):
     T.W = tl(tb.W, True)
     T.nnz_j = tb.nnz_j
     T.jrow, T.jcol, T.jrow_ptr = keep.i32(tb.jrow), keep.i32(tb.jcol), keep.i32(tb.jrow_ptr)
+    T.n_mid = getattr(tb, 'n_mid', 0)
+    T.nnz_jx = getattr(tb, 'nnz_jx', tb.nnz_j)
+    if T.n_mid:
+        T.n_jp, T.n_mu = len(tb.jp_a), len(tb.mu_row)
+        T.jp_ptr, T.jp_a, T.jp_c = keep.i32(tb.jp_ptr), keep.i32(tb.jp_a), keep.i32(tb.jp_c)
+        T.mu_ptr, T.mu_row, T.mu_slot = (keep.i32(tb.mu_ptr), keep.i32(tb.mu_row),
+                                         keep.i32(tb.mu_slot))
     T.nnz_w = tb.nnz_w
     T.wrow, T.wcol, T.w2h = keep.i32(tb.wrow), keep.i32(tb.wcol), keep.i32(tb.w2h)
     T.nnz_h, T.n_hp = tb.nnz_h, len(tb.hp_s1)

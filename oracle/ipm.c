@@ -54,6 +54,25 @@ static double eval_slot(const omg_termlist* L, int s, const double* V, const dou
   return acc;
 }
 
+/* intermediates (include/omg_b200.h): x_ext = [x, 1, mids] */
+static void eval_mids(const omg_tables* T, const double* V, double* xe) {
+  for (int l = 0; l < T->n_mid; ++l) xe[T->n + 1 + l] = eval_slot(&T->G, T->m + l, V, xe);
+}
+
+/* raw A = d row/d mid and C = d mid/d x slots of the J term list */
+static void eval_jx(const omg_tables* T, const double* V, const double* xe, double* jx) {
+  if (!T->n_mid) return;
+  for (int s = T->nnz_j; s < T->nnz_jx; ++s) jx[s] = eval_slot(&T->J, s, V, xe);
+}
+
+/* constraint Jacobian slot: direct part + chain rule through the mids */
+static double jac_slot(const omg_tables* T, int s, const double* V, const double* xe, const double* jx) {
+  double v = eval_slot(&T->J, s, V, xe);
+  if (T->n_mid)
+    for (int e = T->jp_ptr[s]; e < T->jp_ptr[s + 1]; ++e) v += jx[T->jp_a[e]] * jx[T->jp_c[e]];
+  return v;
+}
+
 static void eval_tape(const omg_tables* T, const double* p, double* V) {
   V[0] = 1.0;
   for (int i = 0; i < T->n_par; ++i) V[1 + i] = p[i];
@@ -118,6 +137,7 @@ typedef struct {
   double *V, *xe, *xt, *g, *s, *y, *zL, *zU, *dsc, *sL, *sU, *beq, *sig, *wv, *ds, *dy,
          *dzL, *dzU, *gt, *st, *jval, *gf, *K, *rhs, *rx, *d0, *sol;
   int *rt, *eqidx, *eqrow;
+  double *jx, *mu;
 } Work;
 
 static void* xalloc(size_t n) { return calloc(n ? n : 1, 1); }
@@ -125,7 +145,8 @@ static void* xalloc(size_t n) { return calloc(n ? n : 1, 1); }
 static void work_alloc(Work* w, const omg_tables* T, int Nmax) {
   const int n = T->n, m = T->m;
   w->V = xalloc(sizeof(double) * T->n_v);
-  w->xe = xalloc(sizeof(double) * (n + 1)); w->xt = xalloc(sizeof(double) * (n + 1));
+  w->xe = xalloc(sizeof(double) * (n + 1 + T->n_mid)); w->xt = xalloc(sizeof(double) * (n + 1 + T->n_mid));
+  w->jx = xalloc(sizeof(double) * (T->n_mid ? T->nnz_jx : 1)); w->mu = xalloc(sizeof(double) * (T->n_mid + 1));
   double** mv[] = {&w->g, &w->s, &w->y, &w->zL, &w->zU, &w->dsc, &w->sL, &w->sU, &w->beq,
                    &w->sig, &w->wv, &w->ds, &w->dy, &w->dzL, &w->dzU, &w->gt, &w->st};
   for (unsigned k = 0; k < sizeof(mv) / sizeof(mv[0]); ++k) *mv[k] = xalloc(sizeof(double) * m);
@@ -140,7 +161,7 @@ static void work_alloc(Work* w, const omg_tables* T, int Nmax) {
 static void work_free(Work* w) {
   void* all[] = {w->V, w->xe, w->xt, w->g, w->s, w->y, w->zL, w->zU, w->dsc, w->sL, w->sU, w->beq,
                  w->sig, w->wv, w->ds, w->dy, w->dzL, w->dzU, w->gt, w->st, w->jval, w->gf, w->rx,
-                 w->K, w->rhs, w->d0, w->sol, w->rt, w->eqidx, w->eqrow};
+                 w->K, w->rhs, w->d0, w->sol, w->rt, w->eqidx, w->eqrow, w->jx, w->mu};
   for (unsigned k = 0; k < sizeof(all) / sizeof(all[0]); ++k) free(all[k]);
 }
 
@@ -156,6 +177,8 @@ static void solve_one(const omg_tables* T, const omg_options* O, Work* w, const 
   eval_tape(T, par, V);
   for (int i = 0; i < n; ++i) xe[i] = x0[i];
   xe[n] = 1.0; xt[n] = 1.0;
+  double* jx = w->jx; double* mu_mid = w->mu;
+  eval_mids(T, V, xe); eval_jx(T, V, xe, jx);
   /* scaling */
   const double smg = O->scaling_max_gradient;
   double fmaxv = 0.0;
@@ -165,7 +188,7 @@ static void solve_one(const omg_tables* T, const omg_options* O, Work* w, const 
   for (int i = 0; i < m; ++i) {
     double gm = 0.0;
     for (int sl = T->jrow_ptr[i]; sl < T->jrow_ptr[i + 1]; ++sl)
-      gm = fmax(gm, fabs(eval_slot(&T->J, sl, V, xe)));
+      gm = fmax(gm, fabs(jac_slot(T, sl, V, xe, jx)));
     const double d = (gm > smg) ? fmax(smg / gm, 1e-8) : 1.0;
     dsc[i] = d;
     const double lb = lbg[i], ub = ubg[i];
@@ -208,11 +231,12 @@ static void solve_one(const omg_tables* T, const omg_options* O, Work* w, const 
   int status = OMG_MAX_ITER_EXCEEDED, iter = 0, n_restarts = 0;
 
   for (iter = 0;; ++iter) {
+    eval_jx(T, V, xe, jx);
     double cinf = 0, maxprod = 0, minprod = 1e300, viol = 0, rsinf = 0, rsinf_un = 0, ysum = 0,
            zsum = 0, theta = 0, logsum = 0, rxinf = 0;
     for (int i = 0; i < m; ++i) {
       const int r = rt[i]; const double d = dsc[i];
-      for (int sl = T->jrow_ptr[i]; sl < T->jrow_ptr[i + 1]; ++sl) jval[sl] = d * eval_slot(&T->J, sl, V, xe);
+      for (int sl = T->jrow_ptr[i]; sl < T->jrow_ptr[i + 1]; ++sl) jval[sl] = d * jac_slot(T, sl, V, xe, jx);
       const double gi = g[i], si = s[i], yi = y[i];
       const double ci = (r & 4) ? gi - beq[i] : gi - si;
       cinf = fmax(cinf, fabs(ci)); theta += fabs(ci);
@@ -260,6 +284,11 @@ static void solve_one(const omg_tables* T, const omg_options* O, Work* w, const 
     /* ---- assemble + factorise -------------------------------------------- */
     double delta_w = 0.0, delta_c = 0.0; int first_try = 1, ok = 0;
     double* K = w->K; double* rhs = w->rhs;
+    for (int l = 0; l < T->n_mid; ++l) {   /* multipliers of the mids: mu = A^T lambda */
+      double acc = 0.0;
+      for (int e = T->mu_ptr[l]; e < T->mu_ptr[l + 1]; ++e) acc += y[T->mu_row[e]] * dsc[T->mu_row[e]] * jx[T->mu_slot[e]];
+      mu_mid[l] = acc;
+    }
     for (;;) {
       memset(K, 0, sizeof(double) * N * N);
       for (int q = 0; q < T->nnz_h; ++q) {
@@ -275,7 +304,7 @@ static void solve_one(const omg_tables* T, const omg_options* O, Work* w, const 
           double v = L->coef[t] * V[L->cidx[t]];
           for (int k = 0; k < L->width; ++k) v *= xe[L->xi[t * L->width + k]];
           const int lr = L->lrow[t];
-          v *= (lr < m) ? (y[lr] * dsc[lr]) : fsc;
+          v *= (lr < m) ? (y[lr] * dsc[lr]) : (lr == m ? fsc : mu_mid[lr - m - 1]);
           acc += v;
         }
         const int h = T->w2h[q];
@@ -335,6 +364,7 @@ static void solve_one(const omg_tables* T, const omg_options* O, Work* w, const 
     while (alpha >= a_min && n_ls < MAX_LS) {
       ++n_ls;
       for (int j = 0; j < n; ++j) xt[j] = xe[j] + alpha * dx[j];
+      eval_mids(T, V, xt);
       double tht = 0.0, lg = 0.0;
       for (int i = 0; i < m; ++i) {
         const int r = rt[i]; const double gi = dsc[i] * eval_slot(&T->G, i, V, xt);
@@ -382,7 +412,7 @@ static void solve_one(const omg_tables* T, const omg_options* O, Work* w, const 
       filt[2 * nf] = th; filt[2 * nf + 1] = ph; nfilt = nf + 1;
     }
     f = ft;
-    for (int j = 0; j < n; ++j) xe[j] = xt[j];
+    for (int j = 0; j < n + 1 + T->n_mid; ++j) xe[j] = xt[j];
     for (int i = 0; i < m; ++i) {
       const int r = rt[i]; g[i] = gt[i]; y[i] += alpha * dy[i];
       if (!(r & 4)) { const double si = st[i]; s[i] = si;
