@@ -457,7 +457,9 @@ class OptiFather(object):
     def shifted_entries(self, seg_shift=None):
         """[(offset, len_basis, n_columns, T)] of the spline variables that the
         warm-start knot shift touches: names containing 'seg<k>', k in
-        seg_shift (reference optilayer.py:470-490)."""
+        seg_shift (reference optilayer.py:470-490), plus splines a child marks
+        with ``_splines_prim[name]['shift'] = True`` (Quadrotor3D's
+        acceleration slacks, see vehicles/quadrotor3d.py)."""
         if seg_shift is None:
             seg_shift = [0]
         elif not isinstance(seg_shift, list):
@@ -466,8 +468,9 @@ class OptiFather(object):
         for label, child in self.children.items():
             for name, spl in child._splines_prim.items():
                 if name in child._variables:
-                    if ('seg' in name and
-                            int(name[name.index('seg') + 3]) in seg_shift):
+                    if (('seg' in name and
+                            int(name[name.index('seg') + 3]) in seg_shift) or
+                            (spl.get('shift') and 0 in seg_shift)):
                         off, size, shape = self._var_struct.entries[(label, name)]
                         out.append((label, name, off, shape, spl.get('init')))
         return out

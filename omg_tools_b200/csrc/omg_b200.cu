@@ -69,8 +69,8 @@ struct DevTab {
             *panel_ptr, *panel_rows, *panel_cmin;
   // intermediates (XL kernel only): G term ranges of the mids, term ranges of the extra
   // J slots (A = d row/d mid, C = d mid/d x), chain-rule pair lists, mu = A^T lambda lists
-  int n_mid, nnz_jx;
-  const int2* midg; const int* jx_tptr;
+  int n_mid, nnz_jx, n_hq_heavy;
+  const int2* midg; const int* jtptr; const int* jrow;
   const int *jp_ptr, *jp_a, *jp_c, *mu_ptr, *mu_row, *mu_slot;
 };
 
@@ -79,7 +79,7 @@ struct Smem {                      // offsets in doubles
   int sgn, eptr, efirst, pptr, prow, pcmin;
   int arr[N_ARR];                  // >= 0: shared offset; < 0: -(scratch offset + 1)
   int LDP, total;
-  int Kg, Vg, jxg, mug;            // XL kernel: scratch offsets (K only if S.K < 0)
+  int Kg, Vg, jxg, mug, Kcg;       // XL kernel: scratch offsets (K only if S.K < 0)
 };
 
 struct Batch {
@@ -412,20 +412,23 @@ __device__ __forceinline__ void back_solve_env(const DevTab& T, const Smem& S, c
   }
 }
 
-// Chain rule through the intermediates (XL kernel).  Evaluates the extra Jacobian slots
-// jx[s], s in [nnz_j, nnz_jx): A = d row/d mid (parameter-only) and C = d mid/d x, then
-// initialises every constraint-Jacobian slot with  sum_e A[jp_a[e]] * C[jp_c[e]]  (raw,
-// unscaled); the row pass adds the direct terms.  Ends with a block barrier.
-__device__ __forceinline__ void jac_chain(const DevTab& T, const double* __restrict__ V,
-                                          const double* __restrict__ xe, double* jx, double* jval) {
+// Constraint Jacobian of the XL kernel, one thread per slot (rows differ widely in size).
+// First the extra slots jx[s], s in [nnz_j, nnz_jx): A = d row/d mid (parameter-only) and
+// C = d mid/d x; then every constraint slot = direct terms + chain rule
+// sum_e A[jp_a[e]] * C[jp_c[e]], scaled by the row scaling dsc (nullptr: unscaled).
+// Ends with a block barrier.
+__device__ __forceinline__ void jac_xl(const DevTab& T, const double* __restrict__ V,
+                                       const double* __restrict__ xe, double* jx, double* jval,
+                                       const double* dsc) {
   const int tid = threadIdx.x;
   for (int s = T.nnz_j + tid; s < T.nnz_jx; s += NT)
-    jx[s] = eval_range(T.Jt, T.jx_tptr[s - T.nnz_j], T.jx_tptr[s - T.nnz_j + 1], V, xe);
+    jx[s] = eval_range(T.Jt, T.jtptr[s], T.jtptr[s + 1], V, xe);
   __syncthreads();
   for (int s = tid; s < T.nnz_j; s += NT) {
-    double acc = 0.0;
-    for (int e = T.jp_ptr[s]; e < T.jp_ptr[s + 1]; ++e) acc += jx[T.jp_a[e]] * jx[T.jp_c[e]];
-    jval[s] = acc;
+    double acc = eval_range(T.Jt, T.jtptr[s], T.jtptr[s + 1], V, xe);
+    if (T.n_mid)
+      for (int e = T.jp_ptr[s]; e < T.jp_ptr[s + 1]; ++e) acc += jx[T.jp_a[e]] * jx[T.jp_c[e]];
+    jval[s] = dsc ? dsc[T.jrow[s]] * acc : acc;
   }
   __syncthreads();
 }
@@ -450,6 +453,7 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
   double* V = XL ? Dx + S.Vg : sm + S.V;
   double* jx = XL ? Dx + S.jxg - T.nnz_j : nullptr;   // indexed by slot id >= nnz_j
   double* mu_mid = XL ? Dx + S.mug : nullptr;
+  double* Kc = XL ? Dx + S.Kcg : nullptr;
   const int n_xe = T.n + 1 + (XL ? T.n_mid : 0);
   double* red = sm + S.red;
   double* filt = sm + S.filt;
@@ -527,7 +531,7 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
     if (XL) {
       for (int l = tid; l < T.n_mid; l += NT) { const int2 r = T.midg[l]; xe[n + 1 + l] = eval_range(T.Gt, r.x, r.y, V, xe); }
       __syncthreads();
-      jac_chain(T, V, xe, jx, jval);
+      jac_xl(T, V, xe, jx, jval, nullptr);
     }
 
     // ---- S3: row classification, scaling, starting point -----------------------
@@ -545,16 +549,8 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
       const RowRec rr = T.rowrec[i];
       // Jacobian row: max |J| for the gradient-based scaling
       double gm = 0.0;
-      if (XL) {       // jval holds the chain-rule part (jac_chain); add the direct terms
-        double* jv = jval + rr.s0;
-        double acc = 0.0; int cur = 0, aux;
-        for (int k = rr.jt0; k < rr.jt1; ++k) {
-          const double v = term_value(T.Jt + k, V, xe, &aux);
-          if (aux != cur) { jv[cur] += acc; acc = 0.0; cur = aux; }
-          acc += v;
-        }
-        if (rr.jt1 > rr.jt0) jv[cur] += acc;
-        for (int k = 0; k < rr.ns; ++k) gm = fmax(gm, fabs(jv[k]));
+      if (XL) {       // jval = unscaled Jacobian (jac_xl)
+        for (int k = 0; k < rr.ns; ++k) gm = fmax(gm, fabs(jval[rr.s0 + k]));
       } else {
         double acc = 0.0; int cur = 0, aux;
         for (int k = rr.jt0; k < rr.jt1; ++k) {
@@ -632,22 +628,12 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
                              OP_SUM, OP_SUM, OP_SUM, OP_SUM, OP_MAX, OP_SUM};
       for (int r = 0; r < NRED; ++r) rv[r] = 0.0;
       rv[2] = 1e300;
-      if (XL) jac_chain(T, V, xe, jx, jval);
+      if (XL) jac_xl(T, V, xe, jx, jval, dsc);
       for (int i = tid; i < m; i += NT) {
         const RowRec rr = T.rowrec[i];
         const int r = rt[i];
         const double d = dsc[i];
-        if (XL) {
-          double* jv = jval + rr.s0;
-          for (int k = 0; k < rr.ns; ++k) jv[k] *= d;
-          double acc = 0.0; int cur = 0, aux;
-          for (int k = rr.jt0; k < rr.jt1; ++k) {
-            const double v = term_value(T.Jt + k, V, xe, &aux);
-            if (aux != cur) { jv[cur] += d * acc; acc = 0.0; cur = aux; }
-            acc += v;
-          }
-          if (rr.jt1 > rr.jt0) jv[cur] += d * acc;
-        } else {
+        if (!XL) {
           double acc = 0.0; int cur = 0, aux;
           double* jv = jval + rr.s0;
 #pragma unroll 4
@@ -769,7 +755,26 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
         __syncthreads();
       }
       // ---- I7/I8: assemble + factorise, with inertia correction -----------------
+      bool assembled = false;   // XL: the assembled K (delta = 0) is kept in scratch for retries
       for (;;) {
+        if (XL && assembled) {
+          const double2* C2 = reinterpret_cast<const double2*>(Kc);
+          double2* K2 = reinterpret_cast<double2*>(K);
+          const int h2 = (T.env_size + 1) >> 1;
+          for (int q = tid; q < h2; q += NT) K2[q] = C2[q];
+          __syncthreads();
+          for (int j = tid; j < n; j += NT) {
+            const int pj = T.pos_var[j];
+            const double v = K[T.kdiag[pj]] + ctl.delta_w;
+            K[T.kdiag[pj]] = v; diag0[pj] = fabs(v);
+          }
+          for (int k = tid; k < n_eq; k += NT) {
+            const int pk = T.pos_eq[k];
+            K[T.kdiag[pk]] = -ctl.delta_c; diag0[pk] = ctl.delta_c;
+          }
+          if (tid == 0) { ctl.fail = 0; ctl.eq_fail = 0; }
+          __syncthreads();
+        } else {
         {
           double2* K2 = reinterpret_cast<double2*>(K);
           const int h2 = (T.env_size + 1) >> 1;
@@ -791,6 +796,22 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
         __syncthreads();
         TICK(5);   // zero + H gather
         // Lagrangian Hessian W (lambda = y*dsc, objective factor fsc)
+        if (XL) {   // slots differ widely in term count: one warp per slot
+          const int lane = tid & 31;
+          for (int q = tid >> 5; q < T.nnz_w; q += NWARP) {
+            const WRec w = T.wrec[q];
+            double acc = 0.0;
+            for (int t = w.t0 + lane; t < w.t1; t += 32) {
+              int lr;
+              double v = term_value(T.Wt + t, V, xe, &lr);
+              v *= (lr < m) ? (y[lr] * dsc[lr]) : (lr == m ? ctl.fsc : mu_mid[lr - m - 1]);
+              acc += v;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(FULL, acc, o);
+            if (lane == 0) K[w.dst] += acc;
+          }
+        } else
         for (int q = tid; q < T.nnz_w; q += NT) {
           const WRec w = T.wrec[q];
           double acc = 0.0;
@@ -830,6 +851,14 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
         }
         if (tid == 0) { ctl.fail = 0; ctl.eq_fail = 0; }
         __syncthreads();
+        if (XL) {
+          double2* C2 = reinterpret_cast<double2*>(Kc);
+          const double2* K2 = reinterpret_cast<const double2*>(K);
+          const int h2 = (T.env_size + 1) >> 1;
+          for (int q = tid; q < h2; q += NT) C2[q] = K2[q];
+          assembled = true;
+        }
+        }
         TICK(6);   // W + border + rhs
         factor_env(T, S, K, &ctl, tracing ? phase_cyc : nullptr);
         __syncthreads();
@@ -1317,7 +1346,7 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
     std::vector<int2> mg(n_mid);
     for (int l = 0; l < n_mid; ++l) mg[l] = make_int2(tb->G.ptr[m + l], tb->G.ptr[m + l + 1]);
     T.midg = upload(h, mg.data(), mg.size(), &ok);
-    T.jx_tptr = upload(h, tb->J.ptr + tb->nnz_j, (size_t)(tb->nnz_jx - tb->nnz_j) + 1, &ok);
+
     T.jp_ptr = upload(h, tb->jp_ptr, (size_t)tb->nnz_j + 1, &ok);
     T.jp_a = upload(h, tb->jp_a, tb->n_jp, &ok);
     T.jp_c = upload(h, tb->jp_c, tb->n_jp, &ok);
@@ -1325,6 +1354,8 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
     T.mu_row = upload(h, tb->mu_row, tb->n_mu, &ok);
     T.mu_slot = upload(h, tb->mu_slot, tb->n_mu, &ok);
   }
+  T.jtptr = upload(h, tb->J.ptr, (size_t)T.nnz_jx + 1, &ok);
+  T.jrow = upload(h, tb->jrow, tb->nnz_j, &ok);
   {  // CSC view of the Jacobian pattern: slot | row << 16
     std::vector<int> cptr(n + 1, 0);
     std::vector<unsigned> crec(tb->nnz_j > 0 ? tb->nnz_j : 1);
@@ -1355,6 +1386,7 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
       for (int e = tb->hp_ptr[q]; e < tb->hp_ptr[q + 1]; ++e)
         pack[pos++] = (unsigned)tb->hp_s1[e] | ((unsigned)tb->hp_s2[e] << 16);
       r.p1 = pos;
+      if (r.p1 - r.p0 >= 64) T.n_hq_heavy = k + 1;
     }
     for (int j = 0; j < n; ++j) if (!has[j]) {
       set_err("H pattern lacks a diagonal entry (variable without constraint)"); ok = false; break; }
@@ -1449,13 +1481,14 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
     set_err(buf); ok = false;
   }
   int goff = 0;   // global scratch offset (doubles)
-  S.Kg = S.Vg = S.jxg = S.mug = 0;
+  S.Kg = S.Vg = S.jxg = S.mug = S.Kcg = 0;
   if (h->xl) {
     auto gtake = [&](int cnt) { int o = goff; goff += (cnt + 1) & ~1; return o; };
     S.Vg = gtake(T.n_v);
     S.jxg = gtake(T.nnz_jx - T.nnz_j + 1);
     S.mug = gtake(n_mid + 1);
     if (!k_in_smem) S.Kg = gtake(T.env_size + 2);
+    S.Kcg = gtake(T.env_size + 2);
   }
   const int sizes[N_ARR] = {tb->nnz_j, m, tb->nnz_j, m, m, m, m, m, m, m, m, m, m, m, m, m, m, m, m};
   for (int k = 0; k < N_ARR; ++k) {

@@ -83,6 +83,13 @@ class Quadrotor3D(Vehicle):
             self.ddx = self.define_spline_variable('ddx', 1, 1, basis=bx)[0]
             self.ddy = self.define_spline_variable('ddy', 1, 1, basis=by)[0]
             self.ddz = self.define_spline_variable('ddz', 1, 1, basis=bz)[0]
+            # The reference does not shift these slacks over a knot (their names
+            # lack 'seg', optilayer.py:470-490) and leaves the inconsistent warm
+            # start to IPOPT's restoration phase.  This solver has no restoration
+            # phase: shifting them with the position splines keeps the
+            # warm start consistent; the NLP and its optimum are unchanged.
+            for name in ('ddx', 'ddy', 'ddz'):
+                self._splines_prim[name]['shift'] = True
             self.x, self.dx = self.integrate_twice(self.ddx, self.dpos0[0], self.pos0[0], self.t, T)
             self.y, self.dy = self.integrate_twice(self.ddy, self.dpos0[1], self.pos0[1], self.t, T)
             self.z, self.dz = self.integrate_twice(self.ddz, self.dpos0[2], self.pos0[2], self.t, T)
@@ -204,5 +211,39 @@ class Quadrotor3D(Vehicle):
         return x, dx
 
     def splines2signals(self, splines, time):
-        raise NotImplementedError('trajectory extraction for Quadrotor3D is '
-                                  'host-side bookkeeping outside this round')
+        """State (position, velocity, roll, pitch) and input (thrust, roll and
+        pitch rate) trajectories of the flat outputs; the position is the
+        double integral re-anchored at the predicted state at time[0]
+        (reference quadrotor3d.py:253-275; the err_* plot signals are not
+        produced)."""
+        signals = {}
+        f_til, q_phi, q_theta = splines[0], splines[1], splines[2]
+        dq_phi, dq_theta = q_phi.derivative(), q_theta.derivative()
+        ddx = f_til * (1 - q_phi**2) * (2 * q_theta)
+        ddy = -f_til * (1 + q_theta**2) * (2 * q_phi)
+        ddz = f_til * (1 - q_phi**2) * (1 - q_theta**2) - self.g
+        st = self.prediction['state']
+        x, dx = self.integrate_twice(ddx, st[3], st[0], time[0])
+        y, dy = self.integrate_twice(ddy, st[4], st[1], time[0])
+        z, dz = self.integrate_twice(ddz, st[5], st[2], time[0])
+        x_s, y_s, z_s, dx_s, dy_s, dz_s = sample_splines([x, y, z, dx, dy, dz], time)
+        f_til_s, q_phi_s, q_theta_s, dq_phi_s, dq_theta_s = sample_splines(
+            [f_til, q_phi, q_theta, dq_phi, dq_theta], time)
+        den = sample_splines([(1 + q_phi**2) * (1 + q_theta**2)], time)[0]
+        phi = 2 * np.arctan2(q_phi_s, 1)
+        theta = 2 * np.arctan2(q_theta_s, 1)
+        dphi = 2 * np.array(dq_phi_s) / (1. + np.array(q_phi_s)**2)
+        dtheta = 2 * np.array(dq_theta_s) / (1. + np.array(q_theta_s)**2)
+        f_s = f_til_s * den
+        signals['state'] = np.c_[x_s, y_s, z_s, dx_s, dy_s, dz_s, phi, theta].T
+        signals['input'] = np.c_[f_s, dphi.T, dtheta.T].T
+        return signals
+
+    def state2pose(self, state):
+        return np.r_[state[0], state[1], state[2], state[6], state[7], 0.]
+
+    def ode(self, state, input):
+        phi, theta = state[6], state[7]
+        u1, u2, u3 = input[0], input[1], input[2]
+        return np.r_[state[3:6], u1 * np.sin(theta) * np.cos(phi), -u1 * np.sin(phi),
+                     -self.g + u1 * np.cos(phi) * np.cos(theta), u2, u3].T

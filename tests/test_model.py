@@ -182,3 +182,75 @@ def test_holonomic1d_problem_solves_on_oracle():
     basis = veh.basis
     Bd, P1 = basis.derivative(1)
     assert (P1.dot(res.x[:13]) / 10. <= 0.5 + 1e-6).all()
+
+
+class _OracleSolver(object):
+    """Stand-in for the solver callable of Problem.solve() (reference
+    problem.py:113) backed by the CPU oracle: lets the host loop run without a
+    GPU.  Test infrastructure only."""
+
+    def __init__(self, tb):
+        from oracle import ipm_c
+        self.tb, self.ipm_c = tb, ipm_c
+
+    def __call__(self, x0, p, lbg, ubg, lam_g0=None, **kw):
+        r = self.ipm_c.solve_batch_full(
+            self.tb, np.asarray(x0, float)[None], np.asarray(p, float)[None], threads=1,
+            lbg=np.asarray(lbg, float)[None], ubg=np.asarray(ubg, float)[None])
+        self.last = r
+        return {'x': r['x'][0], 'lam_g': r['lam_g'][0], 'f': r['f'][0]}
+
+    def stats(self):
+        ok = self.last['status'][0] == 0
+        return {'return_status': 'Solve_Succeeded' if ok else 'Restoration_Failed',
+                'iter_count': int(self.last['iters'][0])}
+
+
+def test_quadrotor3d_config4_tables_and_receding_horizon():
+    """BASELINE config 4 (examples/p2p_3dquadrotor.py).  Sizes as surveyed
+    (n=238, m=1319), 236 shared intermediates; derivatives of the chain-rule
+    tables against finite differences; then the reference's MPC loop
+    (predict/init_step/solve/store/simulate, update_time 0.4 s) flies the
+    quadrotor to the goal with every solve converged."""
+    from oracle import ipm_c
+    if not ipm_c.available():
+        pytest.skip('C oracle not built')
+    pr = sc.config4(build_solver=False)
+    tb = pr.father.tables
+    assert (tb.n, tb.m, tb.n_mid, tb.degree) == (238, 1319, 236, 5)
+    ev = TableEval(tb)
+    rng = np.random.default_rng(1)
+    X0, P = sc.instance_data(pr, 1)
+    x = X0[0] + 0.05 * rng.standard_normal(tb.n)
+    V = ev.tape(P[0])
+    J = ev.jac_dense(x, V)
+    lam = rng.standard_normal(tb.m)
+    W = ev.hess_dense(x, V, lam)
+    h = 1e-6
+    for j in rng.choice(tb.n, 8, replace=False):
+        e = np.zeros(tb.n)
+        e[j] = h
+        assert np.abs((ev.g(x + e, V) - ev.g(x - e, V)) / (2 * h) - J[:, j]).max() < 1e-5
+        dj = (ev.jac_dense(x + e, V).T @ lam - ev.jac_dense(x - e, V).T @ lam) / (2 * h)
+        assert np.abs(dj - W[:, j]).max() < 1e-5
+    # rows evaluate to the model's polynomials (intermediates expanded)
+    f = pr.father
+    vals = {pl.resolve(s): v for s, v in zip(f._var_ids, x)}
+    vals.update({pl.resolve(s): v for s, v in zip(f._par_ids, P[0])})
+    rows, _, _ = f.construct_constraints()
+    direct = np.array([r.evaluate(dict(vals)) if isinstance(r, pl.Poly) else float(r)
+                       for r in rows])
+    assert np.abs(direct - ev.g(x, V)).max() < 1e-11
+    # receding horizon
+    pr.problem = _OracleSolver(tb)
+    pr.initialize(0.)
+    t, dt = 0., 0.4
+    for k in range(13):
+        pr.predict(t, dt, 0.01)
+        pr.init_step(t, dt)
+        pr.solve(t, dt)
+        assert pr.problem.stats()['return_status'] == 'Solve_Succeeded', k
+        pr.store(t, dt, 0.01)
+        pr.simulate(t, dt, 0.01)
+        t += dt
+    assert np.abs(pr.vehicles[0].signals['state'][:3, -1] - [3., 2., 0.5]).max() < 1e-2
