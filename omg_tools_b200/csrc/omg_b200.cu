@@ -453,7 +453,7 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
   double* V = XL ? Dx + S.Vg : sm + S.V;
   double* jx = XL ? Dx + S.jxg - T.nnz_j : nullptr;   // indexed by slot id >= nnz_j
   double* mu_mid = XL ? Dx + S.mug : nullptr;
-  double* Kc = XL ? Dx + S.Kcg : nullptr;
+  double* Kc = Dx + S.Kcg;
   const int n_xe = T.n + 1 + (XL ? T.n_mid : 0);
   double* red = sm + S.red;
   double* filt = sm + S.filt;
@@ -755,9 +755,9 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
         __syncthreads();
       }
       // ---- I7/I8: assemble + factorise, with inertia correction -----------------
-      bool assembled = false;   // XL: the assembled K (delta = 0) is kept in scratch for retries
+      bool assembled = false;   // the assembled K (delta = 0) is kept in scratch for the retries
       for (;;) {
-        if (XL && assembled) {
+        if (assembled) {
           const double2* C2 = reinterpret_cast<const double2*>(Kc);
           double2* K2 = reinterpret_cast<double2*>(K);
           const int h2 = (T.env_size + 1) >> 1;
@@ -851,7 +851,7 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
         }
         if (tid == 0) { ctl.fail = 0; ctl.eq_fail = 0; }
         __syncthreads();
-        if (XL) {
+        {
           double2* C2 = reinterpret_cast<double2*>(Kc);
           const double2* K2 = reinterpret_cast<const double2*>(K);
           const int h2 = (T.env_size + 1) >> 1;
@@ -1488,8 +1488,8 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
     S.jxg = gtake(T.nnz_jx - T.nnz_j + 1);
     S.mug = gtake(n_mid + 1);
     if (!k_in_smem) S.Kg = gtake(T.env_size + 2);
-    S.Kcg = gtake(T.env_size + 2);
   }
+  S.Kcg = goff; goff += (T.env_size + 2 + 1) & ~1;
   const int sizes[N_ARR] = {tb->nnz_j, m, tb->nnz_j, m, m, m, m, m, m, m, m, m, m, m, m, m, m, m, m};
   for (int k = 0; k < N_ARR; ++k) {
     const int cnt = (sizes[k] + 1) & ~1;
