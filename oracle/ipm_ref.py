@@ -114,8 +114,9 @@ def solve(tb, x0, p, lbg=None, ubg=None, options=None, lam_g0=None,
                   k1 * np.maximum(1, np.abs(sL)))
     pU = np.where(both, np.minimum(k1 * np.maximum(1, np.abs(sU)), k2 * (sU - sL)),
                   k1 * np.maximum(1, np.abs(sU)))
-    s = np.where(hasL, np.maximum(s, sL + pL), s)
-    s = np.where(hasU, np.minimum(s, sU - pU), s)
+    with np.errstate(invalid='ignore'):      # -inf + inf on rows without that bound (masked)
+        s = np.where(hasL, np.maximum(s, sL + pL), s)
+        s = np.where(hasU, np.minimum(s, sU - pU), s)
     y = np.zeros(m)
     if lam_g0 is not None:
         y = np.asarray(lam_g0, dtype=float) * fsc / dsc

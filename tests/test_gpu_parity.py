@@ -406,3 +406,21 @@ def test_quadrotor3d_receding_horizon_dropin():
         pr.simulate(t, dt, 0.01)
         t += dt
     assert pr.vehicles[0].signals['state'][1, -1] > -1.0     # moved towards the goal
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['config4', 'holonomic3d'])
+def test_matches_vehicle_goldens(name):
+    """CUDA path against the committed numpy-oracle solutions of config 4 and
+    the Holonomic3D example at tight tolerance (end point solver independent)."""
+    GV = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'vehicles_golden.npz'))
+    if name == 'config4':
+        pr = sc.config4()
+    else:
+        pr = sc.config_holonomic3d(start=(-1.7, -1.7, -1.7), goal=(1.7, 1.7, -1.7))
+    pr.problem.set_options(TIGHT)
+    res = pr.problem.solve_batch(GV[name + '_X0'], GV[name + '_P'])
+    assert np.array_equal(res['status'], GV[name + '_tight_status'])
+    assert np.abs(res['iters'] - GV[name + '_tight_iters']).max() <= 2
+    assert np.abs(res['x'] - GV[name + '_tight_x']).max() < NORTH_STAR_TOL
+    assert np.abs(res['f'] - GV[name + '_tight_f']).max() < 1e-6

@@ -95,3 +95,55 @@ def test_kkt_structure_is_consistent(cfg1):
         hi, lo = max(a, b), min(a, b)
         assert lo >= tb.env_first[hi]
         assert tb.kkt_hdst[q] == tb.env_ptr[hi] + lo - tb.env_first[hi]
+
+
+GV = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'vehicles_golden.npz'))
+
+
+@pytest.mark.parametrize('name', ['config4', 'holonomic3d'])
+def test_c_oracle_reproduces_vehicle_goldens(name):
+    """The C port against the committed numpy-oracle solutions of BASELINE
+    config 4 (Quadrotor3D, intermediates + chain rule) and the Holonomic3D
+    example, default and tight tolerance."""
+    from oracle import ipm_c
+    if not ipm_c.available():
+        pytest.skip('C oracle not built')
+    if name == 'config4':
+        pr = sc.config4(build_solver=False)
+        X0, P = sc.instance_data(pr, 2, jitter=0.1, seed=3)
+    else:
+        pr = sc.config_holonomic3d(build_solver=False, start=(-1.7, -1.7, -1.7),
+                                   goal=(1.7, 1.7, -1.7))
+        X0, P = sc.instance_data(pr, 2, jitter=0.1, seed=1)
+    tb = pr.father.tables
+    assert np.array_equal(GV[name + '_dims'], [tb.n, tb.m, tb.n_par])
+    assert np.allclose(X0, GV[name + '_X0'], atol=0, rtol=0)
+    assert np.allclose(P, GV[name + '_P'], atol=1e-15, rtol=0)
+    tight = {'tol': 1e-8, 'compl_inf_tol': 1e-8, 'constr_viol_tol': 1e-8}
+    for tag, opt, tol in (('loose', None, 1e-4), ('tight', tight, 1e-5)):
+        r = ipm_c.solve_batch_full(tb, X0, P, threads=2, options=opt)
+        assert np.array_equal(r['status'], GV['%s_%s_status' % (name, tag)])
+        assert np.abs(r['iters'] - GV['%s_%s_iters' % (name, tag)]).max() <= 1
+        assert np.abs(r['x'] - GV['%s_%s_x' % (name, tag)]).max() < tol
+        assert np.abs(r['f'] - GV['%s_%s_f' % (name, tag)]).max() < 1e-7
+
+
+def test_config4_golden_satisfies_kkt_conditions():
+    """First-order optimality of the tight Quadrotor3D golden solution with the
+    chain-rule Jacobian of the intermediates."""
+    pr = sc.config4(build_solver=False)
+    tb = pr.father.tables
+    ev = TableEval(tb)
+    x, lam = GV['config4_tight_x'][0], GV['config4_tight_lam'][0]
+    V = ev.tape(GV['config4_P'][0])
+    g = ev.g(x, V)
+    assert (g <= tb.ubg + 1e-7).all() and (g >= tb.lbg - 1e-7).all()
+    stat = ev.gradf(x, V) + ev.jac_dense(x, V).T @ lam
+    assert np.abs(stat).max() < 1e-5
+    act_u = np.isfinite(tb.ubg) & (tb.ubg < 1e19) & (tb.lbg != tb.ubg)
+    act_l = (tb.lbg > -1e19) & (tb.lbg != tb.ubg)
+    # multipliers push against the bound they belong to
+    assert (lam[act_u & ~act_l] > -1e-8).all()
+    slack = np.minimum(np.where(act_u, tb.ubg - g, np.inf), np.where(act_l, g - tb.lbg, np.inf))
+    ineq = tb.lbg != tb.ubg
+    assert np.abs(lam[ineq] * slack[ineq]).max() < 1e-5
