@@ -121,7 +121,8 @@ typedef struct omg_options {
    * zero the multipliers, clear the filter and continue from mu = restart_mu;
    * at most max_restarts times, then Restoration_Failed. */
   int32_t max_restarts;
-  int32_t reserved;
+  int32_t soft_resto;     /* 1: IPOPT's soft restoration -- when the filter rejects every trial step,
+                           * accept the step if it reduces the primal-dual error by 1e-4 (default 1) */
   double restart_mu, restart_push;
 } omg_options;
 

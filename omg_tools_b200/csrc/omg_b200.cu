@@ -123,6 +123,7 @@ struct Ctl {                       // uniform per-block control scalars
 #define PIV_TOL 1e-12
 #define INF_BOUND 1e19
 #define MAX_LS 40
+#define SOFT_RESTO_FACTOR 0.9999
 #define DBL_EPS 2.220446049250313e-16
 
 enum { OP_MAX = 0, OP_MIN = 1, OP_SUM = 2 };
@@ -985,6 +986,90 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
         if (ok) { accepted = true; break; }
         alpha *= 0.5;
       }
+      bool soft = false;
+      if (!accepted && O.soft_resto) {
+        // ---- soft restoration (IPOPT): the filter rejected every trial step; accept a step
+        // along the same direction if it reduces the primal-dual error of the barrier problem
+        __syncthreads();
+        double pv[1]; const int pop[1] = {OP_SUM};
+        pv[0] = 0.0;
+        for (int i = tid; i < m; i += NT) {
+          const int r = rt[i];
+          if (r & 4) { pv[0] += fabs(g[i] - beq[i]); continue; }
+          const double si = s[i];
+          double zl = 0.0, zu = 0.0, acc = fabs(g[i] - si);
+          if (r & 1) { zl = zL[i]; acc += fabs((si - sL[i]) * zl - mu); }
+          if (r & 2) { zu = zU[i]; acc += fabs((sU[i] - si) * zu - mu); }
+          pv[0] += acc + fabs(-y[i] - zl + zu);
+        }
+        for (int j = tid; j < n; j += NT) {
+          double rx = gf[j];
+          for (int q = T.colptr[j]; q < T.colptr[j + 1]; ++q) {
+            const unsigned cr = __ldg(T.colrec + q);
+            rx += jval[cr & 0xffffu] * y[cr >> 16];
+          }
+          pv[0] += fabs(rx);
+        }
+        block_reduce<1>(pv, pop, red);
+        const double pd0 = pv[0];
+        alpha = a_p;
+        for (int n_try = 0; n_try < 12; ++n_try) {
+          for (int j = tid; j < n; j += NT) xt[j] = xe[j] + alpha * dx[j];
+          __syncthreads();
+          if (XL) {
+            for (int l = tid; l < T.n_mid; l += NT) { const int2 r = T.midg[l]; xt[n + 1 + l] = eval_range(T.Gt, r.x, r.y, V, xt); }
+            __syncthreads();
+            jac_xl(T, V, xt, jx, jsv, dsc);       // trial Jacobian -> jsv (free until the next sigma pass)
+          }
+          const double az = fmin(alpha, a_d);
+          pv[0] = 0.0;
+          for (int i = tid; i < m; i += NT) {
+            const RowRec rr = T.rowrec[i];
+            const int r = rt[i];
+            const double d = dsc[i];
+            if (!XL) {
+              double acc = 0.0; int cur = 0, aux;
+              double* jv = jsv + rr.s0;
+              for (int k = rr.jt0; k < rr.jt1; ++k) {
+                const double v = term_value(T.Jt + k, V, xt, &aux);
+                if (aux != cur) { jv[cur] = d * acc; acc = 0.0; cur = aux; }
+                acc += v;
+              }
+              if (rr.ns > 0) jv[cur] = d * acc;
+            }
+            const double gi = d * eval_range(T.Gt, rr.g0, rr.g1, V, xt);
+            gt[i] = gi;
+            const double yt = y[i] + alpha * dy[i];
+            wv[i] = yt;
+            if (r & 4) { pv[0] += fabs(gi - beq[i]); continue; }
+            const double si = s[i] + alpha * ds[i];
+            st[i] = si;
+            double zl = 0.0, zu = 0.0, acc = fabs(gi - si);
+            if (r & 1) { zl = zL[i] + az * dzL[i]; acc += fabs((si - sL[i]) * zl - mu); }
+            if (r & 2) { zu = zU[i] + az * dzU[i]; acc += fabs((sU[i] - si) * zu - mu); }
+            pv[0] += acc + fabs(-yt - zl + zu);
+          }
+          __syncthreads();
+          for (int j = tid; j < n; j += NT) {
+            double rx = ctl.fsc * eval_range(T.DFt, T.dfptr[j], T.dfptr[j + 1], V, xt);
+            for (int q = T.colptr[j]; q < T.colptr[j + 1]; ++q) {
+              const unsigned cr = __ldg(T.colrec + q);
+              rx += jsv[cr & 0xffffu] * wv[cr >> 16];
+            }
+            pv[0] += fabs(rx);
+          }
+          block_reduce<1>(pv, pop, red);
+          if (isfinite(pv[0]) && pv[0] <= SOFT_RESTO_FACTOR * pd0) {
+            double fv[1]; fv[0] = 0.0;
+            for (int t = tid; t < T.n_f; t += NT) { int aux; fv[0] += term_value(T.Ft + t, V, xt, &aux); }
+            block_reduce<1>(fv, pop, red);
+            ft = ctl.fsc * fv[0];
+            accepted = true; soft = true; ftype = true;
+            break;
+          }
+          alpha *= 0.5;
+        }
+      }
       if (!accepted) {
         if (ctl.n_restart < O.max_restarts) {
           // feasibility restart (stand-in for IPOPT's restoration phase, oracle/ipm_ref.py):
@@ -1013,6 +1098,7 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
       }
       __syncthreads();
       if (tid == 0) {
+        if (soft) ctl.nfilt = 0;
         if (!ftype) {        // augment the filter, dropping dominated entries
           const double th = (1.0 - GAMMA_THETA) * theta0, ph = phi0 - GAMMA_PHI * theta0;
           int nf = 0;
@@ -1270,7 +1356,7 @@ void omg_default_options(omg_options* o) {
   o->mu_init = 0.1; o->bound_push = 1e-3; o->bound_frac = 1e-3; o->mult_bound_push = 1e-3;
   o->bound_relax_factor = 1e-8; o->scaling_max_gradient = 100.0;
   o->max_iter = 3000; o->trace = 0;
-  o->max_restarts = 5; o->reserved = 0; o->restart_mu = 1.0; o->restart_push = 0.1;
+  o->max_restarts = 5; o->soft_resto = 1; o->restart_mu = 1.0; o->restart_push = 0.1;
 }
 
 omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, int device) {

@@ -3,7 +3,9 @@
 Mirrors the reference's ``omgtools/problems/point2point.py``: construct 53-62,
 initial constraints 64-70, terminal constraints + L1 slack objective 151-172,
 parameters t/T 174-181, knot-crossing warm-start shift 187-201, store 213-229.
-FreeT (T as a variable) is a "next" row of SURVEY.md section 8f.
+``FreeTPoint2point`` (T as a decision variable, reference 269-374) is
+supported for models whose rows stay polynomial in T: no safety-distance
+slack (its objective integrates from t/T) and no rotating obstacles.
 """
 from __future__ import print_function
 
@@ -11,7 +13,8 @@ import numpy as np
 
 from .problem import Problem
 from ..basics.optilayer import inf
-from ..basics.spline_extra import definite_integral, shiftoverknot_T, evalspline
+from ..basics.spline_extra import (definite_integral, shiftoverknot_T, evalspline,
+                                   shift_spline)
 
 
 class Point2point(object):
@@ -19,9 +22,7 @@ class Point2point(object):
 
     def __new__(cls, fleet, environment, options=None, freeT=False):
         if freeT:
-            raise NotImplementedError(
-                'FreeTPoint2point is outside this round\'s hot-path scope '
-                '(SURVEY.md 8f item 3)')
+            return FreeTPoint2point(fleet, environment, options)
         return FixedTPoint2point(fleet, environment, options)
 
 
@@ -36,9 +37,13 @@ class Point2pointProblem(Problem):
         Problem.set_default_options(self)
         self.options['inter_vehicle_avoidance'] = False
 
-    def construct(self):
+    def define_time_symbols(self):
+        """T and t are parameters of the fixed-T problem (reference 176-181)."""
         self.T, self.t = self.define_parameter('T'), self.define_parameter('t')
         self.t0 = self.t / self.T
+
+    def construct(self):
+        self.define_time_symbols()
         Problem.construct(self)
         for vehicle in self.vehicles:
             splines = vehicle.define_splines(n_seg=1)
@@ -192,3 +197,105 @@ class FixedTPoint2point(Point2pointProblem):
                 g = self.father.get_variables(self, 'g' + str(k))[0]
                 obj += self.options['horizon_time'] * g.integral()
         return obj
+
+
+class FreeTPoint2point(Point2pointProblem):
+    """Minimum-time point-to-point problem: the motion time T is a decision
+    variable and the objective (reference point2point.py:269-374).
+
+    The reference evaluates the initial conditions at ``t/T``; its parameter t
+    is always 0 for this problem (point2point.py:300-306, the time axis resets
+    every update) unless a multi-problem scheduler sets ``init_time``.  ``t/T``
+    is not polynomial in the variable T, so the initial conditions are taken
+    at 0 here and a non-zero ``init_time`` is refused.
+    """
+
+    def __init__(self, fleet, environment, options):
+        Point2pointProblem.__init__(self, fleet, environment, options)
+        self.objective = 0.
+
+    def define_time_symbols(self):
+        self.T = self.define_variable('T', value=10.)
+        self.t = self.define_parameter('t')
+        self.t0 = 0.
+
+    def construct(self):
+        Point2pointProblem.construct(self)
+        self.define_objective(self.T)
+        self.define_constraint(-self.T, -inf, 0.)     # positive motion time
+        self.define_init_constraints()
+        self.define_terminal_constraints()
+
+    def define_init_constraints(self):
+        for vehicle in self.vehicles:
+            init_con = vehicle.get_initial_constraints(vehicle.splines[0], self.T)
+            for spline, condition in init_con:
+                self.define_constraint(spline(0.) - condition, 0., 0.)
+
+    def define_terminal_constraints(self):
+        for vehicle in self.vehicles:
+            term_con, term_con_der = vehicle.get_terminal_constraints(
+                vehicle.splines[0])
+            if self.options.get('no_term_con_der'):
+                term_con_der = []
+            for spline, condition in term_con + term_con_der:
+                self.define_constraint(spline(1.) - condition, 0., 0.)
+
+    def set_init_time(self, time):
+        if time:
+            raise NotImplementedError('FreeTPoint2point with a non-zero init_time: '
+                                      't/T is not polynomial in T')
+        self.init_time = time
+
+    def set_parameters(self, current_time):
+        parameters = Point2pointProblem.set_parameters(self, current_time)
+        parameters[self]['t'] = 0.
+        return parameters
+
+    def horizon_time(self):
+        return float(np.asarray(self.father.get_variables(self, 'T')).reshape(-1)[0])
+
+    def store(self, current_time, update_time, sample_time):
+        horizon_time = self.horizon_time()
+        if horizon_time < sample_time:
+            return
+        for vehicle in self.vehicles:
+            n_samp = int(round(horizon_time / sample_time, 6)) + 1
+            time_axis = np.linspace(0., (n_samp - 1) * sample_time, n_samp)
+            spline_segments = [self.father.get_variables(
+                vehicle, 'splines_seg' + str(k)) for k in range(vehicle.n_seg)]
+            vehicle.store(current_time, sample_time, spline_segments,
+                          horizon_time, time_axis)
+
+    def simulate(self, current_time, simulation_time, sample_time):
+        horizon_time = self.horizon_time()
+        if horizon_time < sample_time:
+            return
+        simulation_time = min(simulation_time, horizon_time)
+        self.compute_partial_objective(current_time + simulation_time - self.start_time)
+        Problem.simulate(self, current_time, simulation_time, sample_time)
+
+    def stop_criterium(self, current_time, update_time):
+        if self.horizon_time() < update_time:
+            return True
+        return Point2pointProblem.stop_criterium(self, current_time, update_time)
+
+    def init_step(self, current_time, update_time):
+        if (current_time - self.start_time) > 0:
+            T = self.horizon_time()
+            if T < 2 * update_time:      # almost arrived: shorten the update
+                update_time = T - update_time
+                target_time = T
+            else:
+                target_time = T - update_time
+            # the piece from update_time on, re-expressed on an equidistant basis
+            self.father.transform_primal_splines(
+                lambda coeffs, basis, *_: shift_spline(
+                    coeffs, update_time / target_time, basis))
+            self.father.set_variables(target_time, self, 'T')
+
+    def compute_partial_objective(self, current_time):
+        self.objective = current_time
+
+    def compute_objective(self):
+        return self.objective

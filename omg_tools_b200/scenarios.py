@@ -7,10 +7,10 @@ from . import (Holonomic, Environment, Obstacle, Point2point, Square, Circle,
                Beam, Rectangle)
 
 
-def _p2p(vehicle, environment, options, build_solver):
+def _p2p(vehicle, environment, options, build_solver, freeT=False):
     opts = {'verbose': 0}
     opts.update(options or {})
-    problem = Point2point(vehicle, environment, options=opts, freeT=False)
+    problem = Point2point(vehicle, environment, options=opts, freeT=freeT)
     if build_solver:
         problem.init()
     else:
@@ -139,6 +139,26 @@ def config4(n_obstacles=2, options=None, build_solver=True):
     opts = {'horizon_time': 5.}
     opts.update(options or {})
     return _p2p(vehicle, environment, opts, build_solver)
+
+
+def config_freeT(options=None, build_solver=True, moving=False):
+    """Minimum-time variant of examples/p2p_holonomic.py (freeT=True, the
+    example's commented alternative): two rectangular walls and a circle
+    (moving as in the example if ``moving``), T is a decision variable
+    (n=126, m=622, rows of degree 3)."""
+    vehicle = Holonomic()
+    vehicle.set_initial_conditions([-1.5, -1.5])
+    vehicle.set_terminal_conditions([2., 2.])
+    environment = Environment(room={'shape': Square(5.)})
+    rectangle = Rectangle(width=3., height=0.2)
+    environment.add_obstacle(Obstacle({'position': [-2.1, -0.5]}, shape=rectangle))
+    environment.add_obstacle(Obstacle({'position': [1.7, -0.5]}, shape=rectangle))
+    trajectories = {'velocity': {'time': [3., 4.],
+                                 'values': [[-0.15, 0.0], [0., 0.15]]}}
+    environment.add_obstacle(Obstacle(
+        {'position': [1.5, 0.5]}, shape=Circle(0.4),
+        simulation={'trajectories': trajectories} if moving else None))
+    return _p2p(vehicle, environment, options, build_solver, freeT=True)
 
 
 def instance_data(problem, batch, jitter=0.0, seed=0, current_time=0.):

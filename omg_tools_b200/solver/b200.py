@@ -71,7 +71,7 @@ class _Options(C.Structure):
                 ('bound_relax_factor', C.c_double),
                 ('scaling_max_gradient', C.c_double),
                 ('max_iter', C.c_int32), ('trace', C.c_int32),
-                ('max_restarts', C.c_int32), ('reserved', C.c_int32),
+                ('max_restarts', C.c_int32), ('soft_resto', C.c_int32),
                 ('restart_mu', C.c_double), ('restart_push', C.c_double)]
 
 

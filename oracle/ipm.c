@@ -43,6 +43,7 @@
 #define INF_BOUND 1e19
 #define MAX_LS 40
 #define MAXF 32
+#define SOFT_RESTO_FACTOR 0.9999
 
 static double eval_slot(const omg_termlist* L, int s, const double* V, const double* xe) {
   double acc = 0.0;
@@ -137,7 +138,7 @@ typedef struct {
   double *V, *xe, *xt, *g, *s, *y, *zL, *zU, *dsc, *sL, *sU, *beq, *sig, *wv, *ds, *dy,
          *dzL, *dzU, *gt, *st, *jval, *gf, *K, *rhs, *rx, *d0, *sol;
   int *rt, *eqidx, *eqrow;
-  double *jx, *mu;
+  double *jx, *mu, *sol2;
 } Work;
 
 static void* xalloc(size_t n) { return calloc(n ? n : 1, 1); }
@@ -147,6 +148,7 @@ static void work_alloc(Work* w, const omg_tables* T, int Nmax) {
   w->V = xalloc(sizeof(double) * T->n_v);
   w->xe = xalloc(sizeof(double) * (n + 1 + T->n_mid)); w->xt = xalloc(sizeof(double) * (n + 1 + T->n_mid));
   w->jx = xalloc(sizeof(double) * (T->n_mid ? T->nnz_jx : 1)); w->mu = xalloc(sizeof(double) * (T->n_mid + 1));
+  w->sol2 = xalloc(sizeof(double) * (n + 1));
   double** mv[] = {&w->g, &w->s, &w->y, &w->zL, &w->zU, &w->dsc, &w->sL, &w->sU, &w->beq,
                    &w->sig, &w->wv, &w->ds, &w->dy, &w->dzL, &w->dzU, &w->gt, &w->st};
   for (unsigned k = 0; k < sizeof(mv) / sizeof(mv[0]); ++k) *mv[k] = xalloc(sizeof(double) * m);
@@ -161,7 +163,7 @@ static void work_alloc(Work* w, const omg_tables* T, int Nmax) {
 static void work_free(Work* w) {
   void* all[] = {w->V, w->xe, w->xt, w->g, w->s, w->y, w->zL, w->zU, w->dsc, w->sL, w->sU, w->beq,
                  w->sig, w->wv, w->ds, w->dy, w->dzL, w->dzU, w->gt, w->st, w->jval, w->gf, w->rx,
-                 w->K, w->rhs, w->d0, w->sol, w->rt, w->eqidx, w->eqrow, w->jx, w->mu};
+                 w->K, w->rhs, w->d0, w->sol, w->rt, w->eqidx, w->eqrow, w->jx, w->mu, w->sol2};
   for (unsigned k = 0; k < sizeof(all) / sizeof(all[0]); ++k) free(all[k]);
 }
 
@@ -387,6 +389,49 @@ static void solve_one(const omg_tables* T, const omg_options* O, Work* w, const 
       if (okk) { accepted = 1; break; }
       alpha *= 0.5;
     }
+    if (!accepted && O->soft_resto) {
+      /* soft restoration (ipm_ref.py): accept a step along the same direction that
+       * reduces the primal-dual error of the barrier problem */
+      double pd0 = 0.0;
+      for (int j = 0; j < n; ++j) pd0 += fabs(w->rx[j]);
+      for (int i = 0; i < m; ++i) {
+        const int r = rt[i];
+        if (r & 4) { pd0 += fabs(g[i] - beq[i]); continue; }
+        pd0 += fabs(-y[i] - zL[i] + zU[i]) + fabs(g[i] - s[i]);
+        if (r & 1) pd0 += fabs((s[i] - sL[i]) * zL[i] - mu);
+        if (r & 2) pd0 += fabs((sU[i] - s[i]) * zU[i] - mu);
+      }
+      alpha = a_p;
+      for (int n_try = 0; n_try < 12; ++n_try) {
+        for (int j = 0; j < n; ++j) xt[j] = xe[j] + alpha * dx[j];
+        eval_mids(T, V, xt); eval_jx(T, V, xt, jx);
+        const double az = fmin(alpha, a_d);
+        double pdt = 0.0;
+        for (int j = 0; j < n; ++j) w->sol2[j] = fsc * eval_slot(&T->DF, j, V, xt);
+        for (int i = 0; i < m; ++i) {
+          const int r = rt[i];
+          const double gi = dsc[i] * eval_slot(&T->G, i, V, xt);
+          gt[i] = gi;
+          const double yt = y[i] + alpha * dy[i];
+          for (int sl = T->jrow_ptr[i]; sl < T->jrow_ptr[i + 1]; ++sl)
+            w->sol2[T->jcol[sl]] += dsc[i] * jac_slot(T, sl, V, xt, jx) * yt;
+          if (r & 4) { pdt += fabs(gi - beq[i]); continue; }
+          const double si = s[i] + alpha * ds[i];
+          st[i] = si;
+          const double zl = zL[i] + az * dzL[i], zu = zU[i] + az * dzU[i];
+          pdt += fabs(-yt - zl + zu) + fabs(gi - si);
+          if (r & 1) pdt += fabs((si - sL[i]) * zl - mu);
+          if (r & 2) pdt += fabs((sU[i] - si) * zu - mu);
+        }
+        for (int j = 0; j < n; ++j) pdt += fabs(w->sol2[j]);
+        if (isfinite(pdt) && pdt <= SOFT_RESTO_FACTOR * pd0) {
+          accepted = 1; ftype = 1; nfilt = 0;
+          ft = fsc * eval_slot(&T->F, 0, V, xt);
+          break;
+        }
+        alpha *= 0.5;
+      }
+    }
     if (!accepted) {
       if (n_restarts < O->max_restarts) {   /* feasibility restart (see ipm_ref.py) */
         ++n_restarts;
@@ -481,5 +526,5 @@ void oracle_default_options(omg_options* o) {
   o->tol = 1e-3; o->constr_viol_tol = 1e-4; o->dual_inf_tol = 1.0; o->compl_inf_tol = 1e-4;
   o->mu_init = 0.1; o->bound_push = 1e-3; o->bound_frac = 1e-3; o->mult_bound_push = 1e-3;
   o->bound_relax_factor = 1e-8; o->scaling_max_gradient = 100.0; o->max_iter = 3000; o->trace = 0;
-  o->max_restarts = 5; o->reserved = 0; o->restart_mu = 1.0; o->restart_push = 0.1;
+  o->max_restarts = 5; o->soft_resto = 1; o->restart_mu = 1.0; o->restart_push = 0.1;
 }

@@ -45,7 +45,7 @@ DEFAULTS = dict(
     theta_min_fact=1e-4, delta_w0=1e-4, delta_w_min=1e-20, delta_w_max=1e40,
     kappa_w_plus_first=100.0, kappa_w_plus=8.0, kappa_w_minus=1.0 / 3.0,
     delta_c_val=1e-8, delta_c_exp=0.25, piv_tol=1e-12, inf_bound=1e19,
-    soft_resto_factor=0.9999, soft_resto=0, max_filter=32, max_ls=40,
+    soft_resto_factor=0.9999, soft_resto=1, max_filter=32, max_ls=40,
     max_restarts=5, restart_mu=1.0, restart_push=1e-1)
 
 EPS = np.finfo(float).eps

@@ -424,3 +424,37 @@ def test_matches_vehicle_goldens(name):
     assert np.abs(res['iters'] - GV[name + '_tight_iters']).max() <= 2
     assert np.abs(res['x'] - GV[name + '_tight_x']).max() < NORTH_STAR_TOL
     assert np.abs(res['f'] - GV[name + '_tight_f']).max() < 1e-6
+
+
+@pytest.mark.gpu
+def test_freeT_point2point_matches_oracle():
+    """FreeTPoint2point: cold solves of jittered instances and a receding-
+    horizon run (warm starts need the soft restoration path) vs the oracle."""
+    pr = sc.config_freeT()
+    tb = pr.father.tables
+    X0, P = sc.instance_data(pr, 8, jitter=0.1, seed=2)
+    res = pr.problem.solve_batch(X0, P)
+    ref = ipm_c.solve_batch_full(tb, X0, P, threads=8)
+    assert np.array_equal(res['status'], ref['status'])
+    ok = ref['status'] == 0
+    assert ok.sum() >= 6
+    assert np.abs(res['iters'] - ref['iters'])[ok].max() <= 2
+    iT = pr.father._var_struct.entries[(pr.label, 'T')][0]
+    assert np.abs(res['x'][ok, iT] - ref['x'][ok, iT]).max() < 1e-5      # motion time
+    assert np.median(np.abs(res['x'] - ref['x'])[ok].max(axis=1)) < NORTH_STAR_TOL
+    pr.initialize(0.)
+    t, dt = 0., 0.5
+    for k in range(8):
+        pr.predict(t, dt, 0.01)
+        pr.init_step(t, dt)
+        x0 = pr.father.get_variables().cat.copy()
+        p = pr.father.set_parameters(t).cat.copy()
+        r = oracle_solve(tb, x0, p)
+        pr.solve(t, dt)
+        assert pr.problem.stats()['return_status'] == ipm_ref.STATUS[r.status] == 'Solve_Succeeded'
+        assert abs(pr.horizon_time() - r.x[iT]) < 1e-4
+        # (iteration counts may differ by a few: the bilinear T terms make the
+        # path sensitive to rounding once the soft restoration is active)
+        pr.store(t, dt, 0.01)
+        pr.simulate(t, dt, 0.01)
+        t += dt

@@ -254,3 +254,35 @@ def test_quadrotor3d_config4_tables_and_receding_horizon():
         pr.simulate(t, dt, 0.01)
         t += dt
     assert np.abs(pr.vehicles[0].signals['state'][:3, -1] - [3., 2., 0.5]).max() < 1e-2
+
+
+def test_freeT_point2point_receding_horizon():
+    """FreeTPoint2point (reference point2point.py:269-374): T is a decision
+    variable and the objective, rows are cubic.  The reference's loop
+    (init_step re-expresses the remaining spline piece on a fresh basis and
+    shortens T) drives the vehicle to the goal; every solve converges and the
+    motion time decreases by the update time."""
+    from oracle import ipm_c
+    if not ipm_c.available():
+        pytest.skip('C oracle not built')
+    pr = sc.config_freeT(build_solver=False)
+    tb = pr.father.tables
+    assert (tb.n, tb.m, tb.degree) == (126, 622, 3)
+    pr.problem = _OracleSolver(tb)
+    pr.initialize(0.)
+    t, dt = 0., 0.5
+    Ts = []
+    for k in range(20):
+        pr.predict(t, dt, 0.01)
+        pr.init_step(t, dt)
+        pr.solve(t, dt)
+        assert pr.problem.stats()['return_status'] == 'Solve_Succeeded', k
+        Ts.append(pr.horizon_time())
+        pr.store(t, dt, 0.01)
+        pr.simulate(t, dt, 0.01)
+        t += dt
+        if pr.stop_criterium(t, dt):
+            break
+    assert 9. < Ts[0] < 10.                      # ~7 s of travel at 0.5 m/s + acceleration
+    assert np.abs(np.diff(Ts) + dt).max() < 0.15  # the plan is executed as predicted
+    assert np.abs(pr.vehicles[0].signals['state'][:, -1] - [2., 2.]).max() < 1e-2
