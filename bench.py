@@ -35,6 +35,8 @@ def parse():
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--jitter', type=float, default=0.0)
     ap.add_argument('--cpu-sample', type=int, default=0)
+    ap.add_argument('--workload', default='config2', choices=sorted(WORKLOADS),
+                    help='BASELINE configuration (the metric is quoted on config2)')
     return ap.parse_args()
 
 
@@ -118,15 +120,30 @@ def cpu_baseline(problem, X0, P, sample, threads):
     return cpu_runner.run(problem.father.tables, X0[:sample], P[:sample], threads)
 
 
+WORKLOADS = {
+    'config1': 'config1: Holonomic Point2point (examples/p2p_holonomic.py), 10 knot intervals, '
+               '1 moving circular obstacle',
+    'config2': 'config2: Holonomic Point2point, 10 knot intervals, 3 circular obstacles',
+    'config4': 'config4: Quadrotor3D Point2point (examples/p2p_3dquadrotor.py), 10 knot '
+               'intervals, 2 plate obstacles',
+    'config5': 'config5: Holonomic Point2point through the revolving door '
+               '(examples/revolving_door.py), 2 static + 2 rotating beams',
+}
+
+# DRAM traffic of the solver kernel per solve, from the ncu --set full capture of config 2
+# (profiles/r01_v3_ncu_raw.txt: dram__bytes_read.sum + dram__bytes_write.sum of a 148-solve launch)
+NCU_DRAM_BYTES_PER_SOLVE = {'config2': (1.112832e6 + 1.377536e6) / 148.}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU path (oracle; CasADi+IPOPT is not
     installable in this image) on the host cores, same config and metric."""
     if rank != 0:
         return
     from omg_tools_b200 import scenarios as sc
-    problem = sc.config2(build_solver=False)
+    problem = getattr(sc, args.workload)(build_solver=False)
     cores = os.cpu_count() or 1
-    sample = args.cpu_sample or max(cores, 16)
+    sample = args.cpu_sample or 8 * max(cores, 2)
     X0, P = sc.instance_data(problem, 1, jitter=0.0)
     X0, P = np.repeat(X0, sample, 0), np.repeat(P, sample, 0)
     times = []
@@ -145,12 +162,11 @@ def run_reference(args, rank, world):
         'warmup': args.warmup, 'ms_per_step': 1e3 * tot / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': 'config2: Holonomic Point2point, 10 knot '
-                   'intervals, 3 circular obstacles, cold solve, identical '
+        'config': {'workload': WORKLOADS[args.workload] + ', cold solve, identical '
                    'instances', 'sample_per_step': sample},
         'cpu_baseline': {'value': value, 'unit': 'solves/s', 'cores': cores,
                          'kind': info['kind'],
-                         'sample': '%d identical config-2 instances per step' % sample},
+                         'sample': '%d identical %s instances per step' % (sample, args.workload)},
         'e2e': {'value': value, 'unit': 'solves/s', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
         'gpu_launches': 0}
@@ -180,7 +196,7 @@ def main():
         dist.barrier()
     from omg_tools_b200 import scenarios as sc
     os.environ['OMG_B200_DEVICE'] = str(local)
-    problem = sc.config2()
+    problem = getattr(sc, args.workload)()
     slv, tb = problem.problem, problem.father.tables
     B = args.batch                      # per GPU (weak scaling)
     if args.jitter > 0:
@@ -263,10 +279,10 @@ def main():
             'ms_per_step': tot_ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic',
-            'config': {'workload': 'config2: batch=%d/GPU Holonomic Point2point, '
-                       '10 knot intervals, 3 circular obstacles, cold solve from '
-                       'the linear initial guess, %s instances' %
-                       (B, 'jittered' if args.jitter > 0 else 'identical'),
+            'config': {'workload': '%s, batch=%d/GPU, cold solve from the linear initial '
+                       'guess, %s instances' %
+                       (WORKLOADS[args.workload], B,
+                        'jittered' if args.jitter > 0 else 'identical'),
                        'n': tb.n, 'm': tb.m, 'n_par': tb.n_par,
                        'global_batch': world * B, 'tol': 1e-3,
                        'mean_ip_iterations': K,
@@ -274,7 +290,11 @@ def main():
                        'l2': 'flushed between timed iterations (256 MiB fill)',
                        'parallelism': 'dp%d (batch sharded, no collective)' % world},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak,
-                         'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                         'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': (NCU_DRAM_BYTES_PER_SOLVE[args.workload] * B
+                                     if args.workload in NCU_DRAM_BYTES_PER_SOLVE else None),
+                         'traffic_source': 'ncu dram bytes per solve (profiles/r01_v3_ncu_raw.txt, '
+                                           '148-solve launch) x batch',
                          'peak_source': how,
                          'model': 'staged-KKT bytes/solve = K*2*8*n(n+1)/2 + '
                                   '8(2n+n_par+3m) (SURVEY 8d); K=mean iterations',
@@ -289,7 +309,7 @@ def main():
             'clocks': sampler.summary()}
         cores = os.cpu_count() or 1
         if world == 1:
-            sample = args.cpu_sample or max(cores, 16)
+            sample = min(args.cpu_sample or 8 * max(cores, 2), len(X0h))
             t0 = time.perf_counter()
             cinfo = cpu_baseline(problem, X0h, Ph, sample, cores)
             dt = time.perf_counter() - t0

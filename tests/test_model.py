@@ -286,3 +286,34 @@ def test_freeT_point2point_receding_horizon():
     assert 9. < Ts[0] < 10.                      # ~7 s of travel at 0.5 m/s + acceleration
     assert np.abs(np.diff(Ts) + dt).max() < 0.15  # the plan is executed as predicted
     assert np.abs(pr.vehicles[0].signals['state'][:, -1] - [2., 2.]).max() < 1e-2
+
+
+def test_intermediates_small_example_and_guards():
+    """lowering.py with 'mid' symbols on a hand-checkable NLP:
+    c = x0*x1 (shared), rows  p*c + x2 <= 1  and  2*c - x0 = 0."""
+    from omg_tools_b200.basics.lowering import lower
+    x = [pl.new_symbol('mx%d' % k, 'var') for k in range(3)]
+    p = pl.new_symbol('mp', 'par')
+    c = pl.new_mid('mc', x[0] * x[1])
+    sid = lambda e: e.single_symbol()
+    rows = [p * c + x[2], 2. * c - x[0]]
+    tb = lower([sid(v) for v in x], [sid(p)], rows, x[2] * x[2], [-np.inf, 0.], [1., 0.])
+    assert (tb.n, tb.m, tb.n_mid) == (3, 2, 1)
+    ev = TableEval(tb)
+    xv, pv, lam = np.array([0.5, -2., 3.]), np.array([4.]), np.array([0.7, -1.3])
+    V = ev.tape(pv)
+    assert np.allclose(ev.g(xv, V), [4. * (0.5 * -2.) + 3., 2. * (0.5 * -2.) - 0.5])
+    J = ev.jac_dense(xv, V)
+    assert np.allclose(J, [[4. * -2., 4. * 0.5, 1.], [2. * -2. - 1., 2. * 0.5, 0.]])
+    W = ev.hess_dense(xv, V, lam)
+    # Hessian of lam0*p*x0*x1 + lam1*2*x0*x1 + x2^2
+    ref = np.zeros((3, 3))
+    ref[0, 1] = ref[1, 0] = 0.7 * 4. + (-1.3) * 2.
+    ref[2, 2] = 2.
+    assert np.allclose(W, ref)
+    # guards: rows must be affine in intermediates, intermediates must not nest
+    with pytest.raises(NotImplementedError):
+        lower([sid(v) for v in x], [sid(p)], [c * x[2]], x[2], [0.], [0.])
+    c2 = pl.new_mid('mc2', c * x[2])
+    with pytest.raises(NotImplementedError):
+        lower([sid(v) for v in x], [sid(p)], [c2 + x[0]], x[2], [0.], [0.])
