@@ -113,6 +113,21 @@ def measured_peaks():
     return 6650.0, 'fallback'
 
 
+def host_cores():
+    """Usable host threads: affinity mask, capped by the cgroup CPU quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open('/sys/fs/cgroup/cpu.max').read().split()[:2]
+        if quota != 'max':
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 def cpu_baseline(problem, X0, P, sample, threads):
     """Time the CPU oracle (the host restatement of the reference's
     CasADi+IPOPT path) on `sample` instances using `threads` processes."""
@@ -142,7 +157,7 @@ def run_reference(args, rank, world):
         return
     from omg_tools_b200 import scenarios as sc
     problem = getattr(sc, args.workload)(build_solver=False)
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     sample = args.cpu_sample or 8 * max(cores, 2)
     X0, P = sc.instance_data(problem, 1, jitter=0.0)
     X0, P = np.repeat(X0, sample, 0), np.repeat(P, sample, 0)
@@ -307,7 +322,7 @@ def main():
                     'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
             'gpu_launches': args.steps,
             'clocks': sampler.summary()}
-        cores = os.cpu_count() or 1
+        cores = host_cores()
         if world == 1:
             sample = min(args.cpu_sample or 8 * max(cores, 2), len(X0h))
             t0 = time.perf_counter()
