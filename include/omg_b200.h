@@ -212,6 +212,17 @@ int omg_admm_zl_update(int32_t n_agents, int32_t nsh, int32_t n_nghb, int32_t L,
                        double* z_i, double* z_ij, double* l_i, double* l_ij,
                        double* res, void* stream);
 
+/* Table files: the on-disk form of omg_tables, the stand-in for the nlp.c / nlp.so
+ * bundle that the reference's exporter writes for its C++ runtime
+ * (omgtools/export/export_p2p.py:43-60 -> Point2Point.cpp:80-91 nlpsol("problem",
+ * "ipopt","nlp.so")).  A file is "OMGTBL\0\0", int32 abi_version, int32 record
+ * count, then named records {char name[24]; int32 dtype (0 int32, 1 float64);
+ * int32 pad; int64 count; data}.  Written by omg_tools_b200.solver.b200.save_tables;
+ * omg_tables_read returns a heap object that owns its arrays (release it with
+ * omg_tables_free) or NULL (omg_last_error).  Host only, no GPU needed. */
+omg_tables* omg_tables_read(const char* path);
+void omg_tables_free(omg_tables* tables);
+
 const char* omg_last_error(void);
 int omg_abi_version(void);
 

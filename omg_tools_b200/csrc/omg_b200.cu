@@ -1349,6 +1349,82 @@ static const PTerm* upload_terms(omg_problem* h, const omg_termlist& L, int n_on
 extern "C" {
 
 int omg_abi_version(void) { return OMG_ABI_VERSION; }
+
+// ---- table files ---------------------------------------------------------------
+namespace {
+struct TabField { const char* name; int dtype; size_t off; int scalar; };
+#define TF_S(f)      {#f, 0, offsetof(omg_tables, f), 1}
+#define TF_I(f)      {#f, 0, offsetof(omg_tables, f), 0}
+#define TF_D(f)      {#f, 1, offsetof(omg_tables, f), 0}
+#define TF_LS(l, f)  {#l "." #f, 0, offsetof(omg_tables, l) + offsetof(omg_termlist, f), 1}
+#define TF_LI(l, f)  {#l "." #f, 0, offsetof(omg_tables, l) + offsetof(omg_termlist, f), 0}
+#define TF_LD(l, f)  {#l "." #f, 1, offsetof(omg_tables, l) + offsetof(omg_termlist, f), 0}
+#define TF_LIST(l)   TF_LS(l, n_out), TF_LS(l, n_terms), TF_LS(l, width), TF_LI(l, ptr), TF_LD(l, coef), \
+                     TF_LI(l, cidx), TF_LI(l, xi), TF_LI(l, lrow)
+const TabField kTabFields[] = {
+  TF_S(n), TF_S(m), TF_S(n_par), TF_S(n_v), TF_S(degree), TF_S(n_tape), TF_S(n_tape_terms), TF_S(n_levels),
+  TF_I(tape_func), TF_I(tape_ptr), TF_D(tape_coef), TF_I(tape_fac), TF_I(level_ptr),
+  TF_LIST(G), TF_LIST(F), TF_LIST(DF), TF_LIST(J), TF_LIST(W),
+  TF_S(nnz_j), TF_I(jrow), TF_I(jcol), TF_I(jrow_ptr),
+  TF_S(n_mid), TF_S(nnz_jx), TF_S(n_jp), TF_S(n_mu), TF_I(jp_ptr), TF_I(jp_a), TF_I(jp_c),
+  TF_I(mu_ptr), TF_I(mu_row), TF_I(mu_slot),
+  TF_S(nnz_w), TF_I(wrow), TF_I(wcol), TF_I(w2h),
+  TF_S(nnz_h), TF_S(n_hp), TF_I(hrow), TF_I(hcol), TF_I(hp_ptr), TF_I(hp_s1), TF_I(hp_s2), TF_I(hp_row),
+  TF_D(lbg), TF_D(ubg),
+  TF_S(kkt_n), TF_S(kkt_n_eq), TF_S(env_size), TF_S(n_panel_rows), TF_S(max_panel_rows),
+  TF_I(kkt_eq_rows), TF_I(kkt_pos_var), TF_I(kkt_pos_eq), TF_I(kkt_sign), TF_I(env_first), TF_I(env_ptr),
+  TF_I(kkt_hdst), TF_I(kkt_jdst), TF_I(kkt_diag), TF_I(kkt_panel_ptr), TF_I(kkt_panel_rows),
+};
+struct OwnedTables { omg_tables T; std::vector<void*> blocks; };
+}  // namespace
+
+omg_tables* omg_tables_read(const char* path) {
+  FILE* fp = path ? fopen(path, "rb") : nullptr;
+  if (!fp) { set_err(std::string("cannot open table file ") + (path ? path : "(null)")); return nullptr; }
+  OwnedTables* O = new OwnedTables();
+  memset(&O->T, 0, sizeof(O->T));
+  bool ok = true;
+  char magic[8]; int32_t ver = 0, nrec = 0;
+  if (fread(magic, 1, 8, fp) != 8 || memcmp(magic, "OMGTBL\0\0", 8) != 0) { set_err("not an omg table file"); ok = false; }
+  if (ok && (fread(&ver, 4, 1, fp) != 1 || fread(&nrec, 4, 1, fp) != 1)) { set_err("truncated table file"); ok = false; }
+  if (ok && ver != OMG_ABI_VERSION) { set_err("table file written for another ABI version"); ok = false; }
+  O->T.abi_version = ver;
+  const int nf = (int)(sizeof(kTabFields) / sizeof(kTabFields[0]));
+  std::vector<char> seen(nf, 0);
+  for (int r = 0; ok && r < nrec; ++r) {
+    char name[24]; int32_t dtype = 0, pad = 0; int64_t count = 0;
+    if (fread(name, 1, 24, fp) != 24 || fread(&dtype, 4, 1, fp) != 1 || fread(&pad, 4, 1, fp) != 1 ||
+        fread(&count, 8, 1, fp) != 1 || count < 0) { set_err("truncated table file"); ok = false; break; }
+    name[23] = 0;
+    int k = -1;
+    for (int q = 0; q < nf; ++q) if (strcmp(kTabFields[q].name, name) == 0) { k = q; break; }
+    const size_t esz = dtype ? 8 : 4;
+    if (k < 0 || kTabFields[k].dtype != dtype) { set_err(std::string("unknown record in table file: ") + name); ok = false; break; }
+    char* base = reinterpret_cast<char*>(&O->T) + kTabFields[k].off;
+    if (kTabFields[k].scalar) {
+      if (count != 1 || fread(base, 4, 1, fp) != 1) { set_err("bad scalar record"); ok = false; break; }
+    } else {
+      void* blk = malloc((size_t)(count > 0 ? count : 1) * esz);
+      O->blocks.push_back(blk);
+      if (!blk || (count > 0 && fread(blk, esz, (size_t)count, fp) != (size_t)count)) { set_err("truncated table file"); ok = false; break; }
+      *reinterpret_cast<void**>(base) = (count > 0 || strcmp(name + strlen(name) - 4, "lrow") != 0) ? blk : nullptr;
+    }
+    seen[k] = 1;
+  }
+  fclose(fp);
+  // lrow of the lists without multipliers is legitimately absent; everything else is required
+  for (int q = 0; ok && q < nf; ++q)
+    if (!seen[q] && !strstr(kTabFields[q].name, ".lrow")) { set_err(std::string("table file lacks ") + kTabFields[q].name); ok = false; }
+  if (!ok) { omg_tables_free(&O->T); return nullptr; }
+  return &O->T;
+}
+
+void omg_tables_free(omg_tables* tables) {
+  if (!tables) return;
+  OwnedTables* O = reinterpret_cast<OwnedTables*>(tables);   // T is the first member
+  for (void* b : O->blocks) free(b);
+  delete O;
+}
 const char* omg_last_error(void) { return g_err.c_str(); }
 
 void omg_default_options(omg_options* o) {

@@ -79,7 +79,8 @@ EXPORTS = ['omg_abi_version', 'omg_last_error', 'omg_default_options',
            'omg_problem_create', 'omg_problem_destroy', 'omg_set_options',
            'omg_solve_batch', 'omg_solve_batch_host', 'omg_shift_batch',
            'omg_get_trace', 'omg_get_info', 'omg_last_timing',
-           'omg_admm_zl_update', 'omg_sample_batch']
+           'omg_admm_zl_update', 'omg_sample_batch', 'omg_tables_read',
+           'omg_tables_free']
 
 _lib = None
 
@@ -116,6 +117,10 @@ def load_library(path=None):
     lib.omg_last_timing.argtypes = [vp, C.POINTER(C.c_float), _i32p]
     lib.omg_admm_zl_update.argtypes = [C.c_int32] * 4 + [vp] * 4 + [C.c_double] + [vp] * 8
     lib.omg_sample_batch.argtypes = [C.c_int32, C.c_int32, vp, C.c_int32] + [vp] * 7
+    lib.omg_tables_read.argtypes = [C.c_char_p]
+    lib.omg_tables_read.restype = C.POINTER(_Tables)
+    lib.omg_tables_free.argtypes = [C.POINTER(_Tables)]
+    lib.omg_tables_free.restype = None
     _lib = lib
     return lib
 
@@ -188,6 +193,76 @@ def pack_tables(tb):
     T.kkt_panel_ptr = keep.i32(tb.kkt_panel_ptr)
     T.kkt_panel_rows = keep.i32(tb.kkt_panel_rows)
     return T, keep
+
+
+_TERMLIST_FIELDS = ('G', 'F', 'DF', 'J', 'W')
+
+
+def _table_records(tb):
+    """[(name, dtype, array)] in the order of include/omg_b200.h; dtype 0 =
+    int32, 1 = float64; scalars are int32 arrays of length 1."""
+    T, keep = pack_tables(tb)
+    rec = []
+
+    def scalar(name, v):
+        rec.append((name, 0, np.array([v], dtype=np.int32)))
+
+    def arr(name, a, dtype):
+        a = np.ascontiguousarray(a, dtype=np.float64 if dtype else np.int32).reshape(-1)
+        rec.append((name, dtype, a))
+
+    for f in ('n', 'm', 'n_par', 'n_v', 'degree', 'n_tape', 'n_tape_terms', 'n_levels'):
+        scalar(f, getattr(T, f))
+    arr('tape_func', tb.tape_func, 0), arr('tape_ptr', tb.tape_ptr, 0)
+    arr('tape_coef', tb.tape_coef, 1), arr('tape_fac', tb.tape_fac, 0)
+    arr('level_ptr', tb.level_ptr, 0)
+    for l in _TERMLIST_FIELDS:
+        t = getattr(tb, l)
+        scalar(l + '.n_out', t.n_out), scalar(l + '.n_terms', t.n_terms)
+        scalar(l + '.width', t.width)
+        arr(l + '.ptr', t.ptr, 0), arr(l + '.coef', t.coef, 1), arr(l + '.cidx', t.cidx, 0)
+        arr(l + '.xi', t.xi, 0)
+        if l == 'W':
+            arr(l + '.lrow', t.lrow, 0)
+    scalar('nnz_j', tb.nnz_j)
+    arr('jrow', tb.jrow, 0), arr('jcol', tb.jcol, 0), arr('jrow_ptr', tb.jrow_ptr, 0)
+    n_mid = getattr(tb, 'n_mid', 0)
+    scalar('n_mid', n_mid), scalar('nnz_jx', getattr(tb, 'nnz_jx', tb.nnz_j))
+    scalar('n_jp', len(tb.jp_a) if n_mid else 0), scalar('n_mu', len(tb.mu_row) if n_mid else 0)
+    empty = np.zeros(0, dtype=np.int32)
+    for f in ('jp_ptr', 'jp_a', 'jp_c', 'mu_ptr', 'mu_row', 'mu_slot'):
+        arr(f, getattr(tb, f) if n_mid else empty, 0)
+    scalar('nnz_w', tb.nnz_w)
+    arr('wrow', tb.wrow, 0), arr('wcol', tb.wcol, 0), arr('w2h', tb.w2h, 0)
+    scalar('nnz_h', tb.nnz_h), scalar('n_hp', len(tb.hp_s1))
+    for f in ('hrow', 'hcol', 'hp_ptr', 'hp_s1', 'hp_s2', 'hp_row'):
+        arr(f, getattr(tb, f), 0)
+    arr('lbg', tb.lbg, 1), arr('ubg', tb.ubg, 1)
+    scalar('kkt_n', tb.kkt_n), scalar('kkt_n_eq', tb.kkt_n_eq), scalar('env_size', tb.env_size)
+    scalar('n_panel_rows', len(tb.kkt_panel_rows)), scalar('max_panel_rows', tb.kkt_max_panel_rows)
+    for f in ('kkt_eq_rows', 'kkt_pos_var', 'kkt_pos_eq', 'kkt_sign', 'env_first', 'env_ptr',
+              'kkt_hdst', 'kkt_jdst', 'kkt_diag', 'kkt_panel_ptr', 'kkt_panel_rows'):
+        arr(f, getattr(tb, f), 0)
+    del keep
+    return rec
+
+
+def save_tables(tb, path):
+    """Write the lowered NLP to a table file (include/omg_b200.h:
+    omg_tables_read) -- the deployable artefact for native callers, in place
+    of the nlp.c/.so bundle of the reference's exporter."""
+    import struct
+    rec = _table_records(tb)
+    with open(path, 'wb') as fp:
+        fp.write(b'OMGTBL\0\0')
+        fp.write(struct.pack('<ii', ABI_VERSION, len(rec)))
+        for name, dtype, a in rec:
+            nb = name.encode()
+            if len(nb) > 23:
+                raise ValueError('record name too long: %s' % name)
+            fp.write(nb.ljust(24, b'\0'))
+            fp.write(struct.pack('<iiq', dtype, 0, a.size))
+            fp.write(a.tobytes())
 
 
 class B200Solver(object):

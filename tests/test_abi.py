@@ -54,3 +54,42 @@ def test_no_cpu_fallback_without_device(lib):
         B200Solver(pr.father.tables)
     with pytest.raises(RuntimeError):
         sc.config1(build_solver=True)
+
+
+def test_table_file_round_trip(tmp_path):
+    """save_tables -> omg_tables_read (host only): the deployable artefact for
+    native callers reproduces every array of the lowered NLP, including the
+    intermediates of config 4."""
+    import ctypes as C
+    import numpy as np
+    from omg_tools_b200 import scenarios as sc
+    from omg_tools_b200.solver import b200
+    lib = b200.load_library()
+    for builder in (sc.config1, sc.config4):
+        tb = builder(build_solver=False).father.tables
+        path = str(tmp_path / 'problem.omgtbl')
+        b200.save_tables(tb, path)
+        T = lib.omg_tables_read(path.encode())
+        assert bool(T), lib.omg_last_error()
+        t = T.contents
+        assert (t.abi_version, t.n, t.m, t.n_par) == (b200.ABI_VERSION, tb.n, tb.m, tb.n_par)
+        assert (t.n_mid, t.nnz_j, t.kkt_n, t.env_size) == (
+            getattr(tb, 'n_mid', 0), tb.nnz_j, tb.kkt_n, tb.env_size)
+        arr = lambda ptr, cnt: np.ctypeslib.as_array(ptr, (cnt,))
+        for name in ('G', 'J', 'W'):
+            src, dst = getattr(tb, name), getattr(t, name)
+            assert np.array_equal(arr(dst.coef, dst.n_terms), src.coef)
+            assert np.array_equal(arr(dst.xi, dst.n_terms * dst.width), src.xi.reshape(-1))
+            assert np.array_equal(arr(dst.ptr, dst.n_out + 1), src.ptr)
+        assert np.array_equal(arr(t.W.lrow, t.W.n_terms), tb.W.lrow)
+        assert np.array_equal(arr(t.lbg, t.m), tb.lbg)
+        assert np.array_equal(arr(t.kkt_hdst, t.nnz_h), tb.kkt_hdst)
+        if t.n_mid:
+            assert np.array_equal(arr(t.jp_a, t.n_jp), tb.jp_a)
+            assert np.array_equal(arr(t.mu_slot, t.n_mu), tb.mu_slot)
+        lib.omg_tables_free(T)
+    # a damaged file is refused with a message
+    with open(path, 'r+b') as fp:
+        fp.write(b'XXXX')
+    assert not bool(lib.omg_tables_read(path.encode()))
+    assert b'table file' in lib.omg_last_error()

@@ -458,3 +458,35 @@ def test_freeT_point2point_matches_oracle():
         pr.store(t, dt, 0.01)
         pr.simulate(t, dt, 0.01)
         t += dt
+
+
+@pytest.mark.gpu
+def test_native_cpp_caller(tmp_path):
+    """examples/native/native_solve.cpp: a C++ program that links only
+    libomgb200.so, loads a table file and solves -- the twin of the reference's
+    exported C++ runtime (Point2Point.cpp:80-91, 207-231).  Same result as the
+    Python binding."""
+    import subprocess
+    from omg_tools_b200.solver import b200
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pr = sc.config1()
+    tb = pr.father.tables
+    exe = str(tmp_path / 'native_solve')
+    lib_dir = os.path.join(root, 'omg_tools_b200', 'csrc')
+    subprocess.check_call(['g++', '-O2', '-I', os.path.join(root, 'include'),
+                           os.path.join(root, 'examples', 'native', 'native_solve.cpp'),
+                           '-o', exe, '-L', lib_dir, '-lomgb200', '-Wl,-rpath,' + lib_dir])
+    X0, P = sc.instance_data(pr, 3, jitter=0.2, seed=4)
+    b200.save_tables(tb, str(tmp_path / 'p.omgtbl'))
+    X0.tofile(str(tmp_path / 'x0.f64'))
+    P.tofile(str(tmp_path / 'p.f64'))
+    out = subprocess.check_output([exe, str(tmp_path / 'p.omgtbl'), str(tmp_path / 'x0.f64'),
+                                   str(tmp_path / 'p.f64'), '3', str(tmp_path / 'x.f64')])
+    res = pr.problem.solve_batch(X0, P)
+    x = np.fromfile(str(tmp_path / 'x.f64')).reshape(3, tb.n)
+    assert np.array_equal(x, res['x'])
+    lines = out.decode().strip().splitlines()
+    assert len(lines) == 3
+    for b, line in enumerate(lines):
+        tok = line.split()
+        assert int(tok[3]) == res['status'][b] and int(tok[5]) == res['iters'][b]
