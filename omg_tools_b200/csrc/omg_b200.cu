@@ -1160,6 +1160,11 @@ omg_ipm_kernel_2cta(const DevTab T, const omg_options O, const Batch A, const Sm
 __global__ void __launch_bounds__(512, 1)
 omg_ipm_kernel_xl(const DevTab T, const omg_options O, const Batch A, const Smem S) { ipm_body<true>(T, O, A, S); }
 
+// XL with K in scratch: the block needs little shared memory, and the kernel is bound by the
+// latency of its L2 streams, so two blocks per SM overlap better than one wide block
+__global__ void __launch_bounds__(256, 2)
+omg_ipm_kernel_xl_2cta(const DevTab T, const omg_options O, const Batch A, const Smem S) { ipm_body<true>(T, O, A, S); }
+
 // warm-start shift: x[b, off + c*len + i] <- sum_k T[i,k] x[b, off + c*len + k]
 __global__ void omg_shift_kernel(double* x, int B, int n, int n_blocks, const int* offs,
                                  const int* lens, const int* ncols, const int* toffs,
@@ -1619,7 +1624,8 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
     if (cudaFuncGetAttributes(&fx, (const void*)omg_ipm_kernel_xl) == cudaSuccess)
       bx = (size_t)prop.sharedMemPerBlockOptin - fx.sharedSizeBytes;
     h->xl = (n_mid > 0) || layout(true, true) > b0;
-    if (h->xl && layout(true, false) > bx) { k_in_smem = false; layout(false, false); }
+    const char* kg = getenv("OMG_B200_XL_KGLOBAL");   // tuning knob: 1 = K in scratch even if it fits
+    if (h->xl && (layout(true, false) > bx || (kg && atoi(kg) == 1))) { k_in_smem = false; layout(false, false); }
   }
   // blocks per SM: 2 x 256 threads overlap one block's serial pivots with the other's
   // parallel phases; 1 x 512 keeps every per-instance array in shared memory.
@@ -1630,10 +1636,10 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
   {
     const char* e = getenv("OMG_B200_CTAS");
     const int want = (e && atoi(e) == 1) ? 1 : 2;
-    h->target_ctas = (want == 2 && !h->xl && (size_t)off * 8 <= budget2) ? 2 : 1;
+    h->target_ctas = (want == 2 && (!h->xl || !k_in_smem) && (size_t)off * 8 <= budget2) ? 2 : 1;
     h->nt = (h->target_ctas == 1) ? 512 : 256;
   }
-  const void* kfn = h->xl ? (const void*)omg_ipm_kernel_xl
+  const void* kfn = h->xl ? ((h->target_ctas == 1) ? (const void*)omg_ipm_kernel_xl : (const void*)omg_ipm_kernel_xl_2cta)
                           : (h->target_ctas == 1) ? (const void*)omg_ipm_kernel : (const void*)omg_ipm_kernel_2cta;
   const size_t budget = (h->target_ctas == 1) ? budget1 : budget2;
   if (ok && (size_t)off * 8 > budget) {
@@ -1736,7 +1742,8 @@ int omg_solve_batch(omg_problem* h, int32_t B, const double* x0, const double* p
   A.counter = h->counter; A.trace = h->trace;
   CK(cudaMemsetAsync(h->counter, 0, sizeof(int), stream));
   CK(cudaEventRecord(h->ev0, stream));
-  if (h->xl) omg_ipm_kernel_xl<<<grid, 512, h->smem_bytes, stream>>>(h->T, h->opt, A, h->S);
+  if (h->xl && h->target_ctas == 1) omg_ipm_kernel_xl<<<grid, 512, h->smem_bytes, stream>>>(h->T, h->opt, A, h->S);
+  else if (h->xl) omg_ipm_kernel_xl_2cta<<<grid, 256, h->smem_bytes, stream>>>(h->T, h->opt, A, h->S);
   else if (h->target_ctas == 1) omg_ipm_kernel<<<grid, 512, h->smem_bytes, stream>>>(h->T, h->opt, A, h->S);
   else omg_ipm_kernel_2cta<<<grid, 256, h->smem_bytes, stream>>>(h->T, h->opt, A, h->S);
   CK(cudaGetLastError());
