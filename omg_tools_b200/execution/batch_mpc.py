@@ -1,5 +1,6 @@
 """Batched receding-horizon driver: B independent copies of one Point2point
-scenario advance in lock step, every MPC step is ONE batched solve on the GPU.
+scenario (Holonomic, Holonomic3D or Quadrotor3D vehicle) advance in lock step,
+every MPC step is ONE batched solve on the GPU.
 
 It is the batched counterpart of the reference's ``Simulator.run()`` /
 ``Deployer.update()`` loop (omgtools/execution/simulator.py:39-99,
@@ -17,6 +18,145 @@ The decision variables stay resident on the device between steps (warm start);
 only the parameter rows (n_par doubles per instance) travel each step.
 """
 import numpy as np
+
+
+class _HolonomicAdapter(object):
+    """Holonomic / Holonomic3D: state = position spline value, input = its
+    derivative / T (holonomic.py:87-105, 153-159)."""
+
+    def __init__(self, mpc, vehicle, batch, jitter, rng):
+        self.mpc, self.v = mpc, vehicle
+        self.nd = nd = vehicle.n_dim
+        rep = lambda a: np.repeat(np.asarray(a, float)[None], batch, 0)
+        self.state, self.inp = rep(vehicle.prediction['state']), rep(vehicle.prediction['input'])
+        self.poseT = rep(vehicle.poseT)
+        if jitter > 0:
+            self.state[1:] += rng.uniform(-jitter, jitter, (batch - 1, nd))
+            self.poseT[1:] += rng.uniform(-jitter, jitter, (batch - 1, nd))
+
+    def cold_start(self, X0):
+        L = len(self.v.basis)
+        for k in range(self.nd):
+            X0[:, k * L:(k + 1) * L] = np.linspace(self.state[:, k], self.poseT[:, k], L).T
+
+    def pack(self, P, off):
+        v, nd = self.v.label, self.nd
+        P[:, off[(v, 'state0')]:off[(v, 'state0')] + nd] = self.state
+        P[:, off[(v, 'input0')]:off[(v, 'input0')] + nd] = self.inp
+        P[:, off[(v, 'poseT')]:off[(v, 'poseT')] + nd] = self.poseT
+
+    def predict(self, X, t_rel, dt, T, device=True):
+        from ..solver.b200 import sample_batch
+        basis, nd = self.v.basis, self.nd
+        tau = (t_rel + dt) / T
+        B0 = basis.eval_basis([tau])
+        Bd, P1 = basis.derivative(1)
+        B1 = Bd.eval_basis([tau]).dot(P1) / T
+        L = len(basis)
+        if device:
+            out = sample_batch(X, [(0, L, nd, np.vstack([B0, B1]))]).cpu().numpy()
+            # layout: [column][sample] with samples (value, derivative)
+            for k in range(nd):
+                self.state[:, k], self.inp[:, k] = out[:, 2 * k], out[:, 2 * k + 1]
+        else:
+            Xh = X.cpu().numpy()
+            for k in range(nd):
+                c = Xh[:, k * L:(k + 1) * L]
+                self.state[:, k] = c.dot(B0[0])
+                self.inp[:, k] = c.dot(B1[0])
+
+    def position(self):
+        return self.state
+
+
+class _Quadrotor3DAdapter(object):
+    """Quadrotor3D (quadrotor3d.py): the decision splines are the flat outputs
+    f~, q_phi, q_theta; position and velocity follow from the double integral of
+    the accelerations re-anchored at the previous prediction (splines2signals,
+    quadrotor3d.py:253-275).  The integral over one update is taken exactly by
+    Gauss-Legendre quadrature per knot piece on device-sampled spline values."""
+
+    NQ = 6      # exact for the degree-9 integrand (tau1 - s) * ddx(s)
+
+    def __init__(self, mpc, vehicle, batch, jitter, rng):
+        self.mpc, self.v = mpc, vehicle
+        rep = lambda a: np.repeat(np.asarray(a, float)[None], batch, 0)
+        self.state, self.inp = rep(vehicle.prediction['state']), rep(vehicle.prediction['input'])
+        self.poseT = rep(vehicle.poseT)
+        if jitter > 0:
+            self.state[1:, :3] += rng.uniform(-jitter, jitter, (batch - 1, 3))
+            self.poseT[1:, :3] += rng.uniform(-jitter, jitter, (batch - 1, 3))
+
+    def cold_start(self, X0):
+        L = len(self.v.basis)
+        q0 = np.tan(self.state[:, 6:8] / 2.)
+        qT = np.tan(self.poseT[:, 3:5] / 2.)
+        for k in range(2):
+            X0[:, (k + 1) * L:(k + 2) * L] = np.linspace(q0[:, k], qT[:, k], L).T
+
+    def pack(self, P, off):
+        v = self.v.label
+        st, inp = self.state, self.inp
+        qp, qt = np.tan(st[:, 6] / 2.), np.tan(st[:, 7] / 2.)
+        def put(name, val):
+            val = np.asarray(val, dtype=float)
+            val = val[:, None] if val.ndim == 1 else val
+            P[:, off[(v, name)]:off[(v, name)] + val.shape[1]] = val
+
+        put('q_phi0', qp), put('q_theta0', qt)
+        put('f_til0', inp[:, 0] / ((1 + qp**2) * (1 + qt**2)))
+        put('dq_phi0', 0.5 * inp[:, 1] * (1 + qp**2))
+        put('dq_theta0', 0.5 * inp[:, 2] * (1 + qt**2))
+        put('pos0', st[:, :3]), put('dpos0', st[:, 3:6])
+        put('posT', self.poseT[:, :3])
+        put('q_phiT', np.tan(self.poseT[:, 3] / 2.)), put('q_thetaT', np.tan(self.poseT[:, 4] / 2.))
+
+    def predict(self, X, t_rel, dt, T, device=True):
+        from ..solver.b200 import sample_batch
+        basis, g = self.v.basis, self.v.g
+        L = len(basis)
+        tau0, tau1 = t_rel / T, (t_rel + dt) / T
+        # quadrature nodes on [tau0, tau1], split at the knots in between
+        brk = [tau0] + [k for k in np.unique(basis.knots) if tau0 + 1e-12 < k < tau1 - 1e-12] + [tau1]
+        xg, wg = np.polynomial.legendre.leggauss(self.NQ)
+        nodes = np.concatenate([0.5 * (b - a) * xg + 0.5 * (a + b) for a, b in zip(brk[:-1], brk[1:])])
+        wts = np.concatenate([0.5 * (b - a) * wg for a, b in zip(brk[:-1], brk[1:])])
+        S0 = basis.eval_basis(np.r_[nodes, tau1])
+        Bd, P1 = basis.derivative(1)
+        S1 = Bd.eval_basis([tau1]).dot(P1)
+        ns = len(nodes) + 1
+        if device:
+            out = sample_batch(X, [(0, L, 3, np.vstack([S0, S1]))]).cpu().numpy()
+        else:
+            Xh = X.cpu().numpy()
+            out = np.concatenate([Xh[:, k * L:(k + 1) * L].dot(np.vstack([S0, S1]).T)
+                                  for k in range(3)], axis=1)
+        col = lambda k: out[:, k * (ns + 1):(k + 1) * (ns + 1)]
+        f, qp, qt = col(0)[:, :ns - 1], col(1)[:, :ns - 1], col(2)[:, :ns - 1]
+        acc = np.stack([f * (1 - qp**2) * (2 * qt), -f * (1 + qt**2) * (2 * qp),
+                        f * (1 - qp**2) * (1 - qt**2) - g], axis=2)          # [B, nodes, 3]
+        I1 = np.einsum('q,bqk->bk', wts, acc)
+        I2 = np.einsum('q,bqk->bk', wts * (tau1 - nodes), acc)
+        pos, vel = self.state[:, :3], self.state[:, 3:6]
+        new_pos = pos + T * vel * (tau1 - tau0) + T * T * I2
+        new_vel = vel + T * I1
+        f1, qp1, qt1 = col(0)[:, ns - 1], col(1)[:, ns - 1], col(2)[:, ns - 1]
+        dqp1, dqt1 = col(1)[:, ns] / T, col(2)[:, ns] / T
+        self.state = np.c_[new_pos, new_vel, 2 * np.arctan2(qp1, 1), 2 * np.arctan2(qt1, 1)]
+        self.inp = np.c_[f1 * (1 + qp1**2) * (1 + qt1**2), 2 * dqp1 / (1 + qp1**2),
+                         2 * dqt1 / (1 + qt1**2)]
+
+    def position(self):
+        return self.state[:, :3]
+
+
+def _adapter_for(vehicle):
+    name = type(vehicle).__name__
+    if name in ('Holonomic', 'Holonomic3D'):
+        return _HolonomicAdapter
+    if name == 'Quadrotor3D':
+        return _Quadrotor3DAdapter
+    raise NotImplementedError('BatchMPC has no batched prediction for %s' % name)
 
 
 class BatchMPC(object):
@@ -39,13 +179,8 @@ class BatchMPC(object):
         self.dev = dev
         rng = np.random.default_rng(seed)
         n, m = self.tb.n, self.tb.m
-        # per-instance scenario data (host)
-        self.state = np.repeat(np.asarray(self.vehicle.prediction['state'], float)[None], batch, 0)
-        self.inp = np.repeat(np.asarray(self.vehicle.prediction['input'], float)[None], batch, 0)
-        self.poseT = np.repeat(np.asarray(self.vehicle.poseT, float)[None], batch, 0)
-        if jitter > 0:
-            self.state[1:] += rng.uniform(-jitter, jitter, (batch - 1, 2))
-            self.poseT[1:] += rng.uniform(-jitter, jitter, (batch - 1, 2))
+        # per-instance scenario data (host); the vehicle-specific part lives in the adapter
+        self.veh = _adapter_for(self.vehicle)(self, self.vehicle, batch, jitter, rng)
         self.obs = []
         for o in self.obstacles:
             d = {'x': np.repeat(o.signals['position'][:, -1][None], batch, 0).astype(float),
@@ -59,11 +194,9 @@ class BatchMPC(object):
         self.P = np.repeat(self.father.set_parameters(0.).cat[None], batch, 0)
         ent = self.father._par_struct.entries
         self.off = {key: ent[key][0] for key in ent}
-        # cold start: linear interpolation per instance (holonomic.py:118-127)
+        # cold start per instance (holonomic.py:118-127, quadrotor3d.py:189-201)
         X0 = np.repeat(self.father.get_variables().cat[None], batch, 0)
-        L = len(self.vehicle.basis)
-        for k in range(2):
-            X0[:, k * L:(k + 1) * L] = np.linspace(self.state[:, k], self.poseT[:, k], L).T
+        self.veh.cold_start(X0)
         self.X = torch.tensor(X0, device=dev)
         self.Xn = torch.empty_like(self.X)
         self.LAM = torch.empty((batch, m), dtype=torch.float64, device=dev)
@@ -75,17 +208,19 @@ class BatchMPC(object):
         self.Pd = torch.empty((batch, self.tb.n_par), dtype=torch.float64, device=dev)
         self.blocks = [(off, shape[0], shape[1], T) for (_, _, off, shape, T)
                        in self.father.shifted_entries()]
-        # basis rows for the ideal prediction (value / derivative of the vehicle spline)
         self.time = 0.
         self.time_prev = 0.
         self.history = {'state': [self.state.copy()], 'iters': [], 'status': []}
 
+    # state / input / target of every instance (owned by the vehicle adapter)
+    state = property(lambda self: self.veh.state)
+    inp = property(lambda self: self.veh.inp)
+    poseT = property(lambda self: self.veh.poseT)
+
     # ------------------------------------------------------------------
     def _pack_parameters(self, t):
-        P, off, v = self.P, self.off, self.vehicle.label
-        P[:, off[(v, 'state0')]:off[(v, 'state0')] + 2] = self.state
-        P[:, off[(v, 'input0')]:off[(v, 'input0')] + 2] = self.inp
-        P[:, off[(v, 'poseT')]:off[(v, 'poseT')] + 2] = self.poseT
+        P, off = self.P, self.off
+        self.veh.pack(P, off)
         for o, d in zip(self.obstacles, self.obs):
             nd = o.n_dim
             for key in ('x', 'v', 'a'):
@@ -95,37 +230,23 @@ class BatchMPC(object):
         P[:, off[(self.problem.label, 't')]] = np.round(t, 6) % self.knot_time
         P[:, off[(self.problem.label, 'T')]] = self.T
 
-    def _predict(self, Xh, t_rel, dt):
-        """state/input of every instance at t + dt on its current spline."""
-        basis = self.vehicle.basis
-        tau = (t_rel + dt) / self.T
-        B0 = basis.eval_basis([tau])[0]
-        Bd, P1 = basis.derivative(1)
-        B1 = Bd.eval_basis([tau])[0].dot(P1)
-        L = len(basis)
-        for k in range(2):
-            c = Xh[:, k * L:(k + 1) * L]
-            self.state[:, k] = c.dot(B0)
-            self.inp[:, k] = c.dot(B1) / self.T
-        return Xh
-
-    def _predict_device(self, t_rel, dt):
-        from ..solver.b200 import sample_batch
-        basis = self.vehicle.basis
-        tau = (t_rel + dt) / self.T
-        B0 = basis.eval_basis([tau])
-        Bd, P1 = basis.derivative(1)
-        B1 = Bd.eval_basis([tau]).dot(P1) / self.T
-        out = sample_batch(self.X, [(0, len(basis), 2, np.vstack([B0, B1]))]).cpu().numpy()
-        # layout: [column][sample] with samples (value, derivative)
-        self.state[:, 0], self.inp[:, 0] = out[:, 0], out[:, 1]
-        self.state[:, 1], self.inp[:, 1] = out[:, 2], out[:, 3]
-        return None
-
-    def _advance_obstacles(self, dt):
-        for d in self.obs:
-            d['x'] = d['x'] + dt * d['v'] + 0.5 * dt * dt * d['a']
-            d['v'] = d['v'] + dt * d['a']
+    def _advance_obstacles(self, dt, sample_time=0.01):
+        """Obstacle motion over one update, sample by sample as the reference's
+        simulator does it (obstacle.py:229-247): constant-acceleration steps plus the
+        increments of the obstacle's 'trajectories' at their switching times."""
+        n_samp = int(np.round(dt / sample_time, 6))
+        for o, d in zip(self.obstacles, self.obs):
+            inc = getattr(o, '_increments', [])
+            for _ in range(n_samp):
+                t0 = d.setdefault('time', 0.)
+                t1 = t0 + sample_time
+                d['x'] = d['x'] + sample_time * d['v'] + 0.5 * sample_time**2 * d['a']
+                d['v'] = d['v'] + sample_time * d['a']
+                for tm, l, val in inc:
+                    if t0 < tm <= t1 + 1e-12:
+                        key = ('x', 'v', 'a')[l]
+                        d[key] = d[key] + val
+                d['time'] = t1
             if 'theta' in d:
                 d['theta'] = d['theta'] + dt * d['omega']
 
@@ -144,15 +265,13 @@ class BatchMPC(object):
         self.X, self.Xn = self.Xn, self.X
         self.history['iters'].append(self.IT.cpu().numpy().copy())
         self.history['status'].append(self.ST.cpu().numpy().copy())
-        # ideal update: vehicle and obstacles move over update_time; the prediction
-        # (spline value / derivative at t + update_time) is sampled on the device
+        # ideal update: vehicle and obstacles move over update_time; the prediction at
+        # t + update_time comes from spline values sampled on the device
         t_rel = np.round(t, 6) % self.knot_time
-        Xh = self._predict_device(t_rel, self.update_time) if self.device_predict \
-            else self._predict(self.X.cpu().numpy(), t_rel, self.update_time)
+        self.veh.predict(self.X, t_rel, self.update_time, self.T, device=self.device_predict)
         self._advance_obstacles(self.update_time)
         self.history['state'].append(self.state.copy())
         self.time = np.round(t + self.update_time, 6)
-        return Xh
 
     def run(self, n_steps):
         for _ in range(n_steps):

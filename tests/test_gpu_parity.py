@@ -490,3 +490,36 @@ def test_native_cpp_caller(tmp_path):
     for b, line in enumerate(lines):
         tok = line.split()
         assert int(tok[3]) == res['status'][b] and int(tok[5]) == res['iters'][b]
+
+
+@pytest.mark.gpu
+def test_batched_receding_horizon_config4():
+    """BASELINE config 4 in the batched device-resident MPC loop: equals the
+    reference-style sequential loop step by step (identical instances), and a
+    jittered batch of 64 flies towards its goals."""
+    from omg_tools_b200.execution.batch_mpc import BatchMPC
+    seq = sc.config4()
+    seq.initialize(0.)
+    bat = BatchMPC(sc.config4(), batch=2, update_time=0.4)
+    t, dt = 0., 0.4
+    for k in range(5):                       # crosses the first knot at t = 0.5
+        seq.predict(t, dt, 0.01)
+        seq.init_step(t, dt)
+        seq.solve(t, dt)
+        bat.step()
+        assert seq.problem.stats()['return_status'] == 'Solve_Succeeded'
+        assert np.all(bat.history['status'][-1] == 0)
+        xs = seq.father.get_variables().cat
+        Xb = bat.X.cpu().numpy()
+        assert np.abs(Xb[:, :78] - xs[None, :78]).max() < 5e-3, k
+        seq.store(t, dt, 0.01)
+        seq.simulate(t, dt, 0.01)
+        t = np.round(t + dt, 6)
+    assert np.abs(bat.state[0] - seq.vehicles[0].signals['state'][:, -1]).max() < 5e-3
+    big = BatchMPC(sc.config4(), batch=64, update_time=0.4, jitter=0.1, seed=7)
+    start = big.veh.position().copy()
+    hist = big.run(6)
+    assert (np.array(hist['status']) == 0).mean() > 0.95
+    d0 = np.linalg.norm(start - big.poseT[:, :3], axis=1)
+    d1 = np.linalg.norm(big.veh.position() - big.poseT[:, :3], axis=1)
+    assert np.all(d1 < d0)
