@@ -1,7 +1,12 @@
 // omg_b200.cu -- batched primal-dual interior-point solve of OMG-tools' spline
-// NLP on B200 (sm_100a).  One 512-thread block per problem instance; the whole
+// NLP on B200 (sm_100a).  One thread block per problem instance (persistent
+// blocks pull instances from a counter; 2 x 256 threads or 1 x 512 per SM); the
 // per-instance state (KKT envelope, Jacobian values, iterate vectors) lives in
 // shared memory for the duration of the solve, constant tables stream from L2.
+// Kernel variants: omg_ipm_kernel / _2cta (everything in shared memory) and
+// omg_ipm_kernel_xl / _xl_2cta (problems with shared intermediates or structures
+// larger than one SM's shared memory: tape, chain-rule slots and, if needed, the
+// KKT envelope in an L2-resident per-block scratch).
 //
 // Replaces the CasADi+IPOPT call of the reference (omgtools/problems/
 // problem.py:113, optilayer.py:49-60).  Algorithm = oracle/ipm_ref.py (IPOPT
