@@ -145,9 +145,13 @@ WORKLOADS = {
                '(examples/revolving_door.py), 2 static + 2 rotating beams',
 }
 
-# DRAM traffic of the solver kernel per solve, from the ncu --set full capture of config 2
-# (profiles/r01_v3_ncu_raw.txt: dram__bytes_read.sum + dram__bytes_write.sum of a 148-solve launch)
-NCU_DRAM_BYTES_PER_SOLVE = {'config2': (1.112832e6 + 1.377536e6) / 148.}
+# DRAM traffic of the solver kernel per solve, from the ncu --set full captures
+# (dram__bytes_read.sum + dram__bytes_write.sum of a 148-solve launch):
+# profiles/r01_v4_ncu_raw.txt (config 2), profiles/r01_xl_config4_ncu_raw.txt (config 4)
+NCU_DRAM_BYTES_PER_SOLVE = {'config2': (1.152512e6 + 1.606912e6) / 148.,
+                            'config4': (3.464099e9 + 7.549988e9) / 148.}
+# bounded CPU sample: about 20 s of single-core work of the C oracle per measurement
+CPU_SAMPLE = {'config1': 2048, 'config2': 1024, 'config4': 96, 'config5': 512}
 
 
 def run_reference(args, rank, world):
@@ -158,7 +162,7 @@ def run_reference(args, rank, world):
     from omg_tools_b200 import scenarios as sc
     problem = getattr(sc, args.workload)(build_solver=False)
     cores = host_cores()
-    sample = args.cpu_sample or 8 * max(cores, 2)
+    sample = args.cpu_sample or CPU_SAMPLE[args.workload]
     X0, P = sc.instance_data(problem, 1, jitter=0.0)
     X0, P = np.repeat(X0, sample, 0), np.repeat(P, sample, 0)
     times = []
@@ -308,7 +312,7 @@ def main():
                          'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': (NCU_DRAM_BYTES_PER_SOLVE[args.workload] * B
                                      if args.workload in NCU_DRAM_BYTES_PER_SOLVE else None),
-                         'traffic_source': 'ncu dram bytes per solve (profiles/r01_v3_ncu_raw.txt, '
+                         'traffic_source': 'ncu dram bytes per solve (profiles/*_ncu_raw.txt, '
                                            '148-solve launch) x batch',
                          'peak_source': how,
                          'model': 'staged-KKT bytes/solve = K*2*8*n(n+1)/2 + '
@@ -324,7 +328,7 @@ def main():
             'clocks': sampler.summary()}
         cores = host_cores()
         if world == 1:
-            sample = min(args.cpu_sample or 8 * max(cores, 2), len(X0h))
+            sample = min(args.cpu_sample or CPU_SAMPLE[args.workload], len(X0h))
             t0 = time.perf_counter()
             cinfo = cpu_baseline(problem, X0h, Ph, sample, cores)
             dt = time.perf_counter() - t0
