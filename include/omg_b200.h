@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define OMG_ABI_VERSION 4
+#define OMG_ABI_VERSION 5
 
 /* CSR list of polynomial terms per output slot:
  *   out[s] = sum_{t in [ptr[s],ptr[s+1])} coef[t] * V[cidx[t]]
@@ -124,6 +124,13 @@ typedef struct omg_options {
   int32_t soft_resto;     /* 1: IPOPT's soft restoration -- when the filter rejects every trial step,
                            * accept the step if it reduces the primal-dual error by 1e-4 (default 1) */
   double restart_mu, restart_push;
+  /* inertia test of the factorisation K = L S L^T.  0 (default): IPOPT's -- S takes the
+   * sign of every pivot as it comes and the step is accepted when the NUMBER of negative
+   * pivots equals the number of equality rows (Sylvester); 1: the stricter positional
+   * test (variables +, equality rows -) of the first kernel versions, which over-
+   * regularises problems with non-convex constraints. */
+  int32_t inertia_mode;
+  int32_t reserved;
 } omg_options;
 
 /* per-instance status codes (mapped to IPOPT strings in solver/b200.py) */

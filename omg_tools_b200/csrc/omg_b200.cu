@@ -197,7 +197,7 @@ extern __shared__ double sm[];
 
 // shared-memory copies of the KKT structure arrays, addressed from the block's
 // dynamic shared array so the compiler emits LDS (not generic loads)
-#define KS_SGN    (sm + S.sgn)
+#define KS_SGN    (sm + S.sgn)        // pivot signs S of K = L S L^T (rewritten by every factorisation)
 #define KS_EPTR   (reinterpret_cast<const int*>(sm + S.eptr))
 #define KS_EFIRST (reinterpret_cast<const int*>(sm + S.efirst))
 #define KS_PPTR   (reinterpret_cast<const int*>(sm + S.pptr))
@@ -215,7 +215,8 @@ extern __shared__ double sm[];
 // Pivot j must satisfy sign[j]*pivot > PIV_TOL*|K_jj| (variables) or > 0
 // (equality rows); otherwise ctl->fail (eq_fail for an equality pivot).
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void factor_env(const DevTab& T, const Smem& S, double* K, Ctl* ctl, double* pc) {
+__device__ __forceinline__ void factor_env(const DevTab& T, const Smem& S, double* K, Ctl* ctl, double* pc,
+                                           const int mode) {
   const int tid = threadIdx.x;
   const int N = T.N;
   const int LDP = S.LDP;
@@ -223,7 +224,8 @@ __device__ __forceinline__ void factor_env(const DevTab& T, const Smem& S, doubl
   const double* diag0 = sm + S.diag0; double* invd = sm + S.invd;
   int* rbase = reinterpret_cast<int*>(sm + S.rbase);
   int* rrow = rbase + LDP;
-  const double* sgn = KS_SGN; const int* eptr = KS_EPTR; const int* efirst = KS_EFIRST;
+  double* sgn = KS_SGN; const int* eptr = KS_EPTR; const int* efirst = KS_EFIRST;
+  int n_neg = 0;               // negative pivots so far (thread 0)
   const int* pptr = KS_PPTR; const int* prow = KS_PROW;
   long long t0 = clock64();
 #define FT(k) do { if (pc && tid == 0) { const long long t_ = clock64(); pc[k] += (double)(t_ - t0); t0 = t_; } } while (0)
@@ -250,11 +252,15 @@ __device__ __forceinline__ void factor_env(const DevTab& T, const Smem& S, doubl
       for (int j = 0; j < NB; ++j) {
         // rows >= nb are zero-padded: give them a unit pivot so the arithmetic stays finite
         const bool live = (j < nb);
-        const double sj = live ? sgn[kb + j] : 1.0;
+        // mode 0 (IPOPT's inertia test): S takes the sign of the pivot as it comes, only the
+        // number of negative pivots is checked at the end; mode 1: S fixed (+ variables,
+        // - equality rows), a pivot of the other sign fails
+        const double sj = !live ? 1.0 : (mode ? sgn[kb + j] : (a[j][j] > 0.0 ? 1.0 : -1.0));
         const double d = live ? sj * a[j][j] : 1.0;
-        const double thr = (live && sj > 0.0) ? PIV_TOL * fmax(diag0[kb + j], 1e-300) : 0.0;
+        const double thr = (live && (mode == 0 || sj > 0.0)) ? PIV_TOL * fmax(diag0[kb + j], 1e-300) : 0.0;
         const bool fail_j = !(d > thr) || !(d < 1e300);
-        if (fail_j && !bad) { bad = true; bad_eq = (sj < 0.0); }
+        if (fail_j && !bad) { bad = true; bad_eq = (T.ksign[kb + j] < 0); }
+        if (live) { sgn[kb + j] = sj; n_neg += (sj < 0.0) ? 1 : 0; }
         const double inv = rsqrt(d);
         a[j][j] = d * inv;
         if (live) invd[kb + j] = inv;
@@ -362,6 +368,9 @@ __device__ __forceinline__ void factor_env(const DevTab& T, const Smem& S, doubl
     FT(9);
   }
 #undef FT
+  if (mode == 0 && tid == 0 && !ctl->fail && n_neg != T.n_eq) {   // Sylvester: wrong inertia
+    ctl->fail = 1; ctl->eq_fail = (n_neg < T.n_eq) ? 1 : 0;
+  }
 }
 
 // Back substitution L^T u = w on envelope storage (w = row N of L on entry).
@@ -866,7 +875,7 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
         }
         }
         TICK(6);   // W + border + rhs
-        factor_env(T, S, K, &ctl, tracing ? phase_cyc : nullptr);
+        factor_env(T, S, K, &ctl, tracing ? phase_cyc : nullptr, O.inertia_mode);
         __syncthreads();
         phase_t0 = clock64();
         if (!ctl.fail) break;
@@ -1443,6 +1452,7 @@ void omg_default_options(omg_options* o) {
   o->bound_relax_factor = 1e-8; o->scaling_max_gradient = 100.0;
   o->max_iter = 3000; o->trace = 0;
   o->max_restarts = 5; o->soft_resto = 1; o->restart_mu = 1.0; o->restart_push = 0.1;
+  o->inertia_mode = 0; o->reserved = 0;
 }
 
 omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, int device) {

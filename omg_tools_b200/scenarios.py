@@ -141,6 +141,22 @@ def config4(n_obstacles=2, options=None, build_solver=True):
     return _p2p(vehicle, environment, opts, build_solver)
 
 
+def config_quadrotor2d(options=None, build_solver=True):
+    """examples/p2p_quadrotor.py: planar Quadrotor, one tall Rectangle wall,
+    safety distance 0.1, horizon 5 s; rows of degree 3 (n=154, m=615)."""
+    from . import Quadrotor
+    vehicle = Quadrotor()
+    vehicle.set_options({'safety_distance': 0.1})
+    vehicle.set_initial_conditions([-4., -4., 0., 0., 0.])
+    vehicle.set_terminal_conditions([4., 4.])
+    environment = Environment(room={'shape': Square(10.)})
+    environment.add_obstacle(Obstacle({'position': [-0.6, -5.4]},
+                                      shape=Rectangle(width=0.2, height=12.)))
+    opts = {'horizon_time': 5}
+    opts.update(options or {})
+    return _p2p(vehicle, environment, opts, build_solver)
+
+
 def config_freeT(options=None, build_solver=True, moving=False):
     """Minimum-time variant of examples/p2p_holonomic.py (freeT=True, the
     example's commented alternative): two rectangular walls and a circle

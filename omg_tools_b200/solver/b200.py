@@ -24,7 +24,7 @@ STATUS_STRINGS = {
     2: 'Restoration_Failed', 3: 'Error_In_Step_Computation',
     4: 'Invalid_Number_Detected', 5: 'Infeasible_Problem_Detected'}
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _i32p = C.POINTER(C.c_int32)
 _f64p = C.POINTER(C.c_double)
@@ -72,7 +72,8 @@ class _Options(C.Structure):
                 ('scaling_max_gradient', C.c_double),
                 ('max_iter', C.c_int32), ('trace', C.c_int32),
                 ('max_restarts', C.c_int32), ('soft_resto', C.c_int32),
-                ('restart_mu', C.c_double), ('restart_push', C.c_double)]
+                ('restart_mu', C.c_double), ('restart_push', C.c_double),
+                ('inertia_mode', C.c_int32), ('reserved', C.c_int32)]
 
 
 EXPORTS = ['omg_abi_version', 'omg_last_error', 'omg_default_options',

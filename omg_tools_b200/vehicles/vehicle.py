@@ -246,10 +246,11 @@ class Vehicle(OptiChild):
             self.prediction['input'] = np.asarray(input0, dtype=float)
             return
         n_samp = int(np.round(predict_time / sample_time, 6))
-        self.prediction['state'] = self.trajectories['state'][:, n_samp]
-        self.prediction['input'] = self.trajectories['input'][:, n_samp]
-        if 'dinput' in self.trajectories:
-            self.prediction['dinput'] = self.trajectories['dinput'][:, n_samp]
+        for key, val in self.trajectories.items():
+            # every sampled signal is predicted (state, input, and model specific
+            # ones such as the quadrotor's dspl / ddspl)
+            if key not in ('time', 'splines'):
+                self.prediction[key] = np.atleast_2d(val)[:, n_samp]
 
     def simulate(self, simulation_time, sample_time):
         """Ideal update: follow the stored trajectory."""

@@ -102,14 +102,23 @@ static int cmp_le(double lhs, double rhs, double base) {
 
 /* K = L S L^T, S = diag(sign) in the permuted order of
  * lowering.build_kkt_structure; row-major full storage, lower part used. */
-static int signed_cholesky(double* K, int N, const int32_t* sign, double* d0, int* eq_fail) {
+/* K = L S L^T in the permuted order.  mode 0 (IPOPT's inertia test): S[j] = sign of pivot
+ * j as it comes; accepted when the number of negative pivots equals n_neg (Sylvester's law
+ * of inertia).  mode 1: S fixed to `sign` (+1 variables, -1 equality rows), a pivot of the
+ * other sign fails.  sdyn receives S.  eq_fail: too few negative pivots / failure at an
+ * equality pivot -> the caller regularises the constraint block (delta_c). */
+static int signed_cholesky(double* K, int N, const int32_t* sign, int n_neg, int mode, double* d0,
+                           double* sdyn, int* eq_fail) {
   *eq_fail = 0;
+  int neg = 0;
   for (int j = 0; j < N; ++j) d0[j] = fabs(K[j * N + j]);
   for (int j = 0; j < N; ++j) {
-    const double sgn = (double)sign[j];
-    const double piv = sgn * K[j * N + j];
-    const double thr = (sgn > 0) ? PIV_TOL * fmax(d0[j], 1e-300) : 0.0;
-    if (!(piv > thr) || !isfinite(piv)) { *eq_fail = (sgn < 0); return 0; }
+    const double a = K[j * N + j];
+    const double sgn = mode ? (double)sign[j] : (a > 0.0 ? 1.0 : -1.0);
+    const double piv = sgn * a;
+    const double thr = (mode && sgn < 0) ? 0.0 : PIV_TOL * fmax(d0[j], 1e-300);
+    if (!(piv > thr) || !isfinite(piv)) { *eq_fail = (sign[j] < 0); return 0; }
+    sdyn[j] = sgn; neg += (sgn < 0);
     const double ljj = sqrt(piv);
     K[j * N + j] = ljj;
     for (int i = j + 1; i < N; ++i) K[i * N + j] /= (sgn * ljj);
@@ -119,15 +128,16 @@ static int signed_cholesky(double* K, int N, const int32_t* sign, double* d0, in
       for (int k = j + 1; k <= i; ++k) K[i * N + k] -= lij * K[k * N + j];
     }
   }
+  if (neg != n_neg) { *eq_fail = (neg < n_neg); return 0; }
   return 1;
 }
 
-static void signed_solve(const double* L, int N, const int32_t* sign, double* w) {
+static void signed_solve(const double* L, int N, const double* sdyn, double* w) {
   for (int j = 0; j < N; ++j) {
     w[j] /= L[j * N + j];
     for (int i = j + 1; i < N; ++i) w[i] -= L[i * N + j] * w[j];
   }
-  for (int j = 0; j < N; ++j) w[j] *= (double)sign[j];
+  for (int j = 0; j < N; ++j) w[j] *= sdyn[j];
   for (int j = N - 1; j >= 0; --j) {
     w[j] /= L[j * N + j];
     for (int i = 0; i < j; ++i) w[i] -= L[j * N + i] * w[j];
@@ -138,7 +148,7 @@ typedef struct {
   double *V, *xe, *xt, *g, *s, *y, *zL, *zU, *dsc, *sL, *sU, *beq, *sig, *wv, *ds, *dy,
          *dzL, *dzU, *gt, *st, *jval, *gf, *K, *rhs, *rx, *d0, *sol;
   int *rt, *eqidx, *eqrow;
-  double *jx, *mu, *sol2;
+  double *jx, *mu, *sol2, *sdyn;
 } Work;
 
 static void* xalloc(size_t n) { return calloc(n ? n : 1, 1); }
@@ -149,6 +159,7 @@ static void work_alloc(Work* w, const omg_tables* T, int Nmax) {
   w->xe = xalloc(sizeof(double) * (n + 1 + T->n_mid)); w->xt = xalloc(sizeof(double) * (n + 1 + T->n_mid));
   w->jx = xalloc(sizeof(double) * (T->n_mid ? T->nnz_jx : 1)); w->mu = xalloc(sizeof(double) * (T->n_mid + 1));
   w->sol2 = xalloc(sizeof(double) * (n + 1));
+  w->sdyn = xalloc(sizeof(double) * Nmax);
   double** mv[] = {&w->g, &w->s, &w->y, &w->zL, &w->zU, &w->dsc, &w->sL, &w->sU, &w->beq,
                    &w->sig, &w->wv, &w->ds, &w->dy, &w->dzL, &w->dzU, &w->gt, &w->st};
   for (unsigned k = 0; k < sizeof(mv) / sizeof(mv[0]); ++k) *mv[k] = xalloc(sizeof(double) * m);
@@ -163,7 +174,7 @@ static void work_alloc(Work* w, const omg_tables* T, int Nmax) {
 static void work_free(Work* w) {
   void* all[] = {w->V, w->xe, w->xt, w->g, w->s, w->y, w->zL, w->zU, w->dsc, w->sL, w->sU, w->beq,
                  w->sig, w->wv, w->ds, w->dy, w->dzL, w->dzU, w->gt, w->st, w->jval, w->gf, w->rx,
-                 w->K, w->rhs, w->d0, w->sol, w->rt, w->eqidx, w->eqrow, w->jx, w->mu, w->sol2};
+                 w->K, w->rhs, w->d0, w->sol, w->rt, w->eqidx, w->eqrow, w->jx, w->mu, w->sol2, w->sdyn};
   for (unsigned k = 0; k < sizeof(all) / sizeof(all[0]); ++k) free(all[k]);
 }
 
@@ -326,7 +337,7 @@ static void solve_one(const omg_tables* T, const omg_options* O, Work* w, const 
       for (int j = 0; j < n; ++j) rhs[T->kkt_pos_var[j]] = -gf[j];
       for (int sl = 0; sl < T->nnz_j; ++sl) rhs[T->kkt_pos_var[T->jcol[sl]]] -= jval[sl] * wv[T->jrow[sl]];
       int eq_fail = 0;
-      ok = signed_cholesky(K, N, T->kkt_sign, w->d0, &eq_fail);
+      ok = signed_cholesky(K, N, T->kkt_sign, n_eq, O->inertia_mode, w->d0, w->sdyn, &eq_fail);
       if (ok) break;
       if (eq_fail) delta_c = DELTA_C_VAL * pow(mu, DELTA_C_EXP);
       if (first_try) { delta_w = (delta_w_last == 0.0) ? DELTA_W0 : fmax(DELTA_W_MIN, KAPPA_W_MINUS * delta_w_last); first_try = 0; }
@@ -335,7 +346,7 @@ static void solve_one(const omg_tables* T, const omg_options* O, Work* w, const 
     }
     if (!ok) { status = OMG_ERROR_IN_STEP_COMPUTATION; break; }
     if (delta_w > 0.0) delta_w_last = delta_w;
-    signed_solve(K, N, T->kkt_sign, rhs);
+    signed_solve(K, N, w->sdyn, rhs);
     double* dx = w->sol;   /* natural order: variables, then equality multipliers */
     for (int j = 0; j < n; ++j) dx[j] = rhs[T->kkt_pos_var[j]];
     for (int k = 0; k < n_eq; ++k) dx[n + k] = rhs[T->kkt_pos_eq[k]];
@@ -527,4 +538,5 @@ void oracle_default_options(omg_options* o) {
   o->mu_init = 0.1; o->bound_push = 1e-3; o->bound_frac = 1e-3; o->mult_bound_push = 1e-3;
   o->bound_relax_factor = 1e-8; o->scaling_max_gradient = 100.0; o->max_iter = 3000; o->trace = 0;
   o->max_restarts = 5; o->soft_resto = 1; o->restart_mu = 1.0; o->restart_push = 0.1;
+  o->inertia_mode = 0; o->reserved = 0;
 }

@@ -46,7 +46,7 @@ DEFAULTS = dict(
     kappa_w_plus_first=100.0, kappa_w_plus=8.0, kappa_w_minus=1.0 / 3.0,
     delta_c_val=1e-8, delta_c_exp=0.25, piv_tol=1e-12, inf_bound=1e19,
     soft_resto_factor=0.9999, soft_resto=1, max_filter=32, max_ls=40,
-    max_restarts=5, restart_mu=1.0, restart_push=1e-1)
+    max_restarts=5, restart_mu=1.0, restart_push=1e-1, inertia_mode=0)
 
 EPS = np.finfo(float).eps
 
@@ -219,11 +219,11 @@ def solve(tb, x0, p, lbg=None, ubg=None, options=None, lam_g0=None,
             K[n:, n:] = -delta_c * np.eye(n_eq)
             # symmetric permutation of lowering.build_kkt_structure: equality
             # rows interleaved, K = L S L^T with S = diag(kkt_sign)
-            ok, L, eq_fail = _signed_cholesky(K[np.ix_(kperm, kperm)], ksign,
-                                              o['piv_tol'])
+            ok, L, eq_fail, S_piv = _signed_cholesky(K[np.ix_(kperm, kperm)], ksign,
+                                                     o['piv_tol'], o['inertia_mode'])
             if ok:
                 sol = np.empty(n + n_eq)
-                sol[kperm] = _signed_solve(L, ksign, np.r_[rhs1, rhs2][kperm])
+                sol[kperm] = _signed_solve(L, S_piv, np.r_[rhs1, rhs2][kperm])
                 break
             if eq_fail:
                 delta_c = o['delta_c_val'] * mu ** o['delta_c_exp']
@@ -389,27 +389,40 @@ def _filter_add(filt, th, ph, cap):
     filt.append((th, ph))
 
 
-def _signed_cholesky(K, sign, piv_tol):
-    """K = L S L^T with S = diag(sign) (+1 variables, -1 equality rows, in the
-    permuted order); lower-triangular L.  Fails when a pivot does not have the
-    expected sign (wrong inertia -> caller adds delta_w / delta_c).
-    Returns (ok, L, failure_at_an_equality_pivot)."""
+def _signed_cholesky(K, sign, piv_tol, mode=0):
+    """K = L S L^T in the permuted order, lower-triangular L.
+
+    mode 0 (IPOPT's inertia test): S[j] is the sign of pivot j as it comes and the
+    factorisation is accepted when the NUMBER of negative pivots equals the number
+    of equality rows (Sylvester's law of inertia).  mode 1: S fixed to ``sign``
+    (+1 variables, -1 equality rows); a pivot of the other sign fails -- stricter
+    than necessary, it over-regularises problems with non-convex constraints.
+    Returns (ok, L, regularise_constraint_block, S)."""
     N = K.shape[0]
     A = np.tril(K).copy()
     d0 = np.abs(np.diag(K)).copy()
+    S = np.zeros(N)
+    n_neg = int((np.asarray(sign) < 0).sum())
     for j in range(N):
-        sgn = sign[j]
+        if mode:
+            sgn = float(sign[j])
+        else:
+            sgn = 1.0 if A[j, j] > 0 else -1.0
         piv = sgn * A[j, j]
-        thr = piv_tol * max(d0[j], 1e-300) if sgn > 0 else 0.0
+        thr = 0.0 if (mode and sgn < 0) else piv_tol * max(d0[j], 1e-300)
         if not (piv > thr) or not np.isfinite(piv):
-            return False, None, sgn < 0
+            return False, None, sign[j] < 0, None
+        S[j] = sgn
         ljj = np.sqrt(piv)
         A[j, j] = ljj
         if j + 1 < N:
             A[j + 1:, j] = A[j + 1:, j] / (sgn * ljj)
             col = A[j + 1:, j]
             A[j + 1:, j + 1:] -= sgn * np.tril(np.outer(col, col))
-    return True, A, False
+    neg = int((S < 0).sum())
+    if neg != n_neg:
+        return False, None, neg < n_neg, None
+    return True, A, False, S
 
 
 def _signed_solve(L, sign, rhs):

@@ -30,7 +30,7 @@ def test_exports_match_header(lib):
     assert set(names) == set(b200.EXPORTS)
     for name in names:
         assert hasattr(lib, name), name
-    assert lib.omg_abi_version() == 4
+    assert lib.omg_abi_version() == 5
 
 
 def test_default_options_are_the_reference_ipopt_settings(lib):

@@ -317,3 +317,48 @@ def test_intermediates_small_example_and_guards():
     c2 = pl.new_mid('mc2', c * x[2])
     with pytest.raises(NotImplementedError):
         lower([sid(v) for v in x], [sid(p)], [c2 + x[0]], x[2], [0.], [0.])
+
+
+def test_planar_quadrotor_receding_horizon():
+    """examples/p2p_quadrotor.py (vehicles/quadrotor.py): flat outputs x, y of
+    degree 4, thrust and pitch-rate limits as quadratic rows.  Sizes, table
+    derivatives, and the reference's MPC loop to the goal with the oracle."""
+    from oracle import ipm_c
+    if not ipm_c.available():
+        pytest.skip('C oracle not built')
+    pr = sc.config_quadrotor2d(build_solver=False)
+    tb = pr.father.tables
+    assert (tb.n, tb.m, tb.n_par, tb.degree) == (103, 496, 28, 2)
+    ev = TableEval(tb)
+    rng = np.random.default_rng(2)
+    X0, P = sc.instance_data(pr, 1)
+    x = X0[0] + 0.05 * rng.standard_normal(tb.n)
+    V = ev.tape(P[0])
+    J = ev.jac_dense(x, V)
+    h = 1e-6
+    for j in rng.choice(tb.n, 8, replace=False):
+        e = np.zeros(tb.n)
+        e[j] = h
+        fd = (ev.g(x + e, V) - ev.g(x - e, V)) / (2 * h)
+        assert np.abs(fd - J[:, j]).max() < 1e-6 * max(1., np.abs(J[:, j]).max())
+    pr.problem = _OracleSolver(tb)
+    pr.initialize(0.)
+    t, dt = 0., 0.25
+    n_ok = 0
+    for k in range(21):
+        pr.predict(t, dt, 0.01)
+        pr.init_step(t, dt)
+        pr.solve(t, dt)
+        n_ok += pr.problem.stats()['return_status'] == 'Solve_Succeeded'
+        pr.store(t, dt, 0.01)
+        pr.simulate(t, dt, 0.01)
+        t += dt
+    # The thrust lower bound is a non-convex quadratic: while it is active the reduced
+    # Hessian has negative curvature, the inertia correction adds delta_w ~ 1e3 and the
+    # solve crawls (one step of this run hits the iteration limit; its iterate is
+    # feasible and the loop recovers at the next step).
+    assert n_ok >= 19
+    veh = pr.vehicles[0]
+    assert np.abs(veh.signals['state'][:2, -1] - [4., 4.]).max() < 5e-2
+    u1 = veh.signals['input'][0]
+    assert u1.min() > 2. - 1e-2 and u1.max() < 15. + 1e-2      # thrust limits hold along the flight

@@ -66,16 +66,32 @@ def test_signed_cholesky_solves_permuted_saddle_system():
         list(range(7, 10)) + [n + 2] + list(range(10, n))
     sign = np.array([1.0 if v < n else -1.0 for v in order])
     Kp = K[np.ix_(order, order)]
-    ok, L, eqf = ipm_ref._signed_cholesky(Kp, sign, 1e-12)
-    assert ok and not eqf
-    assert np.abs(L @ np.diag(sign) @ L.T - Kp).max() < 1e-10
-    rhs = rng.standard_normal(n + ne)
-    u = np.empty(n + ne)
-    u[order] = ipm_ref._signed_solve(L, sign, rhs[order])
-    assert np.abs(K @ u - rhs).max() < 1e-10
+    for mode in (0, 1):
+        ok, L, eqf, S = ipm_ref._signed_cholesky(Kp, sign, 1e-12, mode)
+        assert ok and not eqf and np.array_equal(S, sign)
+        assert np.abs(L @ np.diag(S) @ L.T - Kp).max() < 1e-10
+        rhs = rng.standard_normal(n + ne)
+        u = np.empty(n + ne)
+        u[order] = ipm_ref._signed_solve(L, S, rhs[order])
+        assert np.abs(K @ u - rhs).max() < 1e-10
+    # one negative eigenvalue too many: both tests refuse
     Kbad = Kp.copy()
     Kbad[0, 0] -= 1000.0
-    assert not ipm_ref._signed_cholesky(Kbad, sign, 1e-12)[0]
+    assert not ipm_ref._signed_cholesky(Kbad, sign, 1e-12, 0)[0]
+    assert not ipm_ref._signed_cholesky(Kbad, sign, 1e-12, 1)[0]
+    # H indefinite but positive definite on the null space of Jc: the inertia is
+    # right (n positive, ne negative eigenvalues).  IPOPT's test (mode 0, the number
+    # of negative pivots) accepts it, the positional test (mode 1) does not.
+    H2 = np.diag(np.r_[-1.0, np.full(n - 1, 5.0)])
+    J2 = np.zeros((1, n))
+    J2[0, 0] = 1.0
+    K2 = np.block([[H2, J2.T], [J2, np.zeros((1, 1))]])
+    sign2 = np.r_[np.ones(n), -1.0]
+    assert sorted(np.sign(np.linalg.eigvalsh(K2))).count(-1.0) == 1
+    ok0, L0, _, S0 = ipm_ref._signed_cholesky(K2, sign2, 1e-12, 0)
+    assert ok0 and S0[0] == -1.0 and S0[-1] == 1.0
+    assert np.abs(L0 @ np.diag(S0) @ L0.T - K2).max() < 1e-12
+    assert not ipm_ref._signed_cholesky(K2, sign2, 1e-12, 1)[0]
 
 
 def test_kkt_structure_is_consistent(cfg1):
