@@ -247,7 +247,7 @@ __device__ __forceinline__ void factor_env(const DevTab& T, const Smem& S, doubl
       for (int r = 0; r < NB; ++r)
 #pragma unroll
         for (int c = 0; c <= r; ++c) a[r][c] = Ld[r * NB + c];
-      bool bad = false, bad_eq = false;
+      int bad_at = -1;
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
         // rows >= nb are zero-padded: give them a unit pivot so the arithmetic stays finite
@@ -259,7 +259,7 @@ __device__ __forceinline__ void factor_env(const DevTab& T, const Smem& S, doubl
         const double d = live ? sj * a[j][j] : 1.0;
         const double thr = (live && (mode == 0 || sj > 0.0)) ? PIV_TOL * fmax(diag0[kb + j], 1e-300) : 0.0;
         const bool fail_j = !(d > thr) || !(d < 1e300);
-        if (fail_j && !bad) { bad = true; bad_eq = (T.ksign[kb + j] < 0); }
+        if (fail_j && bad_at < 0) bad_at = kb + j;
         if (live) { sgn[kb + j] = sj; n_neg += (sj < 0.0) ? 1 : 0; }
         const double inv = rsqrt(d);
         a[j][j] = d * inv;
@@ -274,7 +274,8 @@ __device__ __forceinline__ void factor_env(const DevTab& T, const Smem& S, doubl
           for (int c = j + 1; c <= r; ++c) a[r][c] -= lr * a[c][j];
         }
       }
-      if (bad) { ctl->fail = 1; ctl->eq_fail = bad_eq ? 1 : 0; }
+      if (bad_at >= 0) { ctl->fail = 1; ctl->eq_fail = (T.ksign[bad_at] < 0) ? 1 : 0; }
+      else if (mode == 0 && n_neg > T.n_eq) { ctl->fail = 1; ctl->eq_fail = 0; }   // too many already: stop early
 #pragma unroll
       for (int r = 0; r < NB; ++r)
 #pragma unroll
