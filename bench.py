@@ -147,8 +147,8 @@ WORKLOADS = {
 
 # DRAM traffic of the solver kernel per solve, from the ncu --set full captures
 # (dram__bytes_read.sum + dram__bytes_write.sum of a 148-solve launch):
-# profiles/r01_v4_ncu_raw.txt (config 2), profiles/r01_xl_config4_ncu_raw.txt (config 4)
-NCU_DRAM_BYTES_PER_SOLVE = {'config2': (1.152512e6 + 1.606912e6) / 148.,
+# profiles/r01_v5_ncu_raw.txt (config 2), profiles/r01_xl_config4_ncu_raw.txt (config 4)
+NCU_DRAM_BYTES_PER_SOLVE = {'config2': (1.151488e6 + 1.359360e6) / 148.,
                             'config4': (3.464099e9 + 7.549988e9) / 148.}
 # bounded CPU sample: about 20 s of single-core work of the C oracle per measurement
 CPU_SAMPLE = {'config1': 2048, 'config2': 1024, 'config4': 96, 'config5': 512}

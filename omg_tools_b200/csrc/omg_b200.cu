@@ -255,8 +255,9 @@ __device__ __forceinline__ void factor_env(const DevTab& T, const Smem& S, doubl
         // mode 0 (IPOPT's inertia test): S takes the sign of the pivot as it comes, only the
         // number of negative pivots is checked at the end; mode 1: S fixed (+ variables,
         // - equality rows), a pivot of the other sign fails
+        // (|pivot| keeps the sign selection off the dependent chain pivot -> rsqrt -> column)
         const double sj = !live ? 1.0 : (mode ? sgn[kb + j] : (a[j][j] > 0.0 ? 1.0 : -1.0));
-        const double d = live ? sj * a[j][j] : 1.0;
+        const double d = !live ? 1.0 : (mode ? sj * a[j][j] : fabs(a[j][j]));
         const double thr = (live && (mode == 0 || sj > 0.0)) ? PIV_TOL * fmax(diag0[kb + j], 1e-300) : 0.0;
         const bool fail_j = !(d > thr) || !(d < 1e300);
         if (fail_j && bad_at < 0) bad_at = kb + j;
