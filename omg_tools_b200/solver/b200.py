@@ -196,6 +196,12 @@ def pack_tables(tb):
     return T, keep
 
 
+_NO_EFFECT_IPOPT_OPTIONS = frozenset([
+    'print_level', 'print_time', 'sb', 'file_print_level', 'output_file',
+    'print_timing_statistics', 'print_user_options', 'linear_solver',
+    'warm_start_init_point', 'fixed_variable_treatment', 'ma57_automatic_scaling',
+    'hessian_approximation', 'verbose'])
+
 _TERMLIST_FIELDS = ('G', 'F', 'DF', 'J', 'W')
 
 
@@ -293,13 +299,19 @@ class B200Solver(object):
         self._stats = {'return_status': None, 'iter_count': 0}
 
     def _apply_options(self, options):
+        import warnings
         fields = dict((f[0], f[1]) for f in _Options._fields_)
         for key, value in options.items():
-            if key in fields:
+            if key in fields and key != 'reserved':
                 setattr(self._opt, key, value)
-            # other IPOPT keys (print_level, warm_start_init_point='yes',
-            # fixed_variable_treatment, linear_solver ...) have no effect here:
-            # warm start pushes are always the 'yes' variants
+            elif key in _NO_EFFECT_IPOPT_OPTIONS:
+                # printing / linear-solver selection, and warm_start_init_point: the
+                # warm-start pushes are always the 'yes' variants the reference sets
+                pass
+            else:
+                # an IPOPT option that changes the algorithm would silently be lost
+                warnings.warn('solver option %r is not supported by the b200 solver and '
+                              'is ignored' % key)
 
     def set_options(self, options):
         self._apply_options(options)

@@ -527,3 +527,22 @@ def test_batched_receding_horizon_config4():
     d0 = np.linalg.norm(start - big.poseT[:, :3], axis=1)
     d1 = np.linalg.norm(big.veh.position() - big.poseT[:, :3], axis=1)
     assert np.all(d1 < d0)
+
+
+@pytest.mark.gpu
+def test_planar_quadrotor_matches_oracle():
+    """examples/p2p_quadrotor.py (vehicles/quadrotor.py): non-convex thrust
+    bound, the case IPOPT's inertia test (number of negative pivots) is needed
+    for.  8 jittered instances vs the CPU oracle."""
+    pr = sc.config_quadrotor2d()
+    tb = pr.father.tables
+    X0, P = sc.instance_data(pr, 8, jitter=0.2, seed=11)
+    res = pr.problem.solve_batch(X0, P)
+    ref = ipm_c.solve_batch_full(tb, X0, P, threads=8)
+    assert np.array_equal(res['status'], ref['status'])
+    ok = ref['status'] == 0
+    assert ok.sum() >= 7
+    assert np.median(res['iters'][ok]) < 80           # 140 with the positional inertia test
+    # the flat outputs (vehicle splines, first 28 coefficients) and the objective
+    assert np.median(np.abs(res['x'] - ref['x'])[ok][:, :28].max(axis=1)) < NORTH_STAR_TOL
+    assert np.abs(res['f'] - ref['f'])[ok].max() < 1e-3
