@@ -8,6 +8,7 @@ iteration = reference ``ADMMProblem.dual_update`` (admm.py:584-628):
     communicate   x_j <- neighbours' x_i        [NCCL all-gather]   (468-475)
     update_z/l    ONE kernel (omg_admm_zl_update)          (407-466, 493-508)
     residuals     sum over agents               [NCCL all-reduce, 3 doubles] (597-605)
+    accelerate    optional Nesterov extrapolation of z, l  (admm.py:510-554)
     communicate   z_ji, l_ji <- neighbours' z_ij, l_ij     [NCCL all-gather]
 
 The exchange is the only collective of the framework; message sizes are tiny
@@ -107,6 +108,7 @@ class FormationADMMRunner(object):
                        in p.father.shifted_entries()]
         self.time_prev = 0.
         self.history = []
+        self.alpha, self.c_res_p = 1., None      # Nesterov state
 
     # ------------------------------------------------------------------
     def _pack_parameters(self, t):
@@ -149,10 +151,31 @@ class FormationADMMRunner(object):
         Tf, Tb = p.first_knot_transforms(t)
         Tf_d = torch.tensor(Tf, dtype=torch.float64, device=self.dev)
         Tb_d = torch.tensor(Tb, dtype=torch.float64, device=self.dev)
+        nesterov = bool(p.options.get('nesterov_acceleration'))
+        if nesterov:
+            prev = [a.clone() for a in (self.z_i, self.z_ij, self.l_i, self.l_ij)]
         self.b200.admm_zl_update(self.PzT, self.c, Tf_d, Tb_d, p.options['rho'], self.x_i,
                                  self.x_j, self.z_i, self.z_ij, self.l_i, self.l_ij,
                                  self.res, p.L)
         tot = self.ex.allreduce_sum(self.res.sum(0))
+        if nesterov:
+            # fast ADMM: the combined residual is global (same decision on every rank)
+            c_res, eta = float(tot[2]), p.options.get('eta', 0.999)
+            if self.c_res_p is None:
+                self.c_res_p = c_res / eta
+            if (not p.options.get('nesterov_reset')) or c_res <= eta * self.c_res_p:
+                alpha_p = self.alpha
+                self.alpha = 0.5 * (1. + np.sqrt(1. + 4. * alpha_p**2))
+                w = (alpha_p - 1.) / self.alpha
+                for name, old in zip(('z_i', 'z_ij', 'l_i', 'l_ij'), prev):
+                    a = getattr(self, name)
+                    a.add_(a - old, alpha=w)
+                self.c_res_p = c_res
+            else:
+                self.alpha = 1.
+                for name, old in zip(('z_i', 'z_ij', 'l_i', 'l_ij'), prev):
+                    getattr(self, name).copy_(old)
+                self.c_res_p = self.c_res_p / eta
         # communicate z, l
         self.z_ji, self.l_ji = self.ex.gather_zl(self.z_ij, self.l_ij)
         tot = tot.cpu().numpy()

@@ -2,7 +2,7 @@
 of the reference's ADMM iteration (omgtools/problems/admm.py:584-628
 ADMMProblem.dual_update with per-updater update_x 383-398, communicate 468-475,
 update_z 407-440 / construct_upd_z 117-168, update_l 442-466, get_residuals
-493-508, init_step 477-491), one agent at a time, x-update through the CPU
+493-508, init_step 477-491, accelerate 510-554), one agent at a time, x-update through the CPU
 interior-point oracle.  The z-update solves the KKT system of the reference
 (f, G, h, mu) literally instead of using the precomputed projector of the
 product path.  parity unpinned (no CasADi/IPOPT here)."""
@@ -21,6 +21,7 @@ class ADMMOracle(object):
         self.z_ji, self.l_ji = p.z_ji.copy(), p.l_ji.copy()
         self.time_prev = 0.
         self.status = None
+        self.alpha, self.c_res_p = 1., None      # Nesterov state (admm.py:510-516)
 
     def _solve(self, x0, par):
         tb = self.p.tb
@@ -76,6 +77,7 @@ class ADMMOracle(object):
             z = TB.dot(-(1. / rho) * (A.T.dot(mu) + f))
             z_i_new[i], z_ij_new[i] = z[:nsh], z[nsh:].reshape(nn, nsh)
         z_i_p, z_ij_p = self.z_i, self.z_ij
+        l_i_p, l_ij_p = self.l_i, self.l_ij
         self.z_i, self.z_ij = z_i_new, z_ij_new
         self.l_i = self.l_i + rho * (self.x_i - self.z_i)
         self.l_ij = self.l_ij + rho * (self.x_j - self.z_ij)
@@ -85,6 +87,24 @@ class ADMMOracle(object):
             e2 = tf(np.r_[self.z_i[i] - z_i_p[i], (self.z_ij[i] - z_ij_p[i]).reshape(-1)])
             pri, dri = e1.dot(e1), rho * e2.dot(e2)
             pr += pri; dr += dri; cr += rho * pri + dri
+        if p.options.get('nesterov_acceleration'):
+            # fast ADMM (Goldstein et al.), admm.py:510-554 with nesterov_reset
+            eta = p.options.get('eta', 0.999)
+            if self.c_res_p is None:
+                self.c_res_p = cr / eta
+            if (not p.options.get('nesterov_reset')) or cr <= eta * self.c_res_p:
+                alpha_p = self.alpha
+                self.alpha = 0.5 * (1. + np.sqrt(1. + 4. * alpha_p**2))
+                w = (alpha_p - 1.) / self.alpha
+                self.z_i = self.z_i + w * (self.z_i - z_i_p)
+                self.z_ij = self.z_ij + w * (self.z_ij - z_ij_p)
+                self.l_i = self.l_i + w * (self.l_i - l_i_p)
+                self.l_ij = self.l_ij + w * (self.l_ij - l_ij_p)
+                self.c_res_p = cr
+            else:
+                self.alpha = 1.
+                self.z_i, self.z_ij, self.l_i, self.l_ij = z_i_p, z_ij_p, l_i_p, l_ij_p
+                self.c_res_p = self.c_res_p / eta
         # ---- communicate z, l ---------------------------------------------------------------
         for i in range(N):
             for k, j in enumerate(p.nghb[i]):

@@ -104,3 +104,27 @@ def test_admm_oracle_reduces_formation_error(formation):
         spread.append(np.abs(cen - cen.mean(0)).max())
         assert np.all(orc.status == 0)
     assert spread[-1] < 0.2 * spread[0]
+
+
+def test_admm_oracle_nesterov_acceleration(formation):
+    """Fast ADMM (reference admm.py:510-554): the extrapolated iteration differs
+    from plain ADMM from the second iteration on and still drives the agents to
+    consensus; with nesterov_reset the step is undone when the combined residual
+    grows."""
+    from oracle.admm_ref import ADMMOracle
+    plain = ADMMOracle(sc.config3(4, build_solver=False))
+    fast = ADMMOracle(sc.config3(4, {'nesterov_acceleration': True}, build_solver=False))
+    reset = ADMMOracle(sc.config3(4, {'nesterov_acceleration': True, 'nesterov_reset': True},
+                                  build_solver=False))
+    hist = {k: [] for k in ('plain', 'fast', 'reset')}
+    for k in range(8):
+        for name, orc in (('plain', plain), ('fast', fast), ('reset', reset)):
+            hist[name].append(orc.dual_update(0.))
+            assert np.all(orc.status == 0)
+        if k == 0:      # alpha_0 = 1: the first extrapolation weight is zero
+            assert np.allclose(fast.z_i, plain.z_i) and np.allclose(fast.l_i, plain.l_i)
+    assert not np.allclose(fast.z_i, plain.z_i)
+    assert fast.alpha > 3.0 and reset.alpha <= fast.alpha
+    for name in ('fast', 'reset'):
+        pr = np.array([h[0] for h in hist[name]])
+        assert pr[-1] < 0.3 * pr[0]          # primal residual (consensus error) shrinks

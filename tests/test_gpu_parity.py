@@ -261,14 +261,17 @@ def test_receding_horizon_batch256_50_steps(solvers):
     assert np.isfinite(bat.state).all()
 
 
-def test_formation_admm_matches_oracle(solvers):
+@pytest.mark.parametrize('opts', [None, {'nesterov_acceleration': True},
+                                  {'nesterov_acceleration': True, 'nesterov_reset': True}])
+def test_formation_admm_matches_oracle(solvers, opts):
     """BASELINE config 3 (4 agents as in the reference example): batched x-update +
-    consensus kernel vs the sequential ADMM oracle, iteration by iteration."""
+    consensus kernel vs the sequential ADMM oracle, iteration by iteration; plain
+    ADMM and the fast (Nesterov) variants of admm.py:510-554."""
     from omg_tools_b200.problems.admm_gpu import FormationADMMRunner
     from oracle.admm_ref import ADMMOracle
-    pr = sc.config3(4)
+    pr = sc.config3(4, opts)
     run = FormationADMMRunner(pr)
-    orc = ADMMOracle(sc.config3(4, build_solver=False))
+    orc = ADMMOracle(sc.config3(4, opts, build_solver=False))
     for it in range(6):
         rg = run.dual_update(0.)
         ro = orc.dual_update(0.)
