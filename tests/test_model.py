@@ -362,3 +362,52 @@ def test_planar_quadrotor_receding_horizon():
     assert np.abs(veh.signals['state'][:2, -1] - [4., 4.]).max() < 5e-2
     u1 = veh.signals['input'][0]
     assert u1.min() > 2. - 1e-2 and u1.max() < 15. + 1e-2      # thrust limits hold along the flight
+
+
+def test_batch_mpc_quadrotor_prediction_matches_reference_loop():
+    """execution/batch_mpc.py: the Quadrotor3D adapter predicts position and
+    velocity by exact Gauss-Legendre quadrature of the flat-output accelerations;
+    it must reproduce the reference-style Vehicle.store/predict bookkeeping
+    (splines2signals + integrate_twice), including a step across a knot."""
+    from oracle import ipm_c
+    if not ipm_c.available():
+        pytest.skip('C oracle not built')
+    from omg_tools_b200.execution import batch_mpc as bm
+
+    class HostTensor(object):          # what the adapter needs from a CUDA tensor
+        def __init__(self, a):
+            self.a = a
+
+        def cpu(self):
+            return self
+
+        def numpy(self):
+            return self.a
+
+    pr = sc.config4(build_solver=False)
+    pr.problem = _OracleSolver(pr.father.tables)
+    pr.initialize(0.)
+    veh = pr.vehicles[0]
+    ad = bm._Quadrotor3DAdapter(None, veh, 1, 0., np.random.default_rng(0))
+    t, dt = 0., 0.4
+    for k in range(3):
+        pr.predict(t, dt, 0.01)
+        pr.init_step(t, dt)
+        if k > 0:
+            assert np.abs(ad.state[0] - veh.prediction['state']).max() < 1e-11
+            assert np.abs(ad.inp[0] - veh.prediction['input']).max() < 1e-11
+        pr.solve(t, dt)
+        x = pr.father.get_variables().cat
+        ad.predict(HostTensor(x[None]), np.round(t, 6) % pr.knot_time, dt, 5.0, device=False)
+        pr.store(t, dt, 0.01)
+        pr.simulate(t, dt, 0.01)
+        t += dt
+    # parameter packing of the adapter == the model's set_parameters
+    P = np.zeros((1, pr.father.tables.n_par))
+    ent = pr.father._par_struct.entries
+    ad.state, ad.inp = veh.prediction['state'][None].copy(), veh.prediction['input'][None].copy()
+    ad.pack(P, {key: ent[key][0] for key in ent})
+    ref = pr.father.set_parameters(t).cat
+    for key, (off, size, _) in ent.items():
+        if key[0] == veh.label:
+            assert np.abs(P[0, off:off + size] - ref[off:off + size]).max() < 1e-12, key
