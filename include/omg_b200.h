@@ -202,6 +202,20 @@ int omg_sample_batch(int32_t B, int32_t n, const double* x, int32_t n_blocks,
                      const int32_t* offs, const int32_t* lens, const int32_t* ncols,
                      const int32_t* nsamp, const double* S, double* out, void* stream);
 
+/* Non-ideal state prediction for a batch (DEVICE pointers): integrate the vehicle ODE from
+ * state0 [B x n_state] over `steps` samples of the planned input trajectory
+ * inputs [B x (steps+1) x n_input] with classical RK4, result in stateT [B x n_state].
+ * Reference: Vehicle.predict / integrate_ode (vehicle.py:302-337, 412-423), C++ twin
+ * Vehicle::predict / integrate (export/vehicles/Vehicle.cpp:61-110; stages 1-3 use
+ * input[i], stage 4 input[i+1]).  Unlike the C++ twin, which evaluates every step's
+ * stages at the initial state, the running state is used (identical for the holonomic
+ * integrator model).  model: 0 integrator (state' = input: Holonomic, Holonomic1D/3D),
+ * 1 Quadrotor3D (8 states, 3 inputs; quadrotor3d.py:308-312), 2 planar Quadrotor
+ * (5 states, 2 inputs; quadrotor.py:154-157). */
+int omg_integrate_rk4(int32_t model, int32_t B, int32_t n_state, int32_t n_input,
+                      const double* state0, const double* inputs, double sample_time,
+                      int32_t steps, double* stateT, void* stream);
+
 /* ADMM consensus step for n_agents agents on the current device (DEVICE pointers):
  * closed-form z-update, lambda-update and squared residuals of the reference's
  * ADMM updater (omgtools/problems/admm.py:117-168 construct_upd_z/update_z,

@@ -1203,6 +1203,52 @@ __global__ void omg_shift_kernel(double* x, int B, int n, int n_blocks, const in
   }
 }
 
+// vehicle models for the batched state prediction (reference Vehicle.ode of each class)
+enum { OMG_ODE_INTEGRATOR = 0, OMG_ODE_QUADROTOR3D = 1, OMG_ODE_QUADROTOR2D = 2 };
+#define OMG_ODE_MAX_STATE 8
+
+__device__ __forceinline__ void ode_rhs(int model, int ns, const double* st, const double* u, double* d) {
+  if (model == OMG_ODE_QUADROTOR3D) {          // quadrotor3d.py:308-312
+    const double phi = st[6], theta = st[7], g = 9.81;
+    d[0] = st[3]; d[1] = st[4]; d[2] = st[5];
+    d[3] = u[0] * sin(theta) * cos(phi); d[4] = -u[0] * sin(phi);
+    d[5] = -g + u[0] * cos(phi) * cos(theta); d[6] = u[1]; d[7] = u[2];
+  } else if (model == OMG_ODE_QUADROTOR2D) {   // quadrotor.py:154-157
+    const double theta = st[4], g = 9.81;
+    d[0] = st[2]; d[1] = st[3]; d[2] = u[0] * sin(theta); d[3] = u[0] * cos(theta) - g; d[4] = u[1];
+  } else {                                     // holonomic*.py: state' = input
+    for (int j = 0; j < ns; ++j) d[j] = u[j];
+  }
+}
+
+// Non-ideal prediction: integrate the vehicle ODE over `steps` samples of the planned input
+// with classical RK4 (reference Vehicle.predict / integrate_ode, vehicle.py:302-337, 412-423;
+// C++ twin Vehicle::integrate, export/vehicles/Vehicle.cpp:80-110: k1..k3 with input[i], k4
+// with input[i+1]).  One thread per instance.
+__global__ void omg_rk4_kernel(int model, int B, int ns, int ni, const double* __restrict__ state0,
+                               const double* __restrict__ inputs, double dt, int steps,
+                               double* __restrict__ stateT) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double x[OMG_ODE_MAX_STATE], k1[OMG_ODE_MAX_STATE], k2[OMG_ODE_MAX_STATE], k3[OMG_ODE_MAX_STATE],
+         k4[OMG_ODE_MAX_STATE], st[OMG_ODE_MAX_STATE];
+  for (int j = 0; j < ns; ++j) x[j] = state0[(size_t)b * ns + j];
+  const double* U = inputs + (size_t)b * (steps + 1) * ni;
+  for (int i = 0; i < steps; ++i) {
+    const double* u0 = U + (size_t)i * ni;
+    const double* u1 = u0 + ni;
+    ode_rhs(model, ns, x, u0, k1);
+    for (int j = 0; j < ns; ++j) st[j] = x[j] + 0.5 * dt * k1[j];
+    ode_rhs(model, ns, st, u0, k2);
+    for (int j = 0; j < ns; ++j) st[j] = x[j] + 0.5 * dt * k2[j];
+    ode_rhs(model, ns, st, u0, k3);
+    for (int j = 0; j < ns; ++j) st[j] = x[j] + dt * k3[j];
+    ode_rhs(model, ns, st, u1, k4);
+    for (int j = 0; j < ns; ++j) x[j] += (dt / 6.0) * (k1[j] + 2.0 * k2[j] + 2.0 * k3[j] + k4[j]);
+  }
+  for (int j = 0; j < ns; ++j) stateT[(size_t)b * ns + j] = x[j];
+}
+
 // trajectory sampling: out[b, blk, c, s] = sum_k S_blk[s,k] * x[b, off_blk + c*len_blk + k]
 // (batched Cox-de Boor evaluation with precomputed basis rows; reference
 //  Vehicle.store -> sample_splines, vehicle.py:250-300, spline_extra.py:406-410;
@@ -1875,6 +1921,19 @@ int omg_sample_batch(int32_t B, int32_t n, const double* x, int32_t n_blocks, co
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(stream));
   cudaFree(d_i); cudaFree(d_S);
+  return 0;
+}
+
+int omg_integrate_rk4(int32_t model, int32_t B, int32_t n_state, int32_t n_input, const double* state0,
+                      const double* inputs, double sample_time, int32_t steps, double* stateT, void* stream_) {
+  if (B <= 0) return 0;
+  if (!state0 || !inputs || !stateT) { set_err("null buffer"); return -1; }
+  const int want_s[3] = {n_input, 8, 5}, want_i[3] = {n_input, 3, 2};
+  if (model < 0 || model > 2 || n_state < 1 || n_state > OMG_ODE_MAX_STATE || steps < 0 ||
+      n_state != want_s[model] || n_input != want_i[model]) { set_err("bad vehicle model / sizes"); return -1; }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  omg_rk4_kernel<<<(B + 127) / 128, 128, 0, stream>>>(model, B, n_state, n_input, state0, inputs, sample_time, steps, stateT);
+  CK(cudaGetLastError());
   return 0;
 }
 

@@ -81,7 +81,7 @@ EXPORTS = ['omg_abi_version', 'omg_last_error', 'omg_default_options',
            'omg_solve_batch', 'omg_solve_batch_host', 'omg_shift_batch',
            'omg_get_trace', 'omg_get_info', 'omg_last_timing',
            'omg_admm_zl_update', 'omg_sample_batch', 'omg_tables_read',
-           'omg_tables_free']
+           'omg_tables_free', 'omg_integrate_rk4']
 
 _lib = None
 
@@ -118,6 +118,7 @@ def load_library(path=None):
     lib.omg_last_timing.argtypes = [vp, C.POINTER(C.c_float), _i32p]
     lib.omg_admm_zl_update.argtypes = [C.c_int32] * 4 + [vp] * 4 + [C.c_double] + [vp] * 8
     lib.omg_sample_batch.argtypes = [C.c_int32, C.c_int32, vp, C.c_int32] + [vp] * 7
+    lib.omg_integrate_rk4.argtypes = [C.c_int32] * 4 + [vp, vp, C.c_double, C.c_int32, vp, vp]
     lib.omg_tables_read.argtypes = [C.c_char_p]
     lib.omg_tables_read.restype = C.POINTER(_Tables)
     lib.omg_tables_free.argtypes = [C.POINTER(_Tables)]
@@ -474,6 +475,32 @@ def sample_batch(X, blocks, stream=None):
     rc = lib.omg_sample_batch(X.shape[0], X.shape[1], X.data_ptr(), len(blocks), offs.ctypes.data,
                               lens.ctypes.data, ncols.ctypes.data, nsamp.ctypes.data,
                               Sm.ctypes.data, out.data_ptr(), C.c_void_p(stream.cuda_stream))
+    if rc != 0:
+        raise RuntimeError('libomgb200: %s' % lib.omg_last_error().decode())
+    return out
+
+
+ODE_MODELS = {'Holonomic': 0, 'Holonomic1D': 0, 'Holonomic3D': 0, 'Quadrotor3D': 1, 'Quadrotor': 2}
+
+
+def integrate_rk4(model, state0, inputs, sample_time, stream=None):
+    """Non-ideal prediction on the device (omg_integrate_rk4): state0 [B, n_state] and the
+    planned inputs [B, steps+1, n_input] are torch CUDA float64 tensors; returns the states
+    after steps*sample_time.  ``model`` is a vehicle class name or a model id."""
+    import torch
+    lib = load_library()
+    mid = ODE_MODELS[model] if isinstance(model, str) else int(model)
+    for t in (state0, inputs):
+        if t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous():
+            raise ValueError('contiguous float64 CUDA tensors expected')
+    B, ns = state0.shape
+    steps, ni = inputs.shape[1] - 1, inputs.shape[2]
+    out = torch.empty_like(state0)
+    if stream is None:
+        stream = torch.cuda.current_stream(state0.device)
+    rc = lib.omg_integrate_rk4(mid, B, ns, ni, state0.data_ptr(), inputs.data_ptr(),
+                               float(sample_time), steps, out.data_ptr(),
+                               C.c_void_p(stream.cuda_stream))
     if rc != 0:
         raise RuntimeError('libomgb200: %s' % lib.omg_last_error().decode())
     return out

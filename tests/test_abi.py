@@ -13,7 +13,7 @@ HEADER = os.path.join(ROOT, 'include', 'omg_b200.h')
 def declared_functions():
     src = open(HEADER).read()
     src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
-    return sorted(set(re.findall(r'\b(omg_[a-z_]+)\s*\(', src)))
+    return sorted(set(re.findall(r'\b(omg_[a-z0-9_]+)\s*\(', src)))
 
 
 @pytest.fixture(scope='module')

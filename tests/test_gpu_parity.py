@@ -549,3 +549,49 @@ def test_planar_quadrotor_matches_oracle():
     # the flat outputs (vehicle splines, first 28 coefficients) and the objective
     assert np.median(np.abs(res['x'] - ref['x'])[ok][:, :28].max(axis=1)) < NORTH_STAR_TOL
     assert np.abs(res['f'] - ref['f'])[ok].max() < 1e-3
+
+
+@pytest.mark.gpu
+def test_rk4_state_prediction():
+    """omg_integrate_rk4 (non-ideal prediction, Vehicle.predict / integrate_ode;
+    C++ twin Vehicle::integrate): batch RK4 on the device vs numpy RK4 with the
+    vehicle classes' own ode(), and vs the exact spline integral for the
+    holonomic model."""
+    import torch
+    from omg_tools_b200 import Holonomic, Quadrotor, Quadrotor3D
+    from omg_tools_b200.solver.b200 import integrate_rk4
+
+    def rk4(veh, x, U, dt):
+        for i in range(U.shape[0] - 1):
+            k1 = veh.ode(x, U[i])
+            k2 = veh.ode(x + 0.5 * dt * k1, U[i])
+            k3 = veh.ode(x + 0.5 * dt * k2, U[i])
+            k4 = veh.ode(x + dt * k3, U[i + 1])
+            x = x + dt / 6. * (k1 + 2 * k2 + 2 * k3 + k4)
+        return x
+
+    rng = np.random.default_rng(5)
+    B, steps, dt = 17, 40, 0.01
+    for veh, ns, ni in ((Holonomic(), 2, 2), (Quadrotor3D(0.5), 8, 3), (Quadrotor(), 5, 2)):
+        x0 = 0.3 * rng.standard_normal((B, ns))
+        U = 0.5 * rng.standard_normal((B, steps + 1, ni))
+        if ni == 3:
+            U[:, :, 0] += 9.81
+        out = integrate_rk4(type(veh).__name__, torch.tensor(x0, device='cuda:0'),
+                            torch.tensor(U, device='cuda:0'), dt).cpu().numpy()
+        ref = np.array([rk4(veh, x0[b], U[b], dt) for b in range(B)])
+        assert np.abs(out - ref).max() < 1e-12
+    # holonomic model on a solved trajectory: RK4 of the sampled velocity == spline value
+    pr = sc.config1()
+    res = pr.problem.solve_batch(G['config1_X0'], G['config1_P'])
+    basis = pr.vehicles[0].basis
+    tau = np.linspace(0., 0.04, steps + 1)            # 0.4 s of the 10 s horizon
+    Bd, P1 = basis.derivative(1)
+    V = Bd.eval_basis(tau).dot(P1) / 10.
+    X = res['x']
+    vel = np.stack([X[:, :13].dot(V.T), X[:, 13:26].dot(V.T)], axis=2)     # [B, steps+1, 2]
+    pos0 = np.stack([X[:, :13].dot(basis.eval_basis([0.])[0]), X[:, 13:26].dot(basis.eval_basis([0.])[0])], 1)
+    pos1 = np.stack([X[:, :13].dot(basis.eval_basis([0.04])[0]), X[:, 13:26].dot(basis.eval_basis([0.04])[0])], 1)
+    out = integrate_rk4('Holonomic', torch.tensor(pos0, device='cuda:0'),
+                        torch.tensor(np.ascontiguousarray(vel), device='cuda:0'), 0.01).cpu().numpy()
+    assert np.abs(out - pos1).max() < 1e-5             # velocity is piecewise quadratic in time
