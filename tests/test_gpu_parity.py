@@ -581,7 +581,9 @@ def test_rk4_state_prediction():
                             torch.tensor(U, device='cuda:0'), dt).cpu().numpy()
         ref = np.array([rk4(veh, x0[b], U[b], dt) for b in range(B)])
         assert np.abs(out - ref).max() < 1e-12
-    # holonomic model on a solved trajectory: RK4 of the sampled velocity == spline value
+    # holonomic model on a solved trajectory.  The scheme of the reference's C++ twin uses
+    # input[i] for the stages 1-3 and input[i+1] for the stage 4, i.e. the quadrature
+    # dt*(5 u_i + u_{i+1})/6 per sample: exact for that rule, first order w.r.t. the spline.
     pr = sc.config1()
     res = pr.problem.solve_batch(G['config1_X0'], G['config1_P'])
     basis = pr.vehicles[0].basis
@@ -590,8 +592,11 @@ def test_rk4_state_prediction():
     V = Bd.eval_basis(tau).dot(P1) / 10.
     X = res['x']
     vel = np.stack([X[:, :13].dot(V.T), X[:, 13:26].dot(V.T)], axis=2)     # [B, steps+1, 2]
-    pos0 = np.stack([X[:, :13].dot(basis.eval_basis([0.])[0]), X[:, 13:26].dot(basis.eval_basis([0.])[0])], 1)
-    pos1 = np.stack([X[:, :13].dot(basis.eval_basis([0.04])[0]), X[:, 13:26].dot(basis.eval_basis([0.04])[0])], 1)
+    b0, b1 = basis.eval_basis([0.])[0], basis.eval_basis([0.04])[0]
+    pos0 = np.stack([X[:, :13].dot(b0), X[:, 13:26].dot(b0)], 1)
+    pos1 = np.stack([X[:, :13].dot(b1), X[:, 13:26].dot(b1)], 1)
     out = integrate_rk4('Holonomic', torch.tensor(pos0, device='cuda:0'),
                         torch.tensor(np.ascontiguousarray(vel), device='cuda:0'), 0.01).cpu().numpy()
-    assert np.abs(out - pos1).max() < 1e-5             # velocity is piecewise quadratic in time
+    rule = pos0 + 0.01 * (5. * vel[:, :-1] + vel[:, 1:]).sum(axis=1) / 6.
+    assert np.abs(out - rule).max() < 1e-13
+    assert np.abs(out - pos1).max() < 5e-3             # and close to the spline itself
