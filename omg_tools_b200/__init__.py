@@ -10,6 +10,7 @@ from .vehicles.holonomic import Holonomic
 from .vehicles.holonomic3d import Holonomic3D
 from .vehicles.holonomic1d import Holonomic1D
 from .vehicles.quadrotor import Quadrotor
+from .vehicles.dubins import Dubins
 from .vehicles.quadrotor3d import Quadrotor3D
 from .vehicles.fleet import Fleet
 from .environment.environment import Environment

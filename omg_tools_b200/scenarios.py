@@ -157,6 +157,22 @@ def config_quadrotor2d(options=None, build_solver=True):
     return _p2p(vehicle, environment, opts, build_solver)
 
 
+def config_dubins(options=None, build_solver=True):
+    """examples/p2p_dubins.py with a fixed end time: Dubins(vmax 0.7, |w| <= pi/3,
+    substitution), Square(5) room centred at (1.5, 1.5), one Circle(0.5) obstacle
+    drifting in x; horizon 10 s."""
+    from . import Dubins
+    vehicle = Dubins(bounds={'vmax': 0.7, 'wmax': np.pi / 3., 'wmin': -np.pi / 3.},
+                     options={'substitution': True})
+    vehicle.set_initial_conditions([0., 0., 0.])
+    vehicle.set_terminal_conditions([3., 3., 0.])
+    environment = Environment(room={'shape': Square(5.), 'position': [1.5, 1.5]})
+    trajectories = {'velocity': {'time': [0.5], 'values': [[0.25, 0.0]]}}
+    environment.add_obstacle(Obstacle({'position': [1., 1.]}, shape=Circle(0.5),
+                                      simulation={'trajectories': trajectories}))
+    return _p2p(vehicle, environment, options, build_solver)
+
+
 def config_freeT(options=None, build_solver=True, moving=False):
     """Minimum-time variant of examples/p2p_holonomic.py (freeT=True, the
     example's commented alternative): two rectangular walls and a circle

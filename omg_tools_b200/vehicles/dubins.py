@@ -1,0 +1,171 @@
+"""Dubins vehicle: forward speed and heading, flat outputs v~ = v / (1 + tan^2(theta/2))
+and tan(theta/2) as degree-3 splines (reference ``omgtools/vehicles/dubins.py``: bounds
+38-45, trajectory constraints 72-126, initial / terminal constraints 155-193, initial
+guess 206-214, parameters 225-233, collision constraints 235-251, integrate_once
+253-259, signals 261-288).
+
+The position is the running integral of v~(1 - tg^2), 2 v~ tg re-anchored at t/T.  This
+framework supports the reference's ``substitution`` formulation (the example
+examples/p2p_dubins.py uses it): slack velocity splines dx, dy carry the position, and
+the band |int(dx) - int(v~(1-tg^2))| <= 1e-3 ties them to the flat outputs, its
+product-spline coefficients being shared intermediates (basics/poly.py).  Without
+substitution the collision rows multiply the integrated position by (1 + tg^2), i.e.
+they are not affine in the intermediates."""
+import numpy as np
+
+from .vehicle import Vehicle
+from ..basics.optilayer import inf
+from ..basics.poly import Poly, new_mid, collapse
+from ..basics.shape import Circle
+from ..basics.spline import BSplineBasis, BSpline
+from ..basics.spline_extra import evalspline, running_integral, sample_splines
+
+
+class Dubins(Vehicle):
+
+    def __init__(self, shapes=None, options=None, bounds=None):
+        bounds = bounds or {}
+        shapes = shapes if shapes is not None else Circle(0.1)
+        degree = options['degree'] if options is not None and 'degree' in options else 3
+        Vehicle.__init__(self, n_spl=2, degree=degree, shapes=shapes, options=options)
+        self.vmax = bounds.get('vmax', 0.5)
+        self.amax = bounds.get('amax', 1.)
+        self.wmin = bounds.get('wmin', -np.pi / 6.)
+        self.wmax = bounds.get('wmax', np.pi / 6.)
+
+    def set_default_options(self):
+        Vehicle.set_default_options(self)
+        self.options.update({'stop_tol': 1.e-2, 'substitution': True,
+                             'exact_substitution': False})
+
+    def init(self):
+        self.t = self.define_symbol('t')
+        self.pos0 = self.define_parameter('pos0', 2)
+
+    def _shared(self, name, spline):
+        coeffs = np.empty(len(spline.coeffs), dtype=object)
+        for k, c in enumerate(spline.coeffs):
+            if isinstance(c, Poly) and c.degree() >= 2:
+                c = new_mid('%s_%s_%d' % (self.label, name, k), c)
+            coeffs[k] = c
+        return BSpline(spline.basis, coeffs)
+
+    def define_trajectory_constraints(self, splines, horizon_time):
+        if not self.options['substitution'] or self.options['exact_substitution']:
+            raise NotImplementedError(
+                'Dubins needs options substitution=True, exact_substitution=False here: '
+                'without the slack velocity splines the collision rows are not affine in '
+                'the shared intermediates')
+        T = horizon_time
+        v_til, tg_ha = splines
+        dtg_ha = tg_ha.derivative()
+        self.define_constraint(v_til * (1 + tg_ha**2) - self.vmax, -inf, 0.)
+        self.define_constraint(-v_til, -inf, 0)          # forward driving only
+        dx = v_til * (1 - tg_ha**2)
+        dy = v_til * (2 * tg_ha)
+        degree = 3
+        knots = np.r_[np.zeros(degree), np.linspace(0., 1., 10 + 1), np.ones(degree)]
+        basis = BSplineBasis(knots, degree)
+        self.dx = self.define_spline_variable('dx', 1, 1, basis=basis)[0]
+        self.dy = self.define_spline_variable('dy', 1, 1, basis=basis)[0]
+        for name in ('dx', 'dy'):       # keep the warm start consistent (see quadrotor3d.py)
+            self._splines_prim[name]['shift'] = True
+        self.x = self.integrate_once(self.dx, self.pos0[0], self.t, T)
+        self.y = self.integrate_once(self.dy, self.pos0[1], self.t, T)
+        x = self.integrate_once(self._shared('dx', dx), self.pos0[0], self.t, T)
+        y = self.integrate_once(self._shared('dy', dy), self.pos0[1], self.t, T)
+        eps = 1e-3
+        self.define_constraint(self.x - x, -eps, eps)
+        self.define_constraint(self.y - y, -eps, eps)
+        self.define_constraint(2 * dtg_ha - (1 + tg_ha**2) * T * self.wmax, -inf, 0.)
+        self.define_constraint(-2 * dtg_ha + (1 + tg_ha**2) * T * self.wmin, -inf, 0.)
+
+    def get_initial_constraints(self, splines, horizon_time):
+        v_til0 = self.define_parameter('v_til0', 1)
+        tg_ha0 = self.define_parameter('tg_ha0', 1)
+        dtg_ha0 = self.define_parameter('dtg_ha0', 1)
+        v_til, tg_ha = splines
+        return [(v_til, v_til0), (tg_ha, tg_ha0),
+                (tg_ha.derivative(), horizon_time * dtg_ha0)]
+
+    def get_terminal_constraints(self, splines, horizon_time=None):
+        posT = self.define_parameter('posT', 2)
+        tg_haT = self.define_parameter('tg_haT', 1)
+        v_til, tg_ha = splines
+        term_con = [(self.x, posT[0]), (self.y, posT[1]), (tg_ha, tg_haT)]
+        term_con_der = [(v_til, 0.), (tg_ha.derivative(), 0.)]
+        return [term_con, term_con_der]
+
+    def set_initial_conditions(self, state, input=None):
+        if input is None:
+            input = np.zeros(2)
+        self.prediction['state'] = np.asarray(state, dtype=float)
+        self.prediction['input'] = np.asarray(input, dtype=float)
+        self.pose0 = np.asarray(state, dtype=float)
+
+    def set_terminal_conditions(self, pose):
+        self.poseT = np.asarray(pose, dtype=float)
+
+    def get_init_spline_value(self, subgoals=None):
+        L = len(self.basis)
+        init_value = np.zeros((L, 2))
+        tg_ha0 = np.tan(self.prediction['state'][2] / 2.)
+        tg_haT = np.tan(self.poseT[2] / 2.)
+        init_value[:, 1] = np.linspace(tg_ha0, tg_haT, L)
+        return [init_value]
+
+    def check_terminal_conditions(self):
+        tol = self.options['stop_tol']
+        if (np.linalg.norm(self.signals['state'][:, -1] - self.poseT) > tol or
+                np.linalg.norm(self.signals['input'][:, -1]) > tol):
+            return False
+        return True
+
+    def set_parameters(self, current_time):
+        parameters = Vehicle.set_parameters(self, current_time)
+        p = parameters[self]
+        p['tg_ha0'] = np.tan(self.prediction['state'][2] / 2.)
+        p['v_til0'] = self.prediction['input'][0] / (1 + p['tg_ha0']**2)
+        p['dtg_ha0'] = 0.5 * self.prediction['input'][1] * (1 + p['tg_ha0']**2)
+        p['pos0'] = self.prediction['state'][:2]
+        p['posT'] = self.poseT[:2]
+        p['tg_haT'] = np.tan(self.poseT[2] / 2.)
+        return parameters
+
+    def define_collision_constraints(self, hyperplanes, room, splines, horizon_time):
+        if not isinstance(self.shapes[0], Circle):
+            raise NotImplementedError('Dubins with a non-circular shape needs the heading '
+                                      'in the collision rows')
+        self.define_collision_constraints_2d(hyperplanes, room, [self.x, self.y], horizon_time)
+
+    def integrate_once(self, dx, x0, t, T=1.):
+        """x(tau) with x(t/T) = x0 (reference dubins.py:253-259)."""
+        dx_int = T * running_integral(dx)
+        if isinstance(t, Poly):
+            return dx_int - collapse(evalspline(dx_int, t / T, True)) + x0
+        return dx_int - dx_int(t / T)[0] + x0
+
+    def splines2signals(self, splines, time):
+        signals = {}
+        v_til, tg_ha = splines[0], splines[1]
+        dtg_ha = tg_ha.derivative()
+        dx = v_til * (1 - tg_ha**2)
+        dy = v_til * (2 * tg_ha)
+        st = self.prediction['state']
+        x = self.integrate_once(dx, st[0], time[0])
+        y = self.integrate_once(dy, st[1], time[0])
+        x_s, y_s, v_til_s, tg_ha_s, dtg_ha_s = [
+            np.asarray(v) for v in sample_splines([x, y, v_til, tg_ha, dtg_ha], time)]
+        den = np.asarray(sample_splines([(1 + tg_ha**2)], time)[0])
+        theta = 2 * np.arctan2(tg_ha_s, 1)
+        dtheta = 2 * dtg_ha_s / (1. + tg_ha_s**2)
+        signals['state'] = np.c_[x_s, y_s, theta].T
+        signals['input'] = np.c_[v_til_s * den, dtheta].T
+        return signals
+
+    def state2pose(self, state):
+        return state
+
+    def ode(self, state, input):
+        theta, v, w = state[2], input[0], input[1]
+        return np.r_[v * np.cos(theta), v * np.sin(theta), w].T

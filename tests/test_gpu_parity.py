@@ -600,3 +600,20 @@ def test_rk4_state_prediction():
     rule = pos0 + 0.01 * (5. * vel[:, :-1] + vel[:, 1:]).sum(axis=1) / 6.
     assert np.abs(out - rule).max() < 1e-13
     assert np.abs(out - pos1).max() < 5e-3             # and close to the spline itself
+
+
+@pytest.mark.gpu
+def test_dubins_matches_oracle():
+    """vehicles/dubins.py (substitution form, 116 shared intermediates): the XL
+    kernel vs the CPU oracle on 8 jittered instances."""
+    pr = sc.config_dubins()
+    tb = pr.father.tables
+    X0, P = sc.instance_data(pr, 8, jitter=0.1, seed=1)
+    res = pr.problem.solve_batch(X0, P)
+    ref = ipm_c.solve_batch_full(tb, X0, P, threads=8)
+    assert np.array_equal(res['status'], ref['status'])
+    ok = ref['status'] == 0
+    assert ok.sum() >= 7
+    err = np.abs(res['x'] - ref['x'])[ok][:, :26].max(axis=1)       # v~ and tan(theta/2) splines
+    assert np.median(err) < NORTH_STAR_TOL
+    assert np.abs(res['f'] - ref['f'])[ok].max() < 1e-3

@@ -411,3 +411,47 @@ def test_batch_mpc_quadrotor_prediction_matches_reference_loop():
     for key, (off, size, _) in ent.items():
         if key[0] == veh.label:
             assert np.abs(P[0, off:off + size] - ref[off:off + size]).max() < 1e-12, key
+
+
+def test_dubins_substitution_receding_horizon():
+    """vehicles/dubins.py (examples/p2p_dubins.py with a fixed end time): flat
+    outputs v~, tan(theta/2); the position band rows share 116 intermediates.
+    Table derivatives, then the MPC loop drives the vehicle to (3, 3, 0) within the
+    speed and turn-rate limits, every solve converged."""
+    from oracle import ipm_c
+    if not ipm_c.available():
+        pytest.skip('C oracle not built')
+    pr = sc.config_dubins(build_solver=False)
+    tb = pr.father.tables
+    assert (tb.n, tb.m, tb.n_mid, tb.degree) == (126, 554, 116, 3)
+    ev = TableEval(tb)
+    rng = np.random.default_rng(3)
+    X0, P = sc.instance_data(pr, 1)
+    x = X0[0] + 0.05 * rng.standard_normal(tb.n)
+    V = ev.tape(P[0])
+    J = ev.jac_dense(x, V)
+    lam = rng.standard_normal(tb.m)
+    W = ev.hess_dense(x, V, lam)
+    h = 1e-6
+    for j in rng.choice(tb.n, 8, replace=False):
+        e = np.zeros(tb.n)
+        e[j] = h
+        fd = (ev.g(x + e, V) - ev.g(x - e, V)) / (2 * h)
+        assert np.abs(fd - J[:, j]).max() < 1e-6 * max(1., np.abs(J[:, j]).max())
+        dj = (ev.jac_dense(x + e, V).T @ lam - ev.jac_dense(x - e, V).T @ lam) / (2 * h)
+        assert np.abs(dj - W[:, j]).max() < 1e-5 * max(1., np.abs(W[:, j]).max())
+    pr.problem = _OracleSolver(tb)
+    pr.initialize(0.)
+    t, dt = 0., 0.5
+    for k in range(22):
+        pr.predict(t, dt, 0.01)
+        pr.init_step(t, dt)
+        pr.solve(t, dt)
+        assert pr.problem.stats()['return_status'] == 'Solve_Succeeded', k
+        pr.store(t, dt, 0.01)
+        pr.simulate(t, dt, 0.01)
+        t = np.round(t + dt, 6)
+    veh = pr.vehicles[0]
+    assert np.abs(veh.signals['state'][:, -1] - [3., 3., 0.]).max() < 1e-2
+    assert veh.signals['input'][0].max() < 0.7 + 1e-3
+    assert np.abs(veh.signals['input'][1]).max() < np.pi / 3. + 1e-3
