@@ -455,3 +455,57 @@ def test_dubins_substitution_receding_horizon():
     assert np.abs(veh.signals['state'][:, -1] - [3., 3., 0.]).max() < 1e-2
     assert veh.signals['input'][0].max() < 0.7 + 1e-3
     assert np.abs(veh.signals['input'][1]).max() < np.pi / 3. + 1e-3
+
+
+def test_more_reference_examples_lower_and_solve():
+    """examples/p2p_holonomic_octroom.py (octagonal room -> half-plane room rows)
+    and a Holonomic with Euclidean (norm_2) velocity/acceleration limits: tables
+    build and the oracle converges to a feasible trajectory."""
+    from omg_tools_b200 import (Holonomic, Environment, Obstacle, Rectangle, Circle,
+                                RegularPolyhedron, Square)
+    from oracle import ipm_c
+    if not ipm_c.available():
+        pytest.skip('C oracle not built')
+
+    def octroom():
+        vehicle = Holonomic()
+        vehicle.set_options({'safety_distance': 0.1})
+        vehicle.set_initial_conditions([-1.5, -1.5])
+        vehicle.set_terminal_conditions([1.0, 1.5])
+        environment = Environment(room={'shape': RegularPolyhedron(2.5, 8)})
+        rectangle = Rectangle(width=3., height=0.2)
+        environment.add_obstacle(Obstacle({'position': [-2.1, -0.5]}, shape=rectangle))
+        environment.add_obstacle(Obstacle({'position': [1.7, -0.5]}, shape=rectangle))
+        traj = {'velocity': {'time': [3., 4.], 'values': [[-0.15, 0.0], [0., 0.15]]}}
+        environment.add_obstacle(Obstacle({'position': [1.5, 0.5]}, shape=Circle(0.4),
+                                          simulation={'trajectories': traj}))
+        return sc._p2p(vehicle, environment, None, False)
+
+    def norm2():
+        vehicle = Holonomic(options={'syslimit': 'norm_2'}, bounds={'vmax': 0.6, 'amax': 1.2})
+        vehicle.set_initial_conditions([-1.5, -1.5])
+        vehicle.set_terminal_conditions([2., 2.])
+        environment = Environment(room={'shape': Square(5.)})
+        environment.add_obstacle(Obstacle({'position': [0.3, 0.2]}, shape=Circle(0.6)))
+        return sc._p2p(vehicle, environment, None, False)
+
+    for build, m_expected in ((octroom, 801), (norm2, None)):
+        pr = build()
+        tb = pr.father.tables
+        if m_expected:
+            assert tb.m == m_expected
+        X0, P = sc.instance_data(pr, 1)
+        r = ipm_c.solve_batch_full(tb, X0, P, threads=1)
+        assert r['status'][0] == 0
+        ev = TableEval(tb)
+        g = ev.g(r['x'][0], ev.tape(P[0]))
+        assert (g <= tb.ubg + 1e-4).all() and (g >= tb.lbg - 1e-4).all()
+    # norm_2 limits: the speed along the solution stays below vmax
+    veh = pr.vehicles[0]
+    basis = veh.basis
+    tau = np.linspace(0, 1, 201)
+    Bd, P1 = basis.derivative(1)
+    D = Bd.eval_basis(tau).dot(P1) / 10.
+    x = r['x'][0]
+    speed = np.hypot(D.dot(x[:13]), D.dot(x[13:26]))
+    assert speed.max() < 0.6 + 1e-3
