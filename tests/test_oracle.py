@@ -163,3 +163,50 @@ def test_config4_golden_satisfies_kkt_conditions():
     slack = np.minimum(np.where(act_u, tb.ubg - g, np.inf), np.where(act_l, g - tb.lbg, np.inf))
     ineq = tb.lbg != tb.ubg
     assert np.abs(lam[ineq] * slack[ineq]).max() < 1e-5
+
+
+def _slsqp_from(tb, p, x_start, maxiter):
+    from scipy.optimize import minimize
+    ev = TableEval(tb)
+    V = ev.tape(p)
+    eq = tb.lbg == tb.ubg
+    has_u = (tb.ubg < 1e19) & ~eq
+    has_l = (tb.lbg > -1e19) & ~eq
+
+    def ineq(x):
+        g = ev.g(x, V)
+        return np.r_[(tb.ubg - g)[has_u], (g - tb.lbg)[has_l]]
+
+    def ineq_jac(x):
+        J = ev.jac_dense(x, V)
+        return np.r_[-J[has_u], J[has_l]]
+
+    cons = [{'type': 'eq', 'fun': lambda x: (ev.g(x, V) - tb.lbg)[eq],
+             'jac': lambda x: ev.jac_dense(x, V)[eq]},
+            {'type': 'ineq', 'fun': ineq, 'jac': ineq_jac}]
+    return minimize(lambda x: ev.f(x, V), x_start, jac=lambda x: ev.gradf(x, V),
+                    constraints=cons, method='SLSQP',
+                    options={'maxiter': maxiter, 'ftol': 1e-12})
+
+
+@pytest.mark.parametrize('name,maxiter,ftol', [('config_quadrotor2d', 100, 1e-6),
+                                               ('config4', 12, 1e-4)])
+def test_oracle_optimum_is_a_local_optimum_for_slsqp(name, maxiter, ftol):
+    """Independent optimiser on the non-convex models (planar quadrotor: non-convex
+    thrust bound; Quadrotor3D: chain-rule tables): started next to the oracle's tight
+    solution, scipy's SLSQP neither finds a lower objective nor moves the vehicle's
+    coefficients."""
+    from oracle import ipm_c
+    if not ipm_c.available():
+        pytest.skip('C oracle not built')
+    pr = getattr(sc, name)(build_solver=False)
+    tb = pr.father.tables
+    X0, P = sc.instance_data(pr, 1)
+    tight = {'tol': 1e-8, 'compl_inf_tol': 1e-8, 'constr_viol_tol': 1e-8}
+    r = ipm_c.solve_batch_full(tb, X0, P, threads=1, options=tight)
+    assert r['status'][0] == 0
+    xs = r['x'][0]
+    rng = np.random.default_rng(0)
+    res = _slsqp_from(tb, P[0], xs + 1e-3 * rng.standard_normal(tb.n), maxiter)
+    assert abs(res.fun - r['f'][0]) < ftol
+    assert np.abs(res.x - xs)[:28].max() < 1e-3
