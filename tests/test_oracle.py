@@ -210,3 +210,25 @@ def test_oracle_optimum_is_a_local_optimum_for_slsqp(name, maxiter, ftol):
     res = _slsqp_from(tb, P[0], xs + 1e-3 * rng.standard_normal(tb.n), maxiter)
     assert abs(res.fun - r['f'][0]) < ftol
     assert np.abs(res.x - xs)[:28].max() < 1e-3
+
+
+@pytest.mark.parametrize('name', ['config_freeT', 'config_quadrotor2d', 'config_dubins'])
+def test_c_oracle_equals_numpy_oracle_on_nonconvex_models(name):
+    """The two CPU restatements take the same path (same iteration count, same
+    point) where the soft restoration (FreeT), the inertia count with sign-indefinite
+    pivots (planar quadrotor) and the chain-rule tables (Dubins) are exercised."""
+    from oracle import ipm_c
+    if not ipm_c.available():
+        pytest.skip('C oracle not built')
+    pr = getattr(sc, name)(build_solver=False)
+    tb = pr.father.tables
+    X0, P = sc.instance_data(pr, 1)
+    rc = ipm_c.solve_batch_full(tb, X0, P, threads=1)
+    rn = ipm_ref.solve(tb, X0[0], P[0])
+    assert rc['status'][0] == rn.status == 0
+    # (the Dubins cold start takes ~270 iterations: rounding differences between the two
+    # codes accumulate to a few iterations and to tol-size in the non-unique variables)
+    assert abs(int(rc['iters'][0]) - rn.iters) <= max(1, 0.03 * rn.iters)
+    assert np.abs(rc['x'][0] - rn.x)[:26].max() < 1e-4
+    assert np.abs(rc['x'][0] - rn.x).max() < 1e-2
+    assert abs(rc['f'][0] - rn.f) < 1e-6
