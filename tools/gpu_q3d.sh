@@ -1,8 +1,6 @@
 #!/bin/bash
-# Quadrotor3D (config 4) on the GPU: parity test + timing of a batch
+# Quadrotor3D (config 4) on the GPU: timing of a batch of 512 (2 and 5 obstacles)
 mkdir -p gpurun_out
-true
-true
 timeout 900 python - <<'PY' 2>&1 | tee gpurun_out/q3d_time.log
 import time, numpy as np
 import __graft_entry__ as ge
