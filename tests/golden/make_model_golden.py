@@ -1,0 +1,347 @@
+"""Generate tests/golden/model_golden.npz from the REFERENCE's own modelling code.
+
+Run in the authoring container only (needs /root/reference):
+
+    python tests/golden/make_model_golden.py
+
+CasADi is not installed, so the reference's NLP cannot be *solved* here -- but its
+modelling layer (omgtools/vehicles, environment, problems, basics/optilayer.OptiChild,
+basics/spline*) only needs a scalar type with arithmetic and comparisons.  A stand-in
+``casadi`` module is registered whose ``MX`` is a 2-D float array that carries one seeded
+random VALUE per symbol (``MX.sym`` draws it; named placeholders take the value of their
+definition), plotting and export modules are stubbed, and the reference's files are loaded
+straight from /root/reference (nothing is copied).  ``Point2point(...).construct()`` then
+runs the reference's own code -- ``define_trajectory_constraints``,
+``define_collision_constraints``, the obstacle models, ``integrate_twice`` of Quadrotor3D,
+the initial/terminal constraints and the objective -- and every constraint row and the
+objective come out as NUMBERS: g_ref(x, p), f_ref(x, p) at that random point.  They are
+stored with the flat layout (children order, entry names, shapes), the values of x and p
+and the bounds; tests/test_model.py evaluates this framework's lowered tables at the same
+points.  That pins the NLP *definition* (every row, its order, its bounds, the objective)
+to the reference for BASELINE configs 1, 2, 4 and 5.
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+REF = '/root/reference/omgtools'
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'model_golden.npz')
+
+
+# --------------------------------------------------------------------------
+# stand-in for casadi.MX: a 2-D float array carrying one seeded random VALUE per symbol
+# --------------------------------------------------------------------------
+class Registry(object):
+    """Values of every symbol, keyed by its full name ('splines_seg0_vehicle0').  Named
+    placeholders (OptiChild.define_symbol: 'T', 't', ...) take the value of the variable or
+    parameter with the same base name (optilayer.py:204-223 translate_symbols)."""
+
+    def __init__(self, seed):
+        self.rng = np.random.default_rng(seed)
+        self.values = {}          # full name -> array
+        self.pending = {}         # base name -> array (placeholder asked before definition)
+        self.fixed = {}           # base name -> value forced by the generator (T, t)
+
+    def new_values(self, name, n, m):
+        base = name.rsplit('_', 1)[0]
+        if base in self.fixed and n * m == 1:
+            return np.full((n, m), self.fixed[base])
+        if base in self.pending and self.pending[base].shape == (n, m):
+            return self.pending.pop(base)
+        return self.rng.uniform(-1., 1., (n, m))
+
+    def define(self, name, n, m):
+        if name not in self.values:
+            self.values[name] = self.new_values(name, n, m)
+        return self.values[name]
+
+    def placeholder(self, base, n, m):
+        for full, val in self.values.items():
+            if full.rsplit('_', 1)[0] == base and val.shape == (n, m):
+                return val
+        if base not in self.pending:
+            self.pending[base] = (np.full((n, m), self.fixed[base]) if base in self.fixed
+                                  else self.rng.uniform(-1., 1., (n, m)))
+        return self.pending[base]
+
+
+REG = None
+
+
+def _num(a):
+    if isinstance(a, (MX, DM)):
+        return a.a
+    arr = np.asarray(a, dtype=float)
+    if arr.ndim == 0:
+        arr = arr.reshape(1, 1)
+    elif arr.ndim == 1:
+        arr = arr.reshape(-1, 1)
+    return arr
+
+
+class MX(object):
+    __array_priority__ = 1000
+    __array_ufunc__ = None
+
+    def __init__(self, a=0.):
+        self.a = _num(a)
+
+    @staticmethod
+    def sym(name, n=1, m=1):
+        return MX(REG.define(name, n, m))
+
+    @property
+    def shape(self):
+        return self.a.shape
+
+    def size(self):
+        return self.a.shape
+
+    def size1(self):
+        return self.a.shape[0]
+
+    def size2(self):
+        return self.a.shape[1]
+
+    def __len__(self):
+        return self.a.shape[0]
+
+    @property
+    def T(self):
+        return MX(self.a.T)
+
+    def __getitem__(self, key):
+        if not isinstance(key, tuple) and self.a.shape[1] == 1:
+            key = (key, slice(None))
+        out = self.a[key]
+        return MX(out)
+
+    def __iter__(self):
+        for i in range(self.a.shape[0]):
+            yield self[i]
+
+    def __float__(self):
+        return float(self.a.reshape(-1)[0])
+
+    def _bin(self, other, fun):
+        if not isinstance(other, (MX, DM, int, float, np.number, np.ndarray, list)):
+            return NotImplemented        # e.g. a reference BSpline: let its __r*__ handle it
+        a, b = self.a, _num(other)
+        if a.shape != b.shape and a.size != 1 and b.size != 1:
+            raise ValueError('shape mismatch %s %s' % (a.shape, b.shape))
+        return MX(fun(a, b))
+
+    def __add__(self, o): return self._bin(o, lambda x, y: x + y)
+    def __radd__(self, o): return self._bin(o, lambda x, y: y + x)
+    def __sub__(self, o): return self._bin(o, lambda x, y: x - y)
+    def __rsub__(self, o): return self._bin(o, lambda x, y: y - x)
+    def __mul__(self, o): return self._bin(o, lambda x, y: x * y)
+    def __rmul__(self, o): return self._bin(o, lambda x, y: y * x)
+    def __truediv__(self, o): return self._bin(o, lambda x, y: x / y)
+    def __rtruediv__(self, o): return self._bin(o, lambda x, y: y / x)
+    __div__, __rdiv__ = __truediv__, __rtruediv__
+    def __neg__(self): return MX(-self.a)
+    def __pos__(self): return self
+    def __pow__(self, k): return MX(self.a ** int(k))
+    def __ge__(self, o): return self._bin(o, lambda x, y: (x >= y).astype(float))
+    def __gt__(self, o): return self._bin(o, lambda x, y: (x > y).astype(float))
+    def __le__(self, o): return self._bin(o, lambda x, y: (x <= y).astype(float))
+    def __lt__(self, o): return self._bin(o, lambda x, y: (x < y).astype(float))
+
+    def column(self):
+        return self.a.reshape(-1, order='F')
+
+
+class DM(object):
+    def __init__(self, a=0.):
+        self.a = _num(a.toarray() if hasattr(a, 'toarray') else a)
+
+
+def mtimes(a, b):
+    A, B = _num(a), _num(b)
+    if A.size == 1 or B.size == 1:
+        return MX(A * B)
+    return MX(A.dot(B))
+
+
+def vertcat(*items):
+    return MX(np.vstack([_num(it) for it in items]))
+
+
+def _unary(fun):
+    return lambda x: MX(fun(x.a)) if isinstance(x, MX) else fun(x)
+
+
+def install_stubs():
+    cas = types.ModuleType('casadi')
+    cas.MX, cas.SX, cas.DM = MX, type('SX', (), {}), DM
+    cas.inf = np.inf
+    cas.mtimes, cas.vertcat = mtimes, vertcat
+    cas.cos, cas.sin = _unary(np.cos), _unary(np.sin)
+    cas.symvar = lambda x: []          # only feeds a bookkeeping dict (optilayer.py:529-533)
+    for name in ('Function', 'nlpsol', 'external', 'substitute', 'vertsplit',
+                 'Compiler', 'Importer'):
+        setattr(cas, name, lambda *a, **k: None)
+    tools = types.ModuleType('casadi.tools')
+    for name in ('struct', 'struct_MX', 'struct_symMX', 'entry'):
+        setattr(tools, name, lambda *a, **k: None)
+    cas.tools = tools
+    sys.modules['casadi'], sys.modules['casadi.tools'] = cas, tools
+    # package skeleton: sub-packages resolve to the reference's directories, none of the
+    # reference's __init__.py files (which import plotting, GUI, export ...) is executed
+    for pkg in ('', '.basics', '.vehicles', '.environment', '.problems', '.execution', '.export'):
+        m = types.ModuleType('omgtools' + pkg)
+        m.__path__ = [REF + pkg.replace('.', '/')]
+        sys.modules['omgtools' + pkg] = m
+    plot = types.ModuleType('omgtools.execution.plotlayer')
+
+    class PlotLayer(object):
+        def __init__(self, *a, **k):
+            pass
+
+    plot.PlotLayer = PlotLayer
+    plot.mix_with_white = lambda *a, **k: None
+    sys.modules['omgtools.execution.plotlayer'] = plot
+    exp = types.ModuleType('omgtools.export.export_p2p')
+    exp.ExportP2P = type('ExportP2P', (), {})
+    sys.modules['omgtools.export.export_p2p'] = exp
+
+
+def ref_import(name):
+    return importlib.import_module('omgtools.' + name)
+
+
+# --------------------------------------------------------------------------
+# scenarios, written against the reference's API (same values as scenarios.py)
+# --------------------------------------------------------------------------
+def build_reference(name):
+    hol = ref_import('vehicles.holonomic')
+    env = ref_import('environment.environment')
+    obs = ref_import('environment.obstacle')
+    shp = ref_import('basics.shape')
+    p2p = ref_import('problems.point2point')
+    from omg_tools_b200.scenarios import CONFIG2_OBSTACLES
+    if name == 'config1':
+        vehicle = hol.Holonomic()
+        vehicle.set_options({'safety_distance': 0.1})
+        vehicle.set_initial_conditions([-1.5, -1.5])
+        vehicle.set_terminal_conditions([2., 2.])
+        environment = env.Environment(room={'shape': shp.Square(5.)})
+        trajectories = {'velocity': {'time': [0., 40.], 'values': [[-0.35, 0.35], [0., 0.15]]}}
+        environment.add_obstacle(obs.Obstacle(
+            {'position': [1.5, -1]}, shape=shp.Circle(0.5), options={'bounce': False},
+            simulation={'trajectories': trajectories}))
+        options = {}
+    elif name == 'config2':
+        vehicle = hol.Holonomic()
+        vehicle.set_options({'safety_distance': 0.1})
+        vehicle.set_initial_conditions([-1.5, -1.5])
+        vehicle.set_terminal_conditions([2., 2.])
+        environment = env.Environment(room={'shape': shp.Square(5.)})
+        for pos in CONFIG2_OBSTACLES:
+            environment.add_obstacle(obs.Obstacle({'position': list(pos)}, shape=shp.Circle(0.4)))
+        options = {}
+    elif name == 'config5':
+        vehicle = hol.Holonomic()
+        vehicle.set_initial_conditions([0., -2.0])
+        vehicle.set_terminal_conditions([0., 2.0])
+        environment = env.Environment(room={'shape': shp.Square(5.)})
+        beam1 = shp.Beam(width=2.2, height=0.2)
+        environment.add_obstacle(obs.Obstacle({'position': [-2., 0.]}, shape=beam1))
+        environment.add_obstacle(obs.Obstacle({'position': [2., 0.]}, shape=beam1))
+        beam2 = shp.Beam(width=1.4, height=0.2)
+        horizon_time = 10.
+        omega = 1.5 * 1. * 2 * np.pi / horizon_time
+        environment.add_obstacle(obs.Obstacle(
+            {'position': [0., 0.], 'velocity': [0., 0.], 'angular_velocity': omega},
+            shape=beam2, simulation={}, options={'horizon_time': horizon_time}))
+        environment.add_obstacle(obs.Obstacle(
+            {'position': [0., 0.], 'velocity': [0., 0.], 'orientation': 0.5 * np.pi,
+             'angular_velocity': omega},
+            shape=beam2, simulation={}, options={'horizon_time': horizon_time}))
+        options = {'horizon_time': horizon_time}
+    elif name == 'config4':
+        quad = ref_import('vehicles.quadrotor3d')
+        vehicle = quad.Quadrotor3D(0.5)
+        vehicle.set_initial_conditions([-3, -2, -0.5, 0, 0, 0, 0, 0])
+        vehicle.set_terminal_conditions([3, 2, 0.5])
+        vehicle.set_options({'safety_distance': 0.1, 'safety_weight': 10})
+        environment = env.Environment(room={'shape': shp.Cuboid(8, 6, 8)})
+        plate = lambda: shp.Plate(shp.Rectangle(5., 8.), 0.1, orientation=[0., np.pi / 2, 0.])
+        trajectory = {'velocity': {'time': [1.5], 'values': [[0, 0, -0.6]]}}
+        environment.add_obstacle(obs.Obstacle({'position': [-2, 0, -2]}, shape=plate()))
+        environment.add_obstacle(obs.Obstacle({'position': [2, 0, 3.5]}, shape=plate(),
+                                              simulation={'trajectories': trajectory}))
+        options = {'horizon_time': 5.}
+    else:
+        raise ValueError(name)
+    opts = {'verbose': 0}
+    opts.update(options)
+    problem = p2p.Point2point(vehicle, environment, options=opts, freeT=False)
+    problem.father.reset()
+    problem.construct()
+    return problem
+
+
+def flatten(problem):
+    """Flat layout, values and rows of the reference problem (optilayer.py:225-272 order)."""
+    children = list(problem.father.children.values())
+    var, par, rows, lb, ub = [], [], [], [], []
+    obj = 0.
+    for ch in children:
+        for nm, v in ch._variables.items():
+            var.append((ch.label, nm, v))
+        for nm, v in ch._parameters.items():
+            par.append((ch.label, nm, v))
+        for nm, con in ch._constraints.items():
+            expr = con[0]
+            vals = expr.column() if isinstance(expr, MX) else np.atleast_1d(np.asarray(expr, float))
+            rows += list(vals)
+            lb += list(np.ones(len(vals)) * con[1])
+            ub += list(np.ones(len(vals)) * con[2])
+        o = ch._objective
+        obj = obj + (float(o) if isinstance(o, MX) else o)
+    return var, par, np.array(rows, float), np.array(lb, float), np.array(ub, float), float(obj)
+
+
+def main():
+    global REG
+    install_stubs()
+    out = {}
+    n_samples = 3
+    for name in ('config1', 'config2', 'config4', 'config5'):
+        Xs, Ps, Gs, Fs = [], [], [], []
+        for k in range(n_samples):
+            REG = Registry(seed=1000 * k + 7)
+            horizon = 5. if name == 'config4' else 10.
+            # T is the horizon of the scenario, t a time inside the first knot interval
+            REG.fixed = {'T': horizon, 't': 0.037 * horizon * (k + 1)}
+            # labels restart for every build so that the layout strings are comparable
+            opt = ref_import('basics.optilayer')
+            for cls in list(opt.OptiChild.__subclasses__()) + [opt.OptiChild]:
+                if hasattr(cls, '_labels'):
+                    cls._labels = []
+            problem = build_reference(name)
+            var, par, g, lb, ub, f = flatten(problem)
+            Xs.append(np.concatenate([v.column() for _, _, v in var]))
+            Ps.append(np.concatenate([v.column() for _, _, v in par]))
+            Gs.append(g)
+            Fs.append(f)
+        print(name, 'reference layout: n', len(Xs[0]), 'm', len(Gs[0]), 'n_par', len(Ps[0]))
+        out[name + '_X'], out[name + '_P'] = np.array(Xs), np.array(Ps)
+        out[name + '_G'], out[name + '_F'] = np.array(Gs), np.array(Fs)
+        out[name + '_lb'], out[name + '_ub'] = lb, ub
+        out[name + '_var_layout'] = np.array(['%s|%s|%dx%d' % ((lab, nm) + v.a.shape) for lab, nm, v in var])
+        out[name + '_par_layout'] = np.array(['%s|%s|%dx%d' % ((lab, nm) + v.a.shape) for lab, nm, v in par])
+    np.savez_compressed(OUT, **out)
+    print('wrote', OUT)
+
+
+if __name__ == '__main__':
+    main()

@@ -509,3 +509,33 @@ def test_more_reference_examples_lower_and_solve():
     x = r['x'][0]
     speed = np.hypot(D.dot(x[:13]), D.dot(x[13:26]))
     assert speed.max() < 0.6 + 1e-3
+
+
+@pytest.mark.parametrize('name', ['config1', 'config2', 'config4', 'config5'])
+def test_nlp_definition_equals_the_references_own_model_code(name):
+    """tests/golden/model_golden.npz holds g_ref(x, p), f_ref(x, p), the bounds and the
+    flat layout produced by the REFERENCE's modelling code itself (vehicles, environment,
+    obstacles, Point2point.construct, spline algebra) run on a numeric stand-in for
+    casadi.MX (tests/golden/make_model_golden.py).  This framework's lowered tables --
+    including the chain-rule tables of Quadrotor3D -- must give the same numbers: every
+    constraint row, in the same order, with the same bounds, and the objective."""
+    import os
+    import re
+    M = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'model_golden.npz'))
+    pr = getattr(sc, name)(build_solver=False)
+    tb, f = pr.father.tables, pr.father
+    norm = lambda s: re.sub(r'(vehicle|obstacle|p2p|environment)\d+', r'\1#', str(s))
+    layout = lambda st: [norm('%s|%s|%dx%d' % (k[0], k[1], v[2][0], v[2][1]))
+                         for k, v in st.entries.items()]
+    assert layout(f._var_struct) == [norm(s) for s in M[name + '_var_layout']]
+    assert layout(f._par_struct) == [norm(s) for s in M[name + '_par_layout']]
+    assert np.array_equal(tb.lbg, M[name + '_lb']) and np.array_equal(tb.ubg, M[name + '_ub'])
+    ev = TableEval(tb)
+    for k in range(M[name + '_X'].shape[0]):
+        x, p = M[name + '_X'][k], M[name + '_P'][k]
+        V = ev.tape(p)
+        g_ref = M[name + '_G'][k]
+        err = np.abs(ev.g(x, V) - g_ref) / np.maximum(1., np.abs(g_ref))
+        assert err.max() < 1e-7, (k, int(np.argmax(err)))
+        assert np.median(err) < 1e-13
+        assert abs(ev.f(x, V) - M[name + '_F'][k]) < 1e-12
