@@ -18,7 +18,8 @@ objective come out as NUMBERS: g_ref(x, p), f_ref(x, p) at that random point.  T
 stored with the flat layout (children order, entry names, shapes), the values of x and p
 and the bounds; tests/test_model.py evaluates this framework's lowered tables at the same
 points.  That pins the NLP *definition* (every row, its order, its bounds, the objective)
-to the reference for BASELINE configs 1, 2, 4 and 5.
+to the reference for BASELINE configs 1, 2, 4 and 5 and for the Holonomic3D, planar
+Quadrotor and Dubins examples.
 """
 import importlib.util
 import os
@@ -279,6 +280,40 @@ def build_reference(name):
         environment.add_obstacle(obs.Obstacle({'position': [2, 0, 3.5]}, shape=plate(),
                                               simulation={'trajectories': trajectory}))
         options = {'horizon_time': 5.}
+    elif name == 'config_holonomic3d':
+        h3 = ref_import('vehicles.holonomic3d')
+        vehicle = h3.Holonomic3D(shp.Plate(shp.Rectangle(0.5, 1.), height=0.1))
+        vehicle.set_initial_conditions([-2., -2., -2])
+        vehicle.set_terminal_conditions([2., 2., -2])
+        environment = env.Environment(room={'shape': shp.Cube(5.)})
+        environment.add_obstacle(obs.Obstacle(
+            {'position': [0., 0., -1.5]}, shape=shp.Cuboid(width=0.5, depth=4., height=2.)))
+        trajectories = {'velocity': {'time': [4.], 'values': [[0.0, 0.0, 1.]]}}
+        environment.add_obstacle(obs.Obstacle(
+            {'position': [1., 1., -2.25]}, shape=shp.RegularPrisma(0.25, 0.25, 6),
+            simulation={'trajectories': trajectories}))
+        options = {'hard_term_con': True, 'horizon_time': 12}
+    elif name == 'config_quadrotor2d':
+        q2 = ref_import('vehicles.quadrotor')
+        vehicle = q2.Quadrotor()
+        vehicle.set_options({'safety_distance': 0.1})
+        vehicle.set_initial_conditions([-4., -4., 0., 0., 0.])
+        vehicle.set_terminal_conditions([4., 4.])
+        environment = env.Environment(room={'shape': shp.Square(10.)})
+        environment.add_obstacle(obs.Obstacle({'position': [-0.6, -5.4]},
+                                              shape=shp.Rectangle(width=0.2, height=12.)))
+        options = {'horizon_time': 5}
+    elif name == 'config_dubins':
+        db = ref_import('vehicles.dubins')
+        vehicle = db.Dubins(bounds={'vmax': 0.7, 'wmax': np.pi / 3., 'wmin': -np.pi / 3.},
+                            options={'substitution': True})
+        vehicle.set_initial_conditions([0., 0., 0.])
+        vehicle.set_terminal_conditions([3., 3., 0.])
+        environment = env.Environment(room={'shape': shp.Square(5.), 'position': [1.5, 1.5]})
+        trajectories = {'velocity': {'time': [0.5], 'values': [[0.25, 0.0]]}}
+        environment.add_obstacle(obs.Obstacle({'position': [1., 1.]}, shape=shp.Circle(0.5),
+                                              simulation={'trajectories': trajectories}))
+        options = {}
     else:
         raise ValueError(name)
     opts = {'verbose': 0}
@@ -315,11 +350,12 @@ def main():
     install_stubs()
     out = {}
     n_samples = 3
-    for name in ('config1', 'config2', 'config4', 'config5'):
+    for name in ('config1', 'config2', 'config4', 'config5', 'config_holonomic3d',
+                 'config_quadrotor2d', 'config_dubins'):
         Xs, Ps, Gs, Fs = [], [], [], []
         for k in range(n_samples):
             REG = Registry(seed=1000 * k + 7)
-            horizon = 5. if name == 'config4' else 10.
+            horizon = {'config4': 5., 'config_quadrotor2d': 5., 'config_holonomic3d': 12.}.get(name, 10.)
             # T is the horizon of the scenario, t a time inside the first knot interval
             REG.fixed = {'T': horizon, 't': 0.037 * horizon * (k + 1)}
             # labels restart for every build so that the layout strings are comparable

@@ -511,7 +511,8 @@ def test_more_reference_examples_lower_and_solve():
     assert speed.max() < 0.6 + 1e-3
 
 
-@pytest.mark.parametrize('name', ['config1', 'config2', 'config4', 'config5'])
+@pytest.mark.parametrize('name', ['config1', 'config2', 'config4', 'config5', 'config_holonomic3d',
+                                  'config_quadrotor2d', 'config_dubins'])
 def test_nlp_definition_equals_the_references_own_model_code(name):
     """tests/golden/model_golden.npz holds g_ref(x, p), f_ref(x, p), the bounds and the
     flat layout produced by the REFERENCE's modelling code itself (vehicles, environment,
