@@ -345,6 +345,32 @@ def flatten(problem):
     return var, par, np.array(rows, float), np.array(lb, float), np.array(ub, float), float(obj)
 
 
+def host_values(problem, par, var, current_time):
+    """What the reference's host code feeds the solver: the parameter vector of
+    OptiFather.set_parameters (optilayer.py:427-445, values from every child's
+    set_parameters) and the initial guess of the vehicle splines
+    (Point2pointProblem.reinitialize -> vehicle.get_init_spline_value)."""
+    children = list(problem.father.children.values())
+    merged = {}
+    for ch in children:
+        for owner, dic in ch.set_parameters(current_time).items():
+            merged.setdefault(owner, {}).update(dic)
+    P = []
+    for ch in children:
+        for nm, v in ch._parameters.items():
+            val = merged.get(ch, {}).get(nm, ch._values[nm])
+            P.append(np.broadcast_to(np.asarray(val, float).reshape(-1, order='F') if np.ndim(val) else
+                                     np.asarray(val, float), (v.a.size,)).reshape(-1))
+    X0 = []
+    for ch in children:
+        for nm, v in ch._variables.items():
+            val = np.zeros(v.a.shape)
+            if nm == 'splines_seg0':
+                val = np.asarray(ch.get_init_spline_value()[0], float).reshape(v.a.shape)
+            X0.append(val.reshape(-1, order='F'))
+    return np.concatenate(P), np.concatenate(X0)
+
+
 def main():
     global REG
     install_stubs()
@@ -369,6 +395,8 @@ def main():
             Ps.append(np.concatenate([v.column() for _, _, v in par]))
             Gs.append(g)
             Fs.append(f)
+        t_host = 0.37
+        out[name + '_host_P'], out[name + '_host_X0'] = host_values(problem, par, var, t_host)
         print(name, 'reference layout: n', len(Xs[0]), 'm', len(Gs[0]), 'n_par', len(Ps[0]))
         out[name + '_X'], out[name + '_P'] = np.array(Xs), np.array(Ps)
         out[name + '_G'], out[name + '_F'] = np.array(Gs), np.array(Fs)

@@ -540,3 +540,7 @@ def test_nlp_definition_equals_the_references_own_model_code(name):
         assert err.max() < 1e-7, (k, int(np.argmax(err)))
         assert np.median(err) < 1e-13
         assert abs(ev.f(x, V) - M[name + '_F'][k]) < 1e-12
+    # what the host feeds the solver: the parameter vector at t = 0.37 (every child's
+    # set_parameters, optilayer.py:427-445) and the initial guess of the vehicle splines
+    assert np.array_equal(f.set_parameters(0.37).cat, M[name + '_host_P'])
+    assert np.array_equal(f.get_variables().cat, M[name + '_host_X0'])
