@@ -161,6 +161,8 @@ class Dubins(Vehicle):
         dtheta = 2 * dtg_ha_s / (1. + tg_ha_s**2)
         signals['state'] = np.c_[x_s, y_s, theta].T
         signals['input'] = np.c_[v_til_s * den, dtheta].T
+        acc = (v_til * (1 + tg_ha**2)).derivative()
+        signals['acc'] = np.c_[np.asarray(sample_splines([acc], time)[0])].T
         return signals
 
     def state2pose(self, state):

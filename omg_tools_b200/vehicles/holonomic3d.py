@@ -106,7 +106,7 @@ class Holonomic3D(Vehicle):
         signals['state'] = np.c_[sample_splines(list(splines[:3]), time)]
         signals['input'] = inp
         signals['v_tot'] = np.sqrt(inp[0, :]**2 + inp[1, :]**2 + inp[2, :]**2)
-        signals['dinput'] = np.c_[sample_splines(acc, time)]
+        signals['a'] = np.c_[sample_splines(acc, time)]
         return signals
 
     def state2pose(self, state):

@@ -371,6 +371,36 @@ def host_values(problem, par, var, current_time):
     return np.concatenate(P), np.concatenate(X0)
 
 
+def trajectories(problem, horizon, seed):
+    """Post-solve extraction by the reference (Vehicle.store -> concat_splines,
+    splines2signals, sample_splines; vehicle.py:250-300): state / input trajectories of
+    a perturbed initial-guess spline, sampled from a time inside the first knot interval."""
+    spl = ref_import('basics.spline')
+    vehicle = problem.vehicles[0]
+    rng = np.random.default_rng(seed)
+    C = np.asarray(vehicle.get_init_spline_value()[0], float)
+    C = C + 0.05 * rng.standard_normal(C.shape)
+    if type(vehicle).__name__ in ('Quadrotor3D',):
+        C[:, 0] += 9.81                      # thrust spline around hover
+    if type(vehicle).__name__ == 'Dubins':
+        C[:, 0] = np.abs(C[:, 0]) + 0.2      # forward speed
+    splines = [spl.BSpline(vehicle.basis, C[:, k]) for k in range(C.shape[1])]
+    sample_time, t_rel = 0.01, 0.17
+    n_samp = int(round((horizon - t_rel) / sample_time, 6)) + 1
+    time_axis = np.linspace(t_rel, t_rel + (n_samp - 1) * sample_time, n_samp)
+    # (the reference's err_* plot signals need a solved problem: switch them off for this call)
+    subst = vehicle.options.get('substitution')
+    if subst is not None:
+        vehicle.options['substitution'] = False
+    vehicle.store(1.3, sample_time, [splines], horizon, time_axis)
+    if subst is not None:
+        vehicle.options['substitution'] = subst
+    tr = vehicle.trajectories
+    keys = sorted(k for k in tr if k not in ('time', 'pose', 'splines', 'fleet_center')
+                  and not k.startswith('err_'))
+    return C, time_axis, {k: np.atleast_2d(np.asarray(tr[k], float)) for k in keys}
+
+
 def main():
     global REG
     install_stubs()
@@ -395,6 +425,11 @@ def main():
             Ps.append(np.concatenate([v.column() for _, _, v in par]))
             Gs.append(g)
             Fs.append(f)
+        C, tax, tr = trajectories(problem, horizon, 11)
+        out[name + '_traj_C'], out[name + '_traj_time'] = C, tax
+        for key, val in tr.items():
+            out[name + '_traj_' + key] = val
+        out[name + '_traj_keys'] = np.array(sorted(tr))
         t_host = 0.37
         out[name + '_host_P'], out[name + '_host_X0'] = host_values(problem, par, var, t_host)
         print(name, 'reference layout: n', len(Xs[0]), 'm', len(Gs[0]), 'n_par', len(Ps[0]))

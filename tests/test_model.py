@@ -544,3 +544,27 @@ def test_nlp_definition_equals_the_references_own_model_code(name):
     # set_parameters, optilayer.py:427-445) and the initial guess of the vehicle splines
     assert np.array_equal(f.set_parameters(0.37).cat, M[name + '_host_P'])
     assert np.array_equal(f.get_variables().cat, M[name + '_host_X0'])
+
+
+@pytest.mark.parametrize('name', ['config1', 'config4', 'config5', 'config_holonomic3d',
+                                  'config_quadrotor2d', 'config_dubins'])
+def test_trajectory_extraction_equals_the_references(name):
+    """Post-solve extraction: the reference's Vehicle.store ->
+    concat_splines / splines2signals / sample_splines, run from /root/reference on a
+    perturbed initial-guess spline (tests/golden/make_model_golden.py), against this
+    framework's Vehicle.store on the same coefficients and time axis -- every signal the
+    reference produces (state, input, and the model specific ones)."""
+    import os
+    from omg_tools_b200.basics.spline import BSpline
+    M = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'model_golden.npz'))
+    pr = getattr(sc, name)(build_solver=False)
+    veh = pr.vehicles[0]
+    C, tax = M[name + '_traj_C'], M[name + '_traj_time']
+    splines = [BSpline(veh.basis, C[:, k]) for k in range(C.shape[1])]
+    veh.store(1.3, 0.01, [splines], pr.options['horizon_time'], tax)
+    assert len(M[name + '_traj_keys']) >= 2
+    for key in M[name + '_traj_keys']:
+        ref = M[name + '_traj_' + str(key)]
+        mine = np.atleast_2d(veh.trajectories[str(key)])
+        assert mine.shape == ref.shape, key
+        assert np.abs(mine - ref).max() < 1e-12 * max(1., np.abs(ref).max()), key
