@@ -157,7 +157,7 @@ class ObstaclexD(OptiChild):
             st[0] = st[0] + sample_time * st[1] + 0.5 * sample_time**2 * st[2]
             st[1] = st[1] + sample_time * st[2]
             for tm, l, val in self._increments:
-                if t0 < tm <= t1 + 1e-12:
+                if t0 + 1e-9 < tm <= t1 + 1e-9:      # (sample times accumulate rounding)
                     st[l] = st[l] + val
             for k, key in enumerate(('position', 'velocity', 'acceleration')):
                 self.signals[key] = np.c_[self.signals[key], st[k]]

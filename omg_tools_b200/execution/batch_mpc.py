@@ -243,7 +243,7 @@ class BatchMPC(object):
                 d['x'] = d['x'] + sample_time * d['v'] + 0.5 * sample_time**2 * d['a']
                 d['v'] = d['v'] + sample_time * d['a']
                 for tm, l, val in inc:
-                    if t0 < tm <= t1 + 1e-12:
+                    if t0 + 1e-9 < tm <= t1 + 1e-9:      # (sample times accumulate rounding)
                         key = ('x', 'v', 'a')[l]
                         d[key] = d[key] + val
                 d['time'] = t1

@@ -206,6 +206,9 @@ def install_stubs():
         def __init__(self, *a, **k):
             pass
 
+        def update_plots(self, *a, **k):
+            pass
+
     plot.PlotLayer = PlotLayer
     plot.mix_with_white = lambda *a, **k: None
     sys.modules['omgtools.execution.plotlayer'] = plot
@@ -401,6 +404,29 @@ def trajectories(problem, horizon, seed):
     return C, time_axis, {k: np.atleast_2d(np.asarray(tr[k], float)) for k in keys}
 
 
+def obstacle_motion(problem, total_time, update_time=0.1, sample_time=0.01):
+    """Obstacle states after every update of the reference's simulator
+    (Environment.simulate -> ObstaclexD.simulate, obstacle.py:246-264, 375-386) and the
+    parameters the obstacles report then (set_parameters, obstacle.py:142-155, 345-348)."""
+    env = problem.environment
+    rows = []
+    t = 0.
+    for _ in range(int(round(total_time / update_time))):
+        env.simulate(update_time, sample_time)
+        t = np.round(t + update_time, 6)
+        row = []
+        for o in env.obstacles:
+            row += list(o.signals['position'][:, -1]) + list(o.signals['velocity'][:, -1])
+            pars = o.set_parameters(t)[o]
+            pars = {k: v for k, v in pars.items() if k in o._parameters}   # what the NLP receives
+            if 'theta' in pars:
+                row += [o.signals['orientation'][0, -1]]
+            for key in sorted(pars):
+                row += list(np.atleast_1d(np.asarray(pars[key], float)).reshape(-1))
+        rows.append(row)
+    return np.array(rows, float)
+
+
 def main():
     global REG
     install_stubs()
@@ -431,8 +457,17 @@ def main():
             out[name + '_traj_' + key] = val
         out[name + '_traj_keys'] = np.array(sorted(tr))
         t_host = 0.37
-        out[name + '_host_P'], out[name + '_host_X0'] = host_values(problem, par, var, t_host)
-        print(name, 'reference layout: n', len(Xs[0]), 'm', len(Gs[0]), 'n_par', len(Ps[0]))
+        if name in ('config1', 'config4', 'config5', 'config_holonomic3d', 'config_dubins'):
+            host = host_values(problem, par, var, t_host)
+            out[name + '_obst'] = obstacle_motion(problem, 5.0)
+            out[name + '_host_P'], out[name + '_host_X0'] = host
+            print(name, 'reference layout: n', len(Xs[0]), 'm', len(Gs[0]), 'n_par', len(Ps[0]))
+            continue_flag = True
+        else:
+            continue_flag = False
+        if not continue_flag:
+            out[name + '_host_P'], out[name + '_host_X0'] = host_values(problem, par, var, t_host)
+            print(name, 'reference layout: n', len(Xs[0]), 'm', len(Gs[0]), 'n_par', len(Ps[0]))
         out[name + '_X'], out[name + '_P'] = np.array(Xs), np.array(Ps)
         out[name + '_G'], out[name + '_F'] = np.array(Gs), np.array(Fs)
         out[name + '_lb'], out[name + '_ub'] = lb, ub

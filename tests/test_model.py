@@ -568,3 +568,35 @@ def test_trajectory_extraction_equals_the_references(name):
         mine = np.atleast_2d(veh.trajectories[str(key)])
         assert mine.shape == ref.shape, key
         assert np.abs(mine - ref).max() < 1e-12 * max(1., np.abs(ref).max()), key
+
+
+@pytest.mark.parametrize('name', ['config1', 'config4', 'config5', 'config_holonomic3d',
+                                  'config_dubins'])
+def test_obstacle_motion_equals_the_references(name):
+    """The reference's simulator (Environment.simulate -> ObstaclexD.simulate with the
+    'trajectories' increments, rotating obstacles) over 5 s in 0.1 s updates, and the
+    parameters every obstacle reports after each update (x, v, a, theta, checkpoints,
+    rad) -- from /root/reference via tests/golden/make_model_golden.py -- against this
+    framework's Obstacle.simulate / set_parameters.  (The reference integrates with
+    scipy's odeint, hence 1e-6.)"""
+    import os
+    M = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'model_golden.npz'))
+    pr = getattr(sc, name)(build_solver=False)
+    env = pr.environment
+    rows, t = [], 0.
+    for _ in range(50):
+        env.simulate(0.1, 0.01)
+        t = np.round(t + 0.1, 6)
+        row = []
+        for o in env.obstacles:
+            row += list(o.signals['position'][:, -1]) + list(o.signals['velocity'][:, -1])
+            pars = o.set_parameters(t)[o]
+            pars = {k: v for k, v in pars.items() if k in o._parameters}
+            if 'theta' in pars:
+                row += [o.signals['orientation'][0, -1]]
+            for key in sorted(pars):
+                row += list(np.atleast_1d(np.asarray(pars[key], float)).reshape(-1))
+        rows.append(row)
+    mine, ref = np.array(rows), M[name + '_obst']
+    assert mine.shape == ref.shape
+    assert np.abs(mine - ref).max() < 1e-6
