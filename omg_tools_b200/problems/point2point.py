@@ -208,6 +208,13 @@ class FreeTPoint2point(Point2pointProblem):
     every update) unless a multi-problem scheduler sets ``init_time``.  ``t/T``
     is not polynomial in the variable T, so the initial conditions are taken
     at 0 here and a non-zero ``init_time`` is refused.
+
+    Note on the surveyed commit of the reference: ``FreeTPoint2point.construct``
+    first runs ``Point2pointProblem.construct`` (point2point.py:53-62), which
+    defines T as a *parameter* and hands that symbol to the vehicle and environment
+    constraints, and only then defines the variable T (point2point.py:281-284) used by
+    the objective; the parameter is never set.  This class implements the intended
+    problem: every row depends on the variable T.
     """
 
     def __init__(self, fleet, environment, options):
