@@ -473,6 +473,16 @@ def main():
         out[name + '_lb'], out[name + '_ub'] = lb, ub
         out[name + '_var_layout'] = np.array(['%s|%s|%dx%d' % ((lab, nm) + v.a.shape) for lab, nm, v in var])
         out[name + '_par_layout'] = np.array(['%s|%s|%dx%d' % ((lab, nm) + v.a.shape) for lab, nm, v in par])
+    # Fleet of the formation examples (vehicles/fleet.py: set_configuration, neighbours)
+    hol, fl = ref_import('vehicles.holonomic'), ref_import('vehicles.fleet')
+    shp = ref_import('basics.shape')
+    for n_agents in (4, 6):
+        conf = shp.RegularPolyhedron(0.2, n_agents, np.pi / 4.).vertices.T
+        fleet = fl.Fleet([hol.Holonomic() for _ in range(n_agents)])
+        fleet.set_configuration(conf.tolist())
+        out['fleet%d_rel_pos_c' % n_agents] = np.array([v.rel_pos_c for v in fleet.vehicles], float)
+        out['fleet%d_nghb' % n_agents] = np.array(
+            [[fleet.vehicles.index(w) for w in fleet.get_neighbors(v)] for v in fleet.vehicles])
     np.savez_compressed(OUT, **out)
     print('wrote', OUT)
 

@@ -128,3 +128,21 @@ def test_admm_oracle_nesterov_acceleration(formation):
     for name in ('fast', 'reset'):
         pr = np.array([h[0] for h in hist[name]])
         assert pr[-1] < 0.3 * pr[0]          # primal residual (consensus error) shrinks
+
+
+def test_fleet_configuration_equals_the_references():
+    """Fleet.set_configuration / get_neighbors (vehicles/fleet.py) of the reference,
+    run from /root/reference (tests/golden/make_model_golden.py): relative positions
+    to the formation centre and the circular neighbour lists."""
+    import os
+    from omg_tools_b200 import Holonomic, Fleet, RegularPolyhedron
+    M = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'model_golden.npz'))
+    for n_agents in (4, 6):
+        conf = RegularPolyhedron(0.2, n_agents, np.pi / 4.).vertices.T
+        fleet = Fleet([Holonomic() for _ in range(n_agents)])
+        fleet.set_configuration(conf.tolist())
+        rel = np.array([v.rel_pos_c for v in fleet.vehicles], float)
+        nghb = np.array([[fleet.vehicles.index(w) for w in fleet.get_neighbors(v)]
+                         for v in fleet.vehicles])
+        assert np.abs(rel - M['fleet%d_rel_pos_c' % n_agents]).max() < 1e-15
+        assert np.array_equal(nghb, M['fleet%d_nghb' % n_agents])
