@@ -427,6 +427,26 @@ def obstacle_motion(problem, total_time, update_time=0.1, sample_time=0.01):
     return np.array(rows, float)
 
 
+def shape_zoo(shp):
+    """One instance of every shape class both code bases provide (same arguments)."""
+    return {
+        'circle': shp.Circle(0.4),
+        'rectangle': shp.Rectangle(width=3., height=0.2),
+        'rectangle_rot': shp.Rectangle(width=0.5, height=1.2, orientation=0.3),
+        'square': shp.Square(0.7),
+        'beam': shp.Beam(width=1.4, height=0.2),
+        'beam_rot': shp.Beam(width=2.2, height=0.2, orientation=0.5 * np.pi),
+        'regpoly8': shp.RegularPolyhedron(2.5, 8),
+        'regpoly5_rot': shp.RegularPolyhedron(0.6, 5, np.pi / 7.),
+        'sphere': shp.Sphere(0.5),
+        'cuboid': shp.Cuboid(width=0.5, depth=4., height=2.),
+        'cuboid_rot': shp.Cuboid(width=0.5, depth=1., height=2., orientation=[0.1, 0.4, -0.3]),
+        'cube': shp.Cube(5.),
+        'plate': shp.Plate(shp.Rectangle(5., 8.), 0.1, orientation=[0., np.pi / 2, 0.]),
+        'prisma': shp.RegularPrisma(0.25, 0.25, 6),
+    }
+
+
 def main():
     global REG
     install_stubs()
@@ -483,6 +503,17 @@ def main():
         out['fleet%d_rel_pos_c' % n_agents] = np.array([v.rel_pos_c for v in fleet.vehicles], float)
         out['fleet%d_nghb' % n_agents] = np.array(
             [[fleet.vehicles.index(w) for w in fleet.get_neighbors(v)] for v in fleet.vehicles])
+    # shapes (basics/shape.py): checkpoints + radii, canvas limits, room half-planes
+    for key, shape in shape_zoo(shp).items():
+        chck, rad = shape.get_checkpoints()
+        out['shape_%s_chck' % key] = np.array(chck, float)
+        out['shape_%s_rad' % key] = np.array(rad, float)
+        out['shape_%s_lims' % key] = np.array(shape.get_canvas_limits(), float)
+        if hasattr(shape, 'get_hyperplanes') and shape.n_dim == 2 and hasattr(shape, 'vertices'):
+            hyp = shape.get_hyperplanes(position=[0.3, -0.2])
+            out['shape_%s_hyp' % key] = np.array(
+                [np.r_[np.asarray(h['a'], float).reshape(-1), float(np.asarray(h['b']).reshape(-1)[0])]
+                 for _, h in sorted(hyp.items())])
     np.savez_compressed(OUT, **out)
     print('wrote', OUT)
 

@@ -600,3 +600,35 @@ def test_obstacle_motion_equals_the_references(name):
     mine, ref = np.array(rows), M[name + '_obst']
     assert mine.shape == ref.shape
     assert np.abs(mine - ref).max() < 1e-6
+
+
+def test_shapes_equal_the_references():
+    """basics/shape.py: checkpoints and radii, canvas limits and (2D polyhedra) the
+    half-planes used for non-rectangular rooms, for every shape class, against the
+    reference's classes run from /root/reference (tests/golden/make_model_golden.py)."""
+    import os
+    import omg_tools_b200 as og
+    M = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'model_golden.npz'))
+    zoo = {
+        'circle': og.Circle(0.4), 'rectangle': og.Rectangle(width=3., height=0.2),
+        'rectangle_rot': og.Rectangle(width=0.5, height=1.2, orientation=0.3),
+        'square': og.Square(0.7), 'beam': og.Beam(width=1.4, height=0.2),
+        'beam_rot': og.Beam(width=2.2, height=0.2, orientation=0.5 * np.pi),
+        'regpoly8': og.RegularPolyhedron(2.5, 8),
+        'regpoly5_rot': og.RegularPolyhedron(0.6, 5, np.pi / 7.),
+        'sphere': og.Sphere(0.5), 'cuboid': og.Cuboid(width=0.5, depth=4., height=2.),
+        'cuboid_rot': og.Cuboid(width=0.5, depth=1., height=2., orientation=[0.1, 0.4, -0.3]),
+        'cube': og.Cube(5.),
+        'plate': og.Plate(og.Rectangle(5., 8.), 0.1, orientation=[0., np.pi / 2, 0.]),
+        'prisma': og.RegularPrisma(0.25, 0.25, 6)}
+    for key, shape in zoo.items():
+        chck, rad = shape.get_checkpoints()
+        assert np.array_equal(np.array(chck, float), M['shape_%s_chck' % key]), key
+        assert np.array_equal(np.array(rad, float), M['shape_%s_rad' % key]), key
+        assert np.array_equal(np.array(shape.get_canvas_limits(), float), M['shape_%s_lims' % key]), key
+        if 'shape_%s_hyp' % key in M.files:
+            hyp = shape.get_hyperplanes(position=[0.3, -0.2])
+            mine = np.array([np.r_[np.asarray(h['a'], float).reshape(-1),
+                                   float(np.asarray(h['b']).reshape(-1)[0])]
+                             for _, h in sorted(hyp.items())])
+            assert np.abs(mine - M['shape_%s_hyp' % key]).max() < 1e-14, key
