@@ -632,3 +632,69 @@ def test_shapes_equal_the_references():
                                    float(np.asarray(h['b']).reshape(-1)[0])]
                              for _, h in sorted(hyp.items())])
             assert np.abs(mine - M['shape_%s_hyp' % key]).max() < 1e-14, key
+
+
+class _RecordingOracleSolver(_OracleSolver):
+    def __init__(self, tb):
+        _OracleSolver.__init__(self, tb)
+        self.calls = []
+
+    def __call__(self, x0, p, lbg, ubg, lam_g0=None, **kw):
+        args = [np.asarray(v, float).reshape(-1).copy() for v in (x0, p, lbg, ubg)]
+        res = _OracleSolver.__call__(self, x0, p, lbg, ubg)
+        self.calls.append(args + [np.asarray(res['x'], float).copy()])
+        return res
+
+
+@pytest.mark.parametrize('name,n_steps', [('config1', 12), ('config5', 12), ('config4', 3)])
+def test_host_loop_equals_the_references_problem_solve_loop(name, n_steps):
+    """tests/golden/loop_golden.npz: the REFERENCE's Deployer.update / Simulator.update /
+    Problem.solve / OptiFather loop, run from /root/reference around this repository's
+    solver (make_loop_golden.py), recorded what it hands to the solver at every MPC
+    step.  This framework's loop must hand over the same x0, p, lbg, ubg -- through the
+    first knot crossing (config 1 and 5 at t = 1.0) -- and unpack the same x.
+
+    Config 4: identical until the first knot crossing; there the reference leaves the
+    acceleration slacks ddx/ddy/ddz unshifted (and relies on IPOPT's restoration phase,
+    see vehicles/quadrotor3d.py) while this framework shifts them with the other splines."""
+    import os
+    from oracle import ipm_c
+    if not ipm_c.available():
+        pytest.skip('C oracle not built')
+    L = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'loop_golden.npz'))
+    pr = getattr(sc, name)(build_solver=False)
+    tb = pr.father.tables
+    pr.problem = _RecordingOracleSolver(tb)
+    dt = float(L[name + '_dt'])
+    pr.initialize(0.)
+    t = 0.
+    for k in range(n_steps):
+        pr.predict(t, dt, 0.01)
+        pr.solve(t, dt)
+        pr.store(t, dt, 0.01)
+        pr.simulate(t, dt, 0.01)
+        t = np.round(t + dt, 6)
+    calls = pr.problem.calls
+    n_same = n_steps if name != 'config4' else 2
+    for k in range(n_same):
+        x0, p, lbg, ubg, x = calls[k]
+        assert np.abs(x0 - L[name + '_x0'][k]).max() < 1e-6, k
+        assert np.abs(p - L[name + '_p'][k]).max() < 1e-7, k        # (reference: odeint obstacle motion)
+        assert np.array_equal(lbg, L[name + '_lbg'][k]) and np.array_equal(ubg, L[name + '_ubg'][k])
+        assert np.abs(x - L[name + '_x'][k]).max() < 1e-5, k
+    if name != 'config4':
+        # tight: the two host paths are numerically the same computation
+        assert max(np.abs(calls[k][0] - L[name + '_x0'][k]).max() for k in range(n_steps)) < 1e-11
+        assert max(np.abs(calls[k][1] - L[name + '_p'][k]).max() for k in range(n_steps)) < 1e-12
+    else:
+        from omg_tools_b200.basics.spline_extra import shiftoverknot_T
+        ent = pr.father._var_struct.entries
+        veh = pr.vehicles[0]
+        mine, ref = calls[2][0], L[name + '_x0'][2]
+        slack = np.zeros(tb.n, dtype=bool)
+        for nm in ('ddx', 'ddy', 'ddz'):
+            off, size, _ = ent[(veh.label, nm)]
+            slack[off:off + size] = True
+            T = shiftoverknot_T(veh._splines_prim[nm]['basis'])
+            assert np.abs(mine[off:off + size] - T.dot(ref[off:off + size])).max() < 1e-5
+        assert np.abs(mine - ref)[~slack].max() < 1e-5
