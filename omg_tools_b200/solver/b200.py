@@ -305,6 +305,8 @@ class B200Solver(object):
         for key, value in options.items():
             if key in fields and key != 'reserved':
                 setattr(self._opt, key, value)
+            elif key == 'retry_mu':
+                self._retry_mu = float(value)
             elif key in _NO_EFFECT_IPOPT_OPTIONS:
                 # printing / linear-solver selection, and warm_start_init_point: the
                 # warm-start pushes are always the 'yes' variants the reference sets
@@ -362,8 +364,14 @@ class B200Solver(object):
             raise ValueError('lbg and ubg shapes differ')
         return lbg, ubg, shared
 
-    def solve_batch(self, X0, P, lbg=None, ubg=None, lam_g0=None):
-        """Host arrays in, host arrays out (H2D + solve + D2H in one C call)."""
+    def solve_batch(self, X0, P, lbg=None, ubg=None, lam_g0=None, _retry=True):
+        """Host arrays in, host arrays out (H2D + solve + D2H in one C call).
+
+        Option ``retry_mu`` > 0 (default 0 = off): instances that did not succeed are
+        solved once more from the same start with ``mu_init = retry_mu`` (e.g. 1e-3).
+        A small initial barrier parameter keeps the iterates near an infeasible warm
+        start instead of pushing every slack to the centre first; it rescues the warm
+        starts that IPOPT leaves to its restoration phase."""
         X0 = np.ascontiguousarray(X0, dtype=np.float64).reshape(-1, self.n)
         B = X0.shape[0]
         P = np.ascontiguousarray(P, dtype=np.float64).reshape(B, self.n_par)
@@ -381,7 +389,23 @@ class B200Solver(object):
             ubg.ctypes.data, shared, lam0.ctypes.data if lam0 is not None else None,
             X.ctypes.data, LAM.ctypes.data, F.ctypes.data, status.ctypes.data,
             iters.ctypes.data))
-        return {'x': X, 'lam_g': LAM, 'f': F, 'status': status, 'iters': iters}
+        res = {'x': X, 'lam_g': LAM, 'f': F, 'status': status, 'iters': iters}
+        mu_r = getattr(self, '_retry_mu', 0.)
+        if _retry and mu_r > 0. and (status != 0).any():
+            idx = np.nonzero(status != 0)[0]
+            mu_old = self._opt.mu_init
+            self.set_options({'mu_init': mu_r})
+            try:
+                r2 = self.solve_batch(X0[idx], P[idx], lbg if shared else lbg[idx],
+                                      ubg if shared else ubg[idx],
+                                      None if lam0 is None else lam0[idx], _retry=False)
+            finally:
+                self.set_options({'mu_init': mu_old})
+            ok = r2['status'] == 0
+            for key in ('x', 'lam_g', 'f', 'status'):
+                res[key][idx[ok]] = r2[key][ok]
+            res['iters'][idx] += r2['iters']
+        return res
 
     def solve_batch_device(self, X0, P, LBG, UBG, X, LAM, F, STATUS, ITERS,
                            lam_g0=None, stream=None):

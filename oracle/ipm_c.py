@@ -38,7 +38,9 @@ def solve_batch_full(tb, X0, P, threads=0, options=None, lbg=None, ubg=None,
     T, keep = pack_tables(tb)
     opt = _Options()
     lib.oracle_default_options(C.byref(opt))
-    for k, v in (options or {}).items():
+    options = dict(options or {})
+    retry_mu = float(options.pop('retry_mu', 0.))     # host-level retry, as B200Solver.solve_batch
+    for k, v in options.items():
         setattr(opt, k, v)
     X0 = np.ascontiguousarray(X0, dtype=np.float64).reshape(-1, tb.n)
     B = X0.shape[0]
@@ -58,4 +60,16 @@ def solve_batch_full(tb, X0, P, threads=0, options=None, lbg=None, ubg=None,
                            X.ctypes.data, LAM.ctypes.data, F.ctypes.data,
                            st.ctypes.data, it.ctypes.data, int(threads))
     del keep
-    return {'x': X, 'lam_g': LAM, 'f': F, 'status': st, 'iters': it}
+    res = {'x': X, 'lam_g': LAM, 'f': F, 'status': st, 'iters': it}
+    if retry_mu > 0. and (st != 0).any():
+        idx = np.nonzero(st != 0)[0]
+        opts2 = dict(options)
+        opts2['mu_init'] = retry_mu
+        r2 = solve_batch_full(tb, X0[idx], P[idx], threads, opts2,
+                              lb if shared else lb[idx], ub if shared else ub[idx],
+                              None if lam0 is None else lam0[idx])
+        ok = r2['status'] == 0
+        for key in ('x', 'lam_g', 'f', 'status'):
+            res[key][idx[ok]] = r2[key][ok]
+        res['iters'][idx] += r2['iters']
+    return res

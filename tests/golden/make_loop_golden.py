@@ -135,14 +135,14 @@ class OracleSolver(object):
     """The solver object behind ``self.problem(x0=, p=, lbg=, ubg=)``: this repository's
     lowered tables + CPU oracle; records what it is given and what it returns."""
 
-    def __init__(self, tables):
+    def __init__(self, tables, options=None):
         from oracle import ipm_c
-        self.tb, self.ipm_c, self.calls = tables, ipm_c, []
+        self.tb, self.ipm_c, self.calls, self.options = tables, ipm_c, [], options
 
     def __call__(self, x0, p, lbg, ubg, **kw):
         x0, p, lbg, ubg = [np.asarray(v, dtype=float).reshape(-1).copy() for v in (x0, p, lbg, ubg)]
         r = self.ipm_c.solve_batch_full(self.tb, x0[None], p[None], threads=1,
-                                        lbg=lbg[None], ubg=ubg[None])
+                                        options=self.options, lbg=lbg[None], ubg=ubg[None])
         self.last = r
         self.calls.append((x0, p, lbg, ubg, r['x'][0].copy(), int(r['status'][0])))
         return {'x': r['x'][0], 'lam_g': r['lam_g'][0], 'f': r['f'][0]}
@@ -152,7 +152,7 @@ class OracleSolver(object):
                 else 'Restoration_Failed', 'iter_count': int(self.last['iters'][0])}
 
 
-def run_reference_loop(name, n_steps, update_time, sample_time=0.01):
+def run_reference_loop(name, n_steps, update_time, sample_time=0.01, solver_options=None):
     from omg_tools_b200 import scenarios as sc
     tables = getattr(sc, name)(build_solver=False).father.tables
     opt = mg.ref_import('basics.optilayer')
@@ -164,7 +164,7 @@ def run_reference_loop(name, n_steps, update_time, sample_time=0.01):
     for vehicle in problem.vehicles:            # this framework implements the ideal case
         vehicle.set_options({'ideal_prediction': True, 'ideal_update': True})
         vehicle.problem = problem               # as examples/p2p_3dquadrotor.py:47 does
-    solver = OracleSolver(tables)
+    solver = OracleSolver(tables, solver_options)
     problem.problem, _ = problem.father.construct_problem(problem.options, problem=solver)
     problem.father.init_transformations(problem.init_primal_transform,
                                         problem.init_dual_transform)
@@ -196,6 +196,10 @@ def main():
         for key, val in res.items():
             out['%s_%s' % (name, key)] = val
         out[name + '_dt'] = dt
+    # config 4 with the reference's unshifted slacks, the solver's retry option on
+    res = run_reference_loop('config4', 13, 0.4, solver_options={'retry_mu': 1e-3})
+    print('config4 + retry_mu', 'status', res['status'], 'final state', np.round(res['state'][:3], 4))
+    out['config4_retry_status'], out['config4_retry_state'] = res['status'], res['state']
     np.savez_compressed(OUT, **out)
     print('wrote', OUT)
 

@@ -617,3 +617,24 @@ def test_dubins_matches_oracle():
     err = np.abs(res['x'] - ref['x'])[ok][:, :26].max(axis=1)       # v~ and tan(theta/2) splines
     assert np.median(err) < NORTH_STAR_TOL
     assert np.abs(res['f'] - ref['f'])[ok].max() < 1e-3
+
+
+@pytest.mark.gpu
+def test_retry_mu_option_on_the_references_quadrotor_warm_start():
+    """Solver option ``retry_mu`` (host level, solver/b200.py): the infeasible warm start
+    the reference's Quadrotor3D loop produces at a knot crossing (loop_golden.npz) fails
+    by default and converges with the retry, to the oracle's point."""
+    L = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'loop_golden.npz'))
+    pr = sc.config4()
+    tb = pr.father.tables
+    X0 = np.vstack([L['config4_x0'][2], L['config4_x0'][0]])
+    P = np.vstack([L['config4_p'][2], L['config4_p'][0]])
+    plain = pr.problem.solve_batch(X0, P)
+    assert plain['status'][0] != 0 and plain['status'][1] == 0
+    pr.problem.set_options({'retry_mu': 1e-3})
+    res = pr.problem.solve_batch(X0, P)
+    ref = ipm_c.solve_batch_full(tb, X0, P, threads=2, options={'retry_mu': 1e-3})
+    assert np.array_equal(res['status'], [0, 0]) and np.array_equal(ref['status'], [0, 0])
+    assert np.abs(res['f'] - ref['f']).max() < 1e-4
+    assert np.abs(res['x'][1] - plain['x'][1]).max() == 0.0        # untouched instance
+    assert np.abs(res['x'] - ref['x'])[:, :78].max() < 5e-3

@@ -232,3 +232,29 @@ def test_c_oracle_equals_numpy_oracle_on_nonconvex_models(name):
     assert np.abs(rc['x'][0] - rn.x)[:26].max() < 1e-4
     assert np.abs(rc['x'][0] - rn.x).max() < 1e-2
     assert abs(rc['f'][0] - rn.f) < 1e-6
+
+
+def test_retry_mu_rescues_the_references_quadrotor_warm_start():
+    """The reference does not shift Quadrotor3D's acceleration slacks at a knot crossing
+    and leaves the infeasible warm start to IPOPT's restoration phase.  tests/golden/
+    loop_golden.npz holds that warm start as produced by the reference's own loop.
+    Without a restoration phase the default solve fails; the opt-in ``retry_mu`` (second
+    attempt with a small initial barrier parameter) converges to the optimum a cold
+    start finds -- and with it the reference's unmodified loop flies to the goal."""
+    import os
+    from oracle import ipm_c
+    if not ipm_c.available():
+        pytest.skip('C oracle not built')
+    L = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'loop_golden.npz'))
+    pr = sc.config4(build_solver=False)
+    tb = pr.father.tables
+    x0, p = L['config4_x0'][2][None], L['config4_p'][2][None]
+    plain = ipm_c.solve_batch_full(tb, x0, p, threads=1)
+    retry = ipm_c.solve_batch_full(tb, x0, p, threads=1, options={'retry_mu': 1e-3})
+    assert plain['status'][0] != 0 and retry['status'][0] == 0
+    assert retry['iters'][0] > plain['iters'][0]              # both attempts are counted
+    g = TableEval(tb).g(retry['x'][0], TableEval(tb).tape(p[0]))
+    assert (g <= tb.ubg + 1e-4).all() and (g >= tb.lbg - 1e-4).all()
+    # the reference's loop around the solver with retry_mu (make_loop_golden.py)
+    assert (L['config4_retry_status'] == 0).all() and len(L['config4_retry_status']) == 13
+    assert np.abs(L['config4_retry_state'][:3] - [3., 2., 0.5]).max() < 1e-2
