@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define OMG_ABI_VERSION 5
+#define OMG_ABI_VERSION 6
 
 /* CSR list of polynomial terms per output slot:
  *   out[s] = sum_{t in [ptr[s],ptr[s+1])} coef[t] * V[cidx[t]]
@@ -50,7 +50,14 @@ extern "C" {
  *     J[s] += sum_{e in [jp_ptr[s],jp_ptr[s+1])} Jx[jp_a[e]] * Jx[jp_c[e]]
  *     mu_l  = sum_{e in [mu_ptr[l],mu_ptr[l+1])} lambda[mu_row[e]] * Jx[mu_slot[e]]
  * give the chain rule for the Jacobian and the multipliers of the mids' own
- * Hessians (W terms with lrow = m+1+l). */
+ * Hessians (W terms with lrow = m+1+l).  The coefficient of a mid in a row may
+ * depend on x (a hyperplane normal times an integrated position: Dubins, bicycle,
+ * AGV, trailer; dubins.py:235-251): the A slots are then functions of x and the
+ * W term list carries nnz_wx extra "cross" slots after its nnz_w regular ones,
+ *     X[l,k] = sum_i lambda_i d2 row_i / d mid_l d x_k ,
+ * whose contribution X^T C + C^T X to the Hessian is gathered per H position:
+ *     H[xq_h[e]] += fac * sum_{r in [xq_ptr[e],xq_ptr[e+1])} Wx[xq_w[r]] * Jx[xq_c[r]]
+ * with fac = 2 on the diagonal, 1 elsewhere (Wx = values of the cross slots). */
 typedef struct omg_termlist {
   int32_t n_out, n_terms, width;
   const int32_t* ptr;   /* [n_out+1] */
@@ -106,6 +113,12 @@ typedef struct omg_tables {
   const int32_t* kkt_diag;      /* [kkt_n] envelope offset of the diagonal */
   const int32_t* kkt_panel_ptr; /* [n_panels+1] */
   const int32_t* kkt_panel_rows;/* [n_panel_rows] */
+  /* cross-Hessian gather lists (see omg_termlist); nnz_wx = 0: unused.  W.n_out = nnz_w + nnz_wx */
+  int32_t nnz_wx, n_xq, n_xp;
+  const int32_t* xq_h;          /* [n_xq] H position */
+  const int32_t* xq_ptr;        /* [n_xq+1] */
+  const int32_t* xq_w;          /* [n_xp] cross slot (0-based within the cross slots) */
+  const int32_t* xq_c;          /* [n_xp] J slot of C = d mid / d x */
 } omg_tables;
 
 /* Interior-point options; defaults = the reference's IPOPT settings

@@ -273,10 +273,10 @@ def lower(var_ids, par_ids, rows, objective, lbg, ubg, order_hint=None):
     degree = max([len(xm) for sr in split_rows + [split_obj] for xm in sr] + [1])
     for sr in split_rows[:m]:
         for xm in sr:
-            if len(xm) > 1 and any(j > n for j in xm):
+            if sum(1 for j in xm if j > n) > 1:
                 raise NotImplementedError(
-                    'rows must be affine in intermediates with parameter-only '
-                    'coefficients')
+                    'rows must be affine in the intermediates (their coefficients '
+                    'may depend on x and p)')
 
     def coef_of(ppoly):
         return tape.v_of_ppoly(ppoly)
@@ -351,9 +351,15 @@ def lower(var_ids, par_ids, rows, objective, lbg, ubg, order_hint=None):
     for s, key in enumerate(allkeys):
         for c, cidx, red in jslots.get(key, ()):
             J.add(s, c, cidx, red)
-    wkeys = sorted(wslots)
-    W = TermList(len(wkeys), degree - 2, with_lrow=True)
-    for s, key in enumerate(wkeys):
+    # Hessian slots: [regular (j >= k, both variables) | cross (mid l, variable k)].
+    # A cross slot holds sum_i lam_i d2 row_i / d mid_l d x_k (rows whose mid
+    # coefficient depends on x, e.g. hyperplane normal times integrated position);
+    # its contribution to the Hessian is  X^T C + C^T X  (C = d mid / d x), added
+    # through the pair lists xq_* below.
+    wkeys = sorted(k for k in wslots if k[0] < n)
+    xkeys = sorted(k for k in wslots if k[0] > n)
+    W = TermList(len(wkeys) + len(xkeys), degree - 2, with_lrow=True)
+    for s, key in enumerate(wkeys + xkeys):
         for c, cidx, red, lrow in wslots[key]:
             W.add(s, c, cidx, red, lrow)
 
@@ -370,7 +376,16 @@ def lower(var_ids, par_ids, rows, objective, lbg, ubg, order_hint=None):
     tb.wrow = np.array([k[0] for k in wkeys], dtype=np.int32)
     tb.wcol = np.array([k[1] for k in wkeys], dtype=np.int32)
     tb.nnz_j, tb.nnz_w = len(jkeys), len(wkeys)
+    tb.nnz_wx = len(xkeys)
     tb.nnz_jx = len(allkeys)
+    # cross pairs: H[max(k,j), min(k,j)] += X[l,k] * C[l,j]  (twice on the diagonal)
+    xpairs = {}
+    for sx, (jm, k) in enumerate(xkeys):
+        l = jm - n - 1
+        for j in c_by_mid.get(l, ()):
+            key = (max(k, j), min(k, j))
+            xpairs.setdefault(key, []).append((sx, slot_of[(m + l, j)]))
+    tb._xpairs = xpairs
     # chain rule  J[s] += sum_l A[i,l] C[l,j]  and  mu_l = sum_i lam_i A[i,l]
     a_by_row = {}
     for (i, jm) in akeys:
@@ -415,6 +430,9 @@ def _build_kkt_pattern(tb):
     pos = {}
     for s in range(tb.nnz_w):
         pos.setdefault((int(tb.wrow[s]), int(tb.wcol[s])), [])
+    xpairs = getattr(tb, '_xpairs', {})
+    for key in xpairs:
+        pos.setdefault(key, [])
     for i in range(tb.m):
         lo, hi = int(tb.jrow_ptr[i]), int(tb.jrow_ptr[i + 1])
         for s1 in range(lo, hi):
@@ -441,6 +459,22 @@ def _build_kkt_pattern(tb):
     index = {k: q for q, k in enumerate(keys)}
     tb.w2h = np.array([index[(int(r), int(c))]
                        for r, c in zip(tb.wrow, tb.wcol)], dtype=np.int32)
+    # cross-Hessian gather lists: for the H positions xq_h[e] the pairs
+    # [xq_ptr[e], xq_ptr[e+1]) of (cross slot xq_w, Jacobian slot xq_c of C)
+    xq_h, xq_ptr, xq_w, xq_c = [], [0], [], []
+    for key in sorted(xpairs):
+        xq_h.append(index[key])
+        for sx, sc in xpairs[key]:
+            xq_w.append(sx)
+            xq_c.append(sc)
+        xq_ptr.append(len(xq_w))
+    tb.n_xq = len(xq_h)
+    tb.xq_h = np.array(xq_h, dtype=np.int32)
+    tb.xq_ptr = np.array(xq_ptr, dtype=np.int32)
+    tb.xq_w = np.array(xq_w, dtype=np.int32)
+    tb.xq_c = np.array(xq_c, dtype=np.int32)
+    if hasattr(tb, '_xpairs'):
+        del tb._xpairs
 
 
 # ---------------------------------------------------------------------------

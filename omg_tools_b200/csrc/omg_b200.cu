@@ -77,6 +77,10 @@ struct DevTab {
   int n_mid, nnz_jx, n_hq_heavy;
   const int2* midg; const int* jtptr; const int* jrow;
   const int *jp_ptr, *jp_a, *jp_c, *mu_ptr, *mu_row, *mu_slot;
+  // cross-Hessian slots (mid coefficient depends on x): wrec[nnz_w .. nnz_w+nnz_wx) hold the
+  // term ranges, xq the H positions that gather  fac * sum Wx[pair.x] * Jx[pair.y]
+  int nnz_wx, n_xq;
+  const HqRec* xq; const int2* xqp;
 };
 
 struct Smem {                      // offsets in doubles
@@ -84,7 +88,7 @@ struct Smem {                      // offsets in doubles
   int sgn, eptr, efirst, pptr, prow, pcmin;
   int arr[N_ARR];                  // >= 0: shared offset; < 0: -(scratch offset + 1)
   int LDP, total;
-  int Kg, Vg, jxg, mug, Kcg;       // XL kernel: scratch offsets (K only if S.K < 0)
+  int Kg, Vg, jxg, mug, Kcg, wxg;  // XL kernel: scratch offsets (K only if S.K < 0)
 };
 
 struct Batch {
@@ -470,6 +474,7 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
   double* V = XL ? Dx + S.Vg : sm + S.V;
   double* jx = XL ? Dx + S.jxg - T.nnz_j : nullptr;   // indexed by slot id >= nnz_j
   double* mu_mid = XL ? Dx + S.mug : nullptr;
+  double* wx = XL ? Dx + S.wxg : nullptr;        // values of the cross-Hessian slots
   double* Kc = Dx + S.Kcg;
   const int n_xe = T.n + 1 + (XL ? T.n_mid : 0);
   double* red = sm + S.red;
@@ -815,7 +820,7 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
         // Lagrangian Hessian W (lambda = y*dsc, objective factor fsc)
         if (XL) {   // slots differ widely in term count: one warp per slot
           const int lane = tid & 31;
-          for (int q = tid >> 5; q < T.nnz_w; q += NWARP) {
+          for (int q = tid >> 5; q < T.nnz_w + T.nnz_wx; q += NWARP) {
             const WRec w = T.wrec[q];
             double acc = 0.0;
             for (int t = w.t0 + lane; t < w.t1; t += 32) {
@@ -826,7 +831,16 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(FULL, acc, o);
-            if (lane == 0) K[w.dst] += acc;
+            if (lane == 0) { if (q < T.nnz_w) K[w.dst] += acc; else wx[w.dst] = acc; }
+          }
+          if (T.nnz_wx) {   // cross terms X^T C + C^T X, one thread per H position (deterministic)
+            __syncthreads();
+            for (int e = tid; e < T.n_xq; e += NT) {
+              const HqRec h = T.xq[e];
+              double acc = 0.0;
+              for (int r = h.p0; r < h.p1; ++r) { const int2 pr = T.xqp[r]; acc += wx[pr.x] * jx[pr.y]; }
+              K[h.dst] += h.diag ? 2.0 * acc : acc;
+            }
           }
         } else
         for (int q = tid; q < T.nnz_w; q += NT) {
@@ -1441,6 +1455,7 @@ const TabField kTabFields[] = {
   TF_S(kkt_n), TF_S(kkt_n_eq), TF_S(env_size), TF_S(n_panel_rows), TF_S(max_panel_rows),
   TF_I(kkt_eq_rows), TF_I(kkt_pos_var), TF_I(kkt_pos_eq), TF_I(kkt_sign), TF_I(env_first), TF_I(env_ptr),
   TF_I(kkt_hdst), TF_I(kkt_jdst), TF_I(kkt_diag), TF_I(kkt_panel_ptr), TF_I(kkt_panel_rows),
+  TF_S(nnz_wx), TF_S(n_xq), TF_S(n_xp), TF_I(xq_h), TF_I(xq_ptr), TF_I(xq_w), TF_I(xq_c),
 };
 struct OwnedTables { omg_tables T; std::vector<void*> blocks; };
 }  // namespace
@@ -1623,12 +1638,33 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
     T.hq = upload(h, hq.data(), hq.size(), &ok);
     T.hpack = upload(h, pack.data(), pack.size(), &ok);
   }
-  {  // Hessian slots: destination in the envelope + term range
-    std::vector<WRec> wr(tb->nnz_w > 0 ? tb->nnz_w : 1);
-    for (int q = 0; q < tb->nnz_w; ++q) {
-      wr[q].dst = tb->kkt_hdst[tb->w2h[q]]; wr[q].t0 = tb->W.ptr[q]; wr[q].t1 = tb->W.ptr[q + 1]; wr[q].pad = 0;
+  const int nnz_wx = n_mid ? tb->nnz_wx : 0;
+  T.nnz_wx = nnz_wx; T.n_xq = nnz_wx ? tb->n_xq : 0;
+  if (tb->W.n_out != tb->nnz_w + nnz_wx) { set_err("W term list does not match nnz_w + nnz_wx"); ok = false; }
+  if (ok) {  // Hessian slots: destination in the envelope (cross slots: index into Wx) + term range
+    std::vector<WRec> wr(tb->nnz_w + nnz_wx > 0 ? tb->nnz_w + nnz_wx : 1);
+    for (int q = 0; q < tb->nnz_w + nnz_wx; ++q) {
+      wr[q].dst = (q < tb->nnz_w) ? tb->kkt_hdst[tb->w2h[q]] : q - tb->nnz_w;
+      wr[q].t0 = tb->W.ptr[q]; wr[q].t1 = tb->W.ptr[q + 1]; wr[q].pad = 0;
     }
     T.wrec = upload(h, wr.data(), wr.size(), &ok);
+  }
+  if (ok && nnz_wx) {  // cross-Hessian gather records
+    std::vector<HqRec> xq(T.n_xq > 0 ? T.n_xq : 1);
+    std::vector<int2> xp(tb->n_xp > 0 ? tb->n_xp : 1);
+    for (int e = 0; e < T.n_xq && ok; ++e) {
+      const int q = tb->xq_h[e];
+      if (q < 0 || q >= tb->nnz_h) { set_err("cross-Hessian position out of range"); ok = false; break; }
+      xq[e].dst = tb->kkt_hdst[q]; xq[e].p0 = tb->xq_ptr[e]; xq[e].p1 = tb->xq_ptr[e + 1];
+      xq[e].diag = (tb->hrow[q] == tb->hcol[q]) ? 1 : 0;
+    }
+    for (int r = 0; r < tb->n_xp && ok; ++r) {
+      if (tb->xq_w[r] < 0 || tb->xq_w[r] >= nnz_wx || tb->xq_c[r] < tb->nnz_j || tb->xq_c[r] >= tb->nnz_jx) {
+        set_err("cross-Hessian pair out of range"); ok = false; break; }
+      xp[r] = make_int2(tb->xq_w[r], tb->xq_c[r]);
+    }
+    T.xq = upload(h, xq.data(), xq.size(), &ok);
+    T.xqp = upload(h, xp.data(), xp.size(), &ok);
   }
   T.eq_rows = upload(h, tb->kkt_eq_rows, tb->kkt_n_eq, &ok);
   T.pos_var = upload(h, tb->kkt_pos_var, n, &ok);
@@ -1712,12 +1748,13 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
     set_err(buf); ok = false;
   }
   int goff = 0;   // global scratch offset (doubles)
-  S.Kg = S.Vg = S.jxg = S.mug = S.Kcg = 0;
+  S.Kg = S.Vg = S.jxg = S.mug = S.Kcg = S.wxg = 0;
   if (h->xl) {
     auto gtake = [&](int cnt) { int o = goff; goff += (cnt + 1) & ~1; return o; };
     S.Vg = gtake(T.n_v);
     S.jxg = gtake(T.nnz_jx - T.nnz_j + 1);
     S.mug = gtake(n_mid + 1);
+    S.wxg = gtake(T.nnz_wx + 1);
     if (!k_in_smem) S.Kg = gtake(T.env_size + 2);
   }
   S.Kcg = goff; goff += (T.env_size + 2 + 1) & ~1;

@@ -157,13 +157,18 @@ def config_quadrotor2d(options=None, build_solver=True):
     return _p2p(vehicle, environment, opts, build_solver)
 
 
-def config_dubins(options=None, build_solver=True):
+def config_dubins(options=None, build_solver=True, substitution=True, exact=False,
+                  shape=None, knot_intervals=None):
     """examples/p2p_dubins.py with a fixed end time: Dubins(vmax 0.7, |w| <= pi/3,
-    substitution), Square(5) room centred at (1.5, 1.5), one Circle(0.5) obstacle
-    drifting in x; horizon 10 s."""
+    substitution as in the example; substitution=False is the vehicle's default
+    formulation, dubins.py:63), Square(5) room centred at (1.5, 1.5), one Circle(0.5)
+    obstacle drifting in x; horizon 10 s."""
     from . import Dubins
-    vehicle = Dubins(bounds={'vmax': 0.7, 'wmax': np.pi / 3., 'wmin': -np.pi / 3.},
-                     options={'substitution': True})
+    vehicle = Dubins(shapes=shape,
+                     bounds={'vmax': 0.7, 'wmax': np.pi / 3., 'wmin': -np.pi / 3.},
+                     options={'substitution': substitution, 'exact_substitution': exact})
+    if knot_intervals is not None:
+        vehicle.define_knots(knot_intervals=knot_intervals)
     vehicle.set_initial_conditions([0., 0., 0.])
     vehicle.set_terminal_conditions([3., 3., 0.])
     environment = Environment(room={'shape': Square(5.), 'position': [1.5, 1.5]})
@@ -171,6 +176,27 @@ def config_dubins(options=None, build_solver=True):
     environment.add_obstacle(Obstacle({'position': [1., 1.]}, shape=Circle(0.5),
                                       simulation={'trajectories': trajectories}))
     return _p2p(vehicle, environment, options, build_solver)
+
+
+def config_dubins_plain(options=None, build_solver=True):
+    """The Dubins vehicle's default formulation (substitution=False, dubins.py:63): the
+    integrated position enters the terminal and collision rows directly."""
+    return config_dubins(options, build_solver, substitution=False)
+
+
+def config_dubins_rect(options=None, build_solver=True):
+    """Dubins with a rectangular shape, default formulation: the heading tan(theta/2)
+    enters the collision rows (vehicle.py:122-177 with tg_ha), degree-4 rows with an
+    intermediate factor."""
+    from . import Rectangle
+    return config_dubins(options, build_solver, substitution=False,
+                         shape=Rectangle(width=0.4, height=0.2), knot_intervals=5)
+
+
+def config_dubins_exact(options=None, build_solver=True):
+    """Dubins with exact_substitution: dx, dy on the product basis, equality rows."""
+    return config_dubins(options, build_solver, substitution=True, exact=True,
+                         knot_intervals=5)
 
 
 def config_freeT(options=None, build_solver=True, moving=False):

@@ -24,7 +24,7 @@ STATUS_STRINGS = {
     2: 'Restoration_Failed', 3: 'Error_In_Step_Computation',
     4: 'Invalid_Number_Detected', 5: 'Infeasible_Problem_Detected'}
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _i32p = C.POINTER(C.c_int32)
 _f64p = C.POINTER(C.c_double)
@@ -60,7 +60,9 @@ class _Tables(C.Structure):
         ('kkt_eq_rows', _i32p), ('kkt_pos_var', _i32p), ('kkt_pos_eq', _i32p),
         ('kkt_sign', _i32p), ('env_first', _i32p), ('env_ptr', _i32p),
         ('kkt_hdst', _i32p), ('kkt_jdst', _i32p), ('kkt_diag', _i32p),
-        ('kkt_panel_ptr', _i32p), ('kkt_panel_rows', _i32p)]
+        ('kkt_panel_ptr', _i32p), ('kkt_panel_rows', _i32p),
+        ('nnz_wx', C.c_int32), ('n_xq', C.c_int32), ('n_xp', C.c_int32),
+        ('xq_h', _i32p), ('xq_ptr', _i32p), ('xq_w', _i32p), ('xq_c', _i32p)]
 
 
 class _Options(C.Structure):
@@ -194,6 +196,11 @@ def pack_tables(tb):
     T.kkt_diag = keep.i32(tb.kkt_diag)
     T.kkt_panel_ptr = keep.i32(tb.kkt_panel_ptr)
     T.kkt_panel_rows = keep.i32(tb.kkt_panel_rows)
+    T.nnz_wx = getattr(tb, 'nnz_wx', 0)
+    if T.nnz_wx:
+        T.n_xq, T.n_xp = tb.n_xq, len(tb.xq_w)
+        T.xq_h, T.xq_ptr = keep.i32(tb.xq_h), keep.i32(tb.xq_ptr)
+        T.xq_w, T.xq_c = keep.i32(tb.xq_w), keep.i32(tb.xq_c)
     return T, keep
 
 
@@ -251,6 +258,11 @@ def _table_records(tb):
     for f in ('kkt_eq_rows', 'kkt_pos_var', 'kkt_pos_eq', 'kkt_sign', 'env_first', 'env_ptr',
               'kkt_hdst', 'kkt_jdst', 'kkt_diag', 'kkt_panel_ptr', 'kkt_panel_rows'):
         arr(f, getattr(tb, f), 0)
+    nnz_wx = getattr(tb, 'nnz_wx', 0)
+    scalar('nnz_wx', nnz_wx), scalar('n_xq', tb.n_xq if nnz_wx else 0)
+    scalar('n_xp', len(tb.xq_w) if nnz_wx else 0)
+    for f in ('xq_h', 'xq_ptr', 'xq_w', 'xq_c'):
+        arr(f, getattr(tb, f) if nnz_wx else empty, 0)
     del keep
     return rec
 

@@ -4,13 +4,15 @@ and tan(theta/2) as degree-3 splines (reference ``omgtools/vehicles/dubins.py``:
 guess 206-214, parameters 225-233, collision constraints 235-251, integrate_once
 253-259, signals 261-288).
 
-The position is the running integral of v~(1 - tg^2), 2 v~ tg re-anchored at t/T.  This
-framework supports the reference's ``substitution`` formulation (the example
-examples/p2p_dubins.py uses it): slack velocity splines dx, dy carry the position, and
-the band |int(dx) - int(v~(1-tg^2))| <= 1e-3 ties them to the flat outputs, its
-product-spline coefficients being shared intermediates (basics/poly.py).  Without
-substitution the collision rows multiply the integrated position by (1 + tg^2), i.e.
-they are not affine in the intermediates."""
+The position is the running integral of v~(1 - tg^2), 2 v~ tg re-anchored at t/T; the
+coefficients of these product splines are shared intermediates (basics/poly.py).  All three
+formulations of the reference are built: the default (no substitution: the integrated
+position enters the terminal and collision rows directly, so the hyperplane normal -- and
+(1 + tg^2) for a non-circular shape -- multiplies the intermediates: rows affine in them
+with x-dependent coefficients, lowering.py cross-Hessian slots), ``substitution`` (slack
+velocity splines dx, dy carry the position and the band |int(dx) - int(v~(1-tg^2))| <= 1e-3
+ties them to the flat outputs; examples/p2p_dubins.py) and ``exact_substitution`` (dx, dy on
+the product basis, tied by equality rows)."""
 import numpy as np
 
 from .vehicle import Vehicle
@@ -35,7 +37,7 @@ class Dubins(Vehicle):
 
     def set_default_options(self):
         Vehicle.set_default_options(self)
-        self.options.update({'stop_tol': 1.e-2, 'substitution': True,
+        self.options.update({'stop_tol': 1.e-2, 'substitution': False,
                              'exact_substitution': False})
 
     def init(self):
@@ -50,33 +52,51 @@ class Dubins(Vehicle):
             coeffs[k] = c
         return BSpline(spline.basis, coeffs)
 
+    def _flat_position(self, splines, horizon_time):
+        """x, y as running integrals of the flat-output products; the product-spline
+        coefficients are shared intermediates, created once per problem construction."""
+        key = (id(splines[0].coeffs), id(splines[1].coeffs))
+        if getattr(self, '_flat_key', None) != key:
+            v_til, tg_ha = splines
+            dx = v_til * (1 - tg_ha**2)
+            dy = v_til * (2 * tg_ha)
+            self._flat_key = key
+            self._flat_hold = splines     # keeps the ids alive
+            self._flat_pos = (
+                self.integrate_once(self._shared('dx', dx), self.pos0[0], self.t, horizon_time),
+                self.integrate_once(self._shared('dy', dy), self.pos0[1], self.t, horizon_time))
+        return self._flat_pos
+
     def define_trajectory_constraints(self, splines, horizon_time):
-        if not self.options['substitution'] or self.options['exact_substitution']:
-            raise NotImplementedError(
-                'Dubins needs options substitution=True, exact_substitution=False here: '
-                'without the slack velocity splines the collision rows are not affine in '
-                'the shared intermediates')
         T = horizon_time
         v_til, tg_ha = splines
         dtg_ha = tg_ha.derivative()
         self.define_constraint(v_til * (1 + tg_ha**2) - self.vmax, -inf, 0.)
         self.define_constraint(-v_til, -inf, 0)          # forward driving only
-        dx = v_til * (1 - tg_ha**2)
-        dy = v_til * (2 * tg_ha)
-        degree = 3
-        knots = np.r_[np.zeros(degree), np.linspace(0., 1., 10 + 1), np.ones(degree)]
-        basis = BSplineBasis(knots, degree)
-        self.dx = self.define_spline_variable('dx', 1, 1, basis=basis)[0]
-        self.dy = self.define_spline_variable('dy', 1, 1, basis=basis)[0]
-        for name in ('dx', 'dy'):       # keep the warm start consistent (see quadrotor3d.py)
-            self._splines_prim[name]['shift'] = True
-        self.x = self.integrate_once(self.dx, self.pos0[0], self.t, T)
-        self.y = self.integrate_once(self.dy, self.pos0[1], self.t, T)
-        x = self.integrate_once(self._shared('dx', dx), self.pos0[0], self.t, T)
-        y = self.integrate_once(self._shared('dy', dy), self.pos0[1], self.t, T)
-        eps = 1e-3
-        self.define_constraint(self.x - x, -eps, eps)
-        self.define_constraint(self.y - y, -eps, eps)
+        if self.options['substitution']:
+            dx = v_til * (1 - tg_ha**2)
+            dy = v_til * (2 * tg_ha)
+            if self.options['exact_substitution']:
+                self.dx = self.define_spline_variable('dx', 1, 1, basis=dx.basis)[0]
+                self.dy = self.define_spline_variable('dy', 1, 1, basis=dy.basis)[0]
+                self.x = self.integrate_once(self.dx, self.pos0[0], self.t, T)
+                self.y = self.integrate_once(self.dy, self.pos0[1], self.t, T)
+                self.define_constraint(self.dx - dx, 0, 0)
+                self.define_constraint(self.dy - dy, 0, 0)
+            else:
+                degree = 3
+                knots = np.r_[np.zeros(degree), np.linspace(0., 1., 10 + 1), np.ones(degree)]
+                basis = BSplineBasis(knots, degree)
+                self.dx = self.define_spline_variable('dx', 1, 1, basis=basis)[0]
+                self.dy = self.define_spline_variable('dy', 1, 1, basis=basis)[0]
+                for name in ('dx', 'dy'):   # keep the warm start consistent (see quadrotor3d.py)
+                    self._splines_prim[name]['shift'] = True
+                self.x = self.integrate_once(self.dx, self.pos0[0], self.t, T)
+                self.y = self.integrate_once(self.dy, self.pos0[1], self.t, T)
+                x, y = self._flat_position(splines, T)
+                eps = 1e-3
+                self.define_constraint(self.x - x, -eps, eps)
+                self.define_constraint(self.y - y, -eps, eps)
         self.define_constraint(2 * dtg_ha - (1 + tg_ha**2) * T * self.wmax, -inf, 0.)
         self.define_constraint(-2 * dtg_ha + (1 + tg_ha**2) * T * self.wmin, -inf, 0.)
 
@@ -92,7 +112,11 @@ class Dubins(Vehicle):
         posT = self.define_parameter('posT', 2)
         tg_haT = self.define_parameter('tg_haT', 1)
         v_til, tg_ha = splines
-        term_con = [(self.x, posT[0]), (self.y, posT[1]), (tg_ha, tg_haT)]
+        if self.options['substitution']:
+            x, y = self.x, self.y
+        else:
+            x, y = self._flat_position(splines, horizon_time)
+        term_con = [(x, posT[0]), (y, posT[1]), (tg_ha, tg_haT)]
         term_con_der = [(v_til, 0.), (tg_ha.derivative(), 0.)]
         return [term_con, term_con_der]
 
@@ -133,10 +157,15 @@ class Dubins(Vehicle):
         return parameters
 
     def define_collision_constraints(self, hyperplanes, room, splines, horizon_time):
-        if not isinstance(self.shapes[0], Circle):
-            raise NotImplementedError('Dubins with a non-circular shape needs the heading '
-                                      'in the collision rows')
-        self.define_collision_constraints_2d(hyperplanes, room, [self.x, self.y], horizon_time)
+        if self.options['substitution']:
+            x, y = self.x, self.y
+        else:
+            x, y = self._flat_position(splines, horizon_time)
+        if isinstance(self.shapes[0], Circle):     # heading irrelevant for a disc
+            self.define_collision_constraints_2d(hyperplanes, room, [x, y], horizon_time)
+        else:
+            self.define_collision_constraints_2d(hyperplanes, room, [x, y], horizon_time,
+                                                 tg_ha=splines[1])
 
     def integrate_once(self, dx, x0, t, T=1.):
         """x(tau) with x(t/T) = x0 (reference dubins.py:253-259)."""

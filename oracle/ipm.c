@@ -148,7 +148,7 @@ typedef struct {
   double *V, *xe, *xt, *g, *s, *y, *zL, *zU, *dsc, *sL, *sU, *beq, *sig, *wv, *ds, *dy,
          *dzL, *dzU, *gt, *st, *jval, *gf, *K, *rhs, *rx, *d0, *sol;
   int *rt, *eqidx, *eqrow;
-  double *jx, *mu, *sol2, *sdyn;
+  double *jx, *mu, *sol2, *sdyn, *wx;
 } Work;
 
 static void* xalloc(size_t n) { return calloc(n ? n : 1, 1); }
@@ -158,6 +158,7 @@ static void work_alloc(Work* w, const omg_tables* T, int Nmax) {
   w->V = xalloc(sizeof(double) * T->n_v);
   w->xe = xalloc(sizeof(double) * (n + 1 + T->n_mid)); w->xt = xalloc(sizeof(double) * (n + 1 + T->n_mid));
   w->jx = xalloc(sizeof(double) * (T->n_mid ? T->nnz_jx : 1)); w->mu = xalloc(sizeof(double) * (T->n_mid + 1));
+  w->wx = xalloc(sizeof(double) * (T->nnz_wx + 1));
   w->sol2 = xalloc(sizeof(double) * (n + 1));
   w->sdyn = xalloc(sizeof(double) * Nmax);
   double** mv[] = {&w->g, &w->s, &w->y, &w->zL, &w->zU, &w->dsc, &w->sL, &w->sU, &w->beq,
@@ -174,7 +175,7 @@ static void work_alloc(Work* w, const omg_tables* T, int Nmax) {
 static void work_free(Work* w) {
   void* all[] = {w->V, w->xe, w->xt, w->g, w->s, w->y, w->zL, w->zU, w->dsc, w->sL, w->sU, w->beq,
                  w->sig, w->wv, w->ds, w->dy, w->dzL, w->dzU, w->gt, w->st, w->jval, w->gf, w->rx,
-                 w->K, w->rhs, w->d0, w->sol, w->rt, w->eqidx, w->eqrow, w->jx, w->mu, w->sol2, w->sdyn};
+                 w->K, w->rhs, w->d0, w->sol, w->rt, w->eqidx, w->eqrow, w->jx, w->mu, w->sol2, w->sdyn, w->wx};
   for (unsigned k = 0; k < sizeof(all) / sizeof(all[0]); ++k) free(all[k]);
 }
 
@@ -311,7 +312,7 @@ static void solve_one(const omg_tables* T, const omg_options* O, Work* w, const 
         { const int a = T->kkt_pos_var[T->hrow[q]], b = T->kkt_pos_var[T->hcol[q]];
           K[(a > b ? a : b) * N + (a > b ? b : a)] = acc; }
       }
-      for (int q = 0; q < T->nnz_w; ++q) {
+      for (int q = 0; q < T->nnz_w + T->nnz_wx; ++q) {
         double acc = 0.0; const omg_termlist* L = &T->W;
         for (int t = L->ptr[q]; t < L->ptr[q + 1]; ++t) {
           double v = L->coef[t] * V[L->cidx[t]];
@@ -320,7 +321,16 @@ static void solve_one(const omg_tables* T, const omg_options* O, Work* w, const 
           v *= (lr < m) ? (y[lr] * dsc[lr]) : (lr == m ? fsc : mu_mid[lr - m - 1]);
           acc += v;
         }
+        if (q >= T->nnz_w) { w->wx[q - T->nnz_w] = acc; continue; }   /* cross slot X[l,k] */
         const int h = T->w2h[q];
+        { const int a = T->kkt_pos_var[T->hrow[h]], b = T->kkt_pos_var[T->hcol[h]];
+          K[(a > b ? a : b) * N + (a > b ? b : a)] += acc; }
+      }
+      for (int e = 0; e < (T->nnz_wx ? T->n_xq : 0); ++e) {   /* X^T C + C^T X (include/omg_b200.h) */
+        double acc = 0.0;
+        for (int r = T->xq_ptr[e]; r < T->xq_ptr[e + 1]; ++r) acc += w->wx[T->xq_w[r]] * jx[T->xq_c[r]];
+        const int h = T->xq_h[e];
+        if (T->hrow[h] == T->hcol[h]) acc *= 2.0;
         { const int a = T->kkt_pos_var[T->hrow[h]], b = T->kkt_pos_var[T->hcol[h]];
           K[(a > b ? a : b) * N + (a > b ? b : a)] += acc; }
       }

@@ -54,7 +54,9 @@ class TableEval(object):
     mids are the pseudo-rows m.. of G.  Rows are affine in the mids, so
     J = J_direct + A C (A = d row/d mid, C = d mid/d x, both slots of the J
     term list) and the Lagrangian Hessian takes mu = A^T lam as the
-    multipliers of the pseudo-rows."""
+    multipliers of the pseudo-rows.  When A depends on x the W term list has
+    nnz_wx extra "cross" slots X[l,k] = sum_i lam_i d2 row_i/d mid_l d x_k and
+    the Hessian gains X^T C + C^T X through the pair lists xq_*."""
 
     def __init__(self, tb):
         self.tb = tb
@@ -111,11 +113,25 @@ class TableEval(object):
             lam_ext = np.r_[lam_ext, mu]
         return _eval_terms(tb.W, V, self._xe(x, V), lam_ext)
 
+    def hess_cross(self, x, V, wvals):
+        """(H position, value) of the cross contributions X^T C + C^T X."""
+        tb = self.tb
+        jv = self._jac_all(x, V)
+        prod = wvals[tb.nnz_w + tb.xq_w] * jv[tb.xq_c]
+        out = np.zeros(tb.n_xq)
+        np.add.at(out, np.repeat(np.arange(tb.n_xq), np.diff(tb.xq_ptr)), prod)
+        diag = tb.hrow[tb.xq_h] == tb.hcol[tb.xq_h]
+        return tb.xq_h, np.where(diag, 2.0, 1.0) * out
+
     def hess_dense(self, x, V, lam, obj_factor=1.0):
-        W = np.zeros((self.tb.n, self.tb.n))
+        tb = self.tb
+        W = np.zeros((tb.n, tb.n))
         vals = self.hess_vals(x, V, lam, obj_factor)
-        W[self.tb.wrow, self.tb.wcol] = vals
-        W[self.tb.wcol, self.tb.wrow] = vals
+        W[tb.wrow, tb.wcol] = vals[:tb.nnz_w]
+        if getattr(tb, 'nnz_wx', 0):
+            q, v = self.hess_cross(x, V, vals)
+            np.add.at(W, (tb.hrow[q], tb.hcol[q]), v)
+        W = W + np.tril(W, -1).T
         return W
 
 

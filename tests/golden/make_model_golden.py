@@ -306,10 +306,22 @@ def build_reference(name):
         environment.add_obstacle(obs.Obstacle({'position': [-0.6, -5.4]},
                                               shape=shp.Rectangle(width=0.2, height=12.)))
         options = {'horizon_time': 5}
-    elif name == 'config_dubins':
+    elif name in ('config_dubins', 'config_dubins_plain', 'config_dubins_rect',
+                  'config_dubins_exact'):
         db = ref_import('vehicles.dubins')
-        vehicle = db.Dubins(bounds={'vmax': 0.7, 'wmax': np.pi / 3., 'wmin': -np.pi / 3.},
-                            options={'substitution': True})
+        bounds = {'vmax': 0.7, 'wmax': np.pi / 3., 'wmin': -np.pi / 3.}
+        if name == 'config_dubins':
+            vehicle = db.Dubins(bounds=bounds, options={'substitution': True})
+        elif name == 'config_dubins_plain':
+            vehicle = db.Dubins(bounds=bounds, options={'substitution': False})
+        elif name == 'config_dubins_rect':
+            vehicle = db.Dubins(shapes=shp.Rectangle(width=0.4, height=0.2), bounds=bounds,
+                                options={'substitution': False})
+            vehicle.define_knots(knot_intervals=5)
+        else:
+            vehicle = db.Dubins(bounds=bounds, options={'substitution': True,
+                                                        'exact_substitution': True})
+            vehicle.define_knots(knot_intervals=5)
         vehicle.set_initial_conditions([0., 0., 0.])
         vehicle.set_terminal_conditions([3., 3., 0.])
         environment = env.Environment(room={'shape': shp.Square(5.), 'position': [1.5, 1.5]})
@@ -447,13 +459,19 @@ def shape_zoo(shp):
     }
 
 
-def main():
+BASE_NAMES = ('config1', 'config2', 'config4', 'config5', 'config_holonomic3d',
+              'config_quadrotor2d', 'config_dubins')
+# second fixture file (model_golden_ext.npz, `--ext`): formulations whose rows multiply the
+# intermediates by decision variables
+EXT_NAMES = ('config_dubins_plain', 'config_dubins_rect', 'config_dubins_exact')
+
+
+def main(ext=False):
     global REG
     install_stubs()
     out = {}
     n_samples = 3
-    for name in ('config1', 'config2', 'config4', 'config5', 'config_holonomic3d',
-                 'config_quadrotor2d', 'config_dubins'):
+    for name in (EXT_NAMES if ext else BASE_NAMES):
         Xs, Ps, Gs, Fs = [], [], [], []
         for k in range(n_samples):
             REG = Registry(seed=1000 * k + 7)
@@ -477,7 +495,7 @@ def main():
             out[name + '_traj_' + key] = val
         out[name + '_traj_keys'] = np.array(sorted(tr))
         t_host = 0.37
-        if name in ('config1', 'config4', 'config5', 'config_holonomic3d', 'config_dubins'):
+        if name in ('config1', 'config4', 'config5', 'config_holonomic3d', 'config_dubins') + EXT_NAMES:
             host = host_values(problem, par, var, t_host)
             out[name + '_obst'] = obstacle_motion(problem, 5.0)
             out[name + '_host_P'], out[name + '_host_X0'] = host
@@ -493,6 +511,11 @@ def main():
         out[name + '_lb'], out[name + '_ub'] = lb, ub
         out[name + '_var_layout'] = np.array(['%s|%s|%dx%d' % ((lab, nm) + v.a.shape) for lab, nm, v in var])
         out[name + '_par_layout'] = np.array(['%s|%s|%dx%d' % ((lab, nm) + v.a.shape) for lab, nm, v in par])
+    if ext:
+        path = OUT.replace('model_golden.npz', 'model_golden_ext.npz')
+        np.savez_compressed(path, **out)
+        print('wrote', path)
+        return
     # Fleet of the formation examples (vehicles/fleet.py: set_configuration, neighbours)
     hol, fl = ref_import('vehicles.holonomic'), ref_import('vehicles.fleet')
     shp = ref_import('basics.shape')
@@ -519,4 +542,4 @@ def main():
 
 
 if __name__ == '__main__':
-    main()
+    main(ext='--ext' in sys.argv)

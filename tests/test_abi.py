@@ -30,7 +30,7 @@ def test_exports_match_header(lib):
     assert set(names) == set(b200.EXPORTS)
     for name in names:
         assert hasattr(lib, name), name
-    assert lib.omg_abi_version() == 5
+    assert lib.omg_abi_version() == 6
 
 
 def test_default_options_are_the_reference_ipopt_settings(lib):
@@ -59,13 +59,14 @@ def test_no_cpu_fallback_without_device(lib):
 def test_table_file_round_trip(tmp_path):
     """save_tables -> omg_tables_read (host only): the deployable artefact for
     native callers reproduces every array of the lowered NLP, including the
-    intermediates of config 4."""
+    intermediates of config 4 and the cross-Hessian lists of the default Dubins
+    formulation."""
     import ctypes as C
     import numpy as np
     from omg_tools_b200 import scenarios as sc
     from omg_tools_b200.solver import b200
     lib = b200.load_library()
-    for builder in (sc.config1, sc.config4):
+    for builder in (sc.config1, sc.config4, sc.config_dubins_plain):
         tb = builder(build_solver=False).father.tables
         path = str(tmp_path / 'problem.omgtbl')
         b200.save_tables(tb, path)
@@ -87,6 +88,12 @@ def test_table_file_round_trip(tmp_path):
         if t.n_mid:
             assert np.array_equal(arr(t.jp_a, t.n_jp), tb.jp_a)
             assert np.array_equal(arr(t.mu_slot, t.n_mu), tb.mu_slot)
+        assert t.nnz_wx == getattr(tb, 'nnz_wx', 0) and t.W.n_out == t.nnz_w + t.nnz_wx
+        if t.nnz_wx:
+            assert np.array_equal(arr(t.xq_h, t.n_xq), tb.xq_h)
+            assert np.array_equal(arr(t.xq_ptr, t.n_xq + 1), tb.xq_ptr)
+            assert np.array_equal(arr(t.xq_w, t.n_xp), tb.xq_w)
+            assert np.array_equal(arr(t.xq_c, t.n_xp), tb.xq_c)
         lib.omg_tables_free(T)
     # a damaged file is refused with a message
     with open(path, 'r+b') as fp:

@@ -1,0 +1,45 @@
+"""GPU parity tests of kernel paths written after the round's GPU budget was spent: they
+have been compiled for sm_100a and checked line by line against the C oracle
+(oracle/ipm.c implements the same table semantics and passes the CPU tests), but have NOT
+run on a GPU yet.  They are non-strict xfail so that a first GPU run reports XPASS / XFAIL
+without masking the verified suite (this file sorts last); drop the marker once XPASS."""
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason='kernel path not yet run on a GPU '
+                                '(cross-Hessian slots of the XL kernel, ABI v6)')]
+
+from omg_tools_b200 import scenarios as sc
+from oracle import ipm_c
+
+NORTH_STAR_TOL = 1e-4
+
+
+def test_dubins_default_formulation_matches_oracle():
+    """Dubins without substitution (dubins.py:63, 235-251): rows affine in the shared
+    intermediates with x-dependent coefficients -> cross-Hessian slots X and the gather
+    X^T C + C^T X in the XL kernel (csrc/omg_b200.cu) vs oracle/ipm.c on 8 jittered
+    instances: same statuses, iteration counts within 2, flat-output splines within the
+    north-star tolerance."""
+    pr = sc.config_dubins_plain()
+    tb = pr.father.tables
+    assert tb.nnz_wx > 0
+    X0, P = sc.instance_data(pr, 8, jitter=0.1, seed=1)
+    res = pr.problem.solve_batch(X0, P)
+    ref = ipm_c.solve_batch_full(tb, X0, P, threads=8)
+    assert np.array_equal(res['status'], ref['status'])
+    ok = ref['status'] == 0
+    assert ok.sum() >= 7
+    assert np.abs(res['iters'] - ref['iters'])[ok].max() <= 2
+    err = np.abs(res['x'] - ref['x'])[ok][:, :26].max(axis=1)       # v~ and tan(theta/2) splines
+    assert np.median(err) < NORTH_STAR_TOL
+    assert np.abs(res['f'] - ref['f'])[ok].max() < 1e-3
+
+
+def test_dubins_default_formulation_problem_solve_dropin():
+    """The reference-facing call Problem.solve() on the same problem."""
+    pr = sc.config_dubins_plain()
+    pr.initialize(0.)
+    pr.solve(0., 0.5)
+    assert pr.problem.stats()['return_status'] == 'Solve_Succeeded'
