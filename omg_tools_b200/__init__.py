@@ -9,6 +9,7 @@ from .vehicles.vehicle import Vehicle
 from .vehicles.holonomic import Holonomic
 from .vehicles.holonomic3d import Holonomic3D
 from .vehicles.holonomic1d import Holonomic1D
+from .vehicles.holonomicorient import HolonomicOrient
 from .vehicles.quadrotor import Quadrotor
 from .vehicles.dubins import Dubins
 from .vehicles.quadrotor3d import Quadrotor3D

@@ -199,6 +199,25 @@ def config_dubins_exact(options=None, build_solver=True):
                          knot_intervals=5)
 
 
+def config_holonomic_orient(options=None, build_solver=True):
+    """examples/p2p_holonomic_orient.py with a fixed end time: HolonomicOrient
+    (Rectangle(0.2, 0.4), heading free, norm-1 regularisation of the heading rate),
+    Square(5) room, two Rectangle(3, 0.2) walls and a moving Circle(0.4)."""
+    from . import HolonomicOrient, Rectangle
+    vehicle = HolonomicOrient()
+    vehicle.set_options({'reg_type': 'norm_1', 'reg_weight': 10})
+    vehicle.set_initial_conditions([-1.5, -1.5, np.pi / 4.])
+    vehicle.set_terminal_conditions([2., 2., np.pi / 2.])
+    environment = Environment(room={'shape': Square(5.)})
+    rectangle = Rectangle(width=3., height=0.2)
+    environment.add_obstacle(Obstacle({'position': [-1.8, -0.5]}, shape=rectangle))
+    environment.add_obstacle(Obstacle({'position': [1.7, -0.5]}, shape=rectangle))
+    trajectories = {'velocity': {'time': [3., 4.], 'values': [[-0.15, 0.0], [0., 0.15]]}}
+    environment.add_obstacle(Obstacle({'position': [1.5, 0.5]}, shape=Circle(0.4),
+                                      simulation={'trajectories': trajectories}))
+    return _p2p(vehicle, environment, options, build_solver)
+
+
 def config_freeT(options=None, build_solver=True, moving=False):
     """Minimum-time variant of examples/p2p_holonomic.py (freeT=True, the
     example's commented alternative): two rectangular walls and a circle

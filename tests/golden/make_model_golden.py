@@ -329,6 +329,20 @@ def build_reference(name):
         environment.add_obstacle(obs.Obstacle({'position': [1., 1.]}, shape=shp.Circle(0.5),
                                               simulation={'trajectories': trajectories}))
         options = {}
+    elif name == 'config_holonomic_orient':
+        ho = ref_import('vehicles.holonomicorient')
+        vehicle = ho.HolonomicOrient()
+        vehicle.set_options({'reg_type': 'norm_1', 'reg_weight': 10})
+        vehicle.set_initial_conditions([-1.5, -1.5, np.pi / 4.])
+        vehicle.set_terminal_conditions([2., 2., np.pi / 2.])
+        environment = env.Environment(room={'shape': shp.Square(5.)})
+        rectangle = shp.Rectangle(width=3., height=0.2)
+        environment.add_obstacle(obs.Obstacle({'position': [-1.8, -0.5]}, shape=rectangle))
+        environment.add_obstacle(obs.Obstacle({'position': [1.7, -0.5]}, shape=rectangle))
+        trajectories = {'velocity': {'time': [3., 4.], 'values': [[-0.15, 0.0], [0., 0.15]]}}
+        environment.add_obstacle(obs.Obstacle({'position': [1.5, 0.5]}, shape=shp.Circle(0.4),
+                                              simulation={'trajectories': trajectories}))
+        options = {}
     else:
         raise ValueError(name)
     opts = {'verbose': 0}
@@ -463,7 +477,8 @@ BASE_NAMES = ('config1', 'config2', 'config4', 'config5', 'config_holonomic3d',
               'config_quadrotor2d', 'config_dubins')
 # second fixture file (model_golden_ext.npz, `--ext`): formulations whose rows multiply the
 # intermediates by decision variables
-EXT_NAMES = ('config_dubins_plain', 'config_dubins_rect', 'config_dubins_exact')
+EXT_NAMES = ('config_dubins_plain', 'config_dubins_rect', 'config_dubins_exact',
+             'config_holonomic_orient')
 
 
 def main(ext=False):

@@ -567,6 +567,27 @@ def test_dubins_exact_substitution_solves():
     assert (g <= tb.ubg + 1e-4).all() and (g >= tb.lbg - 1e-4).all()
 
 
+def test_holonomic_orient_solves():
+    """vehicles/holonomicorient.py (examples/p2p_holonomic_orient.py, fixed end time):
+    rectangular vehicle with free heading, degree-4 collision rows; the oracle converges to a
+    feasible trajectory that ends at the goal pose."""
+    from oracle import ipm_c
+    if not ipm_c.available():
+        pytest.skip('C oracle not built')
+    pr = sc.config_holonomic_orient(build_solver=False)
+    tb = pr.father.tables
+    assert (tb.n, tb.m, tb.n_par, tb.degree, tb.n_mid) == (189, 3035, 56, 4, 0)
+    X0, P = sc.instance_data(pr, 1)
+    r = ipm_c.solve_batch_full(tb, X0, P, threads=1)
+    assert r['status'][0] == 0
+    ev = TableEval(tb)
+    g = ev.g(r['x'][0], ev.tape(P[0]))
+    assert (g <= tb.ubg + 1e-4).all() and (g >= tb.lbg - 1e-4).all()
+    x = r['x'][0]
+    assert abs(x[12] - 2.) < 1e-2 and abs(x[25] - 2.) < 1e-2          # terminal position
+    assert abs(x[38] - np.tan(np.pi / 4.)) < 1e-2                     # terminal tan(theta/2)
+
+
 def test_more_reference_examples_lower_and_solve():
     """examples/p2p_holonomic_octroom.py (octagonal room -> half-plane room rows)
     and a Holonomic with Euclidean (norm_2) velocity/acceleration limits: tables
@@ -621,7 +642,8 @@ def test_more_reference_examples_lower_and_solve():
     assert speed.max() < 0.6 + 1e-3
 
 
-EXT_GOLDEN = ('config_dubins_plain', 'config_dubins_rect', 'config_dubins_exact')
+EXT_GOLDEN = ('config_dubins_plain', 'config_dubins_rect', 'config_dubins_exact',
+              'config_holonomic_orient')
 
 
 def _model_golden(name):
@@ -667,7 +689,7 @@ def test_nlp_definition_equals_the_references_own_model_code(name):
 
 @pytest.mark.parametrize('name', ['config1', 'config4', 'config5', 'config_holonomic3d',
                                   'config_quadrotor2d', 'config_dubins', 'config_dubins_plain',
-                                  'config_dubins_rect'])
+                                  'config_dubins_rect', 'config_holonomic_orient'])
 def test_trajectory_extraction_equals_the_references(name):
     """Post-solve extraction: the reference's Vehicle.store ->
     concat_splines / splines2signals / sample_splines, run from /root/reference on a
