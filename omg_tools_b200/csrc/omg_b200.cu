@@ -33,6 +33,14 @@
 
 #include "../../include/omg_b200.h"
 
+// The same source also builds with g++ as a functional CPU emulation of the kernels
+// (tools/cpu_emu: its cuda_runtime.h stand-in defines OMG_CPU_EMU and these two macros;
+// test infrastructure for a GPU-less container, never loaded by the product).
+#ifndef OMG_CPU_EMU
+#define OMG_DYN_SHARED(name) extern __shared__ double name[]
+#define OMG_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
 #define NT ((int)blockDim.x)   // threads per block: 512 (1 block/SM) or 256 (2 blocks/SM)
 #define NWARP (NT / 32)
 #define MAX_NT 512
@@ -197,7 +205,7 @@ __device__ __forceinline__ bool cmp_le(double lhs, double rhs, double base) {
   return lhs - rhs <= 10.0 * DBL_EPS * fabs(base);
 }
 
-extern __shared__ double sm[];
+OMG_DYN_SHARED(sm);
 
 // shared-memory copies of the KKT structure arrays, addressed from the block's
 // dynamic shared array so the compiler emits LDS (not generic loads)
@@ -1199,7 +1207,7 @@ omg_ipm_kernel_xl_2cta(const DevTab T, const omg_options O, const Batch A, const
 __global__ void omg_shift_kernel(double* x, int B, int n, int n_blocks, const int* offs,
                                  const int* lens, const int* ncols, const int* toffs,
                                  const double* Tm) {
-  extern __shared__ double xs[];
+  OMG_DYN_SHARED(xs);
   const int b = blockIdx.x;
   if (b >= B) return;
   double* xb = x + (size_t)b * n;
@@ -1272,7 +1280,7 @@ __global__ void omg_sample_kernel(const double* __restrict__ x, int B, int n, in
                                   const int* __restrict__ ncols, const int* __restrict__ nsamp,
                                   const int* __restrict__ soffs, const int* __restrict__ ooffs,
                                   const double* __restrict__ Sm, double* __restrict__ out, int n_out) {
-  extern __shared__ double xs[];
+  OMG_DYN_SHARED(xs);
   const int b = blockIdx.x;
   if (b >= B) return;
   const double* xb = x + (size_t)b * n;
@@ -1307,7 +1315,7 @@ __global__ void omg_admm_zl_kernel(int nsh, int nn, int L, const double* __restr
                                    double* __restrict__ z_i, double* __restrict__ z_ij,
                                    double* __restrict__ l_i, double* __restrict__ l_ij,
                                    double* __restrict__ res) {
-  extern __shared__ double sh[];
+  OMG_DYN_SHARED(sh);
   const int nz = nsh * (1 + nn);
   double* xs = sh;            // x  (own, neighbours)      [nz]
   double* ls = xs + nz;       // l                          [nz]
@@ -1842,10 +1850,10 @@ int omg_solve_batch(omg_problem* h, int32_t B, const double* x0, const double* p
   A.counter = h->counter; A.trace = h->trace;
   CK(cudaMemsetAsync(h->counter, 0, sizeof(int), stream));
   CK(cudaEventRecord(h->ev0, stream));
-  if (h->xl && h->target_ctas == 1) omg_ipm_kernel_xl<<<grid, 512, h->smem_bytes, stream>>>(h->T, h->opt, A, h->S);
-  else if (h->xl) omg_ipm_kernel_xl_2cta<<<grid, 256, h->smem_bytes, stream>>>(h->T, h->opt, A, h->S);
-  else if (h->target_ctas == 1) omg_ipm_kernel<<<grid, 512, h->smem_bytes, stream>>>(h->T, h->opt, A, h->S);
-  else omg_ipm_kernel_2cta<<<grid, 256, h->smem_bytes, stream>>>(h->T, h->opt, A, h->S);
+  if (h->xl && h->target_ctas == 1) OMG_LAUNCH(omg_ipm_kernel_xl, grid, 512, h->smem_bytes, stream, h->T, h->opt, A, h->S);
+  else if (h->xl) OMG_LAUNCH(omg_ipm_kernel_xl_2cta, grid, 256, h->smem_bytes, stream, h->T, h->opt, A, h->S);
+  else if (h->target_ctas == 1) OMG_LAUNCH(omg_ipm_kernel, grid, 512, h->smem_bytes, stream, h->T, h->opt, A, h->S);
+  else OMG_LAUNCH(omg_ipm_kernel_2cta, grid, 256, h->smem_bytes, stream, h->T, h->opt, A, h->S);
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->ev1, stream));
   h->timed = true; h->launches = 1;
@@ -1928,7 +1936,7 @@ int omg_shift_batch(omg_problem* h, int32_t B, double* x, int32_t n_blocks, cons
   CK(cudaMemcpyAsync(d_i + 2 * n_blocks, ncols, sizeof(int) * n_blocks, cudaMemcpyHostToDevice, stream));
   CK(cudaMemcpyAsync(d_i + 3 * n_blocks, toffs.data(), sizeof(int) * n_blocks, cudaMemcpyHostToDevice, stream));
   CK(cudaMemcpyAsync(d_T, Tm, sizeof(double) * tot, cudaMemcpyHostToDevice, stream));
-  omg_shift_kernel<<<B, 128, sizeof(double) * h->T.n, stream>>>(x, B, h->T.n, n_blocks, d_i, d_i + n_blocks,
+  OMG_LAUNCH(omg_shift_kernel, B, 128, sizeof(double) * h->T.n, stream, x, B, h->T.n, n_blocks, d_i, d_i + n_blocks,
                                                                d_i + 2 * n_blocks, d_i + 3 * n_blocks, d_T);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(stream));
@@ -1952,7 +1960,7 @@ int omg_sample_batch(int32_t B, int32_t n, const double* x, int32_t n_blocks, co
   for (int k = 0; k < 6; ++k)
     CK(cudaMemcpyAsync(d_i + k * n_blocks, hosts[k], sizeof(int) * n_blocks, cudaMemcpyHostToDevice, stream));
   CK(cudaMemcpyAsync(d_S, Sm, sizeof(double) * stot, cudaMemcpyHostToDevice, stream));
-  omg_sample_kernel<<<B, 128, sizeof(double) * n, stream>>>(x, B, n, n_blocks, d_i, d_i + n_blocks, d_i + 2 * n_blocks,
+  OMG_LAUNCH(omg_sample_kernel, B, 128, sizeof(double) * n, stream, x, B, n, n_blocks, d_i, d_i + n_blocks, d_i + 2 * n_blocks,
                                                            d_i + 3 * n_blocks, d_i + 4 * n_blocks, d_i + 5 * n_blocks,
                                                            d_S, out, otot);
   CK(cudaGetLastError());
@@ -1969,7 +1977,7 @@ int omg_integrate_rk4(int32_t model, int32_t B, int32_t n_state, int32_t n_input
   if (model < 0 || model > 2 || n_state < 1 || n_state > OMG_ODE_MAX_STATE || steps < 0 ||
       n_state != want_s[model] || n_input != want_i[model]) { set_err("bad vehicle model / sizes"); return -1; }
   cudaStream_t stream = (cudaStream_t)stream_;
-  omg_rk4_kernel<<<(B + 127) / 128, 128, 0, stream>>>(model, B, n_state, n_input, state0, inputs, sample_time, steps, stateT);
+  OMG_LAUNCH(omg_rk4_kernel, (B + 127) / 128, 128, 0, stream, model, B, n_state, n_input, state0, inputs, sample_time, steps, stateT);
   CK(cudaGetLastError());
   return 0;
 }
@@ -1984,7 +1992,7 @@ int omg_admm_zl_update(int32_t n_agents, int32_t nsh, int32_t n_nghb, int32_t L,
   int nt = 32; while (nt < nz) nt <<= 1;
   if (nt > 1024 || nsh % L != 0) { set_err("unsupported consensus block size"); return -1; }
   const size_t smem = sizeof(double) * (5 * (size_t)nz + 64);
-  omg_admm_zl_kernel<<<n_agents, nt, smem, (cudaStream_t)stream_>>>(nsh, n_nghb, L, PzT, c, Tf, Tb, rho,
+  OMG_LAUNCH(omg_admm_zl_kernel, n_agents, nt, smem, (cudaStream_t)stream_, nsh, n_nghb, L, PzT, c, Tf, Tb, rho,
                                                                    x_i, x_j, z_i, z_ij, l_i, l_ij, res);
   CK(cudaGetLastError());
   return 0;

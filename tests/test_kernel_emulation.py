@@ -1,0 +1,162 @@
+"""Functional CPU emulation of the CUDA source (tools/cpu_emu): omg_tools_b200/csrc/
+omg_b200.cu compiled with g++ against a cuda_runtime.h stand-in, every thread of a block a
+fiber, __syncthreads / warp shuffles as barriers.  The emulated kernels -- the same source
+lines the GPU runs -- are compared with the CPU oracle.  This is test infrastructure for a
+container without a GPU: it checks table decoding, the shared-memory layout chosen for a
+B200, barrier placement, the blocked envelope factorisation and the interior-point logic,
+not performance and not data races.  The product never loads this library."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from omg_tools_b200 import scenarios as sc
+from omg_tools_b200.solver import b200
+from oracle import ipm_c
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_DIR = os.path.join(ROOT, 'tools', 'cpu_emu')
+EMU_LIB = os.path.join(EMU_DIR, '_build', 'libomgb200_emu.so')
+
+
+@pytest.fixture(scope='module')
+def emu():
+    src = [os.path.join(ROOT, 'omg_tools_b200', 'csrc', 'omg_b200.cu'),
+           os.path.join(ROOT, 'include', 'omg_b200.h'),
+           os.path.join(EMU_DIR, 'cuda_runtime.h'), os.path.join(EMU_DIR, 'emu_runtime.cpp')]
+    if (not os.path.exists(EMU_LIB) or
+            any(os.path.getmtime(s) > os.path.getmtime(EMU_LIB) for s in src)):
+        subprocess.check_call([os.path.join(EMU_DIR, 'build.sh')])
+    if not ipm_c.available():
+        pytest.skip('C oracle not built')
+    saved = b200._lib
+    lib = b200.load_library(EMU_LIB)          # B200Solver objects built below bind to it
+    yield lib
+    b200._lib = saved                          # the product library for everything else
+
+
+def _compare(pr, B, jitter, seed, n_flat, options=None):
+    tb = pr.father.tables
+    X0, P = sc.instance_data(pr, B, jitter=jitter, seed=seed)
+    if options:
+        pr.problem.set_options(options)
+    res = pr.problem.solve_batch(X0, P)
+    ref = ipm_c.solve_batch_full(tb, X0, P, threads=4, options=options)
+    return res, ref
+
+
+@pytest.mark.parametrize('name, B, layout', [('config1', 3, (97408, 2)), ('config2', 2, (113552, 2)),
+                                             ('config5', 2, None)])
+def test_standard_kernel_matches_oracle(emu, name, B, layout):
+    """omg_ipm_kernel_2cta (256 threads, 2 blocks/SM layout) on BASELINE configs 1, 2, 5:
+    same statuses and iteration counts as the C oracle, solutions to rounding."""
+    pr = getattr(sc, name)()
+    info = pr.problem.info()
+    if layout:
+        assert (info['smem_bytes'], info['ctas_per_sm']) == layout   # the B200 layout
+    res, ref = _compare(pr, B, 0.1, 1, 26)
+    assert np.array_equal(res['status'], ref['status']) and (ref['status'] == 0).all()
+    assert np.array_equal(res['iters'], ref['iters'])
+    assert np.abs(res['x'] - ref['x'])[:, :26].max() < 1e-4
+    assert np.abs(res['f'] - ref['f']).max() < 1e-8
+    # tight tolerance: the end point is solver independent for the vehicle splines
+    tight = {'tol': 1e-8, 'compl_inf_tol': 1e-8, 'constr_viol_tol': 1e-8}
+    res, ref = _compare(pr, 1, 0.1, 2, 26, tight)
+    assert res['status'][0] == 0 == ref['status'][0]
+    assert np.abs(res['x'] - ref['x'])[:, :26].max() < 1e-7
+
+
+def test_one_block_per_sm_variant(emu, monkeypatch):
+    """omg_ipm_kernel (512 threads, everything in shared memory)."""
+    monkeypatch.setenv('OMG_B200_CTAS', '1')
+    pr = sc.config2()
+    assert pr.problem.info()['ctas_per_sm'] == 1
+    res, ref = _compare(pr, 1, 0.1, 3, 26)
+    assert res['status'][0] == 0 and res['iters'][0] == ref['iters'][0]
+    assert np.abs(res['x'] - ref['x'])[:, :26].max() < 1e-5
+
+
+def test_xl_kernel_config4(emu):
+    """omg_ipm_kernel_xl with intermediates (Quadrotor3D, 236 mids, K in shared memory)."""
+    pr = sc.config4()
+    res, ref = _compare(pr, 1, 0.0, 0, 36)
+    assert res['status'][0] == 0 and res['iters'][0] == ref['iters'][0]
+    assert np.abs(res['x'] - ref['x']).max() < 1e-4
+    assert abs(res['f'][0] - ref['f'][0]) < 1e-7
+
+
+def test_xl_kernel_cross_hessian_dubins_default(emu):
+    """The cross-Hessian slots of the XL kernel (Dubins without substitution: hyperplane
+    normal times integrated position; include/omg_b200.h xq_*): identical path on the
+    nominal instance."""
+    pr = sc.config_dubins_plain()
+    tb = pr.father.tables
+    assert tb.nnz_wx > 0
+    res, ref = _compare(pr, 1, 0.0, 0, 26)
+    assert res['status'][0] == 0 and res['iters'][0] == ref['iters'][0]
+    assert np.abs(res['x'] - ref['x']).max() < 1e-7
+    assert np.abs(res['lam_g'] - ref['lam_g']).max() < 1e-6
+
+
+def test_edge_cases_and_dropin(emu):
+    """Empty batch, per-instance bounds, NaN parameters, max_iter, warm start with
+    multipliers, Problem.solve()."""
+    pr = sc.config1()
+    tb = pr.father.tables
+    out = pr.problem.solve_batch(np.zeros((0, tb.n)), np.zeros((0, tb.n_par)))
+    assert out['x'].shape == (0, tb.n)
+    X0, P = sc.instance_data(pr, 3, jitter=0.1, seed=0)
+    a = pr.problem.solve_batch(X0, P)
+    LB, UB = np.repeat(tb.lbg[None], 3, 0), np.repeat(tb.ubg[None], 3, 0)
+    b = pr.problem.solve_batch(X0, P, LB, UB)              # per-instance bounds == shared
+    assert np.array_equal(a['x'], b['x'])
+    Pn = P.copy()
+    Pn[1, 0] = np.nan                                      # NaN parameter: reported, isolated
+    r = pr.problem.solve_batch(X0, Pn)
+    assert r['status'][1] == 4 and r['status'][0] == 0 and np.array_equal(r['x'][0], a['x'][0])
+    pr.problem.set_options({'max_iter': 5})
+    try:
+        r = pr.problem.solve_batch(X0[:2], P[:2])
+    finally:
+        pr.problem.set_options({'max_iter': 3000})
+    assert np.all(r['status'] == 1) and np.all(r['iters'] == 5)
+    w = pr.problem.solve_batch(a['x'], P, lam_g0=a['lam_g'])    # warm start incl. multipliers
+    ref = ipm_c.solve_batch_full(tb, a['x'], P, threads=2, lam_g0=a['lam_g'])
+    assert np.all(w['status'] == 0) and np.all(w['iters'] < a['iters'])
+    assert np.array_equal(w['iters'], ref['iters'])
+    pr.solve(0., 0.1)
+    assert pr.problem.stats()['return_status'] == 'Solve_Succeeded'
+
+
+def test_shift_and_sampling_kernels(emu):
+    """omg_shift_kernel == T.dot(coeffs) of the seg0 variables, omg_sample_kernel == the
+    sampled splines (device pointers are host pointers in the emulation)."""
+    pr = sc.config1()
+    slv = pr.problem
+    X0, P = sc.instance_data(pr, 3, jitter=0.1, seed=4)
+    X = slv.solve_batch(X0, P)['x']
+    blocks = [(off, shape[0], shape[1], T) for (_, _, off, shape, T) in pr.father.shifted_entries()]
+    offs = np.array([b[0] for b in blocks], dtype=np.int32)
+    lens = np.array([b[1] for b in blocks], dtype=np.int32)
+    ncols = np.array([b[2] for b in blocks], dtype=np.int32)
+    Tm = np.concatenate([np.asarray(b[3], dtype=np.float64).reshape(-1) for b in blocks])
+    Xs = X.copy()
+    assert emu.omg_shift_batch(slv._handle, Xs.shape[0], Xs.ctypes.data, len(blocks), offs.ctypes.data,
+                               lens.ctypes.data, ncols.ctypes.data, Tm.ctypes.data, None) == 0
+    want = X.copy()
+    for off, L, nc, T in blocks:
+        for c in range(nc):
+            seg = slice(off + c * L, off + (c + 1) * L)
+            want[:, seg] = X[:, seg] @ np.asarray(T).T
+    assert np.abs(Xs - want).max() < 1e-13
+    basis = pr.vehicles[0].basis
+    tau = np.linspace(0., 1., 51)
+    S0 = np.ascontiguousarray(basis.eval_basis(tau), dtype=np.float64)
+    out = np.zeros((X.shape[0], 2 * 51))
+    o1, l1, c1, s1 = (np.array([v], dtype=np.int32) for v in (0, 13, 2, 51))
+    assert emu.omg_sample_batch(X.shape[0], X.shape[1], X.ctypes.data, 1, o1.ctypes.data, l1.ctypes.data,
+                                c1.ctypes.data, s1.ctypes.data, S0.ctypes.data, out.ctypes.data, None) == 0
+    for c in range(2):
+        assert np.abs(out[:, c * 51:(c + 1) * 51] - X[:, c * 13:(c + 1) * 13] @ S0.T).max() < 1e-13

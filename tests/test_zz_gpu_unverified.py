@@ -1,8 +1,8 @@
 """GPU parity tests of kernel paths written after the round's GPU budget was spent: they
-have been compiled for sm_100a and checked line by line against the C oracle
-(oracle/ipm.c implements the same table semantics and passes the CPU tests), but have NOT
-run on a GPU yet.  They are non-strict xfail so that a first GPU run reports XPASS / XFAIL
-without masking the verified suite (this file sorts last); drop the marker once XPASS."""
+compile for sm_100a and pass in the CPU emulation of the kernel source
+(tests/test_kernel_emulation.py, tools/cpu_emu), but have NOT run on a GPU yet.  They are
+non-strict xfail so that a first GPU run reports XPASS / XFAIL without masking the verified
+suite (this file sorts last); drop the marker once XPASS."""
 import numpy as np
 import pytest
 
