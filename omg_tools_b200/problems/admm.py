@@ -113,7 +113,8 @@ class FormationPoint2point(object):
         self.rank, self.world, self.group = rank, world, group
         self.options = {'verbose': 0, 'rho': 2., 'init_iter': 5, 'max_iter_per_update': 1,
                         'AMA': False, 'horizon_time': 10.,
-                        # fast ADMM (reference admm.py:33-37, 510-554); AMA is not built
+                        # 'AMA': alternating minimisation (no quadratic penalty in the x-update,
+                        # admm.py:97-104); fast ADMM / fast AMA (admm.py:33-37, 510-554)
                         'nesterov_acceleration': False, 'nesterov_reset': False, 'eta': 0.999}
         self.options.update(options or {})
         self.iteration = 0

@@ -168,6 +168,8 @@ class FormationADMMRunner(object):
                 self.alpha = 0.5 * (1. + np.sqrt(1. + 4. * alpha_p**2))
                 w = (alpha_p - 1.) / self.alpha
                 for name, old in zip(('z_i', 'z_ij', 'l_i', 'l_ij'), prev):
+                    if p.options.get('AMA') and name.startswith('z'):
+                        continue            # AMA extrapolates the multipliers only (admm.py:527-541)
                     a = getattr(self, name)
                     a.add_(a - old, alpha=w)
                 self.c_res_p = c_res

@@ -96,8 +96,9 @@ class ADMMOracle(object):
                 alpha_p = self.alpha
                 self.alpha = 0.5 * (1. + np.sqrt(1. + 4. * alpha_p**2))
                 w = (alpha_p - 1.) / self.alpha
-                self.z_i = self.z_i + w * (self.z_i - z_i_p)
-                self.z_ij = self.z_ij + w * (self.z_ij - z_ij_p)
+                if not p.options.get('AMA'):       # AMA extrapolates the multipliers only
+                    self.z_i = self.z_i + w * (self.z_i - z_i_p)
+                    self.z_ij = self.z_ij + w * (self.z_ij - z_ij_p)
                 self.l_i = self.l_i + w * (self.l_i - l_i_p)
                 self.l_ij = self.l_ij + w * (self.l_ij - l_ij_p)
                 self.c_res_p = cr

@@ -130,6 +130,27 @@ def test_admm_oracle_nesterov_acceleration(formation):
         assert pr[-1] < 0.3 * pr[0]          # primal residual (consensus error) shrinks
 
 
+def test_admm_ama_option(formation):
+    """Option 'AMA' (alternating minimisation, reference admm.py:97-104): the x-update
+    drops the quadratic penalty -- the agent NLP's objective becomes linear in x (no
+    Hessian terms on the objective row) -- and the fast variant extrapolates the
+    multipliers only (admm.py:527-541).  The holonomic formation objective is not strongly
+    convex, so no convergence claim is made here (the reference uses AMA for the quadrotor
+    comparison only); the iteration must run and keep the consensus constraint A z = b."""
+    from oracle.admm_ref import ADMMOracle
+    pr = sc.config3(4, {'AMA': True, 'nesterov_acceleration': True}, build_solver=False)
+    tb = pr.tb
+    assert (tb.n, tb.m, tb.n_par) == (118, 578, 203)
+    assert not np.any(tb.W.lrow == tb.m) and np.any(formation.tb.W.lrow == formation.tb.m)
+    orc = ADMMOracle(pr)
+    for _ in range(3):
+        res = orc.dual_update(0.)
+        assert np.all(np.isfinite(res))
+    for i in range(pr.N):
+        z = np.r_[orc.z_i[i], orc.z_ij[i].reshape(-1)]
+        assert np.abs(pr.A.dot(z) - pr._b_of(i)).max() < 1e-8
+
+
 def test_fleet_configuration_equals_the_references():
     """Fleet.set_configuration / get_neighbors (vehicles/fleet.py) of the reference,
     run from /root/reference (tests/golden/make_model_golden.py): relative positions

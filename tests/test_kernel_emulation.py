@@ -160,3 +160,69 @@ def test_shift_and_sampling_kernels(emu):
                                 c1.ctypes.data, s1.ctypes.data, S0.ctypes.data, out.ctypes.data, None) == 0
     for c in range(2):
         assert np.abs(out[:, c * 51:(c + 1) * 51] - X[:, c * 13:(c + 1) * 13] @ S0.T).max() < 1e-13
+
+
+def test_rk4_kernel(emu):
+    """omg_rk4_kernel vs numpy RK4 with the vehicle classes' own ode()."""
+    from omg_tools_b200 import Holonomic, Quadrotor, Quadrotor3D
+
+    def rk4(veh, x, U, dt):
+        for i in range(U.shape[0] - 1):
+            k1 = veh.ode(x, U[i])
+            k2 = veh.ode(x + 0.5 * dt * k1, U[i])
+            k3 = veh.ode(x + 0.5 * dt * k2, U[i])
+            k4 = veh.ode(x + dt * k3, U[i + 1])
+            x = x + dt / 6. * (k1 + 2 * k2 + 2 * k3 + k4)
+        return x
+
+    rng = np.random.default_rng(5)
+    B, steps, dt = 131, 20, 0.01              # more instances than one 128-thread block
+    for model, veh, ns, ni in ((0, Holonomic(), 2, 2), (1, Quadrotor3D(0.5), 8, 3), (2, Quadrotor(), 5, 2)):
+        x0 = 0.3 * rng.standard_normal((B, ns))
+        U = 0.5 * rng.standard_normal((B, steps + 1, ni))
+        if ni == 3:
+            U[:, :, 0] += 9.81
+        out = np.zeros_like(x0)
+        assert emu.omg_integrate_rk4(model, B, ns, ni, x0.ctypes.data, U.ctypes.data, dt, steps,
+                                     out.ctypes.data, None) == 0
+        ref = np.array([rk4(veh, x0[b], U[b], dt) for b in range(B)])
+        assert np.abs(out - ref).max() < 1e-12
+
+
+def test_admm_consensus_kernel(emu):
+    """omg_admm_zl_kernel (z-update, multiplier update, residuals of one agent per block)
+    vs the reference's KKT-solve formulas (admm.py:149-155, 260-266, 296-303) on BASELINE
+    config 3's structure, at a time inside the first knot interval (non-trivial first-knot
+    transforms)."""
+    pr = sc.config3(4, build_solver=False)
+    rng = np.random.default_rng(7)
+    N, nsh, nn, L = pr.N, pr.nsh, pr.n_nghb, pr.L
+    rho = 1.3
+    x_i, l_i, z_i = (rng.standard_normal((N, nsh)) for _ in range(3))
+    x_j, l_ij, z_ij = (rng.standard_normal((N, nn, nsh)) for _ in range(3))
+    Tf, Tb = pr.first_knot_transforms(0.37)
+    PzT = np.ascontiguousarray(pr.Pz.T)
+    c = np.ascontiguousarray(pr.c)
+    zi, zij, li, lij = z_i.copy(), z_ij.copy(), l_i.copy(), l_ij.copy()
+    res = np.zeros((N, 3))
+    Tf, Tb = np.ascontiguousarray(Tf), np.ascontiguousarray(Tb)
+    assert emu.omg_admm_zl_update(N, nsh, nn, L, PzT.ctypes.data, c.ctypes.data, Tf.ctypes.data,
+                                  Tb.ctypes.data, rho, x_i.ctypes.data, x_j.ctypes.data,
+                                  zi.ctypes.data, zij.ctypes.data, li.ctypes.data, lij.ctypes.data,
+                                  res.ctypes.data, None) == 0
+    nblk = nsh // L * (1 + nn)
+    TF, TB = np.kron(np.eye(nblk), Tf), np.kron(np.eye(nblk), Tb)
+    for i in range(N):
+        x = TF.dot(np.r_[x_i[i], x_j[i].reshape(-1)])
+        l = TF.dot(np.r_[l_i[i], l_ij[i].reshape(-1)])
+        f = -(l + rho * x)
+        G = -(1. / rho) * pr.A.dot(pr.A.T)
+        h = pr._b_of(i) + (1. / rho) * pr.A.dot(f)
+        z = TB.dot(-(1. / rho) * (pr.A.T.dot(np.linalg.solve(G, h)) + f))
+        assert np.abs(np.r_[zi[i], zij[i].reshape(-1)] - z).max() < 1e-9
+        l_new = np.r_[l_i[i], l_ij[i].reshape(-1)] + rho * (np.r_[x_i[i], x_j[i].reshape(-1)] - z)
+        assert np.abs(np.r_[li[i], lij[i].reshape(-1)] - l_new).max() < 1e-9
+        e1 = TF.dot(np.r_[x_i[i], x_j[i].reshape(-1)] - z)
+        e2 = TF.dot(z - np.r_[z_i[i], z_ij[i].reshape(-1)])
+        pri, dri = e1.dot(e1), rho * e2.dot(e2)
+        assert np.allclose(res[i], [pri, dri, rho * pri + dri], rtol=1e-9, atol=1e-12)
