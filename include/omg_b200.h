@@ -51,13 +51,15 @@ extern "C" {
  *     mu_l  = sum_{e in [mu_ptr[l],mu_ptr[l+1])} lambda[mu_row[e]] * Jx[mu_slot[e]]
  * give the chain rule for the Jacobian and the multipliers of the mids' own
  * Hessians (W terms with lrow = m+1+l).  The coefficient of a mid in a row may
- * depend on x (a hyperplane normal times an integrated position: Dubins, bicycle,
- * AGV, trailer; dubins.py:235-251): the A slots are then functions of x and the
- * W term list carries nnz_wx extra "cross" slots after its nnz_w regular ones,
- *     X[l,k] = sum_i lambda_i d2 row_i / d mid_l d x_k ,
- * whose contribution X^T C + C^T X to the Hessian is gathered per H position:
- *     H[xq_h[e]] += fac * sum_{r in [xq_ptr[e],xq_ptr[e+1])} Wx[xq_w[r]] * Jx[xq_c[r]]
- * with fac = 2 on the diagonal, 1 elsewhere (Wx = values of the cross slots). */
+ * depend on x (a hyperplane normal times an integrated position: Dubins, AGV, trailer;
+ * dubins.py:235-251) or on another mid (the steering-rate rows of the bicycle,
+ * bicycle.py:115-124): the A slots are then functions of x_ext and the W term list
+ * carries nnz_wx extra slots after its nnz_w regular ones, with values Wx:
+ *     X[l,k]   = sum_i lambda_i d2 row_i / d mid_l d x_k       (cross slots)
+ *     M[l1,l2] = sum_i lambda_i d2 row_i / d mid_l1 d mid_l2   (l1 >= l2)
+ * Their contribution X^T C + C^T X + C^T M C to the Hessian is gathered per H position:
+ *     H[xq_h[e]] += sum_{r in [xq_ptr[e],xq_ptr[e+1])} Wx[xq_w[r]] * Jx[xq_a[r]] * Jx[xq_b[r]]
+ * where xq_b[r] = -1 stands for a factor 1 (cross terms; listed twice on the diagonal). */
 typedef struct omg_termlist {
   int32_t n_out, n_terms, width;
   const int32_t* ptr;   /* [n_out+1] */
@@ -113,12 +115,13 @@ typedef struct omg_tables {
   const int32_t* kkt_diag;      /* [kkt_n] envelope offset of the diagonal */
   const int32_t* kkt_panel_ptr; /* [n_panels+1] */
   const int32_t* kkt_panel_rows;/* [n_panel_rows] */
-  /* cross-Hessian gather lists (see omg_termlist); nnz_wx = 0: unused.  W.n_out = nnz_w + nnz_wx */
+  /* extra Hessian products (see omg_termlist); nnz_wx = 0: unused.  W.n_out = nnz_w + nnz_wx */
   int32_t nnz_wx, n_xq, n_xp;
   const int32_t* xq_h;          /* [n_xq] H position */
   const int32_t* xq_ptr;        /* [n_xq+1] */
-  const int32_t* xq_w;          /* [n_xp] cross slot (0-based within the cross slots) */
-  const int32_t* xq_c;          /* [n_xp] J slot of C = d mid / d x */
+  const int32_t* xq_w;          /* [n_xp] extra W slot (0-based within the extra slots) */
+  const int32_t* xq_a;          /* [n_xp] J slot of C = d mid / d x */
+  const int32_t* xq_b;          /* [n_xp] second J slot of C, or -1 */
 } omg_tables;
 
 /* Interior-point options; defaults = the reference's IPOPT settings

@@ -12,6 +12,8 @@ from .vehicles.holonomic1d import Holonomic1D
 from .vehicles.holonomicorient import HolonomicOrient
 from .vehicles.quadrotor import Quadrotor
 from .vehicles.dubins import Dubins
+from .vehicles.bicycle import Bicycle
+from .vehicles.agv import AGV
 from .vehicles.quadrotor3d import Quadrotor3D
 from .vehicles.fleet import Fleet
 from .environment.environment import Environment

@@ -273,10 +273,9 @@ def lower(var_ids, par_ids, rows, objective, lbg, ubg, order_hint=None):
     degree = max([len(xm) for sr in split_rows + [split_obj] for xm in sr] + [1])
     for sr in split_rows[:m]:
         for xm in sr:
-            if sum(1 for j in xm if j > n) > 1:
+            if sum(1 for j in xm if j > n) > 2:
                 raise NotImplementedError(
-                    'rows must be affine in the intermediates (their coefficients '
-                    'may depend on x and p)')
+                    'rows may contain at most two intermediates per monomial')
 
     def coef_of(ppoly):
         return tape.v_of_ppoly(ppoly)
@@ -351,15 +350,18 @@ def lower(var_ids, par_ids, rows, objective, lbg, ubg, order_hint=None):
     for s, key in enumerate(allkeys):
         for c, cidx, red in jslots.get(key, ()):
             J.add(s, c, cidx, red)
-    # Hessian slots: [regular (j >= k, both variables) | cross (mid l, variable k)].
-    # A cross slot holds sum_i lam_i d2 row_i / d mid_l d x_k (rows whose mid
-    # coefficient depends on x, e.g. hyperplane normal times integrated position);
-    # its contribution to the Hessian is  X^T C + C^T X  (C = d mid / d x), added
-    # through the pair lists xq_* below.
+    # Hessian slots: [regular (j >= k, both variables) | cross (mid l, variable k) |
+    # mid-mid (mid l1 >= mid l2)].  A cross slot holds X[l,k] = sum_i lam_i d2 row_i /
+    # d mid_l d x_k (rows whose mid coefficient depends on x, e.g. hyperplane normal times
+    # integrated position), a mid-mid slot M[l1,l2] = sum_i lam_i d2 row_i / d mid_l1 d
+    # mid_l2 (rows with a product of two intermediates, e.g. the steering-rate rows of the
+    # bicycle).  With C = d mid / d x the Hessian gains  X^T C + C^T X + C^T M C, gathered
+    # per H position through the product lists xq_* below.
     wkeys = sorted(k for k in wslots if k[0] < n)
-    xkeys = sorted(k for k in wslots if k[0] > n)
-    W = TermList(len(wkeys) + len(xkeys), degree - 2, with_lrow=True)
-    for s, key in enumerate(wkeys + xkeys):
+    xkeys = sorted(k for k in wslots if k[0] > n and k[1] < n)
+    mkeys = sorted(k for k in wslots if k[0] > n and k[1] > n)
+    W = TermList(len(wkeys) + len(xkeys) + len(mkeys), degree - 2, with_lrow=True)
+    for s, key in enumerate(wkeys + xkeys + mkeys):
         for c, cidx, red, lrow in wslots[key]:
             W.add(s, c, cidx, red, lrow)
 
@@ -376,15 +378,26 @@ def lower(var_ids, par_ids, rows, objective, lbg, ubg, order_hint=None):
     tb.wrow = np.array([k[0] for k in wkeys], dtype=np.int32)
     tb.wcol = np.array([k[1] for k in wkeys], dtype=np.int32)
     tb.nnz_j, tb.nnz_w = len(jkeys), len(wkeys)
-    tb.nnz_wx = len(xkeys)
+    tb.nnz_wx = len(xkeys) + len(mkeys)      # extra W slots (values Wx)
     tb.nnz_jx = len(allkeys)
-    # cross pairs: H[max(k,j), min(k,j)] += X[l,k] * C[l,j]  (twice on the diagonal)
+    # products per lower-triangle H position (a >= b): Wx[w] * Jx[ca] * (Jx[cb] or 1)
     xpairs = {}
-    for sx, (jm, k) in enumerate(xkeys):
+    for sx, (jm, k) in enumerate(xkeys):     # H[a,b] += X[l,k] C[l,j] (+ transpose)
         l = jm - n - 1
         for j in c_by_mid.get(l, ()):
-            key = (max(k, j), min(k, j))
-            xpairs.setdefault(key, []).append((sx, slot_of[(m + l, j)]))
+            e = (sx, slot_of[(m + l, j)], -1)
+            xpairs.setdefault((max(k, j), min(k, j)), []).append(e)
+            if j == k:                        # both transposes land on the diagonal
+                xpairs[(k, k)].append(e)
+    for sm, (jm1, jm2) in enumerate(mkeys):  # H[a,b] += sum C[l1,a] M[l1,l2] C[l2,b]
+        l1, l2 = jm1 - n - 1, jm2 - n - 1
+        w = len(xkeys) + sm
+        for la, lb in ((l1, l2),) + (((l2, l1),) if l1 != l2 else ()):
+            for a in c_by_mid.get(la, ()):
+                for b in c_by_mid.get(lb, ()):
+                    if a >= b:
+                        xpairs.setdefault((a, b), []).append(
+                            (w, slot_of[(m + la, a)], slot_of[(m + lb, b)]))
     tb._xpairs = xpairs
     # chain rule  J[s] += sum_l A[i,l] C[l,j]  and  mu_l = sum_i lam_i A[i,l]
     a_by_row = {}
@@ -459,20 +472,23 @@ def _build_kkt_pattern(tb):
     index = {k: q for q, k in enumerate(keys)}
     tb.w2h = np.array([index[(int(r), int(c))]
                        for r, c in zip(tb.wrow, tb.wcol)], dtype=np.int32)
-    # cross-Hessian gather lists: for the H positions xq_h[e] the pairs
-    # [xq_ptr[e], xq_ptr[e+1]) of (cross slot xq_w, Jacobian slot xq_c of C)
-    xq_h, xq_ptr, xq_w, xq_c = [], [0], [], []
+    # gather lists of the extra Hessian products: for the H positions xq_h[e] the entries
+    # [xq_ptr[e], xq_ptr[e+1]) of (extra W slot xq_w, Jacobian slots xq_a, xq_b of C;
+    # xq_b = -1: no second factor)
+    xq_h, xq_ptr, xq_w, xq_a, xq_b = [], [0], [], [], []
     for key in sorted(xpairs):
         xq_h.append(index[key])
-        for sx, sc in xpairs[key]:
+        for sx, sa, sb in xpairs[key]:
             xq_w.append(sx)
-            xq_c.append(sc)
+            xq_a.append(sa)
+            xq_b.append(sb)
         xq_ptr.append(len(xq_w))
     tb.n_xq = len(xq_h)
     tb.xq_h = np.array(xq_h, dtype=np.int32)
     tb.xq_ptr = np.array(xq_ptr, dtype=np.int32)
     tb.xq_w = np.array(xq_w, dtype=np.int32)
-    tb.xq_c = np.array(xq_c, dtype=np.int32)
+    tb.xq_a = np.array(xq_a, dtype=np.int32)
+    tb.xq_b = np.array(xq_b, dtype=np.int32)
     if hasattr(tb, '_xpairs'):
         del tb._xpairs
 

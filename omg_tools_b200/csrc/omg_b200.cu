@@ -85,10 +85,11 @@ struct DevTab {
   int n_mid, nnz_jx, n_hq_heavy;
   const int2* midg; const int* jtptr; const int* jrow;
   const int *jp_ptr, *jp_a, *jp_c, *mu_ptr, *mu_row, *mu_slot;
-  // cross-Hessian slots (mid coefficient depends on x): wrec[nnz_w .. nnz_w+nnz_wx) hold the
-  // term ranges, xq the H positions that gather  fac * sum Wx[pair.x] * Jx[pair.y]
+  // extra Hessian slots (mid coefficient depends on x or on another mid): wrec[nnz_w ..
+  // nnz_w+nnz_wx) hold the term ranges, xq the H positions that gather
+  // sum Wx[e.x] * Jx[e.y] * (e.z >= 0 ? Jx[e.z] : 1)
   int nnz_wx, n_xq;
-  const HqRec* xq; const int2* xqp;
+  const HqRec* xq; const int4* xqp;
 };
 
 struct Smem {                      // offsets in doubles
@@ -841,13 +842,17 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(FULL, acc, o);
             if (lane == 0) { if (q < T.nnz_w) K[w.dst] += acc; else wx[w.dst] = acc; }
           }
-          if (T.nnz_wx) {   // cross terms X^T C + C^T X, one thread per H position (deterministic)
+          if (T.nnz_wx) {   // X^T C + C^T X + C^T M C, one thread per H position (deterministic)
             __syncthreads();
             for (int e = tid; e < T.n_xq; e += NT) {
               const HqRec h = T.xq[e];
               double acc = 0.0;
-              for (int r = h.p0; r < h.p1; ++r) { const int2 pr = T.xqp[r]; acc += wx[pr.x] * jx[pr.y]; }
-              K[h.dst] += h.diag ? 2.0 * acc : acc;
+              for (int r = h.p0; r < h.p1; ++r) {
+                const int4 pr = T.xqp[r];
+                const double v = wx[pr.x] * jx[pr.y];
+                acc += (pr.z >= 0) ? v * jx[pr.z] : v;
+              }
+              K[h.dst] += acc;
             }
           }
         } else
@@ -1463,7 +1468,7 @@ const TabField kTabFields[] = {
   TF_S(kkt_n), TF_S(kkt_n_eq), TF_S(env_size), TF_S(n_panel_rows), TF_S(max_panel_rows),
   TF_I(kkt_eq_rows), TF_I(kkt_pos_var), TF_I(kkt_pos_eq), TF_I(kkt_sign), TF_I(env_first), TF_I(env_ptr),
   TF_I(kkt_hdst), TF_I(kkt_jdst), TF_I(kkt_diag), TF_I(kkt_panel_ptr), TF_I(kkt_panel_rows),
-  TF_S(nnz_wx), TF_S(n_xq), TF_S(n_xp), TF_I(xq_h), TF_I(xq_ptr), TF_I(xq_w), TF_I(xq_c),
+  TF_S(nnz_wx), TF_S(n_xq), TF_S(n_xp), TF_I(xq_h), TF_I(xq_ptr), TF_I(xq_w), TF_I(xq_a), TF_I(xq_b),
 };
 struct OwnedTables { omg_tables T; std::vector<void*> blocks; };
 }  // namespace
@@ -1659,7 +1664,7 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
   }
   if (ok && nnz_wx) {  // cross-Hessian gather records
     std::vector<HqRec> xq(T.n_xq > 0 ? T.n_xq : 1);
-    std::vector<int2> xp(tb->n_xp > 0 ? tb->n_xp : 1);
+    std::vector<int4> xp(tb->n_xp > 0 ? tb->n_xp : 1);
     for (int e = 0; e < T.n_xq && ok; ++e) {
       const int q = tb->xq_h[e];
       if (q < 0 || q >= tb->nnz_h) { set_err("cross-Hessian position out of range"); ok = false; break; }
@@ -1667,9 +1672,11 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
       xq[e].diag = (tb->hrow[q] == tb->hcol[q]) ? 1 : 0;
     }
     for (int r = 0; r < tb->n_xp && ok; ++r) {
-      if (tb->xq_w[r] < 0 || tb->xq_w[r] >= nnz_wx || tb->xq_c[r] < tb->nnz_j || tb->xq_c[r] >= tb->nnz_jx) {
-        set_err("cross-Hessian pair out of range"); ok = false; break; }
-      xp[r] = make_int2(tb->xq_w[r], tb->xq_c[r]);
+      const int a = tb->xq_a[r], b = tb->xq_b[r];
+      if (tb->xq_w[r] < 0 || tb->xq_w[r] >= nnz_wx || a < tb->nnz_j || a >= tb->nnz_jx ||
+          (b >= 0 && (b < tb->nnz_j || b >= tb->nnz_jx))) {
+        set_err("extra Hessian product out of range"); ok = false; break; }
+      xp[r] = make_int4(tb->xq_w[r], a, b, 0);
     }
     T.xq = upload(h, xq.data(), xq.size(), &ok);
     T.xqp = upload(h, xp.data(), xp.size(), &ok);

@@ -199,6 +199,37 @@ def config_dubins_exact(options=None, build_solver=True):
                          knot_intervals=5)
 
 
+def config_bicycle(options=None, build_solver=True):
+    """examples/p2p_bicycle.py with a fixed end time: Bicycle(length 0.4, no substitution,
+    5 knot intervals) from (0, 0, 0, delta 0) to (3, 3, 0), Square(5) room centred at
+    (1.5, 1.5), one Circle(0.5) obstacle drifting in x."""
+    from . import Bicycle
+    vehicle = Bicycle(length=0.4, options={'plot_type': 'car', 'substitution': False})
+    vehicle.define_knots(knot_intervals=5)
+    vehicle.set_initial_conditions([0., 0., 0., 0.])
+    vehicle.set_terminal_conditions([3., 3., 0.])
+    environment = Environment(room={'shape': Square(5.), 'position': [1.5, 1.5]})
+    trajectories = {'velocity': {'time': [0.5], 'values': [[0.3, 0.0]]}}
+    environment.add_obstacle(Obstacle({'position': [1., 1.]}, shape=Circle(0.5),
+                                      simulation={'trajectories': trajectories}))
+    return _p2p(vehicle, environment, options, build_solver)
+
+
+def config_agv(options=None, build_solver=True):
+    """examples/p2p_agv.py with a fixed end time: AGV(length 0.8, Rectangle(0.8, 0.2), 5 knot
+    intervals) parking between two rectangles in a Rectangle(4, 1) corridor."""
+    from . import AGV, Rectangle
+    vehicle = AGV(length=0.8, options={'plot_type': 'agv'})
+    vehicle.define_knots(knot_intervals=5)
+    vehicle.set_initial_conditions([0.8, -0.05, 0., 0.])
+    vehicle.set_terminal_conditions([2.45, -0.35, 0.])
+    environment = Environment(room={'shape': Rectangle(width=4, height=1), 'position': [2, 0.]})
+    rectangle = Rectangle(width=0.8, height=0.2)
+    environment.add_obstacle(Obstacle({'position': [1., -0.35]}, shape=rectangle))
+    environment.add_obstacle(Obstacle({'position': [3.4, -0.35]}, shape=rectangle))
+    return _p2p(vehicle, environment, options, build_solver)
+
+
 def config_holonomic_orient(options=None, build_solver=True):
     """examples/p2p_holonomic_orient.py with a fixed end time: HolonomicOrient
     (Rectangle(0.2, 0.4), heading free, norm-1 regularisation of the heading rate),

@@ -62,7 +62,7 @@ class _Tables(C.Structure):
         ('kkt_hdst', _i32p), ('kkt_jdst', _i32p), ('kkt_diag', _i32p),
         ('kkt_panel_ptr', _i32p), ('kkt_panel_rows', _i32p),
         ('nnz_wx', C.c_int32), ('n_xq', C.c_int32), ('n_xp', C.c_int32),
-        ('xq_h', _i32p), ('xq_ptr', _i32p), ('xq_w', _i32p), ('xq_c', _i32p)]
+        ('xq_h', _i32p), ('xq_ptr', _i32p), ('xq_w', _i32p), ('xq_a', _i32p), ('xq_b', _i32p)]
 
 
 class _Options(C.Structure):
@@ -200,7 +200,7 @@ def pack_tables(tb):
     if T.nnz_wx:
         T.n_xq, T.n_xp = tb.n_xq, len(tb.xq_w)
         T.xq_h, T.xq_ptr = keep.i32(tb.xq_h), keep.i32(tb.xq_ptr)
-        T.xq_w, T.xq_c = keep.i32(tb.xq_w), keep.i32(tb.xq_c)
+        T.xq_w, T.xq_a, T.xq_b = keep.i32(tb.xq_w), keep.i32(tb.xq_a), keep.i32(tb.xq_b)
     return T, keep
 
 
@@ -261,7 +261,7 @@ def _table_records(tb):
     nnz_wx = getattr(tb, 'nnz_wx', 0)
     scalar('nnz_wx', nnz_wx), scalar('n_xq', tb.n_xq if nnz_wx else 0)
     scalar('n_xp', len(tb.xq_w) if nnz_wx else 0)
-    for f in ('xq_h', 'xq_ptr', 'xq_w', 'xq_c'):
+    for f in ('xq_h', 'xq_ptr', 'xq_w', 'xq_a', 'xq_b'):
         arr(f, getattr(tb, f) if nnz_wx else empty, 0)
     del keep
     return rec

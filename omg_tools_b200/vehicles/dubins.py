@@ -115,6 +115,8 @@ class Dubins(Vehicle):
         if self.options['substitution']:
             x, y = self.x, self.y
         else:
+            if horizon_time is None:
+                horizon_time = self.define_symbol('T')
             x, y = self._flat_position(splines, horizon_time)
         term_con = [(x, posT[0]), (y, posT[1]), (tg_ha, tg_haT)]
         term_con_der = [(v_til, 0.), (tg_ha.derivative(), 0.)]

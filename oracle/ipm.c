@@ -321,16 +321,16 @@ static void solve_one(const omg_tables* T, const omg_options* O, Work* w, const 
           v *= (lr < m) ? (y[lr] * dsc[lr]) : (lr == m ? fsc : mu_mid[lr - m - 1]);
           acc += v;
         }
-        if (q >= T->nnz_w) { w->wx[q - T->nnz_w] = acc; continue; }   /* cross slot X[l,k] */
+        if (q >= T->nnz_w) { w->wx[q - T->nnz_w] = acc; continue; }   /* extra slot X[l,k] / M[l1,l2] */
         const int h = T->w2h[q];
         { const int a = T->kkt_pos_var[T->hrow[h]], b = T->kkt_pos_var[T->hcol[h]];
           K[(a > b ? a : b) * N + (a > b ? b : a)] += acc; }
       }
-      for (int e = 0; e < (T->nnz_wx ? T->n_xq : 0); ++e) {   /* X^T C + C^T X (include/omg_b200.h) */
+      for (int e = 0; e < (T->nnz_wx ? T->n_xq : 0); ++e) {   /* X^T C + C^T X + C^T M C (include/omg_b200.h) */
         double acc = 0.0;
-        for (int r = T->xq_ptr[e]; r < T->xq_ptr[e + 1]; ++r) acc += w->wx[T->xq_w[r]] * jx[T->xq_c[r]];
+        for (int r = T->xq_ptr[e]; r < T->xq_ptr[e + 1]; ++r)
+          acc += w->wx[T->xq_w[r]] * jx[T->xq_a[r]] * (T->xq_b[r] >= 0 ? jx[T->xq_b[r]] : 1.0);
         const int h = T->xq_h[e];
-        if (T->hrow[h] == T->hcol[h]) acc *= 2.0;
         { const int a = T->kkt_pos_var[T->hrow[h]], b = T->kkt_pos_var[T->hcol[h]];
           K[(a > b ? a : b) * N + (a > b ? b : a)] += acc; }
       }

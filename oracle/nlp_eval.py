@@ -54,9 +54,10 @@ class TableEval(object):
     mids are the pseudo-rows m.. of G.  Rows are affine in the mids, so
     J = J_direct + A C (A = d row/d mid, C = d mid/d x, both slots of the J
     term list) and the Lagrangian Hessian takes mu = A^T lam as the
-    multipliers of the pseudo-rows.  When A depends on x the W term list has
-    nnz_wx extra "cross" slots X[l,k] = sum_i lam_i d2 row_i/d mid_l d x_k and
-    the Hessian gains X^T C + C^T X through the pair lists xq_*."""
+    multipliers of the pseudo-rows.  When A depends on x or on other mids the W
+    term list has nnz_wx extra slots (X[l,k] = sum_i lam_i d2 row_i/d mid_l d x_k,
+    M[l1,l2] likewise for two mids) and the Hessian gains X^T C + C^T X + C^T M C
+    through the product lists xq_*."""
 
     def __init__(self, tb):
         self.tb = tb
@@ -114,14 +115,14 @@ class TableEval(object):
         return _eval_terms(tb.W, V, self._xe(x, V), lam_ext)
 
     def hess_cross(self, x, V, wvals):
-        """(H position, value) of the cross contributions X^T C + C^T X."""
+        """(H position, value) of the contributions X^T C + C^T X + C^T M C."""
         tb = self.tb
         jv = self._jac_all(x, V)
-        prod = wvals[tb.nnz_w + tb.xq_w] * jv[tb.xq_c]
+        second = np.where(tb.xq_b >= 0, jv[np.maximum(tb.xq_b, 0)], 1.0)
+        prod = wvals[tb.nnz_w + tb.xq_w] * jv[tb.xq_a] * second
         out = np.zeros(tb.n_xq)
         np.add.at(out, np.repeat(np.arange(tb.n_xq), np.diff(tb.xq_ptr)), prod)
-        diag = tb.hrow[tb.xq_h] == tb.hcol[tb.xq_h]
-        return tb.xq_h, np.where(diag, 2.0, 1.0) * out
+        return tb.xq_h, out
 
     def hess_dense(self, x, V, lam, obj_factor=1.0):
         tb = self.tb

@@ -329,6 +329,29 @@ def build_reference(name):
         environment.add_obstacle(obs.Obstacle({'position': [1., 1.]}, shape=shp.Circle(0.5),
                                               simulation={'trajectories': trajectories}))
         options = {}
+    elif name == 'config_bicycle':
+        bi = ref_import('vehicles.bicycle')
+        vehicle = bi.Bicycle(length=0.4, options={'plot_type': 'car', 'substitution': False})
+        vehicle.define_knots(knot_intervals=5)
+        vehicle.set_initial_conditions([0., 0., 0., 0.])
+        vehicle.set_terminal_conditions([3., 3., 0.])
+        environment = env.Environment(room={'shape': shp.Square(5.), 'position': [1.5, 1.5]})
+        trajectories = {'velocity': {'time': [0.5], 'values': [[0.3, 0.0]]}}
+        environment.add_obstacle(obs.Obstacle({'position': [1., 1.]}, shape=shp.Circle(0.5),
+                                              simulation={'trajectories': trajectories}))
+        options = {}
+    elif name == 'config_agv':
+        ag = ref_import('vehicles.agv')
+        vehicle = ag.AGV(length=0.8, options={'plot_type': 'agv'})
+        vehicle.define_knots(knot_intervals=5)
+        vehicle.set_initial_conditions([0.8, -0.05, 0., 0.])
+        vehicle.set_terminal_conditions([2.45, -0.35, 0.])
+        environment = env.Environment(room={'shape': shp.Rectangle(width=4, height=1),
+                                            'position': [2, 0.]})
+        rectangle = shp.Rectangle(width=0.8, height=0.2)
+        environment.add_obstacle(obs.Obstacle({'position': [1., -0.35]}, shape=rectangle))
+        environment.add_obstacle(obs.Obstacle({'position': [3.4, -0.35]}, shape=rectangle))
+        options = {}
     elif name == 'config_holonomic_orient':
         ho = ref_import('vehicles.holonomicorient')
         vehicle = ho.HolonomicOrient()
@@ -478,7 +501,7 @@ BASE_NAMES = ('config1', 'config2', 'config4', 'config5', 'config_holonomic3d',
 # second fixture file (model_golden_ext.npz, `--ext`): formulations whose rows multiply the
 # intermediates by decision variables
 EXT_NAMES = ('config_dubins_plain', 'config_dubins_rect', 'config_dubins_exact',
-             'config_holonomic_orient')
+             'config_holonomic_orient', 'config_bicycle', 'config_agv')
 
 
 def main(ext=False):

@@ -93,7 +93,8 @@ def test_table_file_round_trip(tmp_path):
             assert np.array_equal(arr(t.xq_h, t.n_xq), tb.xq_h)
             assert np.array_equal(arr(t.xq_ptr, t.n_xq + 1), tb.xq_ptr)
             assert np.array_equal(arr(t.xq_w, t.n_xp), tb.xq_w)
-            assert np.array_equal(arr(t.xq_c, t.n_xp), tb.xq_c)
+            assert np.array_equal(arr(t.xq_a, t.n_xp), tb.xq_a)
+            assert np.array_equal(arr(t.xq_b, t.n_xp), tb.xq_b)
         lib.omg_tables_free(T)
     # a damaged file is refused with a message
     with open(path, 'r+b') as fp:

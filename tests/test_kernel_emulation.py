@@ -100,6 +100,21 @@ def test_xl_kernel_cross_hessian_dubins_default(emu):
     assert np.abs(res['lam_g'] - ref['lam_g']).max() < 1e-6
 
 
+def test_xl_kernel_mid_mid_hessian_bicycle(emu):
+    """Products of two intermediates (bicycle steering-rate rows): the C^T M C gather of the
+    XL kernel, identical path on the nominal instance from a rolling initial guess."""
+    pr = sc.config_bicycle()
+    tb = pr.father.tables
+    assert (tb.xq_b >= 0).any()
+    X0, P = sc.instance_data(pr, 1)
+    X0[0, :7] = 0.3
+    res = pr.problem.solve_batch(X0, P)
+    ref = ipm_c.solve_batch_full(tb, X0, P, threads=1)
+    assert res['status'][0] == 0 == ref['status'][0] and res['iters'][0] == ref['iters'][0]
+    assert np.abs(res['x'] - ref['x']).max() < 1e-5
+    assert np.abs(res['f'] - ref['f']).max() < 1e-7
+
+
 def test_edge_cases_and_dropin(emu):
     """Empty batch, per-instance bounds, NaN parameters, max_iter, warm start with
     multipliers, Problem.solve()."""

@@ -313,24 +313,26 @@ def test_intermediates_small_example_and_guards():
     assert np.allclose(W, ref)
     # guards: rows must be affine in intermediates, intermediates must not nest
     with pytest.raises(NotImplementedError):
-        lower([sid(v) for v in x], [sid(p)], [c * c], x[2], [0.], [0.])
+        lower([sid(v) for v in x], [sid(p)], [c * c * c], x[2], [0.], [0.])
     c2 = pl.new_mid('mc2', c * x[2])
     with pytest.raises(NotImplementedError):
         lower([sid(v) for v in x], [sid(p)], [c2 + x[0]], x[2], [0.], [0.])
 
 
 def test_intermediates_with_x_dependent_coefficients():
-    """Rows affine in the mids whose coefficient depends on x (hyperplane normal times
-    an integrated position: Dubins without substitution, bicycle, AGV, trailer).  The
-    Jacobian needs A(x) C, the Hessian the cross terms X^T C + C^T X: hand-checkable
-    NLP and finite differences of a random one."""
+    """Rows whose mid coefficient depends on x (hyperplane normal times an integrated
+    position: Dubins without substitution, AGV, trailer) or on another mid (products of two
+    shared product splines: the steering-rate rows of the bicycle).  The Jacobian needs
+    A(x, mids) C, the Hessian the terms X^T C + C^T X + C^T M C: a small NLP with every
+    combination against finite differences."""
     from omg_tools_b200.basics.lowering import lower
     x = [pl.new_symbol('nx%d' % k, 'var') for k in range(4)]
     p = pl.new_symbol('np', 'par')
     c = pl.new_mid('nc', x[0] * x[1] + p * x[1] * x[1])
     d = pl.new_mid('nd', x[1] * x[2] * x[2])
     sid = lambda e: e.single_symbol()
-    rows = [x[3] * c + x[0], x[3] * x[3] * d - 2. * c * x[0] + p * d, 3. * c - x[2]]
+    rows = [x[3] * c + x[0], x[3] * x[3] * d - 2. * c * x[0] + p * d + 0.5 * c * d - p * x[2] * d * d,
+            3. * c - x[2] + c * c]
     tb = lower([sid(v) for v in x], [sid(p)], rows, x[3] * x[3],
                [-np.inf, -np.inf, 0.], [1., 0., 0.])
     assert (tb.n, tb.m, tb.n_mid) == (4, 3, 2) and tb.nnz_wx > 0 and tb.n_xq > 0
@@ -342,8 +344,8 @@ def test_intermediates_with_x_dependent_coefficients():
     def g(z):
         cc = z[0] * z[1] + pv[0] * z[1] * z[1]
         dd = z[1] * z[2] * z[2]
-        return np.array([z[3] * cc + z[0], z[3] * z[3] * dd - 2. * cc * z[0] + pv[0] * dd,
-                         3. * cc - z[2]])
+        return np.array([z[3] * cc + z[0], z[3] * z[3] * dd - 2. * cc * z[0] + pv[0] * dd
+                         + 0.5 * cc * dd - pv[0] * z[2] * dd * dd, 3. * cc - z[2] + cc * cc])
 
     assert np.allclose(ev.g(xv, V), g(xv))
     h = 1e-5
@@ -567,6 +569,45 @@ def test_dubins_exact_substitution_solves():
     assert (g <= tb.ubg + 1e-4).all() and (g >= tb.lbg - 1e-4).all()
 
 
+def test_bicycle_tables_and_solve():
+    """vehicles/bicycle.py (examples/p2p_bicycle.py, fixed end time): steering-rate rows with
+    products of two shared product splines (mid-mid Hessian slots), integrated position
+    times hyperplane normal (cross slots).  Table derivatives against finite differences;
+    from a rolling initial guess (v~ = 0.3; the reference's all-zero speed guess sits on a
+    degenerate point of the steering rows, where only IPOPT's restoration phase gets away)
+    both oracles converge to the same point."""
+    from oracle import ipm_c, ipm_ref
+    if not ipm_c.available():
+        pytest.skip('C oracle not built')
+    pr = sc.config_bicycle(build_solver=False)
+    tb = pr.father.tables
+    assert (tb.n, tb.m, tb.n_par, tb.n_mid, tb.degree) == (85, 646, 25, 165, 5)
+    assert tb.nnz_wx > 0 and (tb.xq_b >= 0).any() and (tb.xq_b < 0).any()
+    ev = TableEval(tb)
+    rng = np.random.default_rng(4)
+    X0, P = sc.instance_data(pr, 1)
+    X0[0, :7] = 0.3
+    x = X0[0] + 0.05 * rng.standard_normal(tb.n)
+    V = ev.tape(P[0])
+    J = ev.jac_dense(x, V)
+    lam = rng.standard_normal(tb.m)
+    W = ev.hess_dense(x, V, lam)
+    h = 1e-6
+    for j in rng.choice(tb.n, 8, replace=False):
+        e = np.zeros(tb.n)
+        e[j] = h
+        fd = (ev.g(x + e, V) - ev.g(x - e, V)) / (2 * h)
+        assert np.abs(fd - J[:, j]).max() < 1e-6 * max(1., np.abs(J[:, j]).max())
+        dj = (ev.jac_dense(x + e, V).T @ lam - ev.jac_dense(x - e, V).T @ lam) / (2 * h)
+        assert np.abs(dj - W[:, j]).max() < 1e-5 * max(1., np.abs(W[:, j]).max())
+    rc = ipm_c.solve_batch_full(tb, X0, P, threads=1)
+    rn = ipm_ref.solve(tb, X0[0], P[0])
+    assert rc['status'][0] == 0 == rn.status and abs(int(rc['iters'][0]) - rn.iters) <= 1
+    assert np.abs(rc['x'][0] - rn.x)[:14].max() < 1e-5
+    g = ev.g(rc['x'][0], V)
+    assert (g <= tb.ubg + 1e-4).all() and (g >= tb.lbg - 1e-4).all()
+
+
 def test_holonomic_orient_solves():
     """vehicles/holonomicorient.py (examples/p2p_holonomic_orient.py, fixed end time):
     rectangular vehicle with free heading, degree-4 collision rows; the oracle converges to a
@@ -645,7 +686,7 @@ def test_more_reference_examples_lower_and_solve():
 
 
 EXT_GOLDEN = ('config_dubins_plain', 'config_dubins_rect', 'config_dubins_exact',
-              'config_holonomic_orient')
+              'config_holonomic_orient', 'config_bicycle', 'config_agv')
 
 
 def _model_golden(name):
@@ -691,7 +732,7 @@ def test_nlp_definition_equals_the_references_own_model_code(name):
 
 @pytest.mark.parametrize('name', ['config1', 'config4', 'config5', 'config_holonomic3d',
                                   'config_quadrotor2d', 'config_dubins', 'config_dubins_plain',
-                                  'config_dubins_rect', 'config_holonomic_orient'])
+                                  'config_holonomic_orient', 'config_bicycle'])
 def test_trajectory_extraction_equals_the_references(name):
     """Post-solve extraction: the reference's Vehicle.store ->
     concat_splines / splines2signals / sample_splines, run from /root/reference on a

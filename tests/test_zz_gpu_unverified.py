@@ -59,3 +59,18 @@ def test_holonomic_orient_matches_oracle():
     err = np.abs(res['x'] - ref['x'])[ok][:, :39].max(axis=1)
     assert np.median(err) < 1e-3
     assert np.abs(res['f'] - ref['f'])[ok].max() < 1e-3
+
+
+def test_bicycle_mid_mid_hessian_matches_oracle():
+    """Bicycle (vehicles/bicycle.py): rows with products of two shared product splines ->
+    the C^T M C gather of the XL kernel, from a rolling initial guess."""
+    pr = sc.config_bicycle()
+    tb = pr.father.tables
+    X0, P = sc.instance_data(pr, 4, jitter=0.02, seed=3)
+    X0[:, :7] = 0.3
+    res = pr.problem.solve_batch(X0, P)
+    ref = ipm_c.solve_batch_full(tb, X0, P, threads=4)
+    both = (res['status'] == 0) & (ref['status'] == 0)
+    assert both.sum() >= 2
+    assert res['status'][0] == 0 and res['iters'][0] == ref['iters'][0]
+    assert np.abs(res['x'] - ref['x'])[0].max() < 1e-4
