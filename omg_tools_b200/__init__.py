@@ -15,6 +15,7 @@ from .vehicles.dubins import Dubins
 from .vehicles.bicycle import Bicycle
 from .vehicles.agv import AGV
 from .vehicles.quadrotor3d import Quadrotor3D
+from .vehicles.quadrotor3d_simple import SimpleQuadrotor3D
 from .vehicles.fleet import Fleet
 from .environment.environment import Environment
 from .environment.obstacle import Obstacle

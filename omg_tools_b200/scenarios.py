@@ -230,6 +230,24 @@ def config_agv(options=None, build_solver=True):
     return _p2p(vehicle, environment, options, build_solver)
 
 
+def config_quadrotor3d_simple(options=None, build_solver=True):
+    """SimpleQuadrotor3D (position splines of degree 4, quadratic thrust / rate / tilt rows)
+    in the scene of examples/p2p_3dquadrotor.py: Cuboid(8, 6, 8) room, two plates, the second
+    one moving down; horizon 10 s.  (No reference example uses this model.)"""
+    from . import SimpleQuadrotor3D, Cuboid, Plate, Rectangle
+    vehicle = SimpleQuadrotor3D(0.5)
+    vehicle.set_initial_conditions([-3, -2, -0.5, 0, 0, 0, 0, 0])
+    vehicle.set_terminal_conditions([3, 2, 0.5])
+    vehicle.set_options({'safety_distance': 0.1, 'safety_weight': 10})
+    environment = Environment(room={'shape': Cuboid(8, 6, 8)})
+    plate = lambda: Plate(Rectangle(5., 8.), 0.1, orientation=[0., np.pi / 2, 0.])
+    trajectory = {'velocity': {'time': [1.5], 'values': [[0, 0, -0.6]]}}
+    environment.add_obstacle(Obstacle({'position': [-2, 0, -2]}, shape=plate()))
+    environment.add_obstacle(Obstacle({'position': [2, 0, 3.5]}, shape=plate(),
+                                      simulation={'trajectories': trajectory}))
+    return _p2p(vehicle, environment, options, build_solver)
+
+
 def config_holonomic_orient(options=None, build_solver=True):
     """examples/p2p_holonomic_orient.py with a fixed end time: HolonomicOrient
     (Rectangle(0.2, 0.4), heading free, norm-1 regularisation of the heading rate),
@@ -278,7 +296,8 @@ def instance_data(problem, batch, jitter=0.0, seed=0, current_time=0.):
     rng = np.random.default_rng(seed)
     vehicle = problem.vehicles[0]
     state0 = np.array(vehicle.prediction['state'], dtype=float)
-    poseT = np.array(vehicle.poseT, dtype=float)
+    goal = 'poseT' if hasattr(vehicle, 'poseT') else 'positionT'   # SimpleQuadrotor3D
+    poseT = np.array(getattr(vehicle, goal), dtype=float)
     obst0 = [o.signals['position'][:, -1].copy()
              for o in problem.environment.obstacles]
     X0 = np.zeros((batch, f.tables.n))
@@ -286,14 +305,15 @@ def instance_data(problem, batch, jitter=0.0, seed=0, current_time=0.):
     for b in range(batch):
         if jitter > 0. and b > 0:
             vehicle.prediction['state'] = state0 + rng.uniform(-jitter, jitter, len(state0))
-            vehicle.poseT = poseT + rng.uniform(-jitter, jitter, len(poseT))
+            setattr(vehicle, goal, poseT + rng.uniform(-jitter, jitter, len(poseT)))
             for o, p0 in zip(problem.environment.obstacles, obst0):
                 o.signals['position'][:, -1] = p0 + rng.uniform(
                     -0.5 * jitter, 0.5 * jitter, len(p0))
         problem.reinitialize()
         X0[b] = f.get_variables().cat
         P[b] = f.set_parameters(current_time).cat
-    vehicle.prediction['state'], vehicle.poseT = state0, poseT
+    vehicle.prediction['state'] = state0
+    setattr(vehicle, goal, poseT)
     for o, p0 in zip(problem.environment.obstacles, obst0):
         o.signals['position'][:, -1] = p0
     problem.reinitialize()

@@ -352,6 +352,19 @@ def build_reference(name):
         environment.add_obstacle(obs.Obstacle({'position': [1., -0.35]}, shape=rectangle))
         environment.add_obstacle(obs.Obstacle({'position': [3.4, -0.35]}, shape=rectangle))
         options = {}
+    elif name == 'config_quadrotor3d_simple':
+        qs = ref_import('vehicles.quadrotor3d_simple')
+        vehicle = qs.SimpleQuadrotor3D(0.5)
+        vehicle.set_initial_conditions(np.array([-3, -2, -0.5, 0, 0, 0, 0, 0], float))
+        vehicle.set_terminal_conditions([3, 2, 0.5])
+        vehicle.set_options({'safety_distance': 0.1, 'safety_weight': 10})
+        environment = env.Environment(room={'shape': shp.Cuboid(8, 6, 8)})
+        plate = lambda: shp.Plate(shp.Rectangle(5., 8.), 0.1, orientation=[0., np.pi / 2, 0.])
+        trajectory = {'velocity': {'time': [1.5], 'values': [[0, 0, -0.6]]}}
+        environment.add_obstacle(obs.Obstacle({'position': [-2, 0, -2]}, shape=plate()))
+        environment.add_obstacle(obs.Obstacle({'position': [2, 0, 3.5]}, shape=plate(),
+                                              simulation={'trajectories': trajectory}))
+        options = {}
     elif name == 'config_holonomic_orient':
         ho = ref_import('vehicles.holonomicorient')
         vehicle = ho.HolonomicOrient()
@@ -501,7 +514,8 @@ BASE_NAMES = ('config1', 'config2', 'config4', 'config5', 'config_holonomic3d',
 # second fixture file (model_golden_ext.npz, `--ext`): formulations whose rows multiply the
 # intermediates by decision variables
 EXT_NAMES = ('config_dubins_plain', 'config_dubins_rect', 'config_dubins_exact',
-             'config_holonomic_orient', 'config_bicycle', 'config_agv')
+             'config_holonomic_orient', 'config_bicycle', 'config_agv',
+             'config_quadrotor3d_simple')
 
 
 def main(ext=False):

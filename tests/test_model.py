@@ -608,6 +608,25 @@ def test_bicycle_tables_and_solve():
     assert (g <= tb.ubg + 1e-4).all() and (g >= tb.lbg - 1e-4).all()
 
 
+def test_simple_quadrotor3d_solves():
+    """vehicles/quadrotor3d_simple.py: quadratic (non-convex) thrust / body-rate / tilt rows;
+    the oracle converges to a feasible trajectory that reaches the goal."""
+    from oracle import ipm_c
+    if not ipm_c.available():
+        pytest.skip('C oracle not built')
+    pr = sc.config_quadrotor3d_simple(build_solver=False)
+    tb = pr.father.tables
+    assert (tb.n, tb.m, tb.n_par, tb.degree, tb.n_mid) == (200, 913, 64, 2, 0)
+    X0, P = sc.instance_data(pr, 1)
+    r = ipm_c.solve_batch_full(tb, X0, P, threads=1)
+    assert r['status'][0] == 0
+    ev = TableEval(tb)
+    g = ev.g(r['x'][0], ev.tape(P[0]))
+    assert (g <= tb.ubg + 1e-4).all() and (g >= tb.lbg - 1e-4).all()
+    L = len(pr.vehicles[0].basis)
+    assert np.abs(r['x'][0][[L - 1, 2 * L - 1, 3 * L - 1]] - [3., 2., 0.5]).max() < 1e-2
+
+
 def test_holonomic_orient_solves():
     """vehicles/holonomicorient.py (examples/p2p_holonomic_orient.py, fixed end time):
     rectangular vehicle with free heading, degree-4 collision rows; the oracle converges to a
@@ -686,7 +705,8 @@ def test_more_reference_examples_lower_and_solve():
 
 
 EXT_GOLDEN = ('config_dubins_plain', 'config_dubins_rect', 'config_dubins_exact',
-              'config_holonomic_orient', 'config_bicycle', 'config_agv')
+              'config_holonomic_orient', 'config_bicycle', 'config_agv',
+              'config_quadrotor3d_simple')
 
 
 def _model_golden(name):
@@ -732,7 +752,8 @@ def test_nlp_definition_equals_the_references_own_model_code(name):
 
 @pytest.mark.parametrize('name', ['config1', 'config4', 'config5', 'config_holonomic3d',
                                   'config_quadrotor2d', 'config_dubins', 'config_dubins_plain',
-                                  'config_holonomic_orient', 'config_bicycle'])
+                                  'config_holonomic_orient', 'config_bicycle',
+                                  'config_quadrotor3d_simple'])
 def test_trajectory_extraction_equals_the_references(name):
     """Post-solve extraction: the reference's Vehicle.store ->
     concat_splines / splines2signals / sample_splines, run from /root/reference on a

@@ -74,3 +74,15 @@ def test_bicycle_mid_mid_hessian_matches_oracle():
     assert both.sum() >= 2
     assert res['status'][0] == 0 and res['iters'][0] == ref['iters'][0]
     assert np.abs(res['x'] - ref['x'])[0].max() < 1e-4
+
+
+def test_simple_quadrotor3d_matches_oracle():
+    """SimpleQuadrotor3D (standard kernel, 1 block/SM layout: 226 KB of shared memory)."""
+    pr = sc.config_quadrotor3d_simple()
+    tb = pr.father.tables
+    X0, P = sc.instance_data(pr, 4, jitter=0.05, seed=1)
+    res = pr.problem.solve_batch(X0, P)
+    ref = ipm_c.solve_batch_full(tb, X0, P, threads=4)
+    assert np.array_equal(res['status'], ref['status']) and res['status'][0] == 0
+    ok = ref['status'] == 0
+    assert np.median(np.abs(res['x'] - ref['x'])[ok][:, :42].max(axis=1)) < NORTH_STAR_TOL
