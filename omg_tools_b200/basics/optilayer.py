@@ -555,6 +555,16 @@ class OptiChild(object):
     def _define(self, name, size0, size1, dictionary, kind, value=None):
         if value is None:
             value = np.zeros((size0, size1))
+        # The reference identifies symbols BY NAME when it composes the problem
+        # (optilayer.py:204-223, 274-294): an entry defined twice under one name (the
+        # obstacle parameters when several vehicles share an environment,
+        # environment.py:129; the terminal slacks 'g0', 'g1' of a multi-vehicle
+        # point-to-point problem, point2point.py:160-163) is ONE entry of the
+        # variable / parameter vector.  Symbols here are identified by id, so the
+        # first definition is reused.
+        if name in dictionary and dictionary[name].shape == (size0, size1):
+            self._values[name] = value
+            return dictionary[name]
         dictionary[name] = pl.sym_array(self._add_label(name), kind,
                                         size0, size1)
         self._values[name] = value

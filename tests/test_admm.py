@@ -130,6 +130,86 @@ def test_admm_oracle_nesterov_acceleration(formation):
         assert pr[-1] < 0.3 * pr[0]          # primal residual (consensus error) shrinks
 
 
+def test_admm_converges_to_the_centralised_optimum():
+    """Independent check of the whole ADMM machinery (x-update NLP with the augmented
+    Lagrangian, consensus projector, multiplier update, neighbour exchange): its fixed
+    point must be the optimum of the COUPLED problem -- all four vehicles in one NLP with the
+    formation constraints x_i + r_i = x_j + r_j as equality rows (what the reference's
+    FormationPoint2pointCentral states, formation_central.py:36-78, here with one terminal
+    slack per vehicle so that the objective is the sum of the agents' objectives).  The
+    coupled NLP (n = 472, m = 2390) is solved by the C oracle; 100 ADMM iterations bring every
+    agent's spline coefficients to within 2 cm of it."""
+    from oracle import ipm_c
+    from oracle.admm_ref import ADMMOracle
+    if not ipm_c.available():
+        pytest.skip('C oracle not built')
+    from omg_tools_b200 import (Holonomic, Fleet, Environment, Obstacle, Rectangle, Square,
+                                RegularPolyhedron)
+    from omg_tools_b200.problems.point2point import FixedTPoint2point
+    from omg_tools_b200.basics.optilayer import inf
+    from omg_tools_b200.basics.spline_extra import definite_integral
+    from omg_tools_b200.basics.lowering import lower
+
+    class Coupled(FixedTPoint2point):
+        def define_terminal_constraints(self):
+            objective = 0.
+            for v, vehicle in enumerate(self.vehicles):
+                term_con, term_con_der = vehicle.get_terminal_constraints(vehicle.splines[0])
+                for k, (spline, condition) in enumerate(term_con):
+                    g = self.define_spline_variable('g%d_%d' % (v, k), 1, basis=spline.basis)[0]
+                    objective += definite_integral(g, self.t0, 1.)
+                    self.define_constraint(spline - condition - g, -inf, 0.)
+                    self.define_constraint(-spline + condition - g, -inf, 0.)
+                for spline, condition in term_con_der:
+                    self.define_constraint(spline(1.) - condition, 0., 0.)
+            self.define_objective(objective)
+
+        def construct(self):
+            FixedTPoint2point.construct(self)
+            for a, b in zip(self.vehicles[:-1], self.vehicles[1:]):     # a chain: no redundant rows
+                for d in range(2):
+                    self.define_constraint((a.splines[0][d] + a.rel_pos_c[d]) -
+                                           (b.splines[0][d] + b.rel_pos_c[d]), 0., 0.)
+
+    N = 4
+    vehicles = [Holonomic() for _ in range(N)]
+    fleet = Fleet(vehicles)
+    configuration = RegularPolyhedron(0.2, N, np.pi / 4.).vertices.T
+    fleet.set_configuration(configuration.tolist())
+    fleet.set_initial_conditions((np.array([-1.5, -1.5]) + configuration).tolist())
+    fleet.set_terminal_conditions((np.array([2., 2.]) + configuration).tolist())
+    environment = Environment(room={'shape': Square(5.)})
+    rectangle = Rectangle(width=3., height=0.2)
+    environment.add_obstacle(Obstacle({'position': [-2.1, -0.5]}, shape=rectangle))
+    environment.add_obstacle(Obstacle({'position': [1.7, -0.5]}, shape=rectangle))
+    pr = Coupled(fleet, environment, {'verbose': 0, 'horizon_time': 10})
+    f = pr.father
+    f.reset()
+    pr.construct()
+    f.translate_symbols()
+    f.construct_variables()
+    f.construct_parameters()
+    rows, lb, ub = f.construct_constraints()
+    tb = f.tables = lower(f._var_ids, f._par_ids, rows, f.construct_objective(), lb, ub, f.order_hint())
+    f.init_variables()
+    f.init_parameters()
+    f.init_transformations(pr.init_primal_transform, pr.init_dual_transform)
+    pr.reinitialize()
+    assert (tb.n, tb.m) == (4 * 118, 2390)
+    r = ipm_c.solve_batch_full(tb, f.get_variables().cat[None], f.set_parameters(0.).cat[None], threads=1,
+                               options={'tol': 1e-6, 'compl_inf_tol': 1e-7, 'constr_viol_tol': 1e-7})
+    assert r['status'][0] == 0
+    ent = f._var_struct.entries
+    central = np.array([r['x'][0][ent[(v.label, 'splines_seg0')][0]:][:26] for v in vehicles])
+    orc = ADMMOracle(sc.config3(N, build_solver=False))
+    err = []
+    for k in range(100):
+        p_res, d_res, c_res = orc.dual_update(0.)
+        err.append(np.abs(orc.x_i - central).max())
+    assert err[0] > 0.4 and err[-1] < 0.02 and min(err[-10:]) < 0.01
+    assert p_res < 0.02
+
+
 def test_admm_ama_option(formation):
     """Option 'AMA' (alternating minimisation, reference admm.py:97-104): the x-update
     drops the quadratic penalty -- the agent NLP's objective becomes linear in x (no
