@@ -320,6 +320,50 @@ def instance_data(problem, batch, jitter=0.0, seed=0, current_time=0.):
     return X0, P
 
 
+def config_formation_central(options=None, build_solver=True, soft=True):
+    """examples/formation_holonomic_central.py: four Holonomic vehicles starting in a row,
+    formation RegularPolyhedron(0.2, 4) to (2, 2), two Rectangle(3, 0.2) walls, horizon 15 s,
+    soft formation constraints with weight 100 (the example's inter-vehicle avoidance is
+    not built)."""
+    from .vehicles.fleet import Fleet
+    from .basics.shape import RegularPolyhedron
+    from .problems.formation_central import FormationPoint2pointCentral
+    N = 4
+    vehicles = [Holonomic() for _ in range(N)]
+    for k, vehicle in enumerate(vehicles):
+        vehicle.set_initial_conditions([-1. - 0.5 * N * 0.5 + 0.5 * k, -1.5])
+    fleet = Fleet(vehicles)
+    configuration = RegularPolyhedron(0.2, N, np.pi / 4.).vertices.T
+    fleet.set_configuration(configuration.tolist())
+    fleet.set_terminal_conditions((np.array([2., 2.]) + configuration).tolist())
+    environment = Environment(room={'shape': Square(5.)})
+    rectangle = Rectangle(width=3., height=0.2)
+    environment.add_obstacle(Obstacle({'position': [-1.8, 0.5]}, shape=rectangle))
+    environment.add_obstacle(Obstacle({'position': [1.7, 0.5]}, shape=rectangle))
+    opts = {'verbose': 0, 'horizon_time': 15, 'soft_formation': soft,
+            'soft_formation_weight': 100}
+    opts.update(options or {})
+    problem = FormationPoint2pointCentral(fleet, environment, options=opts)
+    if build_solver:
+        problem.init()
+    else:
+        problem.father.reset()
+        problem.construct()
+        f = problem.father
+        f.translate_symbols()
+        f.construct_variables()
+        f.construct_parameters()
+        rows, lb, ub = f.construct_constraints()
+        from .basics.lowering import lower
+        f.tables = lower(f._var_ids, f._par_ids, rows, f.construct_objective(), lb, ub,
+                         f.order_hint())
+        f.init_variables()
+        f.init_parameters()
+        f.init_transformations(problem.init_primal_transform, problem.init_dual_transform)
+    problem.reinitialize()
+    return problem
+
+
 def config3(n_agents=4, options=None, build_solver=True, rank=0, world=1, group=None):
     """FormationPoint2point ADMM (examples/formation_holonomic.py scaled to
     n_agents, 2 rectangular obstacles as in the C++ formation test): agents on

@@ -186,7 +186,8 @@ def install_stubs():
     cas.mtimes, cas.vertcat = mtimes, vertcat
     cas.cos, cas.sin = _unary(np.cos), _unary(np.sin)
     cas.symvar = lambda x: []          # only feeds a bookkeeping dict (optilayer.py:529-533)
-    for name in ('Function', 'nlpsol', 'external', 'substitute', 'vertsplit',
+    cas.vertsplit = lambda x: [x[i] for i in range(x.shape[0])]
+    for name in ('Function', 'nlpsol', 'external', 'substitute',
                  'Compiler', 'Importer'):
         setattr(cas, name, lambda *a, **k: None)
     tools = types.ModuleType('casadi.tools')
@@ -365,6 +366,27 @@ def build_reference(name):
         environment.add_obstacle(obs.Obstacle({'position': [2, 0, 3.5]}, shape=plate(),
                                               simulation={'trajectories': trajectory}))
         options = {}
+    elif name == 'config_formation_central':
+        fl = ref_import('vehicles.fleet')
+        fc = ref_import('problems.formation_central')
+        N = 4
+        vehicles = [hol.Holonomic() for _ in range(N)]
+        for k, vehicle in enumerate(vehicles):
+            vehicle.set_initial_conditions([-1. - 0.5 * N * 0.5 + 0.5 * k, -1.5])
+        fleet = fl.Fleet(vehicles)
+        configuration = shp.RegularPolyhedron(0.2, N, np.pi / 4.).vertices.T
+        fleet.set_configuration(configuration.tolist())
+        fleet.set_terminal_conditions((np.array([2., 2.]) + configuration).tolist())
+        environment = env.Environment(room={'shape': shp.Square(5.)})
+        rectangle = shp.Rectangle(width=3., height=0.2)
+        environment.add_obstacle(obs.Obstacle({'position': [-1.8, 0.5]}, shape=rectangle))
+        environment.add_obstacle(obs.Obstacle({'position': [1.7, 0.5]}, shape=rectangle))
+        problem = fc.FormationPoint2pointCentral(
+            fleet, environment, options={'verbose': 0, 'horizon_time': 15, 'soft_formation': True,
+                                         'soft_formation_weight': 100})
+        problem.father.reset()
+        problem.construct()
+        return problem
     elif name == 'config_holonomic_orient':
         ho = ref_import('vehicles.holonomicorient')
         vehicle = ho.HolonomicOrient()
@@ -515,7 +537,7 @@ BASE_NAMES = ('config1', 'config2', 'config4', 'config5', 'config_holonomic3d',
 # intermediates by decision variables
 EXT_NAMES = ('config_dubins_plain', 'config_dubins_rect', 'config_dubins_exact',
              'config_holonomic_orient', 'config_bicycle', 'config_agv',
-             'config_quadrotor3d_simple')
+             'config_quadrotor3d_simple', 'config_formation_central')
 
 
 def main(ext=False):
@@ -527,7 +549,8 @@ def main(ext=False):
         Xs, Ps, Gs, Fs = [], [], [], []
         for k in range(n_samples):
             REG = Registry(seed=1000 * k + 7)
-            horizon = {'config4': 5., 'config_quadrotor2d': 5., 'config_holonomic3d': 12.}.get(name, 10.)
+            horizon = {'config4': 5., 'config_quadrotor2d': 5., 'config_holonomic3d': 12.,
+                       'config_formation_central': 15.}.get(name, 10.)
             # T is the horizon of the scenario, t a time inside the first knot interval
             REG.fixed = {'T': horizon, 't': 0.037 * horizon * (k + 1)}
             # labels restart for every build so that the layout strings are comparable

@@ -115,6 +115,20 @@ def test_xl_kernel_mid_mid_hessian_bicycle(emu):
     assert np.abs(res['f'] - ref['f']).max() < 1e-7
 
 
+def test_xl_kernel_k_in_scratch_central_formation(emu):
+    """FormationPoint2pointCentral (n = 420, KKT envelope 390 KB): the XL kernel with K in the
+    L2-resident scratch, 2 blocks/SM layout."""
+    pr = sc.config_formation_central()
+    tb, f = pr.father.tables, pr.father
+    info = pr.problem.info()
+    assert tb.env_size * 8 > 232448 and info['ctas_per_sm'] == 2
+    X0, P = f.get_variables().cat[None], f.set_parameters(0.).cat[None]
+    res = pr.problem.solve_batch(X0, P)
+    ref = ipm_c.solve_batch_full(tb, X0, P, threads=1)
+    assert res['status'][0] == 0 and res['iters'][0] == ref['iters'][0]
+    assert np.abs(res['x'] - ref['x']).max() < 1e-6
+
+
 def test_edge_cases_and_dropin(emu):
     """Empty batch, per-instance bounds, NaN parameters, max_iter, warm start with
     multipliers, Problem.solve()."""

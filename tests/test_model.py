@@ -627,6 +627,33 @@ def test_simple_quadrotor3d_solves():
     assert np.abs(r['x'][0][[L - 1, 2 * L - 1, 3 * L - 1]] - [3., 2., 0.5]).max() < 1e-2
 
 
+def test_formation_central_solves():
+    """problems/formation_central.py (examples/formation_holonomic_central.py): four vehicles
+    in one NLP with soft formation constraints; the fleet shares the terminal and formation
+    slack splines (the reference's name-based composition).  The oracle converges to a
+    feasible (local) solution through the gap with a formation error below 5 cm."""
+    from oracle import ipm_c
+    if not ipm_c.available():
+        pytest.skip('C oracle not built')
+    pr = sc.config_formation_central(build_solver=False)
+    tb, f = pr.father.tables, pr.father
+    assert (tb.n, tb.m, tb.n_par) == (420, 2468, 70)
+    names = [k[1] for k in f._var_struct.entries.keys()]
+    assert names.count('g0') == 1 and names.count('eps_form_00') == 1
+    r = ipm_c.solve_batch_full(tb, f.get_variables().cat[None], f.set_parameters(0.).cat[None], threads=1)
+    assert r['status'][0] == 0
+    x = r['x'][0]
+    ent = f._var_struct.entries
+    C = np.array([x[ent[(v.label, 'splines_seg0')][0]:][:26] for v in pr.vehicles]).reshape(4, 2, 13)
+    ev = TableEval(tb)
+    g = ev.g(x, ev.tape(f.set_parameters(0.).cat))
+    assert (g <= tb.ubg + 1e-4).all() and (g >= tb.lbg - 1e-4).all()
+    goals = np.array([v.poseT for v in pr.vehicles])
+    assert np.abs(C[:, 1, -1] - goals[:, 1]).max() < 1e-2     # through the gap, y reached
+    centre = C + np.array([v.rel_pos_c for v in pr.vehicles])[:, :, None]
+    assert np.abs(centre - centre.mean(0)).max() < 0.05
+
+
 def test_holonomic_orient_solves():
     """vehicles/holonomicorient.py (examples/p2p_holonomic_orient.py, fixed end time):
     rectangular vehicle with free heading, degree-4 collision rows; the oracle converges to a
@@ -706,7 +733,7 @@ def test_more_reference_examples_lower_and_solve():
 
 EXT_GOLDEN = ('config_dubins_plain', 'config_dubins_rect', 'config_dubins_exact',
               'config_holonomic_orient', 'config_bicycle', 'config_agv',
-              'config_quadrotor3d_simple')
+              'config_quadrotor3d_simple', 'config_formation_central')
 
 
 def _model_golden(name):
