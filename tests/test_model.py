@@ -631,7 +631,7 @@ def test_formation_central_solves():
     """problems/formation_central.py (examples/formation_holonomic_central.py): four vehicles
     in one NLP with soft formation constraints; the fleet shares the terminal and formation
     slack splines (the reference's name-based composition).  The oracle converges to a
-    feasible (local) solution through the gap with a formation error below 5 cm."""
+    feasible (local) solution through the gap, in formation from mid-horizon on."""
     from oracle import ipm_c
     if not ipm_c.available():
         pytest.skip('C oracle not built')
@@ -651,7 +651,8 @@ def test_formation_central_solves():
     goals = np.array([v.poseT for v in pr.vehicles])
     assert np.abs(C[:, 1, -1] - goals[:, 1]).max() < 1e-2     # through the gap, y reached
     centre = C + np.array([v.rel_pos_c for v in pr.vehicles])[:, :, None]
-    assert np.abs(centre - centre.mean(0)).max() < 0.05
+    # (the vehicles start in a row; the soft constraints pull them into formation)
+    assert np.abs(centre - centre.mean(0))[:, :, 5:].max() < 1e-3
 
 
 def test_holonomic_orient_solves():
