@@ -652,7 +652,9 @@ def test_formation_central_solves():
     assert np.abs(C[:, 1, -1] - goals[:, 1]).max() < 1e-2     # through the gap, y reached
     centre = C + np.array([v.rel_pos_c for v in pr.vehicles])[:, :, None]
     # (the vehicles start in a row; the soft constraints pull them into formation)
-    assert np.abs(centre - centre.mean(0))[:, :, 5:].max() < 1e-3
+    # and let it deform by a few cm while squeezing through the 0.5 m gap
+    err = np.abs(centre - centre.mean(0)).max(axis=(0, 1))
+    assert err[3:].max() < 0.15 and err[8:].max() < 1e-3
 
 
 def test_holonomic_orient_solves():
