@@ -95,6 +95,40 @@ class Environment(OptiChild):
             vehicle.define_collision_constraints(hyp_veh, room, splines[idx],
                                                  horizon_times[idx])
 
+    def define_intervehicle_collision_constraints(self, vehicles, horizon_times):
+        """Separating hyperplanes between every pair of vehicles (one per pair of shapes):
+        a, b on the degree-1 basis over the union of both vehicles' knots; vehicle k sees
+        (a, b), vehicle l the mirrored (-a, -b) (reference environment.py:148-175)."""
+        horizon_times = horizon_times if isinstance(horizon_times, list) \
+            else [horizon_times] * vehicles[0].n_seg
+        for idx in range(vehicles[0].n_seg):
+            hyp_veh = {veh: {sh: [] for sh in veh.shapes} for veh in vehicles}
+            for k in range(len(vehicles)):
+                for l in range(k + 1, len(vehicles)):
+                    veh1, veh2 = vehicles[k], vehicles[l]
+                    if veh1.n_dim != veh2.n_dim:
+                        raise ValueError('Not possible to combine ' + str(veh1.n_dim) +
+                                         'D and ' + str(veh2.n_dim) + 'D vehicle.')
+                    degree = 1
+                    knots = np.r_[np.zeros(degree),
+                                  np.union1d(veh1.knots[veh1.degree:-veh1.degree],
+                                             veh2.knots[veh2.degree:-veh2.degree]),
+                                  np.ones(degree)]
+                    basis = BSplineBasis(knots, degree)
+                    for kk, shape1 in enumerate(veh1.shapes):
+                        for ll, shape2 in enumerate(veh2.shapes):
+                            tag = '_' + veh1.label + '_' + 'seg' + str(idx) + '_' + str(kk) + \
+                                '_' + veh2.label + '_' + str(ll)
+                            a = self.define_spline_variable('a' + tag, self.n_dim, basis=basis)
+                            b = self.define_spline_variable('b' + tag, 1, basis=basis)[0]
+                            self.define_constraint(
+                                sum([a[p] * a[p] for p in range(self.n_dim)]) - 1, -inf, 0.)
+                            hyp_veh[veh1][shape1].append({'a': a, 'b': b})
+                            hyp_veh[veh2][shape2].append({'a': [-a_i for a_i in a], 'b': -b})
+            for vehicle in vehicles:
+                vehicle.define_collision_constraints(hyp_veh[vehicle], self.room[idx],
+                                                     vehicle.splines[idx], horizon_times[idx])
+
     def init(self, horizon_times=None):
         for obstacle in self.obstacles:
             obstacle.init(horizon_times=horizon_times)

@@ -49,6 +49,8 @@ class Point2pointProblem(Problem):
             splines = vehicle.define_splines(n_seg=1)
             vehicle.define_trajectory_constraints(splines[0], self.T)
             self.environment.define_collision_constraints(vehicle, splines, self.T)
+        if len(self.vehicles) > 1 and self.options.get('inter_vehicle_avoidance'):
+            self.environment.define_intervehicle_collision_constraints(self.vehicles, self.T)
 
     def define_init_constraints(self):
         for vehicle in self.vehicles:

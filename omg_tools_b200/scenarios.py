@@ -320,6 +320,23 @@ def instance_data(problem, batch, jitter=0.0, seed=0, current_time=0.):
     return X0, P
 
 
+def config_interveh(options=None, build_solver=True):
+    """examples/p2p_holonomic_interveh_avoidance.py: two Holonomic vehicles swapping places
+    across an empty Square(5) room, one NLP, separating hyperplanes between the vehicles
+    (Environment.define_intervehicle_collision_constraints)."""
+    N = 2
+    vehicles = [Holonomic() for _ in range(N)]
+    for k, vehicle in enumerate(vehicles):
+        vehicle.set_initial_conditions([1.5 * np.cos((k * 2. * np.pi) / N),
+                                        1.5 * np.sin((k * 2. * np.pi) / N)])
+        vehicle.set_terminal_conditions([-1.5 * np.cos((k * 2. * np.pi) / N),
+                                         -1.5 * np.sin((k * 2. * np.pi) / N)])
+    environment = Environment(room={'shape': Square(5.)})
+    opts = {'inter_vehicle_avoidance': True}
+    opts.update(options or {})
+    return _p2p(vehicles, environment, opts, build_solver)
+
+
 def config_formation_central(options=None, build_solver=True, soft=True):
     """examples/formation_holonomic_central.py: four Holonomic vehicles starting in a row,
     formation RegularPolyhedron(0.2, 4) to (2, 2), two Rectangle(3, 0.2) walls, horizon 15 s,

@@ -366,6 +366,20 @@ def build_reference(name):
         environment.add_obstacle(obs.Obstacle({'position': [2, 0, 3.5]}, shape=plate(),
                                               simulation={'trajectories': trajectory}))
         options = {}
+    elif name == 'config_interveh':
+        N = 2
+        vehicles = [hol.Holonomic() for _ in range(N)]
+        for k, vehicle in enumerate(vehicles):
+            vehicle.set_initial_conditions([1.5 * np.cos((k * 2. * np.pi) / N),
+                                            1.5 * np.sin((k * 2. * np.pi) / N)])
+            vehicle.set_terminal_conditions([-1.5 * np.cos((k * 2. * np.pi) / N),
+                                             -1.5 * np.sin((k * 2. * np.pi) / N)])
+        environment = env.Environment(room={'shape': shp.Square(5.)})
+        problem = p2p.Point2point(vehicles, environment, options={'verbose': 0}, freeT=False)
+        problem.set_options({'inter_vehicle_avoidance': True})
+        problem.father.reset()
+        problem.construct()
+        return problem
     elif name == 'config_formation_central':
         fl = ref_import('vehicles.fleet')
         fc = ref_import('problems.formation_central')
@@ -537,7 +551,7 @@ BASE_NAMES = ('config1', 'config2', 'config4', 'config5', 'config_holonomic3d',
 # intermediates by decision variables
 EXT_NAMES = ('config_dubins_plain', 'config_dubins_rect', 'config_dubins_exact',
              'config_holonomic_orient', 'config_bicycle', 'config_agv',
-             'config_quadrotor3d_simple', 'config_formation_central')
+             'config_quadrotor3d_simple', 'config_formation_central', 'config_interveh')
 
 
 def main(ext=False):

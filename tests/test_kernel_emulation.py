@@ -129,6 +129,28 @@ def test_xl_kernel_k_in_scratch_central_formation(emu):
     assert np.abs(res['x'] - ref['x']).max() < 1e-6
 
 
+def test_two_vehicles_with_intervehicle_avoidance(emu):
+    """A multi-vehicle NLP (examples/p2p_holonomic_interveh_avoidance.py): two vehicles swap
+    places, separated by a hyperplane spline.  The head-on start is symmetric (pass left or
+    right is decided by rounding), so the start is perturbed."""
+    pr = sc.config_interveh()
+    tb, f = pr.father.tables, pr.father
+    assert (tb.n, tb.m, tb.n_par) == (111, 619, 14)
+    rng = np.random.default_rng(0)
+    X0 = f.get_variables().cat[None] + 0.05 * rng.standard_normal((1, tb.n))
+    P = f.set_parameters(0.).cat[None]
+    res = pr.problem.solve_batch(X0, P)
+    ref = ipm_c.solve_batch_full(tb, X0, P, threads=1)
+    assert res['status'][0] == 0 and res['iters'][0] == ref['iters'][0]
+    assert np.abs(res['x'] - ref['x']).max() < 1e-8
+    x = res['x'][0]                      # the vehicles keep their distance: 2 x radius 0.1
+    ent = f._var_struct.entries
+    C = [x[ent[(v.label, 'splines_seg0')][0]:][:26].reshape(2, 13) for v in pr.vehicles]
+    S = pr.vehicles[0].basis.eval_basis(np.linspace(0., 1., 101))
+    d = np.hypot(*(S.dot((C[0] - C[1]).T).T))
+    assert d.min() > 0.2 - 1e-3
+
+
 def test_edge_cases_and_dropin(emu):
     """Empty batch, per-instance bounds, NaN parameters, max_iter, warm start with
     multipliers, Problem.solve()."""
