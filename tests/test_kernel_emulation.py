@@ -277,3 +277,27 @@ def test_admm_consensus_kernel(emu):
         e2 = TF.dot(z - np.r_[z_i[i], z_ij[i].reshape(-1)])
         pri, dri = e1.dot(e1), rho * e2.dot(e2)
         assert np.allclose(res[i], [pri, dri, rho * pri + dri], rtol=1e-9, atol=1e-12)
+
+
+def test_results_do_not_depend_on_the_thread_schedule(emu, monkeypatch):
+    """Race check without a GPU: the emulator resumes the runnable fibers of a block in
+    forward, reverse or random order between barriers (OMG_EMU_SCHED).  A read that no
+    barrier separates from another thread's write would change the result with the order;
+    the standard kernel, the XL kernel and its cross / mid-mid Hessian gathers give
+    bit-identical solutions and multipliers under every schedule.  (compute-sanitizer
+    racecheck on the GPU, profiles/r01_sanitizer.txt, covers the earlier kernel paths.)"""
+    cases = []
+    for name, B in (('config1', 2), ('config2', 1), ('config_dubins_plain', 1), ('config_bicycle', 1)):
+        pr = getattr(sc, name)()
+        X0, P = sc.instance_data(pr, B, jitter=0.1, seed=1)
+        if name == 'config_bicycle':
+            X0[:, :7] = 0.3
+        cases.append((pr, X0, P))
+    results = {}
+    for sched in ('forward', 'reverse', 'random:1', 'random:2'):
+        monkeypatch.setenv('OMG_EMU_SCHED', sched)
+        results[sched] = [pr.problem.solve_batch(X0, P) for pr, X0, P in cases]
+    for sched in ('reverse', 'random:1', 'random:2'):
+        for a, b in zip(results['forward'], results[sched]):
+            assert np.array_equal(a['iters'], b['iters']) and (a['status'] == 0).all()
+            assert np.array_equal(a['x'], b['x']) and np.array_equal(a['lam_g'], b['lam_g'])

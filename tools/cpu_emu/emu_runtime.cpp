@@ -123,9 +123,28 @@ void omg_emu_launch(int grid, int block, size_t smem_bytes, const std::function<
       for (int r = 0; r < 6; ++r) *--sp = nullptr;              // rbp rbx r12 r13 r14 r15
       fibers[i].sp = sp; fibers[i].state = RUN;
     }
+    // Schedule: the order in which runnable fibers are resumed between barriers.  A kernel
+    // without data races gives bit-identical results for every order; OMG_EMU_SCHED=reverse
+    // or =random:<seed> (tests/test_kernel_emulation.py) turns a read that is not separated
+    // from the write of another thread by a barrier into a different result.
+    std::vector<int> order(block);
+    for (int i = 0; i < block; ++i) order[i] = i;
+    const char* sched = getenv("OMG_EMU_SCHED");
+    const bool reverse = sched && strncmp(sched, "reverse", 7) == 0;
+    const bool shuffle = sched && strncmp(sched, "random", 6) == 0;
+    unsigned long long rng = 88172645463325252ULL;
+    if (shuffle && strchr(sched, ':')) rng ^= strtoull(strchr(sched, ':') + 1, nullptr, 10) * 2654435761ULL + (unsigned)b;
+    if (reverse) for (int i = 0; i < block; ++i) order[i] = block - 1 - i;
     while (alive > 0) {
       bool progress = false;
-      for (int i = 0; i < block; ++i) {
+      if (shuffle)
+        for (int i = block - 1; i > 0; --i) {
+          rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+          const int j = (int)(rng % (unsigned long long)(i + 1));
+          const int t = order[i]; order[i] = order[j]; order[j] = t;
+        }
+      for (int oi = 0; oi < block; ++oi) {
+        const int i = order[oi];
         if (fibers[i].state != RUN) continue;
         cur = i; threadIdx = uint3{(unsigned)i, 0, 0};
         omg_emu_switch(&sched_sp, fibers[i].sp);
