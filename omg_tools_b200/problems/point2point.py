@@ -201,6 +201,50 @@ class FixedTPoint2point(Point2pointProblem):
         return obj
 
 
+class FreeEndPoint2point(FixedTPoint2point):
+    """Fixed-T point-to-point problem whose terminal conditions (all, or those listed in
+    ``free_ind[vehicle]``) are decision variables ``conT<l>`` instead of parameters: the
+    agents of a RendezVous agree on them (reference point2point.py:377-417)."""
+
+    def __init__(self, fleet, environment, options, free_ind=None):
+        FixedTPoint2point.__init__(self, fleet, environment, options)
+        self.free_ind = free_ind
+
+    def construct(self):
+        if self.free_ind is None:
+            self._all_free = True
+            self.free_ind = {}
+        FixedTPoint2point.construct(self)
+
+    def define_terminal_constraints(self):
+        objective = 0.
+        self.term_con_len = []
+        spline = condition = None
+        for l, vehicle in enumerate(self.vehicles):
+            term_con, term_con_der = vehicle.get_terminal_constraints(vehicle.splines[0])
+            if getattr(self, '_all_free', False):
+                self.free_ind[vehicle] = list(range(len(term_con)))
+            conditions = self.define_variable('conT' + str(l), len(self.free_ind[vehicle]))
+            cnt = 0
+            self.term_con_len.append(len(term_con))
+            for k, (spl, cond) in enumerate(term_con):
+                if k in self.free_ind[vehicle]:
+                    spline, condition = spl, conditions[cnt]
+                    cnt += 1
+                else:
+                    spline, condition = spl, cond
+                g = self.define_spline_variable('g' + str(k), 1, basis=spline.basis)[0]
+                objective += definite_integral(g, self.t0, 1.)
+                self.define_constraint(spline - condition - g, -inf, 0.)
+                self.define_constraint(-spline + condition - g, -inf, 0.)
+            # as in the reference (point2point.py:415-416) the loop over the derivative
+            # conditions re-uses the LAST position spline and condition: it adds
+            # len(term_con_der) copies of  spline(1) - condition = 0
+            for _ in term_con_der:
+                self.define_constraint(spline(1.) - condition, 0., 0.)
+        self.define_objective(objective)
+
+
 class FreeTPoint2point(Point2pointProblem):
     """Minimum-time point-to-point problem: the motion time T is a decision
     variable and the objective (reference point2point.py:269-374).

@@ -320,6 +320,38 @@ def instance_data(problem, batch, jitter=0.0, seed=0, current_time=0.):
     return X0, P
 
 
+def config_free_end(options=None, build_solver=True):
+    """FreeEndPoint2point (the agent problem of a RendezVous): config 1's scene with the
+    terminal position as decision variables conT0."""
+    from .problems.point2point import FreeEndPoint2point
+    vehicle = Holonomic()
+    vehicle.set_options({'safety_distance': 0.1})
+    vehicle.set_initial_conditions([-1.5, -1.5])
+    vehicle.set_terminal_conditions([2., 2.])
+    environment = Environment(room={'shape': Square(5.)})
+    environment.add_obstacle(Obstacle({'position': [1.5, -1]}, shape=Circle(0.5)))
+    opts = {'verbose': 0}
+    opts.update(options or {})
+    problem = FreeEndPoint2point(vehicle, environment, opts, {vehicle: [0, 1]})
+    if build_solver:
+        problem.init()
+    else:
+        f = problem.father
+        f.reset()
+        problem.construct()
+        f.translate_symbols()
+        f.construct_variables()
+        f.construct_parameters()
+        rows, lb, ub = f.construct_constraints()
+        from .basics.lowering import lower
+        f.tables = lower(f._var_ids, f._par_ids, rows, f.construct_objective(), lb, ub, f.order_hint())
+        f.init_variables()
+        f.init_parameters()
+        f.init_transformations(problem.init_primal_transform, problem.init_dual_transform)
+    problem.reinitialize()
+    return problem
+
+
 def config_interveh(options=None, build_solver=True):
     """examples/p2p_holonomic_interveh_avoidance.py: two Holonomic vehicles swapping places
     across an empty Square(5) room, one NLP, separating hyperplanes between the vehicles

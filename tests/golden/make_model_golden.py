@@ -366,6 +366,17 @@ def build_reference(name):
         environment.add_obstacle(obs.Obstacle({'position': [2, 0, 3.5]}, shape=plate(),
                                               simulation={'trajectories': trajectory}))
         options = {}
+    elif name == 'config_free_end':
+        vehicle = hol.Holonomic()
+        vehicle.set_options({'safety_distance': 0.1})
+        vehicle.set_initial_conditions([-1.5, -1.5])
+        vehicle.set_terminal_conditions([2., 2.])
+        environment = env.Environment(room={'shape': shp.Square(5.)})
+        environment.add_obstacle(obs.Obstacle({'position': [1.5, -1]}, shape=shp.Circle(0.5)))
+        problem = p2p.FreeEndPoint2point(vehicle, environment, {'verbose': 0}, {vehicle: [0, 1]})
+        problem.father.reset()
+        problem.construct()
+        return problem
     elif name == 'config_interveh':
         N = 2
         vehicles = [hol.Holonomic() for _ in range(N)]
@@ -551,7 +562,7 @@ BASE_NAMES = ('config1', 'config2', 'config4', 'config5', 'config_holonomic3d',
 # intermediates by decision variables
 EXT_NAMES = ('config_dubins_plain', 'config_dubins_rect', 'config_dubins_exact',
              'config_holonomic_orient', 'config_bicycle', 'config_agv',
-             'config_quadrotor3d_simple', 'config_formation_central', 'config_interveh')
+             'config_quadrotor3d_simple', 'config_formation_central', 'config_interveh', 'config_free_end')
 
 
 def main(ext=False):

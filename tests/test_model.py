@@ -736,7 +736,8 @@ def test_more_reference_examples_lower_and_solve():
 
 EXT_GOLDEN = ('config_dubins_plain', 'config_dubins_rect', 'config_dubins_exact',
               'config_holonomic_orient', 'config_bicycle', 'config_agv',
-              'config_quadrotor3d_simple', 'config_formation_central', 'config_interveh')
+              'config_quadrotor3d_simple', 'config_formation_central', 'config_interveh',
+              'config_free_end')
 
 
 def _model_golden(name):
