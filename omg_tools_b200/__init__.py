@@ -20,7 +20,7 @@ from .vehicles.fleet import Fleet
 from .environment.environment import Environment
 from .environment.obstacle import Obstacle
 from .problems.problem import Problem
-from .problems.point2point import Point2point, FixedTPoint2point
+from .problems.point2point import Point2point, FixedTPoint2point, FreeEndPoint2point
 from .problems.formation_central import FormationPoint2pointCentral
 
 __version__ = '0.1.0'

@@ -41,7 +41,12 @@ class ADMMUpdater(OptiChild):
     def __init__(self):
         OptiChild.__init__(self, 'admm')
 
-    def construct(self, vehicle, p2p, n_nghb, ama=False):
+    def construct(self, vehicle, p2p, n_nghb, ama=False, shared=None):
+        """shared = None: the vehicle's spline coefficients (formation); otherwise a flat
+        array of symbols that are not splines (the free terminal conditions of a
+        RendezVous): no first-knot transformation."""
+        if shared is not None:
+            return self._construct_plain(np.asarray(shared).reshape(-1), n_nghb, ama)
         L, ns = len(vehicle.basis), vehicle.n_spl
         nsh = L * ns
         z_i = self.define_parameter('z_i', nsh)
@@ -77,6 +82,29 @@ class ADMMUpdater(OptiChild):
         for j in range(n_nghb):
             add(np.asarray(z_ji)[j * nsh:(j + 1) * nsh], np.asarray(l_ji)[j * nsh:(j + 1) * nsh])
         self.define_objective(obj)
+
+
+def _plain_objective(updater, x, n_nghb, ama):
+    nsh = len(x)
+    z_i = updater.define_parameter('z_i', nsh)
+    z_ji = updater.define_parameter('z_ji', nsh * n_nghb)
+    l_i = updater.define_parameter('l_i', nsh)
+    l_ji = updater.define_parameter('l_ji', nsh * n_nghb)
+    rho = updater.define_parameter('rho')
+    obj = Poly()
+    blocks = [(np.asarray(z_i), np.asarray(l_i))]
+    blocks += [(np.asarray(z_ji)[j * nsh:(j + 1) * nsh], np.asarray(l_ji)[j * nsh:(j + 1) * nsh])
+               for j in range(n_nghb)]
+    for z, l in blocks:
+        for k in range(nsh):
+            d = x[k] - z[k]
+            obj = obj + l[k] * d
+            if not ama:
+                obj = obj + 0.5 * rho * d * d
+    updater.define_objective(obj)
+
+
+ADMMUpdater._construct_plain = lambda self, x, n_nghb, ama: _plain_objective(self, x, n_nghb, ama)
 
 
 def _linear_rows(rows, var_syms, par_vals):
@@ -296,3 +324,87 @@ class FormationPoint2point(object):
             for c in range(shape[1]):
                 seg = slice(off + c * shape[0], off + (c + 1) * shape[0])
                 self.X[:, seg] = self.X[:, seg].dot(np.asarray(T).T)
+
+
+
+class RendezVous(FormationPoint2point):
+    """Vehicles that must agree on WHERE to meet: every agent solves a FreeEndPoint2point
+    (its terminal conditions conT0 are variables) and the ADMM consensus runs on conT0 +
+    rel_pos_c instead of on whole trajectories (reference ``omgtools/problems/
+    rendezvous.py``: agents 28-35, coupling constraints 37-61).  Same batched machinery as
+    FormationPoint2point; the shared block has no spline structure (block length 1, identity
+    first-knot transforms, nothing to shift over a knot)."""
+
+    def init(self, build_solver=True):
+        from .point2point import FreeEndPoint2point
+        veh = self.vehicles[0]
+        p2p_opts = {k: v for k, v in self.options.items()
+                    if k in ('horizon_time', 'solver', 'solver_options', 'verbose')}
+        free_ind = sorted(self.fleet.configuration[veh].keys())
+        self.p2p = FreeEndPoint2point(veh, self.environment.copy(), p2p_opts, {veh: free_ind})
+        self.updater = ADMMUpdater()
+        env = self.p2p.environment
+        father = OptiFather([veh, self.p2p, env, self.updater] + list(env.obstacles))
+        father.reset()
+        self.rel_pos_c = veh.define_parameter('rel_pos_c', len(free_ind))
+        self.p2p.father = father
+        self.p2p.construct()
+        conT = self.p2p._variables['conT0']
+        self.updater.construct(veh, self.p2p, self.n_nghb, self.options['AMA'], shared=conT)
+        self.father = father
+        if build_solver:
+            self.solver, _ = father.construct_problem(self.p2p.options)
+        else:
+            father.translate_symbols()
+            father.construct_variables()
+            father.construct_parameters()
+            rows, lb, ub = father.construct_constraints()
+            from ..basics.lowering import lower
+            father.tables = lower(father._var_ids, father._par_ids, rows,
+                                  father.construct_objective(), lb, ub, father.order_hint())
+            father.init_variables()
+            father.init_parameters()
+            self.solver = None
+        father.init_transformations(self.p2p.init_primal_transform, self.p2p.init_dual_transform)
+        self.tb = father.tables
+        self.basis = veh.basis
+        self.L, self.ns = 1, len(free_ind)            # shared blocks of length 1
+        self.nsh = len(free_ind)
+        self.knot_time = self.p2p.knot_time
+        self.T = self.options['horizon_time']
+        self.x_off = father._var_struct.entries[(self.p2p.label, 'conT0')][0]
+        self.par_off = {k: v[0] for k, v in father._par_struct.entries.items()}
+        self.veh_label, self.p2p_label, self.upd_label = veh.label, self.p2p.label, self.updater.label
+        self._build_consensus_projector()
+        self._init_agent_data()
+
+    def _build_consensus_projector(self):
+        """conT_i + r_i - (conT_j + r_j) = 0 for every neighbour j (rendezvous.py:47-58)."""
+        ns, nn = self.ns, self.n_nghb
+        nz = ns * (1 + nn)
+        syms = pl.sym_array('zc', 'var', nz, 1)[:, 0]
+        rel = pl.sym_array('relc', 'par', nz, 1)[:, 0]
+        rows = [(syms[k] + rel[k]) - (syms[(1 + j) * ns + k] + rel[(1 + j) * ns + k])
+                for j in range(nn) for k in range(ns)]
+        self._rel_ids = [r.single_symbol() for r in rel]
+        self._coupling_rows = rows
+        self._z_ids = [s.single_symbol() for s in syms]
+        A, _ = _linear_rows(rows, self._z_ids, {r: 0.0 for r in self._rel_ids})
+        self.A = A
+        self._rown = 1.0 / np.linalg.norm(A, axis=1)
+        An = A * self._rown[:, None]
+        self.M = An.T.dot(np.linalg.inv(An.dot(An.T)))
+        self.Pz = np.eye(nz) - self.M.dot(An)
+        self.nz = nz
+
+    def _cold_start(self, vehicle):
+        x = self.father._var_struct(0.)
+        x[self.veh_label, 'splines_seg0'] = vehicle.get_init_spline_value()[0]
+        x[self.p2p_label, 'conT0'] = np.asarray(vehicle.poseT, dtype=float)[:self.ns]
+        return x.cat
+
+    def first_knot_transforms(self, t):
+        return np.eye(1), np.eye(1)
+
+    def shared_shift_T(self):
+        return np.eye(1)

@@ -190,5 +190,8 @@ class FormationADMMRunner(object):
 
 
 def shift_T(problem):
+    """Knot-crossing transformation of the shared blocks (identity for a RendezVous)."""
+    if hasattr(problem, 'shared_shift_T'):
+        return problem.shared_shift_T()
     from ..basics.spline_extra import shiftoverknot_T
     return shiftoverknot_T(problem.basis)

@@ -442,3 +442,30 @@ def config3(n_agents=4, options=None, build_solver=True, rank=0, world=1, group=
                                    world=world, group=group)
     problem.init(build_solver=build_solver)
     return problem
+
+
+def config_rendezvous(n_agents=4, options=None, build_solver=True, rank=0, world=1, group=None):
+    """RendezVous (problems/admm.py; reference rendezvous.py, examples/
+    rendezvous_holonomic_export.py scaled to n_agents): Holonomic vehicles starting in the
+    corners of the room agree by ADMM on where to meet -- in a RegularPolyhedron(0.2)
+    configuration around a common centre; each agent only proposes its own terminal
+    position."""
+    from .vehicles.fleet import Fleet
+    from .basics.shape import RegularPolyhedron
+    from .problems.admm import RendezVous
+    vehicles = [Holonomic() for _ in range(n_agents)]
+    fleet = Fleet(vehicles)
+    ang = 2 * np.pi * np.arange(n_agents) / n_agents + np.pi / 4.
+    configuration = 0.2 * np.c_[np.cos(ang), np.sin(ang)]
+    init_positions = 1.8 * np.c_[np.cos(ang), np.sin(ang)] * np.array([1., 0.8])
+    terminal_positions = 0.5 * init_positions          # first proposals: half way to the middle
+    fleet.set_configuration(configuration.tolist())
+    fleet.set_initial_conditions(init_positions.tolist())
+    fleet.set_terminal_conditions(terminal_positions.tolist())
+    environment = Environment(room={'shape': Square(5.)})
+    environment.add_obstacle(Obstacle({'position': [0.9, 0.1]}, shape=Circle(0.3)))
+    opts = {'rho': 3., 'horizon_time': 10, 'verbose': 0}
+    opts.update(options or {})
+    problem = RendezVous(fleet, environment, options=opts, rank=rank, world=world, group=group)
+    problem.init(build_solver=build_solver)
+    return problem

@@ -39,7 +39,7 @@ class ADMMOracle(object):
         N, nsh, nn, L = p.N, p.nsh, p.n_nghb, p.L
         rho = p.options['rho']
         if t > 0. and int(np.round(self.time_prev / p.knot_time, 6)) < int(np.round(t / p.knot_time, 6)):
-            Ts = shiftoverknot_T(p.basis)
+            Ts = p.shared_shift_T() if hasattr(p, 'shared_shift_T') else shiftoverknot_T(p.basis)
             for name in ('x_i', 'z_i', 'l_i', 'x_j', 'z_ij', 'l_ij', 'z_ji', 'l_ji'):
                 a = getattr(self, name)
                 setattr(self, name, a.reshape(-1, L).dot(Ts.T).reshape(a.shape))
@@ -59,7 +59,8 @@ class ADMMOracle(object):
         self.x_j = self.x_i[p.nghb]
         # ---- z, l, residuals ------------------------------------------------------------
         t0 = (np.round(t, 6) % p.knot_time) / p.T
-        Tf, Tb = shiftfirstknot_T(p.basis, t0, inverse=True)
+        Tf, Tb = p.first_knot_transforms(t) if hasattr(p, 'shared_shift_T') else \
+            shiftfirstknot_T(p.basis, t0, inverse=True)
         nblk = nsh // L * (1 + nn)
         TF, TB = self._blockdiag(Tf, nblk), self._blockdiag(Tb, nblk)
         A = p.A

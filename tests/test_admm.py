@@ -210,6 +210,37 @@ def test_admm_converges_to_the_centralised_optimum():
     assert p_res < 0.02
 
 
+def test_rendezvous_reaches_consensus():
+    """RendezVous (reference rendezvous.py): agents solving FreeEndPoint2point problems agree
+    by ADMM on their terminal positions conT0 + rel_pos_c; the shared block has no spline
+    structure (block length 1, identity transforms).  Ten iterations bring the proposed
+    meeting centres of four vehicles from 0.5 m apart to below 1 mm, every x-update
+    converged, and the agreed point satisfies the coupling constraints."""
+    from oracle import ipm_c
+    from oracle.admm_ref import ADMMOracle
+    if not ipm_c.available():
+        pytest.skip('C oracle not built')
+    pr = sc.config_rendezvous(4, build_solver=False)
+    assert (pr.tb.n, pr.nsh, pr.L, pr.A.shape) == (87, 2, 1, (4, 6))
+    names = [k[1] for k in pr.father._var_struct.keys()]
+    assert 'conT0' in names
+    orc = ADMMOracle(pr)
+    spread = []
+    for _ in range(12):
+        p_res, d_res, c_res = orc.dual_update(0.)
+        assert np.all(orc.status == 0)
+        centre = orc.x_i + pr.relp
+        spread.append(np.abs(centre - centre.mean(0)).max())
+    assert spread[0] > 0.3 and spread[-1] < 1e-3 and p_res < 2e-3
+    for i in range(pr.N):
+        z = np.r_[orc.z_i[i], orc.z_ij[i].reshape(-1)]
+        assert np.abs(pr.A.dot(z) - pr._b_of(i)).max() < 1e-9
+    # every vehicle's trajectory ends at its agreed terminal position
+    L = len(pr.basis)
+    ends = orc.X[:, [L - 1, 2 * L - 1]]
+    assert np.abs(ends - orc.x_i).max() < 1e-2
+
+
 def test_admm_ama_option(formation):
     """Option 'AMA' (alternating minimisation, reference admm.py:97-104): the x-update
     drops the quadratic penalty -- the agent NLP's objective becomes linear in x (no

@@ -245,13 +245,18 @@ def test_admm_consensus_kernel(emu):
     vs the reference's KKT-solve formulas (admm.py:149-155, 260-266, 296-303) on BASELINE
     config 3's structure, at a time inside the first knot interval (non-trivial first-knot
     transforms)."""
-    pr = sc.config3(4, build_solver=False)
+    _check_consensus_kernel(emu, sc.config3(4, build_solver=False), 0.37)
+    # RendezVous: shared blocks of length 1 (terminal positions), identity transforms
+    _check_consensus_kernel(emu, sc.config_rendezvous(4, build_solver=False), 0.37)
+
+
+def _check_consensus_kernel(emu, pr, t):
     rng = np.random.default_rng(7)
     N, nsh, nn, L = pr.N, pr.nsh, pr.n_nghb, pr.L
     rho = 1.3
     x_i, l_i, z_i = (rng.standard_normal((N, nsh)) for _ in range(3))
     x_j, l_ij, z_ij = (rng.standard_normal((N, nn, nsh)) for _ in range(3))
-    Tf, Tb = pr.first_knot_transforms(0.37)
+    Tf, Tb = pr.first_knot_transforms(t)
     PzT = np.ascontiguousarray(pr.Pz.T)
     c = np.ascontiguousarray(pr.c)
     zi, zij, li, lij = z_i.copy(), z_ij.copy(), l_i.copy(), l_ij.copy()

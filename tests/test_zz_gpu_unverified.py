@@ -86,3 +86,21 @@ def test_simple_quadrotor3d_matches_oracle():
     assert np.array_equal(res['status'], ref['status']) and res['status'][0] == 0
     ok = ref['status'] == 0
     assert np.median(np.abs(res['x'] - ref['x'])[ok][:, :42].max(axis=1)) < NORTH_STAR_TOL
+
+
+def test_rendezvous_admm_matches_oracle():
+    """RendezVous on the GPU runner (shared blocks of length 1 in the consensus kernel) vs
+    the sequential ADMM oracle, iteration by iteration."""
+    from omg_tools_b200.problems.admm_gpu import FormationADMMRunner
+    from oracle.admm_ref import ADMMOracle
+    run = FormationADMMRunner(sc.config_rendezvous(4))
+    orc = ADMMOracle(sc.config_rendezvous(4, build_solver=False))
+    for it in range(8):
+        rg = run.dual_update(0.)
+        ro = orc.dual_update(0.)
+        st, _ = run.status()
+        assert np.all(st == 0) and np.all(orc.status == 0)
+        assert np.abs(run.x_i.cpu().numpy() - orc.x_i).max() < NORTH_STAR_TOL, it
+        assert np.abs(run.z_i.cpu().numpy() - orc.z_i).max() < NORTH_STAR_TOL
+        assert np.abs(run.l_i.cpu().numpy() - orc.l_i).max() < 10 * NORTH_STAR_TOL
+        assert abs(rg[0] - ro[0]) < 1e-3 * max(1., ro[0])
