@@ -22,5 +22,6 @@ from .environment.obstacle import Obstacle
 from .problems.problem import Problem
 from .problems.point2point import Point2point, FixedTPoint2point, FreeEndPoint2point
 from .problems.formation_central import FormationPoint2pointCentral
+from .problems.admm import FormationPoint2point, RendezVous
 
 __version__ = '0.1.0'
