@@ -1443,6 +1443,11 @@ static const PTerm* upload_terms(omg_problem* h, const omg_termlist& L, int n_on
 extern "C" {
 
 int omg_abi_version(void) { return OMG_ABI_VERSION; }
+#ifdef OMG_CPU_EMU
+// only the CPU emulation build (tools/cpu_emu) exports this: its "device" pointers are host
+// pointers, which lets the tests drive the device-pointer API with CPU tensors
+int omg_is_emulation(void) { return 1; }
+#endif
 
 // ---- table files ---------------------------------------------------------------
 namespace {

@@ -175,7 +175,9 @@ class BatchMPC(object):
         self.obstacles = problem.environment.obstacles
         self.T = problem.options['horizon_time']
         self.knot_time = problem.knot_time
-        dev = torch.device('cuda', self.solver.device)
+        from ..solver import b200 as _b200
+        dev = torch.device('cpu') if _b200.is_emulation(self.solver.lib) else \
+            torch.device('cuda', self.solver.device)     # (CPU: kernel emulation, tests only)
         self.dev = dev
         rng = np.random.default_rng(seed)
         n, m = self.tb.n, self.tb.m

@@ -84,7 +84,10 @@ class FormationADMMRunner(object):
         self.ex = AgentExchange(problem.N, problem.nghb, problem.back, rank, world, group)
         lo, hi = self.ex.lo, self.ex.hi
         self.lo, self.hi = lo, hi
-        dev = torch.device('cuda', self.solver.device if device is None else device)
+        if b200.is_emulation(self.solver.lib):      # CPU emulation of the kernels (tests only)
+            dev = torch.device('cpu')
+        else:
+            dev = torch.device('cuda', self.solver.device if device is None else device)
         self.dev = dev
         td = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
         p = problem

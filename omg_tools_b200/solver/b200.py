@@ -133,6 +133,34 @@ def _ptr(arr, typ):
     return arr.ctypes.data_as(typ)
 
 
+def is_emulation(lib=None):
+    """True only for the CPU emulation build of the kernel source (tools/cpu_emu, test
+    infrastructure), whose device pointers are host pointers."""
+    return hasattr(lib or load_library(), 'omg_is_emulation')
+
+
+def _check_device_tensors(tensors, lib=None):
+    """Device-pointer API: contiguous float64 CUDA tensors -- or CPU tensors when (and only
+    when) the loaded library is the CPU emulation.  Returns the stream handle to pass."""
+    import torch
+    on_gpu = tensors[0].is_cuda
+    if not on_gpu and not is_emulation(lib):
+        raise ValueError('expected contiguous float64 CUDA tensors')
+    for t in tensors:
+        if t.dtype != torch.float64 or t.is_cuda != on_gpu or not t.is_contiguous():
+            raise ValueError('expected contiguous float64 CUDA tensors')
+    return on_gpu
+
+
+def _stream_handle(on_gpu, device, stream):
+    import torch
+    if not on_gpu:
+        return None
+    if stream is None:
+        stream = torch.cuda.current_stream(device)
+    return C.c_void_p(stream.cuda_stream)
+
+
 class _Keep(object):
     """Owns contiguous numpy copies referenced by a ctypes struct."""
 
@@ -423,19 +451,14 @@ class B200Solver(object):
                            lam_g0=None, stream=None):
         """torch CUDA tensors (float64 / int32, contiguous); asynchronous on
         ``stream`` (torch.cuda.Stream or None = current)."""
-        import torch
         B = X0.shape[0]
-        for t in (X0, P, LBG, UBG, X, LAM, F):
-            if t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous():
-                raise ValueError('expected contiguous float64 CUDA tensors')
+        on_gpu = _check_device_tensors((X0, P, LBG, UBG, X, LAM, F), self.lib)
         shared = 1 if LBG.dim() == 1 else 0
-        if stream is None:
-            stream = torch.cuda.current_stream(X0.device)
         self._check(self.lib.omg_solve_batch(
             self._handle, B, X0.data_ptr(), P.data_ptr(), LBG.data_ptr(),
             UBG.data_ptr(), shared, lam_g0.data_ptr() if lam_g0 is not None else None,
             X.data_ptr(), LAM.data_ptr(), F.data_ptr(), STATUS.data_ptr(),
-            ITERS.data_ptr(), C.c_void_p(stream.cuda_stream)))
+            ITERS.data_ptr(), _stream_handle(on_gpu, X0.device, stream)))
 
     def shift_batch_device(self, X, blocks, stream=None):
         """In-place warm-start shift of spline variables (torch CUDA tensor X
@@ -446,12 +469,11 @@ class B200Solver(object):
         ncols = np.array([b[2] for b in blocks], dtype=np.int32)
         Tm = np.concatenate([np.asarray(b[3], dtype=np.float64).reshape(-1)
                              for b in blocks])
-        if stream is None:
-            stream = torch.cuda.current_stream(X.device)
+        on_gpu = _check_device_tensors((X,), self.lib)
         self._check(self.lib.omg_shift_batch(
             self._handle, X.shape[0], X.data_ptr(), len(blocks), offs.ctypes.data,
             lens.ctypes.data, ncols.ctypes.data, Tm.ctypes.data,
-            C.c_void_p(stream.cuda_stream)))
+            _stream_handle(on_gpu, X.device, stream)))
 
     # ------------------------------------------------------------------
     # the reference's single-instance call contract
@@ -480,16 +502,12 @@ def admm_zl_update(PzT, c, Tf, Tb, rho, x_i, x_j, z_i, z_ij, l_i, l_ij, res, L, 
     lib = load_library()
     n_agents, nsh = x_i.shape
     nn = x_j.shape[1]
-    for t in (PzT, c, Tf, Tb, x_i, x_j, z_i, z_ij, l_i, l_ij, res):
-        if t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous():
-            raise ValueError('expected contiguous float64 CUDA tensors')
-    if stream is None:
-        stream = torch.cuda.current_stream(x_i.device)
+    on_gpu = _check_device_tensors((PzT, c, Tf, Tb, x_i, x_j, z_i, z_ij, l_i, l_ij, res), lib)
     rc = lib.omg_admm_zl_update(n_agents, nsh, nn, L, PzT.data_ptr(), c.data_ptr(),
                                 Tf.data_ptr(), Tb.data_ptr(), float(rho), x_i.data_ptr(),
                                 x_j.data_ptr(), z_i.data_ptr(), z_ij.data_ptr(),
                                 l_i.data_ptr(), l_ij.data_ptr(), res.data_ptr(),
-                                C.c_void_p(stream.cuda_stream))
+                                _stream_handle(on_gpu, x_i.device, stream))
     if rc != 0:
         raise RuntimeError('libomgb200: %s' % lib.omg_last_error().decode())
 
@@ -506,11 +524,10 @@ def sample_batch(X, blocks, stream=None):
     nsamp = np.array([np.asarray(b[3]).shape[0] for b in blocks], dtype=np.int32)
     Sm = np.concatenate([np.ascontiguousarray(b[3], dtype=np.float64).reshape(-1) for b in blocks])
     out = torch.empty((X.shape[0], int((nsamp * ncols).sum())), dtype=torch.float64, device=X.device)
-    if stream is None:
-        stream = torch.cuda.current_stream(X.device)
+    on_gpu = _check_device_tensors((X,), lib)
     rc = lib.omg_sample_batch(X.shape[0], X.shape[1], X.data_ptr(), len(blocks), offs.ctypes.data,
                               lens.ctypes.data, ncols.ctypes.data, nsamp.ctypes.data,
-                              Sm.ctypes.data, out.data_ptr(), C.c_void_p(stream.cuda_stream))
+                              Sm.ctypes.data, out.data_ptr(), _stream_handle(on_gpu, X.device, stream))
     if rc != 0:
         raise RuntimeError('libomgb200: %s' % lib.omg_last_error().decode())
     return out
@@ -526,17 +543,13 @@ def integrate_rk4(model, state0, inputs, sample_time, stream=None):
     import torch
     lib = load_library()
     mid = ODE_MODELS[model] if isinstance(model, str) else int(model)
-    for t in (state0, inputs):
-        if t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous():
-            raise ValueError('contiguous float64 CUDA tensors expected')
+    on_gpu = _check_device_tensors((state0, inputs), lib)
     B, ns = state0.shape
     steps, ni = inputs.shape[1] - 1, inputs.shape[2]
     out = torch.empty_like(state0)
-    if stream is None:
-        stream = torch.cuda.current_stream(state0.device)
     rc = lib.omg_integrate_rk4(mid, B, ns, ni, state0.data_ptr(), inputs.data_ptr(),
                                float(sample_time), steps, out.data_ptr(),
-                               C.c_void_p(stream.cuda_stream))
+                               _stream_handle(on_gpu, state0.device, stream))
     if rc != 0:
         raise RuntimeError('libomgb200: %s' % lib.omg_last_error().decode())
     return out

@@ -306,3 +306,82 @@ def test_results_do_not_depend_on_the_thread_schedule(emu, monkeypatch):
         for a, b in zip(results['forward'], results[sched]):
             assert np.array_equal(a['iters'], b['iters']) and (a['status'] == 0).all()
             assert np.array_equal(a['x'], b['x']) and np.array_equal(a['lam_g'], b['lam_g'])
+
+
+def test_device_pointer_api_on_cpu_tensors(emu):
+    """solve_batch_device / shift_batch_device with CPU tensors are accepted by the emulation
+    library only; the runner of the formation ADMM then follows the sequential oracle."""
+    import torch
+    from omg_tools_b200.problems.admm_gpu import FormationADMMRunner
+    from oracle.admm_ref import ADMMOracle
+    assert b200.is_emulation(emu)
+    run = FormationADMMRunner(sc.config3(4))
+    orc = ADMMOracle(sc.config3(4, build_solver=False))
+    for it in range(4):
+        rg, ro = run.dual_update(0.), orc.dual_update(0.)
+        st, _ = run.status()
+        assert np.all(st == 0) and np.all(orc.status == 0)
+        assert np.abs(run.x_i.numpy() - orc.x_i).max() < 1e-4, it
+        assert np.abs(run.z_i.numpy() - orc.z_i).max() < 1e-4
+        assert abs(rg[0] - ro[0]) < 1e-3 * max(1., ro[0])
+
+
+def _admm_rank(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    b200.load_library(EMU_LIB)
+    from omg_tools_b200.problems.admm_gpu import FormationADMMRunner
+    run = FormationADMMRunner(sc.config3(8, rank=rank, world=world), rank=rank, world=world)
+    hist = [run.dual_update(0.) for _ in range(4)]
+    torch.save({'x_i': run.x_i, 'z_i': run.z_i, 'l_i': run.l_i, 'hist': hist, 'lo': run.lo},
+               os.path.join(out, 'r%d.pt' % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_formation_admm_two_ranks_gloo_through_the_emulated_kernels(emu, tmp_path):
+    """BASELINE config 3's multi-rank path end to end on the CPU: 8 agents sharded over two
+    processes (gloo), each running its batched x-update and consensus kernel in the kernel
+    emulation, neighbour exchange and residual all-reduce over the process group -- the
+    sharded run reproduces the single-process run of all agents bit for bit."""
+    import torch
+    import torch.multiprocessing as mp
+    from omg_tools_b200.problems.admm_gpu import FormationADMMRunner
+    port = 29900 + (os.getpid() % 90)
+    mp.spawn(_admm_rank, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    single = FormationADMMRunner(sc.config3(8))
+    hist = [single.dual_update(0.) for _ in range(4)]
+    for rank in range(2):
+        d = torch.load(os.path.join(str(tmp_path), 'r%d.pt' % rank))
+        lo = d['lo']
+        assert lo == 4 * rank
+        for key in ('x_i', 'z_i', 'l_i'):
+            assert torch.equal(d[key], getattr(single, key)[lo:lo + 4]), key
+        assert np.allclose(d['hist'], hist, rtol=1e-12, atol=0.)
+
+
+def test_batched_receding_horizon_config5_through_the_emulated_kernels(emu):
+    """BASELINE config 5 (revolving door): the batched device-resident MPC loop
+    (execution/batch_mpc.py: solve, device-side prediction from sampled splines, knot shift)
+    equals the reference-style sequential loop Problem.predict/solve/store/simulate, step by
+    step through the first knot crossing -- run on CPU tensors in the kernel emulation."""
+    from omg_tools_b200.execution.batch_mpc import BatchMPC
+    seq = sc.config5()
+    seq.initialize(0.)
+    bat = BatchMPC(sc.config5(), batch=2, update_time=0.1)
+    t, dt = 0., 0.1
+    for k in range(12):                      # crosses the first knot at t = 1.0
+        seq.predict(t, dt, 0.01)
+        seq.solve(t, dt)
+        bat.step()
+        Xb = bat.X.numpy()
+        xs = seq.father.get_variables().cat
+        assert seq.problem.stats()['return_status'] == 'Solve_Succeeded'
+        assert np.all(bat.history['status'][-1] == 0)
+        assert np.abs(Xb - xs[None]).max() < 1e-6, k
+        seq.store(t, dt, 0.01)
+        seq.simulate(t, dt, 0.01)
+        t = np.round(t + dt, 6)
+    assert np.abs(bat.state[0] - seq.vehicles[0].signals['state'][:, -1]).max() < 1e-6
