@@ -219,8 +219,20 @@ def _split(poly, x_index, tape):
     return out
 
 
+_FD_CACHE = {}
+
+
 def _first_derivs(xmon):
     """d(prod x)/dx_j for every distinct j: [(j, mult, reduced monomial)]."""
+    res = _FD_CACHE.get(xmon)
+    if res is None:
+        if len(_FD_CACHE) > 2000000:
+            _FD_CACHE.clear()
+        res = _FD_CACHE[xmon] = _first_derivs_uncached(xmon)
+    return res
+
+
+def _first_derivs_uncached(xmon):
     res = []
     for j in sorted(set(xmon)):
         mult = xmon.count(j)
