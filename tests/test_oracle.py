@@ -190,10 +190,13 @@ def _slsqp_from(tb, p, x_start, maxiter):
 
 
 @pytest.mark.parametrize('name,maxiter,ftol', [('config_quadrotor2d', 100, 1e-6),
-                                               ('config4', 12, 1e-4)])
+                                               ('config4', 12, 1e-4),
+                                               ('config_dubins_plain', 30, 1e-5),
+                                               ('config_quadrotor3d_simple', 30, 1e-5)])
 def test_oracle_optimum_is_a_local_optimum_for_slsqp(name, maxiter, ftol):
     """Independent optimiser on the non-convex models (planar quadrotor: non-convex
-    thrust bound; Quadrotor3D: chain-rule tables): started next to the oracle's tight
+    thrust bound; Quadrotor3D: chain-rule tables; default Dubins: cross-Hessian tables;
+    SimpleQuadrotor3D: non-convex thrust and body-rate rows): started next to the oracle's tight
     solution, scipy's SLSQP neither finds a lower objective nor moves the vehicle's
     coefficients."""
     from oracle import ipm_c
