@@ -68,6 +68,28 @@ def test_standard_kernel_matches_oracle(emu, name, B, layout):
     assert np.abs(res['x'] - ref['x'])[:, :26].max() < 1e-7
 
 
+@pytest.mark.parametrize('name, nflat, options', [
+    ('config_freeT', 26, None),                 # T as a variable, cubic rows, soft restoration
+    ('config_holonomic3d', 39, None),           # 3-D hyperplanes, 1 block/SM layout
+    ('config_quadrotor2d', 26, None),           # sign-indefinite pivots (IPOPT's inertia count)
+    ('config2', 26, {'inertia_mode': 1}),       # the positional inertia test of the first kernels
+])
+def test_more_models_and_options(emu, name, nflat, options):
+    """Further problem classes through the emulated standard kernel: identical iteration
+    counts as the C oracle, solutions to rounding."""
+    pr = getattr(sc, name)()
+    tb = pr.father.tables
+    X0, P = sc.instance_data(pr, 2, jitter=0.05, seed=1)
+    if options:
+        pr.problem.set_options(options)
+    res = pr.problem.solve_batch(X0, P)
+    ref = ipm_c.solve_batch_full(tb, X0, P, threads=2, options=options)
+    assert np.array_equal(res['status'], ref['status']) and (res['status'] == 0).all()
+    assert np.array_equal(res['iters'], ref['iters'])
+    assert np.abs(res['x'] - ref['x'])[:, :nflat].max() < 1e-6
+    assert np.abs(res['f'] - ref['f']).max() < 1e-9
+
+
 def test_one_block_per_sm_variant(emu, monkeypatch):
     """omg_ipm_kernel (512 threads, everything in shared memory)."""
     monkeypatch.setenv('OMG_B200_CTAS', '1')
