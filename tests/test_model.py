@@ -288,6 +288,30 @@ def test_freeT_point2point_receding_horizon():
     assert np.abs(pr.vehicles[0].signals['state'][:, -1] - [2., 2.]).max() < 1e-2
 
 
+def test_freeT_with_a_moving_obstacle_receding_horizon():
+    """FreeTPoint2point with the example's moving circular obstacle (bilinear T * tau * v
+    terms in the obstacle rows): every MPC step converges and the vehicle arrives."""
+    from oracle import ipm_c
+    if not ipm_c.available():
+        pytest.skip('C oracle not built')
+    pr = sc.config_freeT(build_solver=False, moving=True)
+    pr.problem = _OracleSolver(pr.father.tables)
+    pr.initialize(0.)
+    t, dt = 0., 0.5
+    for k in range(24):
+        pr.predict(t, dt, 0.01)
+        pr.init_step(t, dt)
+        pr.solve(t, dt)
+        assert pr.problem.stats()['return_status'] == 'Solve_Succeeded', k
+        pr.store(t, dt, 0.01)
+        pr.simulate(t, dt, 0.01)
+        t = np.round(t + dt, 6)
+        if pr.stop_criterium(t, dt):
+            break
+    assert k < 23
+    assert np.abs(pr.vehicles[0].signals['state'][:, -1] - [2., 2.]).max() < 1e-2
+
+
 def test_intermediates_small_example_and_guards():
     """lowering.py with 'mid' symbols on a hand-checkable NLP:
     c = x0*x1 (shared), rows  p*c + x2 <= 1  and  2*c - x0 = 0."""
