@@ -89,6 +89,18 @@ def new_mid(name, definition):
     return Poly({(info.id,): 1.0})
 
 
+def rel_time(t, T):
+    """t / T, the relative start of the horizon.  When the motion time T is a decision
+    VARIABLE (FreeTPoint2point) the reference's parameter t is identically 0 -- the time axis
+    resets at every update, point2point.py:300-306 -- and t / T is not polynomial in T:
+    the relative time is then the constant 0."""
+    if isinstance(T, Poly) and len(T.t) == 1:
+        (mono, c), = T.t.items()
+        if len(mono) == 1 and c == 1.0 and _SYMS[resolve(mono[0])].kind == 'var':
+            return 0.
+    return t / T
+
+
 def share(poly):
     """Parameter-only Poly -> one symbol (identity atom) evaluated once."""
     poly = _as_poly(poly)

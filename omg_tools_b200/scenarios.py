@@ -287,6 +287,34 @@ def config_freeT(options=None, build_solver=True, moving=False):
     return _p2p(vehicle, environment, options, build_solver, freeT=True)
 
 
+def config_freeT_safety(options=None, build_solver=True):
+    """Minimum-time problem with a safety-distance slack (examples/p2p_holonomic.py with
+    freeT=True): the relative start t/T of the slack objective is 0 for a free end time."""
+    vehicle = Holonomic()
+    vehicle.set_options({'safety_distance': 0.1})
+    vehicle.set_initial_conditions([-1.5, -1.5])
+    vehicle.set_terminal_conditions([2., 2.])
+    environment = Environment(room={'shape': Square(5.)})
+    environment.add_obstacle(Obstacle({'position': [0.3, 0.2]}, shape=Circle(0.5)))
+    return _p2p(vehicle, environment, options, build_solver, freeT=True)
+
+
+def config_dubins_freeT(options=None, build_solver=True):
+    """examples/p2p_dubins.py as written: substitution, 5 knot intervals, free end time (the
+    motion time multiplies the integrated velocity: T x intermediate cross terms)."""
+    from . import Dubins
+    vehicle = Dubins(bounds={'vmax': 0.7, 'wmax': np.pi / 3., 'wmin': -np.pi / 3.},
+                     options={'substitution': True})
+    vehicle.define_knots(knot_intervals=5)
+    vehicle.set_initial_conditions([0., 0., 0.])
+    vehicle.set_terminal_conditions([3., 3., 0.])
+    environment = Environment(room={'shape': Square(5.), 'position': [1.5, 1.5]})
+    trajectories = {'velocity': {'time': [0.5], 'values': [[0.25, 0.0]]}}
+    environment.add_obstacle(Obstacle({'position': [1., 1.]}, shape=Circle(0.5),
+                                      simulation={'trajectories': trajectories}))
+    return _p2p(vehicle, environment, options, build_solver, freeT=True)
+
+
 def instance_data(problem, batch, jitter=0.0, seed=0, current_time=0.):
     """(X0[B,n], P[B,n_par]) for a cold solve: linear initial guess
     (holonomic.py:118-127) and parameters at current_time.  jitter>0 perturbs

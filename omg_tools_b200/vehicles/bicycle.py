@@ -15,6 +15,7 @@ import numpy as np
 from .dubins import Dubins
 from .vehicle import Vehicle
 from ..basics.optilayer import inf
+from ..basics.poly import rel_time
 from ..basics.shape import Circle
 from ..basics.spline import BSplineBasis
 from ..basics.spline_extra import evalspline, sample_splines
@@ -102,7 +103,7 @@ class Bicycle(Dubins):
         hop0 = self.define_parameter('hop0', 1)
         tdelta0 = self.define_parameter('tdelta0', 1)     # tan(delta0)
         # l'Hopital on tan(delta) = 2 L dtg / (v~ (1+tg^2)^2) when starting from standstill
-        t0 = self.t / T
+        t0 = rel_time(self.t, T)
         self.define_constraint(
             hop0 * (sg * 2. * evalspline(ddtg_ha, t0) * L
                     - tdelta0 * (evalspline(dv_til, t0) * (1. + tg_ha0**2)**2) * T), 0., 0.)

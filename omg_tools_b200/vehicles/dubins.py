@@ -17,7 +17,7 @@ import numpy as np
 
 from .vehicle import Vehicle
 from ..basics.optilayer import inf
-from ..basics.poly import Poly, new_mid, collapse
+from ..basics.poly import Poly, new_mid, collapse, rel_time
 from ..basics.shape import Circle
 from ..basics.spline import BSplineBasis, BSpline
 from ..basics.spline_extra import evalspline, running_integral, sample_splines
@@ -173,7 +173,7 @@ class Dubins(Vehicle):
         """x(tau) with x(t/T) = x0 (reference dubins.py:253-259)."""
         dx_int = T * running_integral(dx)
         if isinstance(t, Poly):
-            return dx_int - collapse(evalspline(dx_int, t / T, True)) + x0
+            return dx_int - collapse(evalspline(dx_int, rel_time(t, T), True)) + x0
         return dx_int - dx_int(t / T)[0] + x0
 
     def splines2signals(self, splines, time):

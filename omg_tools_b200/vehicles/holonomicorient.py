@@ -9,6 +9,7 @@ import numpy as np
 
 from .vehicle import Vehicle
 from ..basics.optilayer import inf
+from ..basics.poly import rel_time
 from ..basics.shape import Rectangle
 from ..basics.spline_extra import sample_splines, definite_integral
 
@@ -58,12 +59,12 @@ class HolonomicOrient(Vehicle):
         reg, weight = self.options['reg_type'], self.options.get('reg_weight', 0.0)
         if reg == 'norm_1' and weight != 0.0:
             g_reg = self.define_spline_variable('g_reg', 1, basis=dtg_ha.basis)[0]
-            objective = definite_integral(g_reg, self.t / T, 1.)
+            objective = definite_integral(g_reg, rel_time(self.t, T), 1.)
             self.define_constraint(dtg_ha - g_reg, -inf, 0.)
             self.define_constraint(-dtg_ha - g_reg, -inf, 0.)
             self.define_objective(weight * objective)
         if reg == 'norm_2' and weight != 0.0:
-            self.define_objective(weight * definite_integral(dtg_ha**2, self.t / T, 1.))
+            self.define_objective(weight * definite_integral(dtg_ha**2, rel_time(self.t, T), 1.))
 
     def get_initial_constraints(self, splines, horizon_time):
         pos0 = self.define_parameter('pos0', 2)

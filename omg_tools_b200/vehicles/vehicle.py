@@ -11,6 +11,7 @@ the ideal, noise-free case: the vehicle follows its computed spline exactly
 import numpy as np
 
 from ..basics.optilayer import OptiChild, inf
+from ..basics.poly import rel_time
 from ..basics.spline import BSplineBasis
 from ..basics.spline_extra import definite_integral, sample_splines
 from ..basics.shape import Rectangle, Square, Circle
@@ -106,7 +107,7 @@ class Vehicle(OptiChild):
                         eps = self.define_spline_variable(
                             'eps_' + str(s) + str(k))[0]
                         obj = safety_weight * definite_integral(
-                            eps, t / horizon_time, 1.)
+                            eps, rel_time(t, horizon_time), 1.)
                         self.define_objective(obj)
                         self.define_constraint(eps - safety_distance, -inf, 0.)
                         self.define_constraint(-eps, -inf, 0.)
@@ -173,7 +174,7 @@ class Vehicle(OptiChild):
                         eps = self.define_spline_variable(
                             'eps_' + str(s) + str(k))[0]
                         obj = safety_weight * definite_integral(
-                            eps, t / horizon_time, 1.)
+                            eps, rel_time(t, horizon_time), 1.)
                         self.define_objective(obj)
                         self.define_constraint(eps - safety_distance, -inf, 0.)
                         self.define_constraint(-eps, -inf, 0.)

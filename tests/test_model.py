@@ -312,6 +312,45 @@ def test_freeT_with_a_moving_obstacle_receding_horizon():
     assert np.abs(pr.vehicles[0].signals['state'][:, -1] - [2., 2.]).max() < 1e-2
 
 
+def test_freeT_with_safety_distance_and_dubins_freeT():
+    """Free end time with a safety-distance slack (the slack objective starts at t/T = 0:
+    basics/poly.py rel_time) -- the MPC loop converges at every step, arrives, and keeps the
+    obstacle at more than its radius; and examples/p2p_dubins.py as written (substitution,
+    freeT): the motion time multiplies the intermediates.  From a rolling speed guess the
+    oracle converges to a motion time between the straight-line bound and 10 s (from the
+    reference's zero-speed guess the Jacobian of the position rows is rank deficient and
+    the line search gives up -- IPOPT's restoration phase)."""
+    from oracle import ipm_c
+    if not ipm_c.available():
+        pytest.skip('C oracle not built')
+    pr = sc.config_freeT_safety(build_solver=False)
+    pr.problem = _OracleSolver(pr.father.tables)
+    pr.initialize(0.)
+    t, dt = 0., 0.5
+    for k in range(24):
+        pr.predict(t, dt, 0.01)
+        pr.init_step(t, dt)
+        pr.solve(t, dt)
+        assert pr.problem.stats()['return_status'] == 'Solve_Succeeded', k
+        pr.store(t, dt, 0.01)
+        pr.simulate(t, dt, 0.01)
+        t = np.round(t + dt, 6)
+        if pr.stop_criterium(t, dt):
+            break
+    pos = pr.vehicles[0].signals['state']
+    assert np.abs(pos[:, -1] - [2., 2.]).max() < 1e-2
+    assert np.hypot(pos[0] - 0.3, pos[1] - 0.2).min() > 0.6 - 1e-3
+    pr = sc.config_dubins_freeT(build_solver=False)
+    tb, f = pr.father.tables, pr.father
+    assert tb.n_mid > 0 and tb.nnz_wx > 0
+    X0, P = f.get_variables().cat[None].copy(), f.set_parameters(0.).cat[None]
+    X0[0, :8] = 0.3
+    r = ipm_c.solve_batch_full(tb, X0, P, threads=1)
+    assert r['status'][0] == 0
+    T = r['x'][0][f._var_struct.entries[(pr.label, 'T')][0]]
+    assert np.hypot(3., 3.) / 0.7 < T < 10. and abs(r['f'][0] - T) < 1e-9
+
+
 def test_intermediates_small_example_and_guards():
     """lowering.py with 'mid' symbols on a hand-checkable NLP:
     c = x0*x1 (shared), rows  p*c + x2 <= 1  and  2*c - x0 = 0."""
