@@ -299,12 +299,13 @@ def config_freeT_safety(options=None, build_solver=True):
     return _p2p(vehicle, environment, options, build_solver, freeT=True)
 
 
-def config_dubins_freeT(options=None, build_solver=True):
+def config_dubins_freeT(options=None, build_solver=True, init_v_til=0.):
     """examples/p2p_dubins.py as written: substitution, 5 knot intervals, free end time (the
-    motion time multiplies the integrated velocity: T x intermediate cross terms)."""
+    motion time multiplies the integrated velocity: T x intermediate cross terms).
+    ``init_v_til`` > 0 replaces the reference's zero-speed initial guess (vehicle option)."""
     from . import Dubins
     vehicle = Dubins(bounds={'vmax': 0.7, 'wmax': np.pi / 3., 'wmin': -np.pi / 3.},
-                     options={'substitution': True})
+                     options={'substitution': True, 'init_v_til': init_v_til})
     vehicle.define_knots(knot_intervals=5)
     vehicle.set_initial_conditions([0., 0., 0.])
     vehicle.set_terminal_conditions([3., 3., 0.])

@@ -40,7 +40,7 @@ class Bicycle(Dubins):
     def set_default_options(self):
         Vehicle.set_default_options(self)
         self.options.update({'plot_type': 'bicycle', 'substitution': False,
-                             'exact_substitution': False})
+                             'exact_substitution': False, 'init_v_til': 0.})
 
     def init(self):
         self.t = self.define_symbol('t')

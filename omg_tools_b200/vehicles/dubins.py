@@ -38,7 +38,7 @@ class Dubins(Vehicle):
     def set_default_options(self):
         Vehicle.set_default_options(self)
         self.options.update({'stop_tol': 1.e-2, 'substitution': False,
-                             'exact_substitution': False})
+                             'exact_substitution': False, 'init_v_til': 0.})
 
     def init(self):
         self.t = self.define_symbol('t')
@@ -135,6 +135,11 @@ class Dubins(Vehicle):
     def get_init_spline_value(self, subgoals=None):
         L = len(self.basis)
         init_value = np.zeros((L, 2))
+        # The reference starts from v~ = 0 (dubins.py:209-214), a point where the position
+        # does not depend on the heading; IPOPT leaves it through its restoration phase,
+        # this solver does not.  Option 'init_v_til' (default 0 = the
+        # reference's guess) sets a rolling initial guess instead.
+        init_value[:, 0] = self.options.get('init_v_til', 0.)
         tg_ha0 = np.tan(self.prediction['state'][2] / 2.)
         tg_haT = np.tan(self.poseT[2] / 2.)
         init_value[:, 1] = np.linspace(tg_ha0, tg_haT, L)

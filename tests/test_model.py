@@ -343,12 +343,26 @@ def test_freeT_with_safety_distance_and_dubins_freeT():
     pr = sc.config_dubins_freeT(build_solver=False)
     tb, f = pr.father.tables, pr.father
     assert tb.n_mid > 0 and tb.nnz_wx > 0
-    X0, P = f.get_variables().cat[None].copy(), f.set_parameters(0.).cat[None]
-    X0[0, :8] = 0.3
-    r = ipm_c.solve_batch_full(tb, X0, P, threads=1)
-    assert r['status'][0] == 0
-    T = r['x'][0][f._var_struct.entries[(pr.label, 'T')][0]]
-    assert np.hypot(3., 3.) / 0.7 < T < 10. and abs(r['f'][0] - T) < 1e-9
+    r = ipm_c.solve_batch_full(tb, f.get_variables().cat[None], f.set_parameters(0.).cat[None], threads=1)
+    assert r['status'][0] != 0                     # the reference's zero-speed guess
+    # vehicle option init_v_til: rolling initial guess; the example's whole MPC loop
+    pr = sc.config_dubins_freeT(build_solver=False, init_v_til=0.3)
+    pr.problem = _OracleSolver(pr.father.tables)
+    pr.initialize(0.)
+    t, dt, Ts = 0., 0.5, []
+    for k in range(30):
+        pr.predict(t, dt, 0.01)
+        pr.init_step(t, dt)
+        pr.solve(t, dt)
+        assert pr.problem.stats()['return_status'] == 'Solve_Succeeded', k
+        Ts.append(pr.horizon_time())
+        pr.store(t, dt, 0.01)
+        pr.simulate(t, dt, 0.01)
+        t = np.round(t + dt, 6)
+        if pr.stop_criterium(t, dt):
+            break
+    assert np.hypot(3., 3.) / 0.7 < Ts[0] < 10.
+    assert np.abs(pr.vehicles[0].signals['state'][:, -1] - [3., 3., 0.]).max() < 1e-2
 
 
 def test_intermediates_small_example_and_guards():
