@@ -49,6 +49,8 @@ def evalspline(s, x, share_weights=False):
                 b = b + (k[i + d + 1] - x) * lvl[i + 1] / den
             nxt.append(b)
         lvl = nxt
+    # numeric abscissa: plain floats (numpy bools / scalars do not combine with Poly)
+    lvl = [b if isinstance(b, Poly) else float(b) for b in lvl]
     if share_weights:
         from .poly import share
         lvl = [share(b) if isinstance(b, Poly) else b for b in lvl]
