@@ -186,6 +186,23 @@ def run_reference_loop(name, n_steps, update_time, sample_time=0.01, solver_opti
             'state': np.asarray(problem.vehicles[0].signals['state'], float)[:, -1]}
 
 
+def main_ext():
+    """loop_golden_ext.npz: the same for models added later (default Dubins formulation,
+    SimpleQuadrotor3D), through their first knot crossing."""
+    mg.install_stubs()
+    install_struct_stubs()
+    out = {}
+    for name, n_steps, dt in (('config_dubins_plain', 6, 0.5), ('config_quadrotor3d_simple', 6, 0.5)):
+        res = run_reference_loop(name, n_steps, dt)
+        print(name, 'steps', n_steps, 'status', res['status'], 'final state', np.round(res['state'], 4))
+        for key, val in res.items():
+            out['%s_%s' % (name, key)] = val
+        out[name + '_dt'] = dt
+    path = OUT.replace('loop_golden.npz', 'loop_golden_ext.npz')
+    np.savez_compressed(path, **out)
+    print('wrote', path)
+
+
 def main():
     mg.install_stubs()
     install_struct_stubs()
@@ -205,4 +222,4 @@ def main():
 
 
 if __name__ == '__main__':
-    main()
+    main_ext() if '--ext' in sys.argv else main()

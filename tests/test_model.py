@@ -959,13 +959,18 @@ class _RecordingOracleSolver(_OracleSolver):
         return res
 
 
-@pytest.mark.parametrize('name,n_steps', [('config1', 12), ('config5', 12), ('config4', 3)])
+@pytest.mark.parametrize('name,n_steps', [('config1', 12), ('config5', 12), ('config4', 3),
+                                          ('config_dubins_plain', 6),
+                                          ('config_quadrotor3d_simple', 6)])
 def test_host_loop_equals_the_references_problem_solve_loop(name, n_steps):
     """tests/golden/loop_golden.npz: the REFERENCE's Deployer.update / Simulator.update /
     Problem.solve / OptiFather loop, run from /root/reference around this repository's
     solver (make_loop_golden.py), recorded what it hands to the solver at every MPC
     step.  This framework's loop must hand over the same x0, p, lbg, ubg -- through the
     first knot crossing (config 1 and 5 at t = 1.0) -- and unpack the same x.
+
+    The default Dubins formulation and SimpleQuadrotor3D (loop_golden_ext.npz) run six 0.5 s
+    updates, through their first knot crossing.
 
     Config 4: identical until the first knot crossing; there the reference leaves the
     acceleration slacks ddx/ddy/ddz unshifted (and relies on IPOPT's restoration phase,
@@ -974,7 +979,9 @@ def test_host_loop_equals_the_references_problem_solve_loop(name, n_steps):
     from oracle import ipm_c
     if not ipm_c.available():
         pytest.skip('C oracle not built')
-    L = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'loop_golden.npz'))
+    L = np.load(os.path.join(os.path.dirname(__file__), 'golden',
+                             'loop_golden.npz' if name in ('config1', 'config4', 'config5')
+                             else 'loop_golden_ext.npz'))   # make_loop_golden.py --ext
     pr = getattr(sc, name)(build_solver=False)
     tb = pr.father.tables
     pr.problem = _RecordingOracleSolver(tb)
@@ -995,7 +1002,11 @@ def test_host_loop_equals_the_references_problem_solve_loop(name, n_steps):
         assert np.abs(p - L[name + '_p'][k]).max() < 1e-7, k        # (reference: odeint obstacle motion)
         assert np.array_equal(lbg, L[name + '_lbg'][k]) and np.array_equal(ubg, L[name + '_ubg'][k])
         assert np.abs(x - L[name + '_x'][k]).max() < 1e-5, k
-    if name != 'config4':
+    if name in ('config_dubins_plain', 'config_quadrotor3d_simple'):
+        # non-convex models, 60+ iterations per solve: last-bit differences of the host
+        # arithmetic (integrated positions, product splines) reach 1e-7 in the solutions
+        assert max(np.abs(calls[k][1] - L[name + '_p'][k]).max() for k in range(n_steps)) < 1e-6
+    elif name != 'config4':
         # tight: the two host paths are numerically the same computation
         assert max(np.abs(calls[k][0] - L[name + '_x0'][k]).max() for k in range(n_steps)) < 1e-11
         assert max(np.abs(calls[k][1] - L[name + '_p'][k]).max() for k in range(n_steps)) < 1e-12
