@@ -287,6 +287,10 @@ def config_freeT(options=None, build_solver=True, moving=False):
     return _p2p(vehicle, environment, options, build_solver, freeT=True)
 
 
+def config_freeT_moving(options=None, build_solver=True):
+    return config_freeT(options, build_solver, moving=True)
+
+
 def config_freeT_safety(options=None, build_solver=True):
     """Minimum-time problem with a safety-distance slack (examples/p2p_holonomic.py with
     freeT=True): the relative start t/T of the slack objective is 0 for a free end time."""

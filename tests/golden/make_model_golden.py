@@ -366,6 +366,44 @@ def build_reference(name):
         environment.add_obstacle(obs.Obstacle({'position': [2, 0, 3.5]}, shape=plate(),
                                               simulation={'trajectories': trajectory}))
         options = {}
+    elif name in ('config_freeT', 'config_freeT_moving', 'config_freeT_safety', 'config_dubins_freeT'):
+        # free end time: the reference defines T twice under one name, as a parameter (handed
+        # to the vehicle / environment rows) and as the variable of the objective
+        # (point2point.py:53-62, 281-284); both carry the same registry value here
+        if name == 'config_dubins_freeT':
+            db = ref_import('vehicles.dubins')
+            vehicle = db.Dubins(bounds={'vmax': 0.7, 'wmax': np.pi / 3., 'wmin': -np.pi / 3.},
+                                options={'substitution': True})
+            vehicle.define_knots(knot_intervals=5)
+            vehicle.set_initial_conditions([0., 0., 0.])
+            vehicle.set_terminal_conditions([3., 3., 0.])
+            environment = env.Environment(room={'shape': shp.Square(5.), 'position': [1.5, 1.5]})
+            trajectories = {'velocity': {'time': [0.5], 'values': [[0.25, 0.0]]}}
+            environment.add_obstacle(obs.Obstacle({'position': [1., 1.]}, shape=shp.Circle(0.5),
+                                                  simulation={'trajectories': trajectories}))
+        elif name == 'config_freeT_safety':
+            vehicle = hol.Holonomic()
+            vehicle.set_options({'safety_distance': 0.1})
+            vehicle.set_initial_conditions([-1.5, -1.5])
+            vehicle.set_terminal_conditions([2., 2.])
+            environment = env.Environment(room={'shape': shp.Square(5.)})
+            environment.add_obstacle(obs.Obstacle({'position': [0.3, 0.2]}, shape=shp.Circle(0.5)))
+        else:
+            vehicle = hol.Holonomic()
+            vehicle.set_initial_conditions([-1.5, -1.5])
+            vehicle.set_terminal_conditions([2., 2.])
+            environment = env.Environment(room={'shape': shp.Square(5.)})
+            rectangle = shp.Rectangle(width=3., height=0.2)
+            environment.add_obstacle(obs.Obstacle({'position': [-2.1, -0.5]}, shape=rectangle))
+            environment.add_obstacle(obs.Obstacle({'position': [1.7, -0.5]}, shape=rectangle))
+            trajectories = {'velocity': {'time': [3., 4.], 'values': [[-0.15, 0.0], [0., 0.15]]}}
+            environment.add_obstacle(obs.Obstacle(
+                {'position': [1.5, 0.5]}, shape=shp.Circle(0.4),
+                simulation={'trajectories': trajectories} if name == 'config_freeT_moving' else None))
+        problem = p2p.Point2point(vehicle, environment, options={'verbose': 0}, freeT=True)
+        problem.father.reset()
+        problem.construct()
+        return problem
     elif name == 'config_free_end':
         vehicle = hol.Holonomic()
         vehicle.set_options({'safety_distance': 0.1})
@@ -477,6 +515,9 @@ def host_values(problem, par, var, current_time):
     for ch in children:
         for nm, v in ch._variables.items():
             val = np.zeros(v.a.shape)
+            init = ch._values.get(nm)            # define_variable(..., value=...): T = 10
+            if init is not None and np.size(init) == v.a.size:
+                val = np.asarray(init, float).reshape(v.a.shape)
             if nm == 'splines_seg0':
                 val = np.asarray(ch.get_init_spline_value()[0], float).reshape(v.a.shape)
             X0.append(val.reshape(-1, order='F'))
@@ -562,7 +603,8 @@ BASE_NAMES = ('config1', 'config2', 'config4', 'config5', 'config_holonomic3d',
 # intermediates by decision variables
 EXT_NAMES = ('config_dubins_plain', 'config_dubins_rect', 'config_dubins_exact',
              'config_holonomic_orient', 'config_bicycle', 'config_agv',
-             'config_quadrotor3d_simple', 'config_formation_central', 'config_interveh', 'config_free_end')
+             'config_quadrotor3d_simple', 'config_formation_central', 'config_interveh', 'config_free_end',
+             'config_freeT', 'config_freeT_moving', 'config_freeT_safety', 'config_dubins_freeT')
 
 
 def main(ext=False):
@@ -578,6 +620,8 @@ def main(ext=False):
                        'config_formation_central': 15.}.get(name, 10.)
             # T is the horizon of the scenario, t a time inside the first knot interval
             REG.fixed = {'T': horizon, 't': 0.037 * horizon * (k + 1)}
+            if 'freeT' in name:
+                REG.fixed = {'t': 0.}             # T is a variable: any value; t is 0 (point2point.py:300-306)
             # labels restart for every build so that the layout strings are comparable
             opt = ref_import('basics.optilayer')
             for cls in list(opt.OptiChild.__subclasses__()) + [opt.OptiChild]:
