@@ -14,6 +14,7 @@ from .vehicles.quadrotor import Quadrotor
 from .vehicles.dubins import Dubins
 from .vehicles.bicycle import Bicycle
 from .vehicles.agv import AGV
+from .vehicles.trailer import Trailer
 from .vehicles.quadrotor3d import Quadrotor3D
 from .vehicles.quadrotor3d_simple import SimpleQuadrotor3D
 from .vehicles.fleet import Fleet

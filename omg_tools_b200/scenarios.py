@@ -320,6 +320,48 @@ def config_dubins_freeT(options=None, build_solver=True, init_v_til=0.):
     return _p2p(vehicle, environment, options, build_solver, freeT=True)
 
 
+def config_trailer(options=None, build_solver=True, init_v_til=0.):
+    """examples/p2p_trailer.py: a Dubins vehicle (Circle(0.2), 9 knot intervals) pulling a
+    Rectangle(0.2, 0.2) trailer on a 0.6 m hitch from (0, 0, 0) to (3.4, 3, 0), trailer heading
+    0 -> 0, empty Square(5) room, free end time; as in the example the lead vehicle is added
+    to the problem as a child and as a vehicle of its own."""
+    from . import Dubins, Trailer, Rectangle
+    vehicle = Dubins(shapes=Circle(0.2), bounds={'vmax': 0.8, 'wmax': np.pi / 3., 'wmin': -np.pi / 3.},
+                     options={'init_v_til': init_v_til})
+    vehicle.define_knots(knot_intervals=9)
+    vehicle.set_initial_conditions([0., 0., 0.])
+    vehicle.set_terminal_conditions([3.4, 3., 0.])
+    trailer = Trailer(lead_veh=vehicle, shapes=Rectangle(0.2, 0.2), l_hitch=0.6,
+                      bounds={'tmax': np.pi / 4., 'tmin': -np.pi / 4.})
+    trailer.define_knots(knot_intervals=9)
+    trailer.set_initial_conditions(0.)
+    trailer.set_terminal_conditions(0.)
+    environment = Environment(room={'shape': Square(5.), 'position': [1.5, 1.5]})
+    opts = {'verbose': 0}
+    opts.update(options or {})
+    problem = Point2point(trailer, environment, options=opts, freeT=True)
+    problem.father.add(vehicle)
+    problem.vehicles.append(vehicle)
+    vehicle.to_simulate = False
+    if build_solver:
+        problem.init()
+    else:
+        f = problem.father
+        f.reset()
+        problem.construct()
+        f.translate_symbols()
+        f.construct_variables()
+        f.construct_parameters()
+        rows, lb, ub = f.construct_constraints()
+        from .basics.lowering import lower
+        f.tables = lower(f._var_ids, f._par_ids, rows, f.construct_objective(), lb, ub, f.order_hint())
+        f.init_variables()
+        f.init_parameters()
+        f.init_transformations(problem.init_primal_transform, problem.init_dual_transform)
+    problem.reinitialize()
+    return problem
+
+
 def instance_data(problem, batch, jitter=0.0, seed=0, current_time=0.):
     """(X0[B,n], P[B,n_par]) for a cold solve: linear initial guess
     (holonomic.py:118-127) and parameters at current_time.  jitter>0 perturbs

@@ -56,16 +56,17 @@ class Dubins(Vehicle):
         """x, y as running integrals of the flat-output products; the product-spline
         coefficients are shared intermediates, created once per problem construction."""
         key = (id(splines[0].coeffs), id(splines[1].coeffs))
-        if getattr(self, '_flat_key', None) != key:
+        cache = self.__dict__.setdefault('_flat_cache', {})
+        if key not in cache:
             v_til, tg_ha = splines
             dx = v_til * (1 - tg_ha**2)
             dy = v_til * (2 * tg_ha)
-            self._flat_key = key
-            self._flat_hold = splines     # keeps the ids alive
-            self._flat_pos = (
-                self.integrate_once(self._shared('dx', dx), self.pos0[0], self.t, horizon_time),
-                self.integrate_once(self._shared('dy', dy), self.pos0[1], self.t, horizon_time))
-        return self._flat_pos
+            tag = '' if not cache else str(len(cache))      # a trailer's copies: own mids
+            cache[key] = (
+                splines,                   # keeps the ids alive
+                self.integrate_once(self._shared('dx' + tag, dx), self.pos0[0], self.t, horizon_time),
+                self.integrate_once(self._shared('dy' + tag, dy), self.pos0[1], self.t, horizon_time))
+        return cache[key][1], cache[key][2]
 
     def define_trajectory_constraints(self, splines, horizon_time):
         T = horizon_time

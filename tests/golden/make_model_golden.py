@@ -404,6 +404,26 @@ def build_reference(name):
         problem.father.reset()
         problem.construct()
         return problem
+    elif name == 'config_trailer':
+        db, tr = ref_import('vehicles.dubins'), ref_import('vehicles.trailer')
+        vehicle = db.Dubins(shapes=shp.Circle(0.2),
+                            bounds={'vmax': 0.8, 'wmax': np.pi / 3., 'wmin': -np.pi / 3.})
+        vehicle.define_knots(knot_intervals=9)
+        vehicle.set_initial_conditions([0., 0., 0.])
+        vehicle.set_terminal_conditions([3.4, 3., 0.])
+        trailer = tr.Trailer(lead_veh=vehicle, shapes=shp.Rectangle(0.2, 0.2), l_hitch=0.6,
+                             bounds={'tmax': np.pi / 4., 'tmin': -np.pi / 4.})
+        trailer.define_knots(knot_intervals=9)
+        trailer.set_initial_conditions(0.)
+        trailer.set_terminal_conditions(0.)
+        environment = env.Environment(room={'shape': shp.Square(5.), 'position': [1.5, 1.5]})
+        problem = p2p.Point2point(trailer, environment, options={'verbose': 0}, freeT=True)
+        problem.father.add(vehicle)            # examples/p2p_trailer.py:43-47
+        problem.vehicles.append(vehicle)
+        vehicle.to_simulate = False
+        problem.father.reset()
+        problem.construct()
+        return problem
     elif name == 'config_free_end':
         vehicle = hol.Holonomic()
         vehicle.set_options({'safety_distance': 0.1})
@@ -604,7 +624,8 @@ BASE_NAMES = ('config1', 'config2', 'config4', 'config5', 'config_holonomic3d',
 EXT_NAMES = ('config_dubins_plain', 'config_dubins_rect', 'config_dubins_exact',
              'config_holonomic_orient', 'config_bicycle', 'config_agv',
              'config_quadrotor3d_simple', 'config_formation_central', 'config_interveh', 'config_free_end',
-             'config_freeT', 'config_freeT_moving', 'config_freeT_safety', 'config_dubins_freeT')
+             'config_freeT', 'config_freeT_moving', 'config_freeT_safety', 'config_dubins_freeT',
+             'config_trailer')
 
 
 def main(ext=False):
@@ -620,8 +641,10 @@ def main(ext=False):
                        'config_formation_central': 15.}.get(name, 10.)
             # T is the horizon of the scenario, t a time inside the first knot interval
             REG.fixed = {'T': horizon, 't': 0.037 * horizon * (k + 1)}
-            if 'freeT' in name:
-                REG.fixed = {'t': 0.}             # T is a variable: any value; t is 0 (point2point.py:300-306)
+            if 'freeT' in name or name == 'config_trailer':
+                # t is 0 (point2point.py:300-306); T -- parameter, variable and the vehicles'
+                # placeholders of that name -- one value per sample
+                REG.fixed = {'t': 0., 'T': 6.3 + 1.7 * k}
             # labels restart for every build so that the layout strings are comparable
             opt = ref_import('basics.optilayer')
             for cls in list(opt.OptiChild.__subclasses__()) + [opt.OptiChild]:

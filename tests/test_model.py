@@ -365,6 +365,35 @@ def test_freeT_with_safety_distance_and_dubins_freeT():
     assert np.abs(pr.vehicles[0].signals['state'][:, -1] - [3., 3., 0.]).max() < 1e-2
 
 
+def test_trailer_solves():
+    """vehicles/trailer.py (examples/p2p_trailer.py: Dubins vehicle + trailer on a 0.6 m hitch,
+    free end time, the lead vehicle added to the problem a second time): from a rolling guess
+    the oracle converges; the hitch kinematics hold along the solution and the articulation
+    angle stays within +-45 degrees."""
+    from oracle import ipm_c
+    if not ipm_c.available():
+        pytest.skip('C oracle not built')
+    pr = sc.config_trailer(build_solver=False, init_v_til=0.3)
+    tb, f = pr.father.tables, pr.father
+    assert (tb.n, tb.m, tb.n_par) == (61, 3081, 12)
+    r = ipm_c.solve_batch_full(tb, f.get_variables().cat[None], f.set_parameters(0.).cat[None], threads=1)
+    assert r['status'][0] == 0
+    x = r['x'][0]
+    T = x[f._var_struct.entries[(pr.label, 'T')][0]]
+    assert np.hypot(3.4, 3.) / 0.8 < T < 20.
+    C = x[:36].reshape(3, 12)                       # tg_tr, v~, tg of the trailer problem
+    basis = pr.vehicles[0].basis
+    tau = np.linspace(0., 1., 201)
+    S = basis.eval_basis(tau)
+    Bd, P1 = basis.derivative(1)
+    tg_tr, v, tg = S.dot(C[0]), S.dot(C[1]), S.dot(C[2])
+    dtg_tr = Bd.eval_basis(tau).dot(P1.dot(C[0]))
+    hitch = T * v * (2 * tg * (1 - tg_tr**2) - (1 - tg**2) * 2 * tg_tr)
+    assert np.abs(2 * dtg_tr * 0.6 - hitch).max() < T * 1e-3 + 0.05     # band + spline relaxation
+    assert np.abs(2 * np.arctan(tg) - 2 * np.arctan(tg_tr)).max() < np.pi / 4. + 0.02
+    assert abs(tg_tr[-1]) < 1e-6 and abs(tg[-1]) < 1e-6
+
+
 def test_intermediates_small_example_and_guards():
     """lowering.py with 'mid' symbols on a hand-checkable NLP:
     c = x0*x1 (shared), rows  p*c + x2 <= 1  and  2*c - x0 = 0."""
@@ -815,7 +844,7 @@ EXT_GOLDEN = ('config_dubins_plain', 'config_dubins_rect', 'config_dubins_exact'
               'config_holonomic_orient', 'config_bicycle', 'config_agv',
               'config_quadrotor3d_simple', 'config_formation_central', 'config_interveh',
               'config_free_end', 'config_freeT', 'config_freeT_moving', 'config_freeT_safety',
-              'config_dubins_freeT')
+              'config_dubins_freeT', 'config_trailer')
 
 
 def _model_golden(name):
@@ -843,7 +872,7 @@ def test_nlp_definition_equals_the_references_own_model_code(name):
     assert layout(f._var_struct) == [norm(s) for s in M[name + '_var_layout']]
     ref_par = [norm(s) for s in M[name + '_par_layout']]
     keep = np.ones(M[name + '_P'].shape[1], dtype=bool)
-    if 'freeT' in name:
+    if 'freeT' in name or name == 'config_trailer':
         # The reference defines T twice under one name: as a parameter handed to the vehicle
         # and environment rows and -- afterwards -- as the variable of the objective
         # (point2point.py:53-62, 281-284); the parameter is never set.  Here T is the variable
@@ -873,7 +902,7 @@ def test_nlp_definition_equals_the_references_own_model_code(name):
 @pytest.mark.parametrize('name', ['config1', 'config4', 'config5', 'config_holonomic3d',
                                   'config_quadrotor2d', 'config_dubins', 'config_dubins_plain',
                                   'config_holonomic_orient', 'config_bicycle',
-                                  'config_quadrotor3d_simple'])
+                                  'config_quadrotor3d_simple', 'config_trailer'])
 def test_trajectory_extraction_equals_the_references(name):
     """Post-solve extraction: the reference's Vehicle.store ->
     concat_splines / splines2signals / sample_splines, run from /root/reference on a
@@ -886,7 +915,7 @@ def test_trajectory_extraction_equals_the_references(name):
     veh = pr.vehicles[0]
     C, tax = M[name + '_traj_C'], M[name + '_traj_time']
     splines = [BSpline(veh.basis, C[:, k]) for k in range(C.shape[1])]
-    veh.store(1.3, 0.01, [splines], pr.options['horizon_time'], tax)
+    veh.store(1.3, 0.01, [splines], pr.options.get('horizon_time', 10.), tax)   # (free T: the generator's 10 s)
     assert len(M[name + '_traj_keys']) >= 2
     for key in M[name + '_traj_keys']:
         ref = M[name + '_traj_' + str(key)]

@@ -104,3 +104,15 @@ def test_rendezvous_admm_matches_oracle():
         assert np.abs(run.z_i.cpu().numpy() - orc.z_i).max() < NORTH_STAR_TOL
         assert np.abs(run.l_i.cpu().numpy() - orc.l_i).max() < 10 * NORTH_STAR_TOL
         assert abs(rg[0] - ro[0]) < 1e-3 * max(1., ro[0])
+
+
+def test_trailer_matches_oracle():
+    """Trailer + Dubins lead vehicle (2.1 M Jacobian terms, T x intermediate cross terms)."""
+    pr = sc.config_trailer(init_v_til=0.3)
+    tb, f = pr.father.tables, pr.father
+    X0, P = f.get_variables().cat[None], f.set_parameters(0.).cat[None]
+    res = pr.problem.solve_batch(X0, P)
+    ref = ipm_c.solve_batch_full(tb, X0, P, threads=1)
+    assert res['status'][0] == 0 == ref['status'][0]
+    assert abs(int(res['iters'][0]) - int(ref['iters'][0])) <= 2
+    assert np.abs(res['x'] - ref['x'])[:, :36].max() < 1e-3
