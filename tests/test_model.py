@@ -373,10 +373,14 @@ def test_trailer_solves():
     from oracle import ipm_c
     if not ipm_c.available():
         pytest.skip('C oracle not built')
-    pr = sc.config_trailer(build_solver=False, init_v_til=0.3)
+    pr = _cached_problem('config_trailer')
     tb, f = pr.father.tables, pr.father
     assert (tb.n, tb.m, tb.n_par) == (61, 3081, 12)
-    r = ipm_c.solve_batch_full(tb, f.get_variables().cat[None], f.set_parameters(0.).cat[None], threads=1)
+    X0 = f.get_variables().cat[None].copy()
+    for veh, col in ((pr.vehicles[0], 1), (pr.vehicles[1], 0)):      # option init_v_til = 0.3
+        off = f._var_struct.entries[(veh.label, 'splines_seg0')][0]
+        X0[0, off + 12 * col:off + 12 * (col + 1)] = 0.3
+    r = ipm_c.solve_batch_full(tb, X0, f.set_parameters(0.).cat[None], threads=1)
     assert r['status'][0] == 0
     x = r['x'][0]
     T = x[f._var_struct.entries[(pr.label, 'T')][0]]
@@ -770,7 +774,7 @@ def test_holonomic_orient_solves():
     from oracle import ipm_c
     if not ipm_c.available():
         pytest.skip('C oracle not built')
-    pr = sc.config_holonomic_orient(build_solver=False)
+    pr = _cached_problem('config_holonomic_orient')
     tb = pr.father.tables
     assert (tb.n, tb.m, tb.n_par, tb.degree, tb.n_mid) == (189, 3035, 56, 4, 0)
     X0, P = sc.instance_data(pr, 1)
@@ -847,6 +851,17 @@ EXT_GOLDEN = ('config_dubins_plain', 'config_dubins_rect', 'config_dubins_exact'
               'config_dubins_freeT', 'config_trailer')
 
 
+_PROBLEMS = {}
+
+
+def _cached_problem(name):
+    """Scenario built once per test session for the tests that only READ the problem (the
+    large models take 10-30 s to lower)."""
+    if name not in _PROBLEMS:
+        _PROBLEMS[name] = getattr(sc, name)(build_solver=False)
+    return _PROBLEMS[name]
+
+
 def _model_golden(name):
     import os
     fn = 'model_golden_ext.npz' if name in EXT_GOLDEN else 'model_golden.npz'
@@ -864,7 +879,7 @@ def test_nlp_definition_equals_the_references_own_model_code(name):
     constraint row, in the same order, with the same bounds, and the objective."""
     import re
     M = _model_golden(name)
-    pr = getattr(sc, name)(build_solver=False)
+    pr = _cached_problem(name)
     tb, f = pr.father.tables, pr.father
     norm = lambda s: re.sub(r'(vehicle|obstacle|p2p|environment)\d+', r'\1#', str(s))
     layout = lambda st: [norm('%s|%s|%dx%d' % (k[0], k[1], v[2][0], v[2][1]))
