@@ -62,10 +62,19 @@ class Dubins(Vehicle):
             dx = v_til * (1 - tg_ha**2)
             dy = v_til * (2 * tg_ha)
             tag = '' if not cache else str(len(cache))      # a trailer's copies: own mids
-            cache[key] = (
-                splines,                   # keeps the ids alive
-                self.integrate_once(self._shared('dx' + tag, dx), self.pos0[0], self.t, horizon_time),
-                self.integrate_once(self._shared('dy' + tag, dy), self.pos0[1], self.t, horizon_time))
+            if not self.options['substitution']:
+                # the coefficients of the integrated, re-anchored POSITION splines are the
+                # shared intermediates: the rows that use the position (terminal rows,
+                # hyperplane normal x position, (1 + tg^2) x position for a non-circular
+                # shape) then hold one intermediate per monomial instead of the sum over
+                # every product-spline coefficient before that knot -- 10-20 x smaller tables
+                x = self._shared('x' + tag, self.integrate_once(dx, self.pos0[0], self.t, horizon_time))
+                y = self._shared('y' + tag, self.integrate_once(dy, self.pos0[1], self.t, horizon_time))
+            else:       # substitution: the position enters two band rows only -- the
+                        # product-spline coefficients are the smaller set
+                x = self.integrate_once(self._shared('dx' + tag, dx), self.pos0[0], self.t, horizon_time)
+                y = self.integrate_once(self._shared('dy' + tag, dy), self.pos0[1], self.t, horizon_time)
+            cache[key] = (splines, x, y)   # (the splines keep the ids alive)
         return cache[key][1], cache[key][2]
 
     def define_trajectory_constraints(self, splines, horizon_time):

@@ -621,8 +621,8 @@ def test_dubins_default_formulation_receding_horizon():
         pytest.skip('C oracle not built')
     pr = sc.config_dubins_plain(build_solver=False)
     tb = pr.father.tables
-    assert (tb.n, tb.m, tb.n_mid, tb.degree) == (190, 856, 116, 3)
-    assert tb.nnz_wx == 1276 and tb.W.n_out == tb.nnz_w + tb.nnz_wx
+    assert (tb.n, tb.m, tb.n_mid, tb.degree) == (190, 856, 118, 3)
+    assert tb.nnz_wx == 308 and tb.W.n_out == tb.nnz_w + tb.nnz_wx
     ev = TableEval(tb)
     rng = np.random.default_rng(3)
     X0, P = sc.instance_data(pr, 1)
@@ -691,7 +691,7 @@ def test_bicycle_tables_and_solve():
         pytest.skip('C oracle not built')
     pr = sc.config_bicycle(build_solver=False)
     tb = pr.father.tables
-    assert (tb.n, tb.m, tb.n_par, tb.n_mid, tb.degree) == (85, 646, 25, 165, 5)
+    assert (tb.n, tb.m, tb.n_par, tb.n_mid, tb.degree) == (85, 646, 25, 167, 5)
     assert tb.nnz_wx > 0 and (tb.xq_b >= 0).any() and (tb.xq_b < 0).any()
     ev = TableEval(tb)
     rng = np.random.default_rng(4)
