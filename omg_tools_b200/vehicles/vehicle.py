@@ -88,6 +88,27 @@ class Vehicle(OptiChild):
             self.splines.append(spline)
         return self.splines
 
+    def _share_spline(self, name, spline):
+        """Spline whose non-linear coefficients are named intermediates (basics/poly.py
+        new_mid): products that many rows repeat -- (1 +- tg^2), position x (1 + tg^2) of a
+        vehicle with a heading -- are then evaluated once and the rows are bilinear in the
+        hyperplane coefficients and the intermediates, instead of expanding every product
+        spline into every row (the shared nodes of CasADi's expression graph).  Coefficients
+        that already contain intermediates are left as they are (no nesting)."""
+        from ..basics.poly import Poly, new_mid, sym_info, resolve
+        from ..basics.spline import BSpline
+        if not isinstance(spline, BSpline):
+            return spline
+        cnt = self.__dict__.setdefault('_share_cnt', [0])
+        coeffs = np.empty(len(spline.coeffs), dtype=object)
+        for k, c in enumerate(spline.coeffs):
+            if (isinstance(c, Poly) and c.degree() >= 2 and
+                    not any(sym_info(resolve(sid)).kind == 'mid' for sid in c.symbols())):
+                c = new_mid('%s_%s%d_%d' % (self.label, name, cnt[0], k), c)
+            coeffs[k] = c
+        cnt[0] += 1
+        return BSpline(spline.basis, coeffs)
+
     def define_collision_constraints_2d(self, hyperplanes, room, positions,
                                         horizon_time, tg_ha=0, offset=0):
         t = self.define_symbol('t')
@@ -95,9 +116,16 @@ class Vehicle(OptiChild):
         safety_weight = self.options['safety_weight']
         positions = [positions] if not isinstance(positions[0], list) \
             else positions
+        from ..basics.spline import BSpline
+        heading = isinstance(tg_ha, BSpline)
+        if heading:     # products shared by every row of this call (see _share_spline)
+            one_m, one_p = self._share_spline('c', 1. - tg_ha**2), self._share_spline('q', 1 + tg_ha**2)
         for s, shape in enumerate(self.shapes):
             position = positions[s]
             checkpoints, rad = shape.get_checkpoints()
+            if heading:
+                posq = [self._share_spline('px', position[0] * (1 + tg_ha**2) + offset * (1 - tg_ha**2)),
+                        self._share_spline('py', position[1] * (1 + tg_ha**2) + offset * (2 * tg_ha))]
             # obstacle avoidance: a.(R chk + pos) - b + rad + sd - eps <= 0
             if shape in hyperplanes:
                 for k, hyperplane in enumerate(hyperplanes[shape]):
@@ -115,13 +143,19 @@ class Vehicle(OptiChild):
                         eps = 0.
                     for l, chck in enumerate(checkpoints):
                         con = 0
-                        con += (a[0] * chck[0] + a[1] * chck[1]) * (1. - tg_ha**2)
-                        con += (-a[0] * chck[1] + a[1] * chck[0]) * (2 * tg_ha)
-                        pos = [0, 0]
-                        pos[0] = position[0] * (1 + tg_ha**2) + offset * (1 - tg_ha**2)
-                        pos[1] = position[1] * (1 + tg_ha**2) + offset * (2 * tg_ha)
-                        con += (a[0] * pos[0] + a[1] * pos[1])
-                        con += (-b + sl * rad[l] + safety_distance - eps) * (1 + tg_ha**2)
+                        if heading:
+                            con += (a[0] * chck[0] + a[1] * chck[1]) * one_m
+                            con += (-a[0] * chck[1] + a[1] * chck[0]) * (2 * tg_ha)
+                            con += (a[0] * posq[0] + a[1] * posq[1])
+                            con += (-b + sl * rad[l] + safety_distance - eps) * one_p
+                        else:
+                            con += (a[0] * chck[0] + a[1] * chck[1]) * (1. - tg_ha**2)
+                            con += (-a[0] * chck[1] + a[1] * chck[0]) * (2 * tg_ha)
+                            pos = [0, 0]
+                            pos[0] = position[0] * (1 + tg_ha**2) + offset * (1 - tg_ha**2)
+                            pos[1] = position[1] * (1 + tg_ha**2) + offset * (2 * tg_ha)
+                            con += (a[0] * pos[0] + a[1] * pos[1])
+                            con += (-b + sl * rad[l] + safety_distance - eps) * (1 + tg_ha**2)
                         self.define_constraint(con, -inf, 0)
             # room constraints
             if self.options['room_constraints']:
@@ -148,13 +182,19 @@ class Vehicle(OptiChild):
                     for l, chck in enumerate(checkpoints):
                         for hpp in hyp_room.values():
                             con = 0
-                            con += (hpp['a'][0] * chck[0] + hpp['a'][1] * chck[1]) * (1. - tg_ha**2)
-                            con += (-hpp['a'][0] * chck[1] + hpp['a'][1] * chck[0]) * (2 * tg_ha)
-                            pos = [0, 0]
-                            pos[0] = position[0] * (1 + tg_ha**2) + offset * (1 - tg_ha**2)
-                            pos[1] = position[1] * (1 + tg_ha**2) + offset * (2 * tg_ha)
-                            con += (hpp['a'][0] * pos[0] + hpp['a'][1] * pos[1])
-                            con += (-hpp['b'] + rad[l]) * (1 + tg_ha**2)
+                            if heading:
+                                con += (hpp['a'][0] * chck[0] + hpp['a'][1] * chck[1]) * one_m
+                                con += (-hpp['a'][0] * chck[1] + hpp['a'][1] * chck[0]) * (2 * tg_ha)
+                                con += (hpp['a'][0] * posq[0] + hpp['a'][1] * posq[1])
+                                con += (-hpp['b'] + rad[l]) * one_p
+                            else:
+                                con += (hpp['a'][0] * chck[0] + hpp['a'][1] * chck[1]) * (1. - tg_ha**2)
+                                con += (-hpp['a'][0] * chck[1] + hpp['a'][1] * chck[0]) * (2 * tg_ha)
+                                pos = [0, 0]
+                                pos[0] = position[0] * (1 + tg_ha**2) + offset * (1 - tg_ha**2)
+                                pos[1] = position[1] * (1 + tg_ha**2) + offset * (2 * tg_ha)
+                                con += (hpp['a'][0] * pos[0] + hpp['a'][1] * pos[1])
+                                con += (-hpp['b'] + rad[l]) * (1 + tg_ha**2)
                             self.define_constraint(con, -inf, 0)
 
     def define_collision_constraints_3d(self, hyperplanes, room, positions,

@@ -776,7 +776,7 @@ def test_holonomic_orient_solves():
         pytest.skip('C oracle not built')
     pr = _cached_problem('config_holonomic_orient')
     tb = pr.father.tables
-    assert (tb.n, tb.m, tb.n_par, tb.degree, tb.n_mid) == (189, 3035, 56, 4, 0)
+    assert (tb.n, tb.m, tb.n_par, tb.degree, tb.n_mid) == (189, 3035, 56, 3, 232)
     X0, P = sc.instance_data(pr, 1)
     r = ipm_c.solve_batch_full(tb, X0, P, threads=1)
     assert r['status'][0] == 0

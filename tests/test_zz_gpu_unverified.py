@@ -46,8 +46,8 @@ def test_dubins_default_formulation_problem_solve_dropin():
 
 
 def test_holonomic_orient_matches_oracle():
-    """HolonomicOrient (m = 3035 rows, 627 k Jacobian terms, no intermediates): the standard
-    kernel at a row count no verified test reaches (most per-row arrays in scratch)."""
+    """HolonomicOrient (m = 3035 rows, 232 shared heading products): the XL kernel with the
+    cross-Hessian gather at a row count no verified test reaches."""
     pr = sc.config_holonomic_orient()
     tb = pr.father.tables
     X0, P = sc.instance_data(pr, 4, jitter=0.05, seed=2)
