@@ -173,6 +173,18 @@ def test_two_vehicles_with_intervehicle_avoidance(emu):
     assert d.min() > 0.2 - 1e-3
 
 
+def test_xl_kernel_trailer_free_end_time(emu):
+    """examples/p2p_trailer.py (two vehicles in one problem, free end time, 290 shared
+    intermediates, 53 k Jacobian slots): the emulated XL kernel follows the oracle."""
+    pr = sc.config_trailer(init_v_til=0.3)
+    tb, f = pr.father.tables, pr.father
+    X0, P = f.get_variables().cat[None], f.set_parameters(0.).cat[None]
+    res = pr.problem.solve_batch(X0, P)
+    ref = ipm_c.solve_batch_full(tb, X0, P, threads=1)
+    assert res['status'][0] == 0 and res['iters'][0] == ref['iters'][0]
+    assert np.abs(res['x'] - ref['x']).max() < 1e-6 and np.abs(res['f'] - ref['f']).max() < 1e-9
+
+
 def test_edge_cases_and_dropin(emu):
     """Empty batch, per-instance bounds, NaN parameters, max_iter, warm start with
     multipliers, Problem.solve()."""
