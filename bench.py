@@ -143,6 +143,12 @@ WORKLOADS = {
                'intervals, 2 plate obstacles',
     'config5': 'config5: Holonomic Point2point through the revolving door '
                '(examples/revolving_door.py), 2 static + 2 rotating beams',
+    # further models (not BASELINE configs; for kernel work on the XL path)
+    'config_dubins_plain': 'Dubins Point2point, default formulation (examples/p2p_dubins.py scene, '
+                           'fixed end time), cross-Hessian tables',
+    'config_holonomic_orient': 'HolonomicOrient Point2point (examples/p2p_holonomic_orient.py scene, '
+                               'fixed end time), shared heading products',
+    'config_quadrotor3d_simple': 'SimpleQuadrotor3D Point2point, 2 plate obstacles',
 }
 
 # DRAM traffic of the solver kernel per solve, from the ncu --set full captures
@@ -151,7 +157,8 @@ WORKLOADS = {
 NCU_DRAM_BYTES_PER_SOLVE = {'config2': (1.151488e6 + 1.359360e6) / 148.,
                             'config4': (3.464099e9 + 7.549988e9) / 148.}
 # bounded CPU sample: about 20 s of single-core work of the C oracle per measurement
-CPU_SAMPLE = {'config1': 2048, 'config2': 1024, 'config4': 96, 'config5': 512}
+CPU_SAMPLE = {'config1': 2048, 'config2': 1024, 'config4': 96, 'config5': 512,
+              'config_dubins_plain': 256, 'config_holonomic_orient': 32, 'config_quadrotor3d_simple': 256}
 
 
 def run_reference(args, rank, world):
