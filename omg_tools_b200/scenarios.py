@@ -444,11 +444,19 @@ def config_interveh(options=None, build_solver=True):
     return _p2p(vehicles, environment, opts, build_solver)
 
 
+def config_formation_central_example(options=None, build_solver=True):
+    """examples/formation_holonomic_central.py exactly: soft formation AND inter-vehicle
+    avoidance (six vehicle pairs, each with a separating hyperplane spline)."""
+    opts = {'inter_vehicle_avoidance': True}
+    opts.update(options or {})
+    return config_formation_central(opts, build_solver)
+
+
 def config_formation_central(options=None, build_solver=True, soft=True):
     """examples/formation_holonomic_central.py: four Holonomic vehicles starting in a row,
     formation RegularPolyhedron(0.2, 4) to (2, 2), two Rectangle(3, 0.2) walls, horizon 15 s,
-    soft formation constraints with weight 100 (the example's inter-vehicle avoidance is
-    not built)."""
+    soft formation constraints with weight 100 (option inter_vehicle_avoidance as in the
+    example: config_formation_central_example)."""
     from .vehicles.fleet import Fleet
     from .basics.shape import RegularPolyhedron
     from .problems.formation_central import FormationPoint2pointCentral

@@ -449,7 +449,7 @@ def build_reference(name):
         problem.father.reset()
         problem.construct()
         return problem
-    elif name == 'config_formation_central':
+    elif name in ('config_formation_central', 'config_formation_central_example'):
         fl = ref_import('vehicles.fleet')
         fc = ref_import('problems.formation_central')
         N = 4
@@ -467,6 +467,8 @@ def build_reference(name):
         problem = fc.FormationPoint2pointCentral(
             fleet, environment, options={'verbose': 0, 'horizon_time': 15, 'soft_formation': True,
                                          'soft_formation_weight': 100})
+        if name.endswith('_example'):
+            problem.set_options({'inter_vehicle_avoidance': True})
         problem.father.reset()
         problem.construct()
         return problem
@@ -625,7 +627,7 @@ EXT_NAMES = ('config_dubins_plain', 'config_dubins_rect', 'config_dubins_exact',
              'config_holonomic_orient', 'config_bicycle', 'config_agv',
              'config_quadrotor3d_simple', 'config_formation_central', 'config_interveh', 'config_free_end',
              'config_freeT', 'config_freeT_moving', 'config_freeT_safety', 'config_dubins_freeT',
-             'config_trailer')
+             'config_trailer', 'config_formation_central_example')
 
 
 def main(ext=False):
@@ -638,7 +640,8 @@ def main(ext=False):
         for k in range(n_samples):
             REG = Registry(seed=1000 * k + 7)
             horizon = {'config4': 5., 'config_quadrotor2d': 5., 'config_holonomic3d': 12.,
-                       'config_formation_central': 15.}.get(name, 10.)
+                       'config_formation_central': 15.,
+                       'config_formation_central_example': 15.}.get(name, 10.)
             # T is the horizon of the scenario, t a time inside the first knot interval
             REG.fixed = {'T': horizon, 't': 0.037 * horizon * (k + 1)}
             if 'freeT' in name or name == 'config_trailer':
