@@ -362,6 +362,53 @@ def config_trailer(options=None, build_solver=True, init_v_til=0.):
     return problem
 
 
+def config_warehouse(options=None, build_solver=True):
+    """examples/p2p_holonomic_warehouse.py: Holonomic with Euclidean speed / acceleration limits
+    and a safety distance, six square racks and two moving circles in a 7 x 4.5 room, free
+    end time (n = 423)."""
+    vehicle = Holonomic(options={'syslimit': 'norm_2', 'safety_distance': 0.1})
+    vehicle.define_knots(knot_intervals=10)
+    vehicle.set_initial_conditions([0., 0.])
+    vehicle.set_terminal_conditions([6., 3.5])
+    environment = Environment(room={'shape': Rectangle(width=7., height=4.5), 'position': [3., 1.75]})
+    rectangle = Rectangle(width=1., height=1.)
+    for pos in ([1., 1.], [3., 1.], [5., 1.], [1., 2.5], [3., 2.5], [5., 2.5]):
+        environment.add_obstacle(Obstacle({'position': pos}, shape=rectangle))
+    trajectories1 = {'velocity': {'time': [0, 2], 'values': [[0., 0.0], [0., 0.15]]}}
+    trajectories2 = {'velocity': {'time': [0, 2], 'values': [[0., 0.0], [0., -0.1]]}}
+    environment.add_obstacle(Obstacle({'position': [4., 2.5]}, shape=Circle(0.5),
+                                      simulation={'trajectories': trajectories2}))
+    environment.add_obstacle(Obstacle({'position': [2., 1.]}, shape=Circle(0.5),
+                                      simulation={'trajectories': trajectories1}))
+    return _p2p(vehicle, environment, options, build_solver, freeT=True)
+
+
+def config_revolving_door_diffdrive(options=None, build_solver=True, init_v_til=0.):
+    """examples/revolving_door_diffdrive.py: a Dubins vehicle (default formulation, 6 knot
+    intervals) through the slowly revolving door: two static and two rotating beams,
+    horizon 15 s, hard terminal constraints."""
+    from . import Dubins, Beam
+    vehicle = Dubins(bounds={'vmax': 0.7, 'wmin': -30., 'wmax': 30.}, options={'init_v_til': init_v_til})
+    vehicle.define_knots(knot_intervals=6)
+    vehicle.set_initial_conditions([0., -2.0, np.pi / 2])
+    vehicle.set_terminal_conditions([-1.5, 2.0, np.pi / 2])
+    environment = Environment(room={'shape': Square(5.)})
+    beam1 = Beam(width=2.2, height=0.2)
+    environment.add_obstacle(Obstacle({'position': [-2., 0.]}, shape=beam1))
+    environment.add_obstacle(Obstacle({'position': [2., 0.]}, shape=beam1))
+    beam2 = Beam(width=1.4, height=0.2)
+    horizon_time = 15.
+    omega = 0.1 * 1. * (2 * np.pi / horizon_time)
+    for orient in (0. + np.pi / 4., 0.5 * np.pi + np.pi / 4.):
+        environment.add_obstacle(Obstacle(
+            {'position': [0., 0.], 'velocity': [0., 0.], 'orientation': orient,
+             'angular_velocity': omega}, shape=beam2, simulation={},
+            options={'horizon_time': horizon_time}))
+    opts = {'horizon_time': horizon_time, 'hard_term_con': True}
+    opts.update(options or {})
+    return _p2p(vehicle, environment, opts, build_solver)
+
+
 def instance_data(problem, batch, jitter=0.0, seed=0, current_time=0.):
     """(X0[B,n], P[B,n_par]) for a cold solve: linear initial guess
     (holonomic.py:118-127) and parameters at current_time.  jitter>0 perturbs

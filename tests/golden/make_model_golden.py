@@ -424,6 +424,45 @@ def build_reference(name):
         problem.father.reset()
         problem.construct()
         return problem
+    elif name == 'config_warehouse':
+        vehicle = hol.Holonomic(options={'syslimit': 'norm_2', 'safety_distance': 0.1})
+        vehicle.define_knots(knot_intervals=10)
+        vehicle.set_initial_conditions([0., 0.])
+        vehicle.set_terminal_conditions([6., 3.5])
+        environment = env.Environment(room={'shape': shp.Rectangle(width=7., height=4.5),
+                                            'position': [3., 1.75]})
+        rectangle = shp.Rectangle(width=1., height=1.)
+        for pos in ([1., 1.], [3., 1.], [5., 1.], [1., 2.5], [3., 2.5], [5., 2.5]):
+            environment.add_obstacle(obs.Obstacle({'position': pos}, shape=rectangle))
+        trajectories1 = {'velocity': {'time': [0, 2], 'values': [[0., 0.0], [0., 0.15]]}}
+        trajectories2 = {'velocity': {'time': [0, 2], 'values': [[0., 0.0], [0., -0.1]]}}
+        environment.add_obstacle(obs.Obstacle({'position': [4., 2.5]}, shape=shp.Circle(0.5),
+                                              simulation={'trajectories': trajectories2}))
+        environment.add_obstacle(obs.Obstacle({'position': [2., 1.]}, shape=shp.Circle(0.5),
+                                              simulation={'trajectories': trajectories1}))
+        problem = p2p.Point2point(vehicle, environment, options={'verbose': 0}, freeT=True)
+        problem.father.reset()
+        problem.construct()
+        return problem
+    elif name == 'config_revolving_door_diffdrive':
+        db = ref_import('vehicles.dubins')
+        vehicle = db.Dubins(bounds={'vmax': 0.7, 'wmin': -30., 'wmax': 30.})
+        vehicle.define_knots(knot_intervals=6)
+        vehicle.set_initial_conditions([0., -2.0, np.pi / 2])
+        vehicle.set_terminal_conditions([-1.5, 2.0, np.pi / 2])
+        environment = env.Environment(room={'shape': shp.Square(5.)})
+        beam1 = shp.Beam(width=2.2, height=0.2)
+        environment.add_obstacle(obs.Obstacle({'position': [-2., 0.]}, shape=beam1))
+        environment.add_obstacle(obs.Obstacle({'position': [2., 0.]}, shape=beam1))
+        beam2 = shp.Beam(width=1.4, height=0.2)
+        horizon_time = 15.
+        omega = 0.1 * 1. * (2 * np.pi / horizon_time)
+        for orient in (0. + np.pi / 4., 0.5 * np.pi + np.pi / 4.):
+            environment.add_obstacle(obs.Obstacle(
+                {'position': [0., 0.], 'velocity': [0., 0.], 'orientation': orient,
+                 'angular_velocity': omega}, shape=beam2, simulation={},
+                options={'horizon_time': horizon_time}))
+        options = {'horizon_time': horizon_time, 'hard_term_con': True}
     elif name == 'config_free_end':
         vehicle = hol.Holonomic()
         vehicle.set_options({'safety_distance': 0.1})
@@ -627,7 +666,8 @@ EXT_NAMES = ('config_dubins_plain', 'config_dubins_rect', 'config_dubins_exact',
              'config_holonomic_orient', 'config_bicycle', 'config_agv',
              'config_quadrotor3d_simple', 'config_formation_central', 'config_interveh', 'config_free_end',
              'config_freeT', 'config_freeT_moving', 'config_freeT_safety', 'config_dubins_freeT',
-             'config_trailer', 'config_formation_central_example')
+             'config_trailer', 'config_formation_central_example', 'config_warehouse',
+             'config_revolving_door_diffdrive')
 
 
 def main(ext=False):
@@ -641,10 +681,11 @@ def main(ext=False):
             REG = Registry(seed=1000 * k + 7)
             horizon = {'config4': 5., 'config_quadrotor2d': 5., 'config_holonomic3d': 12.,
                        'config_formation_central': 15.,
-                       'config_formation_central_example': 15.}.get(name, 10.)
+                       'config_formation_central_example': 15.,
+                       'config_revolving_door_diffdrive': 15.}.get(name, 10.)
             # T is the horizon of the scenario, t a time inside the first knot interval
             REG.fixed = {'T': horizon, 't': 0.037 * horizon * (k + 1)}
-            if 'freeT' in name or name == 'config_trailer':
+            if 'freeT' in name or name in ('config_trailer', 'config_warehouse'):
                 # t is 0 (point2point.py:300-306); T -- parameter, variable and the vehicles'
                 # placeholders of that name -- one value per sample
                 REG.fixed = {'t': 0., 'T': 6.3 + 1.7 * k}

@@ -848,7 +848,8 @@ EXT_GOLDEN = ('config_dubins_plain', 'config_dubins_rect', 'config_dubins_exact'
               'config_holonomic_orient', 'config_bicycle', 'config_agv',
               'config_quadrotor3d_simple', 'config_formation_central', 'config_interveh',
               'config_free_end', 'config_freeT', 'config_freeT_moving', 'config_freeT_safety',
-              'config_dubins_freeT', 'config_trailer', 'config_formation_central_example')
+              'config_dubins_freeT', 'config_trailer', 'config_formation_central_example',
+              'config_warehouse', 'config_revolving_door_diffdrive')
 
 
 _PROBLEMS = {}
@@ -887,7 +888,7 @@ def test_nlp_definition_equals_the_references_own_model_code(name):
     assert layout(f._var_struct) == [norm(s) for s in M[name + '_var_layout']]
     ref_par = [norm(s) for s in M[name + '_par_layout']]
     keep = np.ones(M[name + '_P'].shape[1], dtype=bool)
-    if 'freeT' in name or name == 'config_trailer':
+    if 'freeT' in name or name in ('config_trailer', 'config_warehouse'):
         # The reference defines T twice under one name: as a parameter handed to the vehicle
         # and environment rows and -- afterwards -- as the variable of the objective
         # (point2point.py:53-62, 281-284); the parameter is never set.  Here T is the variable
