@@ -12,6 +12,7 @@
  *                              C++ twin: Point2Point::solve, Point2Point.cpp:207-231
  *   status/iters arrays  <->  self.problem.stats()['return_status']
  *                              omgtools/problems/problem.py:119-128
+ *   omg_feas_batch       <->  (IPOPT's restoration phase inside the same nlpsol call)
  *   omg_shift_batch      <->  father.transform_primal_splines(T.dot(coeffs))
  *                              omgtools/problems/point2point.py:187-198,
  *                              optilayer.py:470-490; C++: transformSplines,
@@ -187,6 +188,25 @@ int omg_solve_batch_host(omg_problem* h, int32_t B,
                          int32_t bounds_shared, const double* lam_g0,
                          double* x, double* lam_g, double* f,
                          int32_t* status, int32_t* iters);
+
+/* Feasibility phase, the fallback the host runs on instances that came back with
+ * OMG_RESTORATION_FAILED before solving them once more (stand-in for the feasibility
+ * part of IPOPT's restoration phase, which the reference relies on implicitly through
+ * nlpsol(...,'ipopt',...), optilayer.py:55-60 / problem.py:113-128): up to max_steps
+ * Levenberg-Marquardt steps on the violation v(x) = g(x,p) - clip(g(x,p), lbg, ubg),
+ * (Jv^T Jv + lam I) dx = -Jv^T v, lam from 1e-3, /10 on an accepted step, x10 (at most
+ * 12 times) on a rejected one; stops when max|v| <= 1e-8.  DEVICE pointers; x [B][n],
+ * viol [B] (max |v| at the returned point), steps [B].  Asynchronous on `stream`. */
+int omg_feas_batch(omg_problem* h, int32_t B,
+                   const double* x0, const double* p,
+                   const double* lbg, const double* ubg, int32_t bounds_shared,
+                   int32_t max_steps, double* x, double* viol, int32_t* steps,
+                   void* stream);
+/* Same call with HOST buffers (synchronous). */
+int omg_feas_batch_host(omg_problem* h, int32_t B,
+                        const double* x0, const double* p,
+                        const double* lbg, const double* ubg, int32_t bounds_shared,
+                        int32_t max_steps, double* x, double* viol, int32_t* steps);
 
 /* Receding-horizon warm start: x[b, off:off+len*ncol] <- T (len x len) applied
  * to each of the ncol columns, for n_blocks spline variables (DEVICE x,

@@ -1386,6 +1386,175 @@ __global__ void omg_admm_zl_kernel(int nsh, int nn, int L, const double* __restr
   }
 }
 
+// ---------------------------------------------------------------------------
+// Feasibility phase (fallback after Restoration_Failed; oracle/ipm_ref.py feasibility_lm):
+// Levenberg-Marquardt on the constraint violation v(x) = g - clip(g, lbg, ubg),
+//   (Jv^T Jv + lam I) dx = -Jv^T v,   Jv = the rows with v != 0,
+// accept x + dx when it lowers 1/2 |v|^2 (then lam /= 10), else lam *= 10 (12 tries).
+// One block per instance at a time; everything lives in the block's L2-resident scratch:
+//   V[n_v] | jx[nnz_jx] | v[m] | vt[m] | A[n*n] | L[(n+1)*n] | rhs[n] | dx[n] | xe[n_xe] | xt[n_xe]
+// A is assembled one thread per column through the CSC view of the Jacobian (no atomics:
+// the sums are in a fixed order), the dense Cholesky carries the right-hand side as row n.
+// ---------------------------------------------------------------------------
+struct FeasArgs {
+  int B, bounds_shared, max_steps;
+  const double *x0, *p, *lbg, *ubg;
+  double *x, *viol; int* steps;
+  double* scr; size_t stride;
+};
+
+__device__ __forceinline__ double feas_viol(double g, double lb, double ub) {
+  return (g < lb) ? g - lb : ((g > ub) ? g - ub : 0.0);
+}
+
+// v[i] for the point xq (mids of xq refreshed first); returns 1/2 |v|^2 and max |v| to all threads
+__device__ __forceinline__ void feas_residual(const DevTab& T, const double* V, double* xq, const double* lbg,
+                                              const double* ubg, double* v, double* red, double* phi, double* vmax) {
+  const int tid = threadIdx.x;
+  for (int l = tid; l < T.n_mid; l += NT) { const int2 r = T.midg[l]; xq[T.n + 1 + l] = eval_range(T.Gt, r.x, r.y, V, xq); }
+  __syncthreads();
+  double ss = 0.0, mx = 0.0;
+  for (int i = tid; i < T.m; i += NT) {
+    const RowRec rr = T.rowrec[i];
+    const double vi = feas_viol(eval_range(T.Gt, rr.g0, rr.g1, V, xq), lbg[i], ubg[i]);
+    v[i] = vi; ss += vi * vi; mx = fmax(mx, fabs(vi));
+  }
+  double r2[2] = {ss, mx}; const int o2[2] = {OP_SUM, OP_MAX};
+  block_reduce<2>(r2, o2, red);
+  *phi = 0.5 * r2[0]; *vmax = r2[1];
+}
+
+__global__ void __launch_bounds__(256, 2)
+omg_feas_kernel(const DevTab T, const FeasArgs F) {
+  __shared__ double red[MAX_NWARP * 2];
+  __shared__ double piv_s;
+  const int tid = threadIdx.x;
+  const int n = T.n, m = T.m, n_xe = T.n + 1 + T.n_mid;
+  double* D = F.scr + (size_t)blockIdx.x * F.stride;
+  double* V = D;            double* jx = V + T.n_v;     double* v = jx + T.nnz_jx;
+  double* vt = v + m;       double* Am = vt + m;        double* L = Am + (size_t)n * n;
+  double* rhs = L + (size_t)(n + 1) * n;  double* dx = rhs + n;
+  double* xe = dx + n;      double* xt = xe + n_xe;
+  for (int inst = blockIdx.x; inst < F.B; inst += gridDim.x) {
+    const double* par = F.p + (size_t)inst * T.n_par;
+    const double* lbg = F.lbg + (F.bounds_shared ? 0 : (size_t)inst * m);
+    const double* ubg = F.ubg + (F.bounds_shared ? 0 : (size_t)inst * m);
+    for (int i = tid; i < 1 + T.n_par; i += NT) V[i] = (i == 0) ? 1.0 : par[i - 1];
+    __syncthreads();
+    for (int l = 0; l < T.n_levels; ++l) {      // parameter tape (as ipm_body S1)
+      for (int e = T.level_ptr[l] + tid; e < T.level_ptr[l + 1]; e += NT) {
+        double acc = 0.0;
+        for (int t = T.tape_ptr[e]; t < T.tape_ptr[e + 1]; ++t) {
+          const int4 f = __ldg(reinterpret_cast<const int4*>(T.tape_fac) + t);
+          acc += T.tape_coef[t] * V[f.x] * V[f.y] * V[f.z] * V[f.w];
+        }
+        switch (T.tape_func[e]) {
+          case 1: acc = 1.0 / acc; break;
+          case 2: acc = (acc >= 0.0) ? 1.0 : 0.0; break;
+          case 3: acc = (acc > 0.0) ? 1.0 : 0.0; break;
+          case 4: acc = sin(acc); break;
+          case 5: acc = cos(acc); break;
+          case 6: acc = sqrt(acc); break;
+          default: break;
+        }
+        V[1 + T.n_par + e] = acc;
+      }
+      __syncthreads();
+    }
+    for (int i = tid; i < n_xe; i += NT) {
+      const double xi = (i < n) ? F.x0[(size_t)inst * n + i] : ((i == n) ? 1.0 : 0.0);
+      xe[i] = xi; xt[i] = xi;
+    }
+    __syncthreads();
+    double phi, vmax, lam = 1e-3;
+    feas_residual(T, V, xe, lbg, ubg, v, red, &phi, &vmax);
+    int steps = 0;
+    while (steps < F.max_steps && vmax > 1e-8) {
+      jac_xl(T, V, xe, jx, jx, nullptr);           // jx[0..nnz_j) = Jacobian slots (jval aliases jx)
+      // normal equations, thread c owns row c of A: sum over the active rows of column c
+      for (int c = tid; c < n; c += NT) {
+        double* Ac = Am + (size_t)c * n;
+        for (int k = 0; k < n; ++k) Ac[k] = 0.0;
+        double bc = 0.0;
+        for (int q = T.colptr[c]; q < T.colptr[c + 1]; ++q) {
+          const unsigned cr = __ldg(T.colrec + q);
+          const int s1 = (int)(cr & 0xffffu), r = (int)(cr >> 16);
+          const double vr = v[r];
+          if (vr == 0.0) continue;
+          const double j1 = jx[s1];
+          bc -= j1 * vr;
+          const RowRec rr = T.rowrec[r];
+          for (int k = 0; k < rr.ns; ++k) Ac[T.jcol16[rr.s0 + k]] += j1 * jx[rr.s0 + k];
+        }
+        rhs[c] = bc;
+      }
+      __syncthreads();
+      bool accepted = false;
+      for (int attempt = 0; attempt < 12 && !accepted; ++attempt) {
+        // L = lower(A) + lam I, row n = rhs
+        for (int e = tid; e < (n + 1) * n; e += NT) {
+          const int i = e / n, k = e - i * n;
+          L[e] = (i == n) ? rhs[k] : ((k <= i) ? Am[e] + ((k == i) ? lam : 0.0) : 0.0);
+        }
+        __syncthreads();
+        bool ok = true;
+        for (int j = 0; j < n; ++j) {
+          if (tid == 0) {
+            const double d = L[(size_t)j * n + j];
+            const double pv = (d > 0.0 && d < 1e300) ? sqrt(d) : -1.0;
+            piv_s = pv;
+            if (pv > 0.0) L[(size_t)j * n + j] = pv;
+          }
+          __syncthreads();
+          const double pv = piv_s;
+          if (!(pv > 0.0)) { ok = false; break; }
+          const double inv = 1.0 / pv;
+          for (int i = j + 1 + tid; i <= n; i += NT) L[(size_t)i * n + j] *= inv;
+          __syncthreads();
+          for (int i = j + 1 + tid; i <= n; i += NT) {
+            double* Li = L + (size_t)i * n;
+            const double lij = Li[j];
+            const int kend = (i < n) ? i : n - 1;
+            for (int k = j + 1; k <= kend; ++k) Li[k] -= lij * L[(size_t)k * n + j];
+          }
+          __syncthreads();
+        }
+        __syncthreads();
+        double pt = 0.0, vmt = 0.0;
+        if (ok) {
+          // back substitution L^T dx = w (w = row n)
+          double* w = L + (size_t)n * n;
+          for (int j = n - 1; j >= 0; --j) {
+            if (tid == 0) dx[j] = w[j] / L[(size_t)j * n + j];
+            __syncthreads();
+            const double dj = dx[j];
+            for (int k = tid; k < j; k += NT) w[k] -= L[(size_t)j * n + k] * dj;
+            __syncthreads();
+          }
+          for (int i = tid; i < n; i += NT) xt[i] = xe[i] + dx[i];
+          __syncthreads();
+          feas_residual(T, V, xt, lbg, ubg, vt, red, &pt, &vmt);
+        }
+        if (ok && pt < phi) {          // (a NaN pt compares false)
+          for (int i = tid; i < n_xe; i += NT) xe[i] = xt[i];
+          for (int i = tid; i < m; i += NT) v[i] = vt[i];
+          phi = pt; vmax = vmt; lam = fmax(lam / 10.0, 1e-12);
+          accepted = true;
+        } else {
+          lam *= 10.0;
+        }
+        __syncthreads();
+      }
+      if (!accepted) break;
+      ++steps;
+    }
+    for (int i = tid; i < n; i += NT) F.x[(size_t)inst * n + i] = xe[i];
+    if (tid == 0) { F.viol[inst] = vmax; F.steps[inst] = steps; }
+    __syncthreads();
+  }
+}
+
+
 // ===========================================================================
 // host side: C ABI
 // ===========================================================================
@@ -1412,6 +1581,8 @@ struct omg_problem {
   double *hx0 = nullptr, *hp = nullptr, *hlb = nullptr, *hub = nullptr, *hlam0 = nullptr,
          *hx = nullptr, *hlam = nullptr, *hf = nullptr;
   int *hst = nullptr, *hit = nullptr; int hostB = 0, host_shared = -1;
+  // scratch of the feasibility phase (omg_feas_batch), sized on first use
+  double* fscr = nullptr; int fscr_ctas = 0; size_t fscr_stride = 0;
 };
 
 template <typename Tp>
@@ -1811,6 +1982,7 @@ void omg_problem_destroy(omg_problem* h) {
   for (void* p : h->allocs) cudaFree(p);
   if (h->dscr) cudaFree(h->dscr);
   if (h->iscr) cudaFree(h->iscr);
+  if (h->fscr) cudaFree(h->fscr);
   if (h->counter) cudaFree(h->counter);
   if (h->trace) cudaFree(h->trace);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1927,6 +2099,60 @@ int omg_solve_batch_host(omg_problem* h, int32_t B, const double* x0, const doub
   CK(cudaMemcpyAsync(f, h->hf, b * 8, cudaMemcpyDeviceToHost, 0));
   CK(cudaMemcpyAsync(status, h->hst, b * 4, cudaMemcpyDeviceToHost, 0));
   CK(cudaMemcpyAsync(iters, h->hit, b * 4, cudaMemcpyDeviceToHost, 0));
+  CK(cudaStreamSynchronize(0));
+  return 0;
+}
+
+static int ensure_feas_scratch(omg_problem* h, int grid) {
+  const DevTab& T = h->T;
+  const size_t n = T.n, m = T.m, n_xe = n + 1 + T.n_mid;
+  const size_t stride = ((size_t)T.n_v + T.nnz_jx + 2 * m + n * n + (n + 1) * n + 2 * n + 2 * n_xe + 7) & ~(size_t)7;
+  if (grid > h->fscr_ctas) {
+    if (h->fscr) cudaFree(h->fscr);
+    h->fscr = nullptr; h->fscr_ctas = 0;
+    CK(cudaMalloc(&h->fscr, (size_t)grid * stride * sizeof(double)));
+    h->fscr_ctas = grid;
+  }
+  h->fscr_stride = stride;
+  return 0;
+}
+
+int omg_feas_batch(omg_problem* h, int32_t B, const double* x0, const double* p, const double* lbg,
+                   const double* ubg, int32_t bounds_shared, int32_t max_steps, double* x, double* viol,
+                   int32_t* steps, void* stream_) {
+  if (!h) { set_err("null handle"); return -1; }
+  if (B <= 0) return 0;
+  if (!x0 || !p || !lbg || !ubg || !x || !viol || !steps) { set_err("null buffer"); return -1; }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CK(cudaSetDevice(h->device));
+  int grid = h->n_sm * 2;
+  if (grid > B) grid = B;
+  if (ensure_feas_scratch(h, grid)) return -1;
+  FeasArgs F;
+  F.B = B; F.bounds_shared = bounds_shared; F.max_steps = max_steps;
+  F.x0 = x0; F.p = p; F.lbg = lbg; F.ubg = ubg; F.x = x; F.viol = viol; F.steps = steps;
+  F.scr = h->fscr; F.stride = h->fscr_stride;
+  OMG_LAUNCH(omg_feas_kernel, grid, 256, 0, stream, h->T, F);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int omg_feas_batch_host(omg_problem* h, int32_t B, const double* x0, const double* p, const double* lbg,
+                        const double* ubg, int32_t bounds_shared, int32_t max_steps, double* x, double* viol,
+                        int32_t* steps) {
+  if (!h) { set_err("null handle"); return -1; }
+  if (B <= 0) return 0;
+  CK(cudaSetDevice(h->device));
+  if (ensure_staging(h, B, bounds_shared ? 1 : 0)) return -1;
+  const size_t n = h->T.n, m = h->T.m, np_ = h->T.n_par, b = B;
+  CK(cudaMemcpyAsync(h->hx0, x0, b * n * 8, cudaMemcpyHostToDevice, 0));
+  CK(cudaMemcpyAsync(h->hp, p, b * np_ * 8, cudaMemcpyHostToDevice, 0));
+  CK(cudaMemcpyAsync(h->hlb, lbg, (bounds_shared ? 1 : b) * m * 8, cudaMemcpyHostToDevice, 0));
+  CK(cudaMemcpyAsync(h->hub, ubg, (bounds_shared ? 1 : b) * m * 8, cudaMemcpyHostToDevice, 0));
+  if (omg_feas_batch(h, B, h->hx0, h->hp, h->hlb, h->hub, bounds_shared, max_steps, h->hx, h->hf, h->hit, nullptr)) return -1;
+  CK(cudaMemcpyAsync(x, h->hx, b * n * 8, cudaMemcpyDeviceToHost, 0));
+  CK(cudaMemcpyAsync(viol, h->hf, b * 8, cudaMemcpyDeviceToHost, 0));
+  CK(cudaMemcpyAsync(steps, h->hit, b * 4, cudaMemcpyDeviceToHost, 0));
   CK(cudaStreamSynchronize(0));
   return 0;
 }

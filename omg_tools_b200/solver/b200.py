@@ -25,6 +25,7 @@ STATUS_STRINGS = {
     4: 'Invalid_Number_Detected', 5: 'Infeasible_Problem_Detected'}
 
 ABI_VERSION = 6
+FEAS_STEPS = 30      # option 'feas_steps': LM steps of the feasibility phase (0 = off)
 
 _i32p = C.POINTER(C.c_int32)
 _f64p = C.POINTER(C.c_double)
@@ -83,7 +84,7 @@ EXPORTS = ['omg_abi_version', 'omg_last_error', 'omg_default_options',
            'omg_solve_batch', 'omg_solve_batch_host', 'omg_shift_batch',
            'omg_get_trace', 'omg_get_info', 'omg_last_timing',
            'omg_admm_zl_update', 'omg_sample_batch', 'omg_tables_read',
-           'omg_tables_free', 'omg_integrate_rk4']
+           'omg_tables_free', 'omg_integrate_rk4', 'omg_feas_batch', 'omg_feas_batch_host']
 
 _lib = None
 
@@ -115,6 +116,8 @@ def load_library(path=None):
     lib.omg_solve_batch_host.argtypes = [vp, C.c_int32, vp, vp, vp, vp, C.c_int32,
                                          vp, vp, vp, vp, vp, vp]
     lib.omg_shift_batch.argtypes = [vp, C.c_int32, vp, C.c_int32, vp, vp, vp, vp, vp]
+    lib.omg_feas_batch.argtypes = [vp, C.c_int32, vp, vp, vp, vp, C.c_int32, C.c_int32, vp, vp, vp, vp]
+    lib.omg_feas_batch_host.argtypes = [vp, C.c_int32, vp, vp, vp, vp, C.c_int32, C.c_int32, vp, vp, vp]
     lib.omg_get_trace.argtypes = [vp, vp, C.c_int32]
     lib.omg_get_info.argtypes = [vp] + [_i32p] * 6
     lib.omg_last_timing.argtypes = [vp, C.POINTER(C.c_float), _i32p]
@@ -347,6 +350,8 @@ class B200Solver(object):
                 setattr(self._opt, key, value)
             elif key == 'retry_mu':
                 self._retry_mu = float(value)
+            elif key == 'feas_steps':
+                self._feas_steps = int(value)
             elif key in _NO_EFFECT_IPOPT_OPTIONS:
                 # printing / linear-solver selection, and warm_start_init_point: the
                 # warm-start pushes are always the 'yes' variants the reference sets
@@ -407,6 +412,10 @@ class B200Solver(object):
     def solve_batch(self, X0, P, lbg=None, ubg=None, lam_g0=None, _retry=True):
         """Host arrays in, host arrays out (H2D + solve + D2H in one C call).
 
+        Instances that end in Restoration_Failed go through the feasibility phase
+        (option ``feas_steps``, default 30 Levenberg-Marquardt steps, 0 = off) and are
+        solved once more from the point it returns; their iteration counts add up.
+
         Option ``retry_mu`` > 0 (default 0 = off): instances that did not succeed are
         solved once more from the same start with ``mu_init = retry_mu`` (e.g. 1e-3).
         A small initial barrier parameter keeps the iterates near an infeasible warm
@@ -430,6 +439,17 @@ class B200Solver(object):
             X.ctypes.data, LAM.ctypes.data, F.ctypes.data, status.ctypes.data,
             iters.ctypes.data))
         res = {'x': X, 'lam_g': LAM, 'f': F, 'status': status, 'iters': iters}
+        n_feas = getattr(self, '_feas_steps', FEAS_STEPS)
+        if _retry and n_feas > 0 and (status == 2).any():
+            # Restoration_Failed: feasibility phase from the point where the line search
+            # gave up, then one more solve from there
+            idx = np.nonzero(status == 2)[0]
+            lb_i, ub_i = (lbg, ubg) if shared else (lbg[idx], ubg[idx])
+            x1, _, _ = self.feasibility_batch(X[idx], P[idx], lb_i, ub_i, n_feas)
+            r2 = self.solve_batch(x1, P[idx], lb_i, ub_i, None, _retry=False)
+            for key in ('x', 'lam_g', 'f', 'status'):
+                res[key][idx] = r2[key]
+            res['iters'][idx] += r2['iters']
         mu_r = getattr(self, '_retry_mu', 0.)
         if _retry and mu_r > 0. and (status != 0).any():
             idx = np.nonzero(status != 0)[0]
@@ -446,6 +466,24 @@ class B200Solver(object):
                 res[key][idx[ok]] = r2[key][ok]
             res['iters'][idx] += r2['iters']
         return res
+
+    def feasibility_batch(self, X0, P, lbg=None, ubg=None, max_steps=None):
+        """Host arrays in / out: up to ``max_steps`` Levenberg-Marquardt steps on the
+        constraint violation from X0 (omg_feas_batch_host).  Returns (X, max |violation|
+        per instance, steps taken per instance)."""
+        X0 = np.ascontiguousarray(X0, dtype=np.float64).reshape(-1, self.n)
+        B = X0.shape[0]
+        P = np.ascontiguousarray(P, dtype=np.float64).reshape(B, self.n_par)
+        lbg, ubg, shared = self._bounds(lbg, ubg, B)
+        if max_steps is None:
+            max_steps = getattr(self, '_feas_steps', FEAS_STEPS)
+        X = np.empty((B, self.n))
+        viol = np.empty(B)
+        steps = np.empty(B, dtype=np.int32)
+        self._check(self.lib.omg_feas_batch_host(
+            self._handle, B, X0.ctypes.data, P.ctypes.data, lbg.ctypes.data, ubg.ctypes.data,
+            shared, int(max_steps), X.ctypes.data, viol.ctypes.data, steps.ctypes.data))
+        return X, viol, steps
 
     def solve_batch_device(self, X0, P, LBG, UBG, X, LAM, F, STATUS, ITERS,
                            lam_g0=None, stream=None):

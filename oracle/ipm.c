@@ -543,6 +543,105 @@ int oracle_solve_batch(const omg_tables* T, const omg_options* O, int B, const d
   return 0;
 }
 
+/* ---------------------------------------------------------------------------
+ * Feasibility phase (oracle/ipm_ref.py feasibility_lm; product: omg_feas_batch):
+ * Levenberg-Marquardt on v(x) = g - clip(g, lbg, ubg).  Same order of operations as
+ * the CUDA kernel: normal equations summed over the Jacobian slots in ascending
+ * order, right-looking dense Cholesky with the right-hand side carried as row n.
+ * ------------------------------------------------------------------------- */
+static double feas_residual(const omg_tables* T, const double* V, double* xq, const double* lb,
+                            const double* ub, double* v, double* vmax) {
+  eval_mids(T, V, xq);
+  double ss = 0.0, mx = 0.0;
+  for (int i = 0; i < T->m; ++i) {
+    const double g = eval_slot(&T->G, i, V, xq);
+    const double vi = (g < lb[i]) ? g - lb[i] : ((g > ub[i]) ? g - ub[i] : 0.0);
+    v[i] = vi; ss += vi * vi; if (fabs(vi) > mx) mx = fabs(vi);
+  }
+  *vmax = mx;
+  return 0.5 * ss;
+}
+
+int oracle_feas_batch(const omg_tables* T, int B, const double* x0, const double* p,
+                      const double* lbg, const double* ubg, int shared, int max_steps,
+                      double* x, double* viol, int* steps_out) {
+  const int n = T->n, m = T->m, n_xe = n + 1 + T->n_mid;
+  double* V = xalloc(sizeof(double) * T->n_v);
+  double* jx = xalloc(sizeof(double) * (T->nnz_jx > T->nnz_j ? T->nnz_jx : T->nnz_j));
+  double* jv = xalloc(sizeof(double) * T->nnz_j);
+  double* v = xalloc(sizeof(double) * m); double* vt = xalloc(sizeof(double) * m);
+  double* A = xalloc(sizeof(double) * n * n); double* L = xalloc(sizeof(double) * (n + 1) * n);
+  double* rhs = xalloc(sizeof(double) * n); double* dx = xalloc(sizeof(double) * n);
+  double* xe = xalloc(sizeof(double) * n_xe); double* xt = xalloc(sizeof(double) * n_xe);
+  int* rs = xalloc(sizeof(int) * (m + 1));       /* slot range of each row (slots are row-sorted) */
+  for (int s = 0; s < T->nnz_j; ++s) rs[T->jrow[s] + 1]++;
+  for (int i = 0; i < m; ++i) rs[i + 1] += rs[i];
+  for (int b = 0; b < B; ++b) {
+    const double* lb = lbg + (shared ? 0 : (size_t)b * m);
+    const double* ub = ubg + (shared ? 0 : (size_t)b * m);
+    eval_tape(T, p + (size_t)b * T->n_par, V);
+    for (int i = 0; i < n_xe; ++i) xe[i] = xt[i] = (i < n) ? x0[(size_t)b * n + i] : ((i == n) ? 1.0 : 0.0);
+    double vmax, lam = 1e-3;
+    double phi = feas_residual(T, V, xe, lb, ub, v, &vmax);
+    int steps = 0;
+    while (steps < max_steps && vmax > 1e-8) {
+      eval_jx(T, V, xe, jx);
+      for (int s = 0; s < T->nnz_j; ++s) jv[s] = jac_slot(T, s, V, xe, jx);
+      memset(A, 0, sizeof(double) * n * n);
+      for (int c = 0; c < n; ++c) rhs[c] = 0.0;
+      for (int s1 = 0; s1 < T->nnz_j; ++s1) {
+        const int c = T->jcol[s1], r = T->jrow[s1];
+        if (v[r] == 0.0) continue;
+        rhs[c] -= jv[s1] * v[r];
+        for (int s2 = rs[r]; s2 < rs[r + 1]; ++s2) A[(size_t)c * n + T->jcol[s2]] += jv[s1] * jv[s2];
+      }
+      int accepted = 0;
+      for (int attempt = 0; attempt < 12 && !accepted; ++attempt) {
+        for (int i = 0; i <= n; ++i)
+          for (int k = 0; k < n; ++k)
+            L[(size_t)i * n + k] = (i == n) ? rhs[k] : ((k <= i) ? A[(size_t)i * n + k] + ((k == i) ? lam : 0.0) : 0.0);
+        int ok = 1;
+        for (int j = 0; j < n && ok; ++j) {
+          const double d = L[(size_t)j * n + j];
+          if (!(d > 0.0 && d < 1e300)) { ok = 0; break; }
+          const double pv = sqrt(d), inv = 1.0 / pv;
+          L[(size_t)j * n + j] = pv;
+          for (int i = j + 1; i <= n; ++i) L[(size_t)i * n + j] *= inv;
+          for (int i = j + 1; i <= n; ++i) {
+            double* Li = L + (size_t)i * n;
+            const double lij = Li[j];
+            const int kend = (i < n) ? i : n - 1;
+            for (int k = j + 1; k <= kend; ++k) Li[k] -= lij * L[(size_t)k * n + j];
+          }
+        }
+        double pt = 0.0, vmt = 0.0;
+        if (ok) {
+          double* w = L + (size_t)n * n;
+          for (int j = n - 1; j >= 0; --j) {
+            dx[j] = w[j] / L[(size_t)j * n + j];
+            for (int k = 0; k < j; ++k) w[k] -= L[(size_t)j * n + k] * dx[j];
+          }
+          for (int i = 0; i < n; ++i) xt[i] = xe[i] + dx[i];
+          pt = feas_residual(T, V, xt, lb, ub, vt, &vmt);
+        }
+        if (ok && pt < phi) {
+          memcpy(xe, xt, sizeof(double) * n_xe); memcpy(v, vt, sizeof(double) * m);
+          phi = pt; vmax = vmt; lam = fmax(lam / 10.0, 1e-12); accepted = 1;
+        } else {
+          lam *= 10.0;
+        }
+      }
+      if (!accepted) break;
+      ++steps;
+    }
+    memcpy(x + (size_t)b * n, xe, sizeof(double) * n);
+    viol[b] = vmax; steps_out[b] = steps;
+  }
+  void* all[] = {V, jx, jv, v, vt, A, L, rhs, dx, xe, xt, rs};
+  for (unsigned k = 0; k < sizeof(all) / sizeof(all[0]); ++k) free(all[k]);
+  return 0;
+}
+
 void oracle_default_options(omg_options* o) {
   o->tol = 1e-3; o->constr_viol_tol = 1e-4; o->dual_inf_tol = 1.0; o->compl_inf_tol = 1e-4;
   o->mu_init = 0.1; o->bound_push = 1e-3; o->bound_frac = 1e-3; o->mult_bound_push = 1e-3;

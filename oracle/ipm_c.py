@@ -21,6 +21,7 @@ def _load():
         vp = C.c_void_p
         _lib.oracle_solve_batch.argtypes = [vp, vp, C.c_int] + [vp] * 4 + [C.c_int] + \
             [vp] * 6 + [C.c_int]
+        _lib.oracle_feas_batch.argtypes = [vp, C.c_int] + [vp] * 4 + [C.c_int, C.c_int] + [vp] * 3
     return _lib
 
 
@@ -30,8 +31,28 @@ def solve_batch(tb, X0, P, threads=0, options=None, lbg=None, ubg=None, lam_g0=N
     return out['x'], out['status'], out['iters']
 
 
+def feas_batch(tb, X0, P, lbg=None, ubg=None, max_steps=30):
+    """oracle_feas_batch: (X, max |violation|, steps) of the feasibility phase."""
+    from omg_tools_b200.solver.b200 import pack_tables
+    lib = _load()
+    T, keep = pack_tables(tb)
+    X0 = np.ascontiguousarray(X0, dtype=np.float64).reshape(-1, tb.n)
+    B = X0.shape[0]
+    P = np.ascontiguousarray(P, dtype=np.float64).reshape(B, tb.n_par)
+    lb = np.ascontiguousarray(tb.lbg if lbg is None else lbg, dtype=np.float64)
+    ub = np.ascontiguousarray(tb.ubg if ubg is None else ubg, dtype=np.float64)
+    X = np.empty((B, tb.n))
+    viol = np.empty(B)
+    steps = np.empty(B, dtype=np.int32)
+    lib.oracle_feas_batch(C.byref(T), B, X0.ctypes.data, P.ctypes.data, lb.ctypes.data,
+                          ub.ctypes.data, 1 if lb.ndim == 1 else 0, int(max_steps),
+                          X.ctypes.data, viol.ctypes.data, steps.ctypes.data)
+    del keep
+    return X, viol, steps
+
+
 def solve_batch_full(tb, X0, P, threads=0, options=None, lbg=None, ubg=None,
-                     lam_g0=None):
+                     lam_g0=None, _feas=True):
     # the struct definitions are data-format declarations shared with the product
     from omg_tools_b200.solver.b200 import pack_tables, _Options
     lib = _load()
@@ -40,6 +61,9 @@ def solve_batch_full(tb, X0, P, threads=0, options=None, lbg=None, ubg=None,
     lib.oracle_default_options(C.byref(opt))
     options = dict(options or {})
     retry_mu = float(options.pop('retry_mu', 0.))     # host-level retry, as B200Solver.solve_batch
+    feas_steps = int(options.pop('feas_steps', 30))   # host-level feasibility phase, likewise
+    if _feas is False:
+        feas_steps = 0
     for k, v in options.items():
         setattr(opt, k, v)
     X0 = np.ascontiguousarray(X0, dtype=np.float64).reshape(-1, tb.n)
@@ -61,6 +85,15 @@ def solve_batch_full(tb, X0, P, threads=0, options=None, lbg=None, ubg=None,
                            st.ctypes.data, it.ctypes.data, int(threads))
     del keep
     res = {'x': X, 'lam_g': LAM, 'f': F, 'status': st, 'iters': it}
+    if feas_steps > 0 and (st == 2).any():
+        idx = np.nonzero(st == 2)[0]
+        lb_i, ub_i = (lb, ub) if shared else (lb[idx], ub[idx])
+        x1, _, _ = feas_batch(tb, X[idx], P[idx], lb_i, ub_i, feas_steps)
+        r2 = solve_batch_full(tb, x1, P[idx], threads, dict(options), lb_i, ub_i, None, _feas=False)
+        for key in ('x', 'lam_g', 'f', 'status'):
+            res[key][idx] = r2[key]
+        res['iters'][idx] += r2['iters']
+        st = res['status']
     if retry_mu > 0. and (st != 0).any():
         idx = np.nonzero(st != 0)[0]
         opts2 = dict(options)

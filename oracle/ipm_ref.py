@@ -436,3 +436,66 @@ def _signed_solve(L, sign, rhs):
         w[j] /= L[j, j]
         w[:j] -= L[j, :j] * w[j]
     return w
+
+
+FEAS_STEPS = 30
+
+
+def feasibility_lm(tb, x0, p, lbg=None, ubg=None, max_steps=FEAS_STEPS):
+    """Feasibility phase the host runs on an instance that ended in Restoration_Failed
+    (stand-in for the feasibility part of IPOPT's restoration phase): Levenberg-Marquardt
+    on the violation v(x) = g - clip(g, lbg, ubg),
+        (Jv^T Jv + lam I) dx = -Jv^T v,   Jv = rows with v != 0,
+    lam from 1e-3, /10 after an accepted step, x10 (at most 12 times) after a rejected
+    one; stops when max|v| <= 1e-8.  Returns (x, max|v|, steps).  oracle/ipm.c
+    (oracle_feas_batch) and the CUDA kernel omg_feas_kernel follow this function."""
+    ev = TableEval(tb)
+    lbg = tb.lbg if lbg is None else np.asarray(lbg, dtype=float)
+    ubg = tb.ubg if ubg is None else np.asarray(ubg, dtype=float)
+    V = ev.tape(p)
+    x = np.array(x0, dtype=float)
+    n = tb.n
+
+    def residual(xx):
+        g = ev.g(xx, V)
+        v = np.where(g < lbg, g - lbg, np.where(g > ubg, g - ubg, 0.0))
+        return v, 0.5 * v.dot(v), (np.abs(v).max() if len(v) else 0.0)
+
+    v, phi, vmax = residual(x)
+    lam, steps = 1e-3, 0
+    while steps < max_steps and vmax > 1e-8:
+        J = ev.jac_dense(x, V)
+        act = v != 0.0
+        A = J[act].T.dot(J[act])
+        rhs = -J[act].T.dot(v[act])
+        accepted = False
+        for _ in range(12):
+            try:
+                Lc = np.linalg.cholesky(A + lam * np.eye(n))
+                dx = np.linalg.solve(Lc.T, np.linalg.solve(Lc, rhs))
+                vt, pt, vmt = residual(x + dx)
+                ok = pt < phi
+            except np.linalg.LinAlgError:
+                ok = False
+            if ok:
+                x, v, phi, vmax = x + dx, vt, pt, vmt
+                lam = max(lam / 10.0, 1e-12)
+                accepted = True
+                break
+            lam *= 10.0
+        if not accepted:
+            break
+        steps += 1
+    return x, vmax, steps
+
+
+def solve_with_feasibility(tb, x0, p, lbg=None, ubg=None, options=None, feas_steps=FEAS_STEPS):
+    """What B200Solver.solve_batch does per instance: solve; on Restoration_Failed run the
+    feasibility phase from the returned point and solve once more from there."""
+    res = solve(tb, x0, p, lbg, ubg, options)
+    if res.status == 2 and feas_steps > 0:
+        x1, _, _ = feasibility_lm(tb, res.x, p, lbg, ubg, feas_steps)
+        r2 = solve(tb, x1, p, lbg, ubg, options)
+        r2.iters += res.iters
+        return r2
+    return res

@@ -629,11 +629,12 @@ def test_retry_mu_option_on_the_references_quadrotor_warm_start():
     tb = pr.father.tables
     X0 = np.vstack([L['config4_x0'][2], L['config4_x0'][0]])
     P = np.vstack([L['config4_p'][2], L['config4_p'][0]])
+    pr.problem.set_options({'feas_steps': 0})       # (the feasibility phase does not rescue this one)
     plain = pr.problem.solve_batch(X0, P)
     assert plain['status'][0] != 0 and plain['status'][1] == 0
     pr.problem.set_options({'retry_mu': 1e-3})
     res = pr.problem.solve_batch(X0, P)
-    ref = ipm_c.solve_batch_full(tb, X0, P, threads=2, options={'retry_mu': 1e-3})
+    ref = ipm_c.solve_batch_full(tb, X0, P, threads=2, options={'retry_mu': 1e-3, 'feas_steps': 0})
     assert np.array_equal(res['status'], [0, 0]) and np.array_equal(ref['status'], [0, 0])
     assert np.abs(res['f'] - ref['f']).max() < 1e-4
     assert np.abs(res['x'][1] - plain['x'][1]).max() == 0.0        # untouched instance

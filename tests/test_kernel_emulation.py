@@ -185,6 +185,50 @@ def test_xl_kernel_trailer_free_end_time(emu):
     assert np.abs(res['x'] - ref['x']).max() < 1e-6 and np.abs(res['f'] - ref['f']).max() < 1e-9
 
 
+def test_feasibility_kernel_and_the_fallback_after_restoration_failed(emu):
+    """omg_feas_kernel (Levenberg-Marquardt on the constraint violation; one block per
+    instance, normal equations through the CSC view of the Jacobian, dense Cholesky with
+    the right-hand side as an extra row) against oracle_feas_batch, on standard tables
+    (config 5, two cold starts whose line search fails, and one that succeeds) and on tables
+    with intermediates (the Dubins example with a free end time from the reference's
+    zero-speed guess) -- and B200Solver.solve_batch's default path around it: solve,
+    feasibility phase for the Restoration_Failed instances, one more solve."""
+    pr = sc.config5()
+    tb = pr.father.tables
+    X0, P = sc.instance_data(pr, 12, jitter=0.3, seed=5)
+    X0, P = X0[[5, 10, 0]], P[[5, 10, 0]]
+    xg, vg, kg = pr.problem.feasibility_batch(X0, P)
+    xc, vc, kc = ipm_c.feas_batch(tb, X0, P)
+    assert np.array_equal(kg, kc) and (kc > 0).all()
+    assert np.abs(xg - xc).max() < 1e-9 and np.abs(vg - vc).max() < 1e-9
+    x5, v5, k5 = pr.problem.feasibility_batch(X0, P, max_steps=5)      # the step limit
+    assert (k5 == 5).all() and (v5 >= vg).all()
+    plain = ipm_c.solve_batch_full(tb, X0, P, threads=3, options={'feas_steps': 0})
+    assert list(plain['status']) == [2, 2, 0]
+    res = pr.problem.solve_batch(X0, P)
+    ref = ipm_c.solve_batch_full(tb, X0, P, threads=3)
+    # (these two are local infeasibilities of the separation constraints: the second solve
+    # wanders for hundreds of iterations and fails again, no iteration-exact comparison)
+    assert np.array_equal(res['status'], ref['status'])
+    assert (res['iters'][:2] > plain['iters'][:2]).all() and res['iters'][2] == plain['iters'][2] == ref['iters'][2]
+    assert np.abs(res['x'] - ref['x'])[2].max() < 1e-6
+    pr.problem.set_options({'feas_steps': 0})                           # switched off
+    off = pr.problem.solve_batch(X0, P)
+    assert np.array_equal(off['status'], plain['status']) and (off['iters'] < res['iters'])[:2].all()
+
+    pr = sc.config_dubins_freeT()
+    tb, f = pr.father.tables, pr.father
+    assert tb.n_mid > 0
+    X0, P = sc.instance_data(pr, 2, jitter=0.05, seed=3)
+    res = pr.problem.solve_batch(X0, P)
+    ref = ipm_c.solve_batch_full(tb, X0, P, threads=2)
+    plain = ipm_c.solve_batch_full(tb, X0, P, threads=2, options={'feas_steps': 0})
+    assert (plain['status'] == 2).all()
+    assert (res['status'] == 0).all() and np.array_equal(res['iters'], ref['iters'])
+    assert np.abs(res['x'] - ref['x']).max() < 1e-4 and np.abs(res['f'] - ref['f']).max() < 1e-7
+    assert (res['f'] > 7.0).all() and (res['f'] < 8.0).all()           # the end time
+
+
 def test_edge_cases_and_dropin(emu):
     """Empty batch, per-instance bounds, NaN parameters, max_iter, warm start with
     multipliers, Problem.solve()."""

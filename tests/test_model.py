@@ -317,9 +317,10 @@ def test_freeT_with_safety_distance_and_dubins_freeT():
     basics/poly.py rel_time) -- the MPC loop converges at every step, arrives, and keeps the
     obstacle at more than its radius; and examples/p2p_dubins.py as written (substitution,
     freeT): the motion time multiplies the intermediates.  From a rolling speed guess the
-    oracle converges to a motion time between the straight-line bound and 10 s (from the
+    oracle converges to a motion time between the straight-line bound and 10 s; from the
     reference's zero-speed guess the Jacobian of the position rows is rank deficient and
-    the line search gives up -- IPOPT's restoration phase)."""
+    the line search gives up -- IPOPT's restoration phase; here the host-level feasibility
+    phase followed by a second solve, DESIGN.md section 2."""
     from oracle import ipm_c
     if not ipm_c.available():
         pytest.skip('C oracle not built')
@@ -343,8 +344,11 @@ def test_freeT_with_safety_distance_and_dubins_freeT():
     pr = sc.config_dubins_freeT(build_solver=False)
     tb, f = pr.father.tables, pr.father
     assert tb.n_mid > 0 and tb.nnz_wx > 0
-    r = ipm_c.solve_batch_full(tb, f.get_variables().cat[None], f.set_parameters(0.).cat[None], threads=1)
-    assert r['status'][0] != 0                     # the reference's zero-speed guess
+    x0, p0 = f.get_variables().cat[None], f.set_parameters(0.).cat[None]
+    r = ipm_c.solve_batch_full(tb, x0, p0, threads=1, options={'feas_steps': 0})
+    assert r['status'][0] == 2                     # the reference's zero-speed guess, line search alone
+    r = ipm_c.solve_batch_full(tb, x0, p0, threads=1)
+    assert r['status'][0] == 0 and 7. < r['f'][0] < 8.     # with the feasibility phase
     # vehicle option init_v_til: rolling initial guess; the example's whole MPC loop
     pr = sc.config_dubins_freeT(build_solver=False, init_v_til=0.3)
     pr.problem = _OracleSolver(pr.father.tables)

@@ -261,3 +261,43 @@ def test_retry_mu_rescues_the_references_quadrotor_warm_start():
     # the reference's loop around the solver with retry_mu (make_loop_golden.py)
     assert (L['config4_retry_status'] == 0).all() and len(L['config4_retry_status']) == 13
     assert np.abs(L['config4_retry_state'][:3] - [3., 2., 0.5]).max() < 1e-2
+
+
+def test_feasibility_phase_rescues_the_dubins_example_from_the_references_own_guess():
+    """examples/p2p_dubins.py as written (free end time, the reference's zero-speed initial
+    guess): the position rows do not depend on the heading at v~ = 0, the filter line search
+    gives up after a few iterations (Restoration_Failed) -- IPOPT would enter its restoration
+    phase here.  The host-level feasibility phase (Levenberg-Marquardt on the constraint
+    violation from the point of failure, oracle/ipm_ref.py feasibility_lm; product:
+    omg_feas_batch) followed by one more solve converges.  numpy twin == C port."""
+    from oracle import ipm_c
+    from oracle.ipm_ref import feasibility_lm, solve_with_feasibility
+    if not ipm_c.available():
+        pytest.skip('C oracle not built')
+    pr = sc.config_dubins_freeT(build_solver=False)
+    f, tb = pr.father, pr.father.tables
+    x0, p = f.get_variables().cat, f.set_parameters(0.).cat
+    plain = ipm_c.solve_batch_full(tb, x0[None], p[None], options={'feas_steps': 0})
+    assert plain['status'][0] == 2 and plain['iters'][0] < 20
+    # the phase itself: monotone decrease of the violation, same point from both restatements
+    ev = TableEval(tb)
+    g0 = ev.g(plain['x'][0], ev.tape(p))
+    v0 = np.abs(g0 - np.clip(g0, tb.lbg, tb.ubg)).max()
+    xn, vn, kn = feasibility_lm(tb, plain['x'][0], p)
+    xc, vc, kc = ipm_c.feas_batch(tb, plain['x'], p[None])
+    assert kn == kc[0] and 0 < kn <= 30
+    assert vn < 1e-2 * v0 and abs(vn - vc[0]) < 1e-9
+    assert np.abs(xn - xc[0]).max() < 1e-8
+    g1 = ev.g(xc[0], ev.tape(p))
+    assert abs(np.abs(g1 - np.clip(g1, tb.lbg, tb.ubg)).max() - vc[0]) < 1e-12
+    # solve -> feasibility phase -> solve (what B200Solver.solve_batch does by default)
+    res = ipm_c.solve_batch_full(tb, x0[None], p[None])
+    rn = solve_with_feasibility(tb, x0, p)
+    assert res['status'][0] == 0 == rn.status and res['iters'][0] == rn.iters
+    assert np.abs(res['x'][0] - rn.x).max() < 1e-6
+    assert 7.0 < res['f'][0] < 8.0          # end time 7.46 s (8.47 s from the rolling guess)
+    g = ev.g(res['x'][0], ev.tape(p))
+    assert (g <= tb.ubg + 1e-4).all() and (g >= tb.lbg - 1e-4).all()
+    # from the optimum (violation below constr_viol_tol) the phase has little left to do
+    _, v2, k2 = ipm_c.feas_batch(tb, res['x'], p[None])
+    assert v2[0] <= 1e-8 and k2[0] <= 3

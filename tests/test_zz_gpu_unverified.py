@@ -116,3 +116,36 @@ def test_trailer_matches_oracle():
     assert res['status'][0] == 0 == ref['status'][0]
     assert abs(int(res['iters'][0]) - int(ref['iters'][0])) <= 2
     assert np.abs(res['x'] - ref['x'])[:, :36].max() < 1e-3
+
+
+def test_feasibility_kernel_matches_oracle():
+    """omg_feas_kernel (written after the GPU budget was spent; emulation-verified in
+    tests/test_kernel_emulation.py) vs oracle_feas_batch: standard tables (config 5) and
+    tables with intermediates (Dubins, free end time), 16 jittered cold starts each."""
+    for name, seed in (('config5', 5), ('config_dubins_freeT', 3)):
+        pr = getattr(sc, name)()
+        tb = pr.father.tables
+        X0, P = sc.instance_data(pr, 16, jitter=0.2, seed=seed)
+        xg, vg, kg = pr.problem.feasibility_batch(X0, P)
+        xc, vc, kc = ipm_c.feas_batch(tb, X0, P)
+        assert np.array_equal(kg, kc), name
+        # FMA contraction on the GPU: agreement to rounding amplified by 30 LM steps
+        assert np.abs(vg - vc).max() < 1e-6 * max(1., np.abs(vc).max()), name
+        assert np.abs(xg - xc).max() < 1e-5, name
+
+
+def test_dubins_example_as_written_converges_through_the_feasibility_phase():
+    """examples/p2p_dubins.py from the reference's zero-speed guess: Restoration_Failed
+    after a few iterations, feasibility phase, second solve -> end time 7.46 s, through
+    B200Solver.solve_batch and through the reference-facing Problem.solve()."""
+    pr = sc.config_dubins_freeT()
+    tb, f = pr.father.tables, pr.father
+    X0, P = f.get_variables().cat[None], f.set_parameters(0.).cat[None]
+    res = pr.problem.solve_batch(X0, P)
+    ref = ipm_c.solve_batch_full(tb, X0, P, threads=1)
+    assert res['status'][0] == 0 == ref['status'][0]
+    assert abs(int(res['iters'][0]) - int(ref['iters'][0])) <= 2
+    assert abs(res['f'][0] - ref['f'][0]) < 1e-4 and 7.0 < res['f'][0] < 8.0
+    pr.initialize(0.)
+    pr.solve(0., 0.5)
+    assert pr.problem.stats()['return_status'] == 'Solve_Succeeded'
