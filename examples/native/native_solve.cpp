@@ -9,6 +9,7 @@
 //   ./native_solve problem.omgtbl x0.f64 p.f64 B x_out.f64
 //
 // x0.f64 / p.f64: raw little-endian doubles, B rows of n / n_par values.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -40,6 +41,30 @@ int main(int argc, char** argv) {
   if (omg_solve_batch_host(h, B, x0.data(), p.data(), tb->lbg, tb->ubg, 1, nullptr, x.data(),
                            lam.data(), f.data(), status.data(), iters.data()) != 0) {
     fprintf(stderr, "solve: %s\n", omg_last_error()); return 1;
+  }
+  // instances whose line search gave up: feasibility phase from where they stopped, one
+  // more solve from there (what B200Solver.solve_batch does; IPOPT's restoration phase in
+  // the reference's runtime happens inside the same nlpsol call, Point2Point.cpp:219)
+  std::vector<int> bad;
+  for (int b = 0; b < B; ++b) if (status[b] == OMG_RESTORATION_FAILED) bad.push_back(b);
+  if (!bad.empty()) {
+    const size_t nb = bad.size(), n = tb->n, np_ = tb->n_par, m = tb->m;
+    std::vector<double> xs(nb * n), ps(nb * np_), x1(nb * n), viol(nb), x2(nb * n), lam2(nb * m), f2(nb);
+    std::vector<int32_t> steps(nb), st2(nb), it2(nb);
+    for (size_t k = 0; k < nb; ++k) {
+      std::copy(x.begin() + bad[k] * n, x.begin() + (bad[k] + 1) * n, xs.begin() + k * n);
+      std::copy(p.begin() + bad[k] * np_, p.begin() + (bad[k] + 1) * np_, ps.begin() + k * np_);
+    }
+    if (omg_feas_batch_host(h, (int)nb, xs.data(), ps.data(), tb->lbg, tb->ubg, 1, 30, x1.data(), viol.data(),
+                            steps.data()) != 0 ||
+        omg_solve_batch_host(h, (int)nb, x1.data(), ps.data(), tb->lbg, tb->ubg, 1, nullptr, x2.data(),
+                             lam2.data(), f2.data(), st2.data(), it2.data()) != 0) {
+      fprintf(stderr, "feasibility phase: %s\n", omg_last_error()); return 1;
+    }
+    for (size_t k = 0; k < nb; ++k) {
+      std::copy(x2.begin() + k * n, x2.begin() + (k + 1) * n, x.begin() + bad[k] * n);
+      status[bad[k]] = st2[k]; iters[bad[k]] += it2[k]; f[bad[k]] = f2[k];
+    }
   }
   for (int b = 0; b < B; ++b) printf("instance %d status %d iters %d f %.12g\n", b, status[b], iters[b], f[b]);
   FILE* fo = fopen(argv[5], "wb");

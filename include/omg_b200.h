@@ -211,7 +211,9 @@ int omg_feas_batch_host(omg_problem* h, int32_t B,
 /* Receding-horizon warm start: x[b, off:off+len*ncol] <- T (len x len) applied
  * to each of the ncol columns, for n_blocks spline variables (DEVICE x,
  * in place).  offs/lens/ncols: HOST int arrays [n_blocks]; T: HOST array of the
- * n_blocks row-major matrices, concatenated. */
+ * n_blocks row-major matrices, concatenated.  Asynchronous on `stream`; the block
+ * descriptor is uploaded on the first call and whenever it changes (the host arrays are
+ * copied before the call returns). */
 int omg_shift_batch(omg_problem* h, int32_t B, double* x,
                     int32_t n_blocks, const int32_t* offs, const int32_t* lens,
                     const int32_t* ncols, const double* T, void* stream);
@@ -233,7 +235,9 @@ int omg_last_timing(omg_problem* h, float* kernel_ms, int32_t* launches);
  * spline_extra.py:406-410; C++ twin Vehicle.cpp:112-190): for each of n_blocks
  * spline variables (offset, basis length, columns) apply the HOST matrix
  * S_blk [nsamp x len] (precomputed basis / derivative rows) to every column:
- * out[b] = concat_blk( [col][sample] ), DEVICE x [B][n] and out [B][sum nsamp*ncols]. */
+ * out[b] = concat_blk( [col][sample] ), DEVICE x [B][n] and out [B][sum nsamp*ncols].
+ * Asynchronous on `stream`; descriptor and S are uploaded on the first call of the host
+ * thread and whenever they change (copied before the call returns). */
 int omg_sample_batch(int32_t B, int32_t n, const double* x, int32_t n_blocks,
                      const int32_t* offs, const int32_t* lens, const int32_t* ncols,
                      const int32_t* nsamp, const double* S, double* out, void* stream);

@@ -1563,6 +1563,22 @@ static void set_err(const std::string& s) { g_err = s; }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
   set_err(std::string(#call) + ": " + cudaGetErrorString(e_)); return -1; } } while (0)
 
+// Block descriptors of the shift / sampling calls live on the device between calls: a
+// receding-horizon loop passes the same blocks every step, so only the first call uploads
+// (and only a changed descriptor frees anything) -- the calls stay asynchronous on `stream`.
+struct DescCache {
+  int device = -1;
+  std::vector<int> ikey; std::vector<double> dkey;
+  int* d_i = nullptr; double* d_d = nullptr;
+};
+
+static void free_desc(DescCache* c) {
+  if (!c) return;
+  if (c->d_i) cudaFree(c->d_i);
+  if (c->d_d) cudaFree(c->d_d);
+  delete c;
+}
+
 struct omg_problem {
   int device = 0;
   DevTab T;
@@ -1583,6 +1599,7 @@ struct omg_problem {
   int *hst = nullptr, *hit = nullptr; int hostB = 0, host_shared = -1;
   // scratch of the feasibility phase (omg_feas_batch), sized on first use
   double* fscr = nullptr; int fscr_ctas = 0; size_t fscr_stride = 0;
+  DescCache* shift_desc = nullptr;   // device copy of the last omg_shift_batch block descriptor
 };
 
 template <typename Tp>
@@ -1983,6 +2000,7 @@ void omg_problem_destroy(omg_problem* h) {
   if (h->dscr) cudaFree(h->dscr);
   if (h->iscr) cudaFree(h->iscr);
   if (h->fscr) cudaFree(h->fscr);
+  free_desc(h->shift_desc);
   if (h->counter) cudaFree(h->counter);
   if (h->trace) cudaFree(h->trace);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -2157,28 +2175,40 @@ int omg_feas_batch_host(omg_problem* h, int32_t B, const double* x0, const doubl
   return 0;
 }
 
+static int desc_upload(DescCache& c, int device, const std::vector<int>& iv, const double* dv, size_t nd,
+                       cudaStream_t stream) {
+  if (c.device == device && c.d_i && c.ikey == iv && c.dkey.size() == nd &&
+      memcmp(c.dkey.data(), dv, nd * sizeof(double)) == 0) return 0;
+  if (c.d_i) cudaFree(c.d_i);
+  if (c.d_d) cudaFree(c.d_d);
+  c.d_i = nullptr; c.d_d = nullptr; c.device = -1;
+  c.ikey = iv; c.dkey.assign(dv, dv + nd);
+  CK(cudaMalloc(&c.d_i, sizeof(int) * (iv.size() ? iv.size() : 1)));
+  CK(cudaMalloc(&c.d_d, sizeof(double) * (nd ? nd : 1)));
+  CK(cudaMemcpyAsync(c.d_i, c.ikey.data(), sizeof(int) * iv.size(), cudaMemcpyHostToDevice, stream));
+  CK(cudaMemcpyAsync(c.d_d, c.dkey.data(), sizeof(double) * nd, cudaMemcpyHostToDevice, stream));
+  c.device = device;
+  return 0;
+}
+
 int omg_shift_batch(omg_problem* h, int32_t B, double* x, int32_t n_blocks, const int32_t* offs,
                     const int32_t* lens, const int32_t* ncols, const double* Tm, void* stream_) {
   if (!h || !x || !offs || !lens || !ncols || !Tm) { set_err("null argument"); return -1; }
   if (B <= 0 || n_blocks <= 0) return 0;
   cudaStream_t stream = (cudaStream_t)stream_;
   CK(cudaSetDevice(h->device));
-  std::vector<int> toffs(n_blocks);
+  std::vector<int> iv(4 * (size_t)n_blocks);
   int tot = 0;
-  for (int b = 0; b < n_blocks; ++b) { toffs[b] = tot; tot += lens[b] * lens[b]; }
-  int *d_i = nullptr; double* d_T = nullptr;
-  CK(cudaMalloc(&d_i, sizeof(int) * 4 * n_blocks));
-  CK(cudaMalloc(&d_T, sizeof(double) * tot));
-  CK(cudaMemcpyAsync(d_i, offs, sizeof(int) * n_blocks, cudaMemcpyHostToDevice, stream));
-  CK(cudaMemcpyAsync(d_i + n_blocks, lens, sizeof(int) * n_blocks, cudaMemcpyHostToDevice, stream));
-  CK(cudaMemcpyAsync(d_i + 2 * n_blocks, ncols, sizeof(int) * n_blocks, cudaMemcpyHostToDevice, stream));
-  CK(cudaMemcpyAsync(d_i + 3 * n_blocks, toffs.data(), sizeof(int) * n_blocks, cudaMemcpyHostToDevice, stream));
-  CK(cudaMemcpyAsync(d_T, Tm, sizeof(double) * tot, cudaMemcpyHostToDevice, stream));
-  OMG_LAUNCH(omg_shift_kernel, B, 128, sizeof(double) * h->T.n, stream, x, B, h->T.n, n_blocks, d_i, d_i + n_blocks,
-                                                               d_i + 2 * n_blocks, d_i + 3 * n_blocks, d_T);
+  for (int b = 0; b < n_blocks; ++b) {
+    iv[b] = offs[b]; iv[n_blocks + b] = lens[b]; iv[2 * n_blocks + b] = ncols[b]; iv[3 * n_blocks + b] = tot;
+    tot += lens[b] * lens[b];
+  }
+  if (!h->shift_desc) h->shift_desc = new DescCache();
+  DescCache& c = *h->shift_desc;
+  if (desc_upload(c, h->device, iv, Tm, (size_t)tot, stream)) return -1;
+  OMG_LAUNCH(omg_shift_kernel, B, 128, sizeof(double) * h->T.n, stream, x, B, h->T.n, n_blocks, c.d_i, c.d_i + n_blocks,
+                                                               c.d_i + 2 * n_blocks, c.d_i + 3 * n_blocks, c.d_d);
   CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(stream));
-  cudaFree(d_i); cudaFree(d_T);
   return 0;
 }
 
@@ -2188,22 +2218,22 @@ int omg_sample_batch(int32_t B, int32_t n, const double* x, int32_t n_blocks, co
   if (!x || !offs || !lens || !ncols || !nsamp || !Sm || !out) { set_err("null argument"); return -1; }
   if (B <= 0 || n_blocks <= 0) return 0;
   cudaStream_t stream = (cudaStream_t)stream_;
-  std::vector<int> soffs(n_blocks), ooffs(n_blocks);
+  std::vector<int> iv(6 * (size_t)n_blocks);
   int stot = 0, otot = 0;
-  for (int b = 0; b < n_blocks; ++b) { soffs[b] = stot; stot += nsamp[b] * lens[b]; ooffs[b] = otot; otot += nsamp[b] * ncols[b]; }
-  int* d_i = nullptr; double* d_S = nullptr;
-  CK(cudaMalloc(&d_i, sizeof(int) * 6 * n_blocks));
-  CK(cudaMalloc(&d_S, sizeof(double) * stot));
-  const int32_t* hosts[6] = {offs, lens, ncols, nsamp, soffs.data(), ooffs.data()};
-  for (int k = 0; k < 6; ++k)
-    CK(cudaMemcpyAsync(d_i + k * n_blocks, hosts[k], sizeof(int) * n_blocks, cudaMemcpyHostToDevice, stream));
-  CK(cudaMemcpyAsync(d_S, Sm, sizeof(double) * stot, cudaMemcpyHostToDevice, stream));
+  for (int b = 0; b < n_blocks; ++b) {
+    iv[b] = offs[b]; iv[n_blocks + b] = lens[b]; iv[2 * n_blocks + b] = ncols[b]; iv[3 * n_blocks + b] = nsamp[b];
+    iv[4 * n_blocks + b] = stot; stot += nsamp[b] * lens[b];
+    iv[5 * n_blocks + b] = otot; otot += nsamp[b] * ncols[b];
+  }
+  int device = 0;
+  CK(cudaGetDevice(&device));
+  static thread_local DescCache cache;         // (no handle in this call: one descriptor per host thread)
+  if (desc_upload(cache, device, iv, Sm, (size_t)stot, stream)) return -1;
+  const int* d_i = cache.d_i;
   OMG_LAUNCH(omg_sample_kernel, B, 128, sizeof(double) * n, stream, x, B, n, n_blocks, d_i, d_i + n_blocks, d_i + 2 * n_blocks,
                                                            d_i + 3 * n_blocks, d_i + 4 * n_blocks, d_i + 5 * n_blocks,
-                                                           d_S, out, otot);
+                                                           cache.d_d, out, otot);
   CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(stream));
-  cudaFree(d_i); cudaFree(d_S);
   return 0;
 }
 

@@ -229,6 +229,31 @@ def test_feasibility_kernel_and_the_fallback_after_restoration_failed(emu):
     assert (res['f'] > 7.0).all() and (res['f'] < 8.0).all()           # the end time
 
 
+def test_native_cpp_caller_with_the_feasibility_fallback(emu, tmp_path):
+    """examples/native/native_solve.cpp (C++ against the C ABI only, table file in, no
+    Python) linked to the emulation library: the Dubins example with a free end time from
+    the zero-speed guess -- omg_solve_batch_host, omg_feas_batch_host for the
+    Restoration_Failed instances, omg_solve_batch_host again -- equals the oracle."""
+    pr = sc.config_dubins_freeT(build_solver=False)
+    tb = pr.father.tables
+    exe = str(tmp_path / 'native_emu')
+    subprocess.check_call(['g++', '-O2', '-I', os.path.join(ROOT, 'include'),
+                           os.path.join(ROOT, 'examples', 'native', 'native_solve.cpp'), '-o', exe,
+                           EMU_LIB, '-Wl,-rpath,' + os.path.dirname(EMU_LIB)])
+    X0, P = sc.instance_data(pr, 2, jitter=0.05, seed=3)
+    b200.save_tables(tb, str(tmp_path / 'p.omgtbl'))
+    X0.tofile(str(tmp_path / 'x0.f64'))
+    P.tofile(str(tmp_path / 'p.f64'))
+    out = subprocess.check_output([exe, str(tmp_path / 'p.omgtbl'), str(tmp_path / 'x0.f64'),
+                                   str(tmp_path / 'p.f64'), '2', str(tmp_path / 'x.f64')])
+    ref = ipm_c.solve_batch_full(tb, X0, P, threads=2)
+    x = np.fromfile(str(tmp_path / 'x.f64')).reshape(2, tb.n)
+    assert (ref['status'] == 0).all() and np.abs(x - ref['x']).max() < 1e-6
+    for b, line in enumerate(out.decode().strip().splitlines()):
+        tok = line.split()
+        assert int(tok[3]) == 0 and int(tok[5]) == ref['iters'][b]
+
+
 def test_edge_cases_and_dropin(emu):
     """Empty batch, per-instance bounds, NaN parameters, max_iter, warm start with
     multipliers, Problem.solve()."""

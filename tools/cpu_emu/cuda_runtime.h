@@ -75,6 +75,7 @@ static inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n)
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
   // B200 (sm_100a): 227 KB opt-in shared memory per block, 228 KB per SM -- the layout
   // decisions of omg_problem_create (kernel variant, blocks per SM) are the GPU's
