@@ -1,6 +1,7 @@
 #!/bin/bash
 # First GPU call of the next round: the kernel paths that so far ran only in the CPU
-# emulation (ABI v6 gathers, new vehicles, RendezVous), then the verified suite and the
+# emulation (ABI v6 gathers, new vehicles, RendezVous, the feasibility-phase kernel
+# omg_feas_kernel), then the verified suite and the
 # default bench.  Writes into gpurun_out/.
 #   gpurun --timeout 1500 -- 'bash tools/gpu_first_call_round2.sh'
 set -x
