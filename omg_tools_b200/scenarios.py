@@ -365,7 +365,9 @@ def config_trailer(options=None, build_solver=True, init_v_til=0.):
 def config_warehouse(options=None, build_solver=True):
     """examples/p2p_holonomic_warehouse.py: Holonomic with Euclidean speed / acceleration limits
     and a safety distance, six square racks and two moving circles in a 7 x 4.5 room, free
-    end time (n = 423)."""
+    end time (n = 395, m = 1628).  The cold start from the straight line through the racks is
+    hard: the oracle ends in Restoration_Failed after ~700 iterations (feasibility phase
+    included) and converges with the solver option retry_mu = 1e-3 (T = 23.5 s)."""
     vehicle = Holonomic(options={'syslimit': 'norm_2', 'safety_distance': 0.1})
     vehicle.define_knots(knot_intervals=10)
     vehicle.set_initial_conditions([0., 0.])
@@ -405,6 +407,32 @@ def config_revolving_door_diffdrive(options=None, build_solver=True, init_v_til=
              'angular_velocity': omega}, shape=beam2, simulation={},
             options={'horizon_time': horizon_time}))
     opts = {'horizon_time': horizon_time, 'hard_term_con': True}
+    opts.update(options or {})
+    return _p2p(vehicle, environment, opts, build_solver)
+
+
+def config_revolving_door_quadrotor(options=None, build_solver=True):
+    """examples/revolving_door_quadrotor.py: the planar Quadrotor (radius 0.1, u1max 10) through
+    the revolving door -- two static and two rotating beams (omega = 0.45 rev / horizon),
+    horizon 10 s."""
+    from . import Quadrotor, Beam
+    vehicle = Quadrotor(radius=0.1, bounds={'u1max': 10, 'u2max': 8})
+    vehicle.define_knots(knot_intervals=10)
+    vehicle.set_initial_conditions([0., -2.0])
+    vehicle.set_terminal_conditions([-0.5, 2.0])
+    environment = Environment(room={'shape': Square(5.)})
+    beam1 = Beam(width=2.2, height=0.2)
+    environment.add_obstacle(Obstacle({'position': [-2., 0.]}, shape=beam1))
+    environment.add_obstacle(Obstacle({'position': [2., 0.]}, shape=beam1))
+    beam2 = Beam(width=1.4, height=0.2)
+    horizon_time = 10.
+    omega = 0.45 * 1. * (2 * np.pi / horizon_time)
+    for orient in (0. + np.pi / 4, 0.5 * np.pi + np.pi / 4):
+        environment.add_obstacle(Obstacle(
+            {'position': [0., 0.], 'velocity': [0., 0.], 'orientation': orient,
+             'angular_velocity': omega}, shape=beam2, simulation={},
+            options={'horizon_time': horizon_time}))
+    opts = {'horizon_time': horizon_time}
     opts.update(options or {})
     return _p2p(vehicle, environment, opts, build_solver)
 

@@ -463,6 +463,25 @@ def build_reference(name):
                  'angular_velocity': omega}, shape=beam2, simulation={},
                 options={'horizon_time': horizon_time}))
         options = {'horizon_time': horizon_time, 'hard_term_con': True}
+    elif name == 'config_revolving_door_quadrotor':
+        q2 = ref_import('vehicles.quadrotor')
+        vehicle = q2.Quadrotor(radius=0.1, bounds={'u1max': 10, 'u2max': 8})
+        vehicle.define_knots(knot_intervals=10)
+        vehicle.set_initial_conditions([0., -2.0])
+        vehicle.set_terminal_conditions([-0.5, 2.0])
+        environment = env.Environment(room={'shape': shp.Square(5.)})
+        beam1 = shp.Beam(width=2.2, height=0.2)
+        environment.add_obstacle(obs.Obstacle({'position': [-2., 0.]}, shape=beam1))
+        environment.add_obstacle(obs.Obstacle({'position': [2., 0.]}, shape=beam1))
+        beam2 = shp.Beam(width=1.4, height=0.2)
+        horizon_time = 10.
+        omega = 0.45 * 1. * (2 * np.pi / horizon_time)
+        for orient in (0. + np.pi / 4, 0.5 * np.pi + np.pi / 4):
+            environment.add_obstacle(obs.Obstacle(
+                {'position': [0., 0.], 'velocity': [0., 0.], 'orientation': orient,
+                 'angular_velocity': omega}, shape=beam2, simulation={},
+                options={'horizon_time': horizon_time}))
+        options = {'horizon_time': horizon_time}
     elif name == 'config_free_end':
         vehicle = hol.Holonomic()
         vehicle.set_options({'safety_distance': 0.1})
@@ -667,7 +686,7 @@ EXT_NAMES = ('config_dubins_plain', 'config_dubins_rect', 'config_dubins_exact',
              'config_quadrotor3d_simple', 'config_formation_central', 'config_interveh', 'config_free_end',
              'config_freeT', 'config_freeT_moving', 'config_freeT_safety', 'config_dubins_freeT',
              'config_trailer', 'config_formation_central_example', 'config_warehouse',
-             'config_revolving_door_diffdrive')
+             'config_revolving_door_diffdrive', 'config_revolving_door_quadrotor')
 
 
 def main(ext=False):

@@ -853,7 +853,8 @@ EXT_GOLDEN = ('config_dubins_plain', 'config_dubins_rect', 'config_dubins_exact'
               'config_quadrotor3d_simple', 'config_formation_central', 'config_interveh',
               'config_free_end', 'config_freeT', 'config_freeT_moving', 'config_freeT_safety',
               'config_dubins_freeT', 'config_trailer', 'config_formation_central_example',
-              'config_warehouse', 'config_revolving_door_diffdrive')
+              'config_warehouse', 'config_revolving_door_diffdrive',
+              'config_revolving_door_quadrotor')
 
 
 _PROBLEMS = {}
