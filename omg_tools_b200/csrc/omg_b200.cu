@@ -37,7 +37,7 @@
 // (tools/cpu_emu: its cuda_runtime.h stand-in defines OMG_CPU_EMU and these two macros;
 // test infrastructure for a GPU-less container, never loaded by the product).
 #ifndef OMG_CPU_EMU
-#define OMG_DYN_SHARED(name) extern __shared__ double name[]
+#define OMG_DYN_SHARED(name) extern __shared__ __align__(16) double name[]
 #define OMG_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif
 
@@ -1197,6 +1197,14 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
 __global__ void __launch_bounds__(512, 1)
 omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S) { ipm_body<false>(T, O, A, S); }
 
+// sparse variant (omg_sp.cuh): L D L^T on the minimum-degree structure, thread streams, 128 or
+// 256 threads per instance, as many blocks per SM as shared memory allows (config 2: 3)
+#include "omg_sp.cuh"
+__global__ void __launch_bounds__(256, 2)
+omg_ipm_kernel_sp(const DevTab T, const SpTab P, const omg_options O, const Batch A, const SpSmem S) {
+  ipm_body_sp(T, P, O, A, S);
+}
+
 __global__ void __launch_bounds__(256, 2)
 omg_ipm_kernel_2cta(const DevTab T, const omg_options O, const Batch A, const Smem S) { ipm_body<false>(T, O, A, S); }
 
@@ -1600,6 +1608,12 @@ struct omg_problem {
   // scratch of the feasibility phase (omg_feas_batch), sized on first use
   double* fscr = nullptr; int fscr_ctas = 0; size_t fscr_stride = 0;
   DescCache* shift_desc = nullptr;   // device copy of the last omg_shift_batch block descriptor
+  // sparse kernel variant (omg_sp.cuh / omg_sp_host.cuh)
+  bool sp = false; SpTab P; SpSmem SS; size_t sp_smem_bytes = 0; int sp_ctas = 0, sp_dscr_stride = 0;
+  std::string sp_info;
+  // launch configuration of the envelope kernels (kept: inertia_mode = 1 is tied to the
+  // envelope's elimination order and always runs there)
+  int env_nt = 0, env_ctas = 0; size_t env_smem_bytes = 0;
 };
 
 template <typename Tp>
@@ -1611,6 +1625,8 @@ static const Tp* upload(omg_problem* h, const Tp* src, size_t count, bool* ok) {
   if (src && cudaMemcpy(d, src, count * sizeof(Tp), cudaMemcpyHostToDevice) != cudaSuccess) *ok = false;
   return (const Tp*)d;
 }
+
+#include "omg_sp_host.cuh"
 
 // pack a term list into 32-byte records; aux = lrow (W) / slot offset within the row (J)
 static const PTerm* upload_terms(omg_problem* h, const omg_termlist& L, int n_one,
@@ -1984,6 +2000,18 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
     h->ctas_per_sm = occ > 0 ? occ : 1;
     h->dscr_stride = goff + 8;
     h->iscr_stride = 2 * m + 8;
+    {  // sparse variant: preferred whenever the problem is inside its coverage
+      const char* e = getenv("OMG_B200_KERNEL");   // "envelope": force the envelope kernels
+      std::string why;
+      h->env_nt = h->nt; h->env_ctas = h->ctas_per_sm; h->env_smem_bytes = h->smem_bytes;
+      if (!(e && strcmp(e, "envelope") == 0) && sp_setup(h, tb, prop, &why)) {
+        h->sp = true;
+        h->nt = h->P.nt; h->ctas_per_sm = h->sp_ctas;
+        h->smem_bytes = h->sp_smem_bytes;
+        if (h->sp_dscr_stride > h->dscr_stride) h->dscr_stride = h->sp_dscr_stride;
+      } else h->sp_info = "envelope kernels (" + (why.empty() ? std::string("forced") : why) + ")";
+      if (getenv("OMG_B200_VERBOSE")) fprintf(stderr, "[omg_b200] %s\n", h->sp_info.c_str());
+    }
     if (cudaMalloc(&h->counter, sizeof(int)) != cudaSuccess) ok = false;
     if (cudaMalloc(&h->trace, sizeof(double) * TRACE_ROWS * TRACE_COLS) != cudaSuccess) ok = false;
     else cudaMemset(h->trace, 0, sizeof(double) * TRACE_ROWS * TRACE_COLS);
@@ -2033,13 +2061,14 @@ int omg_solve_batch(omg_problem* h, int32_t B, const double* x0, const double* p
   if (!x0 || !p || !lbg || !ubg || !x || !lam_g || !f || !status || !iters) { set_err("null buffer"); return -1; }
   cudaStream_t stream = (cudaStream_t)stream_;
   CK(cudaSetDevice(h->device));
-  int grid = h->n_sm * h->ctas_per_sm;
+  const bool use_sp = h->sp && h->opt.inertia_mode == 0;
+  int grid = h->n_sm * (use_sp ? h->sp_ctas : h->env_ctas);
   if (grid > B) grid = B;
   if (grid > h->scr_ctas) {
     if (h->dscr) cudaFree(h->dscr);
     if (h->iscr) cudaFree(h->iscr);
     h->dscr = nullptr; h->iscr = nullptr;
-    const int want = h->n_sm * h->ctas_per_sm;
+    const int want = h->n_sm * std::max(h->ctas_per_sm, h->env_ctas);
     CK(cudaMalloc(&h->dscr, (size_t)want * h->dscr_stride * sizeof(double)));
     CK(cudaMalloc(&h->iscr, (size_t)want * h->iscr_stride * sizeof(int)));
     h->scr_ctas = want;
@@ -2052,10 +2081,11 @@ int omg_solve_batch(omg_problem* h, int32_t B, const double* x0, const double* p
   A.counter = h->counter; A.trace = h->trace;
   CK(cudaMemsetAsync(h->counter, 0, sizeof(int), stream));
   CK(cudaEventRecord(h->ev0, stream));
-  if (h->xl && h->target_ctas == 1) OMG_LAUNCH(omg_ipm_kernel_xl, grid, 512, h->smem_bytes, stream, h->T, h->opt, A, h->S);
-  else if (h->xl) OMG_LAUNCH(omg_ipm_kernel_xl_2cta, grid, 256, h->smem_bytes, stream, h->T, h->opt, A, h->S);
-  else if (h->target_ctas == 1) OMG_LAUNCH(omg_ipm_kernel, grid, 512, h->smem_bytes, stream, h->T, h->opt, A, h->S);
-  else OMG_LAUNCH(omg_ipm_kernel_2cta, grid, 256, h->smem_bytes, stream, h->T, h->opt, A, h->S);
+  if (use_sp) OMG_LAUNCH(omg_ipm_kernel_sp, grid, h->P.nt, h->sp_smem_bytes, stream, h->T, h->P, h->opt, A, h->SS);
+  else if (h->xl && h->target_ctas == 1) OMG_LAUNCH(omg_ipm_kernel_xl, grid, 512, h->env_smem_bytes, stream, h->T, h->opt, A, h->S);
+  else if (h->xl) OMG_LAUNCH(omg_ipm_kernel_xl_2cta, grid, 256, h->env_smem_bytes, stream, h->T, h->opt, A, h->S);
+  else if (h->target_ctas == 1) OMG_LAUNCH(omg_ipm_kernel, grid, 512, h->env_smem_bytes, stream, h->T, h->opt, A, h->S);
+  else OMG_LAUNCH(omg_ipm_kernel_2cta, grid, 256, h->env_smem_bytes, stream, h->T, h->opt, A, h->S);
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->ev1, stream));
   h->timed = true; h->launches = 1;

@@ -1,0 +1,912 @@
+// omg_sp.cuh -- "sparse" variant of the interior-point kernel (included by omg_b200.cu).
+//
+// Same algorithm as ipm_body (oracle/ipm_ref.py; reference call site problem.py:113), with
+// the linear algebra and the table streams re-designed for instance-level parallelism:
+//
+//   * KKT factorisation K = L D L^T on a SPARSE symbolic structure computed once per problem
+//     (constrained minimum-degree ordering; all instances of a batch share it): config 2 needs
+//     3.7 k stored entries / 36 k multiply-adds per factorisation instead of 8.9 k / 320 k for
+//     the envelope of the time-ordered band -> the factor fits 3 blocks per SM, and the
+//     sequential chain shrinks from 200 pivots to ~30 elimination-tree levels + one dense root.
+//       - non-root columns: level-scheduled LEFT-looking gather, one thread per stored entry,
+//         contributions listed as packed pairs (a, b, k): v -= A[a] * A[b] * rd[k]
+//         (unscaled columns A = L D, rd = 1/d: one barrier per level, signs come with d);
+//       - the dense root (the final chain of the elimination tree, <= 48 columns): right-looking
+//         with the trailing triangle held in REGISTERS (static entry ownership), one barrier
+//         per pivot;
+//       - the right-hand side rides along as row N, so only the backward sweep remains
+//         (root: one warp, shuffle broadcast; the rest: level by level, 8 lanes per column).
+//   * every table stream is laid out per THREAD ("thread streams"): a thread owns whole
+//     outputs (slots, rows, H positions, columns), balanced by record count; record k of its
+//     chunk t sits at ((t*8+k)*NT + tid) -> every warp load is one coalesced line, there are
+//     no descriptor loads, 8 independent loads are in flight per thread, and term records
+//     take 16 bytes instead of 32;
+//   * the assembled K is parked in the block's L2-resident scratch with a TMA bulk store
+//     (cp.async.bulk, SASS UBLKCP) and fetched back with a bulk load + mbarrier for the
+//     inertia-correction retries;
+//   * m-vectors that are only streamed (one thread per row, coalesced) live in the L2-resident
+//     scratch; shared memory holds what is gathered at random: L, the Jacobian values, x, the
+//     parameter tape, Sigma, y.
+#pragma once
+
+#define SP_MAXROOT 48
+#define SP_ROOTQ 10            // root entries per thread (>= (48*49/2+48)/128)
+#define SP_MAXCOL 62           // |struct| of a column (pair delta is 6 bits)
+#define SP_MAXL 8191           // stored entries incl. zero slot (13 bits)
+#define SP_MAXN 2046
+
+struct __align__(16) PT16 { double coef; unsigned short cidx, a, b, c; };   // cidx bit 15: last record of its output
+
+// "thread stream": every thread owns whole outputs; its records are stored consecutively,
+// padded to n_chunk chunks of SP_R records; record k of chunk t of thread tid sits at
+// ((t * SP_R + k) * NT + tid) -> every warp load is one coalesced line, no descriptor loads,
+// SP_R independent loads in flight per thread.  The last record of an output carries an end
+// flag and the output index.
+#define SP_R 8
+struct SpStream { int n_chunk; const void* rec; };
+
+struct SpTab {
+  int nt;                          // threads per block the streams were laid out for
+  int Lsz, zslot, R0, nr, n_lev, root0, n_rootent;
+  // factorisation levels (+ the gather into the root as level n_lev): slices of 32 entries
+  const int* lev_ptr;              // [n_lev+2] slice ranges
+  const uint4* fdesc;              // per slice lane: {entry word, pair offset (uint4 units), n4, 0}
+                                   //   entry word: lidx | col<<13 | isdiag<<24 (0xffffffff idle)
+  const uint4* fpair;              // 4 pairs per uint4, [slice][k4][lane]; pair = a | (a-b)<<13 | k<<19
+  const unsigned short* root_ki;   // [n_rootent] k | i<<8 (root-local column / row; row nr = rhs)
+  const int* ksign;                // [N] +1 / -1 by permuted index
+  // backward sweep: per level, rounds of NT/8 columns; one 32-byte record per lane
+  const int* brnd_ptr;             // [n_lev+1] round ranges per level
+  const uint4* bdesc;              // [round][NT][2]: {j | len<<11 | valid<<18, base, rows[0..1], rows[2..3]}, {rows[4..7]}
+  const int* diagidx; const int* rhsidx;     // [N] L index of the diagonal / rhs entry of a column
+  const int* pos_var; const int* pos_eq;     // permutation of this structure
+  const int* jdst;                 // [nnz_j] L index of the border entry of an equality-row slot
+  SpStream J, G, W, H, C, R;
+};
+
+struct SpSmem {   // offsets in doubles
+  int LK, jval, xe, xt, dx, rd, diag0, V, sig, y, red, filt, rt8, rki, lptr, total;
+  // scratch (global) offsets in doubles
+  int Kc, g, s, zU, dsc, sU, ds, dy, dzU, gt, st, wv, zL, sL, dzL, beq, jt, gf, gtotal;
+};
+
+// ---- TMA bulk copies (1-D) ---------------------------------------------------------
+#ifndef OMG_CPU_EMU
+__device__ __forceinline__ unsigned sp_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sp_mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(sp_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void sp_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(sp_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sp_mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n WAIT_%=:\n"
+      " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      " @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n"
+      :: "r"(sp_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void sp_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(sp_smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(sp_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void sp_bulk_s2g(void* dst_gmem, const void* src_smem, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               :: "l"(dst_gmem), "r"(sp_smem_u32(src_smem)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void sp_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void sp_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void sp_fence_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+#else
+static inline void sp_mbar_init(unsigned long long* bar, unsigned) { *bar = 0; }
+static inline void sp_mbar_expect_tx(unsigned long long*, unsigned) {}
+static inline void sp_mbar_wait(unsigned long long*, unsigned) {}
+static inline void sp_bulk_g2s(void* d, const void* s, unsigned bytes, unsigned long long*) { memcpy(d, s, bytes); }
+static inline void sp_bulk_s2g(void* d, const void* s, unsigned bytes) { memcpy(d, s, bytes); }
+static inline void sp_bulk_wait_all() {}
+static inline void sp_bulk_wait_read() {}
+static inline void sp_fence_async() {}
+#endif
+
+// term streams: SP_R independent 16-byte loads per chunk, then the sums in stream order.
+//   VAL(r) -> value of record r (uint4);  BODY uses o_ (the record's uint4) and acc_
+#define SP_STREAM16(ST, VAL, BODY)                                                           \
+  {                                                                                          \
+    const uint4* rp_ = reinterpret_cast<const uint4*>((ST).rec) + tid;                       \
+    double acc_ = 0.0;                                                                       \
+    for (int t_ = 0; t_ < (ST).n_chunk; ++t_, rp_ += SP_R * NT) {                            \
+      uint4 rr_[SP_R];                                                                       \
+      _Pragma("unroll")                                                                      \
+      for (int k_ = 0; k_ < SP_R; ++k_) rr_[k_] = __ldg(rp_ + k_ * NT);                      \
+      _Pragma("unroll")                                                                      \
+      for (int k_ = 0; k_ < SP_R; ++k_) {                                                    \
+        const uint4 o_ = rr_[k_];                                                            \
+        acc_ += (VAL);                                                                     \
+        if (o_.z & 0x8000u) { BODY acc_ = 0.0; }                                             \
+      }                                                                                      \
+    }                                                                                        \
+  }
+// 8-byte index streams; end flag = bit 16 of .y (bit 30 for H)
+#define SP_STREAM8(ST, ENDBIT, VAL, BODY)                                                    \
+  {                                                                                          \
+    const uint2* rp_ = reinterpret_cast<const uint2*>((ST).rec) + tid;                       \
+    double acc_ = 0.0;                                                                       \
+    for (int t_ = 0; t_ < (ST).n_chunk; ++t_, rp_ += SP_R * NT) {                            \
+      uint2 rr_[SP_R];                                                                       \
+      _Pragma("unroll")                                                                      \
+      for (int k_ = 0; k_ < SP_R; ++k_) rr_[k_] = __ldg(rp_ + k_ * NT);                      \
+      _Pragma("unroll")                                                                      \
+      for (int k_ = 0; k_ < SP_R; ++k_) {                                                    \
+        const uint2 o_ = rr_[k_];                                                            \
+        acc_ += (VAL);                                                                     \
+        if (o_.y & (ENDBIT)) { BODY acc_ = 0.0; }                                            \
+      }                                                                                      \
+    }                                                                                        \
+  }
+#define SP_COEF(r) __hiloint2double((int)(r).y, (int)(r).x)
+#define SP_VJ(X) (SP_COEF(o_) * V[o_.z & 0x7fffu] * (X)[o_.z >> 16])                       // J: a = x0, b = slot, c = row
+#define SP_VG(X) (SP_COEF(o_) * V[o_.z & 0x7fffu] * (X)[o_.z >> 16] * (X)[o_.w & 0xffffu])   // G: a, b = x0, x1, c = row
+#define SP_VC(JV, YV) ((JV)[o_.x & 0xffffu] * (YV)[o_.x >> 16])                             // C / R: slot | index<<16
+
+// ---------------------------------------------------------------------------------------
+// factorisation K = L D L^T in LK (unscaled columns A = L D), rd = 1/d.  ctl->fail on a bad
+// pivot or wrong inertia (mode 0: IPOPT's count test; mode 1: sign by position).
+// flags[3]: per-level pivot reports (negative count | bad<<16 | eq-bad<<24), rotating so that
+// a level's report is read after its barrier while the next level already writes its own.
+// ---------------------------------------------------------------------------------------
+#define SP_PIVOT(j, v)                                                                        \
+  {                                                                                           \
+    const bool neg_ = (v) < 0.0;                                                              \
+    const double d_ = fabs(v);                                                                \
+    const bool isneg_ = __ldg(P.ksign + (j)) < 0;                                             \
+    bool bad_;                                                                                \
+    if (mode) bad_ = (neg_ != isneg_) || !(d_ > (isneg_ ? 0.0 : PIV_TOL * fmax(diag0[j], 1e-300))) || !(d_ < 1e300); \
+    else bad_ = !(d_ > PIV_TOL * fmax(diag0[j], 1e-300)) || !(d_ < 1e300);                     \
+    rd[j] = 1.0 / (v);                                                                        \
+    const int rep_ = (neg_ ? 1 : 0) + (bad_ ? (1 << 16) : 0) + ((bad_ && isneg_) ? (1 << 24) : 0); \
+    if (rep_) atomicAdd(&flags[slot_], rep_);                                                 \
+  }
+#define SP_CHECK()                                                                            \
+  {                                                                                           \
+    const int rep_ = flags[slot_];                                                            \
+    if (tid == 0) flags[(slot_ + 2) % 3] = 0;                                                 \
+    slot_ = (slot_ + 1) % 3;                                                                  \
+    nneg += rep_ & 0xffff;                                                                    \
+    if ((rep_ >> 16) || (mode == 0 && nneg > T.n_eq)) {                                       \
+      if (tid == 0) { ctl->fail = 1; ctl->eq_fail = (rep_ >> 24) ? 1 : 0; }                   \
+      __syncthreads();                                                                        \
+      return;                                                                                 \
+    }                                                                                         \
+  }
+
+__device__ __forceinline__ void sp_factor(const DevTab& T, const SpTab& P, const SpSmem& S, Ctl* ctl,
+                                          int* flags, const int mode) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* LK = sm + S.LK; double* rd = sm + S.rd; const double* diag0 = sm + S.diag0;
+  const int* lptr = reinterpret_cast<const int*>(sm + S.lptr);
+  if (tid < 3) flags[tid] = 0;
+  int slot_ = 0, nneg = 0;
+  __syncthreads();
+  // ---- levels of the elimination tree (+ the gather into the root as level n_lev) ----
+  // the descriptor of this warp's first slice of the next level and its first 4 pairs are
+  // fetched one level ahead
+  uint4 nd = make_uint4(0xffffffffu, 0u, 0u, 0u), np = make_uint4(0u, 0u, 0u, 0u);
+  {
+    const int sl = lptr[0] + warp;
+    if (sl < lptr[1]) { nd = __ldg(P.fdesc + sl * 32 + lane); if (nd.z) np = __ldg(P.fpair + nd.y); }
+  }
+  for (int lv = 0; lv <= P.n_lev; ++lv) {
+    const int s0 = lptr[lv], s1 = lptr[lv + 1];
+    for (int sl = s0 + warp; sl < s1; sl += NWARP) {
+      uint4 d, p0;
+      if (sl == s0 + warp) { d = nd; p0 = np; }
+      else { d = __ldg(P.fdesc + sl * 32 + lane); p0 = d.z ? __ldg(P.fpair + d.y) : make_uint4(0u, 0u, 0u, 0u); }
+      const unsigned e = d.x;
+      const int li = (e == 0xffffffffu) ? P.zslot : (int)(e & 0x1fffu);
+      const uint4* pp = P.fpair + d.y;
+      const int n4 = (int)d.z;
+      double v0 = LK[li], v1 = 0.0;
+#define SP_PAIR(acc, r) { const int a_ = (r) & 0x1fffu; acc -= LK[a_] * rd[(r) >> 19] * LK[a_ - (int)(((r) >> 13) & 63u)]; }
+      for (int k = 0; k < n4; ++k) {
+        const uint4 pc = p0;
+        if (k + 1 < n4) p0 = __ldg(pp + (k + 1) * 32);
+        SP_PAIR(v0, pc.x) SP_PAIR(v1, pc.y) SP_PAIR(v0, pc.z) SP_PAIR(v1, pc.w)
+      }
+      const double v = v0 + v1;
+      if (e != 0xffffffffu) {
+        LK[li] = v;
+        if (e >> 24) { const int j = (e >> 13) & 0x7ffu; SP_PIVOT(j, v) }
+      }
+    }
+    if (lv < P.n_lev) {          // prefetch for the next level (independent of this level's results)
+      const int sl = s1 + warp;
+      nd = make_uint4(0xffffffffu, 0u, 0u, 0u);
+      if (sl < lptr[lv + 2]) { nd = __ldg(P.fdesc + sl * 32 + lane); if (nd.z) np = __ldg(P.fpair + nd.y); }
+    }
+    __syncthreads();
+    SP_CHECK()
+  }
+  // ---- dense root: right-looking, trailing entries in registers ------------------------
+  const int nr = P.nr;
+  if (nr > 0) {
+    double* R = LK + P.root0;
+    const unsigned short* rki = reinterpret_cast<const unsigned short*>(sm + S.rki);
+    double val[SP_ROOTQ]; int kq[SP_ROOTQ], iq[SP_ROOTQ];
+#pragma unroll
+    for (int q = 0; q < SP_ROOTQ; ++q) {
+      const int e = tid + q * NT;
+      if (e < P.n_rootent) { const unsigned ki = rki[e]; kq[q] = ki & 0xffu; iq[q] = ki >> 8; val[q] = R[e]; }
+      else { kq[q] = -1; iq[q] = 0; val[q] = 0.0; }
+    }
+    int cbase = 0;                      // R offset of column c
+    for (int c = 0; c < nr; ++c) {
+      // owners of column c publish its (now final) entries; the diagonal owner also the pivot
+#pragma unroll
+      for (int q = 0; q < SP_ROOTQ; ++q) {
+        if (kq[q] == c) {
+          R[tid + q * NT] = val[q];
+          if (iq[q] == c) { const int j = P.R0 + c; const double v = val[q]; SP_PIVOT(j, v) }
+        }
+      }
+      __syncthreads();
+      SP_CHECK()
+      const double rdc = rd[P.R0 + c];
+      const double* Cc = R + cbase - c;    // Cc[i] = entry (row i, column c), i = c..nr
+#pragma unroll
+      for (int q = 0; q < SP_ROOTQ; ++q)
+        if (kq[q] > c) val[q] -= Cc[iq[q]] * rdc * Cc[kq[q]];
+      cbase += nr - c + 1;
+    }
+  }
+  __syncthreads();
+  if (mode == 0 && nneg != T.n_eq) {   // Sylvester: wrong inertia
+    if (tid == 0) { ctl->fail = 1; ctl->eq_fail = (nneg < T.n_eq) ? 1 : 0; }
+    __syncthreads();
+  }
+}
+
+// backward sweep: u = L^-T D^-1 z, z = the rhs entries of LK; result in uu[0..N)
+__device__ __forceinline__ void sp_back_solve(const DevTab& T, const SpTab& P, const SpSmem& S, double* uu) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double* LK = sm + S.LK; const double* rd = sm + S.rd;
+  const int* bptr = reinterpret_cast<const int*>(sm + S.lptr) + (P.n_lev + 2);
+  const int nr = P.nr, R0 = P.R0;
+  // descriptor of the first round of the top level, fetched while warp 0 does the root
+  uint4 na = make_uint4(0u, 0u, 0u, 0u), nb = na;
+  if (P.n_lev > 0) {
+    const int r0 = bptr[P.n_lev - 1];
+    if (r0 < bptr[P.n_lev]) { na = __ldg(P.bdesc + ((size_t)r0 * NT + tid) * 2); nb = __ldg(P.bdesc + ((size_t)r0 * NT + tid) * 2 + 1); }
+  }
+  if (warp == 0 && nr > 0) {
+    // root, one warp: lane l holds rows l and l+32 (root-local)
+    const double* R = LK + P.root0;
+    const int i0 = lane, i1 = lane + 32;
+    // offset of column c in R: c*(nr+1) - c*(c-1)/2
+    const int o0 = i0 * (nr + 1) - (i0 * (i0 - 1)) / 2, o1 = i1 * (nr + 1) - (i1 * (i1 - 1)) / 2;
+    double w0 = (i0 < nr) ? R[o0 + (nr - i0)] : 0.0;
+    double w1 = (i1 < nr) ? R[o1 + (nr - i1)] : 0.0;
+    for (int c = nr - 1; c >= 0; --c) {
+      const double mine = ((c < 32) ? w0 : w1) * rd[R0 + c];
+      const double uc = __shfl_sync(FULL, mine, c & 31);
+      if (i0 < c) w0 -= R[o0 + (c - i0)] * uc;
+      if (i1 < c && i1 < nr) w1 -= R[o1 + (c - i1)] * uc;
+      if (lane == (c & 31)) uu[R0 + c] = uc;
+    }
+  }
+  __syncthreads();
+  // the other columns, level by level from the top, 8 lanes per column
+  const int sub = lane & 7;
+  for (int lv = P.n_lev - 1; lv >= 0; --lv) {
+    const int r0 = bptr[lv], r1 = bptr[lv + 1];
+    for (int r = r0; r < r1; ++r) {
+      uint4 da, db;
+      if (r == r0) { da = na; db = nb; }
+      else { da = __ldg(P.bdesc + ((size_t)r * NT + tid) * 2); db = __ldg(P.bdesc + ((size_t)r * NT + tid) * 2 + 1); }
+      const int j = da.x & 0x7ffu, len = (da.x >> 11) & 0x7fu, valid = (da.x >> 18) & 1u;
+      const int base = (int)da.y;
+      const unsigned rows[8] = {da.z & 0xffffu, da.z >> 16, da.w & 0xffffu, da.w >> 16,
+                                db.x & 0xffffu, db.x >> 16, db.y & 0xffffu, db.y >> 16};
+      double acc = 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int t = sub + 8 * q;
+        if (valid && t < len) acc += LK[base + 1 + t] * uu[rows[q]];
+      }
+      acc += __shfl_xor_sync(FULL, acc, 1);
+      acc += __shfl_xor_sync(FULL, acc, 2);
+      acc += __shfl_xor_sync(FULL, acc, 4);
+      if (valid && sub == 0) uu[j] = rd[j] * (LK[base + 1 + len] - acc);
+    }
+    if (lv > 0) {
+      const int rn = bptr[lv - 1];
+      if (rn < r0) { na = __ldg(P.bdesc + ((size_t)rn * NT + tid) * 2); nb = __ldg(P.bdesc + ((size_t)rn * NT + tid) * 2 + 1); }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// the solver kernel (no intermediates, term degree <= 3)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, const omg_options& O,
+                                            const Batch& A, const SpSmem& S) {
+  __shared__ Ctl ctl;
+  __shared__ int fflags[3];
+  __shared__ unsigned long long kbar;
+  __shared__ double phase_cyc[NPHASE];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = T.n, m = T.m, N = T.N;
+  double* LK = sm + S.LK; double* jval = sm + S.jval;
+  double* xe = sm + S.xe; double* xt = sm + S.xt; double* dx = sm + S.dx;
+  double* rd = sm + S.rd; double* diag0 = sm + S.diag0; double* V = sm + S.V;
+  double* sig = sm + S.sig; double* y = sm + S.y; double* red = sm + S.red; double* filt = sm + S.filt;
+  unsigned char* rt = reinterpret_cast<unsigned char*>(sm + S.rt8);
+  double* D = A.dscr + (size_t)blockIdx.x * A.dscr_stride;
+  double* Kc = D + S.Kc;
+  double* g = D + S.g; double* s = D + S.s; double* zU = D + S.zU; double* dsc = D + S.dsc;
+  double* sU = D + S.sU; double* ds = D + S.ds; double* dy = D + S.dy; double* dzU = D + S.dzU;
+  double* gt = D + S.gt; double* st = D + S.st; double* wv = D + S.wv; double* zL = D + S.zL;
+  double* sL = D + S.sL; double* dzL = D + S.dzL; double* beq = D + S.beq; double* jt = D + S.jt;
+  double* gf = D + S.gf;
+  int* I = A.iscr + (size_t)blockIdx.x * A.iscr_stride;
+  int* eqidx = I; int* eqrow = eqidx + m;
+  unsigned kphase = 0;
+  {  // once per block
+    unsigned short* rki = reinterpret_cast<unsigned short*>(sm + S.rki);
+    for (int e = tid; e < P.n_rootent; e += NT) rki[e] = P.root_ki[e];
+    int* lp = reinterpret_cast<int*>(sm + S.lptr);
+    for (int e = tid; e < P.n_lev + 2; e += NT) lp[e] = P.lev_ptr[e];
+    for (int e = tid; e < P.n_lev + 1; e += NT) lp[P.n_lev + 2 + e] = P.brnd_ptr[e];
+    if (tid == 0) { sp_mbar_init(&kbar, 1); sp_fence_async(); }
+    if (tid == 0) { sig[m] = 0.0; y[m] = 0.0; wv[m] = 0.0; }
+    for (int i = tid; i <= N; i += NT) rd[i] = 0.0;
+  }
+  __syncthreads();
+
+  for (;;) {
+    if (tid == 0) ctl.inst = atomicAdd(A.counter, 1);
+    __syncthreads();
+    const int inst = ctl.inst;
+    if (inst >= A.B) return;
+    const double* x0 = A.x0 + (size_t)inst * n;
+    const double* par = A.p + (size_t)inst * T.n_par;
+    const double* lbg = A.lbg + (A.bounds_shared ? 0 : (size_t)inst * m);
+    const double* ubg = A.ubg + (A.bounds_shared ? 0 : (size_t)inst * m);
+    const bool tracing = (O.trace != 0) && inst == 0 && A.trace != nullptr;
+    long long phase_t0 = clock64();
+    if (tracing && tid == 0) for (int k = 0; k < NPHASE; ++k) phase_cyc[k] = 0.0;
+
+    // ---- S1: parameter tape ---------------------------------------------------------
+    for (int i = tid; i < 1 + T.n_par; i += NT) V[i] = (i == 0) ? 1.0 : par[i - 1];
+    __syncthreads();
+    for (int l = 0; l < T.n_levels; ++l) {
+      for (int e = T.level_ptr[l] + tid; e < T.level_ptr[l + 1]; e += NT) {
+        double acc = 0.0;
+        for (int t = T.tape_ptr[e]; t < T.tape_ptr[e + 1]; ++t) {
+          const int4 f = __ldg(reinterpret_cast<const int4*>(T.tape_fac) + t);
+          acc += T.tape_coef[t] * V[f.x] * V[f.y] * V[f.z] * V[f.w];
+        }
+        switch (T.tape_func[e]) {
+          case 1: acc = 1.0 / acc; break;
+          case 2: acc = (acc >= 0.0) ? 1.0 : 0.0; break;
+          case 3: acc = (acc > 0.0) ? 1.0 : 0.0; break;
+          case 4: acc = sin(acc); break;
+          case 5: acc = cos(acc); break;
+          case 6: acc = sqrt(acc); break;
+          default: break;
+        }
+        V[1 + T.n_par + e] = acc;
+      }
+      __syncthreads();
+    }
+    // ---- S2: x ------------------------------------------------------------------------
+    for (int i = tid; i <= n; i += NT) { xe[i] = (i < n) ? x0[i] : 1.0; xt[i] = 1.0; }
+    __syncthreads();
+
+    // ---- S3: scaling, row classification, starting point --------------------------------
+    double fmaxv = 0.0;
+    for (int j = tid; j < n; j += NT)
+      fmaxv = fmax(fmaxv, fabs(eval_range(T.DFt, T.dfptr[j], T.dfptr[j + 1], V, xe)));
+    {
+      double r1[1] = {fmaxv}; const int o1[1] = {OP_MAX};
+      block_reduce<1>(r1, o1, red);
+      fmaxv = r1[0];
+    }
+    const double smg = O.scaling_max_gradient;
+    const double fsc = (fmaxv > smg) ? fmax(smg / fmaxv, 1e-8) : 1.0;
+    // unscaled Jacobian -> jval, g -> gt
+    SP_STREAM16(P.J, SP_VJ(xe), jval[o_.w & 0xffffu] = acc_;)
+    SP_STREAM16(P.G, SP_VG(xe), gt[o_.w >> 16] = acc_;)
+    __syncthreads();
+    for (int i = tid; i < m; i += NT) {
+      const RowRec rr = T.rowrec[i];
+      double gm = 0.0;
+      for (int k = 0; k < rr.ns; ++k) gm = fmax(gm, fabs(jval[rr.s0 + k]));
+      const double d = (gm > smg) ? fmax(smg / gm, 1e-8) : 1.0;
+      dsc[i] = d;
+      const double lb = lbg[i], ub = ubg[i];
+      const bool eq = (lb == ub);
+      const bool hL = (lb > -INF_BOUND) && !eq, hU = (ub < INF_BOUND) && !eq;
+      rt[i] = (unsigned char)((hL ? 1 : 0) | (hU ? 2 : 0) | (eq ? 4 : 0));
+      double l = lb * d, uu = ub * d;
+      beq[i] = l;
+      if (hL) l -= O.bound_relax_factor * fmax(1.0, fabs(l));
+      if (hU) uu += O.bound_relax_factor * fmax(1.0, fabs(uu));
+      sL[i] = l; sU[i] = uu;
+      const double gi = d * gt[i];
+      g[i] = gi;
+      double si = gi;
+      const double k1 = O.bound_push, k2 = O.bound_frac;
+      double pl = k1 * fmax(1.0, fabs(l)), pu = k1 * fmax(1.0, fabs(uu));
+      if (hL && hU) { pl = fmin(pl, k2 * (uu - l)); pu = fmin(pu, k2 * (uu - l)); }
+      if (hL) si = fmax(si, l + pl);
+      if (hU) si = fmin(si, uu - pu);
+      s[i] = si;
+      double yi = 0.0;
+      if (A.lam0) yi = A.lam0[(size_t)inst * m + i] * fsc / d;
+      y[i] = yi;
+      zL[i] = hL ? fmax(O.mult_bound_push, -yi) : 0.0;
+      zU[i] = hU ? fmax(O.mult_bound_push, yi) : 0.0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int ne = 0, nbnd = 0, bad = 0;
+      for (int i = 0; i < m; ++i) {
+        const int r = rt[i];
+        if (r & 4) {
+          if (ne < T.n_eq && T.eq_rows[ne] == i) { eqrow[ne] = i; eqidx[i] = ne; } else bad = 1;
+          ++ne;
+        } else eqidx[i] = -1;
+        nbnd += (r & 1) + ((r >> 1) & 1);
+      }
+      if (ne != T.n_eq) bad = 1;
+      ctl.n_eq = bad ? -1 : ne; ctl.n_bounds = nbnd;
+      ctl.mu = O.mu_init; ctl.tau = fmax(TAU_MIN, 1.0 - O.mu_init);
+      ctl.theta_max = -1.0; ctl.theta_min = -1.0;
+      ctl.delta_w_last = 0.0; ctl.nfilt = 0; ctl.status = -1; ctl.iter = 0;
+      ctl.fsc = fsc; ctl.alpha = 0.0; ctl.delta_w = 0.0; ctl.n_restart = 0;
+      ctl.f = fsc * eval_range(T.Ft, 0, T.n_f, V, xe);
+    }
+    __syncthreads();
+    if (ctl.n_eq < 0) {   // equality pattern differs from the lowered structure
+      if (tid == 0) { A.status[inst] = OMG_ERROR_IN_STEP_COMPUTATION; A.iters[inst] = 0; A.f[inst] = 0.0; }
+      for (int i = tid; i < n; i += NT) A.x[(size_t)inst * n + i] = x0[i];
+      for (int i = tid; i < m; i += NT) A.lam[(size_t)inst * m + i] = 0.0;
+      __syncthreads();
+      continue;
+    }
+    const int n_eq = ctl.n_eq;
+    const int n_bounds = ctl.n_bounds;
+
+    // =========================== IP iterations ===================================
+    for (int iter = 0;; ++iter) {
+      TICK(0);
+      double rv[NRED];
+      const int rop[NRED] = {OP_MAX, OP_MAX, OP_MIN, OP_MAX, OP_MAX, OP_MAX,
+                             OP_SUM, OP_SUM, OP_SUM, OP_SUM, OP_MAX, OP_SUM};
+      for (int r = 0; r < NRED; ++r) rv[r] = 0.0;
+      rv[2] = 1e300;
+      // ---- I1: Jacobian values (scaled) + per-row residual terms ---------------------
+      SP_STREAM16(P.J, SP_VJ(xe), jval[o_.w & 0xffffu] = dsc[o_.w >> 16] * acc_;)
+      for (int i = tid; i < m; i += NT) {
+        const int r = rt[i];
+        const double d = dsc[i];
+        const double gi = g[i], si = s[i], yi = y[i];
+        const double ci = (r & 4) ? gi - beq[i] : gi - si;
+        rv[0] = fmax(rv[0], fabs(ci));
+        rv[8] += fabs(ci);
+        double zl = 0.0, zu = 0.0;
+        if (r & 1) { zl = zL[i]; const double dl = si - sL[i]; const double pz = dl * zl;
+          rv[1] = fmax(rv[1], pz); rv[2] = fmin(rv[2], pz); rv[9] += log(dl); rv[7] += zl; }
+        if (r & 2) { zu = zU[i]; const double du = sU[i] - si; const double pz = du * zu;
+          rv[1] = fmax(rv[1], pz); rv[2] = fmin(rv[2], pz); rv[9] += log(du); rv[7] += zu; }
+        const double gun = gi / d;
+        if (r & 6) rv[3] = fmax(rv[3], gun - ubg[i]);
+        if (r & 5) rv[3] = fmax(rv[3], lbg[i] - gun);
+        if (!(r & 4)) { const double rs = fabs(-yi - zl + zu);
+          rv[4] = fmax(rv[4], rs); rv[5] = fmax(rv[5], rs * d); }
+        rv[6] += fabs(yi);
+      }
+      __syncthreads();
+      TICK(1);
+      // ---- I2: columns: grad f, dual residual (J^T y through the CSC ELL) --------------
+      for (int j = tid; j < n; j += NT)
+        gf[j] = ctl.fsc * eval_range(T.DFt, T.dfptr[j], T.dfptr[j + 1], V, xe);
+      __syncthreads();
+      SP_STREAM8(P.C, 0x10000u, SP_VC(jval, y), rv[10] = fmax(rv[10], fabs(gf[o_.y & 0xffffu] + acc_));)
+      block_reduce<NRED>(rv, rop, red);
+      const double cinf = rv[0], maxprod = rv[1], minprod = rv[2], viol = rv[3];
+      const double dinf = fmax(rv[10], rv[4]);
+      const double dinf_un = fmax(rv[10], rv[5]) / ctl.fsc;
+      const double ysum = rv[6], zsum = rv[7], theta = rv[8], logsum = rv[9];
+      const double s_d = fmax(S_MAX, (ysum + zsum) / fmax(1.0, (double)(m + n_bounds))) / S_MAX;
+      const double s_c = fmax(S_MAX, zsum / fmax(1.0, (double)n_bounds)) / S_MAX;
+      double mu = ctl.mu;
+      const double cmpl0 = n_bounds ? fmax(fabs(maxprod), fabs(minprod)) : 0.0;
+      const double E0 = fmax(fmax(dinf / s_d, cinf), cmpl0 / s_c);
+      TICK(2);
+      // ---- I3: termination + barrier update (uniform) -----------------------------------
+      int status = -1;
+      if (!isfinite(E0) || !isfinite(theta)) status = OMG_INVALID_NUMBER_DETECTED;
+      else if (E0 <= O.tol && dinf_un <= O.dual_inf_tol && viol <= O.constr_viol_tol &&
+               cmpl0 / ctl.fsc <= O.compl_inf_tol) status = OMG_SOLVE_SUCCEEDED;
+      else if (iter >= O.max_iter) status = OMG_MAX_ITER_EXCEEDED;
+      if (tracing && tid == 0 && iter < TRACE_ROWS - 2) {
+        double* tr = A.trace + iter * TRACE_COLS;
+        tr[0] = iter; tr[1] = ctl.f / ctl.fsc; tr[2] = cinf; tr[3] = dinf; tr[4] = mu; tr[5] = E0;
+        tr[6] = ctl.alpha; tr[7] = ctl.delta_w;
+      }
+      if (status >= 0) { if (tid == 0) { ctl.status = status; ctl.iter = iter; } break; }
+      {
+        const double mu_min = fmin(O.tol, O.compl_inf_tol * ctl.fsc) / (KAPPA_EPS + 1.0);
+        bool changed = false;
+        for (;;) {
+          const double cm = n_bounds ? fmax(fabs(maxprod - mu), fabs(minprod - mu)) : 0.0;
+          const double Emu = fmax(fmax(dinf / s_d, cinf), cm / s_c);
+          if (Emu <= KAPPA_EPS * mu && mu > mu_min) {
+            mu = fmax(mu_min, fmin(KAPPA_MU * mu, pow(mu, THETA_MU)));
+            changed = true;
+          } else break;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          ctl.mu = mu; ctl.tau = fmax(TAU_MIN, 1.0 - mu);
+          if (changed) ctl.nfilt = 0;
+          if (ctl.theta_max < 0.0) {
+            ctl.theta_max = THETA_MAX_FACT * fmax(1.0, theta);
+            ctl.theta_min = THETA_MIN_FACT * fmax(1.0, theta);
+          }
+          ctl.theta = theta;
+          ctl.phi = ctl.f - mu * logsum;
+          ctl.delta_w = 0.0; ctl.delta_c = 0.0; ctl.first_try = 1;
+        }
+      }
+      __syncthreads();
+      const double tau = ctl.tau;
+      TICK(3);
+      // ---- I4: Sigma, w = Sigma r_d + phi_s ----------------------------------------------
+      for (int i = tid; i < m; i += NT) {
+        const int r = rt[i];
+        double sg = 0.0, ph = 0.0, rdd = 0.0;
+        if (!(r & 4)) {
+          const double si = s[i];
+          rdd = g[i] - si;
+          if (r & 1) { const double dl = si - sL[i]; sg += zL[i] / dl; ph -= mu / dl; }
+          if (r & 2) { const double du = sU[i] - si; sg += zU[i] / du; ph += mu / du; }
+        }
+        sig[i] = sg;
+        wv[i] = (r & 4) ? y[i] : (sg * rdd + ph);
+      }
+      __syncthreads();
+      TICK(4);
+      // ---- I7/I8: assemble + factorise, with inertia correction -----------------------
+      bool assembled = false;
+      for (;;) {
+        if (assembled) {
+          // fetch the parked K back (TMA bulk load), shift the diagonal
+          if (tid == 0) {
+            sp_mbar_expect_tx(&kbar, (unsigned)(P.Lsz * 8));
+            sp_bulk_g2s(LK, Kc, (unsigned)(P.Lsz * 8), &kbar);
+          }
+          sp_mbar_wait(&kbar, kphase & 1u);
+          ++kphase;
+          __syncthreads();
+          for (int j = tid; j < n; j += NT) {
+            const int pj = P.pos_var[j];
+            const double v = LK[P.diagidx[pj]] + ctl.delta_w;
+            LK[P.diagidx[pj]] = v; diag0[pj] = fabs(v);
+          }
+          for (int k = tid; k < n_eq; k += NT) {
+            const int pk = P.pos_eq[k];
+            LK[P.diagidx[pk]] = -ctl.delta_c; diag0[pk] = ctl.delta_c;
+          }
+          if (tid == 0) { ctl.fail = 0; ctl.eq_fail = 0; }
+          __syncthreads();
+        } else {
+          {
+            double2* K2 = reinterpret_cast<double2*>(LK);
+            for (int q = tid; q < (P.Lsz >> 1); q += NT) K2[q] = make_double2(0.0, 0.0);
+          }
+          __syncthreads();
+          // H positions: gather J^T Sigma J (+ delta_w on the diagonal)
+          // record: s1 | s2<<16, row | (dst | diag<<13 | end<<14)<<16
+          SP_STREAM8(P.H, 0x40000000u, jval[o_.x & 0xffffu] * sig[o_.y & 0xffffu] * jval[o_.x >> 16],
+                     { double a_ = acc_; if (o_.y & 0x20000000u) a_ += ctl.delta_w; LK[(o_.y >> 16) & 0x1fffu] = a_; })
+          __syncthreads();
+          TICK(5);
+          // Lagrangian Hessian W (lambda = y*dsc, objective factor fsc)
+          // record: a = lambda row (m: objective, m+1: padding), b = x0, c = L index
+          {
+            const double fsc_ = ctl.fsc;
+#define SP_LAM(lr) (((lr) < (unsigned)m) ? (y[lr] * dsc[lr]) : (((lr) == (unsigned)m) ? fsc_ : 0.0))
+            SP_STREAM16(P.W, SP_COEF(o_) * V[o_.z & 0x7fffu] * SP_LAM(o_.z >> 16) * xe[o_.w & 0xffffu],
+                        LK[o_.w >> 16] += acc_;)
+#undef SP_LAM
+          }
+          __syncthreads();
+          for (int j = tid; j < n; j += NT) {
+            const int pj = P.pos_var[j];
+            diag0[pj] = fabs(LK[P.diagidx[pj]]);
+          }
+          // equality border + right-hand-side entries
+          for (int k = tid; k < n_eq; k += NT) {
+            const int i = eqrow[k], pk = P.pos_eq[k];
+            const RowRec rr = T.rowrec[i];
+            for (int q = 0; q < rr.ns; ++q) LK[P.jdst[rr.s0 + q]] = jval[rr.s0 + q];
+            LK[P.diagidx[pk]] = -ctl.delta_c;
+            diag0[pk] = ctl.delta_c;
+            LK[P.rhsidx[pk]] = -(g[i] - beq[i]);
+          }
+          SP_STREAM8(P.C, 0x10000u, SP_VC(jval, wv),
+                     { const int c_ = o_.y & 0xffffu; LK[P.rhsidx[P.pos_var[c_]]] = -(gf[c_] + acc_); })
+          if (tid == 0) { ctl.fail = 0; ctl.eq_fail = 0; }
+          __syncthreads();
+          // park the assembled K (delta = 0 ... current) for the retries: TMA bulk store
+          if (tid == 0) {
+            sp_bulk_wait_read();           // the previous store has finished reading LK
+            sp_fence_async();
+            sp_bulk_s2g(Kc, LK, (unsigned)(P.Lsz * 8));
+            sp_bulk_wait_read();
+          }
+          __syncthreads();
+          assembled = true;
+        }
+        TICK(6);
+        sp_factor(T, P, S, &ctl, fflags, O.inertia_mode);
+        TICK(7);
+        if (!ctl.fail) break;
+        if (tid == 0) {
+          sp_bulk_wait_all();              // the parked copy is complete in global memory
+          if (ctl.eq_fail) ctl.delta_c = DELTA_C_VAL * pow(mu, DELTA_C_EXP);
+          if (ctl.first_try) {
+            ctl.delta_w = (ctl.delta_w_last == 0.0) ? DELTA_W0
+                          : fmax(DELTA_W_MIN, KAPPA_W_MINUS * ctl.delta_w_last);
+            ctl.first_try = 0;
+          } else {
+            ctl.delta_w *= (ctl.delta_w_last == 0.0) ? KAPPA_W_PLUS_FIRST : KAPPA_W_PLUS;
+          }
+        }
+        __syncthreads();
+        if (ctl.delta_w > DELTA_W_MAX) break;
+      }
+      if (ctl.fail) {
+        if (tid == 0) { ctl.status = OMG_ERROR_IN_STEP_COMPUTATION; ctl.iter = iter; }
+        __syncthreads();
+        break;
+      }
+      if (tid == 0 && ctl.delta_w > 0.0) ctl.delta_w_last = ctl.delta_w;
+      // ---- I9: solve ------------------------------------------------------------------
+      sp_back_solve(T, P, S, xt);        // xt is free here: u (permuted) -> xt[0..N)
+      for (int j = tid; j < n; j += NT) dx[j] = xt[P.pos_var[j]];
+      for (int k = tid; k < n_eq; k += NT) dx[n + k] = xt[P.pos_eq[k]];
+      if (tid == 0) dx[n + n_eq] = 0.0;
+      __syncthreads();
+      TICK(10);
+      // ---- I10: ds, dy, dz, fraction to the boundary -----------------------------------
+      double sv[4];
+      const int sop[4] = {OP_MIN, OP_MIN, OP_SUM, OP_SUM};
+      sv[0] = 1.0; sv[1] = 1.0; sv[2] = 0.0; sv[3] = 0.0;
+      // J dx through the row ELL -> ds (temporarily)
+      SP_STREAM8(P.R, 0x10000u, SP_VC(jval, dx), ds[o_.y & 0xffffu] = acc_;)
+      __syncthreads();
+      for (int i = tid; i < m; i += NT) {
+        const int r = rt[i];
+        const double jd = ds[i];
+        if (r & 4) {
+          ds[i] = 0.0; dy[i] = dx[n + eqidx[i]]; dzL[i] = 0.0; dzU[i] = 0.0;
+        } else {
+          const double si = s[i];
+          const double dsi = jd + (g[i] - si);
+          double ph = 0.0, a = 0.0, b = 0.0;
+          if (r & 1) { const double dl = si - sL[i]; const double z = zL[i]; ph -= mu / dl;
+            a = mu / dl - z - (z / dl) * dsi;
+            if (dsi < 0.0) sv[0] = fmin(sv[0], -tau * dl / dsi);
+            if (a < 0.0) sv[1] = fmin(sv[1], -tau * z / a); dzL[i] = a; }
+          if (r & 2) { const double du = sU[i] - si; const double z = zU[i]; ph += mu / du;
+            b = mu / du - z + (z / du) * dsi;
+            if (dsi > 0.0) sv[0] = fmin(sv[0], tau * du / dsi);
+            if (b < 0.0) sv[1] = fmin(sv[1], -tau * z / b); }
+          ds[i] = dsi; dzU[i] = b;
+          dy[i] = sig[i] * dsi + ph - y[i];
+          sv[2] += ph * dsi;
+        }
+      }
+      for (int j = tid; j < n; j += NT) sv[2] += gf[j] * dx[j];
+      block_reduce<4>(sv, sop, red);
+      const double a_p = sv[0], a_d = sv[1], gphi = sv[2];
+      TICK(11);
+      // ---- I11: filter line search ----------------------------------------------------
+      const double theta0 = ctl.theta, phi0 = ctl.phi;
+      double a_min;
+      if (gphi < 0.0) {
+        a_min = fmin(GAMMA_THETA, GAMMA_PHI * theta0 / (-gphi));
+        if (theta0 <= ctl.theta_min)
+          a_min = fmin(a_min, DELTA_LS * pow(theta0, S_THETA) / pow(-gphi, S_PHI));
+      } else a_min = GAMMA_THETA;
+      a_min *= GAMMA_ALPHA;
+      double alpha = a_p;
+      bool accepted = false, ftype = false;
+      double ft = 0.0;
+      int n_ls = 0;
+      while (alpha >= a_min && n_ls < MAX_LS) {
+        ++n_ls;
+        for (int j = tid; j < n; j += NT) xt[j] = xe[j] + alpha * dx[j];
+        if (tid == 0) xt[n] = 1.0;
+        __syncthreads();
+        SP_STREAM16(P.G, SP_VG(xt), { const int i_ = o_.w >> 16; gt[i_] = dsc[i_] * acc_; })
+        __syncthreads();
+        double tv[3];
+        const int top[3] = {OP_SUM, OP_SUM, OP_SUM};
+        tv[0] = 0.0; tv[1] = 0.0; tv[2] = 0.0;
+        for (int i = tid; i < m; i += NT) {
+          const int r = rt[i];
+          const double gi = gt[i];
+          if (r & 4) tv[0] += fabs(gi - beq[i]);
+          else {
+            const double si = s[i] + alpha * ds[i];
+            st[i] = si;
+            tv[0] += fabs(gi - si);
+            if (r & 1) tv[1] += log(si - sL[i]);
+            if (r & 2) tv[1] += log(sU[i] - si);
+          }
+        }
+        for (int t = tid; t < T.n_f; t += NT) { int aux; tv[2] += term_value(T.Ft + t, V, xt, &aux); }
+        block_reduce<3>(tv, top, red);
+        ft = ctl.fsc * tv[2];
+        const double tht = tv[0], pht = ft - mu * tv[1];
+        bool ok = isfinite(pht) && isfinite(tht) && tht <= ctl.theta_max;
+        if (ok) {
+          const int nf = ctl.nfilt;
+          for (int q = 0; q < nf; ++q)
+            if (!(tht < filt[2 * q] || pht < filt[2 * q + 1])) { ok = false; break; }
+        }
+        ftype = false;
+        if (ok) {
+          const bool switching = (theta0 <= ctl.theta_min && gphi < 0.0 &&
+                                  alpha * pow(-gphi, S_PHI) > DELTA_LS * pow(theta0, S_THETA));
+          if (switching) { ok = cmp_le(pht - phi0, ETA_PHI * alpha * gphi, phi0); ftype = ok; }
+          else ok = cmp_le(tht, (1.0 - GAMMA_THETA) * theta0, theta0) ||
+                    cmp_le(pht - phi0, -GAMMA_PHI * theta0, phi0);
+        }
+        if (ok) { accepted = true; break; }
+        alpha *= 0.5;
+      }
+      bool soft = false;
+      if (!accepted && O.soft_resto) {
+        // ---- soft restoration (IPOPT): accept a step along the same direction if it reduces
+        // the primal-dual error of the barrier problem
+        __syncthreads();
+        double pv[1]; const int pop[1] = {OP_SUM};
+        pv[0] = 0.0;
+        for (int i = tid; i < m; i += NT) {
+          const int r = rt[i];
+          if (r & 4) { pv[0] += fabs(g[i] - beq[i]); continue; }
+          const double si = s[i];
+          double zl = 0.0, zu = 0.0, acc = fabs(g[i] - si);
+          if (r & 1) { zl = zL[i]; acc += fabs((si - sL[i]) * zl - mu); }
+          if (r & 2) { zu = zU[i]; acc += fabs((sU[i] - si) * zu - mu); }
+          pv[0] += acc + fabs(-y[i] - zl + zu);
+        }
+        SP_STREAM8(P.C, 0x10000u, SP_VC(jval, y), pv[0] += fabs(gf[o_.y & 0xffffu] + acc_);)
+        block_reduce<1>(pv, pop, red);
+        const double pd0 = pv[0];
+        alpha = a_p;
+        for (int n_try = 0; n_try < 12; ++n_try) {
+          for (int j = tid; j < n; j += NT) xt[j] = xe[j] + alpha * dx[j];
+          if (tid == 0) xt[n] = 1.0;
+          __syncthreads();
+          const double az = fmin(alpha, a_d);
+          pv[0] = 0.0;
+          // trial Jacobian -> jt (scratch), trial g -> gt, trial y -> wv
+          SP_STREAM16(P.J, SP_VJ(xt), jt[o_.w & 0xffffu] = dsc[o_.w >> 16] * acc_;)
+          SP_STREAM16(P.G, SP_VG(xt), { const int i_ = o_.w >> 16; gt[i_] = dsc[i_] * acc_; })
+          __syncthreads();
+          for (int i = tid; i < m; i += NT) {
+            const int r = rt[i];
+            const double gi = gt[i];
+            const double yt = y[i] + alpha * dy[i];
+            wv[i] = yt;
+            if (r & 4) { pv[0] += fabs(gi - beq[i]); continue; }
+            const double si = s[i] + alpha * ds[i];
+            st[i] = si;
+            double zl = 0.0, zu = 0.0, acc = fabs(gi - si);
+            if (r & 1) { zl = zL[i] + az * dzL[i]; acc += fabs((si - sL[i]) * zl - mu); }
+            if (r & 2) { zu = zU[i] + az * dzU[i]; acc += fabs((sU[i] - si) * zu - mu); }
+            pv[0] += acc + fabs(-yt - zl + zu);
+          }
+          __syncthreads();
+          SP_STREAM8(P.C, 0x10000u, SP_VC(jt, wv),
+                     { const int c_ = o_.y & 0xffffu;
+                       pv[0] += fabs(ctl.fsc * eval_range(T.DFt, T.dfptr[c_], T.dfptr[c_ + 1], V, xt) + acc_); })
+          block_reduce<1>(pv, pop, red);
+          if (isfinite(pv[0]) && pv[0] <= SOFT_RESTO_FACTOR * pd0) {
+            double fv[1]; fv[0] = 0.0;
+            for (int t = tid; t < T.n_f; t += NT) { int aux; fv[0] += term_value(T.Ft + t, V, xt, &aux); }
+            block_reduce<1>(fv, pop, red);
+            ft = ctl.fsc * fv[0];
+            accepted = true; soft = true; ftype = true;
+            break;
+          }
+          alpha *= 0.5;
+        }
+      }
+      if (!accepted) {
+        if (ctl.n_restart < O.max_restarts) {
+          __syncthreads();
+          const double mu_r = O.restart_mu;
+          for (int i = tid; i < m; i += NT) {
+            const int r = rt[i];
+            double si = g[i];
+            if (r & 1) si = fmax(si, sL[i] + O.restart_push * fmax(1.0, fabs(sL[i])));
+            if (r & 2) si = fmin(si, sU[i] - O.restart_push * fmax(1.0, fabs(sU[i])));
+            s[i] = si; y[i] = 0.0;
+            if (r & 1) zL[i] = mu_r / (si - sL[i]);
+            if (r & 2) zU[i] = mu_r / (sU[i] - si);
+          }
+          if (tid == 0) {
+            ctl.n_restart += 1; ctl.mu = mu_r; ctl.tau = fmax(TAU_MIN, 1.0 - mu_r);
+            ctl.nfilt = 0; ctl.theta_max = -1.0; ctl.delta_w_last = 0.0;
+          }
+          __syncthreads();
+          continue;
+        }
+        if (tid == 0) { ctl.status = OMG_RESTORATION_FAILED; ctl.iter = iter; }
+        __syncthreads();
+        break;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        if (soft) ctl.nfilt = 0;
+        if (!ftype) {
+          const double th = (1.0 - GAMMA_THETA) * theta0, ph = phi0 - GAMMA_PHI * theta0;
+          int nf = 0;
+          for (int q = 0; q < ctl.nfilt; ++q)
+            if (!(filt[2 * q] >= th && filt[2 * q + 1] >= ph)) {
+              filt[2 * nf] = filt[2 * q]; filt[2 * nf + 1] = filt[2 * q + 1]; ++nf; }
+          if (nf >= MAXF) {
+            for (int q = 1; q < nf; ++q) { filt[2 * (q - 1)] = filt[2 * q]; filt[2 * (q - 1) + 1] = filt[2 * q + 1]; }
+            --nf;
+          }
+          filt[2 * nf] = th; filt[2 * nf + 1] = ph; ++nf;
+          ctl.nfilt = nf;
+        }
+        ctl.f = ft; ctl.alpha = alpha;
+      }
+      TICK(12);
+      // ---- I12: accept ----------------------------------------------------------------------
+      for (int j = tid; j <= n; j += NT) xe[j] = (j < n) ? xt[j] : 1.0;
+      for (int i = tid; i < m; i += NT) {
+        const int r = rt[i];
+        g[i] = gt[i];
+        y[i] += alpha * dy[i];
+        if (!(r & 4)) {
+          const double si = st[i];
+          s[i] = si;
+          if (r & 1) { const double dl = si - sL[i]; double z = zL[i] + a_d * dzL[i];
+            z = fmin(fmax(z, mu / (KAPPA_SIGMA * dl)), KAPPA_SIGMA * mu / dl); zL[i] = z; }
+          if (r & 2) { const double du = sU[i] - si; double z = zU[i] + a_d * dzU[i];
+            z = fmin(fmax(z, mu / (KAPPA_SIGMA * du)), KAPPA_SIGMA * mu / du); zU[i] = z; }
+        }
+      }
+      __syncthreads();
+    }  // iterations
+
+    // ---- write results -------------------------------------------------------------------
+    __syncthreads();
+    if (tid == 0) sp_bulk_wait_all();
+    for (int i = tid; i < n; i += NT) A.x[(size_t)inst * n + i] = xe[i];
+    for (int i = tid; i < m; i += NT) A.lam[(size_t)inst * m + i] = y[i] * dsc[i] / ctl.fsc;
+    if (tracing && tid == 0) {
+      TICK(13);
+      double* tr = A.trace + (TRACE_ROWS - 2) * TRACE_COLS;
+      for (int k = 0; k < NPHASE; ++k) tr[k] = phase_cyc[k];
+    }
+    if (tid == 0) {
+      A.f[inst] = ctl.f / ctl.fsc;
+      A.status[inst] = ctl.status;
+      A.iters[inst] = ctl.iter;
+    }
+    __syncthreads();
+  }
+}

@@ -1,0 +1,418 @@
+// omg_sp_host.cuh -- host side of the sparse kernel variant (included by omg_b200.cu after
+// the definition of omg_problem): symbolic analysis of the condensed KKT matrix
+//     K = [[H, Jc^T], [Jc, -dc I]]           (H = W + J^T Sigma J, Jc = equality rows)
+// and construction of the thread streams.  Everything here runs once per problem structure
+// (the counterpart of IPOPT's symbolic factorisation inside nlpsol, optilayer.py:49-60).
+#pragma once
+#include <queue>
+#include <map>
+
+namespace {
+
+struct SpSym {
+  int N = 0, n = 0, R0 = 0, nr = 0, n_lev = 0, Lsize = 0;
+  std::vector<int> pos;                       // natural node (var j / n + eq k) -> permuted index
+  std::vector<std::vector<int>> st;           // struct of each permuted column (ascending, < N)
+  std::vector<int> colptr, lev, len;
+  int idx(int i, int j) const {               // L index of entry (row i, column j); i == N: rhs
+    if (j >= R0) return colptr[j] + (i - j);
+    if (i == j) return colptr[j];
+    if (i == N) return colptr[j] + len[j] + 1;
+    const std::vector<int>& s = st[j];
+    const auto it = std::lower_bound(s.begin(), s.end(), i);
+    if (it == s.end() || *it != i) return -1;
+    return colptr[j] + 1 + (int)(it - s.begin());
+  }
+};
+
+// constrained minimum-degree ordering (an equality row becomes eligible once every variable it
+// couples is eliminated, so its pivot is a genuine Schur complement) + symbolic factorisation
+static bool sp_symbolic(const omg_tables* tb, SpSym& Y, std::string* why) {
+  const int n = tb->n, n_eq = tb->kkt_n_eq, N = n + n_eq;
+  Y.N = N; Y.n = n;
+  std::vector<std::vector<char>> A(N, std::vector<char>(N, 0));
+  for (int q = 0; q < tb->nnz_h; ++q) {
+    const int r = tb->hrow[q], c = tb->hcol[q];
+    if (r != c) { A[r][c] = 1; A[c][r] = 1; }
+  }
+  std::vector<int> pending(n_eq, 0);          // uneliminated variables coupled to equality row k
+  std::vector<std::vector<int>> eq_of_var(n);
+  for (int k = 0; k < n_eq; ++k) {
+    const int i = tb->kkt_eq_rows[k];
+    for (int s = tb->jrow_ptr[i]; s < tb->jrow_ptr[i + 1]; ++s) {
+      const int c = tb->jcol[s];
+      if (!A[n + k][c]) { A[n + k][c] = 1; A[c][n + k] = 1; pending[k]++; eq_of_var[c].push_back(k); }
+    }
+  }
+  std::vector<int> deg(N, 0);
+  for (int a = 0; a < N; ++a) for (int b = 0; b < N; ++b) deg[a] += A[a][b];
+  std::vector<char> gone(N, 0);
+  std::vector<int> order; order.reserve(N);
+  std::vector<std::vector<int>> st_nodes(N);
+  for (int step = 0; step < N; ++step) {
+    int v = -1;
+    for (int a = 0; a < N; ++a) {
+      if (gone[a]) continue;
+      if (a >= n && pending[a - n] > 0) continue;
+      if (v < 0 || deg[a] < deg[v]) v = a;
+    }
+    if (v < 0) { *why = "no eligible pivot in the ordering"; return false; }
+    std::vector<int> nb;
+    for (int b = 0; b < N; ++b) if (A[v][b] && !gone[b]) nb.push_back(b);
+    for (size_t x = 0; x < nb.size(); ++x)
+      for (size_t y = x + 1; y < nb.size(); ++y) {
+        const int a = nb[x], b = nb[y];
+        if (!A[a][b]) { A[a][b] = 1; A[b][a] = 1; deg[a]++; deg[b]++; }
+      }
+    for (int b : nb) deg[b]--;
+    gone[v] = 1;
+    if (v < n) for (int k : eq_of_var[v]) pending[k]--;
+    st_nodes[step] = nb;
+    order.push_back(v);
+  }
+  Y.pos.assign(N, 0);
+  for (int s = 0; s < N; ++s) Y.pos[order[s]] = s;
+  Y.st.assign(N, {});
+  for (int j = 0; j < N; ++j) {
+    for (int b : st_nodes[j]) Y.st[j].push_back(Y.pos[b]);
+    std::sort(Y.st[j].begin(), Y.st[j].end());
+  }
+  // root = the final chain of the elimination tree while it stays dense enough
+  std::vector<int> parent(N, -1);
+  for (int j = 0; j < N; ++j) if (!Y.st[j].empty()) parent[j] = Y.st[j][0];
+  // (a column joins only while it is alone on its level of the full tree: a chain that runs
+  // beside other chains costs nothing as a level, but a barrier per pivot inside the root)
+  std::vector<int> lev_all(N, 0), cnt(N + 1, 0);
+  for (int j = 0; j < N; ++j) if (parent[j] >= 0) lev_all[parent[j]] = std::max(lev_all[parent[j]], lev_all[j] + 1);
+  for (int j = 0; j < N; ++j) cnt[lev_all[j]]++;
+  int R0 = N - 1;
+  while (R0 > 0 && parent[R0 - 1] == R0 && cnt[lev_all[R0 - 1]] == 1 && (N - (R0 - 1)) <= SP_MAXROOT &&
+         2 * (int)Y.st[R0 - 1].size() >= (N - R0)) --R0;
+  if (N == 0) R0 = 0;
+  Y.R0 = R0; Y.nr = N - R0;
+  Y.lev.assign(N, 0);
+  int n_lev = 0;
+  for (int j = 0; j < R0; ++j) {
+    const int p = parent[j];
+    if (p >= 0 && p < R0) Y.lev[p] = std::max(Y.lev[p], Y.lev[j] + 1);
+    n_lev = std::max(n_lev, Y.lev[j] + 1);
+  }
+  Y.n_lev = n_lev;
+  Y.len.assign(N, 0); Y.colptr.assign(N + 1, 0);
+  for (int j = 0; j < N; ++j) {
+    Y.len[j] = (int)Y.st[j].size();
+    if (j < R0 && Y.len[j] > SP_MAXCOL) { *why = "column structure too long for the packed pairs"; return false; }
+    Y.colptr[j + 1] = Y.colptr[j] + ((j < R0) ? Y.len[j] + 2 : (N - j + 1));
+  }
+  Y.Lsize = Y.colptr[N];
+  if (Y.Lsize + 1 > SP_MAXL || N > SP_MAXN) { *why = "factor too large for the packed pairs"; return false; }
+  return true;
+}
+
+// thread-balanced stream: lists[o] = records of output o (the builder sets the end flag on the
+// last one through `mark_end`; empty outputs get `dummy(o)`), laid out for nt threads
+template <typename Rec, typename MarkEnd>
+static void sp_build_stream(const std::vector<std::vector<Rec>>& lists, const std::vector<Rec>& dummies,
+                            const Rec& pad, MarkEnd mark_end, int nt, std::vector<Rec>& out, int* n_chunk) {
+  const int n_out = (int)lists.size();
+  std::vector<int> ord(n_out);
+  for (int o = 0; o < n_out; ++o) ord[o] = o;
+  auto size_of = [&](int o) { return lists[o].empty() ? 1 : (int)lists[o].size(); };
+  std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return size_of(a) > size_of(b); });
+  typedef std::pair<int, int> LT;   // (load, thread)
+  std::priority_queue<LT, std::vector<LT>, std::greater<LT>> heap;
+  for (int t = 0; t < nt; ++t) heap.push(LT(0, t));
+  std::vector<std::vector<Rec>> per(nt);
+  for (int o : ord) {
+    LT top = heap.top(); heap.pop();
+    std::vector<Rec>& dst = per[top.second];
+    if (lists[o].empty()) { Rec r = dummies[o]; mark_end(r); dst.push_back(r); }
+    else {
+      for (size_t k = 0; k < lists[o].size(); ++k) {
+        Rec r = lists[o][k];
+        if (k + 1 == lists[o].size()) mark_end(r);
+        dst.push_back(r);
+      }
+    }
+    heap.push(LT(top.first + size_of(o), top.second));
+  }
+  size_t mx = 0;
+  for (int t = 0; t < nt; ++t) mx = std::max(mx, per[t].size());
+  const int nc = (int)((mx + SP_R - 1) / SP_R);
+  *n_chunk = nc;
+  out.assign((size_t)std::max(nc, 1) * SP_R * nt, pad);
+  for (int t = 0; t < nt; ++t)
+    for (size_t k = 0; k < per[t].size(); ++k) out[k * nt + t] = per[t][k];
+}
+
+}  // namespace
+
+// Build the sparse structure + streams; false (with a reason) when the problem is outside what
+// the sparse kernel covers -- the caller then uses the envelope kernels.
+static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp& prop, std::string* why) {
+  const int n = tb->n, m = tb->m, n_eq = tb->kkt_n_eq, N = n + n_eq;
+  if (tb->n_mid > 0) { *why = "intermediates"; return false; }
+  if (tb->G.width > 2 || tb->J.width > 1 || tb->W.width > 1) { *why = "term degree > 2"; return false; }
+  if (tb->n_v >= 32768 || tb->nnz_j >= 65535 || m + 2 >= 65535 || n + 2 >= 65535) { *why = "index range"; return false; }
+  int nt = 128;
+  { const char* e = getenv("OMG_B200_SP_NT"); if (e && (atoi(e) == 128 || atoi(e) == 256)) nt = atoi(e); }
+  SpSym Y;
+  if (!sp_symbolic(tb, Y, why)) return false;
+  const int R0 = Y.R0, nr = Y.nr;
+  SpTab& P = h->P;
+  memset(&P, 0, sizeof(P));
+  bool ok = true;
+  P.nt = nt;
+  P.zslot = Y.Lsize; P.Lsz = (Y.Lsize + 2) & ~1;
+  P.R0 = R0; P.nr = nr; P.n_lev = Y.n_lev; P.root0 = Y.colptr[R0];
+  P.n_rootent = Y.Lsize - Y.colptr[R0];
+  if (P.n_rootent > SP_ROOTQ * nt) { *why = "root block too large"; return false; }
+
+  // ---- pair lists of the left-looking gather -----------------------------------------
+  std::vector<std::vector<unsigned>> plist(Y.Lsize);
+  for (int k = 0; k < R0; ++k) {
+    const std::vector<int>& s = Y.st[k];
+    const int base = Y.colptr[k] + 1, L = Y.len[k];
+    for (int bi = 0; bi < L; ++bi) {
+      const int j = s[bi];
+      for (int ai = bi; ai <= L; ++ai) {           // ai == L: the rhs row
+        const int i = (ai < L) ? s[ai] : N;
+        const int tgt = Y.idx(i, j);
+        if (tgt < 0) { *why = "symbolic structure is not closed"; return false; }
+        const unsigned a = (unsigned)(base + ai), b = (unsigned)(base + bi);
+        plist[tgt].push_back(a | ((a - b) << 13) | ((unsigned)k << 19));
+      }
+    }
+  }
+  const unsigned padpair = (unsigned)P.zslot | ((unsigned)N << 19);
+  std::vector<int> lev_ptr;
+  std::vector<uint4> fdesc, fpair;
+  for (int lv = 0; lv <= Y.n_lev; ++lv) {
+    std::vector<unsigned> ents;        // entry words
+    std::vector<int> lidx;
+    if (lv < Y.n_lev) {
+      for (int j = 0; j < R0; ++j) if (Y.lev[j] == lv)
+        for (int e = Y.colptr[j]; e < Y.colptr[j + 1]; ++e) {
+          lidx.push_back(e);
+          ents.push_back((unsigned)e | ((unsigned)j << 13) | ((e == Y.colptr[j]) ? (1u << 24) : 0u));
+        }
+    } else {
+      for (int e = Y.colptr[R0]; e < Y.Lsize; ++e) if (!plist[e].empty()) { lidx.push_back(e); ents.push_back((unsigned)e); }
+    }
+    std::vector<int> ord(ents.size());
+    for (size_t q = 0; q < ord.size(); ++q) ord[q] = (int)q;
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return plist[lidx[a]].size() > plist[lidx[b]].size(); });
+    lev_ptr.push_back((int)(fdesc.size() / 32));
+    for (size_t q0 = 0; q0 < ord.size(); q0 += 32) {
+      size_t mx = 0;
+      for (size_t q = q0; q < std::min(q0 + 32, ord.size()); ++q) mx = std::max(mx, plist[lidx[ord[q]]].size());
+      const unsigned n4 = (unsigned)((mx + 3) / 4);
+      const unsigned pbase = (unsigned)fpair.size();
+      fpair.resize(fpair.size() + (size_t)n4 * 32, make_uint4(padpair, padpair, padpair, padpair));
+      for (int l = 0; l < 32; ++l) {
+        const size_t q = q0 + l;
+        if (q >= ord.size()) { fdesc.push_back(make_uint4(0xffffffffu, pbase + l, n4, 0u)); continue; }
+        const std::vector<unsigned>& pl = plist[lidx[ord[q]]];
+        fdesc.push_back(make_uint4(ents[ord[q]], pbase + l, n4, 0u));
+        for (size_t k = 0; k < pl.size(); ++k) {
+          uint4& w = fpair[pbase + (k / 4) * 32 + l];
+          (&w.x)[k % 4] = pl[k];
+        }
+      }
+    }
+  }
+  lev_ptr.push_back((int)(fdesc.size() / 32));
+  P.lev_ptr = upload(h, lev_ptr.data(), lev_ptr.size(), &ok);
+  P.fdesc = upload(h, fdesc.data(), fdesc.size(), &ok);
+  P.fpair = upload(h, fpair.data(), fpair.size(), &ok);
+  {
+    std::vector<unsigned short> ki;
+    for (int c = 0; c < nr; ++c) for (int i = c; i <= nr; ++i) ki.push_back((unsigned short)(c | (i << 8)));
+    P.root_ki = upload(h, ki.data(), ki.size(), &ok);
+  }
+  // ---- backward sweep descriptors ---------------------------------------------------------
+  {
+    std::vector<int> brnd;
+    std::vector<uint4> bdesc;
+    const int ngrp = nt / 8;
+    int rounds = 0;
+    for (int lv = 0; lv < Y.n_lev; ++lv) {
+      brnd.push_back(rounds);
+      std::vector<int> cols;
+      for (int j = 0; j < R0; ++j) if (Y.lev[j] == lv) cols.push_back(j);
+      for (size_t c0 = 0; c0 < cols.size(); c0 += ngrp) {
+        for (int t = 0; t < nt; ++t) {
+          const size_t cc = c0 + (t >> 3);
+          uint4 da = make_uint4(0u, 0u, 0u, 0u), db = da;
+          if (cc < cols.size()) {
+            const int j = cols[cc], L = Y.len[j], sub = t & 7;
+            unsigned rows[8];
+            for (int q = 0; q < 8; ++q) rows[q] = (sub + 8 * q < L) ? (unsigned)Y.st[j][sub + 8 * q] : 0u;
+            da = make_uint4((unsigned)j | ((unsigned)L << 11) | (1u << 18), (unsigned)Y.colptr[j],
+                            rows[0] | (rows[1] << 16), rows[2] | (rows[3] << 16));
+            db = make_uint4(rows[4] | (rows[5] << 16), rows[6] | (rows[7] << 16), 0u, 0u);
+          }
+          bdesc.push_back(da); bdesc.push_back(db);
+        }
+        ++rounds;
+      }
+    }
+    brnd.push_back(rounds);
+    P.brnd_ptr = upload(h, brnd.data(), brnd.size(), &ok);
+    P.bdesc = upload(h, bdesc.data(), bdesc.size(), &ok);
+  }
+  // ---- index maps ---------------------------------------------------------------------------
+  std::vector<int> pos_var(n), pos_eq(std::max(n_eq, 1)), ksign(N, 1), diagidx(N), rhsidx(N);
+  for (int j = 0; j < n; ++j) pos_var[j] = Y.pos[j];
+  for (int k = 0; k < n_eq; ++k) { pos_eq[k] = Y.pos[n + k]; ksign[Y.pos[n + k]] = -1; }
+  for (int j = 0; j < N; ++j) { diagidx[j] = Y.idx(j, j); rhsidx[j] = Y.idx(N, j); }
+  P.pos_var = upload(h, pos_var.data(), pos_var.size(), &ok);
+  P.pos_eq = upload(h, pos_eq.data(), pos_eq.size(), &ok);
+  P.ksign = upload(h, ksign.data(), ksign.size(), &ok);
+  P.diagidx = upload(h, diagidx.data(), diagidx.size(), &ok);
+  P.rhsidx = upload(h, rhsidx.data(), rhsidx.size(), &ok);
+  auto lidx_of = [&](int pa, int pb) { return (pa >= pb) ? Y.idx(pa, pb) : Y.idx(pb, pa); };
+  std::vector<char> is_eq(m, 0);
+  {
+    std::vector<int> jdst(std::max(tb->nnz_j, 1), -1);
+    for (int k = 0; k < n_eq; ++k) {
+      const int i = tb->kkt_eq_rows[k];
+      is_eq[i] = 1;
+      for (int s = tb->jrow_ptr[i]; s < tb->jrow_ptr[i + 1]; ++s) {
+        jdst[s] = lidx_of(Y.pos[n + k], Y.pos[tb->jcol[s]]);
+        if (jdst[s] < 0) { *why = "border entry outside the structure"; return false; }
+      }
+    }
+    P.jdst = upload(h, jdst.data(), jdst.size(), &ok);
+  }
+  std::vector<int> hdst(std::max(tb->nnz_h, 1));
+  for (int q = 0; q < tb->nnz_h; ++q) {
+    hdst[q] = lidx_of(Y.pos[tb->hrow[q]], Y.pos[tb->hcol[q]]);
+    if (hdst[q] < 0) { *why = "H position outside the structure"; return false; }
+  }
+  // ---- thread streams -------------------------------------------------------------------------
+  auto xi_of = [&](const omg_termlist& L, int t, int w) { return (w < L.width) ? L.xi[(size_t)t * L.width + w] : n; };
+  auto end16 = [](PT16& r) { r.cidx |= 0x8000u; };
+  PT16 pad16; pad16.coef = 0.0; pad16.cidx = 0; pad16.a = (unsigned short)n; pad16.b = (unsigned short)n; pad16.c = 0;
+  {  // J: a = x0, b = slot, c = row
+    std::vector<std::vector<PT16>> lists(tb->nnz_j);
+    std::vector<PT16> dum(tb->nnz_j);
+    for (int s = 0; s < tb->nnz_j; ++s) {
+      PT16 d = pad16; d.b = (unsigned short)s; d.c = (unsigned short)tb->jrow[s]; dum[s] = d;
+      for (int t = tb->J.ptr[s]; t < tb->J.ptr[s + 1]; ++t) {
+        PT16 r; r.coef = tb->J.coef[t]; r.cidx = (unsigned short)tb->J.cidx[t];
+        r.a = (unsigned short)xi_of(tb->J, t, 0); r.b = (unsigned short)s; r.c = (unsigned short)tb->jrow[s];
+        lists[s].push_back(r);
+      }
+    }
+    std::vector<PT16> out;
+    sp_build_stream(lists, dum, pad16, end16, nt, out, &P.J.n_chunk);
+    P.J.rec = upload(h, out.data(), out.size(), &ok);
+  }
+  {  // G: a, b = x0, x1, c = row
+    std::vector<std::vector<PT16>> lists(m);
+    std::vector<PT16> dum(m);
+    for (int i = 0; i < m; ++i) {
+      PT16 d = pad16; d.c = (unsigned short)i; dum[i] = d;
+      for (int t = tb->G.ptr[i]; t < tb->G.ptr[i + 1]; ++t) {
+        PT16 r; r.coef = tb->G.coef[t]; r.cidx = (unsigned short)tb->G.cidx[t];
+        r.a = (unsigned short)xi_of(tb->G, t, 0); r.b = (unsigned short)xi_of(tb->G, t, 1); r.c = (unsigned short)i;
+        lists[i].push_back(r);
+      }
+    }
+    std::vector<PT16> out;
+    sp_build_stream(lists, dum, pad16, end16, nt, out, &P.G.n_chunk);
+    P.G.rec = upload(h, out.data(), out.size(), &ok);
+  }
+  {  // W: a = lambda row, b = x0, c = L index
+    PT16 padw = pad16; padw.a = (unsigned short)(m + 1); padw.c = (unsigned short)P.zslot;
+    std::vector<std::vector<PT16>> lists(tb->nnz_w);
+    std::vector<PT16> dum(tb->nnz_w, padw);
+    for (int q = 0; q < tb->nnz_w; ++q) {
+      const int dst = hdst[tb->w2h[q]];
+      dum[q].c = (unsigned short)dst;
+      for (int t = tb->W.ptr[q]; t < tb->W.ptr[q + 1]; ++t) {
+        PT16 r; r.coef = tb->W.coef[t]; r.cidx = (unsigned short)tb->W.cidx[t];
+        r.a = (unsigned short)(tb->W.lrow ? tb->W.lrow[t] : m); r.b = (unsigned short)xi_of(tb->W, t, 0);
+        r.c = (unsigned short)dst;
+        lists[q].push_back(r);
+      }
+    }
+    std::vector<PT16> out;
+    sp_build_stream(lists, dum, padw, end16, nt, out, &P.W.n_chunk);
+    P.W.rec = upload(h, out.data(), out.size(), &ok);
+  }
+  {  // H: x = s1 | s2<<16, y = row | (dst | diag<<13 | end<<14)<<16
+    std::vector<std::vector<uint2>> lists(tb->nnz_h);
+    std::vector<uint2> dum(tb->nnz_h);
+    for (int q = 0; q < tb->nnz_h; ++q) {
+      const unsigned tag = ((unsigned)hdst[q] | ((tb->hrow[q] == tb->hcol[q]) ? (1u << 13) : 0u)) << 16;
+      dum[q] = make_uint2(0u, (unsigned)m | tag);
+      for (int e = tb->hp_ptr[q]; e < tb->hp_ptr[q + 1]; ++e) {
+        const int row = tb->hp_row[e];
+        if (is_eq[row]) continue;                 // equality rows sit in the border, Sigma = 0
+        lists[q].push_back(make_uint2((unsigned)tb->hp_s1[e] | ((unsigned)tb->hp_s2[e] << 16), (unsigned)row | tag));
+      }
+    }
+    std::vector<uint2> out;
+    sp_build_stream(lists, dum, make_uint2(0u, (unsigned)m | ((unsigned)P.zslot << 16)),
+                    [](uint2& r) { r.y |= 0x40000000u; }, nt, out, &P.H.n_chunk);
+    P.H.rec = upload(h, out.data(), out.size(), &ok);
+  }
+  {  // C (columns: J^T v): x = slot | row<<16, y = column;  R (rows: J dx): x = slot | col<<16, y = row
+    std::vector<std::vector<uint2>> cl(n), rl(m);
+    std::vector<uint2> cd(n), rdm(m);
+    for (int j = 0; j < n; ++j) cd[j] = make_uint2((unsigned)m << 16, (unsigned)j);
+    for (int i = 0; i < m; ++i) rdm[i] = make_uint2((unsigned)N << 16, (unsigned)i);
+    for (int s = 0; s < tb->nnz_j; ++s) {
+      cl[tb->jcol[s]].push_back(make_uint2((unsigned)s | ((unsigned)tb->jrow[s] << 16), (unsigned)tb->jcol[s]));
+      rl[tb->jrow[s]].push_back(make_uint2((unsigned)s | ((unsigned)tb->jcol[s] << 16), (unsigned)tb->jrow[s]));
+    }
+    auto end8 = [](uint2& r) { r.y |= 0x10000u; };
+    std::vector<uint2> out;
+    sp_build_stream(cl, cd, make_uint2((unsigned)m << 16, 0u), end8, nt, out, &P.C.n_chunk);
+    P.C.rec = upload(h, out.data(), out.size(), &ok);
+    sp_build_stream(rl, rdm, make_uint2((unsigned)N << 16, 0u), end8, nt, out, &P.R.n_chunk);
+    P.R.rec = upload(h, out.data(), out.size(), &ok);
+  }
+  if (!ok) { *why = "device allocation/upload failed"; return false; }
+
+  // ---- shared-memory / scratch layout ---------------------------------------------------------
+  SpSmem& S = h->SS;
+  int off = 0;
+  auto take = [&](int cnt) { int o = off; off += (cnt + 1) & ~1; return o; };
+  S.LK = take(P.Lsz); S.jval = take(tb->nnz_j + 1);
+  S.xe = take(n + 2); S.xt = take(N + 2); S.dx = take(N + 2);
+  S.rd = take(N + 2); S.diag0 = S.rd; S.V = take(tb->n_v);   // rd holds |K_jj| until column j is pivoted
+  S.sig = take(m + 2); S.y = take(m + 2);
+  S.red = take((nt / 32) * NRED); S.filt = take(2 * MAXF);
+  S.rt8 = take((m + 7) / 8); S.rki = take((P.n_rootent + 3) / 4 + 1);
+  S.lptr = take((2 * Y.n_lev + 4 + 1) / 2 + 1);
+  S.total = off;
+  int goff = 0;
+  auto gtake = [&](int cnt) { int o = goff; goff += (cnt + 1) & ~1; return o; };
+  S.Kc = gtake(P.Lsz);
+  S.g = gtake(m + 2); S.s = gtake(m + 2); S.zU = gtake(m + 2); S.dsc = gtake(m + 2); S.sU = gtake(m + 2);
+  S.ds = gtake(m + 2); S.dy = gtake(m + 2); S.dzU = gtake(m + 2); S.gt = gtake(m + 2); S.st = gtake(m + 2);
+  S.wv = gtake(m + 2); S.zL = gtake(m + 2); S.sL = gtake(m + 2); S.dzL = gtake(m + 2); S.beq = gtake(m + 2);
+  S.jt = gtake(tb->nnz_j + 2); S.gf = gtake(n + 2);
+  S.gtotal = goff;
+  h->sp_smem_bytes = (size_t)off * sizeof(double);
+  const void* kfn = (const void*)omg_ipm_kernel_sp;
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, kfn) != cudaSuccess) { *why = "cudaFuncGetAttributes failed"; return false; }
+  if (h->sp_smem_bytes + fa.sharedSizeBytes > (size_t)prop.sharedMemPerBlockOptin) { *why = "does not fit shared memory"; return false; }
+  if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)((size_t)prop.sharedMemPerBlockOptin - fa.sharedSizeBytes)) != cudaSuccess) {
+    *why = "cudaFuncSetAttribute failed"; return false; }
+  int occ = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, nt, h->sp_smem_bytes);
+  if (occ < 1) { *why = "zero occupancy"; return false; }
+  h->sp_ctas = occ;
+  h->sp_dscr_stride = goff + 8;
+  h->sp_info = "sparse LDL^T: N=" + std::to_string(N) + " nnz(L)=" + std::to_string(Y.Lsize) +
+               " levels=" + std::to_string(Y.n_lev) + " root=" + std::to_string(nr) +
+               " pairs=" + std::to_string(fpair.size() * 4) + " nt=" + std::to_string(nt) +
+               " ctas/SM=" + std::to_string(occ) + " smem=" + std::to_string(h->sp_smem_bytes);
+  return true;
+}

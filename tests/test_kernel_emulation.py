@@ -47,11 +47,16 @@ def _compare(pr, B, jitter, seed, n_flat, options=None):
     return res, ref
 
 
-@pytest.mark.parametrize('name, B, layout', [('config1', 3, (97408, 2)), ('config2', 2, (113552, 2)),
-                                             ('config5', 2, None)])
-def test_standard_kernel_matches_oracle(emu, name, B, layout):
-    """omg_ipm_kernel_2cta (256 threads, 2 blocks/SM layout) on BASELINE configs 1, 2, 5:
+@pytest.mark.parametrize('kernel, name, B, layout', [
+    ('sparse', 'config1', 3, (38240, 5)), ('sparse', 'config2', 2, (75232, 3)), ('sparse', 'config5', 2, None),
+    ('envelope', 'config1', 3, (97408, 2)), ('envelope', 'config2', 2, (113552, 2)), ('envelope', 'config5', 2, None)])
+def test_standard_kernel_matches_oracle(emu, monkeypatch, kernel, name, B, layout):
+    """BASELINE configs 1, 2, 5 through both kernel families: omg_ipm_kernel_sp (sparse
+    L D L^T on the minimum-degree structure, thread streams, 128 threads, 3 blocks/SM for
+    config 2) and omg_ipm_kernel_2cta (envelope factorisation, 256 threads, 2 blocks/SM):
     same statuses and iteration counts as the C oracle, solutions to rounding."""
+    if kernel == 'envelope':
+        monkeypatch.setenv('OMG_B200_KERNEL', 'envelope')
     pr = getattr(sc, name)()
     info = pr.problem.info()
     if layout:
@@ -91,7 +96,8 @@ def test_more_models_and_options(emu, name, nflat, options):
 
 
 def test_one_block_per_sm_variant(emu, monkeypatch):
-    """omg_ipm_kernel (512 threads, everything in shared memory)."""
+    """omg_ipm_kernel (envelope, 512 threads, everything in shared memory)."""
+    monkeypatch.setenv('OMG_B200_KERNEL', 'envelope')
     monkeypatch.setenv('OMG_B200_CTAS', '1')
     pr = sc.config2()
     assert pr.problem.info()['ctas_per_sm'] == 1

@@ -23,6 +23,9 @@ struct alignas(16) double2 { double x, y; };
 struct alignas(8) int2 { int x, y; };
 struct alignas(16) int4 { int x, y, z, w; };
 struct alignas(16) uint4 { unsigned x, y, z, w; };
+struct alignas(8) uint2 { unsigned x, y; };
+static inline uint2 make_uint2(unsigned x, unsigned y) { uint2 r; r.x = x; r.y = y; return r; }
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 static inline int2 make_int2(int x, int y) { int2 r; r.x = x; r.y = y; return r; }
 static inline int4 make_int4(int x, int y, int z, int w) { int4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
@@ -47,6 +50,8 @@ extern double omg_emu_smem[];      // the running block's dynamic shared memory
 void omg_emu_launch(int grid, int block, size_t smem_bytes, const std::function<void()>& body);
 void __syncthreads();
 double __shfl_down_sync(unsigned mask, double v, int delta);
+double __shfl_sync(unsigned mask, double v, int src_lane);
+double __shfl_xor_sync(unsigned mask, double v, int lane_mask);
 long long clock64();
 static inline double rsqrt(double x) { return 1.0 / sqrt(x); }
 static inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }   // one OS thread

@@ -92,6 +92,26 @@ double __shfl_down_sync(unsigned, double v, int delta) {
   return r;
 }
 
+double __shfl_sync(unsigned, double v, int src_lane) {
+  const int me = cur, base = me & ~31;
+  shfl_slot[me] = v;
+  warp_barrier();
+  const int src = base + (src_lane & 31);
+  const double r = (src < n_threads) ? shfl_slot[src] : v;
+  warp_barrier();
+  return r;
+}
+
+double __shfl_xor_sync(unsigned, double v, int lane_mask) {
+  const int me = cur, base = me & ~31;
+  shfl_slot[me] = v;
+  warp_barrier();
+  const int src = base + ((me ^ lane_mask) & 31);
+  const double r = (src < n_threads) ? shfl_slot[src] : v;
+  warp_barrier();
+  return r;
+}
+
 long long clock64() {
   timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
   return (long long)ts.tv_sec * 1000000000LL + ts.tv_nsec;
