@@ -30,7 +30,8 @@
 #pragma once
 
 #define SP_MAXROOT 48
-#define SP_ROOTQ 10            // root entries per thread (>= (48*49/2+48)/128)
+#define SP_RCH 2               // root: row chunks per thread
+#define SP_RCW 8               // root: columns per chunk
 #define SP_MAXCOL 62           // |struct| of a column (pair delta is 6 bits)
 #define SP_MAXL 8191           // stored entries incl. zero slot (13 bits)
 #define SP_MAXN 2046
@@ -51,9 +52,10 @@ struct SpTab {
   // factorisation levels (+ the gather into the root as level n_lev): slices of 32 entries
   const int* lev_ptr;              // [n_lev+2] slice ranges
   const uint4* fdesc;              // per slice lane: {entry word, pair offset (uint4 units), n4, 0}
-                                   //   entry word: lidx | col<<13 | isdiag<<24 (0xffffffff idle)
+                                   //   entry word: lidx | col<<13 | isdiag<<24 | eq-pivot<<25 (0xffffffff idle)
   const uint4* fpair;              // 4 pairs per uint4, [slice][k4][lane]; pair = a | (a-b)<<13 | k<<19
-  const unsigned short* root_ki;   // [n_rootent] k | i<<8 (root-local column / row; row nr = rhs)
+  const unsigned* root_ch;         // [SP_RCH * nt] row chunk of a thread: i | k0<<6 | cnt<<12 | eq-pivot<<16
+                                   //   (root-local row i (nr = rhs), columns k0 .. k0+cnt-1; 0: none)
   const int* ksign;                // [N] +1 / -1 by permuted index
   // backward sweep: per level, rounds of NT/8 columns; one 32-byte record per lane
   const int* brnd_ptr;             // [n_lev+1] round ranges per level
@@ -65,9 +67,9 @@ struct SpTab {
 };
 
 struct SpSmem {   // offsets in doubles
-  int LK, jval, xe, xt, dx, rd, diag0, V, sig, y, red, filt, rt8, rki, lptr, total;
+  int LK, jval, xe, xt, dx, gf, rd, diag0, V, sig, y, red, filt, rt8, rki, lptr, total;
   // scratch (global) offsets in doubles
-  int Kc, g, s, zU, dsc, sU, ds, dy, dzU, gt, st, wv, zL, sL, dzL, beq, jt, gf, gtotal;
+  int Kc, g, s, zU, dsc, sU, ds, dy, dzU, gt, st, wv, zL, sL, dzL, beq, jt, yg, sigg, gtotal;
 };
 
 // ---- TMA bulk copies (1-D) ---------------------------------------------------------
@@ -107,6 +109,12 @@ static inline void sp_bulk_s2g(void* d, const void* s, unsigned bytes) { memcpy(
 static inline void sp_bulk_wait_all() {}
 static inline void sp_bulk_wait_read() {}
 static inline void sp_fence_async() {}
+#endif
+
+#ifndef OMG_CPU_EMU
+__device__ __forceinline__ double sp_rcp(double x) { return __drcp_rn(x); }   // correctly rounded, = 1.0 / x
+#else
+static inline double sp_rcp(double x) { return 1.0 / x; }
 #endif
 
 // term streams: SP_R independent 16-byte loads per chunk, then the sums in stream order.
@@ -155,16 +163,15 @@ static inline void sp_fence_async() {}
 // flags[3]: per-level pivot reports (negative count | bad<<16 | eq-bad<<24), rotating so that
 // a level's report is read after its barrier while the next level already writes its own.
 // ---------------------------------------------------------------------------------------
-#define SP_PIVOT(j, v)                                                                        \
+#define SP_PIVOT(j, v, isneg_)                                                                 \
   {                                                                                           \
     const bool neg_ = (v) < 0.0;                                                              \
     const double d_ = fabs(v);                                                                \
-    const bool isneg_ = __ldg(P.ksign + (j)) < 0;                                             \
     bool bad_;                                                                                \
-    if (mode) bad_ = (neg_ != isneg_) || !(d_ > (isneg_ ? 0.0 : PIV_TOL * fmax(diag0[j], 1e-300))) || !(d_ < 1e300); \
-    else bad_ = !(d_ > PIV_TOL * fmax(diag0[j], 1e-300)) || !(d_ < 1e300);                     \
-    rd[j] = 1.0 / (v);                                                                        \
-    const int rep_ = (neg_ ? 1 : 0) + (bad_ ? (1 << 16) : 0) + ((bad_ && isneg_) ? (1 << 24) : 0); \
+    if (mode) bad_ = (neg_ != (isneg_)) || !(d_ > ((isneg_) ? 0.0 : PIV_TOL * fmax(rd[j], 1e-300))) || !(d_ < 1e300); \
+    else bad_ = !(d_ > PIV_TOL * fmax(rd[j], 1e-300)) || !(d_ < 1e300);                       \
+    rd[j] = sp_rcp(v);                      /* rd[j] held |K_jj| until now */                 \
+    const int rep_ = (neg_ ? 1 : 0) + (bad_ ? (1 << 16) : 0) + ((bad_ && (isneg_)) ? (1 << 24) : 0); \
     if (rep_) atomicAdd(&flags[slot_], rep_);                                                 \
   }
 #define SP_CHECK()                                                                            \
@@ -179,87 +186,125 @@ static inline void sp_fence_async() {}
       return;                                                                                 \
     }                                                                                         \
   }
+#define SP_PAIR(acc, r) { const int a_ = (r) & 0x1fffu; acc -= LK[a_] * rd[(r) >> 19] * LK[a_ - (int)(((r) >> 13) & 63u)]; }
+#define SP_PAIR4(pc) { SP_PAIR(v0, (pc).x) SP_PAIR(v1, (pc).y) SP_PAIR(v0, (pc).z) SP_PAIR(v1, (pc).w) }
+// descriptor of slice sl (idle if the level has no slice for this warp) / its first 16 pairs
+#define SP_FDESC(d, sl, s_end) { (d) = make_uint4(0xffffffffu, 0u, 0u, 0u); if ((sl) < (s_end)) (d) = __ldg(P.fdesc + (sl) * 32 + lane); }
+#define SP_FPAIRS(p, d) { const uint4* q_ = P.fpair + (d).y;                                   \
+    if ((d).z > 0u) (p)[0] = __ldg(q_); if ((d).z > 1u) (p)[1] = __ldg(q_ + 32);               \
+    if ((d).z > 2u) (p)[2] = __ldg(q_ + 64); if ((d).z > 3u) (p)[3] = __ldg(q_ + 96); }
 
 __device__ __forceinline__ void sp_factor(const DevTab& T, const SpTab& P, const SpSmem& S, Ctl* ctl,
-                                          int* flags, const int mode) {
+                                          int* flags, const int mode, double* pc) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double* LK = sm + S.LK; double* rd = sm + S.rd; const double* diag0 = sm + S.diag0;
+  double* LK = sm + S.LK; double* rd = sm + S.rd;
+  long long t0_ = clock64();
+#define SP_FT(k) do { if (pc && tid == 0) { const long long t_ = clock64(); pc[k] += (double)(t_ - t0_); t0_ = t_; } } while (0)
   const int* lptr = reinterpret_cast<const int*>(sm + S.lptr);
   if (tid < 3) flags[tid] = 0;
   int slot_ = 0, nneg = 0;
-  __syncthreads();
+  // ownership of the root (static): every thread holds up to SP_RCH chunks of SP_RCW
+  // consecutive columns of ONE row in registers
+  unsigned rch[SP_RCH];
+#pragma unroll
+  for (int q = 0; q < SP_RCH; ++q) rch[q] = __ldg(P.root_ch + q * NT + tid);
   // ---- levels of the elimination tree (+ the gather into the root as level n_lev) ----
-  // the descriptor of this warp's first slice of the next level and its first 4 pairs are
-  // fetched one level ahead
-  uint4 nd = make_uint4(0xffffffffu, 0u, 0u, 0u), np = make_uint4(0u, 0u, 0u, 0u);
-  {
-    const int sl = lptr[0] + warp;
-    if (sl < lptr[1]) { nd = __ldg(P.fdesc + sl * 32 + lane); if (nd.z) np = __ldg(P.fpair + nd.y); }
-  }
+  // software pipeline over this warp's first slice of each level: descriptors two levels
+  // ahead, the first 16 pairs of every entry one level ahead (independent of the numerics)
+  uint4 dA, dB, pA[4], pB[4];
+  SP_FDESC(dA, lptr[0] + warp, lptr[1])
+  SP_FDESC(dB, lptr[1] + warp, (P.n_lev >= 1) ? lptr[2] : 0)
+  SP_FPAIRS(pA, dA)
+  __syncthreads();
   for (int lv = 0; lv <= P.n_lev; ++lv) {
     const int s0 = lptr[lv], s1 = lptr[lv + 1];
+    uint4 dC;
+    SP_FPAIRS(pB, dB)                                       // level lv + 1
+    SP_FDESC(dC, (lv + 2 <= P.n_lev) ? lptr[lv + 2] + warp : 0, (lv + 2 <= P.n_lev) ? lptr[lv + 3] : 0)
     for (int sl = s0 + warp; sl < s1; sl += NWARP) {
-      uint4 d, p0;
-      if (sl == s0 + warp) { d = nd; p0 = np; }
-      else { d = __ldg(P.fdesc + sl * 32 + lane); p0 = d.z ? __ldg(P.fpair + d.y) : make_uint4(0u, 0u, 0u, 0u); }
+      uint4 d, p[4];
+      if (sl == s0 + warp) { d = dA; p[0] = pA[0]; p[1] = pA[1]; p[2] = pA[2]; p[3] = pA[3]; }
+      else { SP_FDESC(d, sl, s1) SP_FPAIRS(p, d) }
       const unsigned e = d.x;
       const int li = (e == 0xffffffffu) ? P.zslot : (int)(e & 0x1fffu);
-      const uint4* pp = P.fpair + d.y;
       const int n4 = (int)d.z;
       double v0 = LK[li], v1 = 0.0;
-#define SP_PAIR(acc, r) { const int a_ = (r) & 0x1fffu; acc -= LK[a_] * rd[(r) >> 19] * LK[a_ - (int)(((r) >> 13) & 63u)]; }
-      for (int k = 0; k < n4; ++k) {
-        const uint4 pc = p0;
-        if (k + 1 < n4) p0 = __ldg(pp + (k + 1) * 32);
-        SP_PAIR(v0, pc.x) SP_PAIR(v1, pc.y) SP_PAIR(v0, pc.z) SP_PAIR(v1, pc.w)
+      if (n4 > 0) SP_PAIR4(p[0])
+      if (n4 > 1) SP_PAIR4(p[1])
+      if (n4 > 2) SP_PAIR4(p[2])
+      if (n4 > 3) SP_PAIR4(p[3])
+      for (int k = 4; k < n4; k += 4) {                    // long lists: four loads in flight
+        const uint4* q_ = P.fpair + d.y + k * 32;
+        uint4 r[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) if (k + t < n4) r[t] = __ldg(q_ + t * 32);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) if (k + t < n4) SP_PAIR4(r[t])
       }
       const double v = v0 + v1;
       if (e != 0xffffffffu) {
         LK[li] = v;
-        if (e >> 24) { const int j = (e >> 13) & 0x7ffu; SP_PIVOT(j, v) }
+        if (e & (1u << 24)) { const int j = (e >> 13) & 0x7ffu; SP_PIVOT(j, v, (e & (1u << 25)) != 0u) }
       }
-    }
-    if (lv < P.n_lev) {          // prefetch for the next level (independent of this level's results)
-      const int sl = s1 + warp;
-      nd = make_uint4(0xffffffffu, 0u, 0u, 0u);
-      if (sl < lptr[lv + 2]) { nd = __ldg(P.fdesc + sl * 32 + lane); if (nd.z) np = __ldg(P.fpair + nd.y); }
     }
     __syncthreads();
     SP_CHECK()
+    dA = dB; dB = dC;
+    pA[0] = pB[0]; pA[1] = pB[1]; pA[2] = pB[2]; pA[3] = pB[3];
+    if (lv == P.n_lev - 1) SP_FT(8);
   }
+  SP_FT(15);
   // ---- dense root: right-looking, trailing entries in registers ------------------------
+  // entry (row i, column k) lives at R[off(k) + i - k], off(k) = k (nr + 1) - k (k - 1) / 2.
+  // Step c: the owners of column c publish its final entries (the diagonal owner also the
+  // pivot), barrier, then every chunk of a row i > c does  val[j] -= (A_ic / d_c) * A_{k0+j,c}.
+  // Columns <= c of a chunk are finished: their registers are dead, updating them is harmless.
   const int nr = P.nr;
   if (nr > 0) {
     double* R = LK + P.root0;
-    const unsigned short* rki = reinterpret_cast<const unsigned short*>(sm + S.rki);
-    double val[SP_ROOTQ]; int kq[SP_ROOTQ], iq[SP_ROOTQ];
+    double val[SP_RCH][SP_RCW];
 #pragma unroll
-    for (int q = 0; q < SP_ROOTQ; ++q) {
-      const int e = tid + q * NT;
-      if (e < P.n_rootent) { const unsigned ki = rki[e]; kq[q] = ki & 0xffu; iq[q] = ki >> 8; val[q] = R[e]; }
-      else { kq[q] = -1; iq[q] = 0; val[q] = 0.0; }
+    for (int q = 0; q < SP_RCH; ++q) {
+      const int i = rch[q] & 63u, k0 = (rch[q] >> 6) & 63u, cnt = (rch[q] >> 12) & 15u;
+#pragma unroll
+      for (int j = 0; j < SP_RCW; ++j) {
+        const int k = k0 + j;
+        val[q][j] = (j < cnt) ? R[k * (nr + 1) - (k * (k - 1)) / 2 + i - k] : 0.0;
+      }
     }
     int cbase = 0;                      // R offset of column c
     for (int c = 0; c < nr; ++c) {
-      // owners of column c publish its (now final) entries; the diagonal owner also the pivot
+      double* Cc = R + cbase - c;       // Cc[i] = entry (row i, column c), i = c..nr
 #pragma unroll
-      for (int q = 0; q < SP_ROOTQ; ++q) {
-        if (kq[q] == c) {
-          R[tid + q * NT] = val[q];
-          if (iq[q] == c) { const int j = P.R0 + c; const double v = val[q]; SP_PIVOT(j, v) }
+      for (int q = 0; q < SP_RCH; ++q) {
+        const int i = rch[q] & 63u, k0 = (rch[q] >> 6) & 63u, cnt = (rch[q] >> 12) & 15u;
+        if ((unsigned)(c - k0) < (unsigned)cnt) {
+#pragma unroll
+          for (int j = 0; j < SP_RCW; ++j) if (k0 + j == c) {
+            const double v = val[q][j];
+            Cc[i] = v;
+            if (i == c) { const int jc = P.R0 + c; SP_PIVOT(jc, v, (rch[q] & 0x10000u) != 0u) }
+          }
         }
       }
       __syncthreads();
       SP_CHECK()
       const double rdc = rd[P.R0 + c];
-      const double* Cc = R + cbase - c;    // Cc[i] = entry (row i, column c), i = c..nr
 #pragma unroll
-      for (int q = 0; q < SP_ROOTQ; ++q)
-        if (kq[q] > c) val[q] -= Cc[iq[q]] * rdc * Cc[kq[q]];
+      for (int q = 0; q < SP_RCH; ++q) {
+        const int i = rch[q] & 63u, k0 = (rch[q] >> 6) & 63u, cnt = (rch[q] >> 12) & 15u;
+        if (cnt > 0 && i > c && k0 + cnt - 1 > c) {
+          const double t = Cc[i] * rdc;
+          const double* Ck = Cc + k0;
+#pragma unroll
+          for (int j = 0; j < SP_RCW; ++j) val[q][j] -= t * Ck[j];
+        }
+      }
       cbase += nr - c + 1;
     }
   }
   __syncthreads();
+  SP_FT(9);
   if (mode == 0 && nneg != T.n_eq) {   // Sylvester: wrong inertia
     if (tid == 0) { ctl->fail = 1; ctl->eq_fail = (nneg < T.n_eq) ? 1 : 0; }
     __syncthreads();
@@ -267,8 +312,9 @@ __device__ __forceinline__ void sp_factor(const DevTab& T, const SpTab& P, const
 }
 
 // backward sweep: u = L^-T D^-1 z, z = the rhs entries of LK; result in uu[0..N)
-__device__ __forceinline__ void sp_back_solve(const DevTab& T, const SpTab& P, const SpSmem& S, double* uu) {
+__device__ __forceinline__ void sp_back_solve(const DevTab& T, const SpTab& P, const SpSmem& S, double* uu, double* pc) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  long long t0_ = clock64();
   const double* LK = sm + S.LK; const double* rd = sm + S.rd;
   const int* bptr = reinterpret_cast<const int*>(sm + S.lptr) + (P.n_lev + 2);
   const int nr = P.nr, R0 = P.R0;
@@ -279,22 +325,38 @@ __device__ __forceinline__ void sp_back_solve(const DevTab& T, const SpTab& P, c
     if (r0 < bptr[P.n_lev]) { na = __ldg(P.bdesc + ((size_t)r0 * NT + tid) * 2); nb = __ldg(P.bdesc + ((size_t)r0 * NT + tid) * 2 + 1); }
   }
   if (warp == 0 && nr > 0) {
-    // root, one warp: lane l holds rows l and l+32 (root-local)
+    // root, one warp: lane l holds rows l and l+32 (root-local); four columns per trip so that
+    // the operand loads run ahead of the dependent chain  w -> u_c -> broadcast -> w
     const double* R = LK + P.root0;
     const int i0 = lane, i1 = lane + 32;
     // offset of column c in R: c*(nr+1) - c*(c-1)/2
     const int o0 = i0 * (nr + 1) - (i0 * (i0 - 1)) / 2, o1 = i1 * (nr + 1) - (i1 * (i1 - 1)) / 2;
     double w0 = (i0 < nr) ? R[o0 + (nr - i0)] : 0.0;
     double w1 = (i1 < nr) ? R[o1 + (nr - i1)] : 0.0;
-    for (int c = nr - 1; c >= 0; --c) {
-      const double mine = ((c < 32) ? w0 : w1) * rd[R0 + c];
-      const double uc = __shfl_sync(FULL, mine, c & 31);
-      if (i0 < c) w0 -= R[o0 + (c - i0)] * uc;
-      if (i1 < c && i1 < nr) w1 -= R[o1 + (c - i1)] * uc;
-      if (lane == (c & 31)) uu[R0 + c] = uc;
+    for (int c = nr - 1; c >= 0; c -= 4) {
+      double a0[4], a1[4], rdv[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int ct = c - t;
+        a0[t] = (i0 < ct) ? R[o0 + (ct - i0)] : 0.0;
+        a1[t] = (i1 < ct && i1 < nr) ? R[o1 + (ct - i1)] : 0.0;
+        rdv[t] = (ct >= 0) ? rd[R0 + ct] : 0.0;
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int ct = c - t;
+        if (ct >= 0) {
+          const double mine = ((ct < 32) ? w0 : w1) * rdv[t];
+          const double uc = __shfl_sync(FULL, mine, ct & 31);
+          w0 -= a0[t] * uc;
+          w1 -= a1[t] * uc;
+          if (lane == (ct & 31)) uu[R0 + ct] = uc;
+        }
+      }
     }
   }
   __syncthreads();
+  SP_FT(14);
   // the other columns, level by level from the top, 8 lanes per column
   const int sub = lane & 7;
   for (int lv = P.n_lev - 1; lv >= 0; --lv) {
@@ -304,15 +366,20 @@ __device__ __forceinline__ void sp_back_solve(const DevTab& T, const SpTab& P, c
       if (r == r0) { da = na; db = nb; }
       else { da = __ldg(P.bdesc + ((size_t)r * NT + tid) * 2); db = __ldg(P.bdesc + ((size_t)r * NT + tid) * 2 + 1); }
       const int j = da.x & 0x7ffu, len = (da.x >> 11) & 0x7fu, valid = (da.x >> 18) & 1u;
+      const int nq = (da.x >> 19) & 15u;                 // rounds of 8 entries this level needs (uniform)
       const int base = (int)da.y;
       const unsigned rows[8] = {da.z & 0xffffu, da.z >> 16, da.w & 0xffffu, da.w >> 16,
                                 db.x & 0xffffu, db.x >> 16, db.y & 0xffffu, db.y >> 16};
-      double acc = 0.0;
+      double acc = 0.0, acc2 = 0.0;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int t = sub + 8 * q;
-        if (valid && t < len) acc += LK[base + 1 + t] * uu[rows[q]];
+      for (int q = 0; q < 8; q += 2) {
+        if (q < nq) {
+          const int t = sub + 8 * q;
+          if (valid && t < len) acc += LK[base + 1 + t] * uu[rows[q]];
+          if (valid && t + 8 < len) acc2 += LK[base + 9 + t] * uu[rows[q + 1]];
+        }
       }
+      acc += acc2;
       acc += __shfl_xor_sync(FULL, acc, 1);
       acc += __shfl_xor_sync(FULL, acc, 2);
       acc += __shfl_xor_sync(FULL, acc, 4);
@@ -340,26 +407,27 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
   double* LK = sm + S.LK; double* jval = sm + S.jval;
   double* xe = sm + S.xe; double* xt = sm + S.xt; double* dx = sm + S.dx;
   double* rd = sm + S.rd; double* diag0 = sm + S.diag0; double* V = sm + S.V;
-  double* sig = sm + S.sig; double* y = sm + S.y; double* red = sm + S.red; double* filt = sm + S.filt;
+  // shared: sg2 = Sigma * dsc^2 and yd = y * dsc (what the gathers need with the UNSCALED
+  // Jacobian values kept in jval), grad f; y, Sigma, dsc themselves are only streamed
+  double* sg2 = sm + S.sig; double* yd = sm + S.y; double* gf = sm + S.gf;
+  double* red = sm + S.red; double* filt = sm + S.filt;
   unsigned char* rt = reinterpret_cast<unsigned char*>(sm + S.rt8);
   double* D = A.dscr + (size_t)blockIdx.x * A.dscr_stride;
   double* Kc = D + S.Kc;
-  double* g = D + S.g; double* s = D + S.s; double* zU = D + S.zU; double* dsc = D + S.dsc;
-  double* sU = D + S.sU; double* ds = D + S.ds; double* dy = D + S.dy; double* dzU = D + S.dzU;
-  double* gt = D + S.gt; double* st = D + S.st; double* wv = D + S.wv; double* zL = D + S.zL;
-  double* sL = D + S.sL; double* dzL = D + S.dzL; double* beq = D + S.beq; double* jt = D + S.jt;
-  double* gf = D + S.gf;
+#define SP_GV(name, off) double* __restrict__ name = D + (off)
+  SP_GV(g, S.g); SP_GV(s, S.s); SP_GV(zU, S.zU); SP_GV(dsc, S.dsc); SP_GV(sU, S.sU); SP_GV(ds, S.ds);
+  SP_GV(dy, S.dy); SP_GV(dzU, S.dzU); SP_GV(gt, S.gt); SP_GV(st, S.st); SP_GV(wv, S.wv); SP_GV(zL, S.zL);
+  SP_GV(sL, S.sL); SP_GV(dzL, S.dzL); SP_GV(beq, S.beq); SP_GV(jt, S.jt); SP_GV(y, S.yg); SP_GV(sig, S.sigg);
+#undef SP_GV
   int* I = A.iscr + (size_t)blockIdx.x * A.iscr_stride;
   int* eqidx = I; int* eqrow = eqidx + m;
   unsigned kphase = 0;
   {  // once per block
-    unsigned short* rki = reinterpret_cast<unsigned short*>(sm + S.rki);
-    for (int e = tid; e < P.n_rootent; e += NT) rki[e] = P.root_ki[e];
     int* lp = reinterpret_cast<int*>(sm + S.lptr);
     for (int e = tid; e < P.n_lev + 2; e += NT) lp[e] = P.lev_ptr[e];
     for (int e = tid; e < P.n_lev + 1; e += NT) lp[P.n_lev + 2 + e] = P.brnd_ptr[e];
     if (tid == 0) { sp_mbar_init(&kbar, 1); sp_fence_async(); }
-    if (tid == 0) { sig[m] = 0.0; y[m] = 0.0; wv[m] = 0.0; }
+    if (tid == 0) { sg2[m] = 0.0; yd[m] = 0.0; wv[m] = 0.0; }
     for (int i = tid; i <= N; i += NT) rd[i] = 0.0;
   }
   __syncthreads();
@@ -445,7 +513,7 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
       s[i] = si;
       double yi = 0.0;
       if (A.lam0) yi = A.lam0[(size_t)inst * m + i] * fsc / d;
-      y[i] = yi;
+      y[i] = yi; yd[i] = yi * d;
       zL[i] = hL ? fmax(O.mult_bound_push, -yi) : 0.0;
       zU[i] = hU ? fmax(O.mult_bound_push, yi) : 0.0;
     }
@@ -488,22 +556,24 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
       for (int r = 0; r < NRED; ++r) rv[r] = 0.0;
       rv[2] = 1e300;
       // ---- I1: Jacobian values (scaled) + per-row residual terms ---------------------
-      SP_STREAM16(P.J, SP_VJ(xe), jval[o_.w & 0xffffu] = dsc[o_.w >> 16] * acc_;)
+      SP_STREAM16(P.J, SP_VJ(xe), jval[o_.w & 0xffffu] = acc_;)
+#pragma unroll 2
       for (int i = tid; i < m; i += NT) {
         const int r = rt[i];
         const double d = dsc[i];
         const double gi = g[i], si = s[i], yi = y[i];
-        const double ci = (r & 4) ? gi - beq[i] : gi - si;
+        const double zl_ = zL[i], zu_ = zU[i], sl_ = sL[i], su_ = sU[i], be_ = beq[i], ub_ = ubg[i], lb_ = lbg[i];
+        const double ci = (r & 4) ? gi - be_ : gi - si;
         rv[0] = fmax(rv[0], fabs(ci));
         rv[8] += fabs(ci);
         double zl = 0.0, zu = 0.0;
-        if (r & 1) { zl = zL[i]; const double dl = si - sL[i]; const double pz = dl * zl;
+        if (r & 1) { zl = zl_; const double dl = si - sl_; const double pz = dl * zl;
           rv[1] = fmax(rv[1], pz); rv[2] = fmin(rv[2], pz); rv[9] += log(dl); rv[7] += zl; }
-        if (r & 2) { zu = zU[i]; const double du = sU[i] - si; const double pz = du * zu;
+        if (r & 2) { zu = zu_; const double du = su_ - si; const double pz = du * zu;
           rv[1] = fmax(rv[1], pz); rv[2] = fmin(rv[2], pz); rv[9] += log(du); rv[7] += zu; }
         const double gun = gi / d;
-        if (r & 6) rv[3] = fmax(rv[3], gun - ubg[i]);
-        if (r & 5) rv[3] = fmax(rv[3], lbg[i] - gun);
+        if (r & 6) rv[3] = fmax(rv[3], gun - ub_);
+        if (r & 5) rv[3] = fmax(rv[3], lb_ - gun);
         if (!(r & 4)) { const double rs = fabs(-yi - zl + zu);
           rv[4] = fmax(rv[4], rs); rv[5] = fmax(rv[5], rs * d); }
         rv[6] += fabs(yi);
@@ -514,7 +584,7 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
       for (int j = tid; j < n; j += NT)
         gf[j] = ctl.fsc * eval_range(T.DFt, T.dfptr[j], T.dfptr[j + 1], V, xe);
       __syncthreads();
-      SP_STREAM8(P.C, 0x10000u, SP_VC(jval, y), rv[10] = fmax(rv[10], fabs(gf[o_.y & 0xffffu] + acc_));)
+      SP_STREAM8(P.C, 0x10000u, SP_VC(jval, yd), rv[10] = fmax(rv[10], fabs(gf[o_.y & 0xffffu] + acc_));)
       block_reduce<NRED>(rv, rop, red);
       const double cinf = rv[0], maxprod = rv[1], minprod = rv[2], viol = rv[3];
       const double dinf = fmax(rv[10], rv[4]);
@@ -566,17 +636,19 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
       const double tau = ctl.tau;
       TICK(3);
       // ---- I4: Sigma, w = Sigma r_d + phi_s ----------------------------------------------
+#pragma unroll 2
       for (int i = tid; i < m; i += NT) {
         const int r = rt[i];
         double sg = 0.0, ph = 0.0, rdd = 0.0;
+        const double si = s[i], gi_ = g[i], sl_ = sL[i], su_ = sU[i], zl_ = zL[i], zu_ = zU[i];
         if (!(r & 4)) {
-          const double si = s[i];
-          rdd = g[i] - si;
-          if (r & 1) { const double dl = si - sL[i]; sg += zL[i] / dl; ph -= mu / dl; }
-          if (r & 2) { const double du = sU[i] - si; sg += zU[i] / du; ph += mu / du; }
+          rdd = gi_ - si;
+          if (r & 1) { const double dl = si - sl_; sg += zl_ / dl; ph -= mu / dl; }
+          if (r & 2) { const double du = su_ - si; sg += zu_ / du; ph += mu / du; }
         }
-        sig[i] = sg;
-        wv[i] = (r & 4) ? y[i] : (sg * rdd + ph);
+        const double d = dsc[i];
+        sig[i] = sg; sg2[i] = sg * d * d;
+        wv[i] = d * ((r & 4) ? y[i] : (sg * rdd + ph));
       }
       __syncthreads();
       TICK(4);
@@ -611,7 +683,7 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
           __syncthreads();
           // H positions: gather J^T Sigma J (+ delta_w on the diagonal)
           // record: s1 | s2<<16, row | (dst | diag<<13 | end<<14)<<16
-          SP_STREAM8(P.H, 0x40000000u, jval[o_.x & 0xffffu] * sig[o_.y & 0xffffu] * jval[o_.x >> 16],
+          SP_STREAM8(P.H, 0x40000000u, jval[o_.x & 0xffffu] * sg2[o_.y & 0xffffu] * jval[o_.x >> 16],
                      { double a_ = acc_; if (o_.y & 0x20000000u) a_ += ctl.delta_w; LK[(o_.y >> 16) & 0x1fffu] = a_; })
           __syncthreads();
           TICK(5);
@@ -619,7 +691,7 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
           // record: a = lambda row (m: objective, m+1: padding), b = x0, c = L index
           {
             const double fsc_ = ctl.fsc;
-#define SP_LAM(lr) (((lr) < (unsigned)m) ? (y[lr] * dsc[lr]) : (((lr) == (unsigned)m) ? fsc_ : 0.0))
+#define SP_LAM(lr) (((lr) < (unsigned)m) ? yd[lr] : (((lr) == (unsigned)m) ? fsc_ : 0.0))
             SP_STREAM16(P.W, SP_COEF(o_) * V[o_.z & 0x7fffu] * SP_LAM(o_.z >> 16) * xe[o_.w & 0xffffu],
                         LK[o_.w >> 16] += acc_;)
 #undef SP_LAM
@@ -633,13 +705,14 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
           for (int k = tid; k < n_eq; k += NT) {
             const int i = eqrow[k], pk = P.pos_eq[k];
             const RowRec rr = T.rowrec[i];
-            for (int q = 0; q < rr.ns; ++q) LK[P.jdst[rr.s0 + q]] = jval[rr.s0 + q];
+            const double di = dsc[i];
+            for (int q = 0; q < rr.ns; ++q) LK[P.jdst[rr.s0 + q]] = di * jval[rr.s0 + q];
             LK[P.diagidx[pk]] = -ctl.delta_c;
             diag0[pk] = ctl.delta_c;
             LK[P.rhsidx[pk]] = -(g[i] - beq[i]);
           }
           SP_STREAM8(P.C, 0x10000u, SP_VC(jval, wv),
-                     { const int c_ = o_.y & 0xffffu; LK[P.rhsidx[P.pos_var[c_]]] = -(gf[c_] + acc_); })
+                     { LK[(o_.y >> 17) & 0x1fffu] = -(gf[o_.y & 0xffffu] + acc_); })
           if (tid == 0) { ctl.fail = 0; ctl.eq_fail = 0; }
           __syncthreads();
           // park the assembled K (delta = 0 ... current) for the retries: TMA bulk store
@@ -653,7 +726,7 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
           assembled = true;
         }
         TICK(6);
-        sp_factor(T, P, S, &ctl, fflags, O.inertia_mode);
+        sp_factor(T, P, S, &ctl, fflags, O.inertia_mode, tracing ? phase_cyc : nullptr);
         TICK(7);
         if (!ctl.fail) break;
         if (tid == 0) {
@@ -677,7 +750,7 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
       }
       if (tid == 0 && ctl.delta_w > 0.0) ctl.delta_w_last = ctl.delta_w;
       // ---- I9: solve ------------------------------------------------------------------
-      sp_back_solve(T, P, S, xt);        // xt is free here: u (permuted) -> xt[0..N)
+      sp_back_solve(T, P, S, xt, tracing ? phase_cyc : nullptr);        // xt is free here: u (permuted) -> xt[0..N)
       for (int j = tid; j < n; j += NT) dx[j] = xt[P.pos_var[j]];
       for (int k = tid; k < n_eq; k += NT) dx[n + k] = xt[P.pos_eq[k]];
       if (tid == 0) dx[n + n_eq] = 0.0;
@@ -690,25 +763,26 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
       // J dx through the row ELL -> ds (temporarily)
       SP_STREAM8(P.R, 0x10000u, SP_VC(jval, dx), ds[o_.y & 0xffffu] = acc_;)
       __syncthreads();
+#pragma unroll 2
       for (int i = tid; i < m; i += NT) {
         const int r = rt[i];
-        const double jd = ds[i];
+        const double jd = dsc[i] * ds[i];
+        const double si = s[i], gi_ = g[i], sl_ = sL[i], su_ = sU[i], zl_ = zL[i], zu_ = zU[i], sg_ = sig[i], yi_ = y[i];
         if (r & 4) {
           ds[i] = 0.0; dy[i] = dx[n + eqidx[i]]; dzL[i] = 0.0; dzU[i] = 0.0;
         } else {
-          const double si = s[i];
-          const double dsi = jd + (g[i] - si);
+          const double dsi = jd + (gi_ - si);
           double ph = 0.0, a = 0.0, b = 0.0;
-          if (r & 1) { const double dl = si - sL[i]; const double z = zL[i]; ph -= mu / dl;
+          if (r & 1) { const double dl = si - sl_; const double z = zl_; ph -= mu / dl;
             a = mu / dl - z - (z / dl) * dsi;
             if (dsi < 0.0) sv[0] = fmin(sv[0], -tau * dl / dsi);
             if (a < 0.0) sv[1] = fmin(sv[1], -tau * z / a); dzL[i] = a; }
-          if (r & 2) { const double du = sU[i] - si; const double z = zU[i]; ph += mu / du;
+          if (r & 2) { const double du = su_ - si; const double z = zu_; ph += mu / du;
             b = mu / du - z + (z / du) * dsi;
             if (dsi > 0.0) sv[0] = fmin(sv[0], tau * du / dsi);
             if (b < 0.0) sv[1] = fmin(sv[1], -tau * z / b); }
           ds[i] = dsi; dzU[i] = b;
-          dy[i] = sig[i] * dsi + ph - y[i];
+          dy[i] = sg_ * dsi + ph - yi_;
           sv[2] += ph * dsi;
         }
       }
@@ -734,21 +808,24 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
         for (int j = tid; j < n; j += NT) xt[j] = xe[j] + alpha * dx[j];
         if (tid == 0) xt[n] = 1.0;
         __syncthreads();
-        SP_STREAM16(P.G, SP_VG(xt), { const int i_ = o_.w >> 16; gt[i_] = dsc[i_] * acc_; })
+        SP_STREAM16(P.G, SP_VG(xt), gt[o_.w >> 16] = acc_;)
         __syncthreads();
         double tv[3];
         const int top[3] = {OP_SUM, OP_SUM, OP_SUM};
         tv[0] = 0.0; tv[1] = 0.0; tv[2] = 0.0;
+#pragma unroll 2
         for (int i = tid; i < m; i += NT) {
           const int r = rt[i];
-          const double gi = gt[i];
-          if (r & 4) tv[0] += fabs(gi - beq[i]);
+          const double gi = dsc[i] * gt[i];
+          const double be_ = beq[i], s_ = s[i], ds_ = ds[i], sl_ = sL[i], su_ = sU[i];
+          gt[i] = gi;
+          if (r & 4) tv[0] += fabs(gi - be_);
           else {
-            const double si = s[i] + alpha * ds[i];
+            const double si = s_ + alpha * ds_;
             st[i] = si;
             tv[0] += fabs(gi - si);
-            if (r & 1) tv[1] += log(si - sL[i]);
-            if (r & 2) tv[1] += log(sU[i] - si);
+            if (r & 1) tv[1] += log(si - sl_);
+            if (r & 2) tv[1] += log(su_ - si);
           }
         }
         for (int t = tid; t < T.n_f; t += NT) { int aux; tv[2] += term_value(T.Ft + t, V, xt, &aux); }
@@ -788,7 +865,7 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
           if (r & 2) { zu = zU[i]; acc += fabs((sU[i] - si) * zu - mu); }
           pv[0] += acc + fabs(-y[i] - zl + zu);
         }
-        SP_STREAM8(P.C, 0x10000u, SP_VC(jval, y), pv[0] += fabs(gf[o_.y & 0xffffu] + acc_);)
+        SP_STREAM8(P.C, 0x10000u, SP_VC(jval, yd), pv[0] += fabs(gf[o_.y & 0xffffu] + acc_);)
         block_reduce<1>(pv, pop, red);
         const double pd0 = pv[0];
         alpha = a_p;
@@ -799,14 +876,15 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
           const double az = fmin(alpha, a_d);
           pv[0] = 0.0;
           // trial Jacobian -> jt (scratch), trial g -> gt, trial y -> wv
-          SP_STREAM16(P.J, SP_VJ(xt), jt[o_.w & 0xffffu] = dsc[o_.w >> 16] * acc_;)
-          SP_STREAM16(P.G, SP_VG(xt), { const int i_ = o_.w >> 16; gt[i_] = dsc[i_] * acc_; })
+          SP_STREAM16(P.J, SP_VJ(xt), jt[o_.w & 0xffffu] = acc_;)
+          SP_STREAM16(P.G, SP_VG(xt), gt[o_.w >> 16] = acc_;)
           __syncthreads();
           for (int i = tid; i < m; i += NT) {
             const int r = rt[i];
-            const double gi = gt[i];
+            const double gi = dsc[i] * gt[i];
+            gt[i] = gi;
             const double yt = y[i] + alpha * dy[i];
-            wv[i] = yt;
+            wv[i] = yt * dsc[i];
             if (r & 4) { pv[0] += fabs(gi - beq[i]); continue; }
             const double si = s[i] + alpha * ds[i];
             st[i] = si;
@@ -840,7 +918,7 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
             double si = g[i];
             if (r & 1) si = fmax(si, sL[i] + O.restart_push * fmax(1.0, fabs(sL[i])));
             if (r & 2) si = fmin(si, sU[i] - O.restart_push * fmax(1.0, fabs(sU[i])));
-            s[i] = si; y[i] = 0.0;
+            s[i] = si; y[i] = 0.0; yd[i] = 0.0;
             if (r & 1) zL[i] = mu_r / (si - sL[i]);
             if (r & 2) zU[i] = mu_r / (sU[i] - si);
           }
@@ -876,16 +954,19 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
       TICK(12);
       // ---- I12: accept ----------------------------------------------------------------------
       for (int j = tid; j <= n; j += NT) xe[j] = (j < n) ? xt[j] : 1.0;
+#pragma unroll 2
       for (int i = tid; i < m; i += NT) {
         const int r = rt[i];
-        g[i] = gt[i];
-        y[i] += alpha * dy[i];
+        const double gt_ = gt[i], y_ = y[i], dy_ = dy[i], d_ = dsc[i], st_ = st[i], sl_ = sL[i], su_ = sU[i],
+                     zl_ = zL[i], zu_ = zU[i], dzl_ = dzL[i], dzu_ = dzU[i];
+        g[i] = gt_;
+        { const double yn = y_ + alpha * dy_; y[i] = yn; yd[i] = yn * d_; }
         if (!(r & 4)) {
-          const double si = st[i];
+          const double si = st_;
           s[i] = si;
-          if (r & 1) { const double dl = si - sL[i]; double z = zL[i] + a_d * dzL[i];
+          if (r & 1) { const double dl = si - sl_; double z = zl_ + a_d * dzl_;
             z = fmin(fmax(z, mu / (KAPPA_SIGMA * dl)), KAPPA_SIGMA * mu / dl); zL[i] = z; }
-          if (r & 2) { const double du = sU[i] - si; double z = zU[i] + a_d * dzU[i];
+          if (r & 2) { const double du = su_ - si; double z = zu_ + a_d * dzu_;
             z = fmin(fmax(z, mu / (KAPPA_SIGMA * du)), KAPPA_SIGMA * mu / du); zU[i] = z; }
         }
       }

@@ -155,7 +155,7 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
   if (tb->G.width > 2 || tb->J.width > 1 || tb->W.width > 1) { *why = "term degree > 2"; return false; }
   if (tb->n_v >= 32768 || tb->nnz_j >= 65535 || m + 2 >= 65535 || n + 2 >= 65535) { *why = "index range"; return false; }
   int nt = 128;
-  { const char* e = getenv("OMG_B200_SP_NT"); if (e && (atoi(e) == 128 || atoi(e) == 256)) nt = atoi(e); }
+  // (the kernel is compiled for 128-thread blocks: __launch_bounds__(128, 3))
   SpSym Y;
   if (!sp_symbolic(tb, Y, why)) return false;
   const int R0 = Y.R0, nr = Y.nr;
@@ -166,7 +166,7 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
   P.zslot = Y.Lsize; P.Lsz = (Y.Lsize + 2) & ~1;
   P.R0 = R0; P.nr = nr; P.n_lev = Y.n_lev; P.root0 = Y.colptr[R0];
   P.n_rootent = Y.Lsize - Y.colptr[R0];
-  if (P.n_rootent > SP_ROOTQ * nt) { *why = "root block too large"; return false; }
+
 
   // ---- pair lists of the left-looking gather -----------------------------------------
   std::vector<std::vector<unsigned>> plist(Y.Lsize);
@@ -185,6 +185,8 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
     }
   }
   const unsigned padpair = (unsigned)P.zslot | ((unsigned)N << 19);
+  std::vector<char> is_eq_pos(N, 0);          // permuted index -> pivot of an equality row
+  for (int k = 0; k < n_eq; ++k) is_eq_pos[Y.pos[n + k]] = 1;
   std::vector<int> lev_ptr;
   std::vector<uint4> fdesc, fpair;
   for (int lv = 0; lv <= Y.n_lev; ++lv) {
@@ -194,7 +196,8 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
       for (int j = 0; j < R0; ++j) if (Y.lev[j] == lv)
         for (int e = Y.colptr[j]; e < Y.colptr[j + 1]; ++e) {
           lidx.push_back(e);
-          ents.push_back((unsigned)e | ((unsigned)j << 13) | ((e == Y.colptr[j]) ? (1u << 24) : 0u));
+          ents.push_back((unsigned)e | ((unsigned)j << 13) | ((e == Y.colptr[j]) ? (1u << 24) : 0u) |
+                         ((e == Y.colptr[j] && is_eq_pos[j]) ? (1u << 25) : 0u));
         }
     } else {
       for (int e = Y.colptr[R0]; e < Y.Lsize; ++e) if (!plist[e].empty()) { lidx.push_back(e); ents.push_back((unsigned)e); }
@@ -225,10 +228,21 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
   P.lev_ptr = upload(h, lev_ptr.data(), lev_ptr.size(), &ok);
   P.fdesc = upload(h, fdesc.data(), fdesc.size(), &ok);
   P.fpair = upload(h, fpair.data(), fpair.size(), &ok);
-  {
-    std::vector<unsigned short> ki;
-    for (int c = 0; c < nr; ++c) for (int i = c; i <= nr; ++i) ki.push_back((unsigned short)(c | (i << 8)));
-    P.root_ki = upload(h, ki.data(), ki.size(), &ok);
+  {  // root: row chunks, dealt round-robin to the threads (long rows first)
+    std::vector<unsigned> chunks;
+    for (int i = nr; i >= 0; --i) {
+      const int kmax = std::min(i, nr - 1);
+      for (int k0 = 0; k0 <= kmax; k0 += SP_RCW) {
+        const int cnt = std::min(SP_RCW, kmax - k0 + 1);
+        const bool has_diag = (i < nr && k0 <= i && i < k0 + cnt);
+        chunks.push_back((unsigned)i | ((unsigned)k0 << 6) | ((unsigned)cnt << 12) |
+                         ((has_diag && is_eq_pos[R0 + i]) ? 0x10000u : 0u));
+      }
+    }
+    if ((int)chunks.size() > SP_RCH * nt) { *why = "root block too large"; return false; }
+    std::vector<unsigned> rc((size_t)SP_RCH * nt, 0u);
+    for (size_t c = 0; c < chunks.size(); ++c) rc[(c / nt) * nt + (c % nt)] = chunks[c];
+    P.root_ch = upload(h, rc.data(), rc.size(), &ok);
   }
   // ---- backward sweep descriptors ---------------------------------------------------------
   {
@@ -240,15 +254,18 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
       brnd.push_back(rounds);
       std::vector<int> cols;
       for (int j = 0; j < R0; ++j) if (Y.lev[j] == lv) cols.push_back(j);
+      int maxlen = 0;
+      for (int j : cols) maxlen = std::max(maxlen, Y.len[j]);
+      const unsigned nq = (unsigned)((maxlen + 7) / 8);
       for (size_t c0 = 0; c0 < cols.size(); c0 += ngrp) {
         for (int t = 0; t < nt; ++t) {
           const size_t cc = c0 + (t >> 3);
-          uint4 da = make_uint4(0u, 0u, 0u, 0u), db = da;
+          uint4 da = make_uint4(nq << 19, 0u, 0u, 0u), db = make_uint4(0u, 0u, 0u, 0u);
           if (cc < cols.size()) {
             const int j = cols[cc], L = Y.len[j], sub = t & 7;
             unsigned rows[8];
             for (int q = 0; q < 8; ++q) rows[q] = (sub + 8 * q < L) ? (unsigned)Y.st[j][sub + 8 * q] : 0u;
-            da = make_uint4((unsigned)j | ((unsigned)L << 11) | (1u << 18), (unsigned)Y.colptr[j],
+            da = make_uint4((unsigned)j | ((unsigned)L << 11) | (1u << 18) | (nq << 19), (unsigned)Y.colptr[j],
                             rows[0] | (rows[1] << 16), rows[2] | (rows[3] << 16));
             db = make_uint4(rows[4] | (rows[5] << 16), rows[6] | (rows[7] << 16), 0u, 0u);
           }
@@ -362,10 +379,11 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
   {  // C (columns: J^T v): x = slot | row<<16, y = column;  R (rows: J dx): x = slot | col<<16, y = row
     std::vector<std::vector<uint2>> cl(n), rl(m);
     std::vector<uint2> cd(n), rdm(m);
-    for (int j = 0; j < n; ++j) cd[j] = make_uint2((unsigned)m << 16, (unsigned)j);
+    auto ctag = [&](int j) { return (unsigned)j | ((unsigned)rhsidx[Y.pos[j]] << 17); };
+    for (int j = 0; j < n; ++j) cd[j] = make_uint2((unsigned)m << 16, ctag(j));
     for (int i = 0; i < m; ++i) rdm[i] = make_uint2((unsigned)N << 16, (unsigned)i);
     for (int s = 0; s < tb->nnz_j; ++s) {
-      cl[tb->jcol[s]].push_back(make_uint2((unsigned)s | ((unsigned)tb->jrow[s] << 16), (unsigned)tb->jcol[s]));
+      cl[tb->jcol[s]].push_back(make_uint2((unsigned)s | ((unsigned)tb->jrow[s] << 16), ctag(tb->jcol[s])));
       rl[tb->jrow[s]].push_back(make_uint2((unsigned)s | ((unsigned)tb->jcol[s] << 16), (unsigned)tb->jrow[s]));
     }
     auto end8 = [](uint2& r) { r.y |= 0x10000u; };
@@ -382,11 +400,11 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
   int off = 0;
   auto take = [&](int cnt) { int o = off; off += (cnt + 1) & ~1; return o; };
   S.LK = take(P.Lsz); S.jval = take(tb->nnz_j + 1);
-  S.xe = take(n + 2); S.xt = take(N + 2); S.dx = take(N + 2);
+  S.xe = take(n + 2); S.xt = take(N + 2); S.dx = take(N + 2); S.gf = take(n + 2);
   S.rd = take(N + 2); S.diag0 = S.rd; S.V = take(tb->n_v);   // rd holds |K_jj| until column j is pivoted
   S.sig = take(m + 2); S.y = take(m + 2);
   S.red = take((nt / 32) * NRED); S.filt = take(2 * MAXF);
-  S.rt8 = take((m + 7) / 8); S.rki = take((P.n_rootent + 3) / 4 + 1);
+  S.rt8 = take((m + 7) / 8); S.rki = 0;
   S.lptr = take((2 * Y.n_lev + 4 + 1) / 2 + 1);
   S.total = off;
   int goff = 0;
@@ -395,7 +413,7 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
   S.g = gtake(m + 2); S.s = gtake(m + 2); S.zU = gtake(m + 2); S.dsc = gtake(m + 2); S.sU = gtake(m + 2);
   S.ds = gtake(m + 2); S.dy = gtake(m + 2); S.dzU = gtake(m + 2); S.gt = gtake(m + 2); S.st = gtake(m + 2);
   S.wv = gtake(m + 2); S.zL = gtake(m + 2); S.sL = gtake(m + 2); S.dzL = gtake(m + 2); S.beq = gtake(m + 2);
-  S.jt = gtake(tb->nnz_j + 2); S.gf = gtake(n + 2);
+  S.jt = gtake(tb->nnz_j + 2); S.yg = gtake(m + 2); S.sigg = gtake(m + 2);
   S.gtotal = goff;
   h->sp_smem_bytes = (size_t)off * sizeof(double);
   const void* kfn = (const void*)omg_ipm_kernel_sp;

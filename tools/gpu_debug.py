@@ -33,7 +33,9 @@ ph = slv.trace(512)[510:512].reshape(-1)
 names = ['setup/accept', 'row pass', 'col pass+reduce', 'barrier logic', 'sigma pass', 'zero+H gather',
          'W+border+rhs', 'factor:diag', 'factor:panel', 'factor:trailing', 'back solve', 'step pass',
          'line search', 'tail']
-tot = ph[:14].sum()
+tot = ph[:8].sum() + ph[10:14].sum()
+names[7:10] = ['factor (total)', '  of it: levels', '  of it: root']
+names += ['  back: root part', '  factor: gather into root']
 print('phase cycles of instance 0 (total %.0f, %d iterations -> %.0f cycles/iter):' % (tot, res['iters'][0], tot / max(1, res['iters'][0])))
-for nme, c in zip(names, ph):
+for nme, c in zip(names, ph[:16]):
     print('  %-16s %12.0f  %5.1f%%' % (nme, c, 100 * c / tot))
