@@ -1200,7 +1200,7 @@ omg_ipm_kernel(const DevTab T, const omg_options O, const Batch A, const Smem S)
 // sparse variant (omg_sp.cuh): L D L^T on the minimum-degree structure, thread streams, 128 or
 // 256 threads per instance, as many blocks per SM as shared memory allows (config 2: 3)
 #include "omg_sp.cuh"
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(128, 4)
 omg_ipm_kernel_sp(const DevTab T, const SpTab P, const omg_options O, const Batch A, const SpSmem S) {
   ipm_body_sp(T, P, O, A, S);
 }

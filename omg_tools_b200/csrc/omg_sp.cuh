@@ -21,16 +21,18 @@
 //     chunk t sits at ((t*8+k)*NT + tid) -> every warp load is one coalesced line, there are
 //     no descriptor loads, 8 independent loads are in flight per thread, and term records
 //     take 16 bytes instead of 32;
-//   * the assembled K is parked in the block's L2-resident scratch with a TMA bulk store
-//     (cp.async.bulk, SASS UBLKCP) and fetched back with a bulk load + mbarrier for the
-//     inertia-correction retries;
+//   * K is assembled in the block's L2-resident scratch (structural entries only) and STAGED
+//     into shared memory by a TMA bulk load (cp.async.bulk + mbarrier, SASS UBLKCP) over the
+//     region the Jacobian values occupied during the assembly -- factor and Jacobian share
+//     their shared memory in time, which is what lets a fourth block fit on an SM; the same
+//     load serves the inertia-correction retries;
 //   * m-vectors that are only streamed (one thread per row, coalesced) live in the L2-resident
 //     scratch; shared memory holds what is gathered at random: L, the Jacobian values, x, the
 //     parameter tape, Sigma, y.
 #pragma once
 
-#define SP_MAXROOT 48
-#define SP_RCH 2               // root: row chunks per thread
+#define SP_MAXROOT 40
+#define SP_RCH 1               // root: row chunks per thread (40 columns -> 125 chunks of 8)
 #define SP_RCW 8               // root: columns per chunk
 #define SP_MAXCOL 62           // |struct| of a column (pair delta is 6 bits)
 #define SP_MAXL 8191           // stored entries incl. zero slot (13 bits)
@@ -53,7 +55,7 @@ struct SpTab {
   const int* lev_ptr;              // [n_lev+2] slice ranges
   const uint4* fdesc;              // per slice lane: {entry word, pair offset (uint4 units), n4, 0}
                                    //   entry word: lidx | col<<13 | isdiag<<24 | eq-pivot<<25 (0xffffffff idle)
-  const uint4* fpair;              // 4 pairs per uint4, [slice][k4][lane]; pair = a | (a-b)<<13 | k<<19
+  const uint4* fpair;              // 2 pairs per uint4, [slice][k2][lane]; pair = {a8 | b8<<16, k8}: byte offsets into LK / rd
   const unsigned* root_ch;         // [SP_RCH * nt] row chunk of a thread: i | k0<<6 | cnt<<12 | eq-pivot<<16
                                    //   (root-local row i (nr = rhs), columns k0 .. k0+cnt-1; 0: none)
   const int* ksign;                // [N] +1 / -1 by permuted index
@@ -63,6 +65,8 @@ struct SpTab {
   const int* diagidx; const int* rhsidx;     // [N] L index of the diagonal / rhs entry of a column
   const int* pos_var; const int* pos_eq;     // permutation of this structure
   const int* jdst;                 // [nnz_j] L index of the border entry of an equality-row slot
+  const uint2* border; int n_border;   // equality rows: {slot | row<<16, L index}; slot 0xffff = rhs entry
+  const unsigned short* vdiag;     // [N] L index of the diagonal of permuted column j | eq-row<<15
   SpStream J, G, W, H, C, R;
 };
 
@@ -100,10 +104,12 @@ __device__ __forceinline__ void sp_bulk_s2g(void* dst_gmem, const void* src_smem
 __device__ __forceinline__ void sp_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void sp_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void sp_fence_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void sp_prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 #else
+static inline void sp_prefetch_l1(const void*) {}
 static inline void sp_mbar_init(unsigned long long* bar, unsigned) { *bar = 0; }
 static inline void sp_mbar_expect_tx(unsigned long long*, unsigned) {}
-static inline void sp_mbar_wait(unsigned long long*, unsigned) {}
+static inline void sp_mbar_wait(unsigned long long*, unsigned) { __syncthreads(); }   // every thread waits: the copy (thread 0) is done
 static inline void sp_bulk_g2s(void* d, const void* s, unsigned bytes, unsigned long long*) { memcpy(d, s, bytes); }
 static inline void sp_bulk_s2g(void* d, const void* s, unsigned bytes) { memcpy(d, s, bytes); }
 static inline void sp_bulk_wait_all() {}
@@ -186,13 +192,15 @@ static inline double sp_rcp(double x) { return 1.0 / x; }
       return;                                                                                 \
     }                                                                                         \
   }
-#define SP_PAIR(acc, r) { const int a_ = (r) & 0x1fffu; acc -= LK[a_] * rd[(r) >> 19] * LK[a_ - (int)(((r) >> 13) & 63u)]; }
-#define SP_PAIR4(pc) { SP_PAIR(v0, (pc).x) SP_PAIR(v1, (pc).y) SP_PAIR(v0, (pc).z) SP_PAIR(v1, (pc).w) }
+// pair record (8 bytes): byte offsets a8 | b8<<16 into LK, k8 into rd -- no index arithmetic
+#define SP_LDB(base, off) (*reinterpret_cast<const double*>(reinterpret_cast<const char*>(base) + (off)))
+#define SP_PAIR(acc, lo, hi) { acc -= SP_LDB(LK, (lo) & 0xffffu) * SP_LDB(rd, (hi)) * SP_LDB(LK, (lo) >> 16); }
+#define SP_PAIR4(pc) { SP_PAIR(v0, (pc).x, (pc).y) SP_PAIR(v1, (pc).z, (pc).w) }
 // descriptor of slice sl (idle if the level has no slice for this warp) / its first 16 pairs
 #define SP_FDESC(d, sl, s_end) { (d) = make_uint4(0xffffffffu, 0u, 0u, 0u); if ((sl) < (s_end)) (d) = __ldg(P.fdesc + (sl) * 32 + lane); }
+#define SP_NPF 2                 // uint4 words (2 pairs each) of every entry fetched one level ahead
 #define SP_FPAIRS(p, d) { const uint4* q_ = P.fpair + (d).y;                                   \
-    if ((d).z > 0u) (p)[0] = __ldg(q_); if ((d).z > 1u) (p)[1] = __ldg(q_ + 32);               \
-    if ((d).z > 2u) (p)[2] = __ldg(q_ + 64); if ((d).z > 3u) (p)[3] = __ldg(q_ + 96); }
+    _Pragma("unroll") for (int w_ = 0; w_ < SP_NPF; ++w_) if ((d).z > (unsigned)w_) (p)[w_] = __ldg(q_ + 32 * w_); }
 
 __device__ __forceinline__ void sp_factor(const DevTab& T, const SpTab& P, const SpSmem& S, Ctl* ctl,
                                           int* flags, const int mode, double* pc) {
@@ -211,7 +219,7 @@ __device__ __forceinline__ void sp_factor(const DevTab& T, const SpTab& P, const
   // ---- levels of the elimination tree (+ the gather into the root as level n_lev) ----
   // software pipeline over this warp's first slice of each level: descriptors two levels
   // ahead, the first 16 pairs of every entry one level ahead (independent of the numerics)
-  uint4 dA, dB, pA[4], pB[4];
+  uint4 dA, dB, pA[SP_NPF], pB[SP_NPF];
   SP_FDESC(dA, lptr[0] + warp, lptr[1])
   SP_FDESC(dB, lptr[1] + warp, (P.n_lev >= 1) ? lptr[2] : 0)
   SP_FPAIRS(pA, dA)
@@ -220,22 +228,35 @@ __device__ __forceinline__ void sp_factor(const DevTab& T, const SpTab& P, const
     const int s0 = lptr[lv], s1 = lptr[lv + 1];
     uint4 dC;
     SP_FPAIRS(pB, dB)                                       // level lv + 1
+    {   // the rest of that slice's pair block: one 128-byte line per lane into L1
+      const int nl = ((int)dB.z - SP_NPF) * 4;
+      if (lane < nl) sp_prefetch_l1(P.fpair + (dB.y - lane) + (SP_NPF * 4 + lane) * 8);
+    }
     SP_FDESC(dC, (lv + 2 <= P.n_lev) ? lptr[lv + 2] + warp : 0, (lv + 2 <= P.n_lev) ? lptr[lv + 3] : 0)
     for (int sl = s0 + warp; sl < s1; sl += NWARP) {
-      uint4 d, p[4];
-      if (sl == s0 + warp) { d = dA; p[0] = pA[0]; p[1] = pA[1]; p[2] = pA[2]; p[3] = pA[3]; }
+      uint4 d, p[SP_NPF];
+      if (sl == s0 + warp) { d = dA;
+#pragma unroll
+        for (int w = 0; w < SP_NPF; ++w) p[w] = pA[w]; }
       else { SP_FDESC(d, sl, s1) SP_FPAIRS(p, d) }
       const unsigned e = d.x;
       const int li = (e == 0xffffffffu) ? P.zslot : (int)(e & 0x1fffu);
       const int n4 = (int)d.z;
       double v0 = LK[li], v1 = 0.0;
-      if (n4 > 0) SP_PAIR4(p[0])
-      if (n4 > 1) SP_PAIR4(p[1])
-      if (n4 > 2) SP_PAIR4(p[2])
-      if (n4 > 3) SP_PAIR4(p[3])
-      for (int k = 4; k < n4; k += 4) {                    // long lists: four loads in flight
+      uint4 r[4];
+      if (n4 > SP_NPF) {                                   // the rest of a long list: four loads in flight
+        const uint4* q_ = P.fpair + d.y + SP_NPF * 32;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) if (SP_NPF + t < n4) r[t] = __ldg(q_ + t * 32);
+      }
+#pragma unroll
+      for (int w = 0; w < SP_NPF; ++w) if (n4 > w) SP_PAIR4(p[w])
+      if (n4 > SP_NPF) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) if (SP_NPF + t < n4) SP_PAIR4(r[t])
+      }
+      for (int k = SP_NPF + 4; k < n4; k += 4) {
         const uint4* q_ = P.fpair + d.y + k * 32;
-        uint4 r[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) if (k + t < n4) r[t] = __ldg(q_ + t * 32);
 #pragma unroll
@@ -250,7 +271,8 @@ __device__ __forceinline__ void sp_factor(const DevTab& T, const SpTab& P, const
     __syncthreads();
     SP_CHECK()
     dA = dB; dB = dC;
-    pA[0] = pB[0]; pA[1] = pB[1]; pA[2] = pB[2]; pA[3] = pB[3];
+#pragma unroll
+    for (int w = 0; w < SP_NPF; ++w) pA[w] = pB[w];
     if (lv == P.n_lev - 1) SP_FT(8);
   }
   SP_FT(15);
@@ -413,7 +435,7 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
   double* red = sm + S.red; double* filt = sm + S.filt;
   unsigned char* rt = reinterpret_cast<unsigned char*>(sm + S.rt8);
   double* D = A.dscr + (size_t)blockIdx.x * A.dscr_stride;
-  double* Kc = D + S.Kc;
+  double* Kg = D + S.Kc;
 #define SP_GV(name, off) double* __restrict__ name = D + (off)
   SP_GV(g, S.g); SP_GV(s, S.s); SP_GV(zU, S.zU); SP_GV(dsc, S.dsc); SP_GV(sU, S.sU); SP_GV(ds, S.ds);
   SP_GV(dy, S.dy); SP_GV(dzU, S.dzU); SP_GV(gt, S.gt); SP_GV(st, S.st); SP_GV(wv, S.wv); SP_GV(zL, S.zL);
@@ -429,6 +451,7 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
     if (tid == 0) { sp_mbar_init(&kbar, 1); sp_fence_async(); }
     if (tid == 0) { sg2[m] = 0.0; yd[m] = 0.0; wv[m] = 0.0; }
     for (int i = tid; i <= N; i += NT) rd[i] = 0.0;
+    for (int i = tid; i < P.Lsz; i += NT) Kg[i] = 0.0;      // fill positions stay zero for good
   }
   __syncthreads();
 
@@ -653,84 +676,59 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
       __syncthreads();
       TICK(4);
       // ---- I7/I8: assemble + factorise, with inertia correction -----------------------
-      bool assembled = false;
-      for (;;) {
-        if (assembled) {
-          // fetch the parked K back (TMA bulk load), shift the diagonal
-          if (tid == 0) {
-            sp_mbar_expect_tx(&kbar, (unsigned)(P.Lsz * 8));
-            sp_bulk_g2s(LK, Kc, (unsigned)(P.Lsz * 8), &kbar);
-          }
-          sp_mbar_wait(&kbar, kphase & 1u);
-          ++kphase;
-          __syncthreads();
-          for (int j = tid; j < n; j += NT) {
-            const int pj = P.pos_var[j];
-            const double v = LK[P.diagidx[pj]] + ctl.delta_w;
-            LK[P.diagidx[pj]] = v; diag0[pj] = fabs(v);
-          }
-          for (int k = tid; k < n_eq; k += NT) {
-            const int pk = P.pos_eq[k];
-            LK[P.diagidx[pk]] = -ctl.delta_c; diag0[pk] = ctl.delta_c;
-          }
-          if (tid == 0) { ctl.fail = 0; ctl.eq_fail = 0; }
-          __syncthreads();
-        } else {
-          {
-            double2* K2 = reinterpret_cast<double2*>(LK);
-            for (int q = tid; q < (P.Lsz >> 1); q += NT) K2[q] = make_double2(0.0, 0.0);
-          }
-          __syncthreads();
-          // H positions: gather J^T Sigma J (+ delta_w on the diagonal)
-          // record: s1 | s2<<16, row | (dst | diag<<13 | end<<14)<<16
-          SP_STREAM8(P.H, 0x40000000u, jval[o_.x & 0xffffu] * sg2[o_.y & 0xffffu] * jval[o_.x >> 16],
-                     { double a_ = acc_; if (o_.y & 0x20000000u) a_ += ctl.delta_w; LK[(o_.y >> 16) & 0x1fffu] = a_; })
-          __syncthreads();
-          TICK(5);
-          // Lagrangian Hessian W (lambda = y*dsc, objective factor fsc)
-          // record: a = lambda row (m: objective, m+1: padding), b = x0, c = L index
-          {
-            const double fsc_ = ctl.fsc;
+      // K is assembled in the block's L2-resident scratch Kg (structural entries only: the fill
+      // positions were zeroed once and are never written), then staged into shared memory by a
+      // TMA bulk load over the region the Jacobian values occupied -- the same load serves the
+      // inertia-correction retries.
+      {
+        // H positions: gather J^T Sigma J.  record: s1 | s2<<16, row | (dst | diag<<13 | end<<14)<<16
+        SP_STREAM8(P.H, 0x40000000u, jval[o_.x & 0xffffu] * sg2[o_.y & 0xffffu] * jval[o_.x >> 16],
+                   Kg[(o_.y >> 16) & 0x1fffu] = acc_;)
+        __syncthreads();
+        TICK(5);
+        // Lagrangian Hessian W (lambda = y*dsc, objective factor fsc)
+        // record: a = lambda row (m: objective, m+1: padding), b = x0, c = L index
+        {
+          const double fsc_ = ctl.fsc;
 #define SP_LAM(lr) (((lr) < (unsigned)m) ? yd[lr] : (((lr) == (unsigned)m) ? fsc_ : 0.0))
-            SP_STREAM16(P.W, SP_COEF(o_) * V[o_.z & 0x7fffu] * SP_LAM(o_.z >> 16) * xe[o_.w & 0xffffu],
-                        LK[o_.w >> 16] += acc_;)
+          SP_STREAM16(P.W, SP_COEF(o_) * V[o_.z & 0x7fffu] * SP_LAM(o_.z >> 16) * xe[o_.w & 0xffffu],
+                      Kg[o_.w >> 16] += acc_;)
 #undef SP_LAM
-          }
-          __syncthreads();
-          for (int j = tid; j < n; j += NT) {
-            const int pj = P.pos_var[j];
-            diag0[pj] = fabs(LK[P.diagidx[pj]]);
-          }
-          // equality border + right-hand-side entries
-          for (int k = tid; k < n_eq; k += NT) {
-            const int i = eqrow[k], pk = P.pos_eq[k];
-            const RowRec rr = T.rowrec[i];
-            const double di = dsc[i];
-            for (int q = 0; q < rr.ns; ++q) LK[P.jdst[rr.s0 + q]] = di * jval[rr.s0 + q];
-            LK[P.diagidx[pk]] = -ctl.delta_c;
-            diag0[pk] = ctl.delta_c;
-            LK[P.rhsidx[pk]] = -(g[i] - beq[i]);
-          }
-          SP_STREAM8(P.C, 0x10000u, SP_VC(jval, wv),
-                     { LK[(o_.y >> 17) & 0x1fffu] = -(gf[o_.y & 0xffffu] + acc_); })
-          if (tid == 0) { ctl.fail = 0; ctl.eq_fail = 0; }
-          __syncthreads();
-          // park the assembled K (delta = 0 ... current) for the retries: TMA bulk store
-          if (tid == 0) {
-            sp_bulk_wait_read();           // the previous store has finished reading LK
-            sp_fence_async();
-            sp_bulk_s2g(Kc, LK, (unsigned)(P.Lsz * 8));
-            sp_bulk_wait_read();
-          }
-          __syncthreads();
-          assembled = true;
         }
+        // equality border + right-hand-side entries: one record per border slot
+        // (slot | row<<16, L index; slot 0xffff: the rhs entry of the row)
+        for (int e = tid; e < P.n_border; e += NT) {
+          const uint2 b = __ldg(P.border + e);
+          const int i = (int)(b.x >> 16), sl = (int)(b.x & 0xffffu);
+          Kg[b.y] = (sl == 0xffff) ? -(g[i] - beq[i]) : dsc[i] * jval[sl];
+        }
+        SP_STREAM8(P.C, 0x10000u, SP_VC(jval, wv),
+                   { Kg[(o_.y >> 17) & 0x1fffu] = -(gf[o_.y & 0xffffu] + acc_); })
+        __threadfence();                     // Kg must have reached L2 ...
+        sp_fence_async();                    // ... and be ordered before the async-proxy read
+        __syncthreads();
+      }
+      for (;;) {
+        // stage K (TMA bulk load, mbarrier), then shift the diagonal by (delta_w, -delta_c)
+        if (tid == 0) {
+          sp_fence_async();
+          sp_mbar_expect_tx(&kbar, (unsigned)(P.Lsz * 8));
+          sp_bulk_g2s(LK, Kg, (unsigned)(P.Lsz * 8), &kbar);
+        }
+        sp_mbar_wait(&kbar, kphase & 1u);
+        ++kphase;
+        for (int pj = tid; pj < N; pj += NT) {          // vdiag: L index of the diagonal | eq-row<<15
+          const unsigned dd = __ldg(P.vdiag + pj);
+          if (dd & 0x8000u) { LK[dd & 0x7fffu] = -ctl.delta_c; diag0[pj] = ctl.delta_c; }
+          else { const double v = LK[dd] + ctl.delta_w; LK[dd] = v; diag0[pj] = fabs(v); }
+        }
+        if (tid == 0) { ctl.fail = 0; ctl.eq_fail = 0; }
+        __syncthreads();
         TICK(6);
         sp_factor(T, P, S, &ctl, fflags, O.inertia_mode, tracing ? phase_cyc : nullptr);
         TICK(7);
         if (!ctl.fail) break;
         if (tid == 0) {
-          sp_bulk_wait_all();              // the parked copy is complete in global memory
           if (ctl.eq_fail) ctl.delta_c = DELTA_C_VAL * pow(mu, DELTA_C_EXP);
           if (ctl.first_try) {
             ctl.delta_w = (ctl.delta_w_last == 0.0) ? DELTA_W0
@@ -761,7 +759,9 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
       const int sop[4] = {OP_MIN, OP_MIN, OP_SUM, OP_SUM};
       sv[0] = 1.0; sv[1] = 1.0; sv[2] = 0.0; sv[3] = 0.0;
       // J dx through the row ELL -> ds (temporarily)
-      SP_STREAM8(P.R, 0x10000u, SP_VC(jval, dx), ds[o_.y & 0xffffu] = acc_;)
+      // (the Jacobian values were overwritten by the factor: J dx straight from the terms;
+      //  record: a = x0, b = column, c = row)
+      SP_STREAM16(P.R, SP_COEF(o_) * V[o_.z & 0x7fffu] * xe[o_.z >> 16] * dx[o_.w & 0xffffu], ds[o_.w >> 16] = acc_;)
       __syncthreads();
 #pragma unroll 2
       for (int i = tid; i < m; i += NT) {
@@ -853,6 +853,8 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
       if (!accepted && O.soft_resto) {
         // ---- soft restoration (IPOPT): accept a step along the same direction if it reduces
         // the primal-dual error of the barrier problem
+        __syncthreads();
+        SP_STREAM16(P.J, SP_VJ(xe), jval[o_.w & 0xffffu] = acc_;)      // (the factor is dead by now)
         __syncthreads();
         double pv[1]; const int pop[1] = {OP_SUM};
         pv[0] = 0.0;
@@ -975,7 +977,6 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
 
     // ---- write results -------------------------------------------------------------------
     __syncthreads();
-    if (tid == 0) sp_bulk_wait_all();
     for (int i = tid; i < n; i += NT) A.x[(size_t)inst * n + i] = xe[i];
     for (int i = tid; i < m; i += NT) A.lam[(size_t)inst * m + i] = y[i] * dsc[i] / ctl.fsc;
     if (tracing && tid == 0) {

@@ -169,7 +169,7 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
 
 
   // ---- pair lists of the left-looking gather -----------------------------------------
-  std::vector<std::vector<unsigned>> plist(Y.Lsize);
+  std::vector<std::vector<uint2>> plist(Y.Lsize);
   for (int k = 0; k < R0; ++k) {
     const std::vector<int>& s = Y.st[k];
     const int base = Y.colptr[k] + 1, L = Y.len[k];
@@ -180,11 +180,11 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
         const int tgt = Y.idx(i, j);
         if (tgt < 0) { *why = "symbolic structure is not closed"; return false; }
         const unsigned a = (unsigned)(base + ai), b = (unsigned)(base + bi);
-        plist[tgt].push_back(a | ((a - b) << 13) | ((unsigned)k << 19));
+        plist[tgt].push_back(make_uint2((a * 8u) | ((b * 8u) << 16), (unsigned)k * 8u));
       }
     }
   }
-  const unsigned padpair = (unsigned)P.zslot | ((unsigned)N << 19);
+  const uint2 padpair = make_uint2(((unsigned)P.zslot * 8u) | (((unsigned)P.zslot * 8u) << 16), (unsigned)N * 8u);
   std::vector<char> is_eq_pos(N, 0);          // permuted index -> pivot of an equality row
   for (int k = 0; k < n_eq; ++k) is_eq_pos[Y.pos[n + k]] = 1;
   std::vector<int> lev_ptr;
@@ -209,17 +209,17 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
     for (size_t q0 = 0; q0 < ord.size(); q0 += 32) {
       size_t mx = 0;
       for (size_t q = q0; q < std::min(q0 + 32, ord.size()); ++q) mx = std::max(mx, plist[lidx[ord[q]]].size());
-      const unsigned n4 = (unsigned)((mx + 3) / 4);
+      const unsigned n4 = (unsigned)((mx + 1) / 2);          // uint4 words of 2 pairs
       const unsigned pbase = (unsigned)fpair.size();
-      fpair.resize(fpair.size() + (size_t)n4 * 32, make_uint4(padpair, padpair, padpair, padpair));
+      fpair.resize(fpair.size() + (size_t)n4 * 32, make_uint4(padpair.x, padpair.y, padpair.x, padpair.y));
       for (int l = 0; l < 32; ++l) {
         const size_t q = q0 + l;
         if (q >= ord.size()) { fdesc.push_back(make_uint4(0xffffffffu, pbase + l, n4, 0u)); continue; }
-        const std::vector<unsigned>& pl = plist[lidx[ord[q]]];
+        const std::vector<uint2>& pl = plist[lidx[ord[q]]];
         fdesc.push_back(make_uint4(ents[ord[q]], pbase + l, n4, 0u));
         for (size_t k = 0; k < pl.size(); ++k) {
-          uint4& w = fpair[pbase + (k / 4) * 32 + l];
-          (&w.x)[k % 4] = pl[k];
+          uint4& w = fpair[pbase + (k / 2) * 32 + l];
+          if (k % 2 == 0) { w.x = pl[k].x; w.y = pl[k].y; } else { w.z = pl[k].x; w.w = pl[k].y; }
         }
       }
     }
@@ -301,6 +301,18 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
       }
     }
     P.jdst = upload(h, jdst.data(), jdst.size(), &ok);
+    std::vector<uint2> border;
+    for (int k = 0; k < n_eq; ++k) {
+      const int i = tb->kkt_eq_rows[k];
+      for (int s = tb->jrow_ptr[i]; s < tb->jrow_ptr[i + 1]; ++s)
+        border.push_back(make_uint2((unsigned)s | ((unsigned)i << 16), (unsigned)jdst[s]));
+      border.push_back(make_uint2(0xffffu | ((unsigned)i << 16), (unsigned)rhsidx[Y.pos[n + k]]));
+    }
+    P.n_border = (int)border.size();
+    P.border = upload(h, border.data(), border.size(), &ok);
+    std::vector<unsigned short> vd(N);
+    for (int j = 0; j < N; ++j) vd[j] = (unsigned short)((unsigned)diagidx[j] | (is_eq_pos[j] ? 0x8000u : 0u));
+    P.vdiag = upload(h, vd.data(), vd.size(), &ok);
   }
   std::vector<int> hdst(std::max(tb->nnz_h, 1));
   for (int q = 0; q < tb->nnz_h; ++q) {
@@ -376,21 +388,33 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
                     [](uint2& r) { r.y |= 0x40000000u; }, nt, out, &P.H.n_chunk);
     P.H.rec = upload(h, out.data(), out.size(), &ok);
   }
-  {  // C (columns: J^T v): x = slot | row<<16, y = column;  R (rows: J dx): x = slot | col<<16, y = row
-    std::vector<std::vector<uint2>> cl(n), rl(m);
-    std::vector<uint2> cd(n), rdm(m);
+  {  // C (columns: J^T v): x = slot | row<<16, y = column | end<<16 | rhs L index<<17
+    std::vector<std::vector<uint2>> cl(n);
+    std::vector<uint2> cd(n);
     auto ctag = [&](int j) { return (unsigned)j | ((unsigned)rhsidx[Y.pos[j]] << 17); };
     for (int j = 0; j < n; ++j) cd[j] = make_uint2((unsigned)m << 16, ctag(j));
-    for (int i = 0; i < m; ++i) rdm[i] = make_uint2((unsigned)N << 16, (unsigned)i);
-    for (int s = 0; s < tb->nnz_j; ++s) {
+    for (int s = 0; s < tb->nnz_j; ++s)
       cl[tb->jcol[s]].push_back(make_uint2((unsigned)s | ((unsigned)tb->jrow[s] << 16), ctag(tb->jcol[s])));
-      rl[tb->jrow[s]].push_back(make_uint2((unsigned)s | ((unsigned)tb->jcol[s] << 16), (unsigned)tb->jrow[s]));
-    }
     auto end8 = [](uint2& r) { r.y |= 0x10000u; };
     std::vector<uint2> out;
     sp_build_stream(cl, cd, make_uint2((unsigned)m << 16, 0u), end8, nt, out, &P.C.n_chunk);
     P.C.rec = upload(h, out.data(), out.size(), &ok);
-    sp_build_stream(rl, rdm, make_uint2((unsigned)N << 16, 0u), end8, nt, out, &P.R.n_chunk);
+  }
+  {  // R (rows: J dx from the terms): a = x0, b = column, c = row
+    std::vector<std::vector<PT16>> lists(m);
+    std::vector<PT16> dum(m);
+    PT16 padr = pad16; padr.b = (unsigned short)N;
+    for (int i = 0; i < m; ++i) {
+      PT16 d = padr; d.c = (unsigned short)i; dum[i] = d;
+      for (int s = tb->jrow_ptr[i]; s < tb->jrow_ptr[i + 1]; ++s)
+        for (int t = tb->J.ptr[s]; t < tb->J.ptr[s + 1]; ++t) {
+          PT16 r; r.coef = tb->J.coef[t]; r.cidx = (unsigned short)tb->J.cidx[t];
+          r.a = (unsigned short)xi_of(tb->J, t, 0); r.b = (unsigned short)tb->jcol[s]; r.c = (unsigned short)i;
+          lists[i].push_back(r);
+        }
+    }
+    std::vector<PT16> out;
+    sp_build_stream(lists, dum, padr, end16, nt, out, &P.R.n_chunk);
     P.R.rec = upload(h, out.data(), out.size(), &ok);
   }
   if (!ok) { *why = "device allocation/upload failed"; return false; }
@@ -399,7 +423,7 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
   SpSmem& S = h->SS;
   int off = 0;
   auto take = [&](int cnt) { int o = off; off += (cnt + 1) & ~1; return o; };
-  S.LK = take(P.Lsz); S.jval = take(tb->nnz_j + 1);
+  S.LK = take(std::max(P.Lsz, tb->nnz_j + 2)); S.jval = S.LK;   // the factor is staged over the Jacobian values
   S.xe = take(n + 2); S.xt = take(N + 2); S.dx = take(N + 2); S.gf = take(n + 2);
   S.rd = take(N + 2); S.diag0 = S.rd; S.V = take(tb->n_v);   // rd holds |K_jj| until column j is pivoted
   S.sig = take(m + 2); S.y = take(m + 2);
@@ -430,7 +454,7 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
   h->sp_dscr_stride = goff + 8;
   h->sp_info = "sparse LDL^T: N=" + std::to_string(N) + " nnz(L)=" + std::to_string(Y.Lsize) +
                " levels=" + std::to_string(Y.n_lev) + " root=" + std::to_string(nr) +
-               " pairs=" + std::to_string(fpair.size() * 4) + " nt=" + std::to_string(nt) +
+               " pairs=" + std::to_string(fpair.size() * 2) + " nt=" + std::to_string(nt) +
                " ctas/SM=" + std::to_string(occ) + " smem=" + std::to_string(h->sp_smem_bytes);
   return true;
 }

@@ -49,6 +49,7 @@ extern double omg_emu_smem[];      // the running block's dynamic shared memory
 
 void omg_emu_launch(int grid, int block, size_t smem_bytes, const std::function<void()>& body);
 void __syncthreads();
+static inline void __threadfence() {}
 double __shfl_down_sync(unsigned mask, double v, int delta);
 double __shfl_sync(unsigned mask, double v, int src_lane);
 double __shfl_xor_sync(unsigned mask, double v, int lane_mask);
