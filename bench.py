@@ -37,6 +37,9 @@ def parse():
     ap.add_argument('--cpu-sample', type=int, default=0)
     ap.add_argument('--workload', default='config2', choices=sorted(WORKLOADS),
                     help='BASELINE configuration (the metric is quoted on config2)')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak: --batch instances per GPU; strong: --batch instances in total')
+    ap.add_argument('--agents', type=int, default=64, help='config3: agents of the formation')
     return ap.parse_args()
 
 
@@ -105,6 +108,32 @@ def flops_per_solve(tb, K):
     return K * (n ** 3 / 3.0 + 4 * n * n + 2 * nnz2)
 
 
+def fp64_flops_sparse(slv_info_str, K, tb):
+    """Multiply-adds the sparse kernel actually executes per solve (2 flops each): pairs of the
+    L D L^T gather x 1.5 factorisations per iteration + the J^T Sigma J gather + the term
+    streams; parsed from the library's structure report (OMG_B200_VERBOSE line)."""
+    import re
+    m = re.search(r'pairs=(\d+)', slv_info_str or '')
+    pairs = float(m.group(1)) if m else 0.0
+    nnz2 = float(np.sum(np.diff(tb.jrow_ptr).astype(float) ** 2)) / 2
+    per_iter = 1.5 * 2 * pairs * 1.5 + 2 * 2 * nnz2 + 2 * 3 * (tb.G.n_terms + 2 * tb.J.n_terms + tb.W.n_terms)
+    return K * per_iter
+
+
+def measure_fp64_peak(dev):
+    """cuBLAS DGEMM 4096^3 on this GPU, best of 5 (MEASURED_PEAKS.json has no fp64 entry)."""
+    import torch
+    a = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+    b = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+    torch.matmul(a, b)
+    best = 1e9
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize(dev)
+        best = min(best, e0.elapsed_time(e1))
+    return 2 * 4096.0 ** 3 / (best * 1e-3) / 1e12
+
+
 def measured_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -135,14 +164,28 @@ def cpu_baseline(problem, X0, P, sample, threads):
     return cpu_runner.run(problem.father.tables, X0[:sample], P[:sample], threads)
 
 
+def workload_config(args, tb, world):
+    """The `config` object: identical for the GPU arm and the reference arm of one command."""
+    B = args.batch if args.scaling == 'weak' else args.batch // world
+    return {'workload': '%s, cold solve from the linear initial guess, %s instances' %
+            (WORKLOADS[args.workload], 'jittered' if args.jitter > 0 else 'identical'),
+            'n': int(tb.n), 'm': int(tb.m), 'n_par': int(tb.n_par),
+            'batch_per_gpu': B, 'global_batch': world * B, 'tol': 1e-3,
+            'l2': 'GPU arm: flushed between timed iterations (256 MiB fill)',
+            'parallelism': 'dp%d (batch sharded, no collective)' % world}
+
+
 WORKLOADS = {
     'config1': 'config1: Holonomic Point2point (examples/p2p_holonomic.py), 10 knot intervals, '
                '1 moving circular obstacle',
     'config2': 'config2: Holonomic Point2point, 10 knot intervals, 3 circular obstacles',
+    'config3': 'config3: FormationPoint2point ADMM (metric: ADMM iterations/s)',
     'config4': 'config4: Quadrotor3D Point2point (examples/p2p_3dquadrotor.py), 10 knot '
                'intervals, 2 plate obstacles',
     'config5': 'config5: Holonomic Point2point through the revolving door '
                '(examples/revolving_door.py), 2 static + 2 rotating beams',
+    'config4_5obs': 'config4 at BASELINE size: Quadrotor3D Point2point, 10 knot intervals, '
+                    '5 plate obstacles (n=406)',
     # further models (not BASELINE configs; for kernel work on the XL path)
     'config_dubins_plain': 'Dubins Point2point, default formulation (examples/p2p_dubins.py scene, '
                            'fixed end time), cross-Hessian tables',
@@ -157,8 +200,74 @@ WORKLOADS = {
 NCU_DRAM_BYTES_PER_SOLVE = {'config2': (1.151488e6 + 1.359360e6) / 148.,
                             'config4': (3.464099e9 + 7.549988e9) / 148.}
 # bounded CPU sample: about 20 s of single-core work of the C oracle per measurement
-CPU_SAMPLE = {'config1': 2048, 'config2': 1024, 'config4': 96, 'config5': 512,
+CPU_SAMPLE = {'config1': 2048, 'config2': 1024, 'config4': 96, 'config4_5obs': 32, 'config5': 512,
               'config_dubins_plain': 256, 'config_holonomic_orient': 32, 'config_quadrotor3d_simple': 256}
+
+
+def build_problem(sc, workload, build_solver=True):
+    if workload == 'config4_5obs':
+        return sc.config4(n_obstacles=5, build_solver=build_solver)
+    return getattr(sc, workload)(build_solver=build_solver)
+
+
+def n_flat(problem):
+    """Number of leading entries of x that are the vehicle's spline coefficients."""
+    try:
+        v = problem.vehicles[0]
+        return int(v.n_spl * len(v.basis))
+    except Exception:
+        return 26
+
+
+def run_config3(args, rank, world, dev):
+    """BASELINE config 3: FormationPoint2point ADMM, --agents agents on a ring sharded over the
+    GPUs; a "step" is one ADMM iteration (batched x-update + consensus exchange + z/lambda
+    update + residual all-reduce).  Reports ADMM iterations/s and agent x-updates/s."""
+    import torch
+    import torch.distributed as dist
+    from omg_tools_b200 import scenarios as sc
+    from omg_tools_b200.problems.admm_gpu import FormationADMMRunner
+    pr = sc.config3(args.agents)
+    run = FormationADMMRunner(pr, rank=rank, world=world)
+    for _ in range(max(args.warmup, 3)):
+        run.dual_update(0.)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        res = run.dual_update(0.)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    tm = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    st, it = run.status()
+    if rank == 0:
+        ms = float(tm[0])
+        tb = pr.tb
+        line = {'metric': 'admm_iterations_per_sec', 'value': args.steps / (ms * 1e-3), 'unit': 'iterations/s',
+                'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+                'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong',
+                'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                'config': {'workload': 'config3: FormationPoint2point ADMM, %d holonomic agents on a ring, '
+                           '2 rectangular obstacles, rho = 1' % args.agents, 'n': int(tb.n), 'm': int(tb.m),
+                           'n_par': int(tb.n_par), 'agents': args.agents, 'agents_per_gpu': args.agents // world,
+                           'parallelism': 'agents sharded over %d GPUs; exchange: all-gather of x_i '
+                           '(26 doubles/agent), all-reduce of 3 residuals, all-gather of z_ij, l_ij' % world},
+                'stats': {'agent_x_updates_per_sec': args.agents * args.steps / (ms * 1e-3),
+                          'primal_residual': res[0], 'dual_residual': res[1],
+                          'x_updates_succeeded': bool((st == 0).all()),
+                          'mean_ip_iterations': float(it.mean()),
+                          'limiter': 'latency of one x-update solve (a block per agent, %d blocks per GPU on '
+                                     '%d resident slots) plus three latency-bound collectives per iteration'
+                                     % (args.agents // world, run.solver.info()['ctas_per_sm'] * run.solver.info()['n_sm'])},
+                'gpu_launches': 2 * args.steps}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def run_reference(args, rank, world):
@@ -167,11 +276,14 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from omg_tools_b200 import scenarios as sc
-    problem = getattr(sc, args.workload)(build_solver=False)
+    problem = build_problem(sc, args.workload, build_solver=False)
     cores = host_cores()
     sample = args.cpu_sample or CPU_SAMPLE[args.workload]
-    X0, P = sc.instance_data(problem, 1, jitter=0.0)
-    X0, P = np.repeat(X0, sample, 0), np.repeat(P, sample, 0)
+    if args.jitter > 0:
+        X0, P = sc.instance_data(problem, sample, jitter=args.jitter, seed=100)
+    else:
+        X0, P = sc.instance_data(problem, 1, jitter=0.0)
+        X0, P = np.repeat(X0, sample, 0), np.repeat(P, sample, 0)
     times = []
     info = None
     for k in range(args.warmup + args.steps):
@@ -188,11 +300,13 @@ def run_reference(args, rank, world):
         'warmup': args.warmup, 'ms_per_step': 1e3 * tot / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': WORKLOADS[args.workload] + ', cold solve, identical '
-                   'instances', 'sample_per_step': sample},
+        'config': workload_config(args, problem.father.tables, world),
+        'stats': {'mean_ip_iterations': float(np.mean(info['iters'])),
+                  'succeeded_frac': float(np.mean(info['status'] == 0)), 'sample_per_step': sample},
         'cpu_baseline': {'value': value, 'unit': 'solves/s', 'cores': cores,
-                         'kind': info['kind'],
-                         'sample': '%d identical %s instances per step' % (sample, args.workload)},
+                         'kind': info['kind'], 'impl': info.get('impl'),
+                         'sample': '%d %s instances of the workload per step' %
+                         (sample, 'jittered' if args.jitter > 0 else 'identical')},
         'e2e': {'value': value, 'unit': 'solves/s', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
         'gpu_launches': 0}
@@ -222,9 +336,12 @@ def main():
         dist.barrier()
     from omg_tools_b200 import scenarios as sc
     os.environ['OMG_B200_DEVICE'] = str(local)
-    problem = getattr(sc, args.workload)()
+    if args.workload == 'config3':
+        return run_config3(args, rank, world, dev)
+    os.environ['OMG_B200_VERBOSE'] = '1' if rank == 0 else ''
+    problem = build_problem(sc, args.workload)
     slv, tb = problem.problem, problem.father.tables
-    B = args.batch                      # per GPU (weak scaling)
+    B = args.batch if args.scaling == 'weak' else args.batch // world   # per GPU
     if args.jitter > 0:
         X0h, Ph = sc.instance_data(problem, B, jitter=args.jitter, seed=100 + rank)
     else:
@@ -299,22 +416,19 @@ def main():
         bps = roofline_bytes_per_solve(tb, K)
         achieved = B * bps / (kern_ms * 1e-3) / 1e9
         info = slv.info()
+        fp64_peak = measure_fp64_peak(dev)
+        slots = info['ctas_per_sm'] * info['n_sm']
+        waves = B / float(slots)
         line = {
             'metric': 'mpc_solves_per_sec', 'value': value, 'unit': 'solves/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': tot_ms / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic',
-            'config': {'workload': '%s, batch=%d/GPU, cold solve from the linear initial '
-                       'guess, %s instances' %
-                       (WORKLOADS[args.workload], B,
-                        'jittered' if args.jitter > 0 else 'identical'),
-                       'n': tb.n, 'm': tb.m, 'n_par': tb.n_par,
-                       'global_batch': world * B, 'tol': 1e-3,
-                       'mean_ip_iterations': K,
-                       'succeeded_frac': float((status == 0).mean()),
-                       'l2': 'flushed between timed iterations (256 MiB fill)',
-                       'parallelism': 'dp%d (batch sharded, no collective)' % world},
+            'config': workload_config(args, tb, world),
+            'stats': {'mean_ip_iterations': K, 'succeeded_frac': float((status == 0).mean()),
+                      'resident_slots_per_gpu': slots, 'waves': waves,
+                      'wave_efficiency': waves / float(np.ceil(waves))},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak,
                          'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': (NCU_DRAM_BYTES_PER_SOLVE[args.workload] * B
@@ -325,8 +439,16 @@ def main():
                          'model': 'staged-KKT bytes/solve = K*2*8*n(n+1)/2 + '
                                   '8(2n+n_par+3m) (SURVEY 8d); K=mean iterations',
                          'bytes_per_solve': bps,
-                         'fp64_gflops_achieved': B * flops_per_solve(tb, K) /
+                         'fp64_gflops_dense_model': B * flops_per_solve(tb, K) /
                          (kern_ms * 1e-3) / 1e9,
+                         'fp64': {'achieved_tflops': B * fp64_flops_sparse(getattr(slv, 'structure', ''), K, tb) /
+                                  (kern_ms * 1e-3) / 1e12,
+                                  'peak_tflops': fp64_peak,
+                                  'peak_source': 'cuBLAS DGEMM 4096^3 measured in this run',
+                                  'note': 'flops the sparse kernel executes (L D L^T pairs x 1.5 '
+                                          'factorisations/iteration + gathers + term streams); the '
+                                          'kernel is bound by dependent-instruction latency, not by '
+                                          'this pipe (ncu: profiles/r02_*)'},
                          'kernel_ms': kern_ms, 'smem_bytes': info['smem_bytes'],
                          'ctas_per_sm': info['ctas_per_sm']},
             'e2e': {'value': e2e_v, 'unit': 'solves/s',
@@ -341,9 +463,13 @@ def main():
             dt = time.perf_counter() - t0
             line['cpu_baseline'] = {
                 'value': sample / dt, 'unit': 'solves/s', 'cores': cores,
-                'kind': cinfo['kind'],
+                'kind': cinfo['kind'], 'impl': cinfo.get('impl'),
                 'sample': '%d instances of the same workload, %.3f s' % (sample, dt),
-                'max_abs_dx_vs_gpu': cinfo.get('max_dx')}
+                # the two arms solve the same instances: largest difference of the solutions
+                # (all variables / the vehicle's spline coefficients, which are unique)
+                'max_abs_dx_vs_gpu': float(np.abs(cinfo['x'] - res['x'][:sample]).max()),
+                'max_abs_dx_splines_vs_gpu': float(np.abs(cinfo['x'] - res['x'][:sample])[:, :n_flat(problem)].max()),
+                'iterations_equal_frac': float(np.mean(cinfo['iters'] == res['iters'][:sample]))}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -226,6 +226,10 @@ int omg_get_trace(omg_problem* h, double* out, int32_t max_rows);
 /* Introspection */
 int omg_get_info(omg_problem* h, int32_t* n, int32_t* m, int32_t* n_par,
                  int32_t* smem_bytes, int32_t* ctas_per_sm, int32_t* n_sm);
+/* Which kernel family serves this problem and its structure, as one line of text (e.g.
+ * "sparse LDL^T: N=200 nnz(L)=3861 levels=29 root=36 pairs=41088 nt=128 ctas/SM=4 smem=53104"
+ * or "envelope kernels (intermediates)").  Valid until the handle is destroyed. */
+const char* omg_structure_info(omg_problem* h);
 /* Device time (ms) and kernel-launch count of the last omg_solve_batch,
  * measured with CUDA events on the caller's stream. */
 int omg_last_timing(omg_problem* h, float* kernel_ms, int32_t* launches);

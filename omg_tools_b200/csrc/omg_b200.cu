@@ -2052,6 +2052,8 @@ int omg_get_info(omg_problem* h, int32_t* n, int32_t* m, int32_t* n_par, int32_t
   return 0;
 }
 
+const char* omg_structure_info(omg_problem* h) { return h ? h->sp_info.c_str() : ""; }
+
 int omg_solve_batch(omg_problem* h, int32_t B, const double* x0, const double* p,
                     const double* lbg, const double* ubg, int32_t bounds_shared,
                     const double* lam_g0, double* x, double* lam_g, double* f,

@@ -82,7 +82,7 @@ class _Options(C.Structure):
 EXPORTS = ['omg_abi_version', 'omg_last_error', 'omg_default_options',
            'omg_problem_create', 'omg_problem_destroy', 'omg_set_options',
            'omg_solve_batch', 'omg_solve_batch_host', 'omg_shift_batch',
-           'omg_get_trace', 'omg_get_info', 'omg_last_timing',
+           'omg_get_trace', 'omg_get_info', 'omg_structure_info', 'omg_last_timing',
            'omg_admm_zl_update', 'omg_sample_batch', 'omg_tables_read',
            'omg_tables_free', 'omg_integrate_rk4', 'omg_feas_batch', 'omg_feas_batch_host']
 
@@ -120,6 +120,8 @@ def load_library(path=None):
     lib.omg_feas_batch_host.argtypes = [vp, C.c_int32, vp, vp, vp, vp, C.c_int32, C.c_int32, vp, vp, vp]
     lib.omg_get_trace.argtypes = [vp, vp, C.c_int32]
     lib.omg_get_info.argtypes = [vp] + [_i32p] * 6
+    lib.omg_structure_info.argtypes = [vp]
+    lib.omg_structure_info.restype = C.c_char_p
     lib.omg_last_timing.argtypes = [vp, C.POINTER(C.c_float), _i32p]
     lib.omg_admm_zl_update.argtypes = [C.c_int32] * 4 + [vp] * 4 + [C.c_double] + [vp] * 8
     lib.omg_sample_batch.argtypes = [C.c_int32, C.c_int32, vp, C.c_int32] + [vp] * 7
@@ -383,6 +385,11 @@ class B200Solver(object):
         self._check(self.lib.omg_get_info(self._handle, *[C.byref(v) for v in vals]))
         keys = ('n', 'm', 'n_par', 'smem_bytes', 'ctas_per_sm', 'n_sm')
         return dict(zip(keys, [v.value for v in vals]))
+
+    @property
+    def structure(self):
+        """One-line report of the kernel family / factor structure chosen for this problem."""
+        return self.lib.omg_structure_info(self._handle).decode()
 
     def last_timing(self):
         ms, nl = C.c_float(), C.c_int32()

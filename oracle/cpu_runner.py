@@ -22,12 +22,16 @@ def _solve_one(args):
     return r.x, r.status, r.iters
 
 
-def run(tb, X0, P, threads):
+def run(tb, X0, P, threads, linear_solver='sparse'):
+    """linear_solver='sparse': L D L^T on the minimum-degree structure -- the same
+    linear-algebra work as the GPU kernel (the dense factorisation is the checker's default
+    and ~2x slower on config 2); built with -O3 -march=native (oracle/Makefile)."""
     try:
         from oracle import ipm_c
         if ipm_c.available():
-            X, st, it = ipm_c.solve_batch(tb, X0, P, threads)
-            return {'kind': 'port', 'impl': 'C', 'x': X, 'status': st, 'iters': it}
+            r = ipm_c.solve_batch_full(tb, X0, P, threads, options={'linear_solver': linear_solver})
+            return {'kind': 'port', 'impl': 'C (%s factorisation)' % linear_solver, 'x': r['x'],
+                    'status': r['status'], 'iters': r['iters']}
     except ImportError:
         pass
     ctx = mp.get_context('fork')

@@ -144,11 +144,174 @@ static void signed_solve(const double* L, int N, const double* sdyn, double* w) 
   }
 }
 
+
+/* ---------------------------------------------------------------------------
+ * Sparse alternative of the linear solver (linear_solver = 1, oracle_set_linear_solver):
+ * K = L D L^T on the fill-reducing structure the product's sparse kernel uses -- constrained
+ * minimum-degree ordering (an equality row is eligible once all variables it couples are
+ * eliminated), symbolic factorisation once per table set, then the classical up-looking
+ * numeric factorisation (elimination-tree reach per row).  Same inertia / pivot rules as
+ * signed_cholesky.  It exists so that the CPU arm of bench.py runs the SAME algorithmic
+ * work as the GPU arm (the dense factorisation above stays the checker's default).
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  int N, nnzA, nnzL;
+  int *pos;                 /* natural node (var j / n + eq k) -> permuted index */
+  int *Ap, *Ai;             /* upper triangle of permuted K by columns (row <= col), diagonal last */
+  int *hslot, *jslot, *dslot;   /* Ax slot of H position q / border slot s / diagonal j (permuted) */
+  int *Lp, *Li, *parent;    /* pattern of L (strictly lower, by columns), elimination tree */
+  int *sign;                /* +1 / -1 by permuted index */
+} SpSym;
+
+static int g_linear_solver = 0;
+void oracle_set_linear_solver(int kind) { g_linear_solver = kind; }
+
+static void spsym_free(SpSym* S) {
+  if (!S) return;
+  void* all[] = {S->pos, S->Ap, S->Ai, S->hslot, S->jslot, S->dslot, S->Lp, S->Li, S->parent, S->sign};
+  for (unsigned k = 0; k < sizeof(all) / sizeof(all[0]); ++k) free(all[k]);
+  free(S);
+}
+
+static SpSym* spsym_build(const omg_tables* T) {
+  const int n = T->n, n_eq = T->kkt_n_eq, N = n + n_eq;
+  SpSym* S = (SpSym*)calloc(1, sizeof(SpSym));
+  S->N = N;
+  char* A = (char*)calloc((size_t)N * N, 1);
+  for (int q = 0; q < T->nnz_h; ++q) { const int r = T->hrow[q], c = T->hcol[q]; if (r != c) { A[(size_t)r * N + c] = 1; A[(size_t)c * N + r] = 1; } }
+  int* pending = (int*)calloc(n_eq + 1, sizeof(int));
+  for (int k = 0; k < n_eq; ++k) {
+    const int i = T->kkt_eq_rows[k];
+    for (int s = T->jrow_ptr[i]; s < T->jrow_ptr[i + 1]; ++s) {
+      const int c = T->jcol[s];
+      if (!A[(size_t)(n + k) * N + c]) { A[(size_t)(n + k) * N + c] = 1; A[(size_t)c * N + n + k] = 1; pending[k]++; }
+    }
+  }
+  char* orig = (char*)malloc((size_t)N * N); memcpy(orig, A, (size_t)N * N);
+  int* deg = (int*)calloc(N, sizeof(int)); char* gone = (char*)calloc(N, 1);
+  for (int a = 0; a < N; ++a) for (int b = 0; b < N; ++b) deg[a] += A[(size_t)a * N + b];
+  S->pos = (int*)malloc(sizeof(int) * N);
+  int* nb = (int*)malloc(sizeof(int) * N);
+  for (int step = 0; step < N; ++step) {
+    int v = -1;
+    for (int a = 0; a < N; ++a) {
+      if (gone[a] || (a >= n && pending[a - n] > 0)) continue;
+      if (v < 0 || deg[a] < deg[v]) v = a;
+    }
+    int cnt = 0;
+    for (int b = 0; b < N; ++b) if (A[(size_t)v * N + b] && !gone[b]) nb[cnt++] = b;
+    for (int x = 0; x < cnt; ++x) for (int y = x + 1; y < cnt; ++y) {
+      const int a = nb[x], b = nb[y];
+      if (!A[(size_t)a * N + b]) { A[(size_t)a * N + b] = 1; A[(size_t)b * N + a] = 1; deg[a]++; deg[b]++; }
+    }
+    for (int x = 0; x < cnt; ++x) deg[nb[x]]--;
+    gone[v] = 1;
+    if (v < n) for (int k = 0; k < n_eq; ++k) if (orig[(size_t)(n + k) * N + v]) pending[k]--;
+    S->pos[v] = step;
+  }
+  /* upper triangle of the permuted pattern by columns (the diagonal always present, last) */
+  int* inv = (int*)malloc(sizeof(int) * N);
+  for (int a = 0; a < N; ++a) inv[S->pos[a]] = a;
+  S->Ap = (int*)calloc(N + 1, sizeof(int));
+  for (int j = 0; j < N; ++j) {
+    int c = 1;
+    for (int i = 0; i < j; ++i) if (orig[(size_t)inv[i] * N + inv[j]]) ++c;
+    S->Ap[j + 1] = S->Ap[j] + c;
+  }
+  S->nnzA = S->Ap[N];
+  S->Ai = (int*)malloc(sizeof(int) * S->nnzA);
+  S->dslot = (int*)malloc(sizeof(int) * N);
+  for (int j = 0; j < N; ++j) {
+    int p = S->Ap[j];
+    for (int i = 0; i < j; ++i) if (orig[(size_t)inv[i] * N + inv[j]]) S->Ai[p++] = i;
+    S->Ai[p] = j; S->dslot[j] = p;
+  }
+  #define SLOT_OF(pa, pb, out) { const int lo_ = (pa) < (pb) ? (pa) : (pb), hi_ = (pa) < (pb) ? (pb) : (pa); out = -1; \
+    for (int p_ = S->Ap[hi_]; p_ < S->Ap[hi_ + 1]; ++p_) if (S->Ai[p_] == lo_) { out = p_; break; } }
+  S->hslot = (int*)malloc(sizeof(int) * (T->nnz_h + 1));
+  for (int q = 0; q < T->nnz_h; ++q) SLOT_OF(S->pos[T->hrow[q]], S->pos[T->hcol[q]], S->hslot[q]);
+  S->jslot = (int*)malloc(sizeof(int) * (T->nnz_j + 1));
+  for (int s = 0; s < T->nnz_j; ++s) S->jslot[s] = -1;
+  for (int k = 0; k < n_eq; ++k) {
+    const int i = T->kkt_eq_rows[k];
+    for (int s = T->jrow_ptr[i]; s < T->jrow_ptr[i + 1]; ++s) SLOT_OF(S->pos[n + k], S->pos[T->jcol[s]], S->jslot[s]);
+  }
+  #undef SLOT_OF
+  S->sign = (int*)malloc(sizeof(int) * N);
+  for (int j = 0; j < N; ++j) S->sign[j] = 1;
+  for (int k = 0; k < n_eq; ++k) S->sign[S->pos[n + k]] = -1;
+  /* elimination tree + column counts of L (up-looking symbolic pass) */
+  S->parent = (int*)malloc(sizeof(int) * N); S->Lp = (int*)calloc(N + 1, sizeof(int));
+  int* flag = (int*)malloc(sizeof(int) * N); int* lnz = (int*)calloc(N, sizeof(int));
+  for (int k = 0; k < N; ++k) {
+    S->parent[k] = -1; flag[k] = k;
+    for (int p = S->Ap[k]; p < S->Ap[k + 1]; ++p)
+      for (int i = S->Ai[p]; i < k && flag[i] != k; i = S->parent[i]) {
+        if (S->parent[i] == -1) S->parent[i] = k;
+        lnz[i]++; flag[i] = k;
+      }
+  }
+  for (int k = 0; k < N; ++k) S->Lp[k + 1] = S->Lp[k] + lnz[k];
+  S->nnzL = S->Lp[N];
+  S->Li = (int*)malloc(sizeof(int) * (S->nnzL + 1));
+  free(A); free(orig); free(pending); free(deg); free(gone); free(nb); free(inv); free(flag); free(lnz);
+  return S;
+}
+
+/* numeric up-looking L D L^T; returns 1 on success (inertia = n_neg negatives), like signed_cholesky */
+static int sparse_ldl(const SpSym* S, const double* Ax, double* Lx, int* Li, double* D, double* Y, int* pattern,
+                      int* flag, int* lnz, int n_neg, int mode, int* eq_fail) {
+  const int N = S->N;
+  int neg = 0;
+  *eq_fail = 0;
+  for (int k = 0; k < N; ++k) {
+    Y[k] = 0.0; flag[k] = k; lnz[k] = 0;
+    int top = N;
+    for (int p = S->Ap[k]; p < S->Ap[k + 1]; ++p) {
+      int i = S->Ai[p];
+      Y[i] += Ax[p];
+      int len = 0;
+      for (; flag[i] != k; i = S->parent[i]) { pattern[len++] = i; flag[i] = k; }
+      while (len > 0) pattern[--top] = pattern[--len];
+    }
+    double dk = Y[k]; Y[k] = 0.0;
+    const double d0 = fabs(Ax[S->dslot[k]]);
+    for (; top < N; ++top) {
+      const int i = pattern[top];
+      const double yi = Y[i]; Y[i] = 0.0;
+      const int p2 = S->Lp[i] + lnz[i];
+      for (int p = S->Lp[i]; p < p2; ++p) Y[Li[p]] -= Lx[p] * yi;
+      const double lki = yi / D[i];
+      dk -= lki * yi;
+      Li[p2] = k; Lx[p2] = lki; lnz[i]++;
+    }
+    const int isneg = dk < 0.0;
+    const double piv = fabs(dk);
+    int bad;
+    if (mode) bad = (isneg != (S->sign[k] < 0)) || !(piv > ((S->sign[k] < 0) ? 0.0 : PIV_TOL * fmax(d0, 1e-300))) || !isfinite(piv);
+    else bad = !(piv > PIV_TOL * fmax(d0, 1e-300)) || !isfinite(piv);
+    if (bad) { *eq_fail = (S->sign[k] < 0); return 0; }
+    neg += isneg;
+    D[k] = dk;
+  }
+  if (mode == 0 && neg != n_neg) { *eq_fail = (neg < n_neg); return 0; }
+  return 1;
+}
+
+static void sparse_solve(const SpSym* S, const double* Lx, const int* Li, const double* D, const int* lnz, double* w) {
+  const int N = S->N;
+  for (int j = 0; j < N; ++j) { const double wj = w[j]; for (int p = S->Lp[j]; p < S->Lp[j] + lnz[j]; ++p) w[Li[p]] -= Lx[p] * wj; }
+  for (int j = 0; j < N; ++j) w[j] /= D[j];
+  for (int j = N - 1; j >= 0; --j) { double acc = w[j]; for (int p = S->Lp[j]; p < S->Lp[j] + lnz[j]; ++p) acc -= Lx[p] * w[Li[p]]; w[j] = acc; }
+}
+
 typedef struct {
   double *V, *xe, *xt, *g, *s, *y, *zL, *zU, *dsc, *sL, *sU, *beq, *sig, *wv, *ds, *dy,
          *dzL, *dzU, *gt, *st, *jval, *gf, *K, *rhs, *rx, *d0, *sol;
   int *rt, *eqidx, *eqrow;
   double *jx, *mu, *sol2, *sdyn, *wx;
+  /* sparse linear solver (sym != 0) */
+  const SpSym* sym; double *Ax, *Lx, *Dd, *Yw; int *Lis, *pat, *flg, *lnz;
 } Work;
 
 static void* xalloc(size_t n) { return calloc(n ? n : 1, 1); }
@@ -170,12 +333,22 @@ static void work_alloc(Work* w, const omg_tables* T, int Nmax) {
   w->d0 = xalloc(sizeof(double) * Nmax); w->sol = xalloc(sizeof(double) * Nmax);
   w->rt = xalloc(sizeof(int) * m); w->eqidx = xalloc(sizeof(int) * m);
   w->eqrow = xalloc(sizeof(int) * (m + 1));
+  w->sym = 0; w->Ax = w->Lx = w->Dd = w->Yw = 0; w->Lis = w->pat = w->flg = w->lnz = 0;
+}
+
+static void work_attach_sparse(Work* w, const SpSym* S) {
+  w->sym = S;
+  w->Ax = xalloc(sizeof(double) * (S->nnzA + 1)); w->Lx = xalloc(sizeof(double) * (S->nnzL + 1));
+  w->Dd = xalloc(sizeof(double) * S->N); w->Yw = xalloc(sizeof(double) * S->N);
+  w->Lis = xalloc(sizeof(int) * (S->nnzL + 1)); w->pat = xalloc(sizeof(int) * S->N);
+  w->flg = xalloc(sizeof(int) * S->N); w->lnz = xalloc(sizeof(int) * S->N);
 }
 
 static void work_free(Work* w) {
   void* all[] = {w->V, w->xe, w->xt, w->g, w->s, w->y, w->zL, w->zU, w->dsc, w->sL, w->sU, w->beq,
                  w->sig, w->wv, w->ds, w->dy, w->dzL, w->dzU, w->gt, w->st, w->jval, w->gf, w->rx,
-                 w->K, w->rhs, w->d0, w->sol, w->rt, w->eqidx, w->eqrow, w->jx, w->mu, w->sol2, w->sdyn, w->wx};
+                 w->K, w->rhs, w->d0, w->sol, w->rt, w->eqidx, w->eqrow, w->jx, w->mu, w->sol2, w->sdyn, w->wx,
+                 w->Ax, w->Lx, w->Dd, w->Yw, w->Lis, w->pat, w->flg, w->lnz};
   for (unsigned k = 0; k < sizeof(all) / sizeof(all[0]); ++k) free(all[k]);
 }
 
@@ -303,14 +476,16 @@ static void solve_one(const omg_tables* T, const omg_options* O, Work* w, const 
       for (int e = T->mu_ptr[l]; e < T->mu_ptr[l + 1]; ++e) acc += y[T->mu_row[e]] * dsc[T->mu_row[e]] * jx[T->mu_slot[e]];
       mu_mid[l] = acc;
     }
+    const SpSym* Sy = w->sym;           /* sparse linear solver: values go to the CSC slots */
+#define KH(q) (Sy ? &w->Ax[Sy->hslot[q]] : &K[(size_t)(T->kkt_pos_var[T->hrow[q]] > T->kkt_pos_var[T->hcol[q]] ? T->kkt_pos_var[T->hrow[q]] : T->kkt_pos_var[T->hcol[q]]) * N + \
+                                              (T->kkt_pos_var[T->hrow[q]] > T->kkt_pos_var[T->hcol[q]] ? T->kkt_pos_var[T->hcol[q]] : T->kkt_pos_var[T->hrow[q]])])
     for (;;) {
-      memset(K, 0, sizeof(double) * N * N);
+      if (Sy) memset(w->Ax, 0, sizeof(double) * Sy->nnzA); else memset(K, 0, sizeof(double) * N * N);
       for (int q = 0; q < T->nnz_h; ++q) {
         double acc = 0.0;
         for (int e = T->hp_ptr[q]; e < T->hp_ptr[q + 1]; ++e) acc += sig[T->hp_row[e]] * jval[T->hp_s1[e]] * jval[T->hp_s2[e]];
         if (T->hrow[q] == T->hcol[q]) acc += delta_w;
-        { const int a = T->kkt_pos_var[T->hrow[q]], b = T->kkt_pos_var[T->hcol[q]];
-          K[(a > b ? a : b) * N + (a > b ? b : a)] = acc; }
+        *KH(q) = acc;
       }
       for (int q = 0; q < T->nnz_w + T->nnz_wx; ++q) {
         double acc = 0.0; const omg_termlist* L = &T->W;
@@ -323,31 +498,32 @@ static void solve_one(const omg_tables* T, const omg_options* O, Work* w, const 
         }
         if (q >= T->nnz_w) { w->wx[q - T->nnz_w] = acc; continue; }   /* extra slot X[l,k] / M[l1,l2] */
         const int h = T->w2h[q];
-        { const int a = T->kkt_pos_var[T->hrow[h]], b = T->kkt_pos_var[T->hcol[h]];
-          K[(a > b ? a : b) * N + (a > b ? b : a)] += acc; }
+        *KH(h) += acc;
       }
       for (int e = 0; e < (T->nnz_wx ? T->n_xq : 0); ++e) {   /* X^T C + C^T X + C^T M C (include/omg_b200.h) */
         double acc = 0.0;
         for (int r = T->xq_ptr[e]; r < T->xq_ptr[e + 1]; ++r)
           acc += w->wx[T->xq_w[r]] * jx[T->xq_a[r]] * (T->xq_b[r] >= 0 ? jx[T->xq_b[r]] : 1.0);
         const int h = T->xq_h[e];
-        { const int a = T->kkt_pos_var[T->hrow[h]], b = T->kkt_pos_var[T->hcol[h]];
-          K[(a > b ? a : b) * N + (a > b ? b : a)] += acc; }
+        *KH(h) += acc;
       }
       for (int k = 0; k < n_eq; ++k) {
         const int i = eqrow[k];
-        const int pk = T->kkt_pos_eq[k];
+        const int pk = Sy ? Sy->pos[n + k] : T->kkt_pos_eq[k];
         for (int sl = T->jrow_ptr[i]; sl < T->jrow_ptr[i + 1]; ++sl) {
+          if (Sy) { w->Ax[Sy->jslot[sl]] = jval[sl]; continue; }
           const int b = T->kkt_pos_var[T->jcol[sl]];
           K[(pk > b ? pk : b) * N + (pk > b ? b : pk)] = jval[sl];
         }
-        K[pk * N + pk] = -delta_c;
+        if (Sy) w->Ax[Sy->dslot[pk]] = -delta_c; else K[pk * N + pk] = -delta_c;
         rhs[pk] = -(g[i] - beq[i]);
       }
-      for (int j = 0; j < n; ++j) rhs[T->kkt_pos_var[j]] = -gf[j];
-      for (int sl = 0; sl < T->nnz_j; ++sl) rhs[T->kkt_pos_var[T->jcol[sl]]] -= jval[sl] * wv[T->jrow[sl]];
+#define PV(j) (Sy ? Sy->pos[j] : T->kkt_pos_var[j])
+      for (int j = 0; j < n; ++j) rhs[PV(j)] = -gf[j];
+      for (int sl = 0; sl < T->nnz_j; ++sl) rhs[PV(T->jcol[sl])] -= jval[sl] * wv[T->jrow[sl]];
       int eq_fail = 0;
-      ok = signed_cholesky(K, N, T->kkt_sign, n_eq, O->inertia_mode, w->d0, w->sdyn, &eq_fail);
+      if (Sy) ok = sparse_ldl(Sy, w->Ax, w->Lx, w->Lis, w->Dd, w->Yw, w->pat, w->flg, w->lnz, n_eq, O->inertia_mode, &eq_fail);
+      else ok = signed_cholesky(K, N, T->kkt_sign, n_eq, O->inertia_mode, w->d0, w->sdyn, &eq_fail);
       if (ok) break;
       if (eq_fail) delta_c = DELTA_C_VAL * pow(mu, DELTA_C_EXP);
       if (first_try) { delta_w = (delta_w_last == 0.0) ? DELTA_W0 : fmax(DELTA_W_MIN, KAPPA_W_MINUS * delta_w_last); first_try = 0; }
@@ -356,10 +532,12 @@ static void solve_one(const omg_tables* T, const omg_options* O, Work* w, const 
     }
     if (!ok) { status = OMG_ERROR_IN_STEP_COMPUTATION; break; }
     if (delta_w > 0.0) delta_w_last = delta_w;
-    signed_solve(K, N, w->sdyn, rhs);
+    if (Sy) sparse_solve(Sy, w->Lx, w->Lis, w->Dd, w->lnz, rhs); else signed_solve(K, N, w->sdyn, rhs);
     double* dx = w->sol;   /* natural order: variables, then equality multipliers */
-    for (int j = 0; j < n; ++j) dx[j] = rhs[T->kkt_pos_var[j]];
-    for (int k = 0; k < n_eq; ++k) dx[n + k] = rhs[T->kkt_pos_eq[k]];
+    for (int j = 0; j < n; ++j) dx[j] = rhs[PV(j)];
+    for (int k = 0; k < n_eq; ++k) dx[n + k] = rhs[Sy ? Sy->pos[n + k] : T->kkt_pos_eq[k]];
+#undef PV
+#undef KH
     double a_p = 1.0, a_d = 1.0, gphi = 0.0;
     for (int i = 0; i < m; ++i) {
       const int r = rt[i]; double jd = 0.0;
@@ -495,6 +673,7 @@ typedef struct {
   const omg_tables* T; const omg_options* O; int B, shared, Nw;
   const double *x0, *p, *lbg, *ubg, *lam0; double *x, *lam, *f; int *status, *iters;
   int* next;
+  const SpSym* sym;
 } Job;
 
 static void* worker(void* arg) {
@@ -502,6 +681,7 @@ static void* worker(void* arg) {
   const omg_tables* T = J->T;
   Work w;
   work_alloc(&w, T, J->Nw);
+  if (J->sym) work_attach_sparse(&w, J->sym);
   for (;;) {
     const int b = __atomic_fetch_add(J->next, 1, __ATOMIC_RELAXED);
     if (b >= J->B) break;
@@ -527,7 +707,14 @@ int oracle_solve_batch(const omg_tables* T, const omg_options* O, int B, const d
   for (int i = 0; i < T->m; ++i) if (T->lbg[i] == T->ubg[i]) ++neq;
   int next = 0;
   Job J = {T, O, B, shared, shared ? T->n + neq + 8 : T->n + T->m, x0, p, lbg, ubg, lam0,
-           x, lam, f, status, iters, &next};
+           x, lam, f, status, iters, &next, 0};
+  SpSym* sym = 0;
+  if (g_linear_solver == 1 && shared) {     /* the structure follows the tables' equality rows */
+    int same = 1;
+    for (int i = 0; i < T->m; ++i) if ((lbg[i] == ubg[i]) != (T->lbg[i] == T->ubg[i])) same = 0;
+    if (same) sym = spsym_build(T);
+  }
+  J.sym = sym;
   if (shared) {   /* size the border from the bounds actually passed */
     int ne = 0;
     for (int i = 0; i < T->m; ++i) if (lbg[i] == ubg[i]) ++ne;
@@ -535,11 +722,12 @@ int oracle_solve_batch(const omg_tables* T, const omg_options* O, int B, const d
   }
   if (threads < 1) threads = 1;
   if (threads > B) threads = B;
-  if (threads == 1) { worker(&J); return 0; }
+  if (threads == 1) { worker(&J); spsym_free(sym); return 0; }
   pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * threads);
   for (int t = 0; t < threads; ++t) pthread_create(&th[t], 0, worker, &J);
   for (int t = 0; t < threads; ++t) pthread_join(th[t], 0);
   free(th);
+  spsym_free(sym);
   return 0;
 }
 

@@ -60,6 +60,11 @@ def solve_batch_full(tb, X0, P, threads=0, options=None, lbg=None, ubg=None,
     opt = _Options()
     lib.oracle_default_options(C.byref(opt))
     options = dict(options or {})
+    # 'dense' (the checker's default): dense L S L^T in the tables' envelope order;
+    # 'sparse': up-looking L D L^T on the minimum-degree structure, i.e. the same linear-algebra
+    # work as the product's sparse kernel -- what bench.py's CPU arm runs
+    linear_solver = options.pop('linear_solver', 'dense')
+    lib.oracle_set_linear_solver(1 if linear_solver == 'sparse' else 0)
     retry_mu = float(options.pop('retry_mu', 0.))     # host-level retry, as B200Solver.solve_batch
     feas_steps = int(options.pop('feas_steps', 30))   # host-level feasibility phase, likewise
     if _feas is False:
