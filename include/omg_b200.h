@@ -277,6 +277,41 @@ int omg_admm_zl_update(int32_t n_agents, int32_t nsh, int32_t n_nghb, int32_t L,
                        double* z_i, double* z_ij, double* l_i, double* l_ij,
                        double* res, void* stream);
 
+/* ---- multi-GPU ADMM: the consensus exchange inside the boundary ----------------------------
+ * The reference "communicates" by copying neighbours' fields in one process
+ * (omgtools/problems/admm.py:468-475); its C++ export leaves the transport to the user
+ * (update1 returns x_var and takes z_ji/l_ji, update2 takes x_j and returns z_ij/l_ij/
+ * residuals: export/point2point/admm/ADMMPoint2Point.cpp:107-117, 213-265; the test shuffles
+ * the vectors by hand, export/tests/formation/test.cpp:159-187).  Here one process per GPU
+ * holds a contiguous slice of the agents and the transport is NCCL over NVLink:
+ *
+ *   omg_comm_unique_id   rank 0: 128 opaque bytes to hand to every rank (ncclGetUniqueId)
+ *   omg_comm_create      every rank: join the communicator on `device` (ncclCommInitRank);
+ *                        n_ranks = 1 needs no id and no NCCL
+ *   omg_admm_exchange_x  after the x-update: x_j[i][k] <- x_i of agent nghb[i][k]
+ *                        (ncclAllGather of the local x_i + an index kernel)
+ *   omg_admm_zl_update_dist  omg_admm_zl_update, then ncclAllReduce of the three residual
+ *                        sums and the second exchange z_ji[i][k] <- z_ij[nghb[i][k]][back[i][k]]
+ *                        (likewise l) -- one stream-ordered call, no host synchronisation
+ *
+ * nghb / back are DEVICE int32 [n_local x n_nghb]: global agent id of neighbour k of local agent
+ * i, and the position of agent i in that neighbour's own list.  Every rank holds n_local agents
+ * (rank r: agents r*n_local ..).  NCCL is bound at run time (dlopen of libnccl.so.2, the copy a
+ * host process such as PyTorch already loaded if any): the library has no link-time dependency
+ * on it, and a single-GPU caller never touches it. */
+typedef struct omg_comm omg_comm;
+int omg_comm_unique_id(void* id128);
+omg_comm* omg_comm_create(const void* id128, int32_t n_ranks, int32_t rank, int32_t device);
+void omg_comm_destroy(omg_comm* c);
+int omg_admm_exchange_x(omg_comm* c, int32_t n_local, int32_t nsh, int32_t n_nghb,
+                        const int32_t* nghb, const double* x_i, double* x_j, void* stream);
+int omg_admm_zl_update_dist(omg_comm* c, int32_t n_local, int32_t nsh, int32_t n_nghb, int32_t L,
+                            const double* PzT, const double* cvec, const double* Tf,
+                            const double* Tb, double rho, const double* x_i, const double* x_j,
+                            double* z_i, double* z_ij, double* l_i, double* l_ij, double* res,
+                            const int32_t* nghb, const int32_t* back, double* z_ji, double* l_ji,
+                            double* res_total, void* stream);
+
 /* Table files: the on-disk form of omg_tables, the stand-in for the nlp.c / nlp.so
  * bundle that the reference's exporter writes for its C++ runtime
  * (omgtools/export/export_p2p.py:43-60 -> Point2Point.cpp:80-91 nlpsol("problem",

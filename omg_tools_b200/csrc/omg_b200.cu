@@ -2298,4 +2298,157 @@ int omg_admm_zl_update(int32_t n_agents, int32_t nsh, int32_t n_nghb, int32_t L,
   return 0;
 }
 
+// ---- multi-GPU ADMM exchange (NCCL bound at run time) -----------------------------------------
+struct omg_comm {
+  int n_ranks = 1, rank = 0, device = 0;
+  void* nccl = nullptr;                 // ncclComm_t
+  double* gx = nullptr; double* gz = nullptr; double* gl = nullptr; size_t cap_x = 0, cap_z = 0;
+};
+
+}  // extern "C" (reopened below)
+
+#ifndef OMG_CPU_EMU
+#include <dlfcn.h>
+#endif
+struct OmgNcclId { char internal[128]; };      // layout of ncclUniqueId
+namespace {
+struct NcclApi {
+  bool ok = false;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, OmgNcclId /* ncclUniqueId by value */, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+const int kNcclFloat64 = 8, kNcclSum = 0;
+
+bool nccl_bind() {
+#ifdef OMG_CPU_EMU
+  return false;
+#else
+  if (g_nccl.ok) return true;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);   // the host process' copy, if any
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) { set_err("NCCL not found (dlopen libnccl.so.2)"); return false; }
+  *(void**)(&g_nccl.GetUniqueId) = dlsym(lib, "ncclGetUniqueId");
+  *(void**)(&g_nccl.CommInitRank) = dlsym(lib, "ncclCommInitRank");
+  *(void**)(&g_nccl.CommDestroy) = dlsym(lib, "ncclCommDestroy");
+  *(void**)(&g_nccl.AllGather) = dlsym(lib, "ncclAllGather");
+  *(void**)(&g_nccl.AllReduce) = dlsym(lib, "ncclAllReduce");
+  *(void**)(&g_nccl.GetErrorString) = dlsym(lib, "ncclGetErrorString");
+  g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.AllGather &&
+              g_nccl.AllReduce && g_nccl.GetErrorString;
+  if (!g_nccl.ok) set_err("libnccl lacks a required symbol");
+  return g_nccl.ok;
+#endif
+}
+#define NK(call) do { int r_ = (call); if (r_ != 0) { set_err(std::string(#call) + ": " + g_nccl.GetErrorString(r_)); return -1; } } while (0)
+
+// dst[i][k][:] = src[idx_a[i][k]] [ idx_b ? idx_b[i][k] : - ] [:]  (rows of `len` doubles)
+__global__ void omg_gather_rows_kernel(int n_rows, int len, int stride_a, const int* __restrict__ ia,
+                                       const int* __restrict__ ib, const double* __restrict__ src,
+                                       double* __restrict__ dst) {
+  const int r = blockIdx.x;
+  if (r >= n_rows) return;
+  const size_t base = (size_t)ia[r] * stride_a + (ib ? (size_t)ib[r] * len : 0);
+  for (int q = threadIdx.x; q < len; q += blockDim.x) dst[(size_t)r * len + q] = src[base + q];
+}
+__global__ void omg_colsum3_kernel(int n, const double* __restrict__ res, double* __restrict__ out) {
+  double a = 0.0;
+  for (int i = 0; i < n; ++i) a += res[(size_t)i * 3 + threadIdx.x];   // fixed order: deterministic
+  out[threadIdx.x] = a;
+}
+}  // namespace
+
+extern "C" {
+
+int omg_comm_unique_id(void* id128) {
+  if (!id128) { set_err("null buffer"); return -1; }
+  if (!nccl_bind()) return -1;
+  NK(g_nccl.GetUniqueId(id128));
+  return 0;
+}
+
+omg_comm* omg_comm_create(const void* id128, int32_t n_ranks, int32_t rank, int32_t device) {
+  if (n_ranks < 1 || rank < 0 || rank >= n_ranks) { set_err("bad rank / n_ranks"); return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess) { set_err("cudaSetDevice failed"); return nullptr; }
+  omg_comm* c = new omg_comm();
+  c->n_ranks = n_ranks; c->rank = rank; c->device = device;
+  if (n_ranks > 1) {
+    if (!id128 || !nccl_bind()) { if (!id128) set_err("null unique id"); delete c; return nullptr; }
+    OmgNcclId id; memcpy(&id, id128, sizeof id);
+    const int r = g_nccl.CommInitRank(&c->nccl, n_ranks, id, rank);
+    if (r != 0) { set_err(std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r)); delete c; return nullptr; }
+  }
+  return c;
+}
+
+void omg_comm_destroy(omg_comm* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->nccl && g_nccl.ok) g_nccl.CommDestroy(c->nccl);
+  if (c->gx) cudaFree(c->gx);
+  if (c->gz) cudaFree(c->gz);
+  if (c->gl) cudaFree(c->gl);
+  delete c;
+}
+
+static int comm_reserve(omg_comm* c, size_t nx, size_t nz) {
+  if (nx > c->cap_x) { if (c->gx) cudaFree(c->gx); c->gx = nullptr; CK(cudaMalloc(&c->gx, nx * 8)); c->cap_x = nx; }
+  if (nz > c->cap_z) {
+    if (c->gz) cudaFree(c->gz); if (c->gl) cudaFree(c->gl); c->gz = c->gl = nullptr;
+    CK(cudaMalloc(&c->gz, nz * 8)); CK(cudaMalloc(&c->gl, nz * 8)); c->cap_z = nz;
+  }
+  return 0;
+}
+
+int omg_admm_exchange_x(omg_comm* c, int32_t n_local, int32_t nsh, int32_t n_nghb, const int32_t* nghb,
+                        const double* x_i, double* x_j, void* stream_) {
+  if (!c || !nghb || !x_i || !x_j) { set_err("null argument"); return -1; }
+  if (n_local <= 0) return 0;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CK(cudaSetDevice(c->device));
+  const double* all = x_i;
+  if (c->n_ranks > 1) {
+    if (comm_reserve(c, (size_t)c->n_ranks * n_local * nsh, 0)) return -1;
+    NK(g_nccl.AllGather(x_i, c->gx, (size_t)n_local * nsh, kNcclFloat64, c->nccl, stream));
+    all = c->gx;
+  }
+  OMG_LAUNCH(omg_gather_rows_kernel, n_local * n_nghb, 32, 0, stream, n_local * n_nghb, nsh, nsh, nghb,
+             (const int*)nullptr, all, x_j);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int omg_admm_zl_update_dist(omg_comm* c, int32_t n_local, int32_t nsh, int32_t n_nghb, int32_t L,
+                            const double* PzT, const double* cvec, const double* Tf, const double* Tb,
+                            double rho, const double* x_i, const double* x_j, double* z_i, double* z_ij,
+                            double* l_i, double* l_ij, double* res, const int32_t* nghb, const int32_t* back,
+                            double* z_ji, double* l_ji, double* res_total, void* stream_) {
+  if (!c || !nghb || !back || !z_ji || !l_ji || !res_total) { set_err("null argument"); return -1; }
+  if (n_local <= 0) return 0;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CK(cudaSetDevice(c->device));
+  if (omg_admm_zl_update(n_local, nsh, n_nghb, L, PzT, cvec, Tf, Tb, rho, x_i, x_j, z_i, z_ij, l_i, l_ij,
+                         res, stream_)) return -1;
+  OMG_LAUNCH(omg_colsum3_kernel, 1, 3, 0, stream, n_local, res, res_total);
+  CK(cudaGetLastError());
+  const double* allz = z_ij; const double* alll = l_ij;
+  if (c->n_ranks > 1) {
+    const size_t cnt = (size_t)n_local * n_nghb * nsh;
+    if (comm_reserve(c, 0, (size_t)c->n_ranks * cnt)) return -1;
+    NK(g_nccl.AllReduce(res_total, res_total, 3, kNcclFloat64, kNcclSum, c->nccl, stream));
+    NK(g_nccl.AllGather(z_ij, c->gz, cnt, kNcclFloat64, c->nccl, stream));
+    NK(g_nccl.AllGather(l_ij, c->gl, cnt, kNcclFloat64, c->nccl, stream));
+    allz = c->gz; alll = c->gl;
+  }
+  OMG_LAUNCH(omg_gather_rows_kernel, n_local * n_nghb, 32, 0, stream, n_local * n_nghb, nsh, n_nghb * nsh, nghb, back, allz, z_ji);
+  OMG_LAUNCH(omg_gather_rows_kernel, n_local * n_nghb, 32, 0, stream, n_local * n_nghb, nsh, n_nghb * nsh, nghb, back, alll, l_ji);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 }  // extern "C"

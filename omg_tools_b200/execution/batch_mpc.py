@@ -161,7 +161,8 @@ def _adapter_for(vehicle):
 
 class BatchMPC(object):
 
-    def __init__(self, problem, batch, update_time=0.1, jitter=0.0, seed=0, device_predict=True):
+    def __init__(self, problem, batch, update_time=0.1, jitter=0.0, seed=0, device_predict=True,
+                 device=None):
         import torch
         self.device_predict = device_predict
         self.torch = torch
@@ -175,9 +176,7 @@ class BatchMPC(object):
         self.obstacles = problem.environment.obstacles
         self.T = problem.options['horizon_time']
         self.knot_time = problem.knot_time
-        from ..solver import b200 as _b200
-        dev = torch.device('cpu') if _b200.is_emulation(self.solver.lib) else \
-            torch.device('cuda', self.solver.device)     # (CPU: kernel emulation, tests only)
+        dev = device if device is not None else torch.device('cuda', self.solver.device)
         self.dev = dev
         rng = np.random.default_rng(seed)
         n, m = self.tb.n, self.tb.m

@@ -84,10 +84,8 @@ class FormationADMMRunner(object):
         self.ex = AgentExchange(problem.N, problem.nghb, problem.back, rank, world, group)
         lo, hi = self.ex.lo, self.ex.hi
         self.lo, self.hi = lo, hi
-        if b200.is_emulation(self.solver.lib):      # CPU emulation of the kernels (tests only)
-            dev = torch.device('cpu')
-        else:
-            dev = torch.device('cuda', self.solver.device if device is None else device)
+        dev = device if isinstance(device, torch.device) else \
+            torch.device('cuda', self.solver.device if device is None else device)
         self.dev = dev
         td = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
         p = problem
@@ -112,14 +110,28 @@ class FormationADMMRunner(object):
         self.time_prev = 0.
         self.history = []
         self.alpha, self.c_res_p = 1., None      # Nesterov state
+        # on GPUs the exchange runs inside the C ABI (omg_admm_exchange_x / omg_admm_zl_update_dist:
+        # NCCL all-gather + index kernel + residual all-reduce, one stream, no host round trip);
+        # the torch.distributed exchange above serves the gloo CPU tests
+        self.comm = None
+        self._par_t = None
+        self._tf_t = None
+        if dev.type == 'cuda' and not bool(problem.options.get('nesterov_acceleration')):
+            self.comm = b200.AdmmComm(rank, world, dev.index, group)
+            self.nghb_d = torch.as_tensor(np.ascontiguousarray(problem.nghb[lo:hi], dtype=np.int32), device=dev)
+            self.back_d = torch.as_tensor(np.ascontiguousarray(problem.back[lo:hi], dtype=np.int32), device=dev)
+            self.res_total = torch.zeros(3, dtype=torch.float64, device=dev)
 
     # ------------------------------------------------------------------
     def _pack_parameters(self, t):
         """Host builds the constant part; consensus parameters are written on
         the device (they never leave it)."""
         p, torch = self.pr, self.torch
-        host = p.pack_parameters(t)[self.lo:self.hi]
-        self.P.copy_(torch.from_numpy(np.ascontiguousarray(host)))
+        if self._par_t != t:            # the host part only changes with the time
+            host = p.pack_parameters(t)[self.lo:self.hi]
+            self._P_host = torch.from_numpy(np.ascontiguousarray(host)).to(self.dev)
+            self._par_t = t
+        self.P.copy_(self._P_host)
         off, a = p.par_off, p.upd_label
         n_loc, nsh, nn = self.hi - self.lo, p.nsh, p.n_nghb
         self.P[:, off[(a, 'z_i')]:off[(a, 'z_i')] + nsh] = self.z_i
@@ -135,8 +147,10 @@ class FormationADMMRunner(object):
             setattr(self, name, (a.reshape(-1, L) @ Ts.T).reshape(a.shape).contiguous())
         self.solver.shift_batch_device(self.X, self.blocks)
 
-    def dual_update(self, t):
-        """One ADMM iteration at (relative) time t; returns (p_res, d_res, c_res)."""
+    def dual_update(self, t, fetch=True):
+        """One ADMM iteration at (relative) time t; returns (p_res, d_res, c_res) -- or, with
+        fetch=False on the native path, nothing: the residuals stay on the device
+        (``self.res_total``) and the iteration needs no host synchronisation."""
         p, torch = self.pr, self.torch
         if (t > 0. and int(np.round(self.time_prev / p.knot_time, 6)) <
                 int(np.round(t / p.knot_time, 6))):
@@ -148,12 +162,27 @@ class FormationADMMRunner(object):
                                        self.F, self.ST, self.IT)
         self.X, self.Xn = self.Xn, self.X
         self.x_i = self.X[:, p.x_off:p.x_off + p.nsh].contiguous()
+        if self._tf_t != t:
+            Tf, Tb = p.first_knot_transforms(t)
+            self._Tf_d = torch.tensor(Tf, dtype=torch.float64, device=self.dev)
+            self._Tb_d = torch.tensor(Tb, dtype=torch.float64, device=self.dev)
+            self._tf_t = t
+        Tf_d, Tb_d = self._Tf_d, self._Tb_d
+        if self.comm is not None:
+            # exchange 1, consensus kernel, residual all-reduce, exchange 2: all inside the C ABI
+            self.comm.exchange_x(self.nghb_d, self.x_i, self.x_j)
+            self.comm.zl_update(self.PzT, self.c, Tf_d, Tb_d, p.options['rho'], self.x_i, self.x_j,
+                                self.z_i, self.z_ij, self.l_i, self.l_ij, self.res, p.L,
+                                self.nghb_d, self.back_d, self.z_ji, self.l_ji, self.res_total)
+            if not fetch:
+                return None
+            tot = self.res_total.cpu().numpy()
+            out = (float(np.sqrt(tot[0])), float(np.sqrt(tot[1])), float(tot[2]))
+            self.history.append(out)
+            return out
         # communicate x
         self.x_j = self.ex.gather_x(self.x_i)
         # z / lambda / residuals
-        Tf, Tb = p.first_knot_transforms(t)
-        Tf_d = torch.tensor(Tf, dtype=torch.float64, device=self.dev)
-        Tb_d = torch.tensor(Tb, dtype=torch.float64, device=self.dev)
         nesterov = bool(p.options.get('nesterov_acceleration'))
         if nesterov:
             prev = [a.clone() for a in (self.z_i, self.z_ij, self.l_i, self.l_ij)]

@@ -84,23 +84,30 @@ EXPORTS = ['omg_abi_version', 'omg_last_error', 'omg_default_options',
            'omg_solve_batch', 'omg_solve_batch_host', 'omg_shift_batch',
            'omg_get_trace', 'omg_get_info', 'omg_structure_info', 'omg_last_timing',
            'omg_admm_zl_update', 'omg_sample_batch', 'omg_tables_read',
-           'omg_tables_free', 'omg_integrate_rk4', 'omg_feas_batch', 'omg_feas_batch_host']
+           'omg_tables_free', 'omg_integrate_rk4', 'omg_feas_batch', 'omg_feas_batch_host',
+           'omg_comm_unique_id', 'omg_comm_create', 'omg_comm_destroy', 'omg_admm_exchange_x',
+           'omg_admm_zl_update_dist']
 
 _lib = None
 
 
-def load_library(path=None):
-    """Load libomgb200.so (built by __graft_entry__.build() / csrc/Makefile)."""
+def load_library():
+    """Load libomgb200.so (built by __graft_entry__.build() / csrc/Makefile).  There is exactly
+    one library and no fallback: a missing build raises."""
     global _lib
-    if _lib is not None and path is None:
+    if _lib is not None:
         return _lib
-    path = path or LIB_PATH
-    if not os.path.exists(path):
+    if not os.path.exists(LIB_PATH):
         raise RuntimeError(
             'libomgb200.so not found at %s: build it with '
             '`python -c "import __graft_entry__ as g; g.build()"` '
-            '(there is no CPU fallback)' % path)
-    lib = C.CDLL(path)
+            '(there is no CPU fallback)' % LIB_PATH)
+    _lib = bind(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def bind(lib):
+    """Declare the C signatures of include/omg_b200.h on a loaded library object."""
     lib.omg_abi_version.restype = C.c_int
     lib.omg_last_error.restype = C.c_char_p
     lib.omg_default_options.argtypes = [C.POINTER(_Options)]
@@ -122,6 +129,13 @@ def load_library(path=None):
     lib.omg_get_info.argtypes = [vp] + [_i32p] * 6
     lib.omg_structure_info.argtypes = [vp]
     lib.omg_structure_info.restype = C.c_char_p
+    lib.omg_comm_unique_id.argtypes = [vp]
+    lib.omg_comm_create.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
+    lib.omg_comm_create.restype = C.c_void_p
+    lib.omg_comm_destroy.argtypes = [vp]
+    lib.omg_comm_destroy.restype = None
+    lib.omg_admm_exchange_x.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp]
+    lib.omg_admm_zl_update_dist.argtypes = [vp] + [C.c_int32] * 4 + [vp] * 4 + [C.c_double] + [vp] * 13
     lib.omg_last_timing.argtypes = [vp, C.POINTER(C.c_float), _i32p]
     lib.omg_admm_zl_update.argtypes = [C.c_int32] * 4 + [vp] * 4 + [C.c_double] + [vp] * 8
     lib.omg_sample_batch.argtypes = [C.c_int32, C.c_int32, vp, C.c_int32] + [vp] * 7
@@ -130,7 +144,6 @@ def load_library(path=None):
     lib.omg_tables_read.restype = C.POINTER(_Tables)
     lib.omg_tables_free.argtypes = [C.POINTER(_Tables)]
     lib.omg_tables_free.restype = None
-    _lib = lib
     return lib
 
 
@@ -138,23 +151,20 @@ def _ptr(arr, typ):
     return arr.ctypes.data_as(typ)
 
 
-def is_emulation(lib=None):
-    """True only for the CPU emulation build of the kernel source (tools/cpu_emu, test
-    infrastructure), whose device pointers are host pointers."""
-    return hasattr(lib or load_library(), 'omg_is_emulation')
-
-
 def _check_device_tensors(tensors, lib=None):
-    """Device-pointer API: contiguous float64 CUDA tensors -- or CPU tensors when (and only
-    when) the loaded library is the CPU emulation.  Returns the stream handle to pass."""
+    """Device-pointer API: contiguous float64 CUDA tensors, nothing else."""
     import torch
-    on_gpu = tensors[0].is_cuda
-    if not on_gpu and not is_emulation(lib):
-        raise ValueError('expected contiguous float64 CUDA tensors')
     for t in tensors:
-        if t.dtype != torch.float64 or t.is_cuda != on_gpu or not t.is_contiguous():
+        if t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous():
             raise ValueError('expected contiguous float64 CUDA tensors')
-    return on_gpu
+    return True
+
+
+def _check_int_tensors(tensors):
+    import torch
+    for t in tensors:
+        if t.dtype != torch.int32 or not t.is_cuda or not t.is_contiguous():
+            raise ValueError('expected contiguous int32 CUDA tensors')
 
 
 def _stream_handle(on_gpu, device, stream):
@@ -454,8 +464,9 @@ class B200Solver(object):
             lb_i, ub_i = (lbg, ubg) if shared else (lbg[idx], ubg[idx])
             x1, _, _ = self.feasibility_batch(X[idx], P[idx], lb_i, ub_i, n_feas)
             r2 = self.solve_batch(x1, P[idx], lb_i, ub_i, None, _retry=False)
+            ok = r2['status'] == 0          # the first result stands unless the re-solve succeeds
             for key in ('x', 'lam_g', 'f', 'status'):
-                res[key][idx] = r2[key]
+                res[key][idx[ok]] = r2[key][ok]
             res['iters'][idx] += r2['iters']
         mu_r = getattr(self, '_retry_mu', 0.)
         if _retry and mu_r > 0. and (status != 0).any():
@@ -497,7 +508,13 @@ class B200Solver(object):
         """torch CUDA tensors (float64 / int32, contiguous); asynchronous on
         ``stream`` (torch.cuda.Stream or None = current)."""
         B = X0.shape[0]
-        on_gpu = _check_device_tensors((X0, P, LBG, UBG, X, LAM, F), self.lib)
+        on_gpu = _check_device_tensors((X0, P, LBG, UBG, X, LAM, F) +
+                                       ((lam_g0,) if lam_g0 is not None else ()), self.lib)
+        _check_int_tensors((STATUS, ITERS))
+        if (X0.shape != (B, self.n) or P.shape != (B, self.n_par) or X.shape != (B, self.n) or
+                LAM.shape != (B, self.m) or F.numel() != B or STATUS.numel() != B or ITERS.numel() != B or
+                (lam_g0 is not None and lam_g0.shape != (B, self.m))):
+            raise ValueError('tensor shapes do not match the batch / problem sizes')
         shared = 1 if LBG.dim() == 1 else 0
         self._check(self.lib.omg_solve_batch(
             self._handle, B, X0.data_ptr(), P.data_ptr(), LBG.data_ptr(),
@@ -555,6 +572,58 @@ def admm_zl_update(PzT, c, Tf, Tb, rho, x_i, x_j, z_i, z_ij, l_i, l_ij, res, L, 
                                 _stream_handle(on_gpu, x_i.device, stream))
     if rc != 0:
         raise RuntimeError('libomgb200: %s' % lib.omg_last_error().decode())
+
+
+class AdmmComm(object):
+    """The library's NCCL communicator for the formation ADMM exchange (include/omg_b200.h:
+    omg_comm_*).  The 128-byte unique id is created on rank 0 and handed to the other ranks by
+    the caller's bootstrap -- here a torch.distributed broadcast; a C++ caller uses whatever it
+    has (MPI, a socket, a file)."""
+
+    def __init__(self, rank=0, world=1, device=0, group=None):
+        import torch
+        self.lib = load_library()
+        idbuf = (C.c_char * 128)()
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.zeros(128, dtype=torch.uint8, device=torch.device('cuda', device))
+            if rank == 0:
+                if self.lib.omg_comm_unique_id(idbuf) != 0:
+                    raise RuntimeError('libomgb200: %s' % self.lib.omg_last_error().decode())
+                t.copy_(torch.frombuffer(bytearray(idbuf.raw), dtype=torch.uint8))
+            dist.broadcast(t, src=0, group=group)
+            idbuf.raw = bytes(t.cpu().numpy().tobytes())
+        self.handle = self.lib.omg_comm_create(idbuf, world, rank, device)
+        if not self.handle:
+            raise RuntimeError('libomgb200: %s' % self.lib.omg_last_error().decode())
+        self.rank, self.world, self.device = rank, world, device
+
+    def exchange_x(self, nghb, x_i, x_j, stream=None):
+        n_local, nsh = x_i.shape
+        rc = self.lib.omg_admm_exchange_x(self.handle, n_local, nsh, x_j.shape[1], nghb.data_ptr(),
+                                          x_i.data_ptr(), x_j.data_ptr(), _stream_handle(True, x_i.device, stream))
+        if rc != 0:
+            raise RuntimeError('libomgb200: %s' % self.lib.omg_last_error().decode())
+
+    def zl_update(self, PzT, c, Tf, Tb, rho, x_i, x_j, z_i, z_ij, l_i, l_ij, res, L, nghb, back,
+                  z_ji, l_ji, res_total, stream=None):
+        """Consensus kernel + residual all-reduce + second exchange, one stream-ordered call."""
+        n_local, nsh = x_i.shape
+        rc = self.lib.omg_admm_zl_update_dist(
+            self.handle, n_local, nsh, x_j.shape[1], L, PzT.data_ptr(), c.data_ptr(), Tf.data_ptr(),
+            Tb.data_ptr(), float(rho), x_i.data_ptr(), x_j.data_ptr(), z_i.data_ptr(), z_ij.data_ptr(),
+            l_i.data_ptr(), l_ij.data_ptr(), res.data_ptr(), nghb.data_ptr(), back.data_ptr(),
+            z_ji.data_ptr(), l_ji.data_ptr(), res_total.data_ptr(), _stream_handle(True, x_i.device, stream))
+        if rc != 0:
+            raise RuntimeError('libomgb200: %s' % self.lib.omg_last_error().decode())
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.omg_comm_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
 
 
 def sample_batch(X, blocks, stream=None):

@@ -94,15 +94,19 @@ def solve_batch_full(tb, X0, P, threads=0, options=None, lbg=None, ubg=None,
         idx = np.nonzero(st == 2)[0]
         lb_i, ub_i = (lb, ub) if shared else (lb[idx], ub[idx])
         x1, _, _ = feas_batch(tb, X[idx], P[idx], lb_i, ub_i, feas_steps)
-        r2 = solve_batch_full(tb, x1, P[idx], threads, dict(options), lb_i, ub_i, None, _feas=False)
+        opts2 = dict(options)
+        opts2['linear_solver'] = linear_solver
+        r2 = solve_batch_full(tb, x1, P[idx], threads, opts2, lb_i, ub_i, None, _feas=False)
+        ok = r2['status'] == 0              # as B200Solver.solve_batch: keep the first result otherwise
         for key in ('x', 'lam_g', 'f', 'status'):
-            res[key][idx] = r2[key]
+            res[key][idx[ok]] = r2[key][ok]
         res['iters'][idx] += r2['iters']
         st = res['status']
     if retry_mu > 0. and (st != 0).any():
         idx = np.nonzero(st != 0)[0]
         opts2 = dict(options)
         opts2['mu_init'] = retry_mu
+        opts2['linear_solver'] = linear_solver
         r2 = solve_batch_full(tb, X0[idx], P[idx], threads, opts2,
                               lb if shared else lb[idx], ub if shared else ub[idx],
                               None if lam0 is None else lam0[idx])

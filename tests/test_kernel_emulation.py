@@ -17,24 +17,20 @@ from omg_tools_b200.solver import b200
 from oracle import ipm_c
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-EMU_DIR = os.path.join(ROOT, 'tools', 'cpu_emu')
-EMU_LIB = os.path.join(EMU_DIR, '_build', 'libomgb200_emu.so')
+import sys
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import emu_support                       # noqa: E402
+EMU_LIB = emu_support.EMU_LIB
+CPU = None
 
 
 @pytest.fixture(scope='module')
 def emu():
-    src = [os.path.join(ROOT, 'omg_tools_b200', 'csrc', 'omg_b200.cu'),
-           os.path.join(ROOT, 'include', 'omg_b200.h'),
-           os.path.join(EMU_DIR, 'cuda_runtime.h'), os.path.join(EMU_DIR, 'emu_runtime.cpp')]
-    if (not os.path.exists(EMU_LIB) or
-            any(os.path.getmtime(s) > os.path.getmtime(EMU_LIB) for s in src)):
-        subprocess.check_call([os.path.join(EMU_DIR, 'build.sh')])
     if not ipm_c.available():
         pytest.skip('C oracle not built')
-    saved = b200._lib
-    lib = b200.load_library(EMU_LIB)          # B200Solver objects built below bind to it
-    yield lib
-    b200._lib = saved                          # the product library for everything else
+    saved = emu_support.activate()            # B200Solver objects built below bind to it
+    yield b200._lib
+    emu_support.restore(saved)                # the product library for everything else
 
 
 def _compare(pr, B, jitter, seed, n_flat, options=None):
@@ -48,11 +44,11 @@ def _compare(pr, B, jitter, seed, n_flat, options=None):
 
 
 @pytest.mark.parametrize('kernel, name, B, layout', [
-    ('sparse', 'config1', 3, (38240, 5)), ('sparse', 'config2', 2, (75232, 3)), ('sparse', 'config5', 2, None),
+    ('sparse', 'config1', 3, (27472, 8)), ('sparse', 'config2', 2, (53104, 4)), ('sparse', 'config5', 2, None),
     ('envelope', 'config1', 3, (97408, 2)), ('envelope', 'config2', 2, (113552, 2)), ('envelope', 'config5', 2, None)])
 def test_standard_kernel_matches_oracle(emu, monkeypatch, kernel, name, B, layout):
     """BASELINE configs 1, 2, 5 through both kernel families: omg_ipm_kernel_sp (sparse
-    L D L^T on the minimum-degree structure, thread streams, 128 threads, 3 blocks/SM for
+    L D L^T on the minimum-degree structure, thread streams, 128 threads, 4 blocks/SM for
     config 2) and omg_ipm_kernel_2cta (envelope factorisation, 256 threads, 2 blocks/SM):
     same statuses and iteration counts as the C oracle, solutions to rounding."""
     if kernel == 'envelope':
@@ -423,8 +419,8 @@ def test_device_pointer_api_on_cpu_tensors(emu):
     import torch
     from omg_tools_b200.problems.admm_gpu import FormationADMMRunner
     from oracle.admm_ref import ADMMOracle
-    assert b200.is_emulation(emu)
-    run = FormationADMMRunner(sc.config3(4))
+    assert hasattr(emu, 'omg_is_emulation')
+    run = FormationADMMRunner(sc.config3(4), device=torch.device('cpu'))
     orc = ADMMOracle(sc.config3(4, build_solver=False))
     for it in range(4):
         rg, ro = run.dual_update(0.), orc.dual_update(0.)
@@ -440,9 +436,10 @@ def _admm_rank(rank, world, port, out):
     import torch.distributed as dist
     os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
-    b200.load_library(EMU_LIB)
+    emu_support.activate()
     from omg_tools_b200.problems.admm_gpu import FormationADMMRunner
-    run = FormationADMMRunner(sc.config3(8, rank=rank, world=world), rank=rank, world=world)
+    run = FormationADMMRunner(sc.config3(8, rank=rank, world=world), rank=rank, world=world,
+                              device=torch.device('cpu'))
     hist = [run.dual_update(0.) for _ in range(4)]
     torch.save({'x_i': run.x_i, 'z_i': run.z_i, 'l_i': run.l_i, 'hist': hist, 'lo': run.lo},
                os.path.join(out, 'r%d.pt' % rank))
@@ -460,7 +457,7 @@ def test_formation_admm_two_ranks_gloo_through_the_emulated_kernels(emu, tmp_pat
     from omg_tools_b200.problems.admm_gpu import FormationADMMRunner
     port = 29900 + (os.getpid() % 90)
     mp.spawn(_admm_rank, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    single = FormationADMMRunner(sc.config3(8))
+    single = FormationADMMRunner(sc.config3(8), device=torch.device('cpu'))
     hist = [single.dual_update(0.) for _ in range(4)]
     for rank in range(2):
         d = torch.load(os.path.join(str(tmp_path), 'r%d.pt' % rank))
@@ -479,7 +476,8 @@ def test_batched_receding_horizon_config5_through_the_emulated_kernels(emu):
     from omg_tools_b200.execution.batch_mpc import BatchMPC
     seq = sc.config5()
     seq.initialize(0.)
-    bat = BatchMPC(sc.config5(), batch=2, update_time=0.1)
+    import torch
+    bat = BatchMPC(sc.config5(), batch=2, update_time=0.1, device=torch.device('cpu'))
     t, dt = 0., 0.1
     for k in range(12):                      # crosses the first knot at t = 1.0
         seq.predict(t, dt, 0.01)
