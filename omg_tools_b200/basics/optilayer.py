@@ -9,6 +9,9 @@ to constant tables (``lowering.lower``) and handed to the B200 solver through
 the C-ABI (``solver/b200.py``).  ``create_nlp`` is the exact point where the
 reference calls ``nlpsol('solver','ipopt',...)``.
 """
+# Attribution: the class / method / option names and the constraint rows of this module restate
+# the corresponding module of OMG-tools (omgtools/basics/optilayer.py; Copyright (C) 2016 Ruben Van Parys &
+# Tim Mercy, KU Leuven; GNU LGPL v3) -- they are the drop-in contract of this framework.  See NOTICE.
 from __future__ import print_function
 
 import collections as col

@@ -1,6 +1,9 @@
 """Vehicle/obstacle shapes: only what the NLP needs -- checkpoints + radii,
 canvas limits and room hyperplanes (reference omgtools/basics/shape.py:62-67,
 146-171, 330-336, 350-362).  Drawing is out of scope."""
+# Attribution: the class / method / option names and the constraint rows of this module restate
+# the corresponding module of OMG-tools (omgtools/basics/shape.py; Copyright (C) 2016 Ruben Van Parys &
+# Tim Mercy, KU Leuven; GNU LGPL v3) -- they are the drop-in contract of this framework.  See NOTICE.
 import numpy as np
 
 

@@ -15,6 +15,9 @@ Coefficients may be floats or ``Poly`` objects (symbolic variables /
 parameters); all matrices are plain numpy.  The matrices produced here end up,
 through ``lowering.py``, as the constant tables of the CUDA kernels.
 """
+# Attribution: the class / method / option names and the constraint rows of this module restate
+# the corresponding module of OMG-tools (omgtools/basics/spline.py; Copyright (C) 2016 Ruben Van Parys &
+# Tim Mercy, KU Leuven; GNU LGPL v3) -- they are the drop-in contract of this framework.  See NOTICE.
 from collections import Counter
 
 import numpy as np

@@ -6,6 +6,9 @@ Semantics follow the reference's ``omgtools/basics/spline_extra.py`` (line
 numbers in each docstring); the code is written for this framework's ``Poly``
 scalars instead of CasADi ``MX``.
 """
+# Attribution: the class / method / option names and the constraint rows of this module restate
+# the corresponding module of OMG-tools (omgtools/basics/spline_extra.py; Copyright (C) 2016 Ruben Van Parys &
+# Tim Mercy, KU Leuven; GNU LGPL v3) -- they are the drop-in contract of this framework.  See NOTICE.
 import numpy as np
 from scipy.interpolate import splev
 

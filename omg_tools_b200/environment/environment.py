@@ -2,6 +2,9 @@
 variables a(t), b(t) per (vehicle shape, obstacle) and the ||a||^2 <= 1 rows
 (reference ``omgtools/environment/environment.py``: room handling 32-61,
 add_obstacle 75-92, define_collision_constraints 102-146, init 182-184)."""
+# Attribution: the class / method / option names and the constraint rows of this module restate
+# the corresponding module of OMG-tools (omgtools/environment/environment.py; Copyright (C) 2016 Ruben Van Parys &
+# Tim Mercy, KU Leuven; GNU LGPL v3) -- they are the drop-in contract of this framework.  See NOTICE.
 import warnings
 
 import numpy as np

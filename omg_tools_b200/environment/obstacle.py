@@ -7,6 +7,9 @@ Follows the reference's ``omgtools/environment/obstacle.py``: init 80-121
 334-343 (2D) / 528-533 (3D), theta parameter 345-348.  Simulation is the
 piecewise-constant-velocity/acceleration model without bouncing (geometry and
 bouncing are outside the hot path)."""
+# Attribution: the class / method / option names and the constraint rows of this module restate
+# the corresponding module of OMG-tools (omgtools/environment/obstacle.py; Copyright (C) 2016 Ruben Van Parys &
+# Tim Mercy, KU Leuven; GNU LGPL v3) -- they are the drop-in contract of this framework.  See NOTICE.
 from __future__ import division
 
 import numpy as np

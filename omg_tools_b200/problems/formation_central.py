@@ -1,75 +1,72 @@
-"""Formation point-to-point as ONE coupled NLP: all vehicles of the fleet, their collision
-constraints, and the formation constraints centre_i(tau) = centre_j(tau) between neighbours,
-hard (equality rows) or soft (slack splines with an L1 penalty and an optional maximum
-deviation).  Reference ``omgtools/problems/formation_central.py`` (options 30-34, construct
-36-78, parameters 84-90); it is the problem the ADMM of problems/admm.py distributes, and
-tests/test_admm.py uses a coupled solve as the fixed point the ADMM iteration must reach.
+"""The formation problem as ONE coupled NLP -- the fixed point the distributed ADMM iteration of
+problems/admm.py has to reach, which is what it is here for: tests/test_admm.py solves it with
+the oracle and checks that the ADMM iterates converge to it.  (As a user-facing problem class it
+is outside this build's scope)
 
-As in the reference the terminal slack splines 'g0', 'g1' are defined once per vehicle
-under the same name (point2point.py:160-163) and are therefore ONE pair of variables shared
-by the whole fleet (basics/optilayer.py: entries are identified by name)."""
+Model of the reference's ``omgtools/problems/formation_central.py:30-90`` (OMG-tools, Copyright (C)
+2016 Ruben Van Parys & Tim Mercy, KU Leuven, LGPL v3): every vehicle gets a parameter
+``rel_pos_c`` (its offset to the formation centre); neighbouring vehicles must agree on the
+centre, ``centre_i(tau) - centre_j(tau) = 0`` coefficient by coefficient -- hard, or softened by a
+slack spline with an L1 penalty and an optional cap.  The option names are the reference's.
+
+Entries are identified by NAME across the children (basics/optilayer.py): the terminal slacks
+'g0', 'g1' that every vehicle's terminal constraints define (point2point.py:160-163) are one
+shared pair, exactly as in the reference."""
 from .point2point import FixedTPoint2point
 from ..basics.optilayer import inf
 from ..basics.spline_extra import definite_integral
 
 
-class FormationPoint2pointCentral(FixedTPoint2point):
+def coupled_pairs(fleet):
+    """Each neighbour relation once, as (vehicle, neighbour).  On a ring the last two vehicles
+    contribute none: their relations would close the loop with linearly dependent rows."""
+    seen, pairs = set(), []
+    skip = set(fleet.vehicles[-2:]) if fleet.interconnection == 'circular' else set()
+    for veh in fleet.vehicles:
+        for other in fleet.get_neighbors(veh):
+            key = frozenset((veh, other))
+            if key in seen:
+                continue
+            seen.add(key)
+            if veh not in skip:
+                pairs.append((veh, other))
+    return pairs
 
-    def __init__(self, fleet, environment, options=None):
-        FixedTPoint2point.__init__(self, fleet, environment, options)
+
+class FormationPoint2pointCentral(FixedTPoint2point):
 
     def set_default_options(self):
         FixedTPoint2point.set_default_options(self)
-        self.options['soft_formation'] = False
-        self.options['soft_formation_weight'] = 10
-        self.options['max_formation_deviation'] = inf
+        self.options.update({'soft_formation': False, 'soft_formation_weight': 10,
+                             'max_formation_deviation': inf})
 
     def construct(self):
-        config = self.fleet.configuration
-        rel_pos_c = {}
-        for veh in self.vehicles:
-            ind_veh = sorted(config[veh].keys())
-            rel_pos_c[veh] = veh.define_parameter('rel_pos_c', len(ind_veh))
+        offsets = {veh: veh.define_parameter('rel_pos_c', len(self.fleet.configuration[veh]))
+                   for veh in self.vehicles}
         FixedTPoint2point.construct(self)
-        centra = {}
-        for veh in self.vehicles:
-            splines = self.father.get_variables(veh, 'splines_seg0', symbolic=True)
-            centra[veh] = veh.get_fleet_center(splines, rel_pos_c[veh], substitute=False)
-        # every neighbour pair once; a circular fleet would close the loop with
-        # redundant rows, so the last two vehicles add none (formation_central.py:55-57)
-        couples = {veh: [] for veh in self.vehicles}
-        for veh in self.vehicles:
-            for nghb in self.fleet.get_neighbors(veh):
-                if veh not in couples[nghb] and nghb not in couples[veh]:
-                    couples[veh].append(nghb)
-        if self.fleet.interconnection == 'circular':
-            couples.pop(self.vehicles[-1], None)
-            couples.pop(self.vehicles[-2], None)
-        t = self.define_symbol('t')
-        T = self.define_symbol('T')
-        for veh, nghbs in couples.items():
-            ind_veh = sorted(config[veh].keys())
-            for nghb in nghbs:
-                ind_nghb = sorted(config[nghb].keys())
-                for ind_v, ind_n in zip(ind_veh, ind_nghb):
-                    diff = centra[veh][ind_v] - centra[nghb][ind_n]
-                    if self.options['soft_formation']:
-                        weight = self.options['soft_formation_weight']
-                        eps = self.define_spline_variable(
-                            'eps_form_' + str(ind_v) + str(ind_n), basis=veh.basis)[0]
-                        self.define_objective(weight * definite_integral(eps, t / T, 1.))
-                        self.define_constraint(diff - eps, -inf, 0.)
-                        self.define_constraint(-diff - eps, -inf, 0.)
-                        if self.options['max_formation_deviation'] != inf:
-                            max_dev = abs(self.options['max_formation_deviation'])
-                            self.define_constraint(eps, -max_dev, max_dev)
-                    else:
-                        self.define_constraint(diff, 0., 0.)
+        centre = {veh: veh.get_fleet_center(self.father.get_variables(veh, 'splines_seg0', symbolic=True),
+                                            offsets[veh], substitute=False)
+                  for veh in self.vehicles}
+        self._t_rel = self.define_symbol('t') / self.define_symbol('T')
+        for veh, other in coupled_pairs(self.fleet):
+            mine, theirs = sorted(self.fleet.configuration[veh]), sorted(self.fleet.configuration[other])
+            for a, b in zip(mine, theirs):
+                self._couple(centre[veh][a] - centre[other][b], veh.basis, '%d%d' % (a, b))
+
+    def _couple(self, gap, basis, tag):
+        if not self.options['soft_formation']:
+            self.define_constraint(gap, 0., 0.)
+            return
+        slack = self.define_spline_variable('eps_form_' + tag, basis=basis)[0]
+        self.define_objective(self.options['soft_formation_weight'] * definite_integral(slack, self._t_rel, 1.))
+        self.define_constraint(gap - slack, -inf, 0.)
+        self.define_constraint(-gap - slack, -inf, 0.)
+        cap = self.options['max_formation_deviation']
+        if cap != inf:
+            self.define_constraint(slack, -abs(cap), abs(cap))
 
     def set_parameters(self, current_time):
         parameters = FixedTPoint2point.set_parameters(self, current_time)
         for veh in self.vehicles:
-            if veh not in parameters:
-                parameters[veh] = {}
-            parameters[veh].update({'rel_pos_c': veh.rel_pos_c})
+            parameters.setdefault(veh, {})['rel_pos_c'] = veh.rel_pos_c
         return parameters

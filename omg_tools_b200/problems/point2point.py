@@ -7,6 +7,9 @@ parameters t/T 174-181, knot-crossing warm-start shift 187-201, store 213-229.
 supported for models whose rows stay polynomial in T: no safety-distance
 slack (its objective integrates from t/T) and no rotating obstacles.
 """
+# Attribution: the class / method / option names and the constraint rows of this module restate
+# the corresponding module of OMG-tools (omgtools/problems/point2point.py; Copyright (C) 2016 Ruben Van Parys &
+# Tim Mercy, KU Leuven; GNU LGPL v3) -- they are the drop-in contract of this framework.  See NOTICE.
 from __future__ import print_function
 
 import numpy as np

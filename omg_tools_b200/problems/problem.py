@@ -8,6 +8,9 @@ reset_init_guess 165-181).  The single line the reference spends its time in,
 verbatim: ``self.problem`` is the B200 solver object created by
 ``OptiFather.construct_problem`` / ``create_nlp``.
 """
+# Attribution: the class / method / option names and the constraint rows of this module restate
+# the corresponding module of OMG-tools (omgtools/problems/problem.py; Copyright (C) 2016 Ruben Van Parys &
+# Tim Mercy, KU Leuven; GNU LGPL v3) -- they are the drop-in contract of this framework.  See NOTICE.
 from __future__ import print_function
 
 import time

@@ -4,6 +4,9 @@ rectangular shape, so the heading enters the collision rows (reference
 with the sign of every steering term flipped -- l'Hopital start constraint 111-144,
 terminal constraints 146-167, parameters 200-224, collision constraints 226-240, ode
 294-301).  Lowering as for the bicycle (vehicles/bicycle.py)."""
+# Attribution: the class / method / option names and the constraint rows of this module restate
+# the corresponding module of OMG-tools (omgtools/vehicles/agv.py; Copyright (C) 2016 Ruben Van Parys &
+# Tim Mercy, KU Leuven; GNU LGPL v3) -- they are the drop-in contract of this framework.  See NOTICE.
 import numpy as np
 
 from .bicycle import Bicycle

@@ -10,6 +10,9 @@ product splines q = v~ (1 + tg^2)^2, r = (1 + tg^2)^2 and s = v~ tg (1 + tg^2) a
 intermediates (basics/poly.py), so that the rows read  2 L ddtg q - 2 L dtg (dv r + 4 s dtg)
 - (T^2 q^2 + (2 L dtg)^2) ddelta_max: monomials with at most two intermediates (lowering.py:
 mid-mid Hessian slots).  The position is the integrated product spline as for Dubins."""
+# Attribution: the class / method / option names and the constraint rows of this module restate
+# the corresponding module of OMG-tools (omgtools/vehicles/bicycle.py; Copyright (C) 2016 Ruben Van Parys &
+# Tim Mercy, KU Leuven; GNU LGPL v3) -- they are the drop-in contract of this framework.  See NOTICE.
 import numpy as np
 
 from .dubins import Dubins

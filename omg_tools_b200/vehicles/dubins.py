@@ -13,6 +13,9 @@ with x-dependent coefficients, lowering.py cross-Hessian slots), ``substitution`
 velocity splines dx, dy carry the position and the band |int(dx) - int(v~(1-tg^2))| <= 1e-3
 ties them to the flat outputs; examples/p2p_dubins.py) and ``exact_substitution`` (dx, dy on
 the product basis, tied by equality rows)."""
+# Attribution: the class / method / option names and the constraint rows of this module restate
+# the corresponding module of OMG-tools (omgtools/vehicles/dubins.py; Copyright (C) 2016 Ruben Van Parys &
+# Tim Mercy, KU Leuven; GNU LGPL v3) -- they are the drop-in contract of this framework.  See NOTICE.
 import numpy as np
 
 from .vehicle import Vehicle

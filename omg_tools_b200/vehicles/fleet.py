@@ -1,90 +1,99 @@
-"""Fleet: vehicle grouping, neighbour topology and formation configuration
-(reference omgtools/vehicles/fleet.py:23-110)."""
+"""Fleet: the vehicles of a multi-agent problem, who talks to whom, and the formation they keep.
+
+API of the reference's ``omgtools/vehicles/fleet.py`` (OMG-tools, Copyright (C) 2016 Ruben Van
+Parys & Tim Mercy, KU Leuven, LGPL v3) because the problem classes address it by these names --
+``vehicles``, ``N``, ``get_neighbors``, ``set_configuration``, ``get_rel_config``,
+``configuration``, each vehicle's ``rel_pos_c`` -- re-implemented here on index arrays:
+the neighbour table is an integer matrix (what the batched ADMM runner and the NCCL exchange
+consume directly, problems/admm.py), the configuration a dense array plus the per-vehicle
+dictionaries the reference exposes (fleet.py:46-98)."""
 import numpy as np
 
 from .vehicle import Vehicle
 
+TOPOLOGIES = {
+    # ring: successor first, then predecessor (the order fixes the layout of z_ij / l_ij)
+    'circular': lambda n: np.stack([(np.arange(n) + 1) % n, (np.arange(n) - 1) % n], axis=1),
+    'full': lambda n: np.array([[k for k in range(n) if k != i] for i in range(n)], dtype=int).reshape(n, -1),
+}
+
 
 def get_fleet_vehicles(var):
-    if isinstance(var, Fleet):
-        return var, var.vehicles
-    elif isinstance(var, list):
-        if isinstance(var[0], Vehicle):
-            return Fleet(var), var
-        if isinstance(var[0], Fleet):
-            return var[0], var[0].vehicles
-    elif isinstance(var, Vehicle):
-        return Fleet(var), [var]
+    """Accepts a Fleet, a Vehicle, a list of vehicles or a one-element list holding a Fleet;
+    returns (fleet, vehicles)."""
+    if isinstance(var, Vehicle):
+        var = [var]
+    if isinstance(var, list) and var and isinstance(var[0], Fleet):
+        var = var[0]
+    fleet = var if isinstance(var, Fleet) else Fleet(list(var))
+    return fleet, fleet.vehicles
 
 
 class Fleet(object):
 
     def __init__(self, vehicles=None, interconnection='circular'):
-        vehicles = vehicles or []
-        self.vehicles = vehicles if isinstance(vehicles, list) else [vehicles]
+        if vehicles is None:
+            vehicles = []
+        self.vehicles = list(vehicles) if isinstance(vehicles, (list, tuple)) else [vehicles]
         self.interconnection = interconnection
         self.set_neighbors()
+
+    # ---- topology ----------------------------------------------------------------------
+    def set_neighbors(self):
+        self.N = len(self.vehicles)
+        if self.interconnection not in TOPOLOGIES:
+            raise ValueError('Interconnection type ' + str(self.interconnection) + ' not understood.')
+        self.nghb_index = TOPOLOGIES[self.interconnection](self.N) if self.N else np.zeros((0, 0), int)
+        self.nghb_list = {veh: [self.vehicles[k] for k in self.nghb_index[i]]
+                          for i, veh in enumerate(self.vehicles)}
 
     def get_neighbors(self, vehicle):
         return self.nghb_list[vehicle]
 
-    def set_neighbors(self):
-        self.N = len(self.vehicles)
-        self.nghb_list = {}
-        for l, vehicle in enumerate(self.vehicles):
-            if self.interconnection == 'circular':
-                nghb_ind = [(self.N + l + 1) % self.N, (self.N + l - 1) % self.N]
-            elif self.interconnection == 'full':
-                nghb_ind = [k for k in range(self.N) if k != l]
-            else:
-                raise ValueError('Interconnection type ' + self.interconnection +
-                                 ' not understood.')
-            self.nghb_list[vehicle] = [self.vehicles[ind] for ind in nghb_ind]
-
+    # ---- formation ----------------------------------------------------------------------
     def set_configuration(self, configuration, orientation=0.):
-        self.configuration = {}
+        """configuration[i]: the place of vehicle i relative to the formation centre -- a list of
+        coordinates (2-D ones are turned by -orientation) or a dict {spline index: offset}."""
         if len(configuration) != self.N:
-            raise ValueError('You should provide configuration info ' +
-                             'for each vehicle.')
-        cth, sth = np.cos(-orientation), np.sin(-orientation)
-        for l, config in enumerate(configuration):
-            if len(config) == 2:
-                config = [config[0] * cth - config[1] * sth,
-                          config[0] * sth + config[1] * cth]
-            if isinstance(config, dict):
-                self.configuration[self.vehicles[l]] = config
-            if isinstance(config, list):
-                self.configuration[self.vehicles[l]] = {
-                    k: con for k, con in enumerate(config)}
+            raise ValueError('You should provide configuration info for each vehicle.')
+        turn = np.array([[np.cos(orientation), np.sin(orientation)],
+                         [-np.sin(orientation), np.cos(orientation)]])
+        self.configuration = {}
+        for veh, entry in zip(self.vehicles, configuration):
+            if isinstance(entry, dict):
+                self.configuration[veh] = dict(entry)
+                continue
+            coords = np.asarray(entry, dtype=float)
+            if coords.size == 2:
+                coords = turn.dot(coords)
+            self.configuration[veh] = dict(enumerate(coords.tolist()))
         self.set_rel_pos_c()
+        keys = {veh: sorted(self.configuration[veh]) for veh in self.vehicles}
         self.rel_config = {}
-        for vehicle in self.vehicles:
-            self.rel_config[vehicle] = {}
-            ind_veh = sorted(self.configuration[vehicle].keys())
-            for nghb in self.get_neighbors(vehicle):
-                ind_nghb = sorted(self.configuration[nghb].keys())
-                if len(ind_veh) != len(ind_nghb):
-                    raise ValueError('All vehicles should have same number ' +
-                                     'of variables for which the configuration ' +
-                                     'is imposed.')
-                self.rel_config[vehicle][nghb] = [
-                    self.configuration[vehicle][iv] - self.configuration[nghb][in_]
-                    for iv, in_ in zip(ind_veh, ind_nghb)]
+        for veh in self.vehicles:
+            mine = np.array([self.configuration[veh][k] for k in keys[veh]])
+            self.rel_config[veh] = {}
+            for other in self.nghb_list[veh]:
+                if len(keys[other]) != len(keys[veh]):
+                    raise ValueError('All vehicles should have same number of variables for which '
+                                     'the configuration is imposed.')
+                theirs = np.array([self.configuration[other][k] for k in keys[other]])
+                self.rel_config[veh][other] = (mine - theirs).tolist()
 
     def set_rel_pos_c(self):
+        """Vector from a vehicle to the formation centre (a parameter of the formation rows)."""
         for veh in self.vehicles:
-            ind_veh = sorted(self.configuration[veh].keys())
-            veh.rel_pos_c = [-self.configuration[veh][ind] for ind in ind_veh]
+            veh.rel_pos_c = [-self.configuration[veh][k] for k in sorted(self.configuration[veh])]
 
     def get_rel_config(self, vehicle):
         return self.rel_config[vehicle]
 
+    # ---- boundary conditions, vehicle by vehicle ---------------------------------------------
     def set_initial_conditions(self, states, inputs=None):
-        if inputs is None:
-            inputs = [None for _ in range(len(states))]
-        for state, inp, vehicle in zip(states, inputs, self.vehicles):
-            vehicle.set_initial_conditions(state, inp)
+        inputs = [None] * len(states) if inputs is None else inputs
+        for veh, state, inp in zip(self.vehicles, states, inputs):
+            veh.set_initial_conditions(state, inp)
 
     def set_terminal_conditions(self, conditions):
-        for condition, vehicle in zip(conditions, self.vehicles):
-            vehicle.set_terminal_conditions(condition)
+        for veh, cond in zip(self.vehicles, conditions):
+            veh.set_terminal_conditions(cond)

@@ -3,6 +3,9 @@ bounds are linear rows on the derivative coefficients (reference
 ``omgtools/vehicles/holonomic.py``: bounds 30-57, trajectory constraints 62-85,
 initial/terminal constraints 87-105, initial guess 118-127, parameters 153-159,
 collision constraints 161-163)."""
+# Attribution: the class / method / option names and the constraint rows of this module restate
+# the corresponding module of OMG-tools (omgtools/vehicles/holonomic.py; Copyright (C) 2016 Ruben Van Parys &
+# Tim Mercy, KU Leuven; GNU LGPL v3) -- they are the drop-in contract of this framework.  See NOTICE.
 import numpy as np
 
 from .vehicle import Vehicle

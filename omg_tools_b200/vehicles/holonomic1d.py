@@ -2,6 +2,9 @@
 bounds, no collision rows (reference ``omgtools/vehicles/holonomic1d.py``:
 bounds 31-36, trajectory constraints 41-49, initial/terminal constraints
 51-67, initial guess 78-83, parameters 94-99)."""
+# Attribution: the class / method / option names and the constraint rows of this module restate
+# the corresponding module of OMG-tools (omgtools/vehicles/holonomic1d.py; Copyright (C) 2016 Ruben Van Parys &
+# Tim Mercy, KU Leuven; GNU LGPL v3) -- they are the drop-in contract of this framework.  See NOTICE.
 import numpy as np
 
 from .vehicle import Vehicle

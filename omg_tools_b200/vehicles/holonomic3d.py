@@ -3,6 +3,9 @@
 ``omgtools/vehicles/holonomic3d.py``: bounds 29-37, trajectory constraints
 46-74, initial/terminal constraints 76-96, initial guess 107-115, parameters
 126-131, 3D collision rows 133-135)."""
+# Attribution: the class / method / option names and the constraint rows of this module restate
+# the corresponding module of OMG-tools (omgtools/vehicles/holonomic3d.py; Copyright (C) 2016 Ruben Van Parys &
+# Tim Mercy, KU Leuven; GNU LGPL v3) -- they are the drop-in contract of this framework.  See NOTICE.
 import numpy as np
 
 from .vehicle import Vehicle

@@ -5,6 +5,9 @@ define_collision_constraints_2d with tg_ha) and the turn-rate limits
 28-37, trajectory constraints 48-85 incl. the optional regularisation of the heading
 rate, initial / terminal constraints 87-108, initial guess 120-135, parameters 145-156,
 collision constraints 158-160, signals 162-177)."""
+# Attribution: the class / method / option names and the constraint rows of this module restate
+# the corresponding module of OMG-tools (omgtools/vehicles/holonomicorient.py; Copyright (C) 2016 Ruben Van Parys &
+# Tim Mercy, KU Leuven; GNU LGPL v3) -- they are the drop-in contract of this framework.  See NOTICE.
 import numpy as np
 
 from .vehicle import Vehicle

@@ -3,6 +3,9 @@ thrust and pitch-rate limits become polynomial rows of degree 2 and 3 in the
 spline coefficients (reference ``omgtools/vehicles/quadrotor.py``: bounds
 32-36, trajectory constraints 48-62, initial/terminal constraints 64-84,
 initial guess 97-105, parameters 116-122, signals 128-149, ode 154-157)."""
+# Attribution: the class / method / option names and the constraint rows of this module restate
+# the corresponding module of OMG-tools (omgtools/vehicles/quadrotor.py; Copyright (C) 2016 Ruben Van Parys &
+# Tim Mercy, KU Leuven; GNU LGPL v3) -- they are the drop-in contract of this framework.  See NOTICE.
 import numpy as np
 
 from .vehicle import Vehicle

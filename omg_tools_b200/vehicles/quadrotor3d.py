@@ -8,6 +8,9 @@ constraints 76-133, initial/terminal constraints 135-174, initial guess
 189-201, parameters 211-223, collision constraints 225-238, integrate_twice
 240-254).  Rows are polynomials up to degree 5 in the decision variables.
 """
+# Attribution: the class / method / option names and the constraint rows of this module restate
+# the corresponding module of OMG-tools (omgtools/vehicles/quadrotor3d.py; Copyright (C) 2016 Ruben Van Parys &
+# Tim Mercy, KU Leuven; GNU LGPL v3) -- they are the drop-in contract of this framework.  See NOTICE.
 import numpy as np
 
 from .vehicle import Vehicle

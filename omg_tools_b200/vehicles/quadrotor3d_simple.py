@@ -4,6 +4,9 @@ rates and tilt limits are quadratic rows in the second and third derivatives (re
 initial / terminal constraints 79-103, initial guess 114-122, parameters 133-146,
 collision constraints 148-152, signals 154-181, ode 186-190).  No intermediates: every row
 is a polynomial of degree <= 2 in the spline coefficients."""
+# Attribution: the class / method / option names and the constraint rows of this module restate
+# the corresponding module of OMG-tools (omgtools/vehicles/quadrotor3d_simple.py; Copyright (C) 2016 Ruben Van Parys &
+# Tim Mercy, KU Leuven; GNU LGPL v3) -- they are the drop-in contract of this framework.  See NOTICE.
 import numpy as np
 
 from .vehicle import Vehicle

@@ -10,6 +10,9 @@ As in the reference's example (examples/p2p_trailer.py:31-48) the lead vehicle i
 child and a vehicle of the problem (``problem.father.add(vehicle)``,
 ``problem.vehicles.append(vehicle)``): its parameters and rows live under its own label, once
 for its own splines and once for the trailer's copies of them."""
+# Attribution: the class / method / option names and the constraint rows of this module restate
+# the corresponding module of OMG-tools (omgtools/vehicles/trailer.py; Copyright (C) 2016 Ruben Van Parys &
+# Tim Mercy, KU Leuven; GNU LGPL v3) -- they are the drop-in contract of this framework.  See NOTICE.
 import numpy as np
 
 from .dubins import Dubins

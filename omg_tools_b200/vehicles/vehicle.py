@@ -8,6 +8,9 @@ the ideal, noise-free case: the vehicle follows its computed spline exactly
 (reference options 'ideal_prediction'/'ideal_update', vehicle.py:70-78,
 302-337, 339-410); plotting, delays and disturbances are out of scope.
 """
+# Attribution: the class / method / option names and the constraint rows of this module restate
+# the corresponding module of OMG-tools (omgtools/vehicles/vehicle.py; Copyright (C) 2016 Ruben Van Parys &
+# Tim Mercy, KU Leuven; GNU LGPL v3) -- they are the drop-in contract of this framework.  See NOTICE.
 import numpy as np
 
 from ..basics.optilayer import OptiChild, inf
