@@ -643,6 +643,14 @@ class OptiChild(object):
         else:
             name = name + '_' + str(self._constraint_cnt)
         self._constraint_cnt += 1
+        if shutdown and np.all(np.asarray(lb) == np.asarray(ub)):
+            # the equality rows are part of the KKT STRUCTURE the solver factorises (the border
+            # of the condensed system): they cannot be switched off by the bounds at run time
+            # the way an inequality row can.  (No model of the reference does this.)
+            raise NotImplementedError(
+                "define_constraint(..., shutdown=%r) on an equality constraint (lb == ub) is not "
+                "supported by the 'b200' solver: shut down an inequality pair lb <= expr <= ub "
+                "instead, or build two problems" % (shutdown,))
         if isinstance(expr, BSpline):
             coeffs = expr.coeffs
             if skip:

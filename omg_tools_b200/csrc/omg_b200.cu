@@ -1571,21 +1571,19 @@ static void set_err(const std::string& s) { g_err = s; }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
   set_err(std::string(#call) + ": " + cudaGetErrorString(e_)); return -1; } } while (0)
 
-// Block descriptors of the shift / sampling calls live on the device between calls: a
-// receding-horizon loop passes the same blocks every step, so only the first call uploads
-// (and only a changed descriptor frees anything) -- the calls stay asynchronous on `stream`.
+// Device buffers for the block descriptors of the shift / sampling calls.  They only GROW (a
+// receding-horizon loop passes the same block layout every step, the sampling matrix changes
+// with the time): after the first call there is no cudaMalloc / cudaFree, and the small
+// host-to-device copies are enqueued on the CALLER's stream every time, so calls on different
+// streams are ordered correctly and stay asynchronous.
 struct DescCache {
   int device = -1;
-  std::vector<int> ikey; std::vector<double> dkey;
+  size_t cap_i = 0, cap_d = 0;
   int* d_i = nullptr; double* d_d = nullptr;
+  ~DescCache() { if (d_i) cudaFree(d_i); if (d_d) cudaFree(d_d); }
 };
 
-static void free_desc(DescCache* c) {
-  if (!c) return;
-  if (c->d_i) cudaFree(c->d_i);
-  if (c->d_d) cudaFree(c->d_d);
-  delete c;
-}
+static void free_desc(DescCache* c) { delete c; }
 
 struct omg_problem {
   int device = 0;
@@ -2209,17 +2207,18 @@ int omg_feas_batch_host(omg_problem* h, int32_t B, const double* x0, const doubl
 
 static int desc_upload(DescCache& c, int device, const std::vector<int>& iv, const double* dv, size_t nd,
                        cudaStream_t stream) {
-  if (c.device == device && c.d_i && c.ikey == iv && c.dkey.size() == nd &&
-      memcmp(c.dkey.data(), dv, nd * sizeof(double)) == 0) return 0;
-  if (c.d_i) cudaFree(c.d_i);
-  if (c.d_d) cudaFree(c.d_d);
-  c.d_i = nullptr; c.d_d = nullptr; c.device = -1;
-  c.ikey = iv; c.dkey.assign(dv, dv + nd);
-  CK(cudaMalloc(&c.d_i, sizeof(int) * (iv.size() ? iv.size() : 1)));
-  CK(cudaMalloc(&c.d_d, sizeof(double) * (nd ? nd : 1)));
-  CK(cudaMemcpyAsync(c.d_i, c.ikey.data(), sizeof(int) * iv.size(), cudaMemcpyHostToDevice, stream));
-  CK(cudaMemcpyAsync(c.d_d, c.dkey.data(), sizeof(double) * nd, cudaMemcpyHostToDevice, stream));
-  c.device = device;
+  if (c.device != device || iv.size() > c.cap_i || nd > c.cap_d) {   // (re)allocate: first call / growth only
+    if (c.d_i) cudaFree(c.d_i);
+    if (c.d_d) cudaFree(c.d_d);
+    c.d_i = nullptr; c.d_d = nullptr; c.device = -1;
+    c.cap_i = std::max(iv.size(), (size_t)64) * 2; c.cap_d = std::max(nd, (size_t)64) * 2;
+    CK(cudaMalloc(&c.d_i, sizeof(int) * c.cap_i));
+    CK(cudaMalloc(&c.d_d, sizeof(double) * c.cap_d));
+    c.device = device;
+  }
+  // pageable sources: the runtime stages them before returning, the caller's arrays are free again
+  CK(cudaMemcpyAsync(c.d_i, iv.data(), sizeof(int) * iv.size(), cudaMemcpyHostToDevice, stream));
+  CK(cudaMemcpyAsync(c.d_d, dv, sizeof(double) * nd, cudaMemcpyHostToDevice, stream));
   return 0;
 }
 

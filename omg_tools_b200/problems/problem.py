@@ -124,16 +124,22 @@ class Problem(OptiChild):
     def predict(self, current_time, predict_time, sample_time, states=None,
                 inputs=None, dinputs=None, delay=0, enforce_states=False,
                 enforce_inputs=False):
+        """Reference problem.py:138-163: per-vehicle prediction; a measured state is enforced on
+        the first iteration (current_time == start_time)."""
         nv = len(self.vehicles)
-        states = states if states is not None else [None] * nv
-        inputs = inputs if inputs is not None else [None] * nv
-        if nv == 1 and not isinstance(states, list):
-            states = [states]
-        if nv == 1 and not isinstance(inputs, list):
-            inputs = [inputs]
+
+        def per_vehicle(arg):
+            if arg is None:
+                return [None] * nv
+            if nv == 1 and (not isinstance(arg, list) or isinstance(arg[0], float)):
+                return [arg]
+            return arg
+        states, inputs, dinputs = per_vehicle(states), per_vehicle(inputs), per_vehicle(dinputs)
+        if current_time == self.start_time:
+            enforce_states = True
         for k, vehicle in enumerate(self.vehicles):
-            vehicle.predict(current_time, predict_time, sample_time,
-                            states[k], inputs[k])
+            vehicle.predict(current_time, predict_time, sample_time, states[k], inputs[k],
+                            dinputs[k], delay, enforce_states, enforce_inputs)
 
     def reset_init_guess(self, init_guess=None):
         if init_guess is None:

@@ -547,6 +547,14 @@ class B200Solver(object):
         ub = None if ubg is None else np.asarray(ubg, dtype=np.float64).reshape(-1)
         lam0 = None if lam_g0 is None else \
             np.asarray(lam_g0, dtype=np.float64).reshape(1, self.m)
+        if lb is not None and ub is not None:
+            # the equality rows are part of the factorised structure: bounds that turn an equality
+            # into an inequality (or the reverse) need a re-lowered problem, not another call
+            eq_now, eq_built = (lb == ub), (self.tables.lbg == self.tables.ubg)
+            if not np.array_equal(eq_now, eq_built):
+                rows = np.nonzero(eq_now != eq_built)[0][:5].tolist()
+                raise ValueError('lbg/ubg change which rows are equalities (rows %s ...): the '
+                                 'equality pattern is fixed when the problem is lowered' % rows)
         res = self.solve_batch(x0, p, lb, ub, lam0)
         self._stats = {'return_status': STATUS_STRINGS[int(res['status'][0])],
                        'iter_count': int(res['iters'][0]),

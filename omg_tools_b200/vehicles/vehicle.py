@@ -280,16 +280,32 @@ class Vehicle(OptiChild):
     def predict(self, current_time, predict_time, sample_time, state0=None,
                 input0=None, dinput0=None, delay=0, enforce_states=False,
                 enforce_inputs=False):
-        """Ideal prediction: state/input of the stored trajectory after
-        predict_time (reference vehicle.py:302-337 with ideal_prediction)."""
-        if not hasattr(self, 'trajectories') or enforce_states and state0 is None \
-                and not hasattr(self, 'trajectories'):
+        """Where the vehicle will be when the next trajectory starts (reference vehicle.py:302-337).
+
+        enforce_states (+ enforce_inputs): the measured state0 (and input0) -- or, without a
+        measurement, the last simulated signal -- becomes the initial condition as is.
+        Otherwise the stored trajectory is read predict_time (+ ``delay`` samples of computation
+        delay) ahead.  Only the ideal prediction is done on the host; the non-ideal one (ODE
+        integration of the planned inputs) is the batched RK4 kernel of execution/batch_mpc.py."""
+        last = lambda key: np.atleast_2d(self.signals[key])[:, -1]
+        if enforce_states and enforce_inputs:
+            if state0 is not None and input0 is not None:
+                self.set_initial_conditions(state0, input0)
+            elif hasattr(self, 'signals') and 'state' in self.signals:
+                self.set_initial_conditions(last('state'), last('input'))
             return
-        if state0 is not None and input0 is not None:
-            self.prediction['state'] = np.asarray(state0, dtype=float)
-            self.prediction['input'] = np.asarray(input0, dtype=float)
+        if enforce_states:
+            if state0 is not None:
+                self.set_initial_conditions(state0)
+            elif hasattr(self, 'signals') and 'state' in self.signals:
+                self.set_initial_conditions(last('state'))
             return
-        n_samp = int(np.round(predict_time / sample_time, 6))
+        if not hasattr(self, 'trajectories'):
+            return
+        if not self.options.get('ideal_prediction', True):
+            raise NotImplementedError('non-ideal prediction on the host: use execution.batch_mpc '
+                                      '(omg_integrate_rk4) or ideal_prediction=True')
+        n_samp = int(np.round(predict_time / sample_time, 6)) + int(delay)
         for key, val in self.trajectories.items():
             # every sampled signal is predicted (state, input, and model specific
             # ones such as the quadrotor's dspl / ddspl)

@@ -492,3 +492,19 @@ def test_batched_receding_horizon_config5_through_the_emulated_kernels(emu):
         seq.simulate(t, dt, 0.01)
         t = np.round(t + dt, 6)
     assert np.abs(bat.state[0] - seq.vehicles[0].signals['state'][:, -1]).max() < 1e-6
+
+
+def test_changed_equality_pattern_raises(emu):
+    """Bounds that turn an equality row into a free row: a clear error from the reference-facing
+    call instead of Error_In_Step_Computation with the stale x."""
+    pr = sc.config1()
+    tb = pr.father.tables
+    X0, P = sc.instance_data(pr, 1)
+    lb, ub = tb.lbg.copy(), tb.ubg.copy()
+    k = int(np.nonzero(lb == ub)[0][0])
+    lb[k], ub[k] = -np.inf, np.inf
+    with pytest.raises(ValueError, match='equality pattern'):
+        pr.problem(x0=X0[0], p=P[0], lbg=lb, ubg=ub)
+    # the batched entry reports it per instance
+    res = pr.problem.solve_batch(X0, P, lb, ub)
+    assert res['status'][0] == 3 and res['iters'][0] == 0

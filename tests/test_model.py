@@ -1084,3 +1084,53 @@ def test_host_loop_equals_the_references_problem_solve_loop(name, n_steps):
             T = shiftoverknot_T(veh._splines_prim[nm]['basis'])
             assert np.abs(mine[off:off + size] - T.dot(ref[off:off + size])).max() < 1e-5
         assert np.abs(mine - ref)[~slack].max() < 1e-5
+
+
+def test_shutdown_of_an_equality_constraint_is_rejected():
+    """switching an equality row off through the bounds changes the structure the
+    solver factorises (the border of the condensed KKT system).  The modelling layer refuses it
+    at definition time instead of failing inside the solve."""
+    import pytest
+    from omg_tools_b200.basics.optilayer import OptiChild
+    child = OptiChild('shutdown_test')
+    x = child.define_variable('x', 2)
+    child.define_constraint(x[0] - 1., -np.inf, 0., shutdown='t > 1.')      # inequality: fine
+    with pytest.raises(NotImplementedError):
+        child.define_constraint(x[1] - 2., 0., 0., shutdown='t > 1.')
+
+
+def test_predict_branches_follow_the_reference():
+    """Vehicle.predict / Problem.predict (reference vehicle.py:302-337, problem.py:138-163;
+    ADVICE r1): computation delay shifts the read-out index, measured states are enforced
+    through set_initial_conditions (always on the first iteration), a state + input pair
+    without the enforce flags does NOT override the ideal prediction."""
+    import pytest
+    pr = sc.config1(build_solver=False)
+    veh = pr.vehicles[0]
+    n = 40
+    veh.trajectories = {'time': np.arange(n)[None] * 0.01,
+                        'state': np.vstack([np.arange(n) * 1.0, np.arange(n) * -1.0]),
+                        'input': np.vstack([np.arange(n) * 0.5, np.arange(n) * 0.25])}
+    veh.signals = {'state': np.array([[7., 8.], [9., 10.]]), 'input': np.array([[1., 2.], [3., 4.]])}
+    # ideal prediction, 0.1 s ahead at 0.01 s sampling, 3 samples of delay -> sample 13
+    pr.start_time = 0.
+    pr.predict(0.5, 0.1, 0.01, delay=3)
+    assert np.allclose(veh.prediction['state'], [13., -13.]) and np.allclose(veh.prediction['input'], [6.5, 3.25])
+    # a measurement without enforce flags does not replace the prediction
+    pr.predict(0.5, 0.1, 0.01, states=[0.3, 0.4], inputs=[0.1, 0.2])
+    assert np.allclose(veh.prediction['state'], [10., -10.])
+    # enforce_states: the measurement, or the last simulated signal
+    pr.predict(0.5, 0.1, 0.01, states=[0.3, 0.4], enforce_states=True)
+    assert np.allclose(veh.prediction['state'], [0.3, 0.4])
+    pr.predict(0.5, 0.1, 0.01, enforce_states=True)
+    assert np.allclose(veh.prediction['state'], [8., 10.])
+    pr.predict(0.5, 0.1, 0.01, states=[0.5, 0.6], inputs=[0.1, 0.2], enforce_states=True, enforce_inputs=True)
+    assert np.allclose(veh.prediction['state'], [0.5, 0.6]) and np.allclose(veh.prediction['input'], [0.1, 0.2])
+    # first iteration: the state is enforced whatever the flags say
+    pr.start_time = 0.5
+    pr.predict(0.5, 0.1, 0.01, states=[1.5, 1.6])
+    assert np.allclose(veh.prediction['state'], [1.5, 1.6])
+    veh.options['ideal_prediction'] = False
+    pr.start_time = 0.
+    with pytest.raises(NotImplementedError):
+        pr.predict(0.7, 0.1, 0.01)
