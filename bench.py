@@ -195,9 +195,10 @@ WORKLOADS = {
 }
 
 # DRAM traffic of the solver kernel per solve, from the ncu --set full captures
-# (dram__bytes_read.sum + dram__bytes_write.sum of a 148-solve launch):
-# profiles/r01_v5_ncu_raw.txt (config 2), profiles/r01_xl_config4_ncu_raw.txt (config 4)
-NCU_DRAM_BYTES_PER_SOLVE = {'config2': (1.151488e6 + 1.359360e6) / 148.,
+# (dram__bytes_read.sum + dram__bytes_write.sum of one launch):
+# profiles/r02_sparse_ncu_raw.txt (config 2, sparse kernel, 592-solve launch: the writes are L2
+# write-backs of the per-block scratch, 592 blocks x ~190 KB), profiles/r01_xl_config4_ncu_raw.txt
+NCU_DRAM_BYTES_PER_SOLVE = {'config2': (27.405568e6 + 483.273728e6) / 592.,
                             'config4': (3.464099e9 + 7.549988e9) / 148.}
 # bounded CPU sample: about 20 s of single-core work of the C oracle per measurement
 CPU_SAMPLE = {'config1': 2048, 'config2': 1024, 'config4': 96, 'config4_5obs': 32, 'config5': 512,
@@ -433,8 +434,8 @@ def main():
                          'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': (NCU_DRAM_BYTES_PER_SOLVE[args.workload] * B
                                      if args.workload in NCU_DRAM_BYTES_PER_SOLVE else None),
-                         'traffic_source': 'ncu dram bytes per solve (profiles/*_ncu_raw.txt, '
-                                           '148-solve launch) x batch',
+                         'traffic_source': 'ncu dram__bytes_read+write per solve of one full launch '
+                                           '(profiles/r02_sparse_ncu_raw.txt) x batch',
                          'peak_source': how,
                          'model': 'staged-KKT bytes/solve = K*2*8*n(n+1)/2 + '
                                   '8(2n+n_par+3m) (SURVEY 8d); K=mean iterations',

@@ -301,3 +301,22 @@ def test_feasibility_phase_rescues_the_dubins_example_from_the_references_own_gu
     # from the optimum (violation below constr_viol_tol) the phase has little left to do
     _, v2, k2 = ipm_c.feas_batch(tb, res['x'], p[None])
     assert v2[0] <= 1e-8 and k2[0] <= 3
+
+
+def test_against_ipopt_golden():
+    """The pin that is still missing: IPOPT's own solutions (tests/golden/make_ipopt_golden.py,
+    to be run where `import casadi` works).  With the fixture present the oracle must reproduce
+    IPOPT's spline coefficients to the north-star tolerance at the reference's tol = 1e-3;
+    without it the test is skipped and DESIGN.md section 5 keeps saying "parity unpinned"."""
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ipopt_golden.npz')
+    if not os.path.exists(path):
+        pytest.skip('no IPOPT fixture (CasADi is not installable in this image): parity unpinned')
+    from oracle import ipm_c
+    G = np.load(path)
+    for name in ('config1', 'config2', 'config5'):
+        pr = getattr(sc, name)(build_solver=False)
+        res = ipm_c.solve_batch_full(pr.father.tables, G[name + '_X0'], G[name + '_P'], threads=4)
+        ok = np.array([s == 'Solve_Succeeded' for s in G[name + '_status']])
+        assert (res['status'][ok] == 0).all()
+        assert np.abs(res['x'] - G[name + '_x'])[ok][:, :26].max() < 1e-4, name
