@@ -61,7 +61,8 @@ struct SpTab {
   const int* ksign;                // [N] +1 / -1 by permuted index
   // backward sweep: per level, rounds of NT/8 columns; one 32-byte record per lane
   const int* brnd_ptr;             // [n_lev+1] round ranges per level
-  const uint4* bdesc;              // [round][NT][2]: {j | len<<11 | valid<<18, base, rows[0..1], rows[2..3]}, {rows[4..7]}
+  const uint4* bdesc;              // [round][NT][3]: {j8 | valid<<16 | nq<<17, rhs8, e0, e1}, {e2..e5}, {e6, e7, -, -};
+                                   //   e = LK byte offset | uu byte offset << 16 of entry sub + 8 q (zero slot if none)
   const int* diagidx; const int* rhsidx;     // [N] L index of the diagonal / rhs entry of a column
   const int* pos_var; const int* pos_eq;     // permutation of this structure
   const int* jdst;                 // [nnz_j] L index of the border entry of an equality-row slot
@@ -183,8 +184,8 @@ static inline double sp_rcp(double x) { return 1.0 / x; }
 #define SP_CHECK()                                                                            \
   {                                                                                           \
     const int rep_ = flags[slot_];                                                            \
-    if (tid == 0) flags[(slot_ + 2) % 3] = 0;                                                 \
-    slot_ = (slot_ + 1) % 3;                                                                  \
+    if (tid == 0) flags[(slot_ == 0) ? 2 : slot_ - 1] = 0;                                    \
+    slot_ = (slot_ == 2) ? 0 : slot_ + 1;                                                     \
     nneg += rep_ & 0xffff;                                                                    \
     if ((rep_ >> 16) || (mode == 0 && nneg > T.n_eq)) {                                       \
       if (tid == 0) { ctl->fail = 1; ctl->eq_fail = (rep_ >> 24) ? 1 : 0; }                   \
@@ -344,7 +345,7 @@ __device__ __forceinline__ void sp_back_solve(const DevTab& T, const SpTab& P, c
   uint4 na = make_uint4(0u, 0u, 0u, 0u), nb = na;
   if (P.n_lev > 0) {
     const int r0 = bptr[P.n_lev - 1];
-    if (r0 < bptr[P.n_lev]) { na = __ldg(P.bdesc + ((size_t)r0 * NT + tid) * 2); nb = __ldg(P.bdesc + ((size_t)r0 * NT + tid) * 2 + 1); }
+    if (r0 < bptr[P.n_lev]) { na = __ldg(P.bdesc + ((size_t)r0 * NT + tid) * 3); nb = __ldg(P.bdesc + ((size_t)r0 * NT + tid) * 3 + 1); }
   }
   if (warp == 0 && nr > 0) {
     // root, one warp: lane l holds rows l and l+32 (root-local); four columns per trip so that
@@ -379,40 +380,42 @@ __device__ __forceinline__ void sp_back_solve(const DevTab& T, const SpTab& P, c
   }
   __syncthreads();
   SP_FT(14);
-  // the other columns, level by level from the top, 8 lanes per column
+  // the other columns, level by level from the top, 8 lanes per column; the records hold BYTE
+  // offsets (entry of L, matching component of u), absent entries point at the zero slot
   const int sub = lane & 7;
+#define SP_BENT(e) acc += SP_LDB(LK, (e) & 0xffffu) * SP_LDB(uu, (e) >> 16)
   for (int lv = P.n_lev - 1; lv >= 0; --lv) {
     const int r0 = bptr[lv], r1 = bptr[lv + 1];
     for (int r = r0; r < r1; ++r) {
       uint4 da, db;
       if (r == r0) { da = na; db = nb; }
-      else { da = __ldg(P.bdesc + ((size_t)r * NT + tid) * 2); db = __ldg(P.bdesc + ((size_t)r * NT + tid) * 2 + 1); }
-      const int j = da.x & 0x7ffu, len = (da.x >> 11) & 0x7fu, valid = (da.x >> 18) & 1u;
-      const int nq = (da.x >> 19) & 15u;                 // rounds of 8 entries this level needs (uniform)
-      const int base = (int)da.y;
-      const unsigned rows[8] = {da.z & 0xffffu, da.z >> 16, da.w & 0xffffu, da.w >> 16,
-                                db.x & 0xffffu, db.x >> 16, db.y & 0xffffu, db.y >> 16};
+      else { da = __ldg(P.bdesc + ((size_t)r * NT + tid) * 3); db = __ldg(P.bdesc + ((size_t)r * NT + tid) * 3 + 1); }
+      const int nq = (da.x >> 17) & 15u;                 // rounds of 8 entries this level needs (uniform)
       double acc = 0.0, acc2 = 0.0;
-#pragma unroll
-      for (int q = 0; q < 8; q += 2) {
-        if (q < nq) {
-          const int t = sub + 8 * q;
-          if (valid && t < len) acc += LK[base + 1 + t] * uu[rows[q]];
-          if (valid && t + 8 < len) acc2 += LK[base + 9 + t] * uu[rows[q + 1]];
-        }
+      { SP_BENT(da.z); }
+      if (nq > 1) { acc2 += SP_LDB(LK, da.w & 0xffffu) * SP_LDB(uu, da.w >> 16); }
+      if (nq > 2) { SP_BENT(db.x); acc2 += SP_LDB(LK, db.y & 0xffffu) * SP_LDB(uu, db.y >> 16); }
+      if (nq > 4) { SP_BENT(db.z); acc2 += SP_LDB(LK, db.w & 0xffffu) * SP_LDB(uu, db.w >> 16); }
+      if (nq > 6) {
+        const uint4 dc = __ldg(P.bdesc + ((size_t)r * NT + tid) * 3 + 2);
+        SP_BENT(dc.x); acc2 += SP_LDB(LK, dc.y & 0xffffu) * SP_LDB(uu, dc.y >> 16);
       }
       acc += acc2;
       acc += __shfl_xor_sync(FULL, acc, 1);
       acc += __shfl_xor_sync(FULL, acc, 2);
       acc += __shfl_xor_sync(FULL, acc, 4);
-      if (valid && sub == 0) uu[j] = rd[j] * (LK[base + 1 + len] - acc);
+      if ((da.x & 0x10000u) && sub == 0) {
+        const unsigned j8 = da.x & 0xffffu;
+        *reinterpret_cast<double*>(reinterpret_cast<char*>(uu) + j8) = SP_LDB(rd, j8) * (SP_LDB(LK, da.y & 0xffffu) - acc);
+      }
     }
     if (lv > 0) {
       const int rn = bptr[lv - 1];
-      if (rn < r0) { na = __ldg(P.bdesc + ((size_t)rn * NT + tid) * 2); nb = __ldg(P.bdesc + ((size_t)rn * NT + tid) * 2 + 1); }
+      if (rn < r0) { na = __ldg(P.bdesc + ((size_t)rn * NT + tid) * 3); nb = __ldg(P.bdesc + ((size_t)rn * NT + tid) * 3 + 1); }
     }
     __syncthreads();
   }
+#undef SP_BENT
 }
 
 // ---------------------------------------------------------------------------------------
@@ -704,14 +707,12 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
         }
         SP_STREAM8(P.C, 0x10000u, SP_VC(jval, wv),
                    { Kg[(o_.y >> 17) & 0x1fffu] = -(gf[o_.y & 0xffffu] + acc_); })
-        __threadfence();                     // Kg must have reached L2 ...
-        sp_fence_async();                    // ... and be ordered before the async-proxy read
-        __syncthreads();
+        sp_fence_async();                    // Kg reaches L2 (the fence carries MEMBAR.ALL.GPU) and is
+        __syncthreads();                     // ordered before the async-proxy read; no L1 invalidation
       }
       for (;;) {
         // stage K (TMA bulk load, mbarrier), then shift the diagonal by (delta_w, -delta_c)
         if (tid == 0) {
-          sp_fence_async();
           sp_mbar_expect_tx(&kbar, (unsigned)(P.Lsz * 8));
           sp_bulk_g2s(LK, Kg, (unsigned)(P.Lsz * 8), &kbar);
         }

@@ -260,16 +260,20 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
       for (size_t c0 = 0; c0 < cols.size(); c0 += ngrp) {
         for (int t = 0; t < nt; ++t) {
           const size_t cc = c0 + (t >> 3);
-          uint4 da = make_uint4(nq << 19, 0u, 0u, 0u), db = make_uint4(0u, 0u, 0u, 0u);
+          const unsigned none = (unsigned)P.zslot * 8u;          // LK[zslot] = 0, u[0] finite
+          unsigned ent[8];
+          for (int q = 0; q < 8; ++q) ent[q] = none;
+          unsigned h0 = nq << 17, h1 = none;
           if (cc < cols.size()) {
             const int j = cols[cc], L = Y.len[j], sub = t & 7;
-            unsigned rows[8];
-            for (int q = 0; q < 8; ++q) rows[q] = (sub + 8 * q < L) ? (unsigned)Y.st[j][sub + 8 * q] : 0u;
-            da = make_uint4((unsigned)j | ((unsigned)L << 11) | (1u << 18) | (nq << 19), (unsigned)Y.colptr[j],
-                            rows[0] | (rows[1] << 16), rows[2] | (rows[3] << 16));
-            db = make_uint4(rows[4] | (rows[5] << 16), rows[6] | (rows[7] << 16), 0u, 0u);
+            for (int q = 0; q < 8; ++q) if (sub + 8 * q < L)
+              ent[q] = ((unsigned)(Y.colptr[j] + 1 + sub + 8 * q) * 8u) | (((unsigned)Y.st[j][sub + 8 * q] * 8u) << 16);
+            h0 = ((unsigned)j * 8u) | (1u << 16) | (nq << 17);
+            h1 = (unsigned)(Y.colptr[j] + 1 + L) * 8u;
           }
-          bdesc.push_back(da); bdesc.push_back(db);
+          bdesc.push_back(make_uint4(h0, h1, ent[0], ent[1]));
+          bdesc.push_back(make_uint4(ent[2], ent[3], ent[4], ent[5]));
+          bdesc.push_back(make_uint4(ent[6], ent[7], 0u, 0u));
         }
         ++rounds;
       }

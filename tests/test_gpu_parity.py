@@ -307,6 +307,47 @@ def test_formation_admm_64_agents(solvers):
     assert spread[-1] < spread[0]            # adjacent agents agree better than at start
 
 
+def test_formation_admm_64_agents_matches_oracle(solvers):
+    """Config 3 at BASELINE size against the sequential ADMM oracle (64 agent NLPs per iteration
+    through the C oracle), iteration by iteration: shared variables, consensus variables and
+    residuals to the tolerance of the reference's own formation test (5e-3,
+    export/tests/formation/test.cpp:200-207); the first iterations, where no agent NLP has a
+    second optimal vertex yet, to the north-star 1e-4."""
+    from omg_tools_b200.problems.admm_gpu import FormationADMMRunner
+    from oracle.admm_ref import ADMMOracle
+    run = FormationADMMRunner(sc.config3(64))
+    orc = ADMMOracle(sc.config3(64, build_solver=False))
+    for it in range(5):
+        rg, ro = run.dual_update(0.), orc.dual_update(0.)
+        st, _ = run.status()
+        assert np.all(st == 0) and np.all(orc.status == 0)
+        dx = np.abs(run.x_i.cpu().numpy() - orc.x_i).max()
+        dz = np.abs(run.z_i.cpu().numpy() - orc.z_i).max()
+        assert dx < 5e-3 and dz < 5e-3, (it, dx, dz)
+        if it < 2:
+            assert dx < NORTH_STAR_TOL and dz < NORTH_STAR_TOL, (it, dx, dz)
+        assert abs(rg[0] - ro[0]) < 1e-2 * max(1., ro[0])
+
+
+def test_quadrotor3d_config4_baseline_size_matches_oracle():
+    """BASELINE config 4 at its stated size (5 plate obstacles: n = 406, m = 2039; the XL kernel
+    with K in the L2-resident scratch): statuses and iteration counts as the C oracle, flat-output
+    splines to the north-star tolerance on the nominal instance, all instances to tol-size."""
+    pr = sc.config4(n_obstacles=5)
+    tb = pr.father.tables
+    assert (tb.n, tb.m) == (406, 2039)
+    X0, P = sc.instance_data(pr, 4, jitter=0.05, seed=4)
+    X0[0], P[0] = sc.instance_data(pr, 1)[0][0], sc.instance_data(pr, 1)[1][0]
+    res = pr.problem.solve_batch(X0, P)
+    ref = ipm_c.solve_batch_full(tb, X0, P, threads=4)
+    assert np.array_equal(res['status'], ref['status']) and res['status'][0] == 0
+    ok = ref['status'] == 0
+    assert np.abs(res['iters'] - ref['iters'])[ok].max() <= 3
+    err = np.abs(res['x'] - ref['x'])[:, :36].max(axis=1)
+    assert err[0] < NORTH_STAR_TOL
+    assert err[ok].max() < 5e-2 and np.abs(res['f'] - ref['f'])[ok].max() < 1e-4
+
+
 def test_device_trajectory_sampling(solvers):
     """Post-solve extraction on device == scipy splev of the reference's
     sample_splines (spline_extra.py:406-410), state and input trajectories."""

@@ -10,7 +10,7 @@ one() {
 import json
 try:
     d=json.loads(open('$O/bench_$lbl.json').read())
-    print('$lbl', 'solves/s %.0f'%d['value'], 'ms/step %.2f'%d['ms_per_step'], 'frac %.4f'%d['roofline']['frac'], 'ctas', d['roofline']['ctas_per_sm'], 'smem', d['roofline']['smem_bytes'], 'e2e %.0f'%d['e2e']['value'], 'iters', d['config']['mean_ip_iterations'], 'ok', d['config']['succeeded_frac'])
+    print('$lbl', 'solves/s %.0f'%d['value'], 'ms/step %.2f'%d['ms_per_step'], 'frac %.4f'%d['roofline']['frac'], 'ctas', d['roofline']['ctas_per_sm'], 'smem', d['roofline']['smem_bytes'], 'e2e %.0f'%d['e2e']['value'], 'iters', d['stats']['mean_ip_iterations'], 'ok', d['stats']['succeeded_frac'])
 except Exception as e:
     print('$lbl failed', e); print(open('$O/bench_$lbl.err').read()[-1500:])
 PY
