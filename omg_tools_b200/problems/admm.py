@@ -147,16 +147,22 @@ class FormationPoint2point(object):
         self.options.update(options or {})
         self.iteration = 0
         self.residuals = {'primal': [], 'dual': [], 'combined': []}
-        nn = [len(fleet.get_neighbors(v)) for v in self.vehicles]
-        if len(set(nn)) != 1:
-            raise ValueError('batched ADMM needs the same number of neighbours for every agent')
-        self.n_nghb = nn[0]
         self.index = {v: k for k, v in enumerate(self.vehicles)}
-        self.nghb = np.array([[self.index[w] for w in fleet.get_neighbors(v)]
-                              for v in self.vehicles], dtype=np.int64)
-        # slot of agent i in neighbour j's neighbour list (who holds z_ij for me)
-        self.back = np.array([[list(self.nghb[j]).index(i) for j in self.nghb[i]]
-                              for i in range(self.N)], dtype=np.int64)
+        # neighbour table: one row per agent, as wide as the largest neighbourhood.  Agents with
+        # fewer neighbours (an open chain, an arbitrary graph) get the missing slots filled with
+        # THEMSELVES: a copy z_ii that must agree with z_i is a redundant consensus constraint --
+        # it leaves the fixed point untouched and keeps ONE NLP structure and ONE projector for the
+        # whole batch (the reference builds per-agent problems instead, admm.py:63-168).
+        table = np.array(fleet.nghb_index, dtype=np.int64).reshape(self.N, -1)
+        own = np.arange(self.N)[:, None]
+        self.real_nghb = table >= 0
+        self.nghb = np.where(table >= 0, table, own)
+        self.n_nghb = self.nghb.shape[1]
+        # slot of agent i in neighbour j's list (who holds z_ij for me); a self slot maps to itself
+        self.back = np.zeros_like(self.nghb)
+        for i in range(self.N):
+            for k, j in enumerate(self.nghb[i]):
+                self.back[i, k] = k if j == i else list(self.nghb[j]).index(i)
 
     # ------------------------------------------------------------------
     def init(self, build_solver=True):
@@ -202,7 +208,35 @@ class FormationPoint2point(object):
         self.par_off = {k: v[0] for k, v in father._par_struct.entries.items()}
         self.veh_label, self.p2p_label, self.upd_label = veh.label, self.p2p.label, self.updater.label
         self._build_consensus_projector()
+        self._derive_shared_sets()
         self._init_agent_data()
+
+    def _derive_shared_sets(self):
+        """q_i / q_ij / q_ji from the coupling constraints of the whole fleet (the reference's
+        interprete_constraints, distributedproblem.py:105-169; here problems/distributed.py), and
+        the check that they are what the batched x-update is built for: every agent shares ALL
+        coefficients of its vehicle splines, and needs copies from exactly its fleet neighbours."""
+        from .distributed import interprete_constraints
+        L, ns = self.L, self.ns
+        syms = [pl.sym_array('q%d' % i, 'var', L * ns, 1)[:, 0] for i in range(self.N)]
+        owners = {s.single_symbol(): (i, self.vehicles[i].label, 'splines_seg0', k)
+                  for i in range(self.N) for k, s in enumerate(syms[i])}
+        cons = []
+        for i in range(self.N):
+            for k_slot, j in enumerate(self.nghb[i]):
+                if not self.real_nghb[i, k_slot]:
+                    continue
+                for k in range(ns):
+                    ci = BSpline(self.basis, syms[i][k * L:(k + 1) * L]) + float(self.vehicles[i].rel_pos_c[k])
+                    cj = BSpline(self.basis, syms[j][k * L:(k + 1) * L]) + float(self.vehicles[j].rel_pos_c[k])
+                    cons.append((ci - cj).coeffs)
+        self.q_i, self.q_ij, self.q_ji = interprete_constraints(owners, cons)
+        for i in range(self.N):
+            want = sorted(set(int(j) for k, j in enumerate(self.nghb[i]) if self.real_nghb[i, k]))
+            got_i = self.q_i[i].get(self.vehicles[i].label, {}).get('splines_seg0', [])
+            if got_i != list(range(L * ns)) or list(self.q_ij[i].keys()) != want:
+                raise ValueError('coupling constraints of agent %d do not share the full vehicle splines '
+                                 'with exactly its fleet neighbours: the batched ADMM does not cover it' % i)
 
     def _build_consensus_projector(self):
         """Coupling constraints of one agent's z-update (formation.py:47-65 seen

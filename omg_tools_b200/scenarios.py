@@ -571,7 +571,8 @@ def config_formation_central(options=None, build_solver=True, soft=True):
     return problem
 
 
-def config3(n_agents=4, options=None, build_solver=True, rank=0, world=1, group=None):
+def config3(n_agents=4, options=None, build_solver=True, rank=0, world=1, group=None,
+            interconnection='circular'):
     """FormationPoint2point ADMM (examples/formation_holonomic.py scaled to
     n_agents, 2 rectangular obstacles as in the C++ formation test): agents on
     a circle of radius 0.2, circular interconnection, rho = 1."""
@@ -579,7 +580,7 @@ def config3(n_agents=4, options=None, build_solver=True, rank=0, world=1, group=
     from .basics.shape import RegularPolyhedron
     from .problems.admm import FormationPoint2point
     vehicles = [Holonomic() for _ in range(n_agents)]
-    fleet = Fleet(vehicles)
+    fleet = Fleet(vehicles, interconnection=interconnection)
     if n_agents == 4:
         configuration = RegularPolyhedron(0.2, n_agents, np.pi / 4.).vertices.T
     else:

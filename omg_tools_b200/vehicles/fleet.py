@@ -15,6 +15,10 @@ TOPOLOGIES = {
     # ring: successor first, then predecessor (the order fixes the layout of z_ij / l_ij)
     'circular': lambda n: np.stack([(np.arange(n) + 1) % n, (np.arange(n) - 1) % n], axis=1),
     'full': lambda n: np.array([[k for k in range(n) if k != i] for i in range(n)], dtype=int).reshape(n, -1),
+    # open chain (not in the reference): the end vehicles have ONE neighbour.  -1 marks a missing
+    # neighbour; the batched ADMM pads such slots with the agent itself (problems/admm.py)
+    'line': lambda n: np.stack([np.where(np.arange(n) + 1 < n, np.arange(n) + 1, -1),
+                                np.arange(n) - 1], axis=1),
 }
 
 
@@ -41,10 +45,16 @@ class Fleet(object):
     # ---- topology ----------------------------------------------------------------------
     def set_neighbors(self):
         self.N = len(self.vehicles)
-        if self.interconnection not in TOPOLOGIES:
-            raise ValueError('Interconnection type ' + str(self.interconnection) + ' not understood.')
-        self.nghb_index = TOPOLOGIES[self.interconnection](self.N) if self.N else np.zeros((0, 0), int)
-        self.nghb_list = {veh: [self.vehicles[k] for k in self.nghb_index[i]]
+        if isinstance(self.interconnection, str):
+            if self.interconnection not in TOPOLOGIES:
+                raise ValueError('Interconnection type ' + str(self.interconnection) + ' not understood.')
+            self.nghb_index = TOPOLOGIES[self.interconnection](self.N) if self.N else np.zeros((0, 0), int)
+        else:
+            # explicit adjacency lists [[j, ...], ...] with different lengths: padded with -1
+            lists = [list(row) for row in self.interconnection]
+            width = max([len(row) for row in lists] + [0])
+            self.nghb_index = np.array([row + [-1] * (width - len(row)) for row in lists], dtype=int).reshape(self.N, width)
+        self.nghb_list = {veh: [self.vehicles[k] for k in self.nghb_index[i] if k >= 0]
                           for i, veh in enumerate(self.vehicles)}
 
     def get_neighbors(self, vehicle):
