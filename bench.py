@@ -40,6 +40,9 @@ def parse():
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                     help='weak: --batch instances per GPU; strong: --batch instances in total')
     ap.add_argument('--agents', type=int, default=64, help='config3: agents of the formation')
+    ap.add_argument('--formations', type=int, default=1,
+                    help='config3: independent formations run side by side in one batch (value counts '
+                         'formation-iterations; 9 x 64 agents fill the 592 resident blocks of one B200)')
     return ap.parse_args()
 
 
@@ -229,7 +232,8 @@ def run_config3(args, rank, world, dev):
     from omg_tools_b200 import scenarios as sc
     from omg_tools_b200.problems.admm_gpu import FormationADMMRunner
     pr = sc.config3(args.agents)
-    run = FormationADMMRunner(pr, rank=rank, world=world)
+    F = max(1, args.formations)
+    run = FormationADMMRunner(pr, rank=rank, world=world, formations=F, spread=0.02 if F > 1 else 0.)
     for _ in range(max(args.warmup, 3)):
         run.dual_update(0.)
     torch.cuda.synchronize(dev)
@@ -245,25 +249,30 @@ def run_config3(args, rank, world, dev):
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     st, it = run.status()
+    per = run.formation_residuals()          # collective: every rank
     if rank == 0:
         ms = float(tm[0])
         tb = pr.tb
-        line = {'metric': 'admm_iterations_per_sec', 'value': args.steps / (ms * 1e-3), 'unit': 'iterations/s',
+        slots = run.solver.info()['ctas_per_sm'] * run.solver.info()['n_sm']
+        line = {'metric': 'admm_iterations_per_sec', 'value': F * args.steps / (ms * 1e-3), 'unit': 'iterations/s',
                 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
                 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong',
                 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
                 'config': {'workload': 'config3: FormationPoint2point ADMM, %d holonomic agents on a ring, '
                            '2 rectangular obstacles, rho = 1' % args.agents, 'n': int(tb.n), 'm': int(tb.m),
-                           'n_par': int(tb.n_par), 'agents': args.agents, 'agents_per_gpu': args.agents // world,
+                           'n_par': int(tb.n_par), 'agents': args.agents, 'formations': F,
+                           'agents_per_gpu': F * args.agents // world,
                            'parallelism': 'agents sharded over %d GPUs; exchange: all-gather of x_i '
                            '(26 doubles/agent), all-reduce of 3 residuals, all-gather of z_ij, l_ij' % world},
-                'stats': {'agent_x_updates_per_sec': args.agents * args.steps / (ms * 1e-3),
+                'stats': {'agent_x_updates_per_sec': F * args.agents * args.steps / (ms * 1e-3),
+                          'batch_iterations_per_sec': args.steps / (ms * 1e-3),
                           'primal_residual': res[0], 'dual_residual': res[1],
+                          'primal_residual_per_formation': [float(v) for v in per[:, 0]],
                           'x_updates_succeeded': bool((st == 0).all()),
                           'mean_ip_iterations': float(it.mean()),
                           'limiter': 'latency of one x-update solve (a block per agent, %d blocks per GPU on '
                                      '%d resident slots) plus three latency-bound collectives per iteration'
-                                     % (args.agents // world, run.solver.info()['ctas_per_sm'] * run.solver.info()['n_sm'])},
+                                     % (F * args.agents // world, slots)},
                 'gpu_launches': 2 * args.steps}
         print(json.dumps(line))
     if world > 1:

@@ -85,6 +85,7 @@ struct DevTab {
   int n_mid, nnz_jx, n_hq_heavy;
   const int2* midg; const int* jtptr; const int* jrow;
   const int *jp_ptr, *jp_a, *jp_c, *mu_ptr, *mu_row, *mu_slot;
+  const int* jxvar; int n_jxvar;       // extra J slots with an x factor (the others are constant in a solve)
   // extra Hessian slots (mid coefficient depends on x or on another mid): wrec[nnz_w ..
   // nnz_w+nnz_wx) hold the term ranges, xq the H positions that gather
   // sum Wx[e.x] * Jx[e.y] * (e.z >= 0 ? Jx[e.z] : 1)
@@ -449,10 +450,17 @@ __device__ __forceinline__ void back_solve_env(const DevTab& T, const Smem& S, c
 // Ends with a block barrier.
 __device__ __forceinline__ void jac_xl(const DevTab& T, const double* __restrict__ V,
                                        const double* __restrict__ xe, double* jx, double* jval,
-                                       const double* dsc) {
+                                       const double* dsc, const bool first) {
   const int tid = threadIdx.x;
-  for (int s = T.nnz_j + tid; s < T.nnz_jx; s += NT)
-    jx[s] = eval_range(T.Jt, T.jtptr[s], T.jtptr[s + 1], V, xe);
+  if (first) {   // every extra slot; the parameter-only ones (A of config 4) keep this value
+    for (int s = T.nnz_j + tid; s < T.nnz_jx; s += NT)
+      jx[s] = eval_range(T.Jt, T.jtptr[s], T.jtptr[s + 1], V, xe);
+  } else {
+    for (int q = tid; q < T.n_jxvar; q += NT) {
+      const int s = T.jxvar[q];
+      jx[s] = eval_range(T.Jt, T.jtptr[s], T.jtptr[s + 1], V, xe);
+    }
+  }
   __syncthreads();
   for (int s = tid; s < T.nnz_j; s += NT) {
     double acc = eval_range(T.Jt, T.jtptr[s], T.jtptr[s + 1], V, xe);
@@ -562,7 +570,7 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
     if (XL) {
       for (int l = tid; l < T.n_mid; l += NT) { const int2 r = T.midg[l]; xe[n + 1 + l] = eval_range(T.Gt, r.x, r.y, V, xe); }
       __syncthreads();
-      jac_xl(T, V, xe, jx, jval, nullptr);
+      jac_xl(T, V, xe, jx, jval, nullptr, true);
     }
 
     // ---- S3: row classification, scaling, starting point -----------------------
@@ -659,7 +667,7 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
                              OP_SUM, OP_SUM, OP_SUM, OP_SUM, OP_MAX, OP_SUM};
       for (int r = 0; r < NRED; ++r) rv[r] = 0.0;
       rv[2] = 1e300;
-      if (XL) jac_xl(T, V, xe, jx, jval, dsc);
+      if (XL) jac_xl(T, V, xe, jx, jval, dsc, false);
       for (int i = tid; i < m; i += NT) {
         const RowRec rr = T.rowrec[i];
         const int r = rt[i];
@@ -1062,7 +1070,7 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
           if (XL) {
             for (int l = tid; l < T.n_mid; l += NT) { const int2 r = T.midg[l]; xt[n + 1 + l] = eval_range(T.Gt, r.x, r.y, V, xt); }
             __syncthreads();
-            jac_xl(T, V, xt, jx, jsv, dsc);       // trial Jacobian -> jsv (free until the next sigma pass)
+            jac_xl(T, V, xt, jx, jsv, dsc, false);       // trial Jacobian -> jsv (free until the next sigma pass)
           }
           const double az = fmin(alpha, a_d);
           pv[0] = 0.0;
@@ -1478,7 +1486,7 @@ omg_feas_kernel(const DevTab T, const FeasArgs F) {
     feas_residual(T, V, xe, lbg, ubg, v, red, &phi, &vmax);
     int steps = 0;
     while (steps < F.max_steps && vmax > 1e-8) {
-      jac_xl(T, V, xe, jx, jx, nullptr);           // jx[0..nnz_j) = Jacobian slots (jval aliases jx)
+      jac_xl(T, V, xe, jx, jx, nullptr, true);           // jx[0..nnz_j) = Jacobian slots (jval aliases jx)
       // normal equations, thread c owns row c of A: sum over the active rows of column c
       for (int c = tid; c < n; c += NT) {
         double* Ac = Am + (size_t)c * n;
@@ -1818,6 +1826,16 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
     T.mu_ptr = upload(h, tb->mu_ptr, (size_t)n_mid + 1, &ok);
     T.mu_row = upload(h, tb->mu_row, tb->n_mu, &ok);
     T.mu_slot = upload(h, tb->mu_slot, tb->n_mu, &ok);
+    std::vector<int> xv;   // extra slots with at least one x factor (xi != n, the constant 1)
+    for (int s = tb->nnz_j; s < tb->nnz_jx; ++s) {
+      bool dep = false;
+      for (int t = tb->J.ptr[s]; t < tb->J.ptr[s + 1] && !dep; ++t)
+        for (int w = 0; w < tb->J.width; ++w) if (tb->J.xi[(size_t)t * tb->J.width + w] != n) { dep = true; break; }
+      if (dep) xv.push_back(s);
+    }
+    T.n_jxvar = (int)xv.size();
+    if (xv.empty()) xv.push_back(0);
+    T.jxvar = upload(h, xv.data(), xv.size(), &ok);
   }
   T.jtptr = upload(h, tb->J.ptr, (size_t)T.nnz_jx + 1, &ok);
   T.jrow = upload(h, tb->jrow, tb->nnz_j, &ok);
@@ -2008,7 +2026,17 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
         h->smem_bytes = h->sp_smem_bytes;
         if (h->sp_dscr_stride > h->dscr_stride) h->dscr_stride = h->sp_dscr_stride;
       } else h->sp_info = "envelope kernels (" + (why.empty() ? std::string("forced") : why) + ")";
-      if (getenv("OMG_B200_VERBOSE")) fprintf(stderr, "[omg_b200] %s\n", h->sp_info.c_str());
+      if (getenv("OMG_B200_VERBOSE")) {
+        fprintf(stderr, "[omg_b200] %s\n", h->sp_info.c_str());
+        if (!h->sp) {   // what the sparse ordering would give on this structure (diagnostic only)
+          SpSym Y; std::string w2;
+          const bool sy = sp_symbolic(tb, Y, &w2);
+          int pairs = 0;
+          for (int j = 0; j < Y.R0 && j < (int)Y.st.size(); ++j) pairs += (int)(Y.st[j].size() * (Y.st[j].size() + 1) / 2);
+          fprintf(stderr, "[omg_b200]   symbolic (%s): N=%d Lsize=%d levels=%d root=%d pairs(non-root)=%d env_size=%d\n",
+                  sy ? "ok" : w2.c_str(), Y.N, Y.Lsize, Y.n_lev, Y.nr, pairs, T.env_size);
+        }
+      }
     }
     if (cudaMalloc(&h->counter, sizeof(int)) != cudaSuccess) ok = false;
     if (cudaMalloc(&h->trace, sizeof(double) * TRACE_ROWS * TRACE_COLS) != cudaSuccess) ok = false;

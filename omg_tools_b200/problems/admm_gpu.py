@@ -75,13 +75,22 @@ class AgentExchange(object):
 class FormationADMMRunner(object):
     """Runs ``FormationPoint2point`` (problems/admm.py) on this rank's GPU."""
 
-    def __init__(self, problem, rank=0, world=1, group=None, device=None):
+    def __init__(self, problem, rank=0, world=1, group=None, device=None, formations=1, spread=0.):
+        """``formations`` > 1 runs that many independent copies of the formation side by side:
+        agent a of copy f is global agent f*N + a, its neighbours are offset the same way, so one
+        x-update launch, one consensus kernel and one set of collectives advance all copies by one
+        ADMM iteration (64 agents fill a ninth of a B200's resident blocks; nine formations fill it).
+        ``spread`` perturbs copy f's initial guess (relative, seeded by f) so the copies do not
+        iterate in lock step.  ``formation_residuals()`` gives the residuals per copy."""
         import torch
         from ..solver import b200
         self.torch, self.b200 = torch, b200
         self.pr = problem
         self.solver = problem.solver
-        self.ex = AgentExchange(problem.N, problem.nghb, problem.back, rank, world, group)
+        self.formations, F, N = int(formations), int(formations), problem.N
+        if F > 1:
+            problem = _Tiled(problem, F, spread)
+        self.ex = AgentExchange(N * F, problem.nghb, problem.back, rank, world, group)
         lo, hi = self.ex.lo, self.ex.hi
         self.lo, self.hi = lo, hi
         dev = device if isinstance(device, torch.device) else \
@@ -128,7 +137,7 @@ class FormationADMMRunner(object):
         the device (they never leave it)."""
         p, torch = self.pr, self.torch
         if self._par_t != t:            # the host part only changes with the time
-            host = p.pack_parameters(t)[self.lo:self.hi]
+            host = np.tile(p.pack_parameters(t), (self.formations, 1))[self.lo:self.hi]
             self._P_host = torch.from_numpy(np.ascontiguousarray(host)).to(self.dev)
             self._par_t = t
         self.P.copy_(self._P_host)
@@ -219,6 +228,37 @@ class FormationADMMRunner(object):
 
     def status(self):
         return self.ST.cpu().numpy(), self.IT.cpu().numpy()
+
+    def formation_residuals(self):
+        """(formations, 3) primal / dual / combined residual of each copy from the per-agent
+        contributions of the last iteration (all ranks; a host read)."""
+        res = self.res
+        if self.ex.world > 1:
+            res = self.ex._all_gather(res)
+        tot = res.reshape(self.formations, -1, 3).sum(1).cpu().numpy()
+        return np.stack([np.sqrt(tot[:, 0]), np.sqrt(tot[:, 1]), tot[:, 2]], axis=1)
+
+
+class _Tiled(object):
+    """The arrays of a formation problem repeated for F side-by-side copies (views the runner
+    reads once at construction); everything else is the problem's."""
+
+    def __init__(self, problem, F, spread):
+        self._p = problem
+        N = problem.N
+        for name in ('X', 'x_i', 'z_i', 'l_i', 'x_j', 'z_ij', 'l_ij', 'z_ji', 'l_ji', 'c'):
+            a = np.asarray(getattr(problem, name))
+            setattr(self, name, np.tile(a, (F,) + (1,) * (a.ndim - 1)))
+        if spread:
+            for f in range(1, F):
+                rng = np.random.RandomState(f)
+                self.X[f * N:(f + 1) * N] *= 1. + spread * rng.uniform(-1., 1., self.X[:N].shape)
+        off = (np.arange(F) * N).repeat(N)[:, None]
+        self.nghb = np.tile(np.asarray(problem.nghb), (F, 1)) + off
+        self.back = np.tile(np.asarray(problem.back), (F, 1))
+
+    def __getattr__(self, name):
+        return getattr(self._p, name)
 
 
 def shift_T(problem):

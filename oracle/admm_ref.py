@@ -27,9 +27,9 @@ class ADMMOracle(object):
         tb = self.p.tb
         if ipm_c.available():
             r = ipm_c.solve_batch_full(tb, x0[None], par[None], threads=1)
-            return r['x'][0], int(r['status'][0])
+            return r['x'][0], int(r['status'][0]), int(r['iters'][0])
         r = ipm_ref.solve(tb, x0, par)
-        return r.x, r.status
+        return r.x, r.status, r.iters
 
     def _blockdiag(self, T, nblk):
         return np.kron(np.eye(nblk), T)
@@ -52,8 +52,9 @@ class ADMMOracle(object):
         p.z_i, p.z_ji, p.l_i, p.l_ji = self.z_i, self.z_ji, self.l_i, self.l_ji
         P = p.pack_parameters(t).copy()
         self.status = np.zeros(N, dtype=int)
+        self.iters = np.zeros(N, dtype=int)
         for i in range(N):
-            self.X[i], self.status[i] = self._solve(self.X[i], P[i])
+            self.X[i], self.status[i], self.iters[i] = self._solve(self.X[i], P[i])
         self.x_i = self.X[:, p.x_off:p.x_off + nsh].copy()
         # ---- communicate x --------------------------------------------------------------
         self.x_j = self.x_i[p.nghb]

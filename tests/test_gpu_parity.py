@@ -311,21 +311,28 @@ def test_formation_admm_64_agents_matches_oracle(solvers):
     """Config 3 at BASELINE size against the sequential ADMM oracle (64 agent NLPs per iteration
     through the C oracle), iteration by iteration: shared variables, consensus variables and
     residuals to the tolerance of the reference's own formation test (5e-3,
-    export/tests/formation/test.cpp:200-207); the first iterations, where no agent NLP has a
-    second optimal vertex yet, to the north-star 1e-4."""
+    export/tests/formation/test.cpp:200-207).
+
+    Tighter where it can be justified: in the first x-update every agent whose interior-point
+    iteration count equals the oracle's agrees to 1e-8.  A few of the 64 agents end one iteration
+    earlier or later than the oracle (a termination test decided by the last bits, tol = 1e-3,
+    problem.py:57): those differ by tol-size (measured 2.7e-4 on agent 24) and their difference
+    then travels through the consensus, so later iterations carry the 5e-3 bound only."""
     from omg_tools_b200.problems.admm_gpu import FormationADMMRunner
     from oracle.admm_ref import ADMMOracle
     run = FormationADMMRunner(sc.config3(64))
     orc = ADMMOracle(sc.config3(64, build_solver=False))
     for it in range(5):
         rg, ro = run.dual_update(0.), orc.dual_update(0.)
-        st, _ = run.status()
+        st, its = run.status()
         assert np.all(st == 0) and np.all(orc.status == 0)
-        dx = np.abs(run.x_i.cpu().numpy() - orc.x_i).max()
+        d = np.abs(run.x_i.cpu().numpy() - orc.x_i).max(1)
         dz = np.abs(run.z_i.cpu().numpy() - orc.z_i).max()
-        assert dx < 5e-3 and dz < 5e-3, (it, dx, dz)
-        if it < 2:
-            assert dx < NORTH_STAR_TOL and dz < NORTH_STAR_TOL, (it, dx, dz)
+        assert d.max() < 5e-3 and dz < 5e-3, (it, d.max(), dz)
+        if it == 0:
+            same = its == orc.iters
+            assert same.sum() >= 58, (its, orc.iters)            # at most 10 % decided by rounding
+            assert d[same].max() < 1e-8, d[same].max()
         assert abs(rg[0] - ro[0]) < 1e-2 * max(1., ro[0])
 
 

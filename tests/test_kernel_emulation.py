@@ -431,6 +431,31 @@ def test_device_pointer_api_on_cpu_tensors(emu):
         assert abs(rg[0] - ro[0]) < 1e-3 * max(1., ro[0])
 
 
+def test_side_by_side_formations_equal_the_single_formation(emu):
+    """FormationADMMRunner(formations=F): F copies of the formation advance in ONE x-update
+    launch / consensus kernel / exchange per iteration.  Without spread every copy repeats the
+    single formation bit for bit (the neighbour offsets keep the copies apart); with spread the
+    copies start from different guesses and each still converges on its own residuals."""
+    import torch
+    from omg_tools_b200.problems.admm_gpu import FormationADMMRunner
+    single = FormationADMMRunner(sc.config3(4), device=torch.device('cpu'))
+    multi = FormationADMMRunner(sc.config3(4), device=torch.device('cpu'), formations=3)
+    for it in range(3):
+        rs, rm = single.dual_update(0.), multi.dual_update(0.)
+    for key in ('x_i', 'z_i', 'l_i', 'z_ji'):
+        a, b = getattr(single, key), getattr(multi, key)
+        for f in range(3):
+            assert torch.equal(a, b[4 * f:4 * f + 4]), (key, f)
+    per = multi.formation_residuals()
+    assert per.shape == (3, 3) and np.allclose(per, np.array(rs)[None, :], rtol=1e-12)
+    assert np.isclose(rm[0] ** 2, 3 * rs[0] ** 2, rtol=1e-12)      # the global sum covers all copies
+    spread = FormationADMMRunner(sc.config3(4), device=torch.device('cpu'), formations=2, spread=0.05)
+    for it in range(3):
+        spread.dual_update(0.)
+    assert (spread.status()[0] == 0).all()
+    assert not torch.equal(spread.x_i[:4], spread.x_i[4:])
+
+
 def _admm_rank(rank, world, port, out):
     import torch
     import torch.distributed as dist
