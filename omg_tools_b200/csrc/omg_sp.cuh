@@ -279,14 +279,15 @@ __device__ __forceinline__ void sp_factor(const DevTab& T, const SpTab& P, const
   SP_FT(15);
   // ---- dense root: right-looking by PANELS of four columns, trailing entries in registers ----
   // entry (row i, column k) lives at R[off(k) + i - k], off(k) = k (nr + 1) - k (k - 1) / 2.
-  // Panel p0: the owners publish the columns p0..p0+3 as they stand after the earlier panels
-  // ("pre-final": the updates of the panel's own columns are still missing), ONE barrier, then
-  // every thread factorises the 4 x 4 diagonal block for itself (10 loads, a few dozen flops --
-  // identical in every thread), finishes the four panel entries of its own row and of the rows
-  // its chunk needs by forward substitution with that block, and applies the rank-4 update
-  //     val[j] -= sum_t (x_it / d_t) * x_{k0+j,t}.
-  // One barrier per four pivots instead of four; the finished panel entries are written over
-  // the pre-final ones after the NEXT barrier (nobody reads that panel any more).
+  // Panel p0, two barriers for four pivots:
+  //   1. the owners publish the columns p0..p0+3 as they stand after the earlier panels (the
+  //      updates of the panel's own columns are still missing)                      -- barrier
+  //   2. every owner of a panel row factorises the 4 x 4 diagonal block for itself (10 loads, a
+  //      few dozen flops, identical in all of them), finishes its own row by forward
+  //      substitution and stores it (rows below the block in place; the block's own rows after
+  //      the barrier, they are still being read); the four diagonal owners report the pivots
+  //                                                                                  -- barrier
+  //   3. rank-4 update of the registers:  val[j] -= sum_t (x_it / d_t) x_{k0+j,t}.
   const int nr = P.nr;
   if (nr > 0) {
     static_assert(SP_RCH == 1 && SP_RCW == 8, "panelised root: one chunk of 8 columns per thread");
@@ -300,29 +301,29 @@ __device__ __forceinline__ void sp_factor(const DevTab& T, const SpTab& P, const
       val[j] = (j < cnt) ? R[k * (nr + 1) - (k * (k - 1)) / 2 + i - k] : 0.0;
     }
 #define SP_ROFF(c) ((c) * (nr + 1) - ((c) * ((c) - 1)) / 2 - (c))      /* R[SP_ROFF(c) + row] */
-    bool prev_mine = false; int prev_p0 = 0, prev_half = 0;
     for (int p0 = 0; p0 < nr; p0 += 4) {
       const int pw = (nr - p0 < 4) ? nr - p0 : 4;
       const int half = p0 - k0;                              // 0 / 4: the panel is inside this chunk
       const bool mine = cnt > 0 && (half == 0 || half == 4) && i >= p0;
+      const int u = i - p0;
+      double* C0 = R + SP_ROFF(p0);
+      double* C1 = R + SP_ROFF(p0 + 1);
+      double* C2 = R + SP_ROFF(p0 + 2);
+      double* C3 = R + SP_ROFF(p0 + 3);
+      double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;        // this row's panel entries
       if (mine) {
-#pragma unroll
-        for (int t = 0; t < 4; ++t) if (half + t < cnt) R[SP_ROFF(p0 + t) + i] = (half == 0) ? val[t] : val[4 + t];
+        x0 = (half == 0) ? val[0] : val[4]; x1 = (half == 0) ? val[1] : val[5];
+        x2 = (half == 0) ? val[2] : val[6]; x3 = (half == 0) ? val[3] : val[7];
+        if (u < pw) {                                        // rows of the diagonal block: published
+          C0[i] = x0;
+          if (u >= 1) C1[i] = x1;
+          if (u >= 2) C2[i] = x2;
+          if (u >= 3) C3[i] = x3;
+        }
       }
       __syncthreads();
-      SP_CHECK()
-      if (prev_mine) {                                       // finished entries of the previous panel
-#pragma unroll
-        for (int t = 0; t < 4; ++t) if (prev_half + t < cnt) R[SP_ROFF(prev_p0 + t) + i] = (prev_half == 0) ? val[t] : val[4 + t];
-      }
-      prev_mine = mine; prev_p0 = p0; prev_half = half;
-      const bool live = cnt > 0 && i > p0 + 3 && k0 + cnt - 1 > p0 + 3;    // entries right of the panel
-      if (mine || live) {
+      if (mine) {
         // diagonal block (missing columns of a short last panel: identity)
-        const double* C0 = R + SP_ROFF(p0);
-        const double* C1 = R + SP_ROFF(p0 + 1);
-        const double* C2 = R + SP_ROFF(p0 + 2);
-        const double* C3 = R + SP_ROFF(p0 + 3);
         const double d0 = C0[p0];
         const double a10 = (pw > 1) ? C0[p0 + 1] : 0.0, g11 = (pw > 1) ? C1[p0 + 1] : 1.0;
         const double a20 = (pw > 2) ? C0[p0 + 2] : 0.0, g21 = (pw > 2) ? C1[p0 + 2] : 0.0, g22 = (pw > 2) ? C2[p0 + 2] : 1.0;
@@ -339,54 +340,42 @@ __device__ __forceinline__ void sp_factor(const DevTab& T, const SpTab& P, const
         const double a32 = g32 - l30 * a20 - l31 * a21;
         const double l32 = a32 * r2;
         const double d3 = g33 - l30 * a30 - l31 * a31 - l32 * a32;
-        const double r3 = sp_rcp(d3);
-        // own row: x_t finished, y_t = x_t / d_t
-        double y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
-        const int u = i - p0;
-        if (u < pw) {                                         // a row of the panel itself (then `mine`)
-          if (mine) {
-            double x0 = d0, x1 = 0.0, x2 = 0.0, x3 = 0.0, dv = d0;
-            if (u == 1) { x0 = a10; x1 = d1; dv = d1; }
-            if (u == 2) { x0 = a20; x1 = a21; x2 = d2; dv = d2; }
-            if (u == 3) { x0 = a30; x1 = a31; x2 = a32; x3 = d3; dv = d3; }
-            if (half == 0) { val[0] = x0; val[1] = x1; val[2] = x2; val[3] = x3; }
-            else { val[4] = x0; val[5] = x1; val[6] = x2; val[7] = x3; }
-            { const int jc = P.R0 + i; SP_PIVOT(jc, dv, eqp) }
-          }
-        } else {
-          const double x0 = C0[i];
-          y0 = x0 * r0;
-          const double x1 = ((pw > 1) ? C1[i] : 0.0) - y0 * a10;
-          y1 = x1 * r1;
-          const double x2 = ((pw > 2) ? C2[i] : 0.0) - y0 * a20 - y1 * a21;
-          y2 = x2 * r2;
-          const double x3 = ((pw > 3) ? C3[i] : 0.0) - y0 * a30 - y1 * a31 - y2 * a32;
-          y3 = x3 * r3;
-          if (mine) {
-            if (half == 0) { val[0] = x0; val[1] = x1; val[2] = x2; val[3] = x3; }
-            else { val[4] = x0; val[5] = x1; val[6] = x2; val[7] = x3; }
-          }
-        }
-        if (live) {
-#pragma unroll
-          for (int j = 0; j < SP_RCW; ++j) {
-            const int k = k0 + j;                             // row k of the panel columns
-            if (j < cnt && k > p0 + 3) {
-              const double f0 = C0[k];
-              const double f1 = ((pw > 1) ? C1[k] : 0.0) - (f0 * r0) * a10;
-              const double f2 = ((pw > 2) ? C2[k] : 0.0) - (f0 * r0) * a20 - (f1 * r1) * a21;
-              const double f3 = ((pw > 3) ? C3[k] : 0.0) - (f0 * r0) * a30 - (f1 * r1) * a31 - (f2 * r2) * a32;
-              val[j] -= y0 * f0 + y1 * f1 + y2 * f2 + y3 * f3;
-            }
-          }
+        if (u < pw) {                                        // a row of the block: entries and pivot
+          double dv = d0;
+          x0 = d0;
+          if (u == 1) { x0 = a10; x1 = d1; dv = d1; }
+          if (u == 2) { x0 = a20; x1 = a21; x2 = d2; dv = d2; }
+          if (u == 3) { x0 = a30; x1 = a31; x2 = a32; x3 = d3; dv = d3; }
+          const int jc = P.R0 + i;
+          SP_PIVOT(jc, dv, eqp)
+        } else {                                             // a row below: forward substitution
+          x1 -= (x0 * r0) * a10;
+          x2 -= (x0 * r0) * a20 + (x1 * r1) * a21;
+          x3 -= (x0 * r0) * a30 + (x1 * r1) * a31 + (x2 * r2) * a32;
+          C0[i] = x0;
+          if (pw > 1) C1[i] = x1;
+          if (pw > 2) C2[i] = x2;
+          if (pw > 3) C3[i] = x3;
         }
       }
-    }
-    __syncthreads();
-    SP_CHECK()
-    if (prev_mine) {
+      __syncthreads();
+      SP_CHECK()
+      if (mine && u < pw) {                                  // the block's own rows, finished
+        C0[i] = x0;
+        if (u >= 1) C1[i] = x1;
+        if (u >= 2) C2[i] = x2;
+        if (u >= 3) C3[i] = x3;
+      }
+      if (cnt > 0 && i > p0 + 3 && k0 + cnt - 1 > p0 + 3) { // entries right of the panel
+        if (!mine) { x0 = C0[i]; x1 = C1[i]; x2 = C2[i]; x3 = C3[i]; }   // (pw == 4 here)
+        const double y0 = x0 * rd[P.R0 + p0], y1 = x1 * rd[P.R0 + p0 + 1],
+                     y2 = x2 * rd[P.R0 + p0 + 2], y3 = x3 * rd[P.R0 + p0 + 3];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) if (prev_half + t < cnt) R[SP_ROFF(prev_p0 + t) + i] = (prev_half == 0) ? val[t] : val[4 + t];
+        for (int j = 0; j < SP_RCW; ++j) {
+          const int k = k0 + j;                               // row k of the panel columns
+          if (j < cnt && k > p0 + 3) val[j] -= y0 * C0[k] + y1 * C1[k] + y2 * C2[k] + y3 * C3[k];
+        }
+      }
     }
 #undef SP_ROFF
   }
