@@ -32,6 +32,9 @@
 #pragma once
 
 #define SP_MAXROOT 40
+#define SP_SNW 4                // columns of a supernode (elimination-tree path)
+#define SP_SNZ 8                // explicit zeros a supernode may add
+#define SP_SNZ_TOTAL 400        // ... and all of them together
 #define SP_RCH 1               // root: row chunks per thread (40 columns -> 125 chunks of 8)
 #define SP_RCW 8               // root: columns per chunk
 #define SP_MAXCOL 62           // |struct| of a column (pair delta is 6 bits)
@@ -58,6 +61,11 @@ struct SpTab {
   const uint4* fpair;              // 2 pairs per uint4, [slice][k2][lane]; pair = {a8 | b8<<16, k8}: byte offsets into LK / rd
   const unsigned* root_ch;         // [SP_RCH * nt] row chunk of a thread: i | k0<<6 | cnt<<12 | eq-pivot<<16
                                    //   (root-local row i (nr = rhs), columns k0 .. k0+cnt-1; 0: none)
+  // panel step of the supernodes with 2..SP_SNW columns: per level, rounds of nt tasks
+  const int* ptask_ptr;            // [n_lev+1] round ranges per level
+  const uint4* ptask;              // {c0 | w<<11 | q<<14 | eq-pivots<<17 | valid<<31, cb0 | cb1<<16, cb2 | cb3<<16, r}:
+                                   //   q = 0: row r of the rows below the block (the last one is the rhs row);
+                                   //   q >= 1: row q of the diagonal block.  cb: byte offset of a column's diagonal entry
   const int* ksign;                // [N] +1 / -1 by permuted index
   // backward sweep: per level, rounds of NT/8 columns; one 32-byte record per lane
   const int* brnd_ptr;             // [n_lev+1] round ranges per level
@@ -210,6 +218,7 @@ __device__ __forceinline__ void sp_factor(const DevTab& T, const SpTab& P, const
   long long t0_ = clock64();
 #define SP_FT(k) do { if (pc && tid == 0) { const long long t_ = clock64(); pc[k] += (double)(t_ - t0_); t0_ = t_; } } while (0)
   const int* lptr = reinterpret_cast<const int*>(sm + S.lptr);
+  const int* tptr = lptr + (2 * P.n_lev + 3);
   if (tid < 3) flags[tid] = 0;
   int slot_ = 0, nneg = 0;
   // ownership of the root (static): every thread holds up to SP_RCH chunks of SP_RCW
@@ -271,6 +280,74 @@ __device__ __forceinline__ void sp_factor(const DevTab& T, const SpTab& P, const
     }
     __syncthreads();
     SP_CHECK()
+    if (lv < P.n_lev && tptr[lv] < tptr[lv + 1]) {
+      // ---- panel step of this level's supernodes (2..SP_SNW columns).  After the gather the
+      // panel holds its pre-final entries; every task factorises the w x w diagonal block for
+      // itself (identical arithmetic in all of them) and finishes ONE row by forward
+      // substitution.  Rows below the block are stored in place (nobody else reads them); the
+      // rows of the block itself -- read by every task -- after the closing barrier.
+      double pv1 = 0.0, pv2 = 0.0, pv3 = 0.0;
+      unsigned po1 = 0xffffffffu, po2 = 0xffffffffu, po3 = 0xffffffffu;
+      for (int tr = tptr[lv]; tr < tptr[lv + 1]; ++tr) {
+        const uint4 tk = __ldg(P.ptask + (size_t)tr * NT + tid);
+        if (tk.x & 0x80000000u) {
+          const int w = (tk.x >> 11) & 7, q = (tk.x >> 14) & 7;
+          const unsigned cb0 = tk.y & 0xffffu, cb1 = tk.y >> 16, cb2 = tk.z & 0xffffu, cb3 = tk.z >> 16;
+          const double d0 = SP_LDB(LK, cb0), a10 = SP_LDB(LK, cb0 + 8), g11 = SP_LDB(LK, cb1);
+          const double a20 = (w > 2) ? SP_LDB(LK, cb0 + 16) : 0.0, g21 = (w > 2) ? SP_LDB(LK, cb1 + 8) : 0.0,
+                       g22 = (w > 2) ? SP_LDB(LK, cb2) : 1.0;
+          const double a30 = (w > 3) ? SP_LDB(LK, cb0 + 24) : 0.0, g31 = (w > 3) ? SP_LDB(LK, cb1 + 16) : 0.0,
+                       g32 = (w > 3) ? SP_LDB(LK, cb2 + 8) : 0.0, g33 = (w > 3) ? SP_LDB(LK, cb3) : 1.0;
+          double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+          unsigned o1 = 0u, o2 = 0u, o3 = 0u;
+          if (q == 0) {                                          // a row below the block: offsets, loads first
+            const unsigned r8 = (tk.w + (unsigned)w) * 8u;       // entry of column t: cb_t + 8 (w - t + r)
+            o1 = cb1 + r8 - 8u; o2 = cb2 + r8 - 16u; o3 = cb3 + r8 - 24u;
+            x0 = SP_LDB(LK, cb0 + r8); x1 = SP_LDB(LK, o1);
+            if (w > 2) x2 = SP_LDB(LK, o2);
+            if (w > 3) x3 = SP_LDB(LK, o3);
+          }
+          const double r0 = sp_rcp(d0);
+          const double l10 = a10 * r0, l20 = a20 * r0, l30 = a30 * r0;
+          const double d1 = g11 - l10 * a10;
+          const double r1 = sp_rcp(d1);
+          const double a21 = g21 - l20 * a10, a31 = g31 - l30 * a10;
+          const double l21 = a21 * r1, l31 = a31 * r1;
+          const double d2 = g22 - l20 * a20 - l21 * a21;
+          const double r2 = sp_rcp(d2);
+          const double a32 = g32 - l30 * a20 - l31 * a21;
+          const double l32 = a32 * r2;
+          const double d3 = g33 - l30 * a30 - l31 * a31 - l32 * a32;
+          if (q == 0) {
+            x1 -= (x0 * r0) * a10;
+            x2 -= (x0 * r0) * a20 + (x1 * r1) * a21;
+            x3 -= (x0 * r0) * a30 + (x1 * r1) * a31 + (x2 * r2) * a32;
+            *reinterpret_cast<double*>(reinterpret_cast<char*>(LK) + o1) = x1;
+            if (w > 2) *reinterpret_cast<double*>(reinterpret_cast<char*>(LK) + o2) = x2;
+            if (w > 3) *reinterpret_cast<double*>(reinterpret_cast<char*>(LK) + o3) = x3;
+          } else {                                               // row q of the block: pivots, stores deferred
+            const int c0 = (int)(tk.x & 0x7ffu);
+            const unsigned eqb = (tk.x >> 17) & 15u;
+            if (q == 1) {
+              { const int jc = c0; SP_PIVOT(jc, d0, (eqb & 1u) != 0u) }
+              { const int jc = c0 + 1; SP_PIVOT(jc, d1, (eqb & 2u) != 0u) }
+              pv1 = d1; po1 = cb1;
+            } else if (q == 2) {
+              { const int jc = c0 + 2; SP_PIVOT(jc, d2, (eqb & 4u) != 0u) }
+              pv1 = a21; po1 = cb1 + 8; pv2 = d2; po2 = cb2;
+            } else {
+              { const int jc = c0 + 3; SP_PIVOT(jc, d3, (eqb & 8u) != 0u) }
+              pv1 = a31; po1 = cb1 + 16; pv2 = a32; po2 = cb2 + 8; pv3 = d3; po3 = cb3;
+            }
+          }
+        }
+      }
+      __syncthreads();
+      SP_CHECK()
+      if (po1 != 0xffffffffu) *reinterpret_cast<double*>(reinterpret_cast<char*>(LK) + po1) = pv1;
+      if (po2 != 0xffffffffu) *reinterpret_cast<double*>(reinterpret_cast<char*>(LK) + po2) = pv2;
+      if (po3 != 0xffffffffu) *reinterpret_cast<double*>(reinterpret_cast<char*>(LK) + po3) = pv3;
+    }
     dA = dB; dB = dC;
 #pragma unroll
     for (int w = 0; w < SP_NPF; ++w) pA[w] = pB[w];
@@ -443,24 +520,40 @@ __device__ __forceinline__ void sp_back_solve(const DevTab& T, const SpTab& P, c
       uint4 da, db;
       if (r == r0) { da = na; db = nb; }
       else { da = __ldg(P.bdesc + ((size_t)r * NT + tid) * 3); db = __ldg(P.bdesc + ((size_t)r * NT + tid) * 3 + 1); }
+      const uint4 dc = __ldg(P.bdesc + ((size_t)r * NT + tid) * 3 + 2);
       const int nq = (da.x >> 17) & 15u;                 // rounds of 8 entries this level needs (uniform)
       double acc = 0.0, acc2 = 0.0;
       { SP_BENT(da.z); }
       if (nq > 1) { acc2 += SP_LDB(LK, da.w & 0xffffu) * SP_LDB(uu, da.w >> 16); }
       if (nq > 2) { SP_BENT(db.x); acc2 += SP_LDB(LK, db.y & 0xffffu) * SP_LDB(uu, db.y >> 16); }
       if (nq > 4) { SP_BENT(db.z); acc2 += SP_LDB(LK, db.w & 0xffffu) * SP_LDB(uu, db.w >> 16); }
-      if (nq > 6) {
-        const uint4 dc = __ldg(P.bdesc + ((size_t)r * NT + tid) * 3 + 2);
-        SP_BENT(dc.x); acc2 += SP_LDB(LK, dc.y & 0xffffu) * SP_LDB(uu, dc.y >> 16);
-      }
+      if (nq > 6) { SP_BENT(dc.x); acc2 += SP_LDB(LK, dc.y & 0xffffu) * SP_LDB(uu, dc.y >> 16); }
+      // the supernode's own triangle: rt = columns of the supernode solved before this one
+      const int rt = (int)((dc.w >> 3) & 7u) - 1 - (int)(dc.w & 7u);
+      const unsigned cb = dc.z;
+      const double e0 = (rt > 0) ? SP_LDB(LK, cb + 8u * (unsigned)rt) : 0.0;
+      const double e1 = (rt > 1) ? SP_LDB(LK, cb + 8u * (unsigned)(rt - 1)) : 0.0;
+      const double e2 = (rt > 2) ? SP_LDB(LK, cb + 8u * (unsigned)(rt - 2)) : 0.0;
+      const unsigned j8 = da.x & 0xffffu;
+      const double rdj = SP_LDB(rd, j8);
       acc += acc2;
       acc += __shfl_xor_sync(FULL, acc, 1);
       acc += __shfl_xor_sync(FULL, acc, 2);
       acc += __shfl_xor_sync(FULL, acc, 4);
-      if ((da.x & 0x10000u) && sub == 0) {
-        const unsigned j8 = da.x & 0xffffu;
-        *reinterpret_cast<double*>(reinterpret_cast<char*>(uu) + j8) = SP_LDB(rd, j8) * (SP_LDB(LK, da.y & 0xffffu) - acc);
+      double vj = SP_LDB(LK, da.y & 0xffffu) - acc;
+      double uj = vj * rdj;                              // final where rt <= 0
+      const int grp8 = lane & 24;
+#pragma unroll
+      for (int st = 0; st < SP_SNW - 1; ++st) {
+        const int src = (rt > st) ? grp8 + 8 * (rt - st) : lane;     // lane group of the column solved at step st
+        const double got = __shfl_sync(FULL, uj, src);
+        if (rt > st) {
+          vj -= ((st == 0) ? e0 : (st == 1) ? e1 : e2) * got;
+          if (rt == st + 1) uj = vj * rdj;
+        }
       }
+      if ((da.x & 0x10000u) && sub == 0)
+        *reinterpret_cast<double*>(reinterpret_cast<char*>(uu) + j8) = uj;
     }
     if (lv > 0) {
       const int rn = bptr[lv - 1];
@@ -504,6 +597,7 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
     int* lp = reinterpret_cast<int*>(sm + S.lptr);
     for (int e = tid; e < P.n_lev + 2; e += NT) lp[e] = P.lev_ptr[e];
     for (int e = tid; e < P.n_lev + 1; e += NT) lp[P.n_lev + 2 + e] = P.brnd_ptr[e];
+    for (int e = tid; e < P.n_lev + 1; e += NT) lp[2 * P.n_lev + 3 + e] = P.ptask_ptr[e];
     if (tid == 0) { sp_mbar_init(&kbar, 1); sp_fence_async(); }
     if (tid == 0) { sg2[m] = 0.0; yd[m] = 0.0; wv[m] = 0.0; }
     for (int i = tid; i <= N; i += NT) rd[i] = 0.0;

@@ -14,6 +14,9 @@ struct SpSym {
   std::vector<int> pos;                       // natural node (var j / n + eq k) -> permuted index
   std::vector<std::vector<int>> st;           // struct of each permuted column (ascending, < N)
   std::vector<int> colptr, lev, len;
+  std::vector<std::vector<int>> st_true;      // struct without the explicit zeros of the supernode padding
+  std::vector<int> sn_first, sn_w;            // first column / width of the supernode of a column (root: itself, 1)
+  int n_pad = 0;                              // explicit zeros stored
   int idx(int i, int j) const {               // L index of entry (row i, column j); i == N: rhs
     if (j >= R0) return colptr[j] + (i - j);
     if (i == j) return colptr[j];
@@ -90,14 +93,77 @@ static bool sp_symbolic(const omg_tables* tb, SpSym& Y, std::string* why) {
          2 * (int)Y.st[R0 - 1].size() >= (N - R0)) --R0;
   if (N == 0) R0 = 0;
   Y.R0 = R0; Y.nr = N - R0;
-  Y.lev.assign(N, 0);
-  int n_lev = 0;
+  // ---- supernodes: paths of the elimination tree (column, parent, grandparent ...) of up to
+  // SP_SNW columns.  Their columns get the structure of the LAST one (explicit zeros where a
+  // column's own structure is smaller: all of it lies inside the last column's clique, so the
+  // symbolic structure stays closed and the padded entries stay exactly zero), are numbered
+  // consecutively and are scheduled as ONE level step: gather from outside, then a dense
+  // (w + rows) x w panel finished without block-wide barriers (omg_sp.cuh, sp_factor).
+  int snw_max = SP_SNW;
+  { const char* e = getenv("OMG_B200_SNW"); if (e && atoi(e) >= 1 && atoi(e) <= SP_SNW) snw_max = atoi(e); }
+  std::vector<int> sn_id(R0, -1);
+  std::vector<std::vector<int>> paths;
+  int total_z = 0;
   for (int j = 0; j < R0; ++j) {
-    const int p = parent[j];
-    if (p >= 0 && p < R0) Y.lev[p] = std::max(Y.lev[p], Y.lev[j] + 1);
-    n_lev = std::max(n_lev, Y.lev[j] + 1);
+    if (sn_id[j] >= 0) continue;
+    const int id = (int)paths.size();
+    std::vector<int> path(1, j);
+    sn_id[j] = id;
+    int zcur = 0;
+    while ((int)path.size() < snw_max) {
+      const int p = parent[path.back()];
+      if (p < 0 || p >= R0 || sn_id[p] >= 0) break;
+      const int L = (int)path.size() + 1;
+      int newz = 0;
+      for (int q = 0; q < L - 1; ++q) newz += (L - 1 - q) + (int)Y.st[p].size() - (int)Y.st[path[q]].size();
+      if (newz > SP_SNZ || total_z + newz - zcur > SP_SNZ_TOTAL) break;
+      path.push_back(p); sn_id[p] = id;
+      total_z += newz - zcur; zcur = newz;
+    }
+    paths.push_back(path);
   }
-  Y.n_lev = n_lev;
+  Y.n_pad = total_z;
+  const int n_sn = (int)paths.size();
+  std::vector<int> sn_lev(n_sn, 0), by_last(n_sn);
+  for (int a = 0; a < n_sn; ++a) by_last[a] = a;
+  std::sort(by_last.begin(), by_last.end(), [&](int a, int b) { return paths[a].back() < paths[b].back(); });
+  for (int a : by_last) {                     // children (smaller last column) come first
+    const int p = parent[paths[a].back()];
+    if (p >= 0 && p < R0) sn_lev[sn_id[p]] = std::max(sn_lev[sn_id[p]], sn_lev[a] + 1);
+  }
+  std::vector<int> sn_order(n_sn);
+  for (int a = 0; a < n_sn; ++a) sn_order[a] = a;
+  std::stable_sort(sn_order.begin(), sn_order.end(), [&](int a, int b) {
+    return sn_lev[a] != sn_lev[b] ? sn_lev[a] < sn_lev[b] : paths[a][0] < paths[b][0]; });
+  std::vector<int> new_of(N);
+  {
+    int nxt = 0;
+    for (int a : sn_order) for (int c : paths[a]) new_of[c] = nxt++;
+    for (int j = R0; j < N; ++j) new_of[j] = j;
+  }
+  {
+    std::vector<std::vector<int>> st2(N), tr2(N);
+    Y.lev.assign(N, 0); Y.sn_first.assign(N, 0); Y.sn_w.assign(N, 1);
+    for (int j = R0; j < N; ++j) { st2[j] = Y.st[j]; tr2[j] = Y.st[j]; Y.sn_first[j] = j; }
+    int n_lev = 0;
+    for (int a = 0; a < n_sn; ++a) {
+      const std::vector<int>& path = paths[a];
+      const int w = (int)path.size(), last = path.back();
+      for (int q = 0; q < w; ++q) {
+        const int c = path[q], cn = new_of[c];
+        for (int b : Y.st[c]) tr2[cn].push_back(new_of[b]);
+        for (int q2 = q + 1; q2 < w; ++q2) st2[cn].push_back(new_of[path[q2]]);
+        for (int b : Y.st[last]) st2[cn].push_back(new_of[b]);
+        std::sort(tr2[cn].begin(), tr2[cn].end());
+        std::sort(st2[cn].begin(), st2[cn].end());
+        Y.lev[cn] = sn_lev[a]; Y.sn_first[cn] = new_of[path[0]]; Y.sn_w[cn] = w;
+      }
+      n_lev = std::max(n_lev, sn_lev[a] + 1);
+    }
+    Y.st.swap(st2); Y.st_true.swap(tr2);
+    Y.n_lev = n_lev;
+    for (int v = 0; v < N; ++v) Y.pos[v] = new_of[Y.pos[v]];
+  }
   Y.len.assign(N, 0); Y.colptr.assign(N + 1, 0);
   for (int j = 0; j < N; ++j) {
     Y.len[j] = (int)Y.st[j].size();
@@ -171,16 +237,17 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
   // ---- pair lists of the left-looking gather -----------------------------------------
   std::vector<std::vector<uint2>> plist(Y.Lsize);
   for (int k = 0; k < R0; ++k) {
-    const std::vector<int>& s = Y.st[k];
-    const int base = Y.colptr[k] + 1, L = Y.len[k];
+    const std::vector<int>& s = Y.st_true[k];
+    const int L = (int)s.size();
     for (int bi = 0; bi < L; ++bi) {
       const int j = s[bi];
+      if (j < R0 && Y.sn_first[j] == Y.sn_first[k]) continue;   // same supernode: the panel step's job
+      const int bpos = Y.idx(j, k);
       for (int ai = bi; ai <= L; ++ai) {           // ai == L: the rhs row
         const int i = (ai < L) ? s[ai] : N;
-        const int tgt = Y.idx(i, j);
-        if (tgt < 0) { *why = "symbolic structure is not closed"; return false; }
-        const unsigned a = (unsigned)(base + ai), b = (unsigned)(base + bi);
-        plist[tgt].push_back(make_uint2((a * 8u) | ((b * 8u) << 16), (unsigned)k * 8u));
+        const int tgt = Y.idx(i, j), apos = Y.idx(i, k);
+        if (tgt < 0 || apos < 0 || bpos < 0) { *why = "symbolic structure is not closed"; return false; }
+        plist[tgt].push_back(make_uint2(((unsigned)apos * 8u) | (((unsigned)bpos * 8u) << 16), (unsigned)k * 8u));
       }
     }
   }
@@ -196,8 +263,9 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
       for (int j = 0; j < R0; ++j) if (Y.lev[j] == lv)
         for (int e = Y.colptr[j]; e < Y.colptr[j + 1]; ++e) {
           lidx.push_back(e);
-          ents.push_back((unsigned)e | ((unsigned)j << 13) | ((e == Y.colptr[j]) ? (1u << 24) : 0u) |
-                         ((e == Y.colptr[j] && is_eq_pos[j]) ? (1u << 25) : 0u));
+          const bool piv = (e == Y.colptr[j]) && Y.sn_w[j] == 1;    // wider supernodes: pivots in the panel step
+          ents.push_back((unsigned)e | ((unsigned)j << 13) | (piv ? (1u << 24) : 0u) |
+                         ((piv && is_eq_pos[j]) ? (1u << 25) : 0u));
         }
     } else {
       for (int e = Y.colptr[R0]; e < Y.Lsize; ++e) if (!plist[e].empty()) { lidx.push_back(e); ents.push_back((unsigned)e); }
@@ -228,6 +296,41 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
   P.lev_ptr = upload(h, lev_ptr.data(), lev_ptr.size(), &ok);
   P.fdesc = upload(h, fdesc.data(), fdesc.size(), &ok);
   P.fpair = upload(h, fpair.data(), fpair.size(), &ok);
+  {  // panel tasks of the supernodes (w >= 2), per level in rounds of nt; the rows of the diagonal
+     // block come last (their results are stored after the level's closing barrier)
+    std::vector<int> tptr;
+    std::vector<uint4> tasks;
+    for (int lv = 0; lv < Y.n_lev; ++lv) {
+      tptr.push_back((int)(tasks.size() / nt));
+      std::vector<uint4> rows, blk;
+      for (int c0 = 0; c0 < R0; ++c0) {
+        if (Y.lev[c0] != lv || Y.sn_first[c0] != c0 || Y.sn_w[c0] < 2) continue;
+        const int w = Y.sn_w[c0];
+        unsigned eqb = 0, cb[4] = {0u, 0u, 0u, 0u};
+        for (int t = 0; t < w; ++t) { cb[t] = (unsigned)Y.colptr[c0 + t] * 8u; if (is_eq_pos[c0 + t]) eqb |= 1u << t; }
+        const int nR = Y.len[c0 + w - 1];                     // rows below the block (+ the rhs row)
+        const unsigned head = (unsigned)c0 | ((unsigned)w << 11) | (eqb << 17) | 0x80000000u;
+        for (int r = 0; r <= nR; ++r) rows.push_back(make_uint4(head, cb[0] | (cb[1] << 16), cb[2] | (cb[3] << 16), (unsigned)r));
+        for (int q = 1; q < w; ++q) blk.push_back(make_uint4(head | ((unsigned)q << 14), cb[0] | (cb[1] << 16), cb[2] | (cb[3] << 16), 0u));
+      }
+      if ((int)blk.size() > nt) { *why = "too many supernodes on one level"; return false; }
+      if (!rows.empty() || !blk.empty()) {
+        const size_t tot = rows.size() + blk.size();
+        const size_t padded = (tot + nt - 1) / nt * nt;
+        std::vector<uint4> lvl(padded, make_uint4(0u, 0u, 0u, 0u));
+        for (size_t q = 0; q < rows.size(); ++q) lvl[q] = rows[q];
+        for (size_t q = 0; q < blk.size(); ++q) lvl[padded - blk.size() + q] = blk[q];    // last round
+        // (rows that would share the last round with the block rows stay where they are: a
+        //  thread has at most one task per round)
+        if (rows.size() > padded - blk.size()) { *why = "panel round overflow"; return false; }
+        tasks.insert(tasks.end(), lvl.begin(), lvl.end());
+      }
+    }
+    tptr.push_back((int)(tasks.size() / nt));
+    if (tasks.empty()) tasks.push_back(make_uint4(0u, 0u, 0u, 0u));
+    P.ptask_ptr = upload(h, tptr.data(), tptr.size(), &ok);
+    P.ptask = upload(h, tasks.data(), tasks.size(), &ok);
+  }
   {  // root: row chunks, dealt round-robin to the threads (long rows first)
     std::vector<unsigned> chunks;
     for (int i = nr; i >= 0; --i) {
@@ -245,35 +348,60 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
     P.root_ch = upload(h, rc.data(), rc.size(), &ok);
   }
   // ---- backward sweep descriptors ---------------------------------------------------------
+  // Per level, rounds of nt/8 columns (8 lanes each).  The columns of a supernode sit in
+  // consecutive lane groups of ONE warp, first column first: the lanes gather the part of
+  // column c that lies outside the supernode (ancestors: already solved), then the warp solves
+  // the supernode's own triangle from its last column down with shuffles.
   {
     std::vector<int> brnd;
     std::vector<uint4> bdesc;
-    const int ngrp = nt / 8;
     int rounds = 0;
+    const int wpr = nt / 32;                                   // warps per round
     for (int lv = 0; lv < Y.n_lev; ++lv) {
       brnd.push_back(rounds);
-      std::vector<int> cols;
-      for (int j = 0; j < R0; ++j) if (Y.lev[j] == lv) cols.push_back(j);
+      std::vector<int> firsts;
+      for (int j = 0; j < R0; ++j) if (Y.lev[j] == lv && Y.sn_first[j] == j) firsts.push_back(j);
+      std::stable_sort(firsts.begin(), firsts.end(), [&](int a, int b) { return Y.sn_w[a] > Y.sn_w[b]; });
+      std::vector<std::vector<int>> bins;                      // warp bins: columns (or -1) of its 4 groups
+      for (int c0 : firsts) {
+        const int w = Y.sn_w[c0];
+        size_t b = 0;
+        for (; b < bins.size(); ++b) if ((int)bins[b].size() + w <= 4) break;
+        if (b == bins.size()) bins.push_back({});
+        for (int t = 0; t < w; ++t) bins[b].push_back(c0 + t);
+      }
       int maxlen = 0;
-      for (int j : cols) maxlen = std::max(maxlen, Y.len[j]);
-      const unsigned nq = (unsigned)((maxlen + 7) / 8);
-      for (size_t c0 = 0; c0 < cols.size(); c0 += ngrp) {
+      for (int j = 0; j < R0; ++j) if (Y.lev[j] == lv) {
+        int cntj = 0;
+        for (int i : Y.st_true[j]) if (!(i < R0 && Y.sn_first[i] == Y.sn_first[j])) ++cntj;
+        maxlen = std::max(maxlen, cntj);
+      }
+      const unsigned nq = (unsigned)std::max(1, (maxlen + 7) / 8);
+      for (size_t b0 = 0; b0 < bins.size(); b0 += wpr) {
         for (int t = 0; t < nt; ++t) {
-          const size_t cc = c0 + (t >> 3);
+          const size_t b = b0 + (size_t)(t >> 5);
+          const int grp = (t >> 3) & 3, sub = t & 7;
           const unsigned none = (unsigned)P.zslot * 8u;          // LK[zslot] = 0, u[0] finite
           unsigned ent[8];
           for (int q = 0; q < 8; ++q) ent[q] = none;
-          unsigned h0 = nq << 17, h1 = none;
-          if (cc < cols.size()) {
-            const int j = cols[cc], L = Y.len[j], sub = t & 7;
-            for (int q = 0; q < 8; ++q) if (sub + 8 * q < L)
-              ent[q] = ((unsigned)(Y.colptr[j] + 1 + sub + 8 * q) * 8u) | (((unsigned)Y.st[j][sub + 8 * q] * 8u) << 16);
-            h0 = ((unsigned)j * 8u) | (1u << 16) | (nq << 17);
-            h1 = (unsigned)(Y.colptr[j] + 1 + L) * 8u;
+          unsigned h0 = nq << 17, h1 = none, cb8 = none, snw = 0u;
+          if (b < bins.size() && grp < (int)bins[b].size()) {
+            const int j = bins[b][grp];
+            std::vector<int> outs;                               // rows outside the supernode (true non-zeros)
+            for (int i : Y.st_true[j]) if (!(i < R0 && Y.sn_first[i] == Y.sn_first[j])) outs.push_back(i);
+            for (int q = 0; q < 8; ++q) if (sub + 8 * q < (int)outs.size()) {
+              const int i = outs[sub + 8 * q];
+              ent[q] = ((unsigned)Y.idx(i, j) * 8u) | (((unsigned)i * 8u) << 16);
+            }
+            const int w = Y.sn_w[j], q = j - Y.sn_first[j];
+            h0 = ((unsigned)j * 8u) | (1u << 16) | (nq << 17) | ((w > 1) ? (1u << 21) : 0u);
+            h1 = (unsigned)Y.idx(N, j) * 8u;
+            cb8 = (unsigned)Y.colptr[j] * 8u;
+            snw = (unsigned)q | ((unsigned)w << 3);
           }
           bdesc.push_back(make_uint4(h0, h1, ent[0], ent[1]));
           bdesc.push_back(make_uint4(ent[2], ent[3], ent[4], ent[5]));
-          bdesc.push_back(make_uint4(ent[6], ent[7], 0u, 0u));
+          bdesc.push_back(make_uint4(ent[6], ent[7], cb8, snw));
         }
         ++rounds;
       }
@@ -433,7 +561,7 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
   S.sig = take(m + 2); S.y = take(m + 2);
   S.red = take((nt / 32) * NRED); S.filt = take(2 * MAXF);
   S.rt8 = take((m + 7) / 8); S.rki = 0;
-  S.lptr = take((2 * Y.n_lev + 4 + 1) / 2 + 1);
+  S.lptr = take((3 * Y.n_lev + 6 + 1) / 2 + 1);
   S.total = off;
   int goff = 0;
   auto gtake = [&](int cnt) { int o = goff; goff += (cnt + 1) & ~1; return o; };
