@@ -61,6 +61,8 @@ struct SpTab {
   const uint4* fpair;              // 2 pairs per uint4, [slice][k2][lane]; pair = {a8 | b8<<16, k8}: byte offsets into LK / rd
   const unsigned* root_ch;         // [SP_RCH * nt] row chunk of a thread: i | k0<<6 | cnt<<12 | eq-pivot<<16
                                    //   (root-local row i (nr = rhs), columns k0 .. k0+cnt-1; 0: none)
+  const uint4* sntab; int n_sn;    // per supernode (+ a dummy): {d1 | d2<<16, d3 | r0<<16, r1 | r2<<16, r3}: byte distance from a
+                                   //   row's entry in the first column to column t, byte offset of 1/d_t in rd
   // panel step of the supernodes with 2..SP_SNW columns: per level, rounds of nt tasks
   const int* ptask_ptr;            // [n_lev+1] round ranges per level
   const uint4* ptask;              // {c0 | w<<11 | q<<14 | eq-pivots<<17 | valid<<31, cb0 | cb1<<16, cb2 | cb3<<16, r}:
@@ -80,7 +82,7 @@ struct SpTab {
 };
 
 struct SpSmem {   // offsets in doubles
-  int LK, jval, xe, xt, dx, gf, rd, diag0, V, sig, y, red, filt, rt8, rki, lptr, total;
+  int LK, jval, xe, xt, dx, gf, rd, diag0, V, sig, y, red, filt, rt8, rki, lptr, sntab, total;
   // scratch (global) offsets in doubles
   int Kc, g, s, zU, dsc, sU, ds, dy, dzU, gt, st, wv, zL, sL, dzL, beq, jt, yg, sigg, gtotal;
 };
@@ -203,8 +205,19 @@ static inline double sp_rcp(double x) { return 1.0 / x; }
   }
 // pair record (8 bytes): byte offsets a8 | b8<<16 into LK, k8 into rd -- no index arithmetic
 #define SP_LDB(base, off) (*reinterpret_cast<const double*>(reinterpret_cast<const char*>(base) + (off)))
-#define SP_PAIR(acc, lo, hi) { acc -= SP_LDB(LK, (lo) & 0xffffu) * SP_LDB(rd, (hi)) * SP_LDB(LK, (lo) >> 16); }
-#define SP_PAIR4(pc) { SP_PAIR(v0, (pc).x, (pc).y) SP_PAIR(v1, (pc).z, (pc).w) }
+// (record: byte offsets of the two rows' entries in the source supernode's first column, byte
+// offset of the supernode's table entry; up to four columns contribute)
+#define SP_PAIR(lo, hi)                                                                        \
+  {                                                                                           \
+    const uint4 st_ = *reinterpret_cast<const uint4*>(sntb + (hi));                           \
+    const char* pa_ = reinterpret_cast<const char*>(LK) + ((lo) & 0xffffu);                   \
+    const char* pb_ = reinterpret_cast<const char*>(LK) + ((lo) >> 16);                       \
+    v0 -= SP_LDB(pa_, 0) * SP_LDB(rd, st_.y >> 16) * SP_LDB(pb_, 0);                          \
+    v1 -= SP_LDB(pa_, st_.x & 0xffffu) * SP_LDB(rd, st_.z & 0xffffu) * SP_LDB(pb_, st_.x & 0xffffu); \
+    v0 -= SP_LDB(pa_, st_.x >> 16) * SP_LDB(rd, st_.z >> 16) * SP_LDB(pb_, st_.x >> 16);      \
+    v1 -= SP_LDB(pa_, st_.y & 0xffffu) * SP_LDB(rd, st_.w) * SP_LDB(pb_, st_.y & 0xffffu);    \
+  }
+#define SP_PAIR4(pc) { SP_PAIR((pc).x, (pc).y) SP_PAIR((pc).z, (pc).w) }
 // descriptor of slice sl (idle if the level has no slice for this warp) / its first 16 pairs
 #define SP_FDESC(d, sl, s_end) { (d) = make_uint4(0xffffffffu, 0u, 0u, 0u); if ((sl) < (s_end)) (d) = __ldg(P.fdesc + (sl) * 32 + lane); }
 #define SP_NPF 2                 // uint4 words (2 pairs each) of every entry fetched one level ahead
@@ -219,6 +232,7 @@ __device__ __forceinline__ void sp_factor(const DevTab& T, const SpTab& P, const
 #define SP_FT(k) do { if (pc && tid == 0) { const long long t_ = clock64(); pc[k] += (double)(t_ - t0_); t0_ = t_; } } while (0)
   const int* lptr = reinterpret_cast<const int*>(sm + S.lptr);
   const int* tptr = lptr + (2 * P.n_lev + 3);
+  const char* sntb = reinterpret_cast<const char*>(sm + S.sntab);
   if (tid < 3) flags[tid] = 0;
   int slot_ = 0, nneg = 0;
   // ownership of the root (static): every thread holds up to SP_RCH chunks of SP_RCW
@@ -227,28 +241,33 @@ __device__ __forceinline__ void sp_factor(const DevTab& T, const SpTab& P, const
 #pragma unroll
   for (int q = 0; q < SP_RCH; ++q) rch[q] = __ldg(P.root_ch + q * NT + tid);
   // ---- levels of the elimination tree (+ the gather into the root as level n_lev) ----
-  // software pipeline over this warp's first slice of each level: descriptors two levels
-  // ahead, the first 16 pairs of every entry one level ahead (independent of the numerics)
+  // A level is worked off in steps of NWARP slices (step k of level lv: slice lptr[lv] + k NWARP +
+  // warp).  Software pipeline over ALL steps, across the level barriers (descriptors and pair
+  // records do not depend on the numerics): descriptor two steps ahead, the first pair words of
+  // every entry one step ahead.
+  int lv = 0, b0 = lptr[0], lv1, b1, lv2, b2;
+#define SP_NEXT(lvn, bn, lvc, bc)                                                              \
+  { lvn = lvc; bn = bc + NWARP;                                                               \
+    if (lvc <= P.n_lev && bn >= lptr[lvc + 1]) { lvn = lvc + 1; bn = (lvn <= P.n_lev) ? lptr[lvn] : 0; } }
+  SP_NEXT(lv1, b1, lv, b0)
+  SP_NEXT(lv2, b2, lv1, b1)
   uint4 dA, dB, pA[SP_NPF], pB[SP_NPF];
-  SP_FDESC(dA, lptr[0] + warp, lptr[1])
-  SP_FDESC(dB, lptr[1] + warp, (P.n_lev >= 1) ? lptr[2] : 0)
+  SP_FDESC(dA, b0 + warp, lptr[1])
+  SP_FDESC(dB, b1 + warp, (lv1 <= P.n_lev) ? lptr[lv1 + 1] : 0)
   SP_FPAIRS(pA, dA)
   __syncthreads();
-  for (int lv = 0; lv <= P.n_lev; ++lv) {
-    const int s0 = lptr[lv], s1 = lptr[lv + 1];
+  while (lv <= P.n_lev) {
     uint4 dC;
-    SP_FPAIRS(pB, dB)                                       // level lv + 1
+    SP_FPAIRS(pB, dB)                                       // next step
     {   // the rest of that slice's pair block: one 128-byte line per lane into L1
       const int nl = ((int)dB.z - SP_NPF) * 4;
       if (lane < nl) sp_prefetch_l1(P.fpair + (dB.y - lane) + (SP_NPF * 4 + lane) * 8);
     }
-    SP_FDESC(dC, (lv + 2 <= P.n_lev) ? lptr[lv + 2] + warp : 0, (lv + 2 <= P.n_lev) ? lptr[lv + 3] : 0)
-    for (int sl = s0 + warp; sl < s1; sl += NWARP) {
-      uint4 d, p[SP_NPF];
-      if (sl == s0 + warp) { d = dA;
-#pragma unroll
-        for (int w = 0; w < SP_NPF; ++w) p[w] = pA[w]; }
-      else { SP_FDESC(d, sl, s1) SP_FPAIRS(p, d) }
+    SP_FDESC(dC, b2 + warp, (lv2 <= P.n_lev) ? lptr[lv2 + 1] : 0)
+    uint4 tk0 = make_uint4(0u, 0u, 0u, 0u);                 // first panel task of this level, fetched early
+    if (lv1 != lv && lv < P.n_lev && tptr[lv] < tptr[lv + 1]) tk0 = __ldg(P.ptask + (size_t)tptr[lv] * NT + tid);
+    {
+      const uint4 d = dA;
       const unsigned e = d.x;
       const int li = (e == 0xffffffffu) ? P.zslot : (int)(e & 0x1fffu);
       const int n4 = (int)d.z;
@@ -260,7 +279,7 @@ __device__ __forceinline__ void sp_factor(const DevTab& T, const SpTab& P, const
         for (int t = 0; t < 4; ++t) if (SP_NPF + t < n4) r[t] = __ldg(q_ + t * 32);
       }
 #pragma unroll
-      for (int w = 0; w < SP_NPF; ++w) if (n4 > w) SP_PAIR4(p[w])
+      for (int w = 0; w < SP_NPF; ++w) if (n4 > w) SP_PAIR4(pA[w])
       if (n4 > SP_NPF) {
 #pragma unroll
         for (int t = 0; t < 4; ++t) if (SP_NPF + t < n4) SP_PAIR4(r[t])
@@ -278,8 +297,10 @@ __device__ __forceinline__ void sp_factor(const DevTab& T, const SpTab& P, const
         if (e & (1u << 24)) { const int j = (e >> 13) & 0x7ffu; SP_PIVOT(j, v, (e & (1u << 25)) != 0u) }
       }
     }
+    if (lv1 != lv) {                                        // the level's last step
     __syncthreads();
     SP_CHECK()
+    SP_FT(8);                                               // gathers (levels and root)
     if (lv < P.n_lev && tptr[lv] < tptr[lv + 1]) {
       // ---- panel step of this level's supernodes (2..SP_SNW columns).  After the gather the
       // panel holds its pre-final entries; every task factorises the w x w diagonal block for
@@ -289,7 +310,7 @@ __device__ __forceinline__ void sp_factor(const DevTab& T, const SpTab& P, const
       double pv1 = 0.0, pv2 = 0.0, pv3 = 0.0;
       unsigned po1 = 0xffffffffu, po2 = 0xffffffffu, po3 = 0xffffffffu;
       for (int tr = tptr[lv]; tr < tptr[lv + 1]; ++tr) {
-        const uint4 tk = __ldg(P.ptask + (size_t)tr * NT + tid);
+        const uint4 tk = (tr == tptr[lv]) ? tk0 : __ldg(P.ptask + (size_t)tr * NT + tid);
         if (tk.x & 0x80000000u) {
           const int w = (tk.x >> 11) & 7, q = (tk.x >> 14) & 7;
           const unsigned cb0 = tk.y & 0xffffu, cb1 = tk.y >> 16, cb2 = tk.z & 0xffffu, cb3 = tk.z >> 16;
@@ -348,12 +369,15 @@ __device__ __forceinline__ void sp_factor(const DevTab& T, const SpTab& P, const
       if (po2 != 0xffffffffu) *reinterpret_cast<double*>(reinterpret_cast<char*>(LK) + po2) = pv2;
       if (po3 != 0xffffffffu) *reinterpret_cast<double*>(reinterpret_cast<char*>(LK) + po3) = pv3;
     }
+    SP_FT(15);                                              // panel steps
+    }
     dA = dB; dB = dC;
 #pragma unroll
     for (int w = 0; w < SP_NPF; ++w) pA[w] = pB[w];
-    if (lv == P.n_lev - 1) SP_FT(8);
+    lv = lv1; b0 = b1; lv1 = lv2; b1 = b2;
+    { int lvn_, bn_; SP_NEXT(lvn_, bn_, lv1, b1) lv2 = lvn_; b2 = bn_; }
   }
-  SP_FT(15);
+#undef SP_NEXT
   // ---- dense root: right-looking by PANELS of four columns, trailing entries in registers ----
   // entry (row i, column k) lives at R[off(k) + i - k], off(k) = k (nr + 1) - k (k - 1) / 2.
   // Panel p0, two barriers for four pivots:
@@ -471,11 +495,12 @@ __device__ __forceinline__ void sp_back_solve(const DevTab& T, const SpTab& P, c
   const double* LK = sm + S.LK; const double* rd = sm + S.rd;
   const int* bptr = reinterpret_cast<const int*>(sm + S.lptr) + (P.n_lev + 2);
   const int nr = P.nr, R0 = P.R0;
-  // descriptor of the first round of the top level, fetched while warp 0 does the root
-  uint4 na = make_uint4(0u, 0u, 0u, 0u), nb = na;
+  // descriptors of the first round of the top level, fetched while warp 0 does the root; after
+  // that every round fetches the next one's before it starts (they do not depend on the numerics)
+  uint4 na = make_uint4(0u, 0u, 0u, 0u), nb = na, nc = na;
   if (P.n_lev > 0) {
-    const int r0 = bptr[P.n_lev - 1];
-    if (r0 < bptr[P.n_lev]) { na = __ldg(P.bdesc + ((size_t)r0 * NT + tid) * 3); nb = __ldg(P.bdesc + ((size_t)r0 * NT + tid) * 3 + 1); }
+    const size_t o_ = ((size_t)bptr[P.n_lev - 1] * NT + tid) * 3;
+    na = __ldg(P.bdesc + o_); nb = __ldg(P.bdesc + o_ + 1); nc = __ldg(P.bdesc + o_ + 2);
   }
   if (warp == 0 && nr > 0) {
     // root, one warp: lane l holds rows l and l+32 (root-local); four columns per trip so that
@@ -517,10 +542,11 @@ __device__ __forceinline__ void sp_back_solve(const DevTab& T, const SpTab& P, c
   for (int lv = P.n_lev - 1; lv >= 0; --lv) {
     const int r0 = bptr[lv], r1 = bptr[lv + 1];
     for (int r = r0; r < r1; ++r) {
-      uint4 da, db;
-      if (r == r0) { da = na; db = nb; }
-      else { da = __ldg(P.bdesc + ((size_t)r * NT + tid) * 3); db = __ldg(P.bdesc + ((size_t)r * NT + tid) * 3 + 1); }
-      const uint4 dc = __ldg(P.bdesc + ((size_t)r * NT + tid) * 3 + 2);
+      const uint4 da = na, db = nb, dc = nc;
+      {
+        const int rn = (r + 1 < r1) ? r + 1 : ((lv > 0) ? bptr[lv - 1] : -1);
+        if (rn >= 0) { const size_t o_ = ((size_t)rn * NT + tid) * 3; na = __ldg(P.bdesc + o_); nb = __ldg(P.bdesc + o_ + 1); nc = __ldg(P.bdesc + o_ + 2); }
+      }
       const int nq = (da.x >> 17) & 15u;                 // rounds of 8 entries this level needs (uniform)
       double acc = 0.0, acc2 = 0.0;
       { SP_BENT(da.z); }
@@ -554,10 +580,6 @@ __device__ __forceinline__ void sp_back_solve(const DevTab& T, const SpTab& P, c
       }
       if ((da.x & 0x10000u) && sub == 0)
         *reinterpret_cast<double*>(reinterpret_cast<char*>(uu) + j8) = uj;
-    }
-    if (lv > 0) {
-      const int rn = bptr[lv - 1];
-      if (rn < r0) { na = __ldg(P.bdesc + ((size_t)rn * NT + tid) * 3); nb = __ldg(P.bdesc + ((size_t)rn * NT + tid) * 3 + 1); }
     }
     __syncthreads();
   }
@@ -598,6 +620,7 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
     for (int e = tid; e < P.n_lev + 2; e += NT) lp[e] = P.lev_ptr[e];
     for (int e = tid; e < P.n_lev + 1; e += NT) lp[P.n_lev + 2 + e] = P.brnd_ptr[e];
     for (int e = tid; e < P.n_lev + 1; e += NT) lp[2 * P.n_lev + 3 + e] = P.ptask_ptr[e];
+    for (int e = tid; e < P.n_sn; e += NT) reinterpret_cast<uint4*>(sm + S.sntab)[e] = P.sntab[e];
     if (tid == 0) { sp_mbar_init(&kbar, 1); sp_fence_async(); }
     if (tid == 0) { sg2[m] = 0.0; yd[m] = 0.0; wv[m] = 0.0; }
     for (int i = tid; i <= N; i += NT) rd[i] = 0.0;

@@ -235,23 +235,43 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
 
 
   // ---- pair lists of the left-looking gather -----------------------------------------
+  // One record per (target entry, source SUPERNODE): with the rows i, j of the target among the
+  // rows R below the supernode's block, the w columns contribute
+  //     sum_t x_it x_jt / d_t        (padded entries are zero, so every column may be summed).
+  // Record = {byte offset of (i, first column) | of (j, first column) << 16, byte offset of the
+  // supernode's table entry}; the table entry holds the byte distance from a row's entry in the
+  // first column to its entry in column t, and where 1/d_t lives (a zero for t >= w).
   std::vector<std::vector<uint2>> plist(Y.Lsize);
-  for (int k = 0; k < R0; ++k) {
-    const std::vector<int>& s = Y.st_true[k];
-    const int L = (int)s.size();
-    for (int bi = 0; bi < L; ++bi) {
-      const int j = s[bi];
-      if (j < R0 && Y.sn_first[j] == Y.sn_first[k]) continue;   // same supernode: the panel step's job
-      const int bpos = Y.idx(j, k);
-      for (int ai = bi; ai <= L; ++ai) {           // ai == L: the rhs row
-        const int i = (ai < L) ? s[ai] : N;
-        const int tgt = Y.idx(i, j), apos = Y.idx(i, k);
-        if (tgt < 0 || apos < 0 || bpos < 0) { *why = "symbolic structure is not closed"; return false; }
-        plist[tgt].push_back(make_uint2(((unsigned)apos * 8u) | (((unsigned)bpos * 8u) << 16), (unsigned)k * 8u));
+  std::vector<uint4> sntab;
+  for (int c0 = 0; c0 < R0; ++c0) {
+    if (Y.sn_first[c0] != c0) continue;
+    const int w = Y.sn_w[c0];
+    const unsigned snoff = (unsigned)sntab.size() * 16u;
+    unsigned dl[4] = {0u, 0u, 0u, 0u}, rr[4];
+    for (int t = 0; t < 4; ++t) {
+      rr[t] = (unsigned)((t < w) ? (c0 + t) : N) * 8u;             // rd[N] = 0
+      if (t > 0 && t < w) dl[t] = (unsigned)((Y.colptr[c0 + t] - t) - Y.colptr[c0]) * 8u;
+    }
+    sntab.push_back(make_uint4(dl[1] | (dl[2] << 16), dl[3] | (rr[0] << 16), rr[1] | (rr[2] << 16), rr[3]));
+    const std::vector<int>& Rl = Y.st[c0 + w - 1];                 // rows below the block
+    const int nR = (int)Rl.size();
+    const int row0 = Y.colptr[c0] + w;                             // entry (Rl[0], c0)
+    for (int bi = 0; bi < nR; ++bi) {
+      const int j = Rl[bi];
+      for (int ai = bi; ai <= nR; ++ai) {                          // ai == nR: the rhs row
+        const int i = (ai < nR) ? Rl[ai] : N;
+        const int tgt = Y.idx(i, j);
+        if (tgt < 0) { *why = "symbolic structure is not closed"; return false; }
+        plist[tgt].push_back(make_uint2(((unsigned)(row0 + ai) * 8u) | (((unsigned)(row0 + bi) * 8u) << 16), snoff));
       }
     }
   }
-  const uint2 padpair = make_uint2(((unsigned)P.zslot * 8u) | (((unsigned)P.zslot * 8u) << 16), (unsigned)N * 8u);
+  const unsigned sn_dummy = (unsigned)sntab.size() * 16u;           // pad records: 0 * rd[N] * 0
+  sntab.push_back(make_uint4(0u, ((unsigned)N * 8u) << 16, ((unsigned)N * 8u) | (((unsigned)N * 8u) << 16), (unsigned)N * 8u));
+  if (sntab.size() * 16u >= 65536u) { *why = "too many supernodes"; return false; }
+  P.n_sn = (int)sntab.size();
+  P.sntab = upload(h, sntab.data(), sntab.size(), &ok);
+  const uint2 padpair = make_uint2(((unsigned)P.zslot * 8u) | (((unsigned)P.zslot * 8u) << 16), sn_dummy);
   std::vector<char> is_eq_pos(N, 0);          // permuted index -> pivot of an equality row
   for (int k = 0; k < n_eq; ++k) is_eq_pos[Y.pos[n + k]] = 1;
   std::vector<int> lev_ptr;
@@ -562,6 +582,7 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
   S.red = take((nt / 32) * NRED); S.filt = take(2 * MAXF);
   S.rt8 = take((m + 7) / 8); S.rki = 0;
   S.lptr = take((3 * Y.n_lev + 6 + 1) / 2 + 1);
+  S.sntab = take(2 * P.n_sn);
   S.total = off;
   int goff = 0;
   auto gtake = [&](int cnt) { int o = goff; goff += (cnt + 1) & ~1; return o; };

@@ -314,7 +314,8 @@ def test_formation_admm_64_agents_matches_oracle(solvers):
     export/tests/formation/test.cpp:200-207).
 
     Tighter where it can be justified: in the first x-update every agent whose interior-point
-    iteration count equals the oracle's agrees to 1e-8.  A few of the 64 agents end one iteration
+    iteration count equals the oracle's agrees to 1e-6 (measured on B200: 1.9e-7 -- summation-order
+    rounding of the factorisation carried through ~10 Newton steps; 1e-10 in the CPU emulation).  A few of the 64 agents end one iteration
     earlier or later than the oracle (a termination test decided by the last bits, tol = 1e-3,
     problem.py:57): those differ by tol-size (measured 2.7e-4 on agent 24) and their difference
     then travels through the consensus, so later iterations carry the 5e-3 bound only."""
@@ -332,7 +333,7 @@ def test_formation_admm_64_agents_matches_oracle(solvers):
         if it == 0:
             same = its == orc.iters
             assert same.sum() >= 58, (its, orc.iters)            # at most 10 % decided by rounding
-            assert d[same].max() < 1e-8, d[same].max()
+            assert d[same].max() < 1e-6, d[same].max()
         assert abs(rg[0] - ro[0]) < 1e-2 * max(1., ro[0])
 
 

@@ -44,7 +44,7 @@ def _compare(pr, B, jitter, seed, n_flat, options=None):
 
 
 @pytest.mark.parametrize('kernel, name, B, layout', [
-    ('sparse', 'config1', 3, (27744, 8)), ('sparse', 'config2', 2, (53776, 4)), ('sparse', 'config5', 2, None),
+    ('sparse', 'config1', 3, (28368, 7)), ('sparse', 'config2', 2, (54832, 4)), ('sparse', 'config5', 2, None),
     ('envelope', 'config1', 3, (97408, 2)), ('envelope', 'config2', 2, (113552, 2)), ('envelope', 'config5', 2, None)])
 def test_standard_kernel_matches_oracle(emu, monkeypatch, kernel, name, B, layout):
     """BASELINE configs 1, 2, 5 through both kernel families: omg_ipm_kernel_sp (sparse

@@ -34,8 +34,8 @@ names = ['setup/accept', 'row pass', 'col pass+reduce', 'barrier logic', 'sigma 
          'W+border+rhs', 'factor:diag', 'factor:panel', 'factor:trailing', 'back solve', 'step pass',
          'line search', 'tail']
 tot = ph[:8].sum() + ph[10:14].sum()
-names[7:10] = ['factor (total)', '  of it: levels', '  of it: root']
-names += ['  back: root part', '  factor: gather into root']
+names[7:10] = ['factor (total)', '  of it: gathers', '  of it: root']
+names += ['  back: root part', '  factor: panel steps']
 print('phase cycles of instance 0 (total %.0f, %d iterations -> %.0f cycles/iter):' % (tot, res['iters'][0], tot / max(1, res['iters'][0])))
 for nme, c in zip(names, ph[:16]):
     print('  %-16s %12.0f  %5.1f%%' % (nme, c, 100 * c / tot))
