@@ -54,6 +54,8 @@ struct SpStream { int n_chunk; const void* rec; };
 struct SpTab {
   int nt;                          // threads per block the streams were laid out for
   int Lsz, zslot, R0, nr, n_lev, root0, n_rootent;
+  int neg_lev;                     // levels < neg_lev hold only variables no equality row touches: a negative
+                                   //   pivot there already decides the inertia test (see SP_CHECK)
   // factorisation levels (+ the gather into the root as level n_lev): slices of 32 entries
   const int* lev_ptr;              // [n_lev+2] slice ranges
   const uint4* fdesc;              // per slice lane: {entry word, pair offset (uint4 units), n4, 0}
@@ -174,11 +176,30 @@ static inline double sp_rcp(double x) { return 1.0 / x; }
 #define SP_VG(X) (SP_COEF(o_) * V[o_.z & 0x7fffu] * (X)[o_.z >> 16] * (X)[o_.w & 0xffffu])   // G: a, b = x0, x1, c = row
 #define SP_VC(JV, YV) ((JV)[o_.x & 0xffffu] * (YV)[o_.x >> 16])                             // C / R: slot | index<<16
 
+// objective terms (few, off the hot path): ONE out-of-line copy instead of an unrolled inline
+// expansion at every call site -- the kernel's code is larger than the instruction cache
+#ifndef OMG_CPU_EMU
+__device__ __noinline__
+#else
+static
+#endif
+double sp_eval_range(const PTerm* t, int lo, int hi, const double* V, const double* xe) {
+  double acc = 0.0;
+  int aux;
+#pragma unroll 1
+  for (int k = lo; k < hi; ++k) acc += term_value(t + k, V, xe, &aux);
+  return acc;
+}
+
 // ---------------------------------------------------------------------------------------
 // factorisation K = L D L^T in LK (unscaled columns A = L D), rd = 1/d.  ctl->fail on a bad
 // pivot or wrong inertia (mode 0: IPOPT's count test; mode 1: sign by position).
 // flags[3]: per-level pivot reports (negative count | bad<<16 | eq-bad<<24), rotating so that
 // a level's report is read after its barrier while the next level already writes its own.
+// Early rejection (mode 0): while every eliminated column is a variable v that no equality row
+// touches (levels < P.neg_lev), a negative pivot means v^T H v < 0 for a v with J_eq v = 0 --
+// the reduced Hessian is not positive definite, the inertia cannot be (n, n_eq, 0), and the
+// count at the end of the factorisation would say the same (more than n_eq negatives).
 // ---------------------------------------------------------------------------------------
 #define SP_PIVOT(j, v, isneg_)                                                                 \
   {                                                                                           \
@@ -197,7 +218,7 @@ static inline double sp_rcp(double x) { return 1.0 / x; }
     if (tid == 0) flags[(slot_ == 0) ? 2 : slot_ - 1] = 0;                                    \
     slot_ = (slot_ == 2) ? 0 : slot_ + 1;                                                     \
     nneg += rep_ & 0xffff;                                                                    \
-    if ((rep_ >> 16) || (mode == 0 && nneg > T.n_eq)) {                                       \
+    if ((rep_ >> 16) || (mode == 0 && (nneg > T.n_eq || (nneg > 0 && lv < P.neg_lev)))) {    \
       if (tid == 0) { ctl->fail = 1; ctl->eq_fail = (rep_ >> 24) ? 1 : 0; }                   \
       __syncthreads();                                                                        \
       return;                                                                                 \
@@ -671,7 +692,7 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
     // ---- S3: scaling, row classification, starting point --------------------------------
     double fmaxv = 0.0;
     for (int j = tid; j < n; j += NT)
-      fmaxv = fmax(fmaxv, fabs(eval_range(T.DFt, T.dfptr[j], T.dfptr[j + 1], V, xe)));
+      fmaxv = fmax(fmaxv, fabs(sp_eval_range(T.DFt, T.dfptr[j], T.dfptr[j + 1], V, xe)));
     {
       double r1[1] = {fmaxv}; const int o1[1] = {OP_MAX};
       block_reduce<1>(r1, o1, red);
@@ -730,7 +751,7 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
       ctl.theta_max = -1.0; ctl.theta_min = -1.0;
       ctl.delta_w_last = 0.0; ctl.nfilt = 0; ctl.status = -1; ctl.iter = 0;
       ctl.fsc = fsc; ctl.alpha = 0.0; ctl.delta_w = 0.0; ctl.n_restart = 0;
-      ctl.f = fsc * eval_range(T.Ft, 0, T.n_f, V, xe);
+      ctl.f = fsc * sp_eval_range(T.Ft, 0, T.n_f, V, xe);
     }
     __syncthreads();
     if (ctl.n_eq < 0) {   // equality pattern differs from the lowered structure
@@ -778,7 +799,7 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
       TICK(1);
       // ---- I2: columns: grad f, dual residual (J^T y through the CSC ELL) --------------
       for (int j = tid; j < n; j += NT)
-        gf[j] = ctl.fsc * eval_range(T.DFt, T.dfptr[j], T.dfptr[j + 1], V, xe);
+        gf[j] = ctl.fsc * sp_eval_range(T.DFt, T.dfptr[j], T.dfptr[j + 1], V, xe);
       __syncthreads();
       SP_STREAM8(P.C, 0x10000u, SP_VC(jval, yd), rv[10] = fmax(rv[10], fabs(gf[o_.y & 0xffffu] + acc_));)
       block_reduce<NRED>(rv, rop, red);
@@ -999,7 +1020,7 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
             if (r & 2) tv[1] += log(su_ - si);
           }
         }
-        for (int t = tid; t < T.n_f; t += NT) { int aux; tv[2] += term_value(T.Ft + t, V, xt, &aux); }
+        for (int t = tid; t < T.n_f; t += NT) tv[2] += sp_eval_range(T.Ft, t, t + 1, V, xt);
         block_reduce<3>(tv, top, red);
         ft = ctl.fsc * tv[2];
         const double tht = tv[0], pht = ft - mu * tv[1];
@@ -1069,11 +1090,11 @@ __device__ __forceinline__ void ipm_body_sp(const DevTab& T, const SpTab& P, con
           __syncthreads();
           SP_STREAM8(P.C, 0x10000u, SP_VC(jt, wv),
                      { const int c_ = o_.y & 0xffffu;
-                       pv[0] += fabs(ctl.fsc * eval_range(T.DFt, T.dfptr[c_], T.dfptr[c_ + 1], V, xt) + acc_); })
+                       pv[0] += fabs(ctl.fsc * sp_eval_range(T.DFt, T.dfptr[c_], T.dfptr[c_ + 1], V, xt) + acc_); })
           block_reduce<1>(pv, pop, red);
           if (isfinite(pv[0]) && pv[0] <= SOFT_RESTO_FACTOR * pd0) {
             double fv[1]; fv[0] = 0.0;
-            for (int t = tid; t < T.n_f; t += NT) { int aux; fv[0] += term_value(T.Ft + t, V, xt, &aux); }
+            for (int t = tid; t < T.n_f; t += NT) fv[0] += sp_eval_range(T.Ft, t, t + 1, V, xt);
             block_reduce<1>(fv, pop, red);
             ft = ctl.fsc * fv[0];
             accepted = true; soft = true; ftype = true;

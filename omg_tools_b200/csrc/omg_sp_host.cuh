@@ -232,6 +232,21 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
   P.zslot = Y.Lsize; P.Lsz = (Y.Lsize + 2) & ~1;
   P.R0 = R0; P.nr = nr; P.n_lev = Y.n_lev; P.root0 = Y.colptr[R0];
   P.n_rootent = Y.Lsize - Y.colptr[R0];
+  {  // leading levels made of variables that no equality row touches (early inertia rejection)
+    std::vector<char> touched(n, 0);
+    for (int k = 0; k < n_eq; ++k) {
+      const int i = tb->kkt_eq_rows[k];
+      for (int s = tb->jrow_ptr[i]; s < tb->jrow_ptr[i + 1]; ++s) touched[tb->jcol[s]] = 1;
+    }
+    std::vector<int> node_of(N, 0);
+    for (int v = 0; v < N; ++v) node_of[Y.pos[v]] = v;
+    int nl = Y.n_lev;
+    for (int j = 0; j < R0; ++j) {
+      const int v = node_of[j];
+      if (v >= n || touched[v]) nl = std::min(nl, Y.lev[j]);
+    }
+    P.neg_lev = nl;
+  }
 
 
   // ---- pair lists of the left-looking gather -----------------------------------------
@@ -606,7 +621,7 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
   h->sp_ctas = occ;
   h->sp_dscr_stride = goff + 8;
   h->sp_info = "sparse LDL^T: N=" + std::to_string(N) + " nnz(L)=" + std::to_string(Y.Lsize) +
-               " levels=" + std::to_string(Y.n_lev) + " root=" + std::to_string(nr) +
+               " levels=" + std::to_string(Y.n_lev) + " (early-reject " + std::to_string(P.neg_lev) + ")" + " root=" + std::to_string(nr) +
                " pairs=" + std::to_string(fpair.size() * 2) + " nt=" + std::to_string(nt) +
                " ctas/SM=" + std::to_string(occ) + " smem=" + std::to_string(h->sp_smem_bytes);
   return true;
