@@ -1616,7 +1616,7 @@ struct omg_problem {
   DescCache* shift_desc = nullptr;   // device copy of the last omg_shift_batch block descriptor
   // sparse kernel variant (omg_sp.cuh / omg_sp_host.cuh)
   bool sp = false; SpTab P; SpSmem SS; size_t sp_smem_bytes = 0; int sp_ctas = 0, sp_dscr_stride = 0;
-  std::string sp_info;
+  std::string sp_info, sp_info_extra;
   // launch configuration of the envelope kernels (kept: inertia_mode = 1 is tied to the
   // envelope's elimination order and always runs there)
   int env_nt = 0, env_ctas = 0; size_t env_smem_bytes = 0;

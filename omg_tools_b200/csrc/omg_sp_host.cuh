@@ -100,7 +100,9 @@ static bool sp_symbolic(const omg_tables* tb, SpSym& Y, std::string* why) {
   // consecutively and are scheduled as ONE level step: gather from outside, then a dense
   // (w + rows) x w panel finished without block-wide barriers (omg_sp.cuh, sp_factor).
   int snw_max = SP_SNW;
+  int snz_max = SP_SNZ;                       // (both: tuning knobs for experiments)
   { const char* e = getenv("OMG_B200_SNW"); if (e && atoi(e) >= 1 && atoi(e) <= SP_SNW) snw_max = atoi(e); }
+  { const char* e = getenv("OMG_B200_SNZ"); if (e && atoi(e) >= 0) snz_max = atoi(e); }
   std::vector<int> sn_id(R0, -1);
   std::vector<std::vector<int>> paths;
   int total_z = 0;
@@ -116,7 +118,7 @@ static bool sp_symbolic(const omg_tables* tb, SpSym& Y, std::string* why) {
       const int L = (int)path.size() + 1;
       int newz = 0;
       for (int q = 0; q < L - 1; ++q) newz += (L - 1 - q) + (int)Y.st[p].size() - (int)Y.st[path[q]].size();
-      if (newz > SP_SNZ || total_z + newz - zcur > SP_SNZ_TOTAL) break;
+      if (newz > snz_max || total_z + newz - zcur > SP_SNZ_TOTAL) break;
       path.push_back(p); sn_id[p] = id;
       total_z += newz - zcur; zcur = newz;
     }
@@ -246,6 +248,7 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
       if (v >= n || touched[v]) nl = std::min(nl, Y.lev[j]);
     }
     P.neg_lev = nl;
+    { const char* e = getenv("OMG_B200_EARLY_REJECT"); if (e && atoi(e) == 0) P.neg_lev = 0; }   // experiment knob
   }
 
 
@@ -363,6 +366,7 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
     }
     tptr.push_back((int)(tasks.size() / nt));
     if (tasks.empty()) tasks.push_back(make_uint4(0u, 0u, 0u, 0u));
+    h->sp_info_extra = " panel-rounds=" + std::to_string(tptr.back());
     P.ptask_ptr = upload(h, tptr.data(), tptr.size(), &ok);
     P.ptask = upload(h, tasks.data(), tasks.size(), &ok);
   }
@@ -442,6 +446,7 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
       }
     }
     brnd.push_back(rounds);
+    h->sp_info_extra += " back-rounds=" + std::to_string(rounds);
     P.brnd_ptr = upload(h, brnd.data(), brnd.size(), &ok);
     P.bdesc = upload(h, bdesc.data(), bdesc.size(), &ok);
   }
@@ -621,7 +626,7 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
   h->sp_ctas = occ;
   h->sp_dscr_stride = goff + 8;
   h->sp_info = "sparse LDL^T: N=" + std::to_string(N) + " nnz(L)=" + std::to_string(Y.Lsize) +
-               " levels=" + std::to_string(Y.n_lev) + " (early-reject " + std::to_string(P.neg_lev) + ")" + " root=" + std::to_string(nr) +
+               h->sp_info_extra + " levels=" + std::to_string(Y.n_lev) + " (early-reject " + std::to_string(P.neg_lev) + ")" + " root=" + std::to_string(nr) +
                " pairs=" + std::to_string(fpair.size() * 2) + " nt=" + std::to_string(nt) +
                " ctas/SM=" + std::to_string(occ) + " smem=" + std::to_string(h->sp_smem_bytes);
   return true;
