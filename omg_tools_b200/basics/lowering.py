@@ -609,9 +609,11 @@ def build_kkt_structure(tb, hint=None):
         key[low[np.asarray(sub)]] = np.arange(len(low)) / float(len(low))
         arrows.append(finish(key))
     pos, first, size, flops = min(cands, key=lambda c: c[2])
-    if arrows:      # adopted only where it pays clearly (small problems keep their band ordering)
+    if arrows:      # adopted only where the factorisation is heavy and the border at least halves it
+        # (small problems keep their band ordering: nothing to gain, and their long cold starts
+        #  -- Dubins, ~250 iterations -- are sensitive to any change of the summation order)
         best = min(arrows, key=lambda c: (c[3], c[2]))
-        if 2 * best[3] <= flops:
+        if flops >= 1000000 and 2 * best[3] <= flops:
             pos, first, size, flops = best
 
     tb.kkt_n = N
