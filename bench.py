@@ -32,7 +32,8 @@ def parse():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--batch', type=int, default=BATCH)
+    ap.add_argument('--batch', type=int, default=0,
+                    help='instances (default: the BASELINE size of the workload: 1024; config 4: 512; config 5: 256)')
     ap.add_argument('--jitter', type=float, default=0.0)
     ap.add_argument('--cpu-sample', type=int, default=0)
     ap.add_argument('--workload', default='config2', choices=sorted(WORKLOADS),
@@ -43,7 +44,10 @@ def parse():
     ap.add_argument('--formations', type=int, default=1,
                     help='config3: independent formations run side by side in one batch (value counts '
                          'formation-iterations; 9 x 64 agents fill the 592 resident blocks of one B200)')
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.batch <= 0:
+        args.batch = {'config4': 512, 'config4_5obs': 512, 'config5': 256}.get(args.workload, BATCH)
+    return args
 
 
 class ClockSampler(object):
