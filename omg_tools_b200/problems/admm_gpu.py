@@ -267,3 +267,122 @@ def shift_T(problem):
         return problem.shared_shift_T()
     from ..basics.spline_extra import shiftoverknot_T
     return shiftoverknot_T(problem.basis)
+
+
+class FormationDDRunner(object):
+    """Runs ``FormationPoint2pointDualDecomposition`` (problems/dualdecomposition.py) on this
+    rank's GPU.  One iteration = reference ``DDProblem.dual_update`` (dualdecomposition.py:279-314):
+
+        init_step     knot shift of x_i, x_j, z_ij, l_ij, l_ji and of the NLP's variables
+        update_xz     ONE batched NLP solve (omg_solve_batch): own trajectory + neighbour copies
+        communicate   x_j <- neighbours' x_i                    [NCCL all-gather, C ABI]
+        update_l      l_ij += rho (x_j - z_ij), residual ||Tf (x_j - z_ij)||^2   (elementwise, device)
+        communicate   l_ji <- neighbours' l_ij                  [NCCL all-gather, C ABI]
+    """
+
+    def __init__(self, problem, rank=0, world=1, group=None, device=None):
+        import torch
+        from ..solver import b200
+        self.torch, self.b200 = torch, b200
+        self.pr = p = problem
+        self.solver = problem.solver
+        self.ex = AgentExchange(p.N, p.nghb, p.back, rank, world, group)
+        lo, hi = self.ex.lo, self.ex.hi
+        self.lo, self.hi = lo, hi
+        dev = device if isinstance(device, torch.device) else \
+            torch.device('cuda', self.solver.device if device is None else device)
+        self.dev = dev
+        td = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
+        self.X = td(p.X[lo:hi])
+        self.Xn = torch.empty_like(self.X)
+        self.x_i, self.x_j, self.z_ij = td(p.x_i[lo:hi]), td(p.x_j[lo:hi]), td(p.z_ij[lo:hi])
+        self.l_ij, self.l_ji = td(p.l_ij[lo:hi]), td(p.l_ji[lo:hi])
+        n_loc, m = hi - lo, p.tb.m
+        self.LAM = torch.empty((n_loc, m), dtype=torch.float64, device=dev)
+        self.F = torch.empty(n_loc, dtype=torch.float64, device=dev)
+        self.ST = torch.empty(n_loc, dtype=torch.int32, device=dev)
+        self.IT = torch.empty(n_loc, dtype=torch.int32, device=dev)
+        self.LB, self.UB = td(p.tb.lbg), td(p.tb.ubg)
+        self.P = torch.empty((n_loc, p.tb.n_par), dtype=torch.float64, device=dev)
+        self.blocks = [(off, shape[0], shape[1], T) for (_, _, off, shape, T) in p.father.shifted_entries()]
+        self.Ts = td(shift_T(p))
+        self.time_prev = 0.
+        self.history = []
+        self._par_t = self._tf_t = None
+        self.comm = None
+        if dev.type == 'cuda':
+            self.comm = b200.AdmmComm(rank, world, dev.index, group)
+            nn = p.n_nghb
+            self.nghb_d = torch.as_tensor(np.ascontiguousarray(p.nghb[lo:hi], dtype=np.int32), device=dev)
+            # rows of the all-gathered l_ij, seen as (N * nn, nsh): what neighbour j holds for agent i
+            rows = (p.nghb[lo:hi] * nn + p.back[lo:hi]).reshape(-1, 1)
+            self.lrow_d = torch.as_tensor(np.ascontiguousarray(rows, dtype=np.int32), device=dev)
+
+    def _pack_parameters(self, t):
+        p, torch = self.pr, self.torch
+        if self._par_t != t:
+            host = p.pack_parameters(t)[self.lo:self.hi]
+            self._P_host = torch.from_numpy(np.ascontiguousarray(host)).to(self.dev)
+            self._par_t = t
+        self.P.copy_(self._P_host)
+        off, a = p.par_off, p.upd_label
+        n_loc, w = self.hi - self.lo, p.nsh * p.n_nghb
+        self.P[:, off[(a, 'l_ij')]:off[(a, 'l_ij')] + w] = self.l_ij.reshape(n_loc, -1)
+        self.P[:, off[(a, 'l_ji')]:off[(a, 'l_ji')] + w] = self.l_ji.reshape(n_loc, -1)
+
+    def _shift_over_knot(self):
+        L, Ts, p = self.pr.L, self.Ts, self.pr
+        for name in ('x_i', 'x_j', 'z_ij', 'l_ij', 'l_ji'):
+            a = getattr(self, name)
+            setattr(self, name, (a.reshape(-1, L) @ Ts.T).reshape(a.shape).contiguous())
+        self.solver.shift_batch_device(self.X, self.blocks)
+        self.X[:, p.z_off:p.z_off + p.nsh * p.n_nghb] = self.z_ij.reshape(self.X.shape[0], -1)
+
+    def dual_update(self, t):
+        """One dual decomposition iteration at (relative) time t; returns the primal residual."""
+        p, torch = self.pr, self.torch
+        if (t > 0. and int(np.round(self.time_prev / p.knot_time, 6)) < int(np.round(t / p.knot_time, 6))):
+            self._shift_over_knot()
+        self.time_prev = t
+        self._pack_parameters(t)
+        self.solver.solve_batch_device(self.X, self.P, self.LB, self.UB, self.Xn, self.LAM,
+                                       self.F, self.ST, self.IT)
+        self.X, self.Xn = self.Xn, self.X
+        n_loc, nn, nsh = self.X.shape[0], p.n_nghb, p.nsh
+        st = self.ST.cpu().numpy()
+        bad = np.nonzero(st == 2)[0]
+        if len(bad):
+            # Restoration_Failed (the cold xz-update of an agent can end there): these instances go
+            # once more through the host call, which adds the feasibility phase and the re-solve
+            # (solver/b200.py: solve_batch) -- what IPOPT's restoration does inside the same nlpsol call
+            idx = torch.as_tensor(bad, device=self.dev)
+            r = self.solver.solve_batch(self.Xn[idx].cpu().numpy(), self.P[idx].cpu().numpy())
+            self.X[idx] = torch.tensor(r['x'], dtype=torch.float64, device=self.dev)
+            self.ST[idx] = torch.tensor(r['status'], dtype=torch.int32, device=self.dev)
+            self.IT[idx] = torch.tensor(r['iters'], dtype=torch.int32, device=self.dev)
+        self.x_i = self.X[:, p.x_off:p.x_off + nsh].contiguous()
+        self.z_ij = self.X[:, p.z_off:p.z_off + nsh * nn].reshape(n_loc, nn, nsh).contiguous()
+        if self.comm is not None:
+            self.comm.exchange_x(self.nghb_d, self.x_i, self.x_j)
+        else:
+            self.x_j = self.ex.gather_x(self.x_i)
+        if self._tf_t != t:
+            Tf, _ = p.first_knot_transforms(t)
+            self._Tf_d = torch.tensor(Tf, dtype=torch.float64, device=self.dev)
+            self._tf_t = t
+        d = self.x_j - self.z_ij
+        self.l_ij = (self.l_ij + p.options['rho'] * d).contiguous()
+        e = d.reshape(-1, p.L) @ self._Tf_d.T
+        tot = self.ex.allreduce_sum((e * e).sum().reshape(1))
+        if self.comm is not None:
+            flat_in = self.l_ij.reshape(n_loc * nn, nsh)
+            flat_out = self.l_ji.reshape(n_loc * nn, 1, nsh)
+            self.comm.exchange_x(self.lrow_d, flat_in, flat_out)
+        else:
+            _, self.l_ji = self.ex.gather_zl(self.l_ij, self.l_ij)
+        out = float(np.sqrt(float(tot[0])))
+        self.history.append(out)
+        return out
+
+    def status(self):
+        return self.ST.cpu().numpy(), self.IT.cpu().numpy()

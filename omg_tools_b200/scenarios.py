@@ -628,3 +628,33 @@ def config_rendezvous(n_agents=4, options=None, build_solver=True, rank=0, world
     problem = RendezVous(fleet, environment, options=opts, rank=rank, world=world, group=group)
     problem.init(build_solver=build_solver)
     return problem
+
+
+def config_formation_dd(n_agents=4, options=None, build_solver=True, rank=0, world=1, group=None):
+    """The formation of config 3 solved by dual decomposition (reference formation_dualdec.py;
+    the method the reference compares with ADMM in examples/compare_distributed_optimization_
+    quadrotors.py): every agent's NLP holds its own trajectory and copies of its two
+    neighbours', coupled by hard formation rows; dual ascent with step rho."""
+    from .vehicles.fleet import Fleet
+    from .basics.shape import RegularPolyhedron
+    from .problems.dualdecomposition import FormationPoint2pointDualDecomposition
+    vehicles = [Holonomic() for _ in range(n_agents)]
+    fleet = Fleet(vehicles, interconnection='circular')
+    if n_agents == 4:
+        configuration = RegularPolyhedron(0.2, n_agents, np.pi / 4.).vertices.T
+    else:
+        ang = 2 * np.pi * np.arange(n_agents) / n_agents
+        configuration = 0.2 * np.c_[np.cos(ang), np.sin(ang)]
+    fleet.set_configuration(configuration.tolist())
+    fleet.set_initial_conditions((np.array([-1.5, -1.5]) + configuration).tolist())
+    fleet.set_terminal_conditions((np.array([2., 2.]) + configuration).tolist())
+    environment = Environment(room={'shape': Square(5.)})
+    rectangle = Rectangle(width=3., height=0.2)
+    environment.add_obstacle(Obstacle({'position': [-2.1, -0.5]}, shape=rectangle))
+    environment.add_obstacle(Obstacle({'position': [1.7, -0.5]}, shape=rectangle))
+    opts = {'rho': 0.5, 'horizon_time': 10, 'verbose': 0}
+    opts.update(options or {})
+    problem = FormationPoint2pointDualDecomposition(fleet, environment, options=opts, rank=rank,
+                                                    world=world, group=group)
+    problem.init(build_solver=build_solver)
+    return problem

@@ -114,3 +114,52 @@ class ADMMOracle(object):
                 self.z_ji[i, k] = self.z_ij[j, p.back[i, k]]
                 self.l_ji[i, k] = self.l_ij[j, p.back[i, k]]
         return float(np.sqrt(pr)), float(np.sqrt(dr)), float(cr)
+
+
+class DDOracle(object):
+    """Sequential restatement of the reference's dual decomposition iteration
+    (omgtools/problems/dualdecomposition.py: DDProblem.dual_update 279-314 = init_step,
+    update_xz, communicate, update_l + get_residuals, communicate) on the problem object of
+    omg_tools_b200/problems/dualdecomposition.py.  Test infrastructure."""
+
+    def __init__(self, problem):
+        p = self.p = problem
+        self.X = p.X.copy()
+        self.x_i, self.x_j, self.z_ij = p.x_i.copy(), p.x_j.copy(), p.z_ij.copy()
+        self.l_ij, self.l_ji = p.l_ij.copy(), p.l_ji.copy()
+        self.time_prev = 0.
+        self.status = self.iters = None
+
+    def dual_update(self, t):
+        p = self.p
+        N, nsh, nn, L = p.N, p.nsh, p.n_nghb, p.L
+        rho = p.options['rho']
+        if t > 0. and int(np.round(self.time_prev / p.knot_time, 6)) < int(np.round(t / p.knot_time, 6)):
+            Ts = shiftoverknot_T(p.basis)                      # dualdecomposition.py:232-246
+            for name in ('x_i', 'x_j', 'z_ij', 'l_ij', 'l_ji'):
+                a = getattr(self, name)
+                setattr(self, name, a.reshape(-1, L).dot(Ts.T).reshape(a.shape))
+            for (_, _, off, shape, T) in p.father.shifted_entries():
+                for c in range(shape[1]):
+                    seg = slice(off + c * shape[0], off + (c + 1) * shape[0])
+                    self.X[:, seg] = self.X[:, seg].dot(np.asarray(T).T)
+            self.X[:, p.z_off:p.z_off + nsh * nn] = self.z_ij.reshape(N, -1)
+        self.time_prev = t
+        # ---- xz-update, one agent after the other (update_xz, 190-207) -------------------
+        p.l_ij, p.l_ji = self.l_ij, self.l_ji
+        P = p.pack_parameters(t).copy()
+        self.status, self.iters = np.zeros(N, dtype=int), np.zeros(N, dtype=int)
+        for i in range(N):
+            r = ipm_c.solve_batch_full(p.tb, self.X[i][None], P[i][None], threads=1)
+            self.X[i], self.status[i], self.iters[i] = r['x'][0], int(r['status'][0]), int(r['iters'][0])
+        self.x_i = self.X[:, p.x_off:p.x_off + nsh].copy()
+        self.z_ij = self.X[:, p.z_off:p.z_off + nsh * nn].reshape(N, nn, nsh).copy()
+        # ---- communicate x (225-230), multiplier update (209-223), residual (248-258) ------
+        self.x_j = self.x_i[p.nghb]
+        self.l_ij = self.l_ij + rho * (self.x_j - self.z_ij)
+        Tf, _ = p.first_knot_transforms(t)
+        e = (self.x_j - self.z_ij).reshape(-1, L).dot(np.asarray(Tf).T)
+        p_res = float(np.sqrt((e * e).sum()))
+        # ---- communicate l: what neighbour j holds for me ------------------------------------
+        self.l_ji = self.l_ij[p.nghb, p.back]
+        return p_res

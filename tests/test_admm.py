@@ -333,3 +333,31 @@ def test_interprete_constraints_derives_the_shared_sets(interconnection):
                                           [splines[0][0].coeffs[-1] - s[0]])
     assert q_i[0][vehicles[0].label]['splines_seg0'] == [L - 1] and q_i[3][vehicles[3].label]['meet'] == [0]
     assert q_ij[0][3][vehicles[3].label]['meet'] == [0] and q_ij[3][0][vehicles[0].label]['splines_seg0'] == [L - 1]
+
+
+def test_dual_decomposition_subproblem_and_ascent():
+    """Dual decomposition (reference dualdecomposition.py / formation_dualdec.py): every agent's
+    NLP returns its own trajectory and copies of its neighbours' that satisfy the formation rows
+    exactly; with the multipliers at zero the agents ignore each other (residual = the mismatch of
+    the uncoordinated plans); the dual ascent with a small step then drives the residual down --
+    a sub-gradient method on a piecewise-linear dual, so plateaus and jumps, not a monotone
+    sequence (the reference runs it with rho = 0.003, examples/compare_distributed_optimization_
+    quadrotors.py:95)."""
+    from oracle import ipm_c
+    from oracle.admm_ref import DDOracle
+    if not ipm_c.available():
+        pytest.skip('C oracle not built')
+    pr = sc.config_formation_dd(4, build_solver=False, options={'rho': 0.02})
+    assert (pr.tb.n, pr.tb.kkt_n_eq) == (118 + 52, 10 + 52)
+    orc = DDOracle(pr)
+    res = []
+    for it in range(16):
+        res.append(orc.dual_update(0.))
+        assert np.all(orc.status == 0)
+        # formation rows inside every agent's NLP: centre_i(x_i) + r_i = centre_j(z_ij) + r_j
+        ci = orc.x_i.reshape(pr.N, 1, pr.ns, pr.L) + pr.relp[:, None, :, None]
+        cj = orc.z_ij.reshape(pr.N, pr.n_nghb, pr.ns, pr.L) + pr.relp[pr.nghb][:, :, :, None]
+        assert np.abs(ci - cj).max() < 1e-6
+    assert res[0] > 1.0 and min(res[8:]) < 0.35 * res[0]
+    # multipliers a pair holds for each other are exchanged consistently
+    assert np.array_equal(orc.l_ji, orc.l_ij[pr.nghb, pr.back])

@@ -171,3 +171,24 @@ def test_dubins_example_as_written_converges_through_the_feasibility_phase():
     pr.initialize(0.)
     pr.solve(0., 0.5)
     assert pr.problem.stats()['return_status'] == 'Solve_Succeeded'
+
+
+def test_dual_decomposition_runner_matches_oracle():
+    """problems/dualdecomposition.py (reference dualdecomposition.py:58-314) on the GPU: one
+    batched xz-update of 8 agents, multiplier update and residual on the device, both exchanges
+    through omg_admm_exchange_x -- against the sequential DDOracle, iteration by iteration and
+    across a knot crossing."""
+    from omg_tools_b200.problems.admm_gpu import FormationDDRunner
+    from oracle.admm_ref import DDOracle
+    run = FormationDDRunner(sc.config_formation_dd(8, options={'rho': 0.02}))
+    orc = DDOracle(sc.config_formation_dd(8, build_solver=False, options={'rho': 0.02}))
+    for it, t in enumerate([0., 0., 0.5, 1.0, 1.0]):
+        rg, ro = run.dual_update(t), orc.dual_update(t)
+        st, its = run.status()
+        assert np.all(st == 0) and np.all(orc.status == 0)
+        same = its == orc.iters
+        assert same.sum() >= 7, (it, its, orc.iters)
+        for key in ('x_i', 'z_ij', 'l_ij', 'l_ji'):
+            d = np.abs(getattr(run, key).cpu().numpy() - getattr(orc, key)).reshape(8, -1).max(1)
+            assert d.max() < 5e-3 and (it > 0 or d[same].max() < 1e-6), (it, key, d)
+        assert abs(rg - ro) < 1e-2 * max(1., ro)

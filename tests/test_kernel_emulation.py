@@ -456,6 +456,25 @@ def test_side_by_side_formations_equal_the_single_formation(emu):
     assert not torch.equal(spread.x_i[:4], spread.x_i[4:])
 
 
+def test_dual_decomposition_runner_follows_the_oracle(emu):
+    """problems/dualdecomposition.py through FormationDDRunner (one batched xz-update, device-side
+    multiplier update, the two exchanges) against the sequential DDOracle (reference
+    dualdecomposition.py:279-314), iteration by iteration and across a knot crossing."""
+    import torch
+    from omg_tools_b200.problems.admm_gpu import FormationDDRunner
+    from oracle.admm_ref import DDOracle
+    run = FormationDDRunner(sc.config_formation_dd(4, options={'rho': 0.02}), device=torch.device('cpu'))
+    orc = DDOracle(sc.config_formation_dd(4, build_solver=False, options={'rho': 0.02}))
+    for it, t in enumerate([0., 0., 0.5, 1.0, 1.0]):          # knot_time = 1: the fourth call shifts
+        rg, ro = run.dual_update(t), orc.dual_update(t)
+        st, its = run.status()
+        assert np.all(st == 0) and np.all(orc.status == 0)
+        assert np.array_equal(its, orc.iters), (it, its, orc.iters)
+        for key in ('x_i', 'z_ij', 'l_ij', 'l_ji', 'x_j'):
+            assert np.abs(getattr(run, key).numpy() - getattr(orc, key)).max() < 1e-6, (it, key)
+        assert abs(rg - ro) < 1e-6 * max(1., ro)
+
+
 def _admm_rank(rank, world, port, out):
     import torch
     import torch.distributed as dist
