@@ -103,6 +103,7 @@ struct Smem {                      // offsets in doubles
   int sgn, eptr, efirst, pptr, prow, pcmin;
   int arr[N_ARR];                  // >= 0: shared offset; < 0: -(scratch offset + 1)
   int LDP, total;
+  int hst, hch;                    // staging buffer of the chunked H gather: 2 x hch doubles at hst
   int Kg, Vg, jxg, mug, Kcg, wxg;  // XL kernel: scratch offsets (K only if S.K < 0)
 };
 
@@ -832,7 +833,7 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
           // panel buffers (free until the factorisation) with coalesced loads, and every thread
           // adds the pairs of ITS H positions that fall into the chunk, from a coalesced record
           // stream (positions are owned by one virtual thread, so no atomics).
-          double* Ach = sm + S.Pt; double* Bch = sm + S.PtS;
+          double* Ach = sm + S.hst; double* Bch = Ach + S.hch;
           for (int c = 0; c < T.hc_nchunk; ++c) {
             const int s0 = T.hc_slot[c], nsl = T.hc_slot[c + 1] - s0;
             for (int k = tid; k < nsl; k += NT) { Ach[k] = jval[s0 + k]; Bch[k] = jsv[s0 + k]; }
@@ -842,11 +843,15 @@ __device__ __forceinline__ void ipm_body(const DevTab& T, const omg_options& O, 
               const int cnt = T.hc_cnt[c * T.hc_vt + vt];
               unsigned cur = 0xffffffffu;
               double acc = 0.0;
-#pragma unroll 4
-              for (int k = 0; k < cnt; ++k) {
-                const uint2 r = __ldg(rp + (size_t)k * T.hc_vt + vt);
-                if (r.x != cur) { if (cur != 0xffffffffu) K[cur] += acc; cur = r.x; acc = 0.0; }
-                acc += Bch[r.y & 0xffffu] * Ach[r.y >> 16];
+              for (int k0 = 0; k0 < cnt; k0 += 8) {        // eight record loads in flight
+                uint2 r[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) if (k0 + u < cnt) r[u] = __ldg(rp + (size_t)(k0 + u) * T.hc_vt + vt);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) if (k0 + u < cnt) {
+                  if (r[u].x != cur) { if (cur != 0xffffffffu) K[cur] += acc; cur = r[u].x; acc = 0.0; }
+                  acc += Bch[r[u].y & 0xffffu] * Ach[r[u].y >> 16];
+                }
               }
               if (cur != 0xffffffffu) K[cur] += acc;
             }
@@ -2039,6 +2044,15 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
   }
   S.Kcg = goff; goff += (T.env_size + 2 + 1) & ~1;
   const int sizes[N_ARR] = {tb->nnz_j, m, tb->nnz_j, m, m, m, m, m, m, m, m, m, m, m, m, m, m, m, m};
+  // staging buffer of the chunked J^T Sigma J gather (XL kernel with the Jacobian values in
+  // scratch): the panel buffers by default; three quarters of the free shared memory (up to
+  // 2 x 4096 doubles) when that is more -- fewer, longer chunks; the streamed m-vectors take the rest
+  S.hst = S.Pt; S.hch = NB * S.LDP;
+  if (h->xl && (size_t)(off + 2 * ((tb->nnz_j + 1) & ~1)) * 8 > budget) {
+    const long long free_d = ((long long)budget - (long long)off * 8) / 8;
+    int ch = (int)std::min<long long>(4096, (free_d * 3 / 4) / 2) & ~1;
+    if (ch > S.hch) { S.hst = off; S.hch = ch; off += 2 * ch; }
+  }
   for (int k = 0; k < N_ARR; ++k) {
     const int cnt = (sizes[k] + 1) & ~1;
     const bool optional_low = (k >= A_ZL);     // lower-bound / equality-only arrays: rarely touched
@@ -2049,7 +2063,7 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
   T.hc_nchunk = 0; T.hc_vt = 0;
   if (ok && h->xl && S.arr[A_JVAL] < 0 && S.arr[A_JSV] < 0 && tb->nnz_h > 0 && !getenv("OMG_B200_NO_HCHUNK")) {
     // chunked J^T Sigma J gather (see the kernel): chunks of whole rows that fit one panel buffer
-    const int CH = std::min(NB * S.LDP, 65535), VT = 512;
+    const int CH = std::min(S.hch, 65535), VT = 512;
     std::vector<int> cslot(1, 0), chunk_of_row(m, 0);
     bool fits = true;
     int cur0 = 0;
