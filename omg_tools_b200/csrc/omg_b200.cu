@@ -2048,7 +2048,8 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
   // scratch): the panel buffers by default; three quarters of the free shared memory (up to
   // 2 x 4096 doubles) when that is more -- fewer, longer chunks; the streamed m-vectors take the rest
   S.hst = S.Pt; S.hch = NB * S.LDP;
-  if (h->xl && (size_t)(off + 2 * ((tb->nnz_j + 1) & ~1)) * 8 > budget) {
+  if (h->xl && getenv("OMG_B200_HCHUNK") && atoi(getenv("OMG_B200_HCHUNK")) == 1 &&
+      (size_t)(off + 2 * ((tb->nnz_j + 1) & ~1)) * 8 > budget) {
     const long long free_d = ((long long)budget - (long long)off * 8) / 8;
     int ch = (int)std::min<long long>(4096, (free_d * 3 / 4) / 2) & ~1;
     if (ch > S.hch) { S.hst = off; S.hch = ch; off += 2 * ch; }
@@ -2061,7 +2062,12 @@ omg_problem* omg_problem_create(const omg_tables* tb, const omg_options* opt, in
   }
   S.total = off;
   T.hc_nchunk = 0; T.hc_vt = 0;
-  if (ok && h->xl && S.arr[A_JVAL] < 0 && S.arr[A_JSV] < 0 && tb->nnz_h > 0 && !getenv("OMG_B200_NO_HCHUNK")) {
+  // (experimental, off by default: OMG_B200_HCHUNK=1.  Measured on config 4: the gather phase -21 %
+  //  and the solve -4 % at n = 238 with 16 chunks, nothing at n = 406 where only the panel buffers
+  //  are free (69 chunks); it changes the summation order, which the 300-600-iteration cold starts
+  //  of HolonomicOrient amplify to 3e-4 -- not worth that without a larger gain)
+  const char* hce = getenv("OMG_B200_HCHUNK");
+  if (ok && hce && atoi(hce) == 1 && h->xl && S.arr[A_JVAL] < 0 && S.arr[A_JSV] < 0 && tb->nnz_h > 0) {
     // chunked J^T Sigma J gather (see the kernel): chunks of whole rows that fit one panel buffer
     const int CH = std::min(S.hch, 65535), VT = 512;
     std::vector<int> cslot(1, 0), chunk_of_row(m, 0);
