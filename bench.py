@@ -116,14 +116,15 @@ def flops_per_solve(tb, K):
 
 
 def fp64_flops_sparse(slv_info_str, K, tb):
-    """Multiply-adds the sparse kernel actually executes per solve (2 flops each): pairs of the
-    L D L^T gather x 1.5 factorisations per iteration + the J^T Sigma J gather + the term
-    streams; parsed from the library's structure report (OMG_B200_VERBOSE line)."""
+    """Flops the sparse kernel actually executes per solve: gather records of the L D L^T
+    factorisation (4 column terms of 3 flops each) x ~1.35 factorisations per iteration + the
+    J^T Sigma J gather + the term streams; parsed from the library's structure report
+    (OMG_B200_VERBOSE line, "pairs" = record slots)."""
     import re
     m = re.search(r'pairs=(\d+)', slv_info_str or '')
     pairs = float(m.group(1)) if m else 0.0
     nnz2 = float(np.sum(np.diff(tb.jrow_ptr).astype(float) ** 2)) / 2
-    per_iter = 1.5 * 2 * pairs * 1.5 + 2 * 2 * nnz2 + 2 * 3 * (tb.G.n_terms + 2 * tb.J.n_terms + tb.W.n_terms)
+    per_iter = 1.35 * pairs * 4 * 3 + 2 * 2 * nnz2 + 2 * 3 * (tb.G.n_terms + 2 * tb.J.n_terms + tb.W.n_terms)
     return K * per_iter
 
 
@@ -203,10 +204,14 @@ WORKLOADS = {
 
 # DRAM traffic of the solver kernel per solve, from the ncu --set full captures
 # (dram__bytes_read.sum + dram__bytes_write.sum of one launch):
-# profiles/r02_sparse_ncu_raw.txt (config 2, sparse kernel, 592-solve launch: the writes are L2
-# write-backs of the per-block scratch, 592 blocks x ~190 KB), profiles/r01_xl_config4_ncu_raw.txt
-NCU_DRAM_BYTES_PER_SOLVE = {'config2': (27.405568e6 + 483.273728e6) / 592.,
+# profiles/r02b_sparse_ncu_raw.txt (config 2, final sparse kernel, 592-solve launch: the writes are L2
+# write-backs of the per-block scratch, 592 blocks x ~190 KB), profiles/r02b_xl_config4_5obs_ncu_raw.txt
+# (config 4 at n = 406, 148-solve launch), profiles/r01_xl_config4_ncu_raw.txt (n = 238, round 1's kernel)
+NCU_DRAM_BYTES_PER_SOLVE = {'config2': (25.132032e6 + 485.795072e6) / 592.,
+                            'config4_5obs': (16.760825e9 + 12.967669e9) / 148.,
                             'config4': (3.464099e9 + 7.549988e9) / 148.}
+NCU_SOURCE = {'config2': 'profiles/r02b_sparse_ncu_raw.txt', 'config4_5obs': 'profiles/r02b_xl_config4_5obs_ncu_raw.txt',
+              'config4': 'profiles/r01_xl_config4_ncu_raw.txt (round 1 kernel)'}
 # bounded CPU sample: about 20 s of single-core work of the C oracle per measurement
 CPU_SAMPLE = {'config1': 2048, 'config2': 1024, 'config4': 96, 'config4_5obs': 32, 'config5': 512,
               'config_dubins_plain': 256, 'config_holonomic_orient': 32, 'config_quadrotor3d_simple': 256}
@@ -447,8 +452,8 @@ def main():
                          'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': (NCU_DRAM_BYTES_PER_SOLVE[args.workload] * B
                                      if args.workload in NCU_DRAM_BYTES_PER_SOLVE else None),
-                         'traffic_source': 'ncu dram__bytes_read+write per solve of one full launch '
-                                           '(profiles/r02_sparse_ncu_raw.txt) x batch',
+                         'traffic_source': ('ncu dram__bytes_read+write per solve of one full launch (%s) x batch'
+                                            % NCU_SOURCE[args.workload]) if args.workload in NCU_SOURCE else None,
                          'peak_source': how,
                          'model': 'staged-KKT bytes/solve = K*2*8*n(n+1)/2 + '
                                   '8(2n+n_par+3m) (SURVEY 8d); K=mean iterations',
@@ -459,10 +464,10 @@ def main():
                                   (kern_ms * 1e-3) / 1e12,
                                   'peak_tflops': fp64_peak,
                                   'peak_source': 'cuBLAS DGEMM 4096^3 measured in this run',
-                                  'note': 'flops the sparse kernel executes (L D L^T pairs x 1.5 '
+                                  'note': 'flops the sparse kernel executes (L D L^T gather records x 1.35 '
                                           'factorisations/iteration + gathers + term streams); the '
-                                          'kernel is bound by dependent-instruction latency, not by '
-                                          'this pipe (ncu: profiles/r02_*)'},
+                                          'kernel is bound by instruction issue and dependent latency, '
+                                          'not by this pipe (ncu: profiles/r02b_*)'},
                          'kernel_ms': kern_ms, 'smem_bytes': info['smem_bytes'],
                          'ctas_per_sm': info['ctas_per_sm']},
             'e2e': {'value': e2e_v, 'unit': 'solves/s',

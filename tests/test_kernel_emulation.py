@@ -69,6 +69,28 @@ def test_standard_kernel_matches_oracle(emu, monkeypatch, kernel, name, B, layou
     assert np.abs(res['x'] - ref['x'])[:, :26].max() < 1e-7
 
 
+def test_sparse_structure_of_config2_is_pinned(emu):
+    """The host-side symbolic analysis (csrc/omg_sp_host.cuh): constrained minimum degree, dense
+    root, supernodes of four columns with at most 8 explicit zeros each -- config 2 has 8
+    supernode levels (29 column levels), 3 960 stored entries, a root of 36 columns, every level
+    free of equality rows (early inertia rejection on all of them), 4 blocks per SM."""
+    info = sc.config2().problem.structure
+    for piece in ('N=200', 'nnz(L)=3960', 'levels=8 (early-reject 8)', 'root=36', 'ctas/SM=4', 'smem=54832'):
+        assert piece in info, (piece, info)
+
+
+@pytest.mark.parametrize('snw', ['1', '2', '3'])
+def test_narrower_supernodes_give_the_same_iterates(emu, monkeypatch, snw):
+    """OMG_B200_SNW limits the supernode width (1 = one column per level step, the kernel before
+    the supernodes): other level schedules, records and panel shapes, the same factorisation --
+    statuses and iteration counts as the oracle, solutions to rounding."""
+    monkeypatch.setenv('OMG_B200_SNW', snw)
+    res, ref = _compare(sc.config2(), 2, 0.1, 1, 26)
+    assert np.array_equal(res['status'], ref['status']) and (ref['status'] == 0).all()
+    assert np.array_equal(res['iters'], ref['iters'])
+    assert np.abs(res['x'] - ref['x'])[:, :26].max() < 1e-6
+
+
 @pytest.mark.parametrize('name, nflat, options', [
     ('config_freeT', 26, None),                 # T as a variable, cubic rows, soft restoration
     ('config_holonomic3d', 39, None),           # 3-D hyperplanes, 1 block/SM layout
@@ -508,6 +530,43 @@ def test_formation_admm_two_ranks_gloo_through_the_emulated_kernels(emu, tmp_pat
         lo = d['lo']
         assert lo == 4 * rank
         for key in ('x_i', 'z_i', 'l_i'):
+            assert torch.equal(d[key], getattr(single, key)[lo:lo + 4]), key
+        assert np.allclose(d['hist'], hist, rtol=1e-12, atol=0.)
+
+
+def _dd_rank(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    emu_support.activate()
+    from omg_tools_b200.problems.admm_gpu import FormationDDRunner
+    run = FormationDDRunner(sc.config_formation_dd(8, options={'rho': 0.02}, rank=rank, world=world),
+                            rank=rank, world=world, device=torch.device('cpu'))
+    hist = [run.dual_update(0.) for _ in range(3)]
+    torch.save({'x_i': run.x_i, 'z_ij': run.z_ij, 'l_ij': run.l_ij, 'l_ji': run.l_ji, 'hist': hist, 'lo': run.lo},
+               os.path.join(out, 'r%d.pt' % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dual_decomposition_two_ranks_gloo(emu, tmp_path):
+    """The multi-rank path of the dual decomposition on the CPU: 8 agents sharded over two
+    processes (gloo), neighbour exchange of x_j and of the multipliers l_ji and the residual
+    all-reduce over the process group -- the sharded run reproduces the single-process run of
+    all agents bit for bit."""
+    import torch
+    import torch.multiprocessing as mp
+    from omg_tools_b200.problems.admm_gpu import FormationDDRunner
+    port = 29700 + (os.getpid() % 90)
+    mp.spawn(_dd_rank, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    single = FormationDDRunner(sc.config_formation_dd(8, options={'rho': 0.02}), device=torch.device('cpu'))
+    hist = [single.dual_update(0.) for _ in range(3)]
+    for rank in range(2):
+        d = torch.load(os.path.join(str(tmp_path), 'r%d.pt' % rank))
+        lo = d['lo']
+        assert lo == 4 * rank
+        for key in ('x_i', 'z_ij', 'l_ij', 'l_ji'):
             assert torch.equal(d[key], getattr(single, key)[lo:lo + 4]), key
         assert np.allclose(d['hist'], hist, rtol=1e-12, atol=0.)
 
