@@ -79,6 +79,22 @@ def test_sparse_structure_of_config2_is_pinned(emu):
         assert piece in info, (piece, info)
 
 
+def test_early_inertia_rejection_does_not_change_the_iterates(emu, monkeypatch):
+    """The early rejection stops a factorisation at the first negative pivot among variables that
+    no equality row touches (omg_sp.cuh: SP_CHECK) instead of counting the pivots to the end; the
+    verdict -- wrong inertia, increase delta_w -- is the same, so every iterate is: bit-identical
+    solutions, iteration counts and multipliers with the switch on and off, on jittered cold
+    starts (which take the inertia correction in about a third of their iterations)."""
+    pr = sc.config2()
+    X0, P = sc.instance_data(pr, 6, jitter=0.2, seed=7)
+    on = pr.problem.solve_batch(X0, P)
+    monkeypatch.setenv('OMG_B200_EARLY_REJECT', '0')
+    off = sc.config2().problem.solve_batch(X0, P)
+    assert 'early-reject 0' in sc.config2().problem.structure
+    for key in ('x', 'lam_g', 'f', 'iters', 'status'):
+        assert np.array_equal(on[key], off[key]), key
+
+
 @pytest.mark.parametrize('snw', ['1', '2', '3'])
 def test_narrower_supernodes_give_the_same_iterates(emu, monkeypatch, snw):
     """OMG_B200_SNW limits the supernode width (1 = one column per level step, the kernel before
@@ -131,6 +147,28 @@ def test_xl_kernel_config4(emu):
     assert res['status'][0] == 0 and res['iters'][0] == ref['iters'][0]
     assert np.abs(res['x'] - ref['x']).max() < 1e-4
     assert abs(res['f'][0] - ref['f'][0]) < 1e-7
+
+
+def test_xl_chunked_gather_option_agrees_with_the_default(emu, monkeypatch):
+    """OMG_B200_HCHUNK=1: the J^T Sigma J gather of the XL kernel by row chunks staged in shared
+    memory (off by default) -- another summation order of the same assembly:
+    the nominal instance step for step (59 iterations, 7e-7), a jittered one within an iteration
+    and tol-size (1.4e-3: this NLP amplifies rounding, tests/test_gpu_parity.py -- the reason the
+    option is off by default)."""
+    X0, P = None, None
+    out = []
+    for flag in (None, '1'):
+        if flag:
+            monkeypatch.setenv('OMG_B200_HCHUNK', flag)
+        pr = sc.config4()
+        if X0 is None:
+            X0, P = sc.instance_data(pr, 2, jitter=0.05, seed=3)
+            X0[0], P[0] = sc.instance_data(pr, 1)[0][0], sc.instance_data(pr, 1)[1][0]
+        out.append(pr.problem.solve_batch(X0, P))
+    a, b = out
+    assert np.array_equal(a['status'], b['status']) and (a['status'] == 0).all()
+    assert a['iters'][0] == b['iters'][0] and abs(int(a['iters'][1]) - int(b['iters'][1])) <= 2
+    assert np.abs(a['x'] - b['x'])[0].max() < 1e-6 and np.abs(a['x'] - b['x'])[:, :36].max() < 5e-3
 
 
 def test_xl_kernel_cross_hessian_dubins_default(emu):
