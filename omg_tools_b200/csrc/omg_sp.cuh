@@ -5,17 +5,25 @@
 //
 //   * KKT factorisation K = L D L^T on a SPARSE symbolic structure computed once per problem
 //     (constrained minimum-degree ordering; all instances of a batch share it): config 2 needs
-//     3.7 k stored entries / 36 k multiply-adds per factorisation instead of 8.9 k / 320 k for
-//     the envelope of the time-ordered band -> the factor fits 3 blocks per SM, and the
-//     sequential chain shrinks from 200 pivots to ~30 elimination-tree levels + one dense root.
-//       - non-root columns: level-scheduled LEFT-looking gather, one thread per stored entry,
-//         contributions listed as packed pairs (a, b, k): v -= A[a] * A[b] * rd[k]
-//         (unscaled columns A = L D, rd = 1/d: one barrier per level, signs come with d);
-//       - the dense root (the final chain of the elimination tree, <= 48 columns): right-looking
-//         with the trailing triangle held in REGISTERS (static entry ownership), one barrier
-//         per pivot;
+//     4.0 k stored entries instead of 8.9 k for the envelope of the time-ordered band -> the
+//     factor fits 4 blocks per SM -- and the sequential chain shrinks from 200 pivots to 8
+//     supernode levels + one dense root of 36 columns.
+//       - SUPERNODES: paths of the elimination tree of up to SP_SNW columns with the structure
+//         of their last column (few explicit zeros), one level step each:
+//         GATHER, left-looking, one thread per stored entry: one record per (entry, source
+//         supernode) -- byte offsets of the two rows in the supernode's first column + its table
+//         entry -- contributes  v -= sum_t A_it * rd_t * A_jt  over the supernode's columns
+//         (unscaled columns A = L D, rd = 1/d: the pivot signs come with d);
+//         PANEL: one task per panel row; every task factorises the w x w diagonal block for
+//         itself (identical arithmetic) and finishes its row -- no block barrier inside;
+//       - the dense root (the final chain of the elimination tree, <= 40 columns): right-looking
+//         by panels of four columns with the trailing triangle held in REGISTERS (static entry
+//         ownership), two barriers per four pivots;
+//       - early rejection of an attempt at the first negative pivot among variables that no
+//         equality row touches (the inertia count could not come out right any more);
 //       - the right-hand side rides along as row N, so only the backward sweep remains
-//         (root: one warp, shuffle broadcast; the rest: level by level, 8 lanes per column).
+//         (root: one warp, shuffle broadcast; the rest: level by level, 8 lanes per column, the
+//         supernode's own triangle solved inside its warp with shuffles).
 //   * every table stream is laid out per THREAD ("thread streams"): a thread owns whole
 //     outputs (slots, rows, H positions, columns), balanced by record count; record k of its
 //     chunk t sits at ((t*8+k)*NT + tid) -> every warp load is one coalesced line, there are
