@@ -56,7 +56,9 @@ struct __align__(16) PT16 { double coef; unsigned short cidx, a, b, c; };   // c
 // ((t * SP_R + k) * NT + tid) -> every warp load is one coalesced line, no descriptor loads,
 // SP_R independent loads in flight per thread.  The last record of an output carries an end
 // flag and the output index.
+#ifndef SP_R
 #define SP_R 8
+#endif
 struct SpStream { int n_chunk; const void* rec; };
 
 struct SpTab {
