@@ -533,6 +533,7 @@ __device__ __forceinline__ void sp_back_solve(const DevTab& T, const SpTab& P, c
     const size_t o_ = ((size_t)bptr[P.n_lev - 1] * NT + tid) * 3;
     na = __ldg(P.bdesc + o_); nb = __ldg(P.bdesc + o_ + 1); nc = __ldg(P.bdesc + o_ + 2);
   }
+  if (tid == NT - 1) uu[T.N] = 0.0;      // what the absent entries of the level records point at
   if (warp == 0 && nr > 0) {
     // root, one warp: lane l holds rows l and l+32 (root-local); four columns per trip so that
     // the operand loads run ahead of the dependent chain  w -> u_c -> broadcast -> w

@@ -420,9 +420,12 @@ static bool sp_setup(omg_problem* h, const omg_tables* tb, const cudaDeviceProp&
         for (int t = 0; t < nt; ++t) {
           const size_t b = b0 + (size_t)(t >> 5);
           const int grp = (t >> 3) & 3, sub = t & 7;
-          const unsigned none = (unsigned)P.zslot * 8u;          // LK[zslot] = 0, u[0] finite
+          const unsigned none = (unsigned)P.zslot * 8u;          // LK[zslot] = 0
+          // absent entries: 0 * u[N] -- a slot of u that the sweep sets to zero and never writes again
+          // (u[0] would do numerically, but reading it races with the round that solves column 0)
+          const unsigned none_ent = none | (((unsigned)N * 8u) << 16);
           unsigned ent[8];
-          for (int q = 0; q < 8; ++q) ent[q] = none;
+          for (int q = 0; q < 8; ++q) ent[q] = none_ent;
           unsigned h0 = nq << 17, h1 = none, cb8 = none, snw = 0u;
           if (b < bins.size() && grp < (int)bins[b].size()) {
             const int j = bins[b][grp];

@@ -1,5 +1,5 @@
 """Small solves for compute-sanitizer (memcheck / racecheck):
-   python tools/sanitize.py [config1|config4|freeT|freeT_warm]"""
+   python tools/sanitize.py [config1|config2|config4|freeT|freeT_warm]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -14,6 +14,10 @@ elif which.startswith('freeT'):  # soft-restoration path (fires at the first ite
     pr = sc.config_freeT()
     X0, P = sc.instance_data(pr, 2, jitter=0.1, seed=2)
     pr.problem.set_options({'max_iter': 12})
+elif which == 'config2':        # sparse kernel: supernodes, panel steps, panelised root, early rejection
+    pr = sc.config2()
+    X0, P = sc.instance_data(pr, 2, jitter=0.2, seed=1)
+    pr.problem.set_options({'max_iter': 8})
 else:
     pr = sc.config1()
     X0, P = sc.instance_data(pr, 2, jitter=0.2, seed=1)
