@@ -161,6 +161,9 @@ typedef struct {
   int *hslot, *jslot, *dslot;   /* Ax slot of H position q / border slot s / diagonal j (permuted) */
   int *Lp, *Li, *parent;    /* pattern of L (strictly lower, by columns), elimination tree */
   int *sign;                /* +1 / -1 by permuted index */
+  int n_free;               /* leading permuted columns that are variables no equality row touches: a negative
+                             * pivot there already decides the inertia test (same early rejection as the
+                             * product's sparse kernel, csrc/omg_sp.cuh: SP_CHECK) */
 } SpSym;
 
 static int g_linear_solver = 0;
@@ -240,6 +243,17 @@ static SpSym* spsym_build(const omg_tables* T) {
   S->sign = (int*)malloc(sizeof(int) * N);
   for (int j = 0; j < N; ++j) S->sign[j] = 1;
   for (int k = 0; k < n_eq; ++k) S->sign[S->pos[n + k]] = -1;
+  {
+    char* touched = (char*)calloc(N, 1);                 /* by permuted index */
+    for (int k = 0; k < n_eq; ++k) {
+      const int i = T->kkt_eq_rows[k];
+      touched[S->pos[n + k]] = 1;
+      for (int s = T->jrow_ptr[i]; s < T->jrow_ptr[i + 1]; ++s) touched[S->pos[T->jcol[s]]] = 1;
+    }
+    S->n_free = 0;
+    while (S->n_free < N && !touched[S->n_free]) S->n_free++;
+    free(touched);
+  }
   /* elimination tree + column counts of L (up-looking symbolic pass) */
   S->parent = (int*)malloc(sizeof(int) * N); S->Lp = (int*)calloc(N + 1, sizeof(int));
   int* flag = (int*)malloc(sizeof(int) * N); int* lnz = (int*)calloc(N, sizeof(int));
@@ -292,6 +306,7 @@ static int sparse_ldl(const SpSym* S, const double* Ax, double* Lx, int* Li, dou
     else bad = !(piv > PIV_TOL * fmax(d0, 1e-300)) || !isfinite(piv);
     if (bad) { *eq_fail = (S->sign[k] < 0); return 0; }
     neg += isneg;
+    if (mode == 0 && isneg && k < S->n_free) { *eq_fail = 0; return 0; }   /* v^T H v < 0 with J_eq v = 0 */
     D[k] = dk;
   }
   if (mode == 0 && neg != n_neg) { *eq_fail = (neg < n_neg); return 0; }
